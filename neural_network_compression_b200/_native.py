@@ -1,0 +1,220 @@
+"""ctypes binding of the C ABI in include/nnc.h (libnnc_b200.so, built in-tree by build.py).
+
+There is no CPU fallback: if the library is missing or no CUDA device is visible, every compute call
+raises.  PyTorch / NumPy are used only to own buffers; the library sees raw pointers and sizes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnnc_b200.so")
+
+NNC_OK = 0
+NNC_ERR_BAD_ARG = 1
+NNC_ERR_CUDA = 2
+NNC_ERR_NOT_ENOUGH = 3
+NNC_ERR_NONFINITE = 4
+NNC_ERR_UNSUPPORTED = 5
+NNC_ERR_INTERNAL = 6
+NNC_ERR_COMM = 7
+NNC_KMAX = 1024
+
+# every symbol include/nnc.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "nnc_version", "nnc_last_error", "nnc_ctx_create", "nnc_ctx_destroy", "nnc_ctx_set_stream", "nnc_ctx_reserve",
+    "nnc_timer_start", "nnc_timer_stop", "nnc_last_profile", "nnc_stats_f32", "nnc_prune_f32", "nnc_mask_apply_f32",
+    "nnc_compact_nonzero_f32", "nnc_minmax_f32", "nnc_hist_edges_f32", "nnc_weight_cdf_f32", "nnc_gather_f32",
+    "nnc_kmeans1d_f32", "nnc_assign_f32", "nnc_unpack_gather_f32", "nnc_grad_segsum_f32", "nnc_ctx_set_comm",
+]
+
+
+class NncError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("libnnc_b200 error %d: %s" % (code, msg))
+        self.code = code
+        self.msg = msg
+
+
+class KMeansInfo(C.Structure):
+    _fields_ = [
+        ("n_iter", C.c_int),
+        ("strict", C.c_int),
+        ("n_relocations", C.c_int),
+        ("fixed_exp", C.c_int),
+        ("mean", C.c_float),
+        ("tol", C.c_float),
+        ("inertia", C.c_double),
+        ("n_nonzero", C.c_int64),
+    ]
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p)
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def lib():
+    """Loads libnnc_b200.so.  Fails loudly when it has not been built (python -m neural_network_compression_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "libnnc_b200.so is missing at %s: build it with `python -m neural_network_compression_b200.build` "
+                "(needs nvcc; there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, i64, i32, f32, f64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double
+        P = C.POINTER
+        L.nnc_version.restype = i32
+        L.nnc_last_error.restype = C.c_char_p
+        L.nnc_ctx_create.argtypes = [i32, P(vp)]
+        L.nnc_ctx_destroy.argtypes = [vp]
+        L.nnc_ctx_destroy.restype = None
+        L.nnc_ctx_set_stream.argtypes = [vp, vp]
+        L.nnc_ctx_reserve.argtypes = [vp, C.c_size_t]
+        L.nnc_timer_start.argtypes = [vp]
+        L.nnc_timer_stop.argtypes = [vp, P(f32)]
+        L.nnc_last_profile.argtypes = [vp, P(f32), i32, P(i32), P(C.c_char_p), P(i64)]
+        L.nnc_stats_f32.argtypes = [vp, vp, i64, P(f32), P(f32), P(f32)]
+        L.nnc_prune_f32.argtypes = [vp, vp, i64, f64, i32, i32, vp, P(f64), P(i64)]
+        L.nnc_mask_apply_f32.argtypes = [vp, vp, vp, i64]
+        L.nnc_compact_nonzero_f32.argtypes = [vp, vp, i64, vp, P(i64)]
+        L.nnc_minmax_f32.argtypes = [vp, vp, i64, i32, P(f32), P(f32), P(i64)]
+        L.nnc_hist_edges_f32.argtypes = [vp, vp, i64, vp, i32, i32, vp]
+        L.nnc_weight_cdf_f32.argtypes = [vp, vp, i64, i32, vp, vp]
+        L.nnc_gather_f32.argtypes = [vp, vp, i64, vp, i32, vp]
+        L.nnc_kmeans1d_f32.argtypes = [vp, vp, i64, vp, i32, i32, f64, vp, vp, vp, vp, vp, i32, vp, P(KMeansInfo)]
+        L.nnc_assign_f32.argtypes = [vp, vp, i64, vp, i32, f32, vp, vp, vp, vp, i32, vp, P(f64)]
+        L.nnc_unpack_gather_f32.argtypes = [vp, vp, i64, i32, vp, i32, vp]
+        L.nnc_grad_segsum_f32.argtypes = [vp, vp, vp, i64, i32, i32, vp]
+        L.nnc_ctx_set_comm.argtypes = [vp, i32, i32, ALLREDUCE_FN, vp]
+        for name in EXPORTS:
+            fn = getattr(L, name)
+            if name not in ("nnc_last_error", "nnc_ctx_destroy"):
+                fn.restype = i32
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != NNC_OK:
+        raise NncError(rc, lib().nnc_last_error().decode("utf-8", "replace"))
+
+
+class Context:
+    """One nnc_ctx: a device, a stream and a workspace.  Not thread-safe; one per host thread / rank."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        check(lib().nnc_ctx_create(int(device), C.byref(self._h)))
+        self.device = int(device)
+        self._comm_cb = None
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            lib().nnc_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int | None):
+        check(lib().nnc_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def reserve(self, nbytes: int):
+        check(lib().nnc_ctx_reserve(self._h, int(nbytes)))
+
+    def timer_start(self):
+        check(lib().nnc_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        check(lib().nnc_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def last_profile(self):
+        """({phase: ms}, kernel launches) of the last prune / k-means call."""
+        buf = (C.c_float * 64)()
+        n = C.c_int()
+        names = C.c_char_p()
+        launches = C.c_int64()
+        check(lib().nnc_last_profile(self._h, buf, 64, C.byref(n), C.byref(names), C.byref(launches)))
+        keys = names.value.decode().split(";") if names.value else []
+        out = {}
+        for i, kname in enumerate(keys[: n.value]):
+            out[kname] = out.get(kname, 0.0) + buf[i]
+        return out, launches.value
+
+    def set_comm(self, rank: int, world: int, allreduce):
+        """allreduce(dev_ptr: int, count: int, op: int, stream: int) -> None sums/mins/maxes int64 in place."""
+        if world > 1:
+            def _cb(_user, buf, count, op, stream):
+                try:
+                    allreduce(buf, count, op, stream)
+                    return 0
+                except Exception:  # pragma: no cover - surfaced as NNC_ERR_COMM
+                    import traceback
+
+                    traceback.print_exc()
+                    return 1
+
+            self._comm_cb = ALLREDUCE_FN(_cb)
+        else:
+            self._comm_cb = C.cast(None, ALLREDUCE_FN)
+        check(lib().nnc_ctx_set_comm(self._h, rank, world, self._comm_cb, None))
+
+
+_tls = threading.local()
+
+
+def default_context(device: int | None = None) -> Context:
+    """A per-thread, per-device context, created on first use."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) if "NNC_DEVICE" not in os.environ else int(os.environ["NNC_DEVICE"])
+    cache = getattr(_tls, "ctx", None)
+    if cache is None:
+        cache = _tls.ctx = {}
+    if device not in cache:
+        cache[device] = Context(device)
+    return cache[device]
+
+
+# ---- buffer plumbing -------------------------------------------------------------------------------------
+def is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+def ptr(x) -> int:
+    """Raw address of a NumPy array or torch tensor (host or device)."""
+    if x is None:
+        return 0
+    if is_torch(x):
+        return x.data_ptr()
+    return x.ctypes.data
+
+
+def device_of(x) -> int | None:
+    """CUDA device index of a torch CUDA tensor, else None."""
+    if is_torch(x) and x.is_cuda:
+        return x.device.index
+    return None
+
+
+def np_buffer(shape, dtype):
+    return np.empty(shape, dtype=dtype)

@@ -1,0 +1,369 @@
+"""B200-native drop-in for the compression helpers of the reference's
+neural_network_compression/common/utility.py: same names, arguments, return values and error behaviour,
+computed by the sm_100a kernels behind the C ABI of include/nnc.h.
+
+    prune_weigth(original_weigth, threshold=0.25, std_smooth=True)        utility.py:134-163
+    get_weight_distribution(weight_matrix)                                 utility.py:334-392
+    get_quantized_weight(layer_weight, bits=4, mode="linear", cdfs=None)   utility.py:172-240
+
+Inputs may be float32 NumPy arrays (what the reference's callers pass, trainer.py:185-191, :52-69) or float32
+torch tensors on the host or on a CUDA device; outputs come back as the same kind (device tensors stay on the
+device).  There is no CPU implementation in this package: without the CUDA library the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Any, Optional
+
+import numpy as np
+
+from .. import _native as N
+
+__all__ = [
+    "prune_weigth", "apply_mask", "get_weight_distribution", "get_quantized_weight", "KMeansResult",
+    "nonzero_weights", "weight_stats", "assign_codes", "dequantize", "cluster_gradient_sum", "index_bits",
+]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# buffer plumbing
+# ---------------------------------------------------------------------------------------------------------
+class _Buf:
+    """A flat, contiguous float32 view of a caller array plus what is needed to hand results back."""
+
+    def __init__(self, x, name: str, writable: bool = False):
+        self.orig = x
+        self.copied_back = None
+        if N.is_torch(x):
+            import torch
+
+            if x.dtype != torch.float32:
+                raise TypeError("%s must be float32 (got %s)" % (name, x.dtype))
+            self.kind = "torch"
+            self.shape = tuple(x.shape)
+            self.device = N.device_of(x)
+            self.arr = x if x.is_contiguous() else x.contiguous()
+            if writable and self.arr is not x:
+                self.copied_back = lambda: x.copy_(self.arr)
+            self.n = x.numel()
+        else:
+            if not isinstance(x, np.ndarray):
+                raise TypeError("%s must be a numpy.ndarray or a torch.Tensor (got %s)" % (name, type(x).__name__))
+            if x.dtype != np.float32:
+                raise TypeError("%s must be float32 (got %s); the reference's callers pass Keras float32 weights"
+                                % (name, x.dtype))
+            self.kind = "numpy"
+            self.shape = x.shape
+            self.device = None
+            if x.flags.c_contiguous and (x.flags.writeable or not writable):
+                self.arr = x
+            else:
+                if writable and not x.flags.writeable:
+                    raise ValueError("assignment destination is read-only")
+                self.arr = np.ascontiguousarray(x)
+                if writable:
+                    self.copied_back = lambda: np.copyto(x, self.arr)
+            self.n = x.size
+
+    @property
+    def ptr(self) -> int:
+        return N.ptr(self.arr)
+
+    def finish(self):
+        if self.copied_back is not None:
+            self.copied_back()
+
+    def empty(self, n, dtype):
+        """A new flat output buffer living where the input lives."""
+        if self.kind == "torch":
+            import torch
+
+            tdt = {np.uint8: torch.uint8, np.int32: torch.int32, np.float32: torch.float32, np.bool_: torch.bool}[dtype]
+            return torch.empty(int(n), dtype=tdt, device=self.arr.device)
+        return np.empty(int(n), dtype=dtype)
+
+
+def _ctx_for(buf: _Buf) -> N.Context:
+    ctx = N.default_context(buf.device)
+    if buf.kind == "torch" and buf.device is not None:
+        import torch
+
+        ctx.set_stream(torch.cuda.current_stream(buf.device).cuda_stream)
+    else:
+        ctx.set_stream(None)
+    return ctx
+
+
+# ---------------------------------------------------------------------------------------------------------
+# pruning
+# ---------------------------------------------------------------------------------------------------------
+def prune_weigth(original_weigth, threshold=0.25, std_smooth=True):
+    """Std-scaled magnitude pruning, restating utility.py:134-163.
+
+    thr = np.std(w) * threshold when std_smooth (population std, NumPy float32 pairwise arithmetic, bit exact);
+    mask = |w| < thr (strict); w[mask] = 0 IN PLACE; returns the boolean mask, same shape as the input.
+    """
+    buf = _Buf(original_weigth, "original_weigth", writable=True)
+    ctx = _ctx_for(buf)
+    # NEP 50: a Python float/int or np.float32 threshold keeps the product and the comparison in float32;
+    # a np.float64 scalar promotes both to float64.
+    thr_mode = 1 if isinstance(threshold, np.float64) else 0
+    mask = buf.empty(buf.n, np.uint8)
+    thr_out = C.c_double()
+    n_pruned = C.c_int64()
+    N.check(N.lib().nnc_prune_f32(ctx.handle, buf.ptr, buf.n, float(threshold), int(bool(std_smooth)), thr_mode,
+                                  N.ptr(mask), C.byref(thr_out), C.byref(n_pruned)))
+    buf.finish()
+    prune_weigth.last_threshold = thr_out.value
+    prune_weigth.last_pruned = n_pruned.value
+    if buf.kind == "torch":
+        import torch
+
+        return mask.view(torch.bool).reshape(buf.shape)
+    return mask.view(np.bool_).reshape(buf.shape)
+
+
+prune_weigth.last_threshold = None
+prune_weigth.last_pruned = None
+
+
+def apply_mask(weights, mask):
+    """weights[mask] = 0 in place: Trainer._reset_pruned_parameters (trainer.py:195-206); also the masked
+    gradient apply."""
+    buf = _Buf(weights, "weights", writable=True)
+    ctx = _ctx_for(buf)
+    if N.is_torch(mask):
+        import torch
+
+        m = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.contiguous()
+        if m.numel() != buf.n:
+            raise IndexError("boolean index did not match indexed array")
+    else:
+        m = np.ascontiguousarray(mask)
+        if m.size != buf.n:
+            raise IndexError("boolean index did not match indexed array")
+        m = m.view(np.uint8) if m.dtype == np.bool_ else m.astype(np.uint8)
+    N.check(N.lib().nnc_mask_apply_f32(ctx.handle, buf.ptr, N.ptr(m), buf.n))
+    buf.finish()
+    return weights
+
+
+def weight_stats(w):
+    """(mean, var, std) as np.mean / np.var / np.std give them for a float32 array."""
+    buf = _Buf(w, "w")
+    ctx = _ctx_for(buf)
+    m, v, s = C.c_float(), C.c_float(), C.c_float()
+    N.check(N.lib().nnc_stats_f32(ctx.handle, buf.ptr, buf.n, C.byref(m), C.byref(v), C.byref(s)))
+    return np.float32(m.value), np.float32(v.value), np.float32(s.value)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# weight distribution
+# ---------------------------------------------------------------------------------------------------------
+def nonzero_weights(params):
+    """flat[flat != 0], order preserving: the survivor selection of Trainer.quantize (trainer.py:55-59)."""
+    buf = _Buf(params, "params")
+    ctx = _ctx_for(buf)
+    out = buf.empty(buf.n, np.float32)
+    cnt = C.c_int64()
+    N.check(N.lib().nnc_compact_nonzero_f32(ctx.handle, buf.ptr, buf.n, N.ptr(out), C.byref(cnt)))
+    return out[: cnt.value]
+
+
+def get_weight_distribution(weight_matrix, skip_zeros: bool = False):
+    """Restates utility.py:334-392: 31 half-open bins over linspace(min, max, 32), normalised cumulative sum,
+    linear interpolation onto 300 points.  Returns (xnew float32[300], cdf float64[300]).
+
+    skip_zeros=True fuses the caller's survivor selection (trainer.py:55-60): the distribution is taken over
+    the non-zero entries without materialising them.
+    """
+    buf = _Buf(weight_matrix, "weight_matrix")
+    if buf.n == 0:
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")
+    ctx = _ctx_for(buf)
+    xnew = np.empty(300, dtype=np.float32)
+    cdf = np.empty(300, dtype=np.float64)
+    try:
+        N.check(N.lib().nnc_weight_cdf_f32(ctx.handle, buf.ptr, buf.n, int(bool(skip_zeros)), N.ptr(xnew), N.ptr(cdf)))
+    except N.NncError as e:
+        if e.code == N.NNC_ERR_NOT_ENOUGH:
+            raise ValueError("zero-size array to reduction operation minimum which has no identity") from None
+        raise
+    return xnew, cdf
+
+
+# ---------------------------------------------------------------------------------------------------------
+# quantization
+# ---------------------------------------------------------------------------------------------------------
+def index_bits(n_clusters: int) -> int:
+    """Bits per packed cluster index.  Density init yields 2^bits + 1 centroids, hence bits + 1 here."""
+    return max(1, int(n_clusters - 1).bit_length())
+
+
+@dataclass
+class KMeansResult:
+    """What the reference's callers read from the fitted sklearn model (utility.py:239), plus the compressed
+    representation the reference never materialises (packed n-bit indices, code histogram)."""
+
+    cluster_centers_: Any  # (k, 1) float32 ndarray
+    labels_: Any  # (n,) int32, array kind of the input
+    n_iter_: int
+    inertia_: float
+    packed_codes: Any = None  # uint8 little-endian bit stream, `code_bits` per weight
+    code_bits: int = 0
+    code_histogram: Optional[np.ndarray] = None  # (k,) int64
+    centred_centers: Optional[np.ndarray] = None  # (k,) float32: centres in sklearn's mean-centred space
+    mean: np.float32 = np.float32(0)
+    strict_convergence: bool = False
+    n_relocations: int = 0
+    n_nonzero: int = 0
+    tol_: float = 0.0
+    profile: dict = field(default_factory=dict)
+
+    @property
+    def n_clusters(self) -> int:
+        return int(self.cluster_centers_.shape[0])
+
+
+def _init_density(bits: int, cdfs):
+    # utility.py:210-223, verbatim semantics: for each of the 2^bits + 1 targets take the FIRST cdf value
+    # closest to it (Python min), then the x of the first cdf entry equal to that value (np.argmax).
+    tmp = np.linspace(0, 1, num=(2 ** bits) + 1)
+    xval, yval = cdfs[0], np.asarray(cdfs[1])
+    space = []
+    for t in tmp:
+        j = int(np.argmin(np.abs(yval - t)))  # first minimum, like min(key=abs(x - t))
+        idx_val = int(np.argmax(yval == yval[j]))
+        space.append(xval[idx_val])
+    return np.array(space, dtype=np.float32)
+
+
+def _kmeans_device(buf: _Buf, ctx: N.Context, space: np.ndarray, want_labels=True, want_ris=True, want_packed=True,
+                   max_iter: int = 300, tol: float = 1e-4):
+    k = int(space.size)
+    bits = index_bits(k)
+    centers = np.empty(k, dtype=np.float32)
+    centred = np.empty(k, dtype=np.float32)
+    hist = np.empty(k, dtype=np.int64)
+    labels = buf.empty(buf.n, np.int32) if want_labels else None
+    ris = buf.empty(buf.n, np.float32) if want_ris else None
+    packed = buf.empty((buf.n * bits + 7) // 8, np.uint8) if want_packed else None
+    info = N.KMeansInfo()
+    space = np.ascontiguousarray(space, dtype=np.float32)
+    N.check(N.lib().nnc_kmeans1d_f32(ctx.handle, buf.ptr, buf.n, N.ptr(space), k, int(max_iter), float(tol),
+                                     N.ptr(centers), N.ptr(centred), N.ptr(labels), N.ptr(ris), N.ptr(packed), bits,
+                                     N.ptr(hist), C.byref(info)))
+    prof, launches = ctx.last_profile()
+    prof["launches"] = launches
+    res = KMeansResult(
+        cluster_centers_=centers.reshape(-1, 1), labels_=labels, n_iter_=info.n_iter, inertia_=info.inertia,
+        packed_codes=packed, code_bits=bits, code_histogram=hist, centred_centers=centred, mean=np.float32(info.mean),
+        strict_convergence=bool(info.strict), n_relocations=info.n_relocations, n_nonzero=info.n_nonzero,
+        tol_=float(info.tol), profile=prof)
+    return ris, res
+
+
+def get_quantized_weight(layer_weight, bits=4, mode="linear", cdfs=None):
+    """1-D k-means weight sharing, restating utility.py:172-240.
+
+    Returns (ris, kmeans): `ris` has the input's shape with every weight replaced by its centroid
+    (cluster_centers_[labels_]); `kmeans` carries cluster_centers_ (k, 1), labels_ (n,), n_iter_, inertia_ like
+    the sklearn model the reference returns, plus packed n-bit codes and their histogram.  Fewer elements than
+    2^bits + 1: prints the reference's message and returns (layer_weight, None).  Unknown mode, or "density"
+    without cdfs: Exception(" error mode not found").
+    """
+    n_elem = int(np.prod(tuple(layer_weight.shape)))
+    if n_elem < (2 ** bits) + 1:
+        print("not enough bits:", n_elem, " vs ", 2 ** bits)
+        return layer_weight, None
+
+    if mode == "linear":
+        buf = _Buf(layer_weight, "layer_weight")
+        ctx = _ctx_for(buf)
+        mn, mx, cnt = C.c_float(), C.c_float(), C.c_int64()
+        N.check(N.lib().nnc_minmax_f32(ctx.handle, buf.ptr, buf.n, 0, C.byref(mn), C.byref(mx), C.byref(cnt)))
+        if cnt.value != buf.n:  # NaNs are skipped by the device min/max; sklearn rejects them
+            raise ValueError("Input X contains NaN.")
+        space = np.linspace(np.float32(mn.value), np.float32(mx.value), num=2 ** bits)
+    elif mode == "density" and cdfs is not None:
+        buf = _Buf(layer_weight, "layer_weight")
+        ctx = _ctx_for(buf)
+        space = _init_density(bits, cdfs)
+    elif mode == "forgy":
+        buf = _Buf(layer_weight, "layer_weight")
+        ctx = _ctx_for(buf)
+        # np.random.choice(flat, size=k) draws randint(0, n, k) from the global legacy RNG and indexes with it
+        idx = np.random.randint(0, buf.n, size=2 ** bits).astype(np.int64)
+        space = np.empty(idx.size, dtype=np.float32)
+        N.check(N.lib().nnc_gather_f32(ctx.handle, buf.ptr, buf.n, N.ptr(idx), idx.size, N.ptr(space)))
+    elif mode == "kmeans++":
+        # Outside the hot path: the reference's unseeded sklearn default.  The
+        # seeding runs on the host through scikit-learn; the Lloyd iterations run on the device like every
+        # other mode.
+        from sklearn.cluster import kmeans_plusplus
+
+        buf = _Buf(layer_weight, "layer_weight")
+        ctx = _ctx_for(buf)
+        host = buf.arr.detach().cpu().numpy() if buf.kind == "torch" else buf.arr
+        centers, _ = kmeans_plusplus(host.reshape(-1, 1), n_clusters=2 ** bits)
+        space = centers.astype(np.float32).ravel()
+    else:
+        raise Exception(" error mode not found")
+
+    try:
+        ris, res = _kmeans_device(buf, ctx, np.asarray(space, dtype=np.float32))
+    except N.NncError as e:
+        if e.code == N.NNC_ERR_NONFINITE:
+            raise ValueError("Input X contains NaN or infinity.") from None
+        if e.code == N.NNC_ERR_NOT_ENOUGH:
+            raise ValueError(e.msg) from None
+        raise
+    return ris.reshape(buf.shape), res
+
+
+def assign_codes(weights, kmeans: KMeansResult, want_labels=True, want_packed=True):
+    """E-step only: labels / packed codes of `weights` against a fitted codebook (the sklearn label rule)."""
+    buf = _Buf(weights, "weights")
+    ctx = _ctx_for(buf)
+    k = kmeans.n_clusters
+    bits = kmeans.code_bits or index_bits(k)
+    labels = buf.empty(buf.n, np.int32) if want_labels else None
+    packed = buf.empty((buf.n * bits + 7) // 8, np.uint8) if want_packed else None
+    hist = np.empty(k, dtype=np.int64)
+    centred = np.ascontiguousarray(kmeans.centred_centers, dtype=np.float32)
+    N.check(N.lib().nnc_assign_f32(ctx.handle, buf.ptr, buf.n, N.ptr(centred), k, float(kmeans.mean), None,
+                                   N.ptr(labels), None, N.ptr(packed), bits, N.ptr(hist), None))
+    return labels, packed, hist
+
+
+def dequantize(packed_codes, n: int, bits: int, cluster_centers, like=None):
+    """cluster_centers_[codes] from packed n-bit codes (the decode side of utility.py:239)."""
+    values = np.ascontiguousarray(np.asarray(cluster_centers, dtype=np.float32).ravel())
+    if N.is_torch(packed_codes):
+        import torch
+
+        out = torch.empty(int(n), dtype=torch.float32, device=packed_codes.device)
+        dev = N.device_of(packed_codes)
+    else:
+        packed_codes = np.ascontiguousarray(packed_codes, dtype=np.uint8)
+        out = np.empty(int(n), dtype=np.float32)
+        dev = None
+    ctx = N.default_context(dev)
+    N.check(N.lib().nnc_unpack_gather_f32(ctx.handle, N.ptr(packed_codes), int(n), int(bits), N.ptr(values), values.size,
+                                          N.ptr(out)))
+    return out
+
+
+def cluster_gradient_sum(grad, codes, n_clusters: int, bits: int = 0):
+    """Trained-quantization centroid gradient (papers/lat/report.tex:152): out[k] = sum_i grad_i [code_i == k].
+    `codes`: int32 labels (bits=0) or a packed n-bit stream.  Returns float64[n_clusters]."""
+    buf = _Buf(grad, "grad")
+    ctx = _ctx_for(buf)
+    if not N.is_torch(codes):
+        codes = np.ascontiguousarray(codes, dtype=np.int32 if bits == 0 else np.uint8)
+    elif not codes.is_contiguous():
+        codes = codes.contiguous()
+    out = np.empty(int(n_clusters), dtype=np.float64)
+    N.check(N.lib().nnc_grad_segsum_f32(ctx.handle, buf.ptr, N.ptr(codes), buf.n, int(bits), int(n_clusters), N.ptr(out)))
+    return out

@@ -1,0 +1,190 @@
+// internal.h -- host-side plumbing shared by the .cu translation units (context, workspace arena,
+// host/device pointer staging, error handling, launch accounting).  Not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/nnc.h"
+
+namespace nnc {
+
+void set_error(const char *fmt, ...);
+
+struct Error {
+    int code;
+};
+
+#define NNC_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            nnc::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));   \
+            throw nnc::Error{NNC_ERR_CUDA};                                                         \
+        }                                                                                           \
+    } while (0)
+
+#define NNC_FAIL(code, ...)          \
+    do {                             \
+        nnc::set_error(__VA_ARGS__); \
+        throw nnc::Error{code};      \
+    } while (0)
+
+// Scalars that flow between kernels of one call without a host round trip.  One instance lives in
+// device memory (ctx->d_scal); the host reads it back once at the end of a call.
+struct DevScalars {
+    // numpy-exact statistics
+    float tree_sum;      // result of the last pairwise tree reduction
+    float mean;          // fl32(sum / n)
+    float var;           // fl32(sum((x-mean)^2) / n)
+    float std_;          // sqrtf(var)
+    // fp64 side statistics (order dependent, estimates only)
+    double sum_d, sumsq_d;
+    unsigned long long n_nonfinite;
+    // pruning
+    double thr;          // exact threshold used by the final comparison
+    double band_lo, band_hi;
+    unsigned long long n_pruned;
+    unsigned long long band_count;    // entries appended to the side list
+    unsigned long long band_dropped;  // entries that did not fit
+    int spec_failed;     // exact threshold fell outside the speculation band
+    // quantization prologue
+    uint32_t min_ord, max_ord;        // ordered-uint min / max over all elements
+    uint32_t min_nz_ord, max_nz_ord;  // ... over non-zero elements
+    unsigned long long n_nz;          // non-zero count (also the compaction cursor)
+    int pad_;
+};
+
+struct PhaseTimer {
+    std::vector<cudaEvent_t> ev;
+    std::vector<std::string> names;
+    int used = 0;
+};
+
+}  // namespace nnc
+
+struct nnc_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    // bump arena for per-call device scratch
+    char *ws = nullptr;
+    size_t ws_bytes = 0;
+    size_t ws_off = 0;
+    size_t call_bytes = 0;      // bytes requested by the current call
+    size_t high_water = 0;      // largest call so far: the main block is regrown to this at the next reset
+    std::vector<void *> overflow;  // extra blocks taken when the main block was too small
+    bool user_stream = false;
+    nnc::DevScalars *d_scal = nullptr;
+    nnc::DevScalars *h_scal = nullptr;  // pinned mirror
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    nnc::PhaseTimer prof;
+    std::vector<float> prof_ms;
+    std::string prof_names;
+    int64_t launches = 0;       // kernels launched by the current / last call
+    int64_t last_launches = 0;
+    // multi-GPU
+    int rank = 0, world = 1;
+    nnc_allreduce_i64_fn allreduce = nullptr;
+    void *allreduce_user = nullptr;
+};
+
+namespace nnc {
+
+// ---- arena -----------------------------------------------------------------------------------
+void arena_reset(nnc_ctx *ctx);
+void arena_reserve(nnc_ctx *ctx, size_t bytes);  // make sure `bytes` fit (may reallocate; only when empty)
+void *arena_alloc(nnc_ctx *ctx, size_t bytes);
+template <class T>
+T *arena_alloc_t(nnc_ctx *ctx, size_t count) {
+    return reinterpret_cast<T *>(arena_alloc(ctx, count * sizeof(T)));
+}
+
+bool is_device_ptr(const void *p);
+
+// Stages a caller buffer: device pointers pass through, host pointers get an arena copy.
+struct Staged {
+    void *dev = nullptr;
+    void *host = nullptr;  // non-null when a copy back / in is needed
+    size_t bytes = 0;
+};
+Staged stage_in(nnc_ctx *ctx, const void *p, size_t bytes);    // read-only input
+Staged stage_out(nnc_ctx *ctx, void *p, size_t bytes);         // output only
+Staged stage_inout(nnc_ctx *ctx, void *p, size_t bytes);       // in place
+void stage_finish(nnc_ctx *ctx, const Staged &s);              // async D2H if host-backed
+
+// ---- phases / launches -------------------------------------------------------------------------
+void prof_begin(nnc_ctx *ctx);
+void prof_mark(nnc_ctx *ctx, const char *name);  // ends the phase `name` that started at the previous mark
+void prof_end(nnc_ctx *ctx);
+
+#define NNC_LAUNCH(ctx, kernel, grid, block, smem, ...)                 \
+    do {                                                                \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+        (ctx)->launches++;                                              \
+        NNC_CUDA(cudaGetLastError());                                   \
+    } while (0)
+
+void read_scalars(nnc_ctx *ctx);  // D2H of DevScalars + stream sync
+
+// ---- kernels' host entry points (one per .cu file) ----------------------------------------------
+// reduce_np.cu
+struct NpPlan {
+    int depth;
+    uint32_t num_tiles;
+};
+NpPlan np_plan(int64_t n);
+size_t np_partials_bytes(const NpPlan &p);
+void np_stats(nnc_ctx *ctx, const float *d_w, int64_t n);  // fills mean/var/std_ in d_scal (2 passes)
+void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth, int thr_mode, uint8_t *d_mask);
+void mask_apply_device(nnc_ctx *ctx, float *d_w, const uint8_t *d_mask, int64_t n);
+// np mean + min/max + non-zero count (+ optional unordered compaction into d_out)
+void quant_prologue(nnc_ctx *ctx, const float *d_w, int64_t n, float *d_out_nz);
+
+// select.cu : min/max, edge histogram, ordered compaction, gather
+void minmax_device(nnc_ctx *ctx, const float *d_w, int64_t n, int skip_zeros, float *mn, float *mx, int64_t *cnt);
+void hist_edges_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *h_edges, int n_edges, int skip_zeros,
+                       int64_t *h_counts);
+int64_t compact_ordered_device(nnc_ctx *ctx, const float *d_w, int64_t n, float *d_out);
+void gather_device(nnc_ctx *ctx, const float *d_w, int64_t n, const int64_t *h_idx, int m, float *h_out);
+
+// sort.cu : onesweep LSD radix sort of float32 keys; returns pointer to the sorted buffer (d_a or d_b)
+float *radix_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n);
+
+// lloyd.cu
+struct LloydResult {
+    int n_iter, strict, n_reloc, fixed_exp;
+    float tol;
+};
+struct LloydDevice;  // opaque device-side state
+struct LloydHandle {
+    LloydDevice *d_state = nullptr;
+    const float *d_sorted = nullptr;
+    int64_t n_nz = 0, n0 = 0, n = 0;
+    int k = 0;
+    float mean = 0.f;
+    void *d_ptile = nullptr, *d_samp = nullptr;
+    int64_t n_tiles = 0;
+};
+LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max_iter, double tol_rel,
+                      float *h_centred_final, float *h_centred_emit);
+
+// emit.cu : final E-step over the tensor in original order
+// h_centred: centroids the labels are taken against; h_centred_final (optional): final centroids (codebook
+// values and inertia); they differ only after a strict stop in which relocation fired.
+// xabs: max |w - mean| over the tensor when the caller already knows it, negative to have it measured here.
+void emit_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *h_centred, const float *h_centred_final, int k,
+                 float mean, float xabs, const float *h_values, int32_t *d_labels, float *d_ris, uint8_t *d_packed, int bits,
+                 int64_t *h_hist, double *h_inertia);
+void unpack_gather_device(nnc_ctx *ctx, const uint8_t *d_packed, int64_t n, int bits, const float *h_values, int k,
+                          float *d_out);
+// segsum.cu
+void grad_segsum_device(nnc_ctx *ctx, const float *d_grad, const void *d_codes, int64_t n, int bits, int k,
+                        double *h_out);
+
+}  // namespace nnc

@@ -1,0 +1,782 @@
+// lloyd.cu -- Lloyd iterations of 1-D k-means on the SORTED surviving weights.
+//
+// Restates sklearn's _kmeans_single_lloyd / lloyd_iter_chunked_dense / _relocate_empty_clusters_dense /
+// _average_centers / _center_shift (sklearn/cluster/_kmeans.py:630-758, _k_means_lloyd.pyx:23-218,
+// _k_means_common.pyx:167-311), which the reference reaches through KMeans(...).fit in
+// neural_network_compression/common/utility.py:237-238.
+//
+// Data layout (all in HBM):
+//   ks[n_nz]        sorted non-zero weights (float32, raw values)
+//   ptile[T+1]      int64 exclusive prefix sums of q(x') at tile granularity (tile = 1024 sorted elements),
+//                   q(x') = rint(fl(x - mean) * 2^(30-E)) the fixed-point image of the centred sample
+//   samp[T]         first key of every tile (32-ary search index, L2 resident)
+//   the n0 pruned zeros are not stored: they are one value with multiplicity n0.
+//
+// One iteration = four small kernels on the context stream, no host round trip:
+//   table   (1 CTA)   sort the k centroids, build the region table (table.cuh)
+//   search  (grid)    one warp per region boundary: position in ks[] and prefix sum of q up to it
+//   zone    (grid)    evaluate the float32 label rule for the few samples inside the zones
+//   update  (1 CTA)   per-cluster counts and sums (SAFE regions via prefix differences + zone partials +
+//                     the zero run), empty-cluster relocation, averages, centre shift, convergence test
+// Per-cluster sums are exact integers, so the result does not depend on reduction order or sharding.
+#include <algorithm>
+
+#include "common.cuh"
+#include "internal.h"
+#include "table.cuh"
+
+namespace nnc {
+
+constexpr int LL_TS = 1024;  // sorted-array tile
+
+__host__ __device__ __forceinline__ long long llmin2(long long a, long long b) { return a < b ? a : b; }
+__host__ __device__ __forceinline__ long long llmax2(long long a, long long b) { return a > b ? a : b; }
+
+struct LloydHeader {
+    int k, max_iter, fixed_exp, pad0;
+    long long n, n_nz, n0, n_tiles;
+    float mean, tol, xabs_max, pad1;
+    double scale, tol_rel;
+};
+struct LloydDevice : LloydHeader {
+    // exact moments of q over all n samples (for the tolerance)
+    long long s1;
+    unsigned long long s2_lo, s2_hi;
+    long long total_q;  // sum of q over the sorted survivors
+    // centroids (centred space) by cluster id
+    float c[TB_KMAX];
+    float c_emit[TB_KMAX];
+    RegionTable tab;
+    long long rpos[2 * TB_KMAX + 2];
+    long long rsum[2 * TB_KMAX + 2];
+    // zone partials per distinct index
+    long long zW[TB_KMAX], zS[TB_KMAX], zmin[TB_KMAX], zmax[TB_KMAX];
+    // per-id partials (pre-relocation) of the previous iteration: label-equality proxy
+    long long Wprev[TB_KMAX], Sprev[TB_KMAX];
+    // control
+    int iter, done, strict, n_reloc, n_iter, pad2;
+};
+
+// ---------------------------------------------------------------------------------------------
+// prep: per-tile sums of q, samples, moments
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ll_tilesum_kernel(const float *__restrict__ ks, long long n_nz, float mean,
+                                                         double scale, long long *tsum, float *samp, LloydDevice *st) {
+    const long long n_tiles = (n_nz + LL_TS - 1) / LL_TS;
+    const int wpb = blockDim.x >> 5;
+    long long s1 = 0;
+    unsigned long long s2lo = 0, s2hi = 0;
+    for (long long t = blockIdx.x * (long long)wpb + warp_id(); t < n_tiles; t += (long long)gridDim.x * wpb) {
+        long long base = t * LL_TS;
+        long long acc = 0;
+#pragma unroll 4
+        for (int j = 0; j < LL_TS / 32; ++j) {
+            long long i = base + j * 32 + lane_id();
+            if (i < n_nz) {
+                float x = ks[i];
+                long long q = fixed_q(fsub(x, mean), scale);
+                acc += q;
+                unsigned long long qq = (unsigned long long)(q * q);
+                s2lo += qq & 0x7fffffffull;
+                s2hi += qq >> 31;
+                if (j == 0 && lane_id() == 0) samp[t] = x;
+            }
+        }
+        acc = warp_sum_ll(acc);
+        if (lane_id() == 0) tsum[t] = acc;
+        s1 += acc;  // every lane holds the warp total; only lane 0 contributes below
+    }
+    s2lo = warp_sum_ull(s2lo);
+    s2hi = warp_sum_ull(s2hi);
+    if (lane_id() == 0) {
+        atomicAdd((unsigned long long *)&st->s1, (unsigned long long)s1);
+        atomicAdd(&st->s2_lo, s2lo);
+        atomicAdd(&st->s2_hi, s2hi);
+    }
+}
+
+// exclusive scan of tile sums -> ptile[0..T]; single CTA
+__global__ void __launch_bounds__(1024) ll_scan_kernel(const long long *tsum, long long n_tiles, long long *ptile,
+                                                       LloydDevice *st) {
+    __shared__ long long s_warp[32];
+    const long long per = (n_tiles + blockDim.x - 1) / blockDim.x;
+    const long long lo = llmin2(n_tiles, threadIdx.x * per), hi = llmin2(n_tiles, lo + per);
+    long long sum = 0;
+    for (long long i = lo; i < hi; ++i) sum += tsum[i];
+    long long incl = block_scan_incl<long long>(sum, [](long long a, long long b) { return a + b; }, s_warp);
+    long long run = incl - sum;
+    for (long long i = lo; i < hi; ++i) {
+        ptile[i] = run;
+        run += tsum[i];
+    }
+    if (threadIdx.x == blockDim.x - 1) {
+        ptile[n_tiles] = incl;
+        st->total_q = incl;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// init: centre the initial centroids, tolerance from exact integer moments
+// ---------------------------------------------------------------------------------------------
+__global__ void ll_init_kernel(LloydDevice *st, const float *init) {
+    const int tid = threadIdx.x;
+    if (tid < st->k) {
+        st->c[tid] = fsub(init[tid], st->mean);  // init -= X_mean  (_kmeans.py:1493)
+        st->Wprev[tid] = -1;
+        st->Sprev[tid] = 0;
+    }
+    if (tid == 0) {
+        // zero run joins the moments
+        long long q0 = fixed_q(fsub(0.f, st->mean), st->scale);
+        __int128 s1 = (__int128)st->s1 + (__int128)st->n0 * q0;
+        unsigned __int128 s2 = ((unsigned __int128)st->s2_hi << 31) + st->s2_lo +
+                               (unsigned __int128)st->n0 * (unsigned __int128)((unsigned long long)(q0 * q0));
+        unsigned __int128 num = (unsigned __int128)st->n * s2 - (unsigned __int128)(s1 * s1);
+        double numd = __dadd_rn(__dmul_rn((double)(unsigned long long)(num >> 64), 18446744073709551616.0),
+                                (double)(unsigned long long)num);
+        double nd = (double)st->n;
+        double var_d = __ddiv_rn(__ddiv_rn(numd, __dmul_rn(nd, nd)), __dmul_rn(st->scale, st->scale));
+        float tol = fmul((float)var_d, (float)st->tol_rel);
+        if (st->tol_rel == 0.0) tol = 0.f;
+        st->tol = tol;
+        st->iter = 0;
+        st->done = 0;
+        st->strict = 0;
+        st->n_reloc = 0;
+        st->n_iter = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-iteration kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TB_THREADS) ll_table_kernel(LloydDevice *st) {
+    __shared__ TableScratch S;
+    if (st->done) return;
+    build_region_table(st->c, st->k, st->xabs_max, &st->tab, S);
+    const int tid = threadIdx.x;
+    if (tid < st->k) {
+        st->zW[tid] = 0;
+        st->zS[tid] = 0;
+        st->zmin[tid] = 0x7fffffffffffffffll;
+        st->zmax[tid] = -1;
+    }
+    if (tid == 0) {
+        const int G = st->tab.G;
+        st->rpos[0] = 0;
+        st->rsum[0] = 0;
+        st->rpos[2 * G + 1] = st->n_nz;
+        st->rsum[2 * G + 1] = st->total_q;
+    }
+}
+
+// number of sorted survivors with fl(x - mean) < t, and the sum of q over them; one warp per boundary
+__device__ __forceinline__ void warp_boundary_search(const float *__restrict__ ks, const float *__restrict__ samp,
+                                                     const long long *__restrict__ ptile, long long n_nz,
+                                                     long long n_tiles, float mean, double scale, float t,
+                                                     long long &pos_out, long long &sum_out) {
+    const int lane = lane_id();
+    long long lo = 0, hi = n_tiles;  // first tile whose first key fails the predicate lies in [lo, hi]
+    while (lo < hi) {
+        long long span = hi - lo;
+        long long step = (span + 31) >> 5;
+        long long cs = lo + (long long)lane * step;  // chunk start
+        bool inr = cs < hi;
+        long long last = llmin2(cs + step, hi) - 1;
+        bool p = inr ? (fsub(samp[last], mean) < t) : false;
+        unsigned b = __ballot_sync(0xffffffffu, p);
+        int c = __popc(b);
+        long long nlo = llmin2(lo + (long long)c * step, hi);
+        long long nhi = llmin2(nlo + step, hi) - 1;
+        if (nlo >= hi) {
+            lo = hi;
+            break;
+        }
+        lo = nlo;
+        hi = nhi;
+    }
+    if (lo == 0) {
+        pos_out = 0;
+        sum_out = 0;
+        return;
+    }
+    const long long tile = lo - 1;
+    const long long base = tile * LL_TS;
+    long long cnt = 0, acc = 0;
+#pragma unroll 4
+    for (int j = 0; j < LL_TS / 32; ++j) {
+        long long i = base + j * 32 + lane;
+        bool p = false;
+        if (i < n_nz) {
+            float xc = fsub(ks[i], mean);
+            p = xc < t;
+            if (p) acc += fixed_q(xc, scale);
+        }
+        cnt += __popc(__ballot_sync(0xffffffffu, p));
+    }
+    acc = warp_sum_ll(acc);
+    pos_out = base + cnt;
+    sum_out = ptile[tile] + acc;
+}
+
+__global__ void __launch_bounds__(256) ll_search_kernel(LloydDevice *st, const float *__restrict__ ks,
+                                                        const float *__restrict__ samp,
+                                                        const long long *__restrict__ ptile) {
+    if (st->done) return;
+    const int G = st->tab.G;
+    const int nb = 2 * G;  // boundaries 1 .. 2G
+    const int wpb = blockDim.x >> 5;
+    for (int r = 1 + blockIdx.x * wpb + warp_id(); r <= nb; r += gridDim.x * wpb) {
+        long long pos, sum;
+        warp_boundary_search(ks, samp, ptile, st->n_nz, st->n_tiles, st->mean, st->scale, st->tab.rstart[r], pos, sum);
+        if (lane_id() == 0) {
+            st->rpos[r] = pos;
+            st->rsum[r] = sum;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) ll_zone_kernel(LloydDevice *st, const float *__restrict__ ks) {
+    if (st->done) return;
+    __shared__ long long zpre[TB_KMAX + 1];
+    __shared__ long long s_warp[32];
+    __shared__ unsigned int sW[TB_KMAX];
+    __shared__ long long sS[TB_KMAX];
+    __shared__ long long sMin[TB_KMAX];
+    __shared__ long long sMax[TB_KMAX];
+    const RegionTable &T = st->tab;
+    const int G = T.G, m = T.m;
+    if (G == 0) return;
+    // prefix of zone sizes (G <= 1023): chunked scan by the 256 threads
+    {
+        const int per = (G + blockDim.x - 1) / blockDim.x;
+        const int lo = min(G, (int)threadIdx.x * per), hi = min(G, lo + per);
+        long long sum = 0;
+        for (int g = lo; g < hi; ++g) sum += st->rpos[2 * g + 2] - st->rpos[2 * g + 1];
+        long long incl = block_scan_incl<long long>(sum, [](long long a, long long b) { return a + b; }, s_warp);
+        long long run = incl - sum;
+        for (int g = lo; g < hi; ++g) {
+            zpre[g] = run;
+            run += st->rpos[2 * g + 2] - st->rpos[2 * g + 1];
+        }
+        if (threadIdx.x == blockDim.x - 1) zpre[G] = incl;
+    }
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        sW[i] = 0;
+        sS[i] = 0;
+        sMin[i] = 0x7fffffffffffffffll;
+        sMax[i] = -1;
+    }
+    __syncthreads();
+    const long long Z = zpre[G];
+    if (Z == 0) return;
+    long long chunk = (Z + gridDim.x - 1) / gridDim.x;
+    chunk = (chunk + blockDim.x - 1) / blockDim.x * blockDim.x;
+    const long long e0 = (long long)blockIdx.x * chunk, e1 = llmin2(Z, e0 + chunk);
+    const float mean = st->mean;
+    const double scale = st->scale;
+    const int lane = lane_id();
+    for (long long eb = e0; eb < e1; eb += blockDim.x) {  // e1 - e0 is a multiple of blockDim.x or ends at Z: uniform trips
+        long long e = eb + threadIdx.x;
+        bool valid = e < e1;
+        int di = -1;
+        long long q = 0, p = 0;
+        if (valid) {
+            int lo = 0, hi = G;  // largest g with zpre[g] <= e
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (zpre[mid] <= e)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            const int g = lo;
+            p = st->rpos[2 * g + 1] + (e - zpre[g]);
+            float xc = fsub(ks[p], mean);
+            di = zone_argmin(xc, T.dv, T.dcn, T.down, T.gp_lo[g], T.gp_hi[g] + 1);
+            q = fixed_q(xc, scale);
+        }
+        unsigned active = __ballot_sync(0xffffffffu, valid);
+        while (active) {
+            int leader = __ffs(active) - 1;
+            int L = __shfl_sync(0xffffffffu, di, leader);
+            bool mine = valid && di == L;
+            unsigned grp = __ballot_sync(0xffffffffu, mine);
+            long long sq = warp_sum_ll(mine ? q : 0);
+            long long pf = __shfl_sync(0xffffffffu, p, __ffs(grp) - 1);
+            long long pl = __shfl_sync(0xffffffffu, p, 31 - __clz(grp));
+            if (lane == leader) {
+                atomicAdd(&sW[L], (unsigned)__popc(grp));
+                atomicAdd((unsigned long long *)&sS[L], (unsigned long long)sq);
+                atomicMin(&sMin[L], pf);
+                atomicMax(&sMax[L], pl);
+            }
+            active &= ~grp;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        if (sW[i]) {
+            atomicAdd((unsigned long long *)&st->zW[i], (unsigned long long)sW[i]);
+            atomicAdd((unsigned long long *)&st->zS[i], (unsigned long long)sS[i]);
+            atomicMin(&st->zmin[i], sMin[i]);
+            atomicMax(&st->zmax[i], sMax[i]);
+        }
+    }
+}
+
+// ---- update ------------------------------------------------------------------------------------
+// NumPy pairwise sum of a small float32 array (numpy/_core/src/umath/loops_utils.h.src), single thread.
+__device__ float np_pairwise_small(const float *a, int n) {
+    if (n < 8) {
+        float r = 0.f;
+        for (int i = 0; i < n; ++i) r = fadd(r, a[i]);
+        return r;
+    }
+    if (n <= 128) {
+        float r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] = fadd(r[j], a[i + j]);
+        float res = fadd(fadd(fadd(r[0], r[1]), fadd(r[2], r[3])), fadd(fadd(r[4], r[5]), fadd(r[6], r[7])));
+        for (; i < n; ++i) res = fadd(res, a[i]);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return fadd(np_pairwise_small(a, n2), np_pairwise_small(a + n2, n - n2));
+}
+
+struct FarKey {  // priority of a relocation candidate: larger is farther
+    uint32_t d2, gap, ordx;
+};
+__device__ __forceinline__ bool far_before(const FarKey &a, const FarKey &b) {
+    if (a.d2 != b.d2) return a.d2 > b.d2;
+    if (a.gap != b.gap) return a.gap > b.gap;
+    return a.ordx > b.ordx;
+}
+__device__ __forceinline__ FarKey far_key(float xc, float c) {
+    float t = fsub(xc, c);
+    float d2 = fmul(t, t);
+    FarKey k;
+    k.d2 = __float_as_uint(d2);
+    uint32_t ox = f2ord(xc), oc = f2ord(c);
+    k.gap = ox > oc ? ox - oc : oc - ox;
+    k.ordx = ox;
+    return k;
+}
+
+// label (distinct index) of the sorted survivor at position p, from the region table + searched positions
+__device__ int label_at(const LloydDevice *st, const float *ks, long long p) {
+    const RegionTable &T = st->tab;
+    const int R = 2 * T.G + 1;
+    int lo = 0, hi = R;  // largest r with rpos[r] <= p
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (st->rpos[mid] <= p)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    if ((lo & 1) == 0) return safe_distinct_index(T.gp_hi, lo >> 1);
+    const int g = lo >> 1;
+    return zone_argmin(fsub(ks[p], st->mean), T.dv, T.dcn, T.down, T.gp_lo[g], T.gp_hi[g] + 1);
+}
+
+struct UpdateSmem {
+    long long Wd[TB_KMAX], Sd[TB_KMAX];    // per distinct index, then reused per id
+    long long W[TB_KMAX], S[TB_KMAX];      // per id
+    long long first[TB_KMAX], last[TB_KMAX];  // member cursors per distinct index
+    float raw[TB_KMAX], cnew[TB_KMAX], sq[TB_KMAX];
+    int empt[TB_KMAX];
+    float far_x[TB_KMAX];
+    int far_old[TB_KMAX];
+    float red_d[32];
+    int red_i[32], red_id[32];
+    uint32_t rk_d2[32], rk_gap[32], rk_ord[32];
+    int rk_who[32];
+    int n_empty, zdi, same, winner, stop_reloc;
+    long long zero_left;
+};
+
+__global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, const float *__restrict__ ks) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    UpdateSmem &U = *reinterpret_cast<UpdateSmem *>(smem_raw);
+    if (st->done) return;
+    const RegionTable &T = st->tab;
+    const int tid = threadIdx.x, k = st->k, m = T.m, G = T.G;
+    const float mean = st->mean;
+    const double scale = st->scale;
+    // ---- 1. per distinct index: zone partials + SAFE regions
+    if (tid < m) {
+        U.Wd[tid] = st->zW[tid];
+        U.Sd[tid] = st->zS[tid];
+        U.first[tid] = st->zmin[tid];
+        U.last[tid] = st->zmax[tid];
+    }
+    if (tid < k) {
+        U.W[tid] = 0;
+        U.S[tid] = 0;
+    }
+    __syncthreads();
+    if (tid <= G) {  // SAFE region s = tid is region 2s: positions [rpos[2s], rpos[2s+1])
+        const int di = safe_distinct_index(T.gp_hi, tid);
+        long long lo = st->rpos[2 * tid], hi = st->rpos[2 * tid + 1];
+        if (hi > lo) {
+            U.Wd[di] += hi - lo;  // one SAFE region per distinct index: no conflicts
+            U.Sd[di] += st->rsum[2 * tid + 1] - st->rsum[2 * tid];
+            U.first[di] = llmin2(U.first[di], lo);
+            U.last[di] = llmax2(U.last[di], hi - 1);
+        }
+    }
+    __syncthreads();
+    // ---- 2. zero run: label of x'_0 = fl(0 - mean) over all distinct centroids
+    const float x0 = fsub(0.f, mean);
+    if (st->n0 > 0) {
+        float d = INFINITY;
+        int id = 0x7fffffff, di = -1;
+        if (tid < m) {
+            d = skl_dist(fmul(-2.0f, x0), T.dv[tid], T.dcn[tid]);
+            id = T.down[tid];
+            di = tid;
+        }
+        // block argmin by (d, id)
+        for (int o = 16; o > 0; o >>= 1) {
+            float d2 = __shfl_xor_sync(0xffffffffu, d, o);
+            int id2 = __shfl_xor_sync(0xffffffffu, id, o);
+            int di2 = __shfl_xor_sync(0xffffffffu, di, o);
+            if (d2 < d || (d2 == d && id2 < id)) {
+                d = d2;
+                id = id2;
+                di = di2;
+            }
+        }
+        if (lane_id() == 0) {
+            U.red_d[warp_id()] = d;
+            U.red_id[warp_id()] = id;
+            U.red_i[warp_id()] = di;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < TB_THREADS / 32; ++w) {
+                if (U.red_d[w] < d || (U.red_d[w] == d && U.red_id[w] < id)) {
+                    d = U.red_d[w];
+                    id = U.red_id[w];
+                    di = U.red_i[w];
+                }
+            }
+            U.zdi = di;
+            const long long q0 = fixed_q(x0, scale);
+            U.Wd[di] += st->n0;
+            U.Sd[di] += st->n0 * q0;
+        }
+        __syncthreads();
+    } else if (tid == 0) {
+        U.zdi = -1;
+    }
+    __syncthreads();
+    // ---- 3. per cluster id
+    if (tid < m) {
+        U.W[T.down[tid]] = U.Wd[tid];
+        U.S[T.down[tid]] = U.Sd[tid];
+    }
+    if (tid == 0) {
+        U.same = 1;
+        U.n_empty = 0;
+    }
+    __syncthreads();
+    // ---- 4. label-equality proxy: identical exact (count, sum) per cluster as in the previous iteration
+    if (tid < k) {
+        if (U.W[tid] != st->Wprev[tid] || U.S[tid] != st->Sprev[tid]) U.same = 0;
+        st->Wprev[tid] = U.W[tid];
+        st->Sprev[tid] = U.S[tid];
+    }
+    __syncthreads();
+    // ---- 5. empty clusters (ascending id) and relocation
+    {
+        int e = (tid < k) && (U.W[tid] == 0);
+        int incl = block_scan_incl<int>(e, [](int a, int b) { return a + b; }, U.red_i);
+        if (e) U.empt[incl - 1] = tid;
+        if (tid == TB_THREADS - 1) U.n_empty = incl;
+        __syncthreads();
+    }
+    const int n_empty = U.n_empty;
+    if (n_empty > 0) {
+        // Streams of candidates: for every distinct index its members walked from the left end and from the
+        // right end (|x' - c| is V-shaped along a cluster's sorted members), plus the zero run.  The farthest
+        // remaining sample overall is always at the head of one of the streams; pop n_empty times.
+        // Thread di owns both cursors of distinct index di; the owner of the zero run's cluster also owns
+        // the zero run (a third head).
+        long long pl = -1, pr = -2;  // empty stream when pl > pr
+        float cown = 0.f;
+        FarKey kl{0, 0, 0}, kr{0, 0, 0};
+        float xl = 0.f, xr = 0.f;
+        bool has_l = false, has_r = false;
+        if (tid < m) {
+            cown = T.dv[tid];
+            if (U.last[tid] >= U.first[tid] && U.last[tid] >= 0) {
+                pl = U.first[tid];
+                pr = U.last[tid];
+            }
+        }
+        auto refresh = [&]() {
+            has_l = has_r = false;
+            if (tid < m && pl <= pr) {
+                xl = fsub(ks[pl], mean);
+                kl = far_key(xl, cown);
+                has_l = true;
+                if (pr > pl) {
+                    xr = fsub(ks[pr], mean);
+                    kr = far_key(xr, cown);
+                    has_r = true;
+                }
+            }
+        };
+        refresh();
+        if (tid == 0) {
+            U.zero_left = st->n0;
+            U.stop_reloc = 0;
+        }
+        __syncthreads();
+        const FarKey kz = far_key(x0, U.zdi >= 0 ? T.dv[U.zdi] : 0.f);
+        int n_done = 0;
+        for (int pop = 0; pop < n_empty; ++pop) {
+            // best head of this thread: 0 = left, 1 = right, 2 = zero run
+            FarKey best{0, 0, 0};
+            int who = -1;
+            if (has_l) {
+                best = kl;
+                who = 0;
+            }
+            if (has_r && (who < 0 || far_before(kr, best))) {
+                best = kr;
+                who = 1;
+            }
+            if (tid == U.zdi && U.zero_left > 0 && (who < 0 || far_before(kz, best))) {
+                best = kz;
+                who = 2;
+            }
+            int owner = who >= 0 ? tid : -1;
+            // block argmax
+            for (int o = 16; o > 0; o >>= 1) {
+                FarKey ob;
+                ob.d2 = __shfl_xor_sync(0xffffffffu, best.d2, o);
+                ob.gap = __shfl_xor_sync(0xffffffffu, best.gap, o);
+                ob.ordx = __shfl_xor_sync(0xffffffffu, best.ordx, o);
+                int oo = __shfl_xor_sync(0xffffffffu, owner, o);
+                if (oo >= 0 && (owner < 0 || far_before(ob, best) ||
+                                (!far_before(best, ob) && oo < owner))) {
+                    best = ob;
+                    owner = oo;
+                }
+            }
+            if (lane_id() == 0) {
+                U.rk_d2[warp_id()] = best.d2;
+                U.rk_gap[warp_id()] = best.gap;
+                U.rk_ord[warp_id()] = best.ordx;
+                U.rk_who[warp_id()] = owner;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < TB_THREADS / 32; ++w) {
+                    FarKey ob{U.rk_d2[w], U.rk_gap[w], U.rk_ord[w]};
+                    int oo = U.rk_who[w];
+                    if (oo >= 0 && (owner < 0 || far_before(ob, best) || (!far_before(best, ob) && oo < owner))) {
+                        best = ob;
+                        owner = oo;
+                    }
+                }
+                U.winner = owner;
+                // np.max(distances) == 0 -> relocation is skipped altogether (_k_means_common.pyx:192-195)
+                if (pop == 0 && (owner < 0 || best.d2 == 0u)) U.stop_reloc = 1;
+            }
+            __syncthreads();
+            if (U.stop_reloc || U.winner < 0) break;
+            if (tid == U.winner) {
+                if (who == 2) {
+                    U.far_x[pop] = x0;
+                    U.far_old[pop] = T.down[U.zdi];
+                    U.zero_left -= 1;
+                } else {
+                    U.far_x[pop] = who == 0 ? xl : xr;
+                    U.far_old[pop] = T.down[tid];
+                    // advance the cursor to the next member of this distinct index
+                    if (who == 0) {
+                        do {
+                            ++pl;
+                        } while (pl <= pr && label_at(st, ks, pl) != tid);
+                    } else {
+                        do {
+                            --pr;
+                        } while (pr >= pl && label_at(st, ks, pr) != tid);
+                    }
+                    refresh();
+                }
+            }
+            n_done = pop + 1;
+            __syncthreads();
+        }
+        __syncthreads();
+        if (tid == 0 && !U.stop_reloc) {
+            for (int i = 0; i < n_done; ++i) {
+                const int nw = U.empt[i], od = U.far_old[i];
+                const long long q = fixed_q(U.far_x[i], scale);
+                U.S[od] -= q;
+                U.S[nw] = q;
+                U.W[nw] = 1;
+                U.W[od] -= 1;
+            }
+            st->n_reloc += n_done;
+        }
+        __syncthreads();
+    }
+    // ---- 6. averages (_average_centers), shift (_center_shift)
+    if (tid < k) U.raw[tid] = (float)__ddiv_rn((double)U.S[tid], scale);
+    __syncthreads();
+    if (tid == 0) {
+        int amax = 0;
+        for (int j = 1; j < k; ++j)
+            if (U.W[j] > U.W[amax]) amax = j;
+        U.winner = amax;
+    }
+    __syncthreads();
+    if (tid < k) {
+        const int amax = U.winner;
+        auto avg = [&](int j) { return fmul(U.raw[j], (float)__ddiv_rn(1.0, (double)U.W[j])); };
+        float cn;
+        if (U.W[tid] > 0)
+            cn = avg(tid);
+        else  // in-place ascending loop: rows below amax see its raw sum, rows above see its average
+            cn = amax < tid ? (U.W[amax] > 0 ? avg(amax) : U.raw[amax]) : U.raw[amax];
+        U.cnew[tid] = cn;
+        float t = fsub(cn, st->c[tid]);
+        float r = fmul(t, t);
+        float sh = (float)__dsqrt_rn((double)r);
+        U.sq[tid] = fmul(sh, sh);
+    }
+    __syncthreads();
+    // ---- 7. convergence (_kmeans.py:721-738)
+    if (tid == 0) {
+        float tot = np_pairwise_small(U.sq, k);
+        int stop = 0, strict = 0;
+        if (U.same) {
+            stop = 1;
+            strict = 1;
+        } else if (tot <= st->tol) {
+            stop = 1;
+        }
+        U.same = strict;
+        U.stop_reloc = stop;
+    }
+    __syncthreads();
+    {
+        const int strict = U.same, stop = U.stop_reloc;
+        const int last_iter = st->iter + 1 >= st->max_iter;
+        if (tid < k) {
+            // labels of a strict stop belong to the centroids the E-step used; otherwise a final E-step
+            // with the new centroids follows (emit.cu)
+            if (stop || last_iter) st->c_emit[tid] = strict ? st->c[tid] : U.cnew[tid];
+            st->c[tid] = U.cnew[tid];
+        }
+        if (tid == 0) {
+            st->iter += 1;
+            if (stop || last_iter) {
+                st->done = 1;
+                st->strict = strict;
+                st->n_iter = st->iter;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------
+LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max_iter, double tol_rel,
+                      float *h_centred_final, float *h_centred_emit) {
+    const int k = h.k;
+    if (k < 1 || k > TB_KMAX) NNC_FAIL(NNC_ERR_UNSUPPORTED, "k-means: k = %d outside [1, %d]", k, TB_KMAX);
+    static bool configured = false;
+    if (!configured) {
+        NNC_CUDA(cudaFuncSetAttribute(ll_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateSmem)));
+        configured = true;
+    }
+    LloydDevice *st = arena_alloc_t<LloydDevice>(ctx, 1);
+    h.d_state = st;
+    const long long n_tiles = (h.n_nz + LL_TS - 1) / LL_TS;
+    h.n_tiles = n_tiles;
+    long long *tsum = arena_alloc_t<long long>(ctx, n_tiles + 1);
+    long long *ptile = arena_alloc_t<long long>(ctx, n_tiles + 2);
+    float *samp = arena_alloc_t<float>(ctx, n_tiles + 1);
+    float *d_init = arena_alloc_t<float>(ctx, k);
+    h.d_ptile = ptile;
+    h.d_samp = samp;
+
+    // fixed-point exponent from the data range (zeros included through min/max over all elements)
+    const DevScalars &sc = *ctx->h_scal;
+    const float mean = h.mean;
+    volatile float xmin = ord2f(sc.min_ord) - mean, xmax = ord2f(sc.max_ord) - mean;
+    float xabs = fmaxf(fabsf(xmin), fabsf(xmax));
+    int E = xabs > 0.f ? ilogbf(xabs) + 1 : 0;
+    double scale = ldexp(1.0, 30 - E);
+
+    LloydHeader hs;
+    memset(&hs, 0, sizeof(hs));
+    hs.k = k;
+    hs.max_iter = max_iter;
+    hs.fixed_exp = E;
+    hs.n = h.n;
+    hs.n_nz = h.n_nz;
+    hs.n0 = h.n0;
+    hs.n_tiles = n_tiles;
+    hs.mean = mean;
+    hs.xabs_max = xabs;
+    hs.scale = scale;
+    hs.tol_rel = tol_rel;
+    NNC_CUDA(cudaMemsetAsync(st, 0, sizeof(LloydDevice), ctx->stream));
+    NNC_CUDA(cudaMemcpyAsync(static_cast<LloydHeader *>(st), &hs, sizeof(hs), cudaMemcpyHostToDevice, ctx->stream));
+    NNC_CUDA(cudaMemcpyAsync(d_init, h_init, sizeof(float) * k, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_tiles > 0) {
+        int grid = (int)std::min<long long>((long long)ctx->sm_count * 8, (n_tiles + 7) / 8);
+        NNC_LAUNCH(ctx, ll_tilesum_kernel, grid, 256, 0, h.d_sorted, h.n_nz, mean, scale, tsum, samp, st);
+    }
+    NNC_LAUNCH(ctx, ll_scan_kernel, 1, 1024, 0, tsum, n_tiles, ptile, st);
+    NNC_LAUNCH(ctx, ll_init_kernel, 1, TB_KMAX, 0, st, d_init);
+    prof_mark(ctx, "lloyd_prep");
+
+    struct Ctl {
+        int iter, done, strict, n_reloc, n_iter, pad;
+    } ctl;
+    const int batch = 8;
+    const int search_grid = std::max(1, std::min(ctx->sm_count * 2, (2 * k + 7) / 8));
+    const int zone_grid = ctx->sm_count * 2;
+    int launched = 0;
+    for (;;) {
+        for (int b = 0; b < batch && launched < max_iter; ++b, ++launched) {
+            NNC_LAUNCH(ctx, ll_table_kernel, 1, TB_THREADS, 0, st);
+            NNC_LAUNCH(ctx, ll_search_kernel, search_grid, 256, 0, st, h.d_sorted, samp, ptile);
+            NNC_LAUNCH(ctx, ll_zone_kernel, zone_grid, 256, 0, st, h.d_sorted);
+            NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted);
+        }
+        NNC_CUDA(cudaMemcpyAsync(&ctl, &st->iter, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
+        NNC_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctl.done || launched >= max_iter) break;
+    }
+    if (!ctl.done) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: loop ended without a stop decision (iter %d)", ctl.iter);
+    NNC_CUDA(cudaMemcpyAsync(h_centred_final, st->c, sizeof(float) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    NNC_CUDA(cudaMemcpyAsync(h_centred_emit, st->c_emit, sizeof(float) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    float tol_h = 0.f;
+    NNC_CUDA(cudaMemcpyAsync(&tol_h, &st->tol, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    NNC_CUDA(cudaStreamSynchronize(ctx->stream));
+    prof_mark(ctx, "lloyd_iters");
+    LloydResult r;
+    r.n_iter = ctl.n_iter;
+    r.strict = ctl.strict;
+    r.n_reloc = ctl.n_reloc;
+    r.fixed_exp = E;
+    r.tol = tol_h;
+    return r;
+}
+
+}  // namespace nnc

@@ -1,0 +1,635 @@
+// reduce_np.cu -- float32 reductions that reproduce NumPy's pairwise summation bit for bit, with the
+// pruning passes fused into them.
+//
+// Replaces np.std / |w| < thr / w[mask] = 0 of the reference's prune_weigth
+// (neural_network_compression/common/utility.py:159-163) and X.mean(axis=0) of sklearn's KMeans.fit
+// (sklearn/cluster/_kmeans.py:1486-1493).
+//
+// NumPy's float32 add.reduce is a fixed binary tree (numpy/_core/src/umath/loops_utils.h.src,
+// @TYPE@_pairwise_sum): a node of n > 128 elements splits at n2 = (n/2) rounded down to a multiple of 8;
+// a leaf (n <= 128) keeps 8 strided accumulators, combines them as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) and
+// then adds the n%8 tail sequentially.  Because the tree only depends on n, the GPU evaluates exactly the
+// same tree: the top `depth` levels form a complete binary tree whose 2^depth subtrees ("tiles", <= 4096
+// elements each) are reduced by one CTA each out of shared memory; a one-CTA kernel then folds the 2^depth
+// partials pairwise.  Every addition is an explicit __fadd_rn, so the result equals NumPy's float32 value.
+//
+// Pruning is two such passes (13 B/weight instead of 17):
+//   pass 1  tree-sum of x (-> mean), plus fp64 sum / sum of squares as an ESTIMATE of the std;
+//   pass 2  tree-sum of fl((x-mean)^2) (-> NumPy's exact var/std/threshold) and, in the same read, the
+//           speculative apply: elements whose |x| is outside a +-2^-16 relative band around the estimated
+//           threshold are final (written as 0 / kept, mask byte emitted); the few elements inside the band
+//           go to a side list and are decided by a fix-up kernel once the exact threshold is known.
+#include <math.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace nnc {
+
+constexpr int NP_TILE_MAX = 4096;
+constexpr int NP_THREADS = 256;
+constexpr int NP_HEAP = 128;  // heap slots of a tile's sub-tree (depth <= 6)
+
+static inline int64_t half_down(int64_t s) {
+    int64_t n2 = s / 2;
+    return n2 - n2 % 8;
+}
+
+NpPlan np_plan(int64_t n) {
+    int d = 0;
+    int64_t s = n;
+    while (s > NP_TILE_MAX) {  // follow the right (larger) children
+        s = s - half_down(s);
+        d++;
+    }
+    NpPlan p;
+    p.depth = d;
+    p.num_tiles = 1u << d;
+    return p;
+}
+size_t np_partials_bytes(const NpPlan &p) { return sizeof(float) * 2 * (size_t)p.num_tiles; }
+
+__device__ __forceinline__ void np_tile_root(int64_t n, int depth, uint32_t t, int64_t &off, int &sz) {
+    int64_t o = 0, s = n;
+    for (int lvl = depth - 1; lvl >= 0; --lvl) {
+        int64_t n2 = s / 2;
+        n2 -= n2 % 8;
+        if ((t >> lvl) & 1u) {
+            o += n2;
+            s -= n2;
+        } else {
+            s = n2;
+        }
+    }
+    off = o;
+    sz = (int)s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Visitors: what one pass does with each element besides producing the term that is tree-summed.
+// ---------------------------------------------------------------------------------------------
+struct BlockAux {  // shared scratch for visitor epilogues
+    double d[2][NP_THREADS / 32];
+    unsigned long long u[2][NP_THREADS / 32];
+    uint32_t o[4][NP_THREADS / 32];
+};
+
+// pass 1 of pruning / nnc_stats: term = x; side: fp64 sum, sum of squares, non-finite count.
+struct VisitStats {
+    DevScalars *sc;
+    double s = 0.0, s2 = 0.0;
+    unsigned long long bad = 0;
+    __device__ __forceinline__ void begin() {}
+    __device__ __forceinline__ float4 load4(const float *p) const { return ld_stream_f4(p); }
+    __device__ __forceinline__ float load1(const float *p) const { return ld_stream_f1(p); }
+    __device__ __forceinline__ float one(float x) {
+        double xd = (double)x;
+        s += xd;
+        s2 = fma(xd, xd, s2);
+        bad += !isfinite(x);
+        return x;
+    }
+    __device__ __forceinline__ float4 visit4(int64_t, const float *, float4 x) {
+        return make_float4(one(x.x), one(x.y), one(x.z), one(x.w));
+    }
+    __device__ __forceinline__ float visit1(int64_t, const float *, float x) { return one(x); }
+    __device__ void finish(BlockAux &aux) {
+        double a = warp_sum_d(s), b = warp_sum_d(s2);
+        unsigned long long c = warp_sum_ull(bad);
+        if (lane_id() == 0) {
+            aux.d[0][warp_id()] = a;
+            aux.d[1][warp_id()] = b;
+            aux.u[0][warp_id()] = c;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double ta = 0, tb = 0;
+            unsigned long long tc = 0;
+            for (int i = 0; i < NP_THREADS / 32; i++) {
+                ta += aux.d[0][i];
+                tb += aux.d[1][i];
+                tc += aux.u[0][i];
+            }
+            atomicAdd(&sc->sum_d, ta);
+            atomicAdd(&sc->sumsq_d, tb);
+            if (tc) atomicAdd(&sc->n_nonfinite, tc);
+        }
+    }
+};
+
+// plain centred squares (nnc_stats second pass, non-speculative prune fallback)
+struct VisitCenSq {
+    DevScalars *sc;
+    float mean;
+    __device__ __forceinline__ void begin() { mean = sc->mean; }
+    __device__ __forceinline__ float4 load4(const float *p) const { return ld_stream_f4(p); }
+    __device__ __forceinline__ float load1(const float *p) const { return ld_stream_f1(p); }
+    __device__ __forceinline__ float one(float x) const {
+        float t = fsub(x, mean);
+        return fmul(t, t);
+    }
+    __device__ __forceinline__ float4 visit4(int64_t, const float *, float4 x) {
+        return make_float4(one(x.x), one(x.y), one(x.z), one(x.w));
+    }
+    __device__ __forceinline__ float visit1(int64_t, const float *, float x) { return one(x); }
+    __device__ void finish(BlockAux &) {}
+};
+
+// pass 2 of pruning: centred squares + speculative apply (see file header).
+struct VisitCenSqApply {
+    DevScalars *sc;
+    float *w;            // in place
+    uint8_t *mask;
+    long long *side_idx;
+    float *side_val;
+    unsigned long long side_cap;
+    int mask_vec_ok;     // mask base 4-byte aligned
+    float mean, lo, hi;
+    unsigned long long pruned = 0;
+    __device__ __forceinline__ void begin() {
+        mean = sc->mean;
+        lo = (float)sc->band_lo;  // already fp32-exact thresholds (see prune_finalize1)
+        hi = (float)sc->band_hi;
+    }
+    // the kernel writes the memory it reads: no non-coherent path here
+    __device__ __forceinline__ float4 load4(const float *p) const { return *reinterpret_cast<const float4 *>(p); }
+    __device__ __forceinline__ float load1(const float *p) const { return *p; }
+    __device__ __forceinline__ float one(int64_t g, float x, float &outv, uint32_t &m) {
+        float t = fsub(x, mean);
+        float a = fabsf(x);
+        if (a < lo) {
+            outv = 0.f;
+            m = 1;
+            pruned++;
+        } else {
+            outv = x;
+            m = 0;
+            if (a < hi) {  // inside the band: decided later with the exact threshold
+                unsigned long long slot = atomicAdd(&sc->band_count, 1ull);
+                if (slot < side_cap) {
+                    side_idx[slot] = g;
+                    side_val[slot] = x;
+                } else {
+                    atomicAdd(&sc->band_dropped, 1ull);
+                }
+            }
+        }
+        return fmul(t, t);
+    }
+    __device__ __forceinline__ float4 visit4(int64_t g, const float *p, float4 x) {
+        float4 o, r;
+        uint32_t m0, m1, m2, m3;
+        r.x = one(g, x.x, o.x, m0);
+        r.y = one(g + 1, x.y, o.y, m1);
+        r.z = one(g + 2, x.z, o.z, m2);
+        r.w = one(g + 3, x.w, o.w, m3);
+        if (m0 | m1 | m2 | m3) *reinterpret_cast<float4 *>(w + g) = o;
+        uint32_t mm = m0 | (m1 << 8) | (m2 << 16) | (m3 << 24);
+        if (mask_vec_ok) {
+            *reinterpret_cast<uint32_t *>(mask + g) = mm;
+        } else {
+            mask[g] = (uint8_t)m0;
+            mask[g + 1] = (uint8_t)m1;
+            mask[g + 2] = (uint8_t)m2;
+            mask[g + 3] = (uint8_t)m3;
+        }
+        (void)p;
+        return r;
+    }
+    __device__ __forceinline__ float visit1(int64_t g, const float *, float x) {
+        float o;
+        uint32_t m;
+        float r = one(g, x, o, m);
+        if (m) w[g] = o;
+        mask[g] = (uint8_t)m;
+        return r;
+    }
+    __device__ void finish(BlockAux &aux) {
+        unsigned long long c = warp_sum_ull(pruned);
+        if (lane_id() == 0) aux.u[0][warp_id()] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t = 0;
+            for (int i = 0; i < NP_THREADS / 32; i++) t += aux.u[0][i];
+            if (t) atomicAdd(&sc->n_pruned, t);
+        }
+    }
+};
+
+// k-means prologue: term = x (-> mean); side: min / max (all and non-zero), non-zero count, non-finite.
+struct VisitQuant {
+    DevScalars *sc;
+    uint32_t mn = 0xffffffffu, mx = 0u, mnz = 0xffffffffu, mxz = 0u;
+    unsigned long long nz = 0, bad = 0;
+    __device__ __forceinline__ void begin() {}
+    __device__ __forceinline__ float4 load4(const float *p) const { return ld_stream_f4(p); }
+    __device__ __forceinline__ float load1(const float *p) const { return ld_stream_f1(p); }
+    __device__ __forceinline__ float one(float x) {
+        float xc = x == 0.f ? 0.f : x;  // -0.0 -> +0.0 for the ordered key
+        uint32_t o = f2ord(xc);
+        mn = min(mn, o);
+        mx = max(mx, o);
+        if (x != 0.f) {
+            nz++;
+            mnz = min(mnz, o);
+            mxz = max(mxz, o);
+        }
+        bad += !isfinite(x);
+        return x;
+    }
+    __device__ __forceinline__ float4 visit4(int64_t, const float *, float4 x) {
+        return make_float4(one(x.x), one(x.y), one(x.z), one(x.w));
+    }
+    __device__ __forceinline__ float visit1(int64_t, const float *, float x) { return one(x); }
+    __device__ void finish(BlockAux &aux) {
+        uint32_t a = warp_min_u(mn), b = warp_max_u(mx), c = warp_min_u(mnz), d = warp_max_u(mxz);
+        unsigned long long e = warp_sum_ull(nz), f = warp_sum_ull(bad);
+        if (lane_id() == 0) {
+            aux.o[0][warp_id()] = a;
+            aux.o[1][warp_id()] = b;
+            aux.o[2][warp_id()] = c;
+            aux.o[3][warp_id()] = d;
+            aux.u[0][warp_id()] = e;
+            aux.u[1][warp_id()] = f;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < NP_THREADS / 32; i++) {
+                a = min(a, aux.o[0][i]);
+                b = max(b, aux.o[1][i]);
+                c = min(c, aux.o[2][i]);
+                d = max(d, aux.o[3][i]);
+                e += aux.u[0][i];
+                f += aux.u[1][i];
+            }
+            atomicMin(&sc->min_ord, a);
+            atomicMax(&sc->max_ord, b);
+            atomicMin(&sc->min_nz_ord, c);
+            atomicMax(&sc->max_nz_ord, d);
+            if (e) atomicAdd(&sc->n_nz, e);
+            if (f) atomicAdd(&sc->n_nonfinite, f);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// The tree kernel: one tile (= one depth-`depth` subtree of NumPy's recursion) per loop iteration.
+// ---------------------------------------------------------------------------------------------
+template <class V>
+__global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, int64_t n, int depth, int vec_ok,
+                                                             float *partials, V v) {
+    __shared__ __align__(16) float tile[NP_TILE_MAX + 8];
+    __shared__ float heap_val[NP_HEAP];
+    __shared__ short node_off[NP_HEAP];
+    __shared__ short node_sz[NP_HEAP];
+    __shared__ unsigned char leaf_list[NP_HEAP];
+    __shared__ int n_leaves;
+    __shared__ BlockAux aux;
+
+    v.begin();
+    const uint32_t num_tiles = 1u << depth;
+    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int64_t off;
+        int sz;
+        np_tile_root(n, depth, t, off, sz);
+        if (threadIdx.x == 0) n_leaves = 0;
+        // ---- load + visit: global -> terms in shared memory
+        const float *src = a + off;
+        if (vec_ok) {
+            int nvec = sz >> 2;
+            for (int i = threadIdx.x; i < nvec; i += NP_THREADS) {
+                float4 x = v.load4(src + 4 * i);
+                float4 r = v.visit4(off + 4 * i, src + 4 * i, x);
+                *reinterpret_cast<float4 *>(&tile[4 * i]) = r;
+            }
+            for (int i = (nvec << 2) + threadIdx.x; i < sz; i += NP_THREADS) tile[i] = v.visit1(off + i, src + i, v.load1(src + i));
+        } else {
+            for (int i = threadIdx.x; i < sz; i += NP_THREADS) tile[i] = v.visit1(off + i, src + i, v.load1(src + i));
+        }
+        __syncthreads();  // n_leaves = 0 visible; tile complete
+        // ---- node table of this tile's sub-tree (heap indexing, root = 1)
+        {
+            int h = threadIdx.x;
+            if (h >= 1 && h < NP_HEAP) {
+                int e = 31 - __clz(h);
+                int o = 0, s = sz;
+                bool ok = true;
+                for (int lvl = e - 1; lvl >= 0; --lvl) {
+                    if (s <= 128) {
+                        ok = false;
+                        break;
+                    }
+                    int n2 = s / 2;
+                    n2 -= n2 % 8;
+                    if ((h >> lvl) & 1) {
+                        o += n2;
+                        s -= n2;
+                    } else {
+                        s = n2;
+                    }
+                }
+                node_off[h] = (short)o;
+                node_sz[h] = ok ? (short)s : (short)0;
+                if (ok && s <= 128) {
+                    int slot = atomicAdd(&n_leaves, 1);
+                    leaf_list[slot] = (unsigned char)h;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- leaves: 8 lanes per leaf, NumPy's 8 strided accumulators
+        {
+            const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;
+            const int nl = n_leaves;
+            for (int base = 0; base < nl; base += NP_THREADS / 8) {
+                int li = base + grp;
+                bool valid = li < nl;
+                int h = valid ? leaf_list[li] : 0;
+                int o = valid ? node_off[h] : 0;
+                int s = valid ? node_sz[h] : 0;
+                float r = 0.f;
+                if (s >= 8) {
+                    int lim = s - (s & 7);
+                    r = tile[o + j];
+                    for (int i = 8; i < lim; i += 8) r = fadd(r, tile[o + i + j]);
+                }
+                r = fadd(r, __shfl_xor_sync(0xffffffffu, r, 1));
+                r = fadd(r, __shfl_xor_sync(0xffffffffu, r, 2));
+                r = fadd(r, __shfl_xor_sync(0xffffffffu, r, 4));
+                if (valid && j == 0) {
+                    if (s >= 8) {
+                        for (int i = s - (s & 7); i < s; ++i) r = fadd(r, tile[o + i]);
+                    } else {  // n < 8: plain sequential sum starting from 0
+                        r = 0.f;
+                        for (int i = 0; i < s; ++i) r = fadd(r, tile[o + i]);
+                    }
+                    heap_val[h] = r;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- fold the sub-tree bottom-up
+        for (int lvl = 5; lvl >= 0; --lvl) {
+            int h = threadIdx.x;
+            if (h >= (1 << lvl) && h < (2 << lvl) && node_sz[h] > 128) heap_val[h] = fadd(heap_val[2 * h], heap_val[2 * h + 1]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) partials[t] = heap_val[1];
+        __syncthreads();  // tile / tables are reused by the next iteration
+    }
+    v.finish(aux);
+}
+
+// Fold the 2^depth partials pairwise (complete binary tree) and run a scalar epilogue.
+enum { FIN_NONE = 0, FIN_MEAN = 1, FIN_VAR = 2, FIN_PRUNE1 = 3, FIN_PRUNE2 = 4 };
+
+struct FinArgs {
+    int mode;
+    int64_t n;
+    double q;
+    int thr_mode;   // 0: float32 product/compare, 1: float64
+    int std_smooth;
+};
+
+__device__ __forceinline__ float f32_ceil_of(double d) { return __double2float_ru(d); }
+
+__global__ void __launch_bounds__(1024) np_final_kernel(float *partials, uint32_t count, DevScalars *sc, FinArgs fa) {
+    float *src = partials, *dst = partials + count;
+    for (uint32_t len = count; len > 1; len >>= 1) {
+        uint32_t half = len >> 1;
+        for (uint32_t i = threadIdx.x; i < half; i += blockDim.x) dst[i] = fadd(src[2 * i], src[2 * i + 1]);
+        __syncthreads();
+        float *tmp = src;
+        src = dst;
+        dst = tmp;
+    }
+    if (threadIdx.x != 0) return;
+    float total = src[0];
+    sc->tree_sum = total;
+    double nd = (double)fa.n;
+    if (fa.mode == FIN_MEAN || fa.mode == FIN_PRUNE1) {
+        sc->mean = (float)((double)total / nd);  // np: true_divide(sum, intp count) in float64, cast back
+    }
+    if (fa.mode == FIN_PRUNE1) {
+        // fp64 estimate of the std -> speculation band around the threshold.  All comparisons against a
+        // double bound B are done in float32 as |x| < ceil32(B), which is equivalent for float32 |x|.
+        double m = sc->sum_d / nd;
+        double var = sc->sumsq_d / nd - m * m;
+        if (var < 0) var = 0;
+        double sd = sqrt(var);
+        double thr = fa.thr_mode == 0 ? (double)((float)sd * (float)fa.q) : sd * fa.q;
+        double lo = thr * (1.0 - 1.0 / 65536.0), hi = thr * (1.0 + 1.0 / 65536.0);
+        if (!(thr > 0)) {  // zero, negative or NaN threshold: nothing can be pruned speculatively
+            lo = 0.0;
+            hi = 0.0;
+        }
+        sc->band_lo = (double)f32_ceil_of(lo);
+        sc->band_hi = (double)f32_ceil_of(hi);
+    }
+    if (fa.mode == FIN_VAR || fa.mode == FIN_PRUNE2) {
+        float var = (float)((double)total / nd);
+        sc->var = var;
+        sc->std_ = sqrtf(var);
+    }
+    if (fa.mode == FIN_PRUNE2) {
+        double thr = fa.thr_mode == 0 ? (double)fmul(sc->std_, (float)fa.q) : (double)sc->std_ * fa.q;
+        sc->thr = thr;
+        float thr_f = f32_ceil_of(thr);  // |x| < thr  <=>  |x| < thr_f for float32 |x|
+        float lo = (float)sc->band_lo, hi = (float)sc->band_hi;
+        // the band [lo, hi) must contain the exact threshold, otherwise speculative decisions may be wrong
+        bool ok = (thr_f >= lo && thr_f <= hi) || (thr != thr) || (lo == 0.f && hi == 0.f && !(thr > 0));
+        sc->spec_failed = ok ? 0 : 1;
+    }
+}
+
+// Decide the band elements with the exact threshold.
+__global__ void prune_fixup_kernel(float *w, uint8_t *mask, const long long *side_idx, const float *side_val,
+                                   unsigned long long cap, DevScalars *sc) {
+    unsigned long long cnt = sc->band_count;
+    if (cnt > cap) cnt = cap;
+    float thr_f = f32_ceil_of(sc->thr);
+    unsigned long long pruned = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < cnt;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        long long g = side_idx[i];
+        if (fabsf(side_val[i]) < thr_f) {
+            w[g] = 0.f;
+            mask[g] = 1;
+            pruned++;
+        }
+    }
+    pruned = warp_sum_ull(pruned);
+    if (lane_id() == 0 && pruned) atomicAdd(&sc->n_pruned, pruned);
+}
+
+// Plain elementwise apply with a known threshold (std_smooth = False, and the safe fallback).
+// mode 0: fresh apply over original data.  mode 1: resolve pass after a speculative pass -- elements that are
+// already zero keep their mask byte, everything else is decided with the exact threshold.
+__global__ void __launch_bounds__(256) prune_apply_kernel(float *w, uint8_t *mask, int64_t n, DevScalars *sc, int vec_ok,
+                                                          int mode) {
+    float thr_f = f32_ceil_of(sc->thr);
+    unsigned long long pruned = 0;
+    int64_t nvec = vec_ok ? (n >> 2) : 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 x = *reinterpret_cast<const float4 *>(w + 4 * i);
+        uint32_t old = mode ? *reinterpret_cast<const uint32_t *>(mask + 4 * i) : 0u;
+        uint32_t m0 = fabsf(x.x) < thr_f, m1 = fabsf(x.y) < thr_f, m2 = fabsf(x.z) < thr_f, m3 = fabsf(x.w) < thr_f;
+        uint32_t mm = m0 | (m1 << 8) | (m2 << 16) | (m3 << 24);
+        if (mode) {
+            uint32_t fresh = mm & ~old;  // newly pruned by this pass
+            pruned += __popc(fresh);
+            mm |= old;
+        } else {
+            pruned += m0 + m1 + m2 + m3;
+        }
+        if (m0 | m1 | m2 | m3) {
+            x.x = m0 ? 0.f : x.x;
+            x.y = m1 ? 0.f : x.y;
+            x.z = m2 ? 0.f : x.z;
+            x.w = m3 ? 0.f : x.w;
+            *reinterpret_cast<float4 *>(w + 4 * i) = x;
+        }
+        *reinterpret_cast<uint32_t *>(mask + 4 * i) = mm;
+    }
+    for (int64_t i = (nvec << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float x = w[i];
+        uint32_t old = mode ? mask[i] : 0u;
+        uint32_t m = fabsf(x) < thr_f;
+        if (m) w[i] = 0.f;
+        if (mode) {
+            pruned += (m & ~old) & 1u;
+            m |= old;
+        } else {
+            pruned += m;
+        }
+        mask[i] = (uint8_t)m;
+    }
+    pruned = warp_sum_ull(pruned);
+    if (lane_id() == 0 && pruned) atomicAdd(&sc->n_pruned, pruned);
+}
+
+__global__ void set_thr_kernel(DevScalars *sc, double thr) { sc->thr = thr; }
+
+__global__ void __launch_bounds__(256) mask_apply_kernel(float *w, const uint8_t *mask, int64_t n, int vec_ok) {
+    int64_t nvec = vec_ok ? (n >> 2) : 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t mm = *reinterpret_cast<const uint32_t *>(mask + 4 * i);
+        if (mm) {
+            float4 x = *reinterpret_cast<const float4 *>(w + 4 * i);
+            if (mm & 0xffu) x.x = 0.f;
+            if (mm & 0xff00u) x.y = 0.f;
+            if (mm & 0xff0000u) x.z = 0.f;
+            if (mm & 0xff000000u) x.w = 0.f;
+            *reinterpret_cast<float4 *>(w + 4 * i) = x;
+        }
+    }
+    for (int64_t i = (nvec << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        if (mask[i]) w[i] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool aligned4(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+
+static int tree_grid(nnc_ctx *ctx, const NpPlan &p) {
+    int64_t g = (int64_t)ctx->sm_count * 8;
+    if ((int64_t)p.num_tiles < g) g = p.num_tiles;
+    return (int)g;
+}
+
+template <class V>
+static void run_tree(nnc_ctx *ctx, const float *d_w, int64_t n, V v, const FinArgs &fa) {
+    NpPlan p = np_plan(n);
+    float *partials = arena_alloc_t<float>(ctx, 2 * (size_t)p.num_tiles);
+    NNC_LAUNCH(ctx, np_tree_kernel<V>, tree_grid(ctx, p), NP_THREADS, 0, d_w, n, p.depth, aligned16(d_w) ? 1 : 0, partials,
+               v);
+    NNC_LAUNCH(ctx, np_final_kernel, 1, 1024, 0, partials, p.num_tiles, ctx->d_scal, fa);
+}
+
+static void clear_scalars(nnc_ctx *ctx) {
+    DevScalars z;
+    memset(&z, 0, sizeof(z));
+    z.min_ord = 0xffffffffu;
+    z.min_nz_ord = 0xffffffffu;
+    *ctx->h_scal = z;
+    NNC_CUDA(cudaMemcpyAsync(ctx->d_scal, ctx->h_scal, sizeof(DevScalars), cudaMemcpyHostToDevice, ctx->stream));
+}
+
+void np_stats(nnc_ctx *ctx, const float *d_w, int64_t n) {
+    clear_scalars(ctx);
+    VisitStats v1;
+    v1.sc = ctx->d_scal;
+    run_tree(ctx, d_w, n, v1, FinArgs{FIN_MEAN, n, 0.0, 0, 1});
+    VisitCenSq v2;
+    v2.sc = ctx->d_scal;
+    v2.mean = 0.f;
+    run_tree(ctx, d_w, n, v2, FinArgs{FIN_VAR, n, 0.0, 0, 1});
+}
+
+void quant_prologue(nnc_ctx *ctx, const float *d_w, int64_t n, float *) {
+    clear_scalars(ctx);
+    VisitQuant v;
+    v.sc = ctx->d_scal;
+    run_tree(ctx, d_w, n, v, FinArgs{FIN_MEAN, n, 0.0, 0, 1});
+}
+
+void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth, int thr_mode, uint8_t *d_mask) {
+    clear_scalars(ctx);
+    const int vec_ok = aligned16(d_w) && aligned4(d_mask);
+    const int ew_grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 16, (n / 4 + 255) / 256 + 1);
+    if (!std_smooth) {
+        double thr = thr_mode == 0 ? (double)(float)q : q;
+        NNC_LAUNCH(ctx, set_thr_kernel, 1, 1, 0, ctx->d_scal, thr);
+        NNC_LAUNCH(ctx, prune_apply_kernel, ew_grid, 256, 0, d_w, d_mask, n, ctx->d_scal, vec_ok, 0);
+        prof_mark(ctx, "apply");
+        return;
+    }
+    // pass 1: NumPy mean + fp64 estimate of the std -> speculation band
+    VisitStats v1;
+    v1.sc = ctx->d_scal;
+    run_tree(ctx, d_w, n, v1, FinArgs{FIN_PRUNE1, n, q, thr_mode, 1});
+    prof_mark(ctx, "mean");
+    // pass 2: NumPy var/std/threshold + speculative apply
+    unsigned long long cap = (unsigned long long)std::max<int64_t>(65536, n / 256);
+    long long *side_idx = arena_alloc_t<long long>(ctx, cap);
+    float *side_val = arena_alloc_t<float>(ctx, cap);
+    VisitCenSqApply v2;
+    v2.sc = ctx->d_scal;
+    v2.w = d_w;
+    v2.mask = d_mask;
+    v2.side_idx = side_idx;
+    v2.side_val = side_val;
+    v2.side_cap = cap;
+    v2.mask_vec_ok = aligned4(d_mask) ? 1 : 0;
+    v2.mean = v2.lo = v2.hi = 0.f;
+    run_tree(ctx, d_w, n, v2, FinArgs{FIN_PRUNE2, n, q, thr_mode, 1});
+    prof_mark(ctx, "var+apply");
+    NNC_LAUNCH(ctx, prune_fixup_kernel, 64, 256, 0, d_w, d_mask, side_idx, side_val, cap, ctx->d_scal);
+    prof_mark(ctx, "fixup");
+    read_scalars(ctx);
+    const DevScalars &s = *ctx->h_scal;
+    if (s.spec_failed || s.band_dropped) {
+        // Either the exact threshold left the speculation band (non-finite or badly scaled data) or the side
+        // list overflowed.  Everything that is still non-zero is re-decided with the exact threshold.  This is
+        // only wrong if the band was ABOVE the exact threshold (elements were zeroed that should have stayed),
+        // which cannot be undone in place: report it.
+        if (s.spec_failed && s.thr < s.band_lo && s.n_pruned > 0)
+            NNC_FAIL(NNC_ERR_INTERNAL, "prune: exact threshold %.9g below speculation band [%.9g, %.9g]", s.thr, s.band_lo,
+                     s.band_hi);
+        NNC_LAUNCH(ctx, prune_apply_kernel, ew_grid, 256, 0, d_w, d_mask, n, ctx->d_scal, vec_ok, 1);
+        prof_mark(ctx, "resolve");
+        read_scalars(ctx);
+    }
+}
+
+void mask_apply_device(nnc_ctx *ctx, float *d_w, const uint8_t *d_mask, int64_t n) {
+    const int vec_ok = aligned16(d_w) && aligned4(d_mask);
+    const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 16, (n / 4 + 255) / 256 + 1);
+    NNC_LAUNCH(ctx, mask_apply_kernel, grid, 256, 0, d_w, d_mask, n, vec_ok);
+}
+
+}  // namespace nnc

@@ -1,0 +1,317 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the utility.py mirror) against the CPU oracle.
+
+Bars (BASELINE.json north_star): masks and cluster indices bit-exact; centroids within 1e-5 relative of the
+reference semantics (oracle REF32 mode, itself pinned to the reference by tests/golden) and BIT-EXACT against
+the oracle's DET mode (the device's order-independent fixed-point accumulation).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from . import _data as D
+
+pytestmark = pytest.mark.gpu
+
+CENTROID_RTOL = 1e-5  # north_star: "Centroids must match within 1e-5 relative"
+
+
+@pytest.fixture(scope="module")
+def U():
+    from neural_network_compression_b200.common import utility
+
+    return utility
+
+
+# ---------------------------------------------------------------------------------------------------------
+# np.std restatement
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 127, 128, 129, 1000, 4095, 4096, 4097, 8193, 100003, (1 << 20) + 5, 3 * 1000 * 1000 + 1])
+def test_stats_bit_exact_vs_numpy(U, n):
+    w = D.gaussian(n, seed=n % 9973, sigma=0.05) + np.float32(0.01)
+    m, v, s = U.weight_stats(w)
+    assert m.tobytes() == np.mean(w).tobytes()
+    assert v.tobytes() == np.var(w).tobytes()
+    assert s.tobytes() == np.std(w).tobytes()
+
+
+def test_stats_16m(U):
+    w = D.gaussian(4096 * 4096)
+    m, v, s = U.weight_stats(w)
+    assert (m, v, s) == (np.mean(w), np.var(w), np.std(w))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# pruning
+# ---------------------------------------------------------------------------------------------------------
+def _check_prune(U, w, q, std_smooth=True):
+    w_dev, w_ora, w_np = w.copy(), w.copy(), w.copy()
+    mask_dev = U.prune_weigth(w_dev, q, std_smooth)
+    mask_ora = O.prune_weigth(w_ora, q, std_smooth)
+    # the reference expression itself (utility.py:159-162), NumPy being the real thing here
+    thr = np.std(w_np) * q if std_smooth else q
+    mask_np = np.abs(w_np) < thr
+    w_np[mask_np] = 0
+    assert mask_dev.dtype == np.bool_ and mask_dev.shape == w.shape
+    assert np.array_equal(mask_dev, mask_np)
+    assert np.array_equal(mask_dev, mask_ora)
+    assert w_dev.tobytes() == w_np.tobytes()
+    # NEP 50: a Python-float threshold is compared in float32
+    assert U.prune_weigth.last_threshold == (float(thr) if isinstance(thr, np.floating) else float(np.float32(thr)))
+    assert U.prune_weigth.last_pruned == int(mask_np.sum())
+
+
+def test_prune_lenet300(U):
+    for kind in ("glorot", "gauss"):
+        for name, w, b, (qw, qb) in D.lenet300_tensors(kind=kind):
+            _check_prune(U, w, qw)
+            _check_prune(U, b, qb)  # includes threshold 0 on the output bias: strict < prunes nothing
+
+
+def test_prune_lenet5(U):
+    for name, w, b, (qw, qb) in D.lenet5_tensors():
+        _check_prune(U, w, qw)
+        _check_prune(U, b, qb)
+
+
+@pytest.mark.parametrize("n", [1, 3, 5, 31, 1023, 4099, 65537, 1 << 20])
+@pytest.mark.parametrize("q", [0.25, 1, 2.5])
+def test_prune_sizes(U, n, q):
+    _check_prune(U, D.gaussian(n, seed=n), q)
+
+
+def test_prune_hard_threshold_and_f64_scalar(U):
+    w = D.gaussian(50001, seed=3)
+    _check_prune(U, w, 0.01, std_smooth=False)
+    _check_prune(U, w, np.float64(0.7))
+    _check_prune(U, w, np.float32(0.7))
+    _check_prune(U, w, 0)
+
+
+def test_prune_repeated_on_sparse(U):
+    # the trainer re-prunes the already sparse tensor every batch (trainer.py:144-148)
+    w = D.gaussian(235200, seed=5, sigma=0.05).reshape(784, 300)
+    for _ in range(4):
+        _check_prune(U, w, 1)
+        m = U.prune_weigth(w, 1)
+        assert m.sum() > 0
+
+
+def test_prune_special_values(U):
+    w = D.gaussian(10007, seed=11)
+    w[5] = -0.0
+    w[6] = 0.0
+    w[100:200] = 0.0
+    _check_prune(U, w, 1)
+    w = np.zeros(300, dtype=np.float32)  # all-zero bias: std 0, nothing is < 0
+    _check_prune(U, w, 1)
+    w = np.full(1000, 0.25, dtype=np.float32)
+    _check_prune(U, w, 1)
+
+
+def test_prune_torch_device_tensor(U):
+    import torch
+
+    w = D.gaussian(1 << 20, seed=21).reshape(1024, 1024)
+    ref = w.copy()
+    mask_ref = O.prune_weigth(ref, 1)
+    t = torch.from_numpy(w.copy()).cuda()
+    mask = U.prune_weigth(t, 1)
+    assert mask.is_cuda and mask.dtype == torch.bool and mask.shape == t.shape
+    assert np.array_equal(mask.cpu().numpy(), mask_ref)
+    assert t.cpu().numpy().tobytes() == ref.tobytes()
+    # unaligned device views take the scalar path
+    t2 = torch.from_numpy(w.copy()).cuda().reshape(-1)[1:100000]
+    ref2 = w.reshape(-1)[1:100000].copy()
+    m2 = U.prune_weigth(t2, 1)
+    mr2 = O.prune_weigth(ref2, 1)
+    assert np.array_equal(m2.cpu().numpy(), mr2)
+    assert t2.cpu().numpy().tobytes() == ref2.tobytes()
+
+
+def test_mask_apply(U):
+    w = D.gaussian(100003, seed=8)
+    mask = np.abs(w) < 0.01
+    g = D.gaussian(100003, seed=9)
+    expect = g.copy()
+    expect[mask] = 0
+    U.apply_mask(g, mask)
+    assert g.tobytes() == expect.tobytes()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# survivor selection, weight CDF
+# ---------------------------------------------------------------------------------------------------------
+def test_nonzero_and_cdf(U):
+    for n in [40, 1000, 30000, 235200, 1 << 20]:
+        w = D.gaussian(n, seed=n + 1, sigma=0.05)
+        O.prune_weigth(w, 1)
+        nz = U.nonzero_weights(w)
+        nz_ref = w[w != 0]
+        assert nz.tobytes() == nz_ref.tobytes()
+        x_ref, y_ref = O.get_weight_distribution(nz_ref)
+        x, y = U.get_weight_distribution(nz_ref)
+        assert x.tobytes() == x_ref.tobytes() and y.tobytes() == y_ref.tobytes()
+        x2, y2 = U.get_weight_distribution(w, skip_zeros=True)  # fused survivor selection
+        assert x2.tobytes() == x_ref.tobytes() and y2.tobytes() == y_ref.tobytes()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# k-means
+# ---------------------------------------------------------------------------------------------------------
+def _init_for(w, bits, mode, seed=0):
+    if mode == "linear":
+        return O.init_centroids(w, bits, "linear"), None
+    if mode == "density":
+        nz = w.ravel()[w.ravel() != 0]
+        cdfs = O.get_weight_distribution(nz)
+        return O.init_centroids(w, bits, "density", cdfs), cdfs
+    if mode == "forgy":
+        np.random.seed(seed)
+        idx = np.random.randint(0, w.size, size=2 ** bits)
+        return O.init_centroids(w, bits, "forgy", forgy_indices=idx), None
+    raise ValueError(mode)
+
+
+def _check_kmeans(U, w, bits, mode, seed=0, check_ref32=True):
+    space, cdfs = _init_for(w, bits, mode, seed)
+    if mode == "forgy":
+        np.random.seed(seed)
+    ris, km = U.get_quantized_weight(w, bits, mode, cdfs)
+    k = space.size
+    assert km.cluster_centers_.shape == (k, 1) and km.cluster_centers_.dtype == np.float32
+    assert km.labels_.dtype == np.int32 and km.labels_.shape == (w.size,)
+    assert ris.shape == w.shape and ris.dtype == np.float32
+    # --- bit-exact against the device semantic (oracle DET mode)
+    det = O.kmeans1d(w, space, mode=O.MODE_DET)
+    assert km.n_iter_ == det.n_iter_, (km.n_iter_, det.n_iter_)
+    assert km.cluster_centers_.tobytes() == det.cluster_centers_.tobytes()
+    assert np.array_equal(km.labels_, det.labels_)
+    assert km.inertia_ == det.inertia_
+    assert km.strict_convergence == det.strict and km.n_relocations == det.n_relocations
+    assert km.mean == det.mean and np.float32(km.tol_) == det.tol
+    # --- utility.py:239
+    assert ris.tobytes() == km.cluster_centers_[km.labels_].reshape(w.shape).tobytes()
+    # --- packed codes / histogram / decode round trip
+    assert np.array_equal(O.unpack_codes(km.packed_codes, w.size, km.code_bits), km.labels_)
+    assert km.packed_codes.tobytes() == O.pack_codes(km.labels_, km.code_bits).tobytes()
+    assert np.array_equal(km.code_histogram, np.bincount(km.labels_, minlength=k))
+    assert U.dequantize(km.packed_codes, w.size, km.code_bits, km.cluster_centers_).tobytes() == ris.tobytes()
+    # --- against the reference semantic (sequential float32 sums, sklearn at one thread)
+    if check_ref32:
+        ref = O.kmeans1d(w, space, mode=O.MODE_REF32)
+        scale = np.abs(ref.cluster_centers_).max()
+        # the reference's own sequential float32 sums drift beyond 1e-5 on big clusters;
+        # large tensors are compared with the float64 run of the reference in tests/test_gpu_golden.py
+        if ref.n_relocations == 0 and det.n_relocations == 0 and w.size <= 65536:
+            np.testing.assert_allclose(km.cluster_centers_, ref.cluster_centers_, rtol=CENTROID_RTOL, atol=CENTROID_RTOL * scale)
+        # indices: bit-exact given identical centroids (north_star) -- feed the reference's centroids
+        ref_km = U.KMeansResult(ref.cluster_centers_, None, 0, 0.0, centred_centers=ref.centred_centers, mean=ref.mean,
+                                code_bits=km.code_bits)
+        labels, packed, hist = U.assign_codes(w, ref_km)
+        if ref.strict and ref.n_relocations:
+            pass  # labels of a strict stop belong to the pre-relocation centroids, which the result does not expose
+        else:
+            assert np.array_equal(labels, ref.labels_)
+            assert np.array_equal(hist, np.bincount(ref.labels_, minlength=k))
+    return km
+
+
+def test_kmeans_lenet300_density2(U):
+    # config 1: prune with the trainer's thresholds, then 2-bit density k-means (k = 5) on the full tensors
+    for name, w, b, (qw, qb) in D.lenet300_tensors():
+        O.prune_weigth(w, qw)
+        O.prune_weigth(b, qb)
+        _check_kmeans(U, w, 2, "density")
+        _check_kmeans(U, b, 2, "density")
+
+
+def test_kmeans_lenet5_linear4(U):
+    # config 2
+    for name, w, b, (qw, qb) in D.lenet5_tensors():
+        O.prune_weigth(w, qw)
+        O.prune_weigth(b, qb)
+        _check_kmeans(U, w, 4, "linear")
+        if b.size >= 17:
+            _check_kmeans(U, b, 4, "linear")
+        else:
+            out, km = U.get_quantized_weight(b, 4, "linear")
+            assert out is b and km is None
+
+
+@pytest.mark.parametrize("bits,mode", [(5, "forgy"), (8, "linear"), (3, "density"), (8, "density"), (1, "linear")])
+def test_kmeans_pruned_gaussian(U, bits, mode):
+    w = D.gaussian(300 * 1000, seed=77).reshape(300, 1000)
+    O.prune_weigth(w, 1)
+    _check_kmeans(U, w, bits, mode)
+
+
+@pytest.mark.parametrize("bits,mode", [(4, "linear"), (5, "forgy"), (2, "density")])
+def test_kmeans_dense_gaussian(U, bits, mode):
+    w = D.gaussian(200 * 1000, seed=78)
+    _check_kmeans(U, w, bits, mode, seed=3)
+
+
+def test_kmeans_edge_cases(U):
+    # all-equal tensor (zero bias): one distinct label, all centroids equal
+    w = np.zeros(300, dtype=np.float32)
+    _check_kmeans(U, w, 2, "linear")
+    w = np.full(1000, 0.5, dtype=np.float32)
+    _check_kmeans(U, w, 3, "linear")
+    # tiny tensors around the guard n < 2^bits + 1
+    w = D.gaussian(17, seed=1)
+    _check_kmeans(U, w, 4, "linear")
+    out, km = U.get_quantized_weight(D.gaussian(16, seed=1), 4, "linear")
+    assert km is None
+    # few distinct values
+    w = np.repeat(np.array([-1.0, -0.5, 0.0, 0.25, 2.0], dtype=np.float32), 50)
+    np.random.RandomState(0).shuffle(w)
+    _check_kmeans(U, w, 2, "linear")
+    _check_kmeans(U, w, 3, "linear")
+    # non-zero mean, wide dynamic range
+    w = (D.gaussian(50000, seed=4, sigma=1.0) * 100 + 1000).astype(np.float32)
+    _check_kmeans(U, w, 4, "linear")
+
+
+def test_kmeans_errors(U):
+    w = D.gaussian(1000, seed=2)
+    with pytest.raises(Exception, match="error mode not found"):
+        U.get_quantized_weight(w, 2, "nope")
+    with pytest.raises(Exception, match="error mode not found"):
+        U.get_quantized_weight(w, 2, "density", None)
+    bad = w.copy()
+    bad[3] = np.nan
+    with pytest.raises(ValueError):
+        U.get_quantized_weight(bad, 2, "forgy")
+    with pytest.raises(TypeError):
+        U.get_quantized_weight(w.astype(np.float64), 2, "linear")
+
+
+def test_kmeans_torch_device(U):
+    import torch
+
+    w = D.gaussian(1 << 20, seed=31)
+    O.prune_weigth(w, 1)
+    space, _ = _init_for(w, 4, "linear")
+    det = O.kmeans1d(w, space, mode=O.MODE_DET)
+    t = torch.from_numpy(w).cuda().reshape(1024, 1024)
+    ris, km = U.get_quantized_weight(t, 4, "linear")
+    assert ris.is_cuda and km.labels_.is_cuda and km.packed_codes.is_cuda
+    assert km.cluster_centers_.tobytes() == det.cluster_centers_.tobytes()
+    assert np.array_equal(km.labels_.cpu().numpy(), det.labels_)
+    assert ris.cpu().numpy().tobytes() == det.cluster_centers_[det.labels_].reshape(1024, 1024).tobytes()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# trained-quantization gradient sum
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,k,bits", [(1000, 4, 0), (100003, 16, 4), (1 << 20, 256, 8), (1 << 20, 256, 0), (77777, 33, 6), (50000, 5, 3)])
+def test_grad_segsum(U, n, k, bits):
+    rng = np.random.RandomState(7)
+    grad = (rng.randn(n) * 1e-3).astype(np.float32)
+    labels = np.random.RandomState(8).randint(0, k, size=n).astype(np.int32)
+    expect = O.grad_segsum(grad, labels, k)
+    assert np.allclose(expect, np.bincount(labels, weights=grad.astype(np.float64), minlength=k), rtol=1e-12, atol=0)
+    codes = labels if bits == 0 else O.pack_codes(labels, bits)
+    got = U.cluster_gradient_sum(grad, codes, k, bits)
+    mag = np.bincount(labels, weights=np.abs(grad).astype(np.float64), minlength=k)
+    assert np.all(np.abs(got - expect) <= 1e-13 * mag + 1e-300)
