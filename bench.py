@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- weights/sec of prune + k-means weight sharing on B200 (BASELINE.json metric).
+
+One "step" = the whole compression of one synthetic layer:
+    std-threshold magnitude prune (q = 1.0, in place, bool mask out)            utility.py:134-163
+    + 8-bit linear-init 1-D k-means of the pruned tensor (zeros included)        utility.py:172-240
+    emitting the codebook, packed 8-bit cluster indices and their histogram.
+Workload (configs[3] of BASELINE.json): N(0, 0.02^2) float32, 2^30 weights in total ("bimodal post-prune":
+about 68 % zeros, survivors in two lobes |w| > sigma), contiguous shards over the ranks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 the CUDA path (one JSON line)
+    python bench.py --impl reference ...                                the CPU restatement, all host threads
+
+Timing: CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks.  Every step
+reads a fresh 4 GiB tensor (larger than the 126 MB L2), so no L2 flush is needed between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "weights/sec prune+k-means"
+UNIT = "weights/s"
+SIGMA = 0.02
+SEED = 2024
+QUALITY = 1.0
+BITS = 8
+MODE = "linear"
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons = [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    out["sm_max_mhz"] = float(f[2])
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = [x for x in sm if x >= 0.5 * max(sm)] or sm
+            out["sm_mhz"] = statistics.median(busy)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arms (oracle = test infrastructure; used here only as the timed baseline)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_pipeline(n_sample, threads):
+    """prune + 8-bit linear k-means of an n_sample-weight tensor of the same distribution with the CPU
+    restatement of the reference (oracle/nnc_oracle.c).  Returns (seconds, n_iter)."""
+    from oracle import oracle as O
+
+    O.set_threads(threads)
+    w = (np.random.RandomState(SEED).randn(n_sample) * SIGMA).astype(np.float32)
+    t0 = time.perf_counter()
+    O.prune_weigth(w, QUALITY)
+    space = O.init_centroids(w, BITS, MODE)
+    km = O.kmeans1d(w, space, mode=O.MODE_DET if threads > 1 else O.MODE_REF32)
+    O.pack_codes(km.labels_, BITS)
+    dt = time.perf_counter() - t0
+    return dt, km.n_iter_
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n_sample = args.cpu_sample
+    times = []
+    n_iter = 0
+    for i in range(args.warmup + args.steps):
+        dt, n_iter = cpu_pipeline(n_sample, cores)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = n_sample * len(times) / total
+    sample = "2^%d-weight N(0,0.02^2) tensor, same pipeline to convergence (%d Lloyd iterations)" % (int(np.log2(n_sample)), n_iter)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, world):
+    return {
+        "workload": "synthetic 2^%d-weight fp32 layer N(0,0.02^2), std-threshold prune q=1.0 (bimodal post-prune), "
+                    "8-bit linear-init k-means to convergence, packed 8-bit codes + histogram out" % int(np.log2(args.n)),
+        "n_weights": args.n, "bits": BITS, "init": MODE, "quality": QUALITY, "shards": world,
+        "l2": "every step reads a fresh %.1f GiB tensor (> 126 MB L2); no flush needed" % (args.n * 4 / world / 2 ** 30),
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+
+    from neural_network_compression_b200 import _native as N
+    from neural_network_compression_b200.common import utility as U
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ctx = N.default_context(local)
+    n_local = args.n // world
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- inputs: one fresh tensor per step (pruning is in place), generated on the device before timing
+    pool = min(K + W, args.pool)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(SEED + rank)
+    bufs = [torch.empty(n_local, dtype=torch.float32, device=dev) for _ in range(pool)]
+
+    def refill(count):
+        for b in bufs[:count]:
+            b.normal_(0.0, SIGMA, generator=gen)
+
+    def step(t):
+        mask, km = U.compress_weight(t, QUALITY, True, BITS, MODE)
+        return mask, km
+
+    # ---- warm-up
+    done = 0
+    refill(min(pool, W))
+    for i in range(W):
+        if i and i % pool == 0:
+            refill(min(pool, W - i))
+        step(bufs[i % pool])
+    # ---- timed region: K steps in chunks of `pool` fresh tensors
+    clocks = ClockSampler(local)
+    ctx.set_kernel_timing(True)
+    launches0 = ctx.total_launches()
+    total_ms = 0.0
+    n_iters = []
+    launches = 0
+    ktimes = {}
+    phases = {}
+    if rank == 0:
+        clocks.start()
+    while done < K:
+        cnt = min(pool, K - done)
+        refill(cnt)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(torch.cuda.current_stream())
+        for i in range(cnt):
+            mask, km = step(bufs[i])
+            # accounting only (host side, after the call returned)
+            n_iters.append(km.n_iter_)
+            for kname, ms in km.profile.items():
+                if kname != "launches":
+                    phases[kname] = phases.get(kname, 0.0) + ms
+        ev1.record(torch.cuda.current_stream())
+        barrier()
+        total_ms += ev0.elapsed_time(ev1)
+        done += cnt
+    clk = clocks.stop() if rank == 0 else None
+    ktimes = {name: [c, ms] for name, (c, ms) in ctx.last_kernel_times().items()}
+    launches = ctx.total_launches() - launches0
+    ctx.set_kernel_timing(False)
+    if dist is not None:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = args.n * K / (total_ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, torch, U, n_local, rank, world, dist, dev)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    # ---- roofline of the dominant kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    survivors = km.n_nonzero
+    s_frac = survivors / float(n_local)
+    dom = max(ktimes.items(), key=lambda kv: kv[1][1]) if ktimes else (None, (1, 0.0))
+    dom_name, (dom_cnt, dom_ms) = dom
+    kbytes = kernel_bytes(dom_name, n_local, survivors)
+    avg_ms = dom_ms / max(dom_cnt, 1)
+    achieved = kbytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    step_bytes = 13.0 + 4.0 + BITS / 8.0 + 52.0 * s_frac  # prune 13 + quantize 4 + b/8 + 52 s
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+        "roofline": {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "kernel": dom_name, "kernel_launches_per_step": dom_cnt / K, "kernel_ms_per_launch": avg_ms,
+            "kernel_algorithmic_bytes_per_launch": kbytes, "peak_source": peak_src,
+            "step_algorithmic_bytes_per_weight": step_bytes,
+            "step_achieved_gbs": step_bytes * args.n / world / (total_ms / K * 1e-3) / 1e9,
+            "step_frac": step_bytes * args.n / world / (total_ms / K * 1e-3) / 1e9 / peak,
+        },
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "n_iter": n_iters,
+        "survivor_fraction": s_frac,
+        "phase_ms_per_step": {kname: ms / K for kname, ms in sorted(phases.items())},
+        "kernel_ms_per_step": {kname: v[1] / K for kname, v in sorted(ktimes.items(), key=lambda kv: -kv[1][1])},
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        cores = 1
+        t_cpu, it_cpu = cpu_pipeline(args.cpu_sample, cores)
+        line["cpu_baseline"] = {
+            "value": args.cpu_sample / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "2^%d-weight tensor of the same distribution, same pipeline to convergence (%d Lloyd iterations, %.1f s), "
+                      "scalar C restatement of numpy/sklearn float32 arithmetic" % (int(np.log2(args.cpu_sample)), it_cpu, t_cpu),
+        }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def kernel_bytes(name, n, n_nz):
+    """Algorithmic bytes one launch of `name` moves."""
+    table = {
+        "np_tree_kernel<V>": 4.0 * n,                       # read once (the apply pass adds 5 B/weight: see DESIGN)
+        "(rs_pass_kernel<A, B>)": 8.0 * n_nz,               # read + write every key
+        "rs_hist_kernel": 4.0 * n_nz,
+        "compact_kernel": 4.0 * n + 4.0 * n_nz,
+        "emit_kernel<true>": 4.0 * n + BITS / 8.0 * n,
+        "emit_kernel<false>": 4.0 * n + BITS / 8.0 * n,
+        "ll_tilesum_kernel": 4.0 * n_nz,
+        "minmax_kernel": 4.0 * n,
+    }
+    return table.get(name, 0.0)
+
+
+def run_e2e(args, torch, U, n_local, rank, world, dist, dev):
+    steps = max(1, min(args.steps, args.e2e_steps))
+    host = torch.empty(n_local, dtype=torch.float32).pin_memory()
+    src = (torch.randn(n_local, generator=torch.Generator().manual_seed(SEED + 100 + rank)) * SIGMA) if n_local <= (1 << 26) else None
+    total = 0.0
+    h2d = d2h = 0
+    for i in range(steps + 1):
+        if src is not None:
+            host.copy_(src)
+        else:  # big tensors: fill from the device generator (untimed)
+            tmp = torch.empty(n_local, dtype=torch.float32, device=dev).normal_(0.0, SIGMA)
+            host.copy_(tmp)
+            del tmp
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        arr = host.numpy()
+        mask, km = U.compress_weight(arr, QUALITY, True, BITS, MODE)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i > 0:
+            total += dt
+        # prune: w in + (w, mask) out; quantize: w in + packed out (+ k centroids, histogram)
+        h2d = 2 * 4 * n_local
+        d2h = 4 * n_local + n_local + km.packed_codes.nbytes + 4 * km.n_clusters + 8 * km.n_clusters
+    if dist is not None:
+        t = torch.tensor([total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total = float(t.item())
+    return {"value": args.n * steps / total, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "steps": steps, "ms_per_step": 1e3 * total / steps, "api": "utility.compress_weight(numpy float32 in pinned host memory)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1 << 30, help="total weights over all ranks")
+    ap.add_argument("--pool", type=int, default=8, help="distinct input tensors kept resident")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 21)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -65,6 +65,13 @@ int nnc_timer_stop(nnc_ctx *ctx, float *ms_out);
 int nnc_last_profile(nnc_ctx *ctx, float *ms_out, int cap, int *n_out, const char **names_out,
                      int64_t *launches_out);
 
+/* Benchmarks: when on, every kernel launch is bracketed by CUDA events on the context's stream;
+ * nnc_last_kernel_times returns "kernel:launches:total_ms;..." accumulated since the last
+ * nnc_ctx_set_kernel_timing call.  nnc_ctx_total_launches: kernels launched over the context's lifetime. */
+int nnc_ctx_set_kernel_timing(nnc_ctx *ctx, int on);
+int nnc_last_kernel_times(nnc_ctx *ctx, const char **out);
+int nnc_ctx_total_launches(nnc_ctx *ctx, int64_t *out);
+
 /* ---- pruning (utility.py:134-163, trainer.py:177-206) ------------------------------------ */
 /* np.mean / np.var / np.std of a float32 tensor, bit-exact with NumPy's float32 pairwise
  * reduction (numpy/_core/_methods.py:117-233). */

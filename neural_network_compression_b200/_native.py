@@ -30,6 +30,7 @@ EXPORTS = [
     "nnc_timer_start", "nnc_timer_stop", "nnc_last_profile", "nnc_stats_f32", "nnc_prune_f32", "nnc_mask_apply_f32",
     "nnc_compact_nonzero_f32", "nnc_minmax_f32", "nnc_hist_edges_f32", "nnc_weight_cdf_f32", "nnc_gather_f32",
     "nnc_kmeans1d_f32", "nnc_assign_f32", "nnc_unpack_gather_f32", "nnc_grad_segsum_f32", "nnc_ctx_set_comm",
+    "nnc_ctx_set_kernel_timing", "nnc_last_kernel_times", "nnc_ctx_total_launches",
 ]
 
 
@@ -96,6 +97,9 @@ def lib():
         L.nnc_assign_f32.argtypes = [vp, vp, i64, vp, i32, f32, vp, vp, vp, vp, i32, vp, P(f64)]
         L.nnc_unpack_gather_f32.argtypes = [vp, vp, i64, i32, vp, i32, vp]
         L.nnc_grad_segsum_f32.argtypes = [vp, vp, vp, i64, i32, i32, vp]
+        L.nnc_ctx_set_kernel_timing.argtypes = [vp, i32]
+        L.nnc_last_kernel_times.argtypes = [vp, P(C.c_char_p)]
+        L.nnc_ctx_total_launches.argtypes = [vp, P(i64)]
         L.nnc_ctx_set_comm.argtypes = [vp, i32, i32, ALLREDUCE_FN, vp]
         for name in EXPORTS:
             fn = getattr(L, name)
@@ -160,6 +164,25 @@ class Context:
         for i, kname in enumerate(keys[: n.value]):
             out[kname] = out.get(kname, 0.0) + buf[i]
         return out, launches.value
+
+    def set_kernel_timing(self, on: bool):
+        check(lib().nnc_ctx_set_kernel_timing(self._h, int(bool(on))))
+
+    def total_launches(self) -> int:
+        v = C.c_int64()
+        check(lib().nnc_ctx_total_launches(self._h, C.byref(v)))
+        return v.value
+
+    def last_kernel_times(self):
+        """{kernel name: (launches, total ms)} accumulated since set_kernel_timing(True)."""
+        s = C.c_char_p()
+        check(lib().nnc_last_kernel_times(self._h, C.byref(s)))
+        out = {}
+        for item in (s.value.decode() if s.value else "").split(";"):
+            if item:
+                name, cnt, ms = item.rsplit(":", 2)
+                out[name] = (int(cnt), float(ms))
+        return out
 
     def set_comm(self, rank: int, world: int, allreduce):
         """allreduce(dev_ptr: int, count: int, op: int, stream: int) -> None sums/mins/maxes int64 in place."""

@@ -22,7 +22,7 @@ from .. import _native as N
 
 __all__ = [
     "prune_weigth", "apply_mask", "get_weight_distribution", "get_quantized_weight", "KMeansResult",
-    "nonzero_weights", "weight_stats", "assign_codes", "dequantize", "cluster_gradient_sum", "index_bits",
+    "compress_weight", "nonzero_weights", "weight_stats", "assign_codes", "dequantize", "cluster_gradient_sum", "index_bits",
 ]
 
 
@@ -320,6 +320,48 @@ def get_quantized_weight(layer_weight, bits=4, mode="linear", cdfs=None):
             raise ValueError(e.msg) from None
         raise
     return ris.reshape(buf.shape), res
+
+
+def _init_space(buf: _Buf, ctx: N.Context, bits: int, mode: str, cdfs):
+    """Initial centroids for the deterministic / seeded modes (utility.py:206-226)."""
+    if mode == "linear":
+        mn, mx, cnt = C.c_float(), C.c_float(), C.c_int64()
+        N.check(N.lib().nnc_minmax_f32(ctx.handle, buf.ptr, buf.n, 0, C.byref(mn), C.byref(mx), C.byref(cnt)))
+        if cnt.value != buf.n:
+            raise ValueError("Input X contains NaN.")
+        return np.linspace(np.float32(mn.value), np.float32(mx.value), num=2 ** bits)
+    if mode == "density" and cdfs is not None:
+        return _init_density(bits, cdfs)
+    if mode == "forgy":
+        idx = np.random.randint(0, buf.n, size=2 ** bits).astype(np.int64)
+        space = np.empty(idx.size, dtype=np.float32)
+        N.check(N.lib().nnc_gather_f32(ctx.handle, buf.ptr, buf.n, N.ptr(idx), idx.size, N.ptr(space)))
+        return space
+    raise Exception(" error mode not found")
+
+
+def compress_weight(original_weigth, threshold=0.25, std_smooth=True, bits=4, mode="linear", with_cdf=True):
+    """The whole compression of one tensor as Trainer._prune_parameters + Trainer.quantize apply it
+    (trainer.py:177-193, :42-72): std-threshold prune IN PLACE, then k-means weight sharing of the pruned tensor,
+    keeping only the compressed representation -- the boolean mask, the codebook, the packed n-bit cluster
+    indices and their histogram -- instead of the dense de-quantised tensor and int32 labels.
+
+    Returns (mask, KMeansResult); `KMeansResult.labels_` is None (decode with `dequantize`)."""
+    mask = prune_weigth(original_weigth, threshold, std_smooth)
+    buf = _Buf(original_weigth, "original_weigth")
+    if buf.n < (2 ** bits) + 1:
+        print("not enough bits:", buf.n, " vs ", 2 ** bits)
+        return mask, None
+    ctx = _ctx_for(buf)
+    prune_prof, _ = ctx.last_profile()
+    cdfs = None
+    if mode == "density" and with_cdf:
+        cdfs = get_weight_distribution(original_weigth, skip_zeros=True)
+    space = _init_space(buf, ctx, bits, mode, cdfs)
+    _, res = _kmeans_device(buf, ctx, np.asarray(space, dtype=np.float32), want_labels=False, want_ris=False, want_packed=True)
+    for name, ms in prune_prof.items():
+        res.profile["prune." + name] = ms
+    return mask, res
 
 
 def assign_codes(weights, kmeans: KMeansResult, want_labels=True, want_packed=True):

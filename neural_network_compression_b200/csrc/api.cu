@@ -130,6 +130,7 @@ void stage_finish(nnc_ctx *ctx, const Staged &s) {
 }
 
 // ---- phases ------------------------------------------------------------------------------------------
+static void kfold(nnc_ctx *ctx);
 static cudaEvent_t prof_event(nnc_ctx *ctx, int i) {
     while ((int)ctx->prof.ev.size() <= i) {
         cudaEvent_t e;
@@ -164,6 +165,40 @@ void prof_end(nnc_ctx *ctx) {
     }
     ctx->prof.used = 0;
     ctx->last_launches = ctx->launches;
+    if (ctx->ktime) kfold(ctx);
+}
+
+static cudaEvent_t kevent(nnc_ctx *ctx) {
+    if (ctx->kused == ctx->kev.size()) {
+        cudaEvent_t e;
+        NNC_CUDA(cudaEventCreate(&e));
+        ctx->kev.push_back(e);
+    }
+    return ctx->kev[ctx->kused++];
+}
+void klaunch_begin(nnc_ctx *ctx, const char *name) {
+    NNC_CUDA(cudaEventRecord(kevent(ctx), ctx->stream));
+    ctx->knames.push_back(name);
+}
+void klaunch_end(nnc_ctx *ctx) { NNC_CUDA(cudaEventRecord(kevent(ctx), ctx->stream)); }
+static void kfold(nnc_ctx *ctx) {  // after a stream synchronize: fold this call's launches into the running totals
+    for (size_t i = 0; i < ctx->knames.size(); ++i) {
+        float t = 0.f;
+        NNC_CUDA(cudaEventElapsedTime(&t, ctx->kev[2 * i], ctx->kev[2 * i + 1]));
+        std::string nm = ctx->knames[i];
+        size_t j = 0;
+        for (; j < ctx->kacc_names.size(); ++j)
+            if (ctx->kacc_names[j] == nm) break;
+        if (j == ctx->kacc_names.size()) {
+            ctx->kacc_names.push_back(nm);
+            ctx->kacc_ms.push_back(0.0);
+            ctx->kacc_cnt.push_back(0);
+        }
+        ctx->kacc_ms[j] += t;
+        ctx->kacc_cnt[j] += 1;
+    }
+    ctx->knames.clear();
+    ctx->kused = 0;
 }
 
 void read_scalars(nnc_ctx *ctx) {
@@ -203,11 +238,14 @@ struct Call {  // RAII: device selection, arena reset, launch accounting, profil
         NNC_CUDA(cudaSetDevice(c->device));
         arena_reset(c);
         c->launches = 0;
+        c->knames.clear();
+        c->kused = 0;
         prof_begin(c);
     }
     void finish() {
         prof_end(ctx);
         ctx->last_launches = ctx->launches;
+        ctx->total_launches += ctx->launches;
     }
 };
 
@@ -274,6 +312,7 @@ void nnc_ctx_destroy(nnc_ctx *ctx) {
     if (ctx->d_scal) cudaFree(ctx->d_scal);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -322,6 +361,34 @@ int nnc_last_profile(nnc_ctx *ctx, float *ms_out, int cap, int *n_out, const cha
     if (n_out) *n_out = n;
     if (names_out) *names_out = ctx->prof_names.c_str();
     if (launches_out) *launches_out = ctx->last_launches;
+    NNC_CATCH
+}
+
+int nnc_ctx_set_kernel_timing(nnc_ctx *ctx, int on) {
+    NNC_TRY
+    if (!ctx) NNC_FAIL(NNC_ERR_BAD_ARG, "null context");
+    ctx->ktime = on != 0;
+    ctx->kacc_names.clear();
+    ctx->kacc_ms.clear();
+    ctx->kacc_cnt.clear();
+    NNC_CATCH
+}
+int nnc_ctx_total_launches(nnc_ctx *ctx, int64_t *out) {
+    NNC_TRY
+    if (!ctx || !out) NNC_FAIL(NNC_ERR_BAD_ARG, "null argument");
+    *out = ctx->total_launches;
+    NNC_CATCH
+}
+int nnc_last_kernel_times(nnc_ctx *ctx, const char **out) {
+    NNC_TRY
+    if (!ctx || !out) NNC_FAIL(NNC_ERR_BAD_ARG, "null argument");
+    ctx->ktimes.clear();
+    char line[256];
+    for (size_t j = 0; j < ctx->kacc_names.size(); ++j) {
+        snprintf(line, sizeof(line), "%s%s:%lld:%.6f", j ? ";" : "", ctx->kacc_names[j].c_str(), ctx->kacc_cnt[j], ctx->kacc_ms[j]);
+        ctx->ktimes += line;
+    }
+    *out = ctx->ktimes.c_str();
     NNC_CATCH
 }
 

@@ -39,14 +39,13 @@ __global__ void __launch_bounds__(EM_THREADS) emit_kernel(const float *__restric
                                                           uint8_t *packed, int bits, int want_hist, int want_inertia) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RegionTable &T = ed->tab;
-    const int G = T.G, k = T.k;
-    const int R = 2 * G + 1;
+    const int R = T.R, k = T.k;
     float *s_start = reinterpret_cast<float *>(smem_raw);                 // R + 1 region starts
-    int *s_safe_id = reinterpret_cast<int *>(s_start + (R + 1));          // G + 1 labels of SAFE regions
-    float *s_val = reinterpret_cast<float *>(s_safe_id + (G + 1));        // k codebook values
+    int *s_rid = reinterpret_cast<int *>(s_start + (R + 1));              // R: cluster id of a SAFE region, -1 for a ZONE
+    float *s_val = reinterpret_cast<float *>(s_rid + R);                  // k codebook values
     uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_val + k);           // k counters
     for (int i = threadIdx.x; i <= R; i += EM_THREADS) s_start[i] = T.rstart[i];
-    for (int i = threadIdx.x; i <= G; i += EM_THREADS) s_safe_id[i] = T.down[safe_distinct_index(T.gp_hi, i)];
+    for (int i = threadIdx.x; i < R; i += EM_THREADS) s_rid[i] = T.rJ1[i] == T.rJ2[i] ? T.down[T.rJ1[i]] : -1;
     for (int i = threadIdx.x; i < k; i += EM_THREADS) {
         s_val[i] = ed->values[i];
         s_hist[i] = 0;
@@ -89,14 +88,11 @@ __global__ void __launch_bounds__(EM_THREADS) emit_kernel(const float *__restric
                     else
                         hi = mid;
                 }
-                int di;
-                if (lo & 1) {
-                    const int g = lo >> 1;
-                    di = zone_argmin(xc, T.dv, T.dcn, T.down, T.gp_lo[g], T.gp_hi[g] + 1);
-                    id[j] = T.down[di];
-                } else {
-                    id[j] = s_safe_id[lo >> 1];
-                }
+                const int rid = s_rid[lo];
+                if (rid < 0)
+                    id[j] = T.down[zone_argmin(xc, T.dv, T.dcn, T.down, T.rJ2[lo], T.rJ1[lo])];
+                else
+                    id[j] = rid;
                 if (want_inertia) {
                     // distance to the centroid in centred space, as sklearn's _inertia_dense computes it
                     float t = fsub(xc, ed->cfin[id[j]]);
@@ -214,7 +210,7 @@ void emit_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *h_centr
                      (!d_packed || (reinterpret_cast<uintptr_t>(d_packed) & 15u) == 0);
     const int64_t n_chunks = (n + EM_PER - 1) / EM_PER;
     const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, (n_chunks + EM_THREADS - 1) / EM_THREADS);
-    const size_t smem = sizeof(float) * (2 * (size_t)k + 2) + sizeof(int) * ((size_t)k + 1) + sizeof(float) * k +
+    const size_t smem = sizeof(float) * (2 * (size_t)k + 2) + sizeof(int) * (2 * (size_t)k + 1) + sizeof(float) * k +
                         sizeof(uint32_t) * k;
     const int want_hist = h_hist ? 1 : 0, want_inertia = h_inertia ? 1 : 0;
     if (vec)

@@ -80,6 +80,16 @@ struct nnc_ctx {
     size_t high_water = 0;      // largest call so far: the main block is regrown to this at the next reset
     std::vector<void *> overflow;  // extra blocks taken when the main block was too small
     bool user_stream = false;
+    // optional per-kernel CUDA-event timing (benchmarks): one event pair per launch, folded by kernel name
+    bool ktime = false;
+    std::vector<cudaEvent_t> kev;
+    std::vector<const char *> knames;
+    size_t kused = 0;
+    std::vector<std::string> kacc_names;  // running totals since nnc_ctx_set_kernel_timing
+    std::vector<double> kacc_ms;
+    std::vector<long long> kacc_cnt;
+    std::string ktimes;  // "name:launches:total_ms;..."
+    int64_t total_launches = 0;  // kernels launched over the context's lifetime
     nnc::DevScalars *d_scal = nullptr;
     nnc::DevScalars *h_scal = nullptr;  // pinned mirror
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -123,10 +133,15 @@ void prof_begin(nnc_ctx *ctx);
 void prof_mark(nnc_ctx *ctx, const char *name);  // ends the phase `name` that started at the previous mark
 void prof_end(nnc_ctx *ctx);
 
+void klaunch_begin(nnc_ctx *ctx, const char *name);
+void klaunch_end(nnc_ctx *ctx);
+
 #define NNC_LAUNCH(ctx, kernel, grid, block, smem, ...)                 \
     do {                                                                \
+        if ((ctx)->ktime) nnc::klaunch_begin((ctx), #kernel);           \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
         (ctx)->launches++;                                              \
+        if ((ctx)->ktime) nnc::klaunch_end((ctx));                      \
         NNC_CUDA(cudaGetLastError());                                   \
     } while (0)
 

@@ -13,12 +13,15 @@
 //   the n0 pruned zeros are not stored: they are one value with multiplicity n0.
 //
 // One iteration = four small kernels on the context stream, no host round trip:
-//   table   (1 CTA)   sort the k centroids, build the region table (table.cuh)
+//   table   (1 CTA)   sort the k centroids, build the region table (table.cuh): <= 2m-1 regions, each either
+//                     SAFE (one label) or a ZONE (float32 rule over a short candidate range)
 //   search  (grid)    one warp per region boundary: position in ks[] and prefix sum of q up to it
 //   zone    (grid)    evaluate the float32 label rule for the few samples inside the zones
 //   update  (1 CTA)   per-cluster counts and sums (SAFE regions via prefix differences + zone partials +
 //                     the zero run), empty-cluster relocation, averages, centre shift, convergence test
 // Per-cluster sums are exact integers, so the result does not depend on reduction order or sharding.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -28,6 +31,7 @@
 namespace nnc {
 
 constexpr int LL_TS = 1024;  // sorted-array tile
+constexpr int LL_LOG = 304;  // per-iteration diagnostics kept for the first LL_LOG iterations
 
 __host__ __device__ __forceinline__ long long llmin2(long long a, long long b) { return a < b ? a : b; }
 __host__ __device__ __forceinline__ long long llmax2(long long a, long long b) { return a > b ? a : b; }
@@ -55,6 +59,9 @@ struct LloydDevice : LloydHeader {
     long long Wprev[TB_KMAX], Sprev[TB_KMAX];
     // control
     int iter, done, strict, n_reloc, n_iter, pad2;
+    // per-iteration log (diagnostics): zone elements, zone groups, distinct centroids, empty clusters
+    long long logZ[LL_LOG];
+    int logG[LL_LOG], logM[LL_LOG], logE[LL_LOG];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -162,11 +169,11 @@ __global__ void __launch_bounds__(TB_THREADS) ll_table_kernel(LloydDevice *st) {
         st->zmax[tid] = -1;
     }
     if (tid == 0) {
-        const int G = st->tab.G;
+        const int R = st->tab.R;
         st->rpos[0] = 0;
         st->rsum[0] = 0;
-        st->rpos[2 * G + 1] = st->n_nz;
-        st->rsum[2 * G + 1] = st->total_q;
+        st->rpos[R] = st->n_nz;
+        st->rsum[R] = st->total_q;
     }
 }
 
@@ -223,8 +230,7 @@ __global__ void __launch_bounds__(256) ll_search_kernel(LloydDevice *st, const f
                                                         const float *__restrict__ samp,
                                                         const long long *__restrict__ ptile) {
     if (st->done) return;
-    const int G = st->tab.G;
-    const int nb = 2 * G;  // boundaries 1 .. 2G
+    const int nb = st->tab.R - 1;  // boundaries 1 .. R-1
     const int wpb = blockDim.x >> 5;
     for (int r = 1 + blockIdx.x * wpb + warp_id(); r <= nb; r += gridDim.x * wpb) {
         long long pos, sum;
@@ -238,28 +244,29 @@ __global__ void __launch_bounds__(256) ll_search_kernel(LloydDevice *st, const f
 
 __global__ void __launch_bounds__(256) ll_zone_kernel(LloydDevice *st, const float *__restrict__ ks) {
     if (st->done) return;
-    __shared__ long long zpre[TB_KMAX + 1];
+    __shared__ long long zpre[2 * TB_KMAX + 2];
     __shared__ long long s_warp[32];
     __shared__ unsigned int sW[TB_KMAX];
     __shared__ long long sS[TB_KMAX];
     __shared__ long long sMin[TB_KMAX];
     __shared__ long long sMax[TB_KMAX];
     const RegionTable &T = st->tab;
-    const int G = T.G, m = T.m;
-    if (G == 0) return;
-    // prefix of zone sizes (G <= 1023): chunked scan by the 256 threads
+    const int R = T.R, m = T.m;
+    if (R <= 1) return;
+    // prefix of zone sizes over the regions (SAFE regions count 0): chunked scan by the 256 threads
     {
-        const int per = (G + blockDim.x - 1) / blockDim.x;
-        const int lo = min(G, (int)threadIdx.x * per), hi = min(G, lo + per);
+        auto zsize = [&](int r) -> long long { return T.rJ1[r] > T.rJ2[r] ? st->rpos[r + 1] - st->rpos[r] : 0ll; };
+        const int per = (R + blockDim.x - 1) / blockDim.x;
+        const int lo = min(R, (int)threadIdx.x * per), hi = min(R, lo + per);
         long long sum = 0;
-        for (int g = lo; g < hi; ++g) sum += st->rpos[2 * g + 2] - st->rpos[2 * g + 1];
+        for (int r = lo; r < hi; ++r) sum += zsize(r);
         long long incl = block_scan_incl<long long>(sum, [](long long a, long long b) { return a + b; }, s_warp);
         long long run = incl - sum;
-        for (int g = lo; g < hi; ++g) {
-            zpre[g] = run;
-            run += st->rpos[2 * g + 2] - st->rpos[2 * g + 1];
+        for (int r = lo; r < hi; ++r) {
+            zpre[r] = run;
+            run += zsize(r);
         }
-        if (threadIdx.x == blockDim.x - 1) zpre[G] = incl;
+        if (threadIdx.x == blockDim.x - 1) zpre[R] = incl;
     }
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
         sW[i] = 0;
@@ -268,7 +275,12 @@ __global__ void __launch_bounds__(256) ll_zone_kernel(LloydDevice *st, const flo
         sMax[i] = -1;
     }
     __syncthreads();
-    const long long Z = zpre[G];
+    const long long Z = zpre[R];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && st->iter < LL_LOG) {
+        st->logZ[st->iter] = Z;
+        st->logG[st->iter] = R;
+        st->logM[st->iter] = m;
+    }
     if (Z == 0) return;
     long long chunk = (Z + gridDim.x - 1) / gridDim.x;
     chunk = (chunk + blockDim.x - 1) / blockDim.x * blockDim.x;
@@ -282,7 +294,7 @@ __global__ void __launch_bounds__(256) ll_zone_kernel(LloydDevice *st, const flo
         int di = -1;
         long long q = 0, p = 0;
         if (valid) {
-            int lo = 0, hi = G;  // largest g with zpre[g] <= e
+            int lo = 0, hi = R;  // largest r with zpre[r] <= e: the non-empty zone that holds e
             while (hi - lo > 1) {
                 int mid = (lo + hi) >> 1;
                 if (zpre[mid] <= e)
@@ -290,10 +302,10 @@ __global__ void __launch_bounds__(256) ll_zone_kernel(LloydDevice *st, const flo
                 else
                     hi = mid;
             }
-            const int g = lo;
-            p = st->rpos[2 * g + 1] + (e - zpre[g]);
+            const int r = lo;
+            p = st->rpos[r] + (e - zpre[r]);
             float xc = fsub(ks[p], mean);
-            di = zone_argmin(xc, T.dv, T.dcn, T.down, T.gp_lo[g], T.gp_hi[g] + 1);
+            di = zone_argmin(xc, T.dv, T.dcn, T.down, T.rJ2[r], T.rJ1[r]);
             q = fixed_q(xc, scale);
         }
         unsigned active = __ballot_sync(0xffffffffu, valid);
@@ -370,7 +382,7 @@ __device__ __forceinline__ FarKey far_key(float xc, float c) {
 // label (distinct index) of the sorted survivor at position p, from the region table + searched positions
 __device__ int label_at(const LloydDevice *st, const float *ks, long long p) {
     const RegionTable &T = st->tab;
-    const int R = 2 * T.G + 1;
+    const int R = T.R;
     int lo = 0, hi = R;  // largest r with rpos[r] <= p
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
@@ -379,9 +391,8 @@ __device__ int label_at(const LloydDevice *st, const float *ks, long long p) {
         else
             hi = mid;
     }
-    if ((lo & 1) == 0) return safe_distinct_index(T.gp_hi, lo >> 1);
-    const int g = lo >> 1;
-    return zone_argmin(fsub(ks[p], st->mean), T.dv, T.dcn, T.down, T.gp_lo[g], T.gp_hi[g] + 1);
+    if (T.rJ1[lo] == T.rJ2[lo]) return T.rJ1[lo];
+    return zone_argmin(fsub(ks[p], st->mean), T.dv, T.dcn, T.down, T.rJ2[lo], T.rJ1[lo]);
 }
 
 struct UpdateSmem {
@@ -405,7 +416,7 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
     UpdateSmem &U = *reinterpret_cast<UpdateSmem *>(smem_raw);
     if (st->done) return;
     const RegionTable &T = st->tab;
-    const int tid = threadIdx.x, k = st->k, m = T.m, G = T.G;
+    const int tid = threadIdx.x, k = st->k, m = T.m, R = T.R;
     const float mean = st->mean;
     const double scale = st->scale;
     // ---- 1. per distinct index: zone partials + SAFE regions
@@ -420,12 +431,13 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
         U.S[tid] = 0;
     }
     __syncthreads();
-    if (tid <= G) {  // SAFE region s = tid is region 2s: positions [rpos[2s], rpos[2s+1])
-        const int di = safe_distinct_index(T.gp_hi, tid);
-        long long lo = st->rpos[2 * tid], hi = st->rpos[2 * tid + 1];
+    for (int r = tid; r < R; r += TB_THREADS) {  // SAFE regions: positions [rpos[r], rpos[r+1]) carry one label
+        if (T.rJ1[r] != T.rJ2[r]) continue;
+        const int di = T.rJ1[r];
+        long long lo = st->rpos[r], hi = st->rpos[r + 1];
         if (hi > lo) {
-            U.Wd[di] += hi - lo;  // one SAFE region per distinct index: no conflicts
-            U.Sd[di] += st->rsum[2 * tid + 1] - st->rsum[2 * tid];
+            U.Wd[di] += hi - lo;  // (J, J) occurs in at most one region: no conflicts
+            U.Sd[di] += st->rsum[r + 1] - st->rsum[r];
             U.first[di] = llmin2(U.first[di], lo);
             U.last[di] = llmax2(U.last[di], hi - 1);
         }
@@ -502,6 +514,7 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
         __syncthreads();
     }
     const int n_empty = U.n_empty;
+    if (tid == 0 && st->iter < LL_LOG) st->logE[st->iter] = n_empty;
     if (n_empty > 0) {
         // Streams of candidates: for every distinct index its members walked from the left end and from the
         // right end (|x' - c| is V-shaped along a cluster's sorted members), plus the zero run.  The farthest
@@ -770,6 +783,18 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
     NNC_CUDA(cudaMemcpyAsync(&tol_h, &st->tol, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     NNC_CUDA(cudaStreamSynchronize(ctx->stream));
     prof_mark(ctx, "lloyd_iters");
+    if (getenv("NNC_LLOYD_LOG")) {
+        const int cnt = std::min(ctl.n_iter, LL_LOG);
+        std::vector<long long> z(cnt);
+        std::vector<int> g(cnt), mm(cnt), ee(cnt);
+        NNC_CUDA(cudaMemcpy(z.data(), st->logZ, sizeof(long long) * cnt, cudaMemcpyDeviceToHost));
+        NNC_CUDA(cudaMemcpy(g.data(), st->logG, sizeof(int) * cnt, cudaMemcpyDeviceToHost));
+        NNC_CUDA(cudaMemcpy(mm.data(), st->logM, sizeof(int) * cnt, cudaMemcpyDeviceToHost));
+        NNC_CUDA(cudaMemcpy(ee.data(), st->logE, sizeof(int) * cnt, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < cnt; ++i)
+            fprintf(stderr, "[nnc lloyd] iter %d zone_elems %lld (%.3f%% of survivors) groups %d distinct %d empty %d\n", i, z[i],
+                    h.n_nz ? 100.0 * (double)z[i] / (double)h.n_nz : 0.0, g[i], mm[i], ee[i]);
+    }
     LloydResult r;
     r.n_iter = ctl.n_iter;
     r.strict = ctl.strict;

@@ -2,17 +2,22 @@
 // on the real line, built from the current centroids.
 //
 // sklearn labels a centred sample x' with the FIRST j minimising d_j = fl(fl(c_j c_j) + fl(fl(-2 x') c_j))
-// (sklearn/cluster/_k_means_lloyd.pyx:196-213).  In exact arithmetic that is the nearest centroid; in
-// float32 the comparison of two neighbouring centroids a < b can go either way only in a narrow window
-// around their midpoint.  With u = 2^-24 and M >= max(|x'|, |c|) every computed d_j is within
-// 2u(1+4u)(c_j^2 + 2|x' c_j|) + eta <= E1 := 6u(1+4u)M^2 + eta of its exact value, and the exact margin
-// between neighbours is 2(b-a)|mid - x'|.  So outside the "zone" |x' - mid| <= E2/(2(b-a)), E2 = 2 E1, the
-// float32 comparison agrees with exact arithmetic, and (margins to farther centroids being larger) the label is
-// the exact nearest distinct centroid, lowest id among exact duplicates.  Overlapping zones are merged into
-// groups.  The line is thereby cut into alternating regions
-//     SAFE_0 | ZONE_0 | SAFE_1 | ZONE_1 | ... | ZONE_{G-1} | SAFE_G
-// SAFE_s has one label; inside ZONE_g the label is found by evaluating the float32 rule over the group's
-// candidates (distinct centroids gp_lo[g] .. gp_hi[g]+1).  Both are bit-exact restatements of the rule.
+// (sklearn/cluster/_k_means_lloyd.pyx:196-213).  In exact arithmetic that is the nearest centroid; in float32
+// the comparison of two centroids can go either way when x' is close to their midpoint.  With u = 2^-24,
+// u' = u(1+4u), every computed d_j is within err_j(x') = 2u'(c_j^2 + 2|x' c_j|) + eta of its exact value.
+//
+// For every pair of ADJACENT distinct centroids a < b (mid = (a+b)/2) a half-width delta is computed such that
+// 2(b-a)|x' - mid| > err_a(x') + err_b(x') for all data x' with |x' - mid| > delta, i.e. the float32 comparison
+// of a and b is decided exactly as in real arithmetic outside [A, B] = [mid - delta, mid + delta].
+// Lemma: for x' < A the left centroid a beats EVERY centroid right of it in float32, and
+// for x' > B the right centroid b beats every centroid left of it.  Hence centroid j can only be the float32
+// argmin for  lo_j <= x' <= hi_j,  lo_j = max_{pairs left of j} A,  hi_j = min_{pairs right of j} B.  Both
+// sequences are non-decreasing in j, so the candidates at x' are the contiguous range [J2(x'), J1(x')],
+// J1 = #{j >= 1 : lo_j <= x'},  J2 = #{j <= m-2 : hi_j < x'}.  Sorting the 2(m-1) breakpoints cuts the line into
+// 2m-1 regions with constant (J2, J1): J1 == J2 is a SAFE region (one label, no arithmetic); otherwise the
+// float32 rule is evaluated over the candidates J2..J1 (a ZONE).  Near-duplicate centroids (delta huge) simply
+// never eliminate each other and stay joint candidates inside their common cell; they do not widen anyone
+// else's zone.  Both cases are bit-exact restatements of the rule.
 #pragma once
 #include <float.h>
 
@@ -26,17 +31,15 @@ constexpr int TB_THREADS = 1024;
 struct RegionTable {
     int k;   // clusters
     int m;   // distinct centroid values
-    int G;   // zone groups; regions = 2G + 1
+    int R;   // regions = 2m - 1 (region r covers x' in [rstart[r], rstart[r+1]))
     int pad_;
     float dv[TB_KMAX];      // distinct centroid values, ascending
     float dcn[TB_KMAX];     // fl(dv * dv)
     int down[TB_KMAX];      // owner id = lowest cluster id with that value
-    int gp_lo[TB_KMAX];     // group g spans adjacent pairs gp_lo..gp_hi, i.e. distinct indices gp_lo..gp_hi+1
-    int gp_hi[TB_KMAX];
-    float rstart[2 * TB_KMAX + 2];  // region r covers x' in [rstart[r], rstart[r+1]);  r even: SAFE, odd: ZONE
+    float rstart[2 * TB_KMAX + 2];  // rstart[0] = -inf, rstart[R] = +inf
+    short rJ2[2 * TB_KMAX + 2];     // candidates of region r: distinct indices rJ2[r] .. rJ1[r]
+    short rJ1[2 * TB_KMAX + 2];
 };
-
-__device__ __forceinline__ int safe_distinct_index(const int *gp_hi, int s) { return s == 0 ? 0 : gp_hi[s - 1] + 1; }
 
 __device__ __forceinline__ float f32_nextup(float f) {
     if (f != f || f == INFINITY) return f;
@@ -95,6 +98,8 @@ struct TableScratch {
     int warp_i[32];
     float warp_f[32];
     int flag[TB_KMAX];
+    float tlo[TB_KMAX];
+    float thi[TB_KMAX];
 };
 
 // Build the table for centroids c[0..k) (centred space).  Must be called by all TB_THREADS threads of a CTA.
@@ -159,56 +164,87 @@ static __device__ void build_region_table(const float *c, int k, float xabs_max,
     __syncthreads();
     const int m = S.flag[0];
     __syncthreads();
-    // ---- 3. zones of adjacent pairs
+    // ---- 3. decision intervals [A, B] of adjacent pairs
+    // Two valid half-widths, the smaller one is used:
+    //   global:  |x'|, |c| <= M, so err_a + err_b <= 12u'M^2 =: E2 and delta = E2 / (2(b-a));
+    //   pair:    err_a + err_b <= alpha + beta|x'|, alpha = 2u'(a^2+b^2), beta = 4u'(|a|+|b|); with
+    //            |x'| <= |mid| + t the pair is decided once 2(b-a)t > alpha + beta(|mid| + t), i.e.
+    //            t > (alpha + beta|mid|) / (2(b-a) - beta).
     const double u = 5.9604644775390625e-08;  // 2^-24
+    const double up = u * (1.0 + 4.0 * u);
     const double Md = (double)M;
-    const double E2 = 12.0 * u * (1.0 + 4.0 * u) * Md * Md + 1e-42;
-    double L = DBL_MAX, R = -DBL_MAX;
+    const double eta = 1e-42;  // absorbs float32 underflow in the products
+    const double E2 = 12.0 * up * Md * Md + 2.0 * eta;
+    double A = -DBL_MAX, B = DBL_MAX;
     const int npairs = m - 1;
     if (tid < npairs) {
         double a = S.a[tid], b = S.a[tid + 1];
         double mid = 0.5 * (a + b);
-        double delta = E2 / (2.0 * (b - a));
-        L = mid - delta;
-        R = mid + delta;
+        double g2 = 2.0 * (b - a);
+        double delta = E2 / g2 * (1.0 + 1e-9);
+        double alpha = 2.0 * up * (a * a + b * b) + 2.0 * eta, beta = 4.0 * up * (fabs(a) + fabs(b));
+        if (g2 > 2.0 * beta) {  // keep the denominator well conditioned
+            double dp = (alpha + beta * fabs(mid)) / (g2 - beta) * (1.0 + 1e-9);
+            if (dp < delta) delta = dp;
+        }
+        A = mid - delta;
+        B = mid + delta;
     }
     __syncthreads();
-    // prefix max of R, suffix min of L
-    double pmaxR = block_scan_incl<double>(R, [](double x, double y) { return x > y ? x : y; }, S.warp_d);
-    if (tid < npairs) S.b[tid] = L;
+    // lo_{j} = max_{i < j} A_i (j = 1..m-1), hi_j = min_{i >= j} B_i (j = 0..m-2)
+    double pmaxA = block_scan_incl<double>(A, [](double x, double y) { return x > y ? x : y; }, S.warp_d);
+    if (tid < npairs) S.b[tid] = B;
     __syncthreads();
-    double Lrev = tid < npairs ? S.b[npairs - 1 - tid] : DBL_MAX;
-    double sminL_rev = block_scan_incl<double>(Lrev, [](double x, double y) { return x < y ? x : y; }, S.warp_d);
-    if (tid < npairs) S.a[npairs - 1 - tid] = sminL_rev;  // S.a[i] = min_{j>=i} L_j
-    __syncthreads();
-    // ---- 4. groups
-    int brk = 0;  // a new group starts at pair tid+1
-    if (tid + 1 < npairs) brk = pmaxR < S.a[tid + 1];
-    S.flag[tid] = brk;
-    int brk_incl = block_scan_incl<int>(brk, [](int x, int y) { return x + y; }, S.warp_i);
+    double Brev = tid < npairs ? S.b[npairs - 1 - tid] : DBL_MAX;
+    double sminB_rev = block_scan_incl<double>(Brev, [](double x, double y) { return x < y ? x : y; }, S.warp_d);
+    // breakpoints as float thresholds T with the predicate "x' >= T is right of it":
+    //   T_lo(j) = largest float <= lo_j              (j - 1 = tid)   -> S.tlo[tid]
+    //   T_hi(j) = smallest float >  ceil32(hi_j)     (j = tid)       -> S.thi[tid]
     if (tid < npairs) {
-        int gid = brk_incl - brk;  // breaks strictly before this pair
-        bool is_start = tid == 0 || S.flag[tid - 1];
-        bool is_end = tid == npairs - 1 || brk;
-        if (is_start) {
-            T->gp_lo[gid] = tid;
-            T->rstart[2 * gid + 1] = __double2float_ru(S.a[tid]);  // smallest float >= group's min L
+        S.tlo[tid] = __double2float_rd(pmaxA);
+        S.thi[npairs - 1 - tid] = f32_nextup(__double2float_ru(sminB_rev));
+    }
+    __syncthreads();
+    // ---- 4. merge the two sorted breakpoint lists (lo first on ties); region r starts at merged breakpoint r-1
+    if (tid < npairs) {
+        {   // lo breakpoint of distinct index j = tid + 1
+            const float t = S.tlo[tid];
+            int lo = 0, hi = npairs;  // #{i : thi[i] < t}
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (S.thi[mid] < t)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            const int p = tid + lo;  // merged position
+            T->rstart[p + 1] = t;
+            T->rJ1[p + 1] = (short)(tid + 1);
+            T->rJ2[p + 1] = (short)(p + 1 - (tid + 1));
         }
-        if (is_end) {
-            T->gp_hi[gid] = tid;
-            T->rstart[2 * gid + 2] = f32_nextup(__double2float_rd(pmaxR));  // smallest float > group's max R
-        }
-        if (tid == npairs - 1) {
-            T->G = gid + 1;
-            T->rstart[2 * (gid + 1) + 1] = INFINITY;
+        {   // hi breakpoint of distinct index j = tid
+            const float t = S.thi[tid];
+            int lo = 0, hi = npairs;  // #{j : tlo[j] <= t}
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (S.tlo[mid] <= t)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            const int p = tid + lo;
+            T->rstart[p + 1] = t;
+            T->rJ2[p + 1] = (short)(tid + 1);
+            T->rJ1[p + 1] = (short)(p - tid);
         }
     }
     if (tid == 0) {
+        const int R = npairs > 0 ? 2 * npairs + 1 : 1;
+        T->R = R;
         T->rstart[0] = -INFINITY;
-        if (npairs <= 0) {
-            T->G = 0;
-            T->rstart[1] = INFINITY;
-        }
+        T->rJ1[0] = 0;
+        T->rJ2[0] = 0;
+        T->rstart[R] = INFINITY;
     }
     __syncthreads();
 }

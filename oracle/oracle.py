@@ -52,6 +52,7 @@ def lib():
         build()
         L = C.CDLL(_SO)
         vp, i64, f32p = C.c_void_p, C.c_int64, C.POINTER(C.c_float)
+        L.nnco_set_threads.argtypes = [C.c_int]
         L.nnco_pairwise_sum_f32.restype = C.c_float
         L.nnco_pairwise_sum_f32.argtypes = [vp, i64]
         L.nnco_std_f32.argtypes = [vp, i64, f32p, f32p, f32p]
@@ -79,6 +80,11 @@ def lib():
         L.nnco_grad_segsum_fixed.argtypes = [vp, vp, i64, C.c_int, vp]
         _lib = L
     return _lib
+
+
+def set_threads(t: int):
+    """Threads for the DET-mode loops (result independent of the count); REF32 is always sequential."""
+    lib().nnco_set_threads(int(t))
 
 
 def _f32(a):

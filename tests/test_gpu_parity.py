@@ -315,3 +315,45 @@ def test_grad_segsum(U, n, k, bits):
     got = U.cluster_gradient_sum(grad, codes, k, bits)
     mag = np.bincount(labels, weights=np.abs(grad).astype(np.float64), minlength=k)
     assert np.all(np.abs(got - expect) <= 1e-13 * mag + 1e-300)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the label rule under adversarial centroid layouts (region table / zones vs brute force over all k)
+# ---------------------------------------------------------------------------------------------------------
+def _centroid_layouts(rng, lo, hi):
+    span = hi - lo
+    yield np.linspace(lo, hi, 256).astype(np.float32)
+    yield np.sort(rng.uniform(lo, hi, 37)).astype(np.float32)
+    c = rng.uniform(lo, hi, 64).astype(np.float32)
+    c[10:20] = c[10]  # exact duplicates
+    yield c
+    c = rng.uniform(lo, hi, 64).astype(np.float32)
+    for i in range(0, 60, 3):  # neighbours a few ulps apart
+        c[i + 1] = np.nextafter(c[i], np.float32(np.inf))
+        c[i + 2] = np.nextafter(c[i + 1], np.float32(np.inf))
+    yield c
+    c = (lo + span * rng.beta(0.3, 0.3, 500)).astype(np.float32)  # crowded at both ends, unsorted ids
+    yield c
+    c = (rng.randn(1000) * span * 1e-4 + (lo + hi) / 2).astype(np.float32)  # k = 1000 in a sliver
+    yield c
+    yield np.array([lo, hi], dtype=np.float32)
+    yield np.array([(lo + hi) / 2], dtype=np.float32)
+    yield (rng.standard_cauchy(300) * span * 0.01).astype(np.float32).clip(-1e3, 1e3)  # far outside the data too
+
+
+@pytest.mark.parametrize("offset,sigma", [(0.0, 0.02), (0.37, 0.02), (-1000.0, 3.0), (1e-3, 1e-5)])
+def test_label_rule_stress(U, offset, sigma):
+    rng = np.random.RandomState(123)
+    w = (rng.randn(200003) * sigma + offset).astype(np.float32)
+    w[::7] = 0.0
+    w[5:5000:11] = w[4]  # repeated values
+    mean = np.mean(w)
+    lo, hi = float(w.min() - mean), float(w.max() - mean)
+    for centred in _centroid_layouts(rng, lo, hi):
+        k = centred.size
+        expect = O.assign(w, centred, mean)
+        km = U.KMeansResult(centred.reshape(-1, 1) + mean, None, 0, 0.0, centred_centers=centred, mean=mean)
+        labels, packed, hist = U.assign_codes(w, km)
+        assert np.array_equal(labels, expect), (k, int((labels != expect).sum()))
+        assert np.array_equal(hist, np.bincount(expect, minlength=k))
+        assert np.array_equal(O.unpack_codes(packed, w.size, U.index_bits(k)), expect)
