@@ -115,13 +115,16 @@ typedef struct {
     int64_t n_nonzero;    /* survivors that were sorted */
 } nnc_kmeans_info;
 
+#define NNC_KM_INERTIA 1     /* also compute KMeans.inertia_ (costs arithmetic in the emission pass) */
+#define NNC_KM_INIT_LINEAR 2 /* init = np.linspace(w.min(), w.max(), k) in float32 (utility.py:206-209); `init` may be NULL */
+
 /* KMeans(n_clusters=k, init=init, n_init=1, algorithm="lloyd", max_iter, tol).fit(w.reshape(-1,1)).
  * Outputs (any may be NULL): centers[k] = cluster_centers_; centred[k] = centres in sklearn's
  * mean-centred space; labels[n] int32 = labels_; ris[n] = cluster_centers_[labels_];
  * packed = n-bit codes, code i in bits [i*bits,(i+1)*bits) of a little-endian byte stream
  * (ceil(n*bits/8) bytes, bits >= ceil(log2 k)); hist[k] = code histogram. */
 int nnc_kmeans1d_f32(nnc_ctx *ctx, const float *w, int64_t n, const float *init, int k, int max_iter, double tol,
-                     float *centers, float *centred, int32_t *labels, float *ris, uint8_t *packed, int bits,
+                     int flags, float *centers, float *centred, int32_t *labels, float *ris, uint8_t *packed, int bits,
                      int64_t *hist, nnc_kmeans_info *info);
 
 /* E-step / emission only: labels[i] = first argmin_j fl(c_j^2 + fl(-2 x'_i) c_j), x' = fl(w - mean),

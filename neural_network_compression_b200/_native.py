@@ -23,6 +23,8 @@ NNC_ERR_UNSUPPORTED = 5
 NNC_ERR_INTERNAL = 6
 NNC_ERR_COMM = 7
 NNC_KMAX = 1024
+NNC_KM_INERTIA = 1
+NNC_KM_INIT_LINEAR = 2
 
 # every symbol include/nnc.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -93,7 +95,7 @@ def lib():
         L.nnc_hist_edges_f32.argtypes = [vp, vp, i64, vp, i32, i32, vp]
         L.nnc_weight_cdf_f32.argtypes = [vp, vp, i64, i32, vp, vp]
         L.nnc_gather_f32.argtypes = [vp, vp, i64, vp, i32, vp]
-        L.nnc_kmeans1d_f32.argtypes = [vp, vp, i64, vp, i32, i32, f64, vp, vp, vp, vp, vp, i32, vp, P(KMeansInfo)]
+        L.nnc_kmeans1d_f32.argtypes = [vp, vp, i64, vp, i32, i32, f64, i32, vp, vp, vp, vp, vp, i32, vp, P(KMeansInfo)]
         L.nnc_assign_f32.argtypes = [vp, vp, i64, vp, i32, f32, vp, vp, vp, vp, i32, vp, P(f64)]
         L.nnc_unpack_gather_f32.argtypes = [vp, vp, i64, i32, vp, i32, vp]
         L.nnc_grad_segsum_f32.argtypes = [vp, vp, vp, i64, i32, i32, vp]

@@ -239,9 +239,11 @@ def _init_density(bits: int, cdfs):
     return np.array(space, dtype=np.float32)
 
 
-def _kmeans_device(buf: _Buf, ctx: N.Context, space: np.ndarray, want_labels=True, want_ris=True, want_packed=True,
-                   max_iter: int = 300, tol: float = 1e-4):
-    k = int(space.size)
+def _kmeans_device(buf: _Buf, ctx: N.Context, space, want_labels=True, want_ris=True, want_packed=True,
+                   max_iter: int = 300, tol: float = 1e-4, want_inertia=True, linear_k: int = 0):
+    """space: initial centroids, or None with linear_k = k for np.linspace(min, max, k) computed by the library."""
+    flags = (N.NNC_KM_INERTIA if want_inertia else 0) | (N.NNC_KM_INIT_LINEAR if space is None else 0)
+    k = int(linear_k if space is None else space.size)
     bits = index_bits(k)
     centers = np.empty(k, dtype=np.float32)
     centred = np.empty(k, dtype=np.float32)
@@ -250,8 +252,9 @@ def _kmeans_device(buf: _Buf, ctx: N.Context, space: np.ndarray, want_labels=Tru
     ris = buf.empty(buf.n, np.float32) if want_ris else None
     packed = buf.empty((buf.n * bits + 7) // 8, np.uint8) if want_packed else None
     info = N.KMeansInfo()
-    space = np.ascontiguousarray(space, dtype=np.float32)
-    N.check(N.lib().nnc_kmeans1d_f32(ctx.handle, buf.ptr, buf.n, N.ptr(space), k, int(max_iter), float(tol),
+    if space is not None:
+        space = np.ascontiguousarray(space, dtype=np.float32)
+    N.check(N.lib().nnc_kmeans1d_f32(ctx.handle, buf.ptr, buf.n, N.ptr(space), k, int(max_iter), float(tol), flags,
                                      N.ptr(centers), N.ptr(centred), N.ptr(labels), N.ptr(ris), N.ptr(packed), bits,
                                      N.ptr(hist), C.byref(info)))
     prof, launches = ctx.last_profile()
@@ -281,11 +284,7 @@ def get_quantized_weight(layer_weight, bits=4, mode="linear", cdfs=None):
     if mode == "linear":
         buf = _Buf(layer_weight, "layer_weight")
         ctx = _ctx_for(buf)
-        mn, mx, cnt = C.c_float(), C.c_float(), C.c_int64()
-        N.check(N.lib().nnc_minmax_f32(ctx.handle, buf.ptr, buf.n, 0, C.byref(mn), C.byref(mx), C.byref(cnt)))
-        if cnt.value != buf.n:  # NaNs are skipped by the device min/max; sklearn rejects them
-            raise ValueError("Input X contains NaN.")
-        space = np.linspace(np.float32(mn.value), np.float32(mx.value), num=2 ** bits)
+        space = None  # np.linspace(min, max, 2**bits): the library derives it from its own min/max sweep
     elif mode == "density" and cdfs is not None:
         buf = _Buf(layer_weight, "layer_weight")
         ctx = _ctx_for(buf)
@@ -312,7 +311,7 @@ def get_quantized_weight(layer_weight, bits=4, mode="linear", cdfs=None):
         raise Exception(" error mode not found")
 
     try:
-        ris, res = _kmeans_device(buf, ctx, np.asarray(space, dtype=np.float32))
+        ris, res = _kmeans_device(buf, ctx, None if space is None else np.asarray(space, dtype=np.float32), linear_k=2 ** bits)
     except N.NncError as e:
         if e.code == N.NNC_ERR_NONFINITE:
             raise ValueError("Input X contains NaN or infinity.") from None
@@ -357,8 +356,14 @@ def compress_weight(original_weigth, threshold=0.25, std_smooth=True, bits=4, mo
     cdfs = None
     if mode == "density" and with_cdf:
         cdfs = get_weight_distribution(original_weigth, skip_zeros=True)
-    space = _init_space(buf, ctx, bits, mode, cdfs)
-    _, res = _kmeans_device(buf, ctx, np.asarray(space, dtype=np.float32), want_labels=False, want_ris=False, want_packed=True)
+    space = None if mode == "linear" else np.asarray(_init_space(buf, ctx, bits, mode, cdfs), dtype=np.float32)
+    try:
+        _, res = _kmeans_device(buf, ctx, space, want_labels=False, want_ris=False, want_packed=True, want_inertia=False,
+                                linear_k=2 ** bits)
+    except N.NncError as e:
+        if e.code == N.NNC_ERR_NONFINITE:
+            raise ValueError("Input X contains NaN or infinity.") from None
+        raise
     for name, ms in prune_prof.items():
         res.profile["prune." + name] = ms
     return mask, res

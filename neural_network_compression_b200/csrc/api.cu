@@ -575,16 +575,18 @@ int nnc_gather_f32(nnc_ctx *ctx, const float *w, int64_t n, const int64_t *idx, 
 
 // ---- k-means ---------------------------------------------------------------------------------------------
 int nnc_kmeans1d_f32(nnc_ctx *ctx, const float *w, int64_t n, const float *init, int k, int max_iter, double tol,
-                     float *centers, float *centred, int32_t *labels, float *ris, uint8_t *packed, int bits,
+                     int flags, float *centers, float *centred, int32_t *labels, float *ris, uint8_t *packed, int bits,
                      int64_t *hist, nnc_kmeans_info *info) {
     NNC_TRY
     Call call(ctx);
-    if (!w || !init || n <= 0 || k <= 0 || max_iter < 1 || tol < 0)
+    const bool init_linear = (flags & NNC_KM_INIT_LINEAR) != 0;
+    if (!w || (!init && !init_linear) || n <= 0 || k <= 0 || max_iter < 1 || tol < 0)
         NNC_FAIL(NNC_ERR_BAD_ARG, "nnc_kmeans1d_f32: bad argument (n = %lld, k = %d, max_iter = %d)", (long long)n, k, max_iter);
     if (k > NNC_KMAX) NNC_FAIL(NNC_ERR_UNSUPPORTED, "k = %d exceeds NNC_KMAX = %d", k, NNC_KMAX);
     if ((int64_t)k > n) NNC_FAIL(NNC_ERR_NOT_ENOUGH, "n_samples=%lld should be >= n_clusters=%d.", (long long)n, k);
-    for (int j = 0; j < k; ++j)
-        if (!isfinite(init[j])) NNC_FAIL(NNC_ERR_NONFINITE, "initial centroid %d is not finite", j);
+    if (!init_linear)
+        for (int j = 0; j < k; ++j)
+            if (!isfinite(init[j])) NNC_FAIL(NNC_ERR_NONFINITE, "initial centroid %d is not finite", j);
     Staged sw = stage_in(ctx, w, sizeof(float) * (size_t)n);
     const float *d_w = static_cast<const float *>(sw.dev);
     prof_mark(ctx, "h2d");
@@ -603,7 +605,7 @@ int nnc_kmeans1d_f32(nnc_ctx *ctx, const float *w, int64_t n, const float *init,
         int64_t c = compact_ordered_device(ctx, d_w, n, buf_a);
         if (c != n_nz) NNC_FAIL(NNC_ERR_INTERNAL, "compaction kept %lld of %lld survivors", (long long)c, (long long)n_nz);
         prof_mark(ctx, "compact");
-        d_sorted = radix_sort_f32(ctx, buf_a, buf_b, n_nz);
+        d_sorted = radix_sort_f32(ctx, buf_a, buf_b, n_nz, sc.amin_nz_m1 + 1u, sc.amax_bits);
         prof_mark(ctx, "sort");
     }
     // 3. Lloyd iterations on the sorted survivors + the zero run
@@ -614,20 +616,26 @@ int nnc_kmeans1d_f32(nnc_ctx *ctx, const float *w, int64_t n, const float *init,
     h.n = n;
     h.k = k;
     h.mean = sc.mean;
-    std::vector<float> c_final(k), c_emit(k);
+    std::vector<float> c_final(k), c_emit(k), lin;
+    if (init_linear) {  // utility.py:206-209: np.linspace(min, max, num=k) on float32 scalars
+        lin.resize(k);
+        linspace_f32(ord2f(sc.min_ord), ord2f(sc.max_ord), k, lin.data());
+        init = lin.data();
+    }
     LloydResult lr = lloyd_run(ctx, h, init, max_iter, tol, c_final.data(), c_emit.data());
     // 4. final E-step in original order
     volatile float xlo = ord2f(sc.min_ord) - sc.mean, xhi = ord2f(sc.max_ord) - sc.mean;
     const float xabs = fmaxf(fabsf(xlo), fabsf(xhi));
     double inertia = NAN;
-    const bool want_emit = labels || ris || packed || hist || info;
+    const bool want_emit = labels || ris || packed || hist || (info && (flags & NNC_KM_INERTIA));
     if (want_emit) {
         Staged sl, sr, sp;
         if (labels) sl = stage_out(ctx, labels, sizeof(int32_t) * (size_t)n);
         if (ris) sr = stage_out(ctx, ris, sizeof(float) * (size_t)n);
         if (packed) sp = stage_out(ctx, packed, (size_t)((n * (int64_t)bits + 7) / 8));
-        emit_device(ctx, d_w, n, c_emit.data(), c_final.data(), k, sc.mean, xabs, nullptr, static_cast<int32_t *>(sl.dev),
-                    static_cast<float *>(sr.dev), static_cast<uint8_t *>(sp.dev), bits, hist, info ? &inertia : nullptr);
+        emit_device(ctx, d_w, n, c_emit.data(), c_final.data(), k, sc.mean, xabs, xlo, xhi, nullptr, static_cast<int32_t *>(sl.dev),
+                    static_cast<float *>(sr.dev), static_cast<uint8_t *>(sp.dev), bits, hist,
+                    (info && (flags & NNC_KM_INERTIA)) ? &inertia : nullptr);
         prof_mark(ctx, "emit");
         stage_finish(ctx, sl);
         stage_finish(ctx, sr);
@@ -667,7 +675,7 @@ int nnc_assign_f32(nnc_ctx *ctx, const float *w, int64_t n, const float *centred
     if (labels) sl = stage_out(ctx, labels, sizeof(int32_t) * (size_t)n);
     if (ris) sr = stage_out(ctx, ris, sizeof(float) * (size_t)n);
     if (packed) sp = stage_out(ctx, packed, (size_t)((n * (int64_t)bits + 7) / 8));
-    emit_device(ctx, static_cast<const float *>(sw.dev), n, centred, centred, k, mean, -1.f, values,
+    emit_device(ctx, static_cast<const float *>(sw.dev), n, centred, centred, k, mean, -1.f, 0.f, 0.f, values,
                 static_cast<int32_t *>(sl.dev), static_cast<float *>(sr.dev), static_cast<uint8_t *>(sp.dev), bits, hist,
                 inertia_out);
     prof_mark(ctx, "emit");

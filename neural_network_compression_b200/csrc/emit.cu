@@ -16,6 +16,9 @@
 
 namespace nnc {
 
+constexpr int EM_LUT = 16384;      // buckets of the label look-up table over [x'_min, x'_max]
+constexpr uint16_t EM_SLOW = 0x8000;  // LUT entry: bit 15 set -> low bits = first candidate region, resolve by search
+
 struct EmitDevice {
     RegionTable tab;
     float c[TB_KMAX];                  // centred centroids by id the labels are taken against (table input)
@@ -23,93 +26,144 @@ struct EmitDevice {
     float values[TB_KMAX];             // codebook by id
     unsigned long long hist[TB_KMAX];  // code histogram by id
     unsigned long long inertia_q;      // fixed-point sum of fl32 squared distances
+    int rid[2 * TB_KMAX + 2];          // cluster id of a SAFE region, -1 for a ZONE
+    int zid;                           // cluster id of the value 0.0 (the pruned weights)
+    float lut_lo, lut_scale;           // bucket(x') = clamp(int((x' - lut_lo) * lut_scale), 0, EM_LUT - 1)
+    alignas(16) uint32_t lut_cnt[EM_LUT];  // breakpoints per bucket (scratch of the table kernel)
+    alignas(16) uint16_t lut[EM_LUT];
 };
 
-__global__ void __launch_bounds__(TB_THREADS) emit_table_kernel(EmitDevice *ed, int k, float xabs_max) {
+// Monotone non-decreasing in xc: float subtraction, multiplication by a non-negative scale, truncation and the
+// clamp all preserve order, so "bucket(T) < b  =>  T < every x' of bucket b" and "bucket(T) > b  =>  T > ...".
+__device__ __forceinline__ int lut_bucket(float xc, float lo, float scale) {
+    int b = __float2int_rz(fmul(fsub(xc, lo), scale));
+    return min(max(b, 0), EM_LUT - 1);
+}
+
+// region of xc: number of breakpoints rstart[1..R-1] that are <= xc, scanning upwards from region r0
+__device__ __forceinline__ int region_from(const float *s_start, int R, int r0, float xc) {
+    int r = r0;
+    while (r + 1 < R && s_start[r + 1] <= xc) ++r;
+    return r;
+}
+
+__global__ void __launch_bounds__(TB_THREADS) emit_table_kernel(EmitDevice *ed, int k, float xabs_max, float mean, float lut_lo,
+                                                                float lut_scale) {
     __shared__ TableScratch S;
+    __shared__ uint32_t s_scan[32];
     build_region_table(ed->c, k, xabs_max, &ed->tab, S);
+    const RegionTable &T = ed->tab;
+    const int R = T.R, tid = threadIdx.x;
+    for (int r = tid; r < R; r += TB_THREADS) ed->rid[r] = T.rJ1[r] == T.rJ2[r] ? T.down[T.rJ1[r]] : -1;
+    for (int b = tid; b < EM_LUT; b += TB_THREADS) ed->lut_cnt[b] = 0;
+    __syncthreads();
+    for (int r = 1 + tid; r < R; r += TB_THREADS) atomicAdd(&ed->lut_cnt[lut_bucket(T.rstart[r], lut_lo, lut_scale)], 1u);
+    __syncthreads();
+    // exclusive scan of the bucket counts: region of the first x' of every bucket
+    constexpr int PER = EM_LUT / TB_THREADS;
+    uint32_t loc[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        loc[i] = ed->lut_cnt[tid * PER + i];
+        sum += loc[i];
+    }
+    uint32_t incl = block_scan_incl<uint32_t>(sum, [](uint32_t a, uint32_t b) { return a + b; }, s_scan);
+    uint32_t run = incl - sum;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int b = tid * PER + i;
+        const int rid = ed->rid[run];
+        ed->lut[b] = (loc[i] == 0 && rid >= 0) ? (uint16_t)rid : (uint16_t)(EM_SLOW | run);
+        run += loc[i];
+    }
+    if (tid == 0) {  // label of the pruned weights (value 0.0)
+        const float x0 = fsub(0.f, mean);
+        int r = 0;
+        while (r + 1 < R && T.rstart[r + 1] <= x0) ++r;
+        ed->zid = T.rJ1[r] == T.rJ2[r] ? T.down[T.rJ1[r]] : T.down[zone_argmin(x0, T.dv, T.dcn, T.down, T.rJ2[r], T.rJ1[r])];
+        ed->lut_lo = lut_lo;
+        ed->lut_scale = lut_scale;
+    }
 }
 
 constexpr int EM_THREADS = 256;
 constexpr int EM_PER = 8;  // weights per thread
 
-template <bool VEC>
+struct EmitSmem {
+    alignas(16) uint16_t lut[EM_LUT];
+    float start[2 * TB_KMAX + 2];
+    int rid[2 * TB_KMAX + 2];
+    float val[TB_KMAX];
+    uint32_t hist[TB_KMAX];
+    unsigned long long red[EM_THREADS / 32];
+};
+
+template <bool VEC, bool INERTIA>
 __global__ void __launch_bounds__(EM_THREADS) emit_kernel(const float *__restrict__ w, int64_t n, EmitDevice *ed, float mean,
                                                           double inertia_scale, int32_t *labels, float *ris,
-                                                          uint8_t *packed, int bits, int want_hist, int want_inertia) {
+                                                          uint8_t *packed, int bits, int want_hist) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    EmitSmem &S = *reinterpret_cast<EmitSmem *>(smem_raw);
     const RegionTable &T = ed->tab;
     const int R = T.R, k = T.k;
-    float *s_start = reinterpret_cast<float *>(smem_raw);                 // R + 1 region starts
-    int *s_rid = reinterpret_cast<int *>(s_start + (R + 1));              // R: cluster id of a SAFE region, -1 for a ZONE
-    float *s_val = reinterpret_cast<float *>(s_rid + R);                  // k codebook values
-    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_val + k);           // k counters
-    for (int i = threadIdx.x; i <= R; i += EM_THREADS) s_start[i] = T.rstart[i];
-    for (int i = threadIdx.x; i < R; i += EM_THREADS) s_rid[i] = T.rJ1[i] == T.rJ2[i] ? T.down[T.rJ1[i]] : -1;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(ed->lut);
+        uint4 *dst = reinterpret_cast<uint4 *>(S.lut);
+        for (int i = threadIdx.x; i < EM_LUT * 2 / 16; i += EM_THREADS) dst[i] = src[i];
+    }
+    for (int i = threadIdx.x; i <= R; i += EM_THREADS) S.start[i] = T.rstart[i];
+    for (int i = threadIdx.x; i < R; i += EM_THREADS) S.rid[i] = ed->rid[i];
     for (int i = threadIdx.x; i < k; i += EM_THREADS) {
-        s_val[i] = ed->values[i];
-        s_hist[i] = 0;
+        S.val[i] = ed->values[i];
+        S.hist[i] = 0;
     }
     __syncthreads();
+    const int zid = ed->zid;
+    const float lut_lo = ed->lut_lo, lut_scale = ed->lut_scale;
+    const float zval = S.val[zid];
 
     unsigned long long inert = 0;
+    unsigned int zcount = 0;
     const int64_t n_chunks = (n + EM_PER - 1) / EM_PER;
     const int64_t total_bytes = (n * bits + 7) / 8;
     const int64_t stride = (int64_t)gridDim.x * EM_THREADS;
-    const int64_t iters = (n_chunks + stride - 1) / stride;  // uniform trip count (warp collectives below)
-    for (int64_t it = 0; it < iters; ++it) {
-        const int64_t chunk = it * stride + (int64_t)blockIdx.x * EM_THREADS + threadIdx.x;
+    for (int64_t chunk = (int64_t)blockIdx.x * EM_THREADS + threadIdx.x; chunk < n_chunks; chunk += stride) {
         const int64_t base = chunk * EM_PER;
-        const bool live = chunk < n_chunks;
         float x[EM_PER];
-        int cnt = 0;
-        if (live) {
-            cnt = (int)min((int64_t)EM_PER, n - base);
-            if (VEC && cnt == EM_PER) {
-                float4 a = ld_stream_f4(w + base), b = ld_stream_f4(w + base + 4);
-                x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w;
-                x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
-            } else {
+        const int cnt = (int)min((int64_t)EM_PER, n - base);
+        if (VEC && cnt == EM_PER) {
+            float4 a = ld_stream_f4(w + base), b = ld_stream_f4(w + base + 4);
+            x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w;
+            x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
+        } else {
 #pragma unroll
-                for (int j = 0; j < EM_PER; ++j) x[j] = j < cnt ? w[base + j] : 0.f;
-            }
+            for (int j = 0; j < EM_PER; ++j) x[j] = j < cnt ? w[base + j] : 0.f;
         }
         int id[EM_PER];
 #pragma unroll
         for (int j = 0; j < EM_PER; ++j) {
-            id[j] = 0;
-            if (j < cnt) {
+            if (x[j] == 0.f) {  // pruned weight (or padding): one known label, counted in a register
+                id[j] = zid;
+                zcount += j < cnt;
+            } else {
                 const float xc = fsub(x[j], mean);
-                int lo = 0, hi = R;  // largest r with start[r] <= xc  (start[0] = -inf, start[R] = +inf)
-                while (hi - lo > 1) {
-                    int mid = (lo + hi) >> 1;
-                    if (s_start[mid] <= xc)
-                        lo = mid;
-                    else
-                        hi = mid;
+                const uint32_t e = S.lut[lut_bucket(xc, lut_lo, lut_scale)];
+                int lab = (int)e;
+                if (e & EM_SLOW) {
+                    const int r = region_from(S.start, R, (int)(e & (EM_SLOW - 1)), xc);
+                    lab = S.rid[r];
+                    if (lab < 0) lab = T.down[zone_argmin(xc, T.dv, T.dcn, T.down, T.rJ2[r], T.rJ1[r])];
                 }
-                const int rid = s_rid[lo];
-                if (rid < 0)
-                    id[j] = T.down[zone_argmin(xc, T.dv, T.dcn, T.down, T.rJ2[lo], T.rJ1[lo])];
-                else
-                    id[j] = rid;
-                if (want_inertia) {
-                    // distance to the centroid in centred space, as sklearn's _inertia_dense computes it
-                    float t = fsub(xc, ed->cfin[id[j]]);
-                    float d2 = fmul(t, t);
-                    inert += (unsigned long long)__double2ll_rn(__dmul_rn((double)d2, inertia_scale));
-                }
+                id[j] = lab;
+                if (want_hist) atomicAdd(&S.hist[lab], 1u);
+            }
+            if (INERTIA && j < cnt) {
+                // distance to the centroid in centred space, as sklearn's _inertia_dense computes it
+                const float t = fsub(fsub(x[j], mean), ed->cfin[id[j]]);
+                const float d2 = fmul(t, t);
+                inert += (unsigned long long)__double2ll_rn(__dmul_rn((double)d2, inertia_scale));
             }
         }
-        if (want_hist) {
-#pragma unroll
-            for (int j = 0; j < EM_PER; ++j) {
-                int key = j < cnt ? id[j] : -1;
-                uint32_t peers = __match_any_sync(0xffffffffu, key);
-                if (key >= 0 && (int)(__ffs(peers) - 1) == lane_id()) atomicAdd(&s_hist[key], (uint32_t)__popc(peers));
-            }
-        }
-        if (!live) continue;
         if (labels) {
             if (VEC && cnt == EM_PER) {
                 reinterpret_cast<int4 *>(labels + base)[0] = make_int4(id[0], id[1], id[2], id[3]);
@@ -120,10 +174,10 @@ __global__ void __launch_bounds__(EM_THREADS) emit_kernel(const float *__restric
         }
         if (ris) {
             if (VEC && cnt == EM_PER) {
-                st_stream_f4(ris + base, make_float4(s_val[id[0]], s_val[id[1]], s_val[id[2]], s_val[id[3]]));
-                st_stream_f4(ris + base + 4, make_float4(s_val[id[4]], s_val[id[5]], s_val[id[6]], s_val[id[7]]));
+                st_stream_f4(ris + base, make_float4(S.val[id[0]], S.val[id[1]], S.val[id[2]], S.val[id[3]]));
+                st_stream_f4(ris + base + 4, make_float4(S.val[id[4]], S.val[id[5]], S.val[id[6]], S.val[id[7]]));
             } else {
-                for (int j = 0; j < cnt; ++j) ris[base + j] = s_val[id[j]];
+                for (int j = 0; j < cnt; ++j) ris[base + j] = S.val[id[j]];
             }
         }
         if (packed) {
@@ -131,7 +185,7 @@ __global__ void __launch_bounds__(EM_THREADS) emit_kernel(const float *__restric
             unsigned long long lo64 = 0, hi64 = 0;
 #pragma unroll
             for (int j = 0; j < EM_PER; ++j) {
-                const unsigned long long v = (unsigned long long)(uint32_t)id[j];
+                const unsigned long long v = j < cnt ? (unsigned long long)(uint32_t)id[j] : 0ull;
                 const int sh = j * bits;
                 if (sh < 64) {
                     lo64 |= v << sh;
@@ -159,20 +213,28 @@ __global__ void __launch_bounds__(EM_THREADS) emit_kernel(const float *__restric
             }
         }
     }
-    if (want_inertia) {
+    (void)zval;
+    if (INERTIA) {
         inert = warp_sum_ull(inert);
         if (lane_id() == 0 && inert) atomicAdd(&ed->inertia_q, inert);
     }
     if (want_hist) {
+        unsigned long long z = warp_sum_ull((unsigned long long)zcount);
+        if (lane_id() == 0) S.red[warp_id()] = z;
         __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t = 0;
+            for (int i = 0; i < EM_THREADS / 32; ++i) t += S.red[i];
+            if (t) atomicAdd(&ed->hist[zid], t);
+        }
         for (int i = threadIdx.x; i < k; i += EM_THREADS)
-            if (s_hist[i]) atomicAdd(&ed->hist[i], (unsigned long long)s_hist[i]);
+            if (S.hist[i]) atomicAdd(&ed->hist[i], (unsigned long long)S.hist[i]);
     }
 }
 
 void emit_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *h_centred, const float *h_centred_final, int k,
-                 float mean, float xabs, const float *h_values, int32_t *d_labels, float *d_ris, uint8_t *d_packed, int bits,
-                 int64_t *h_hist, double *h_inertia) {
+                 float mean, float xabs, float xlo, float xhi, const float *h_values, int32_t *d_labels, float *d_ris,
+                 uint8_t *d_packed, int bits, int64_t *h_hist, double *h_inertia) {
     if (!h_centred_final) h_centred_final = h_centred;
     if (k < 1 || k > TB_KMAX) NNC_FAIL(NNC_ERR_UNSUPPORTED, "emit: k = %d outside [1, %d]", k, TB_KMAX);
     if (d_packed) {
@@ -198,27 +260,50 @@ void emit_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *h_centr
         minmax_device(ctx, d_w, n, 0, &mn, &mx, &cnt);
         volatile float a = mn - mean, b = mx - mean;
         xabs = fmaxf(fabsf(a), fabsf(b));
+        xlo = a;
+        xhi = b;
     }
     float cmax = xabs;
     for (int j = 0; j < k; ++j) cmax = fmaxf(cmax, fabsf(h_centred_final[j]));
     int Ed = cmax > 0.f ? ilogbf(cmax) + 1 : 0;
     const double inertia_scale = ldexp(1.0, 31 - (2 * Ed + 2));
-    NNC_LAUNCH(ctx, emit_table_kernel, 1, TB_THREADS, 0, ed, k, xabs);
+    // label LUT over the data range [x'_min, x'_max] (callers that do not know the range pass the symmetric bound)
+    if (!(xlo <= xhi)) {
+        xlo = -xabs;
+        xhi = xabs;
+    }
+    volatile float span = xhi - xlo;
+    float lut_scale = span > 0.f ? (float)((double)EM_LUT / (double)span * (1.0 - 1e-6)) : 0.f;
+    if (!isfinite(lut_scale)) lut_scale = 0.f;
+    NNC_LAUNCH(ctx, emit_table_kernel, 1, TB_THREADS, 0, ed, k, xabs, mean, xlo, lut_scale);
     const bool vec = ((reinterpret_cast<uintptr_t>(d_w) & 15u) == 0) &&
                      (!d_labels || (reinterpret_cast<uintptr_t>(d_labels) & 15u) == 0) &&
                      (!d_ris || (reinterpret_cast<uintptr_t>(d_ris) & 15u) == 0) &&
                      (!d_packed || (reinterpret_cast<uintptr_t>(d_packed) & 15u) == 0);
     const int64_t n_chunks = (n + EM_PER - 1) / EM_PER;
-    const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, (n_chunks + EM_THREADS - 1) / EM_THREADS);
-    const size_t smem = sizeof(float) * (2 * (size_t)k + 2) + sizeof(int) * (2 * (size_t)k + 1) + sizeof(float) * k +
-                        sizeof(uint32_t) * k;
-    const int want_hist = h_hist ? 1 : 0, want_inertia = h_inertia ? 1 : 0;
-    if (vec)
-        NNC_LAUNCH(ctx, emit_kernel<true>, grid, EM_THREADS, smem, d_w, n, ed, mean, inertia_scale, d_labels, d_ris, d_packed,
-                   bits, want_hist, want_inertia);
+    const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 4, (n_chunks + EM_THREADS - 1) / EM_THREADS);
+    const size_t smem = sizeof(EmitSmem);
+    const int want_hist = h_hist ? 1 : 0;
+    static bool configured = false;
+    if (!configured) {
+        NNC_CUDA(cudaFuncSetAttribute(emit_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NNC_CUDA(cudaFuncSetAttribute(emit_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NNC_CUDA(cudaFuncSetAttribute(emit_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NNC_CUDA(cudaFuncSetAttribute(emit_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    if (vec && h_inertia)
+        NNC_LAUNCH(ctx, (emit_kernel<true, true>), grid, EM_THREADS, smem, d_w, n, ed, mean, inertia_scale, d_labels, d_ris,
+                   d_packed, bits, want_hist);
+    else if (vec)
+        NNC_LAUNCH(ctx, (emit_kernel<true, false>), grid, EM_THREADS, smem, d_w, n, ed, mean, inertia_scale, d_labels, d_ris,
+                   d_packed, bits, want_hist);
+    else if (h_inertia)
+        NNC_LAUNCH(ctx, (emit_kernel<false, true>), grid, EM_THREADS, smem, d_w, n, ed, mean, inertia_scale, d_labels, d_ris,
+                   d_packed, bits, want_hist);
     else
-        NNC_LAUNCH(ctx, emit_kernel<false>, grid, EM_THREADS, smem, d_w, n, ed, mean, inertia_scale, d_labels, d_ris,
-                   d_packed, bits, want_hist, want_inertia);
+        NNC_LAUNCH(ctx, (emit_kernel<false, false>), grid, EM_THREADS, smem, d_w, n, ed, mean, inertia_scale, d_labels, d_ris,
+                   d_packed, bits, want_hist);
     if (h_hist || h_inertia) {
         std::vector<unsigned long long> hh(k + 1);
         if (h_hist) NNC_CUDA(cudaMemcpyAsync(hh.data(), ed->hist, sizeof(unsigned long long) * k, cudaMemcpyDeviceToHost, ctx->stream));

@@ -55,6 +55,9 @@ struct DevScalars {
     // quantization prologue
     uint32_t min_ord, max_ord;        // ordered-uint min / max over all elements
     uint32_t min_nz_ord, max_nz_ord;  // ... over non-zero elements
+    uint32_t amax_bits;               // largest |x| bit pattern (>= 0x7f800000: a NaN or infinity is present)
+    uint32_t amin_nz_m1;              // smallest non-zero |x| bit pattern, minus one (0xffffffff: all zero)
+    float fmin_all, fmax_all;         // float min / max over all elements (scratch; folded into min_ord / max_ord)
     unsigned long long n_nz;          // non-zero count (also the compaction cursor)
     int pad_;
 };
@@ -169,7 +172,7 @@ int64_t compact_ordered_device(nnc_ctx *ctx, const float *d_w, int64_t n, float 
 void gather_device(nnc_ctx *ctx, const float *d_w, int64_t n, const int64_t *h_idx, int m, float *h_out);
 
 // sort.cu : onesweep LSD radix sort of float32 keys; returns pointer to the sorted buffer (d_a or d_b)
-float *radix_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n);
+float *radix_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n, uint32_t amin, uint32_t amax);
 
 // lloyd.cu
 struct LloydResult {
@@ -192,9 +195,10 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
 // emit.cu : final E-step over the tensor in original order
 // h_centred: centroids the labels are taken against; h_centred_final (optional): final centroids (codebook
 // values and inertia); they differ only after a strict stop in which relocation fired.
-// xabs: max |w - mean| over the tensor when the caller already knows it, negative to have it measured here.
+// xabs / xlo / xhi: max |w - mean|, min and max of (w - mean) over the tensor when the caller already knows
+// them; xabs negative to have them measured here.
 void emit_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *h_centred, const float *h_centred_final, int k,
-                 float mean, float xabs, const float *h_values, int32_t *d_labels, float *d_ris, uint8_t *d_packed, int bits,
+                 float mean, float xabs, float xlo, float xhi, const float *h_values, int32_t *d_labels, float *d_ris, uint8_t *d_packed, int bits,
                  int64_t *h_hist, double *h_inertia);
 void unpack_gather_device(nnc_ctx *ctx, const uint8_t *d_packed, int64_t n, int bits, const float *h_values, int k,
                           float *d_out);

@@ -216,25 +216,23 @@ struct VisitCenSqApply {
     }
 };
 
-// k-means prologue: term = x (-> mean); side: min / max (all and non-zero), non-zero count, non-finite.
+// k-means prologue: term = x (-> mean); side: min / max, non-zero count, range of |x| bit patterns over the
+// non-zero elements (the radix-sort key range), non-finite detection (|x| bits >= 0x7f800000).
 struct VisitQuant {
     DevScalars *sc;
-    uint32_t mn = 0xffffffffu, mx = 0u, mnz = 0xffffffffu, mxz = 0u;
-    unsigned long long nz = 0, bad = 0;
+    float mn = INFINITY, mx = -INFINITY;
+    uint32_t amax = 0u, amin_m1 = 0xffffffffu;
+    unsigned int nz = 0;
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ float4 load4(const float *p) const { return ld_stream_f4(p); }
     __device__ __forceinline__ float load1(const float *p) const { return ld_stream_f1(p); }
     __device__ __forceinline__ float one(float x) {
-        float xc = x == 0.f ? 0.f : x;  // -0.0 -> +0.0 for the ordered key
-        uint32_t o = f2ord(xc);
-        mn = min(mn, o);
-        mx = max(mx, o);
-        if (x != 0.f) {
-            nz++;
-            mnz = min(mnz, o);
-            mxz = max(mxz, o);
-        }
-        bad += !isfinite(x);
+        const uint32_t a = __float_as_uint(x) & 0x7fffffffu;
+        amax = max(amax, a);
+        amin_m1 = min(amin_m1, a - 1u);  // zero wraps to 0xffffffff and never wins
+        nz += a != 0u;
+        mn = fminf(mn, x);
+        mx = fmaxf(mx, x);
         return x;
     }
     __device__ __forceinline__ float4 visit4(int64_t, const float *, float4 x) {
@@ -242,32 +240,37 @@ struct VisitQuant {
     }
     __device__ __forceinline__ float visit1(int64_t, const float *, float x) { return one(x); }
     __device__ void finish(BlockAux &aux) {
-        uint32_t a = warp_min_u(mn), b = warp_max_u(mx), c = warp_min_u(mnz), d = warp_max_u(mxz);
-        unsigned long long e = warp_sum_ull(nz), f = warp_sum_ull(bad);
+        // a thread sees at most 2^32 / 4 elements only for absurd grids; the per-thread count fits 32 bits
+        float a = warp_min_f(mn), b = warp_max_f(mx);
+        uint32_t c = warp_max_u(amax), d = warp_min_u(amin_m1);
+        unsigned long long e = warp_sum_ull((unsigned long long)nz);
         if (lane_id() == 0) {
-            aux.o[0][warp_id()] = a;
-            aux.o[1][warp_id()] = b;
+            aux.o[0][warp_id()] = __float_as_uint(a);
+            aux.o[1][warp_id()] = __float_as_uint(b);
             aux.o[2][warp_id()] = c;
             aux.o[3][warp_id()] = d;
             aux.u[0][warp_id()] = e;
-            aux.u[1][warp_id()] = f;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
             for (int i = 1; i < NP_THREADS / 32; i++) {
-                a = min(a, aux.o[0][i]);
-                b = max(b, aux.o[1][i]);
-                c = min(c, aux.o[2][i]);
-                d = max(d, aux.o[3][i]);
+                a = fminf(a, __uint_as_float(aux.o[0][i]));
+                b = fmaxf(b, __uint_as_float(aux.o[1][i]));
+                c = max(c, aux.o[2][i]);
+                d = min(d, aux.o[3][i]);
                 e += aux.u[0][i];
-                f += aux.u[1][i];
             }
-            atomicMin(&sc->min_ord, a);
-            atomicMax(&sc->max_ord, b);
-            atomicMin(&sc->min_nz_ord, c);
-            atomicMax(&sc->max_nz_ord, d);
+            // -0.0 -> +0.0 so that the ordered image of the extrema is canonical
+            if (a == 0.f) a = 0.f;
+            if (b == 0.f) b = 0.f;
+            if (a <= b) {  // false only if every element seen was NaN
+                atomicMin(&sc->min_ord, f2ord(a));
+                atomicMax(&sc->max_ord, f2ord(b));
+            }
+            atomicMax(&sc->amax_bits, c);
+            atomicMin(&sc->amin_nz_m1, d);
             if (e) atomicAdd(&sc->n_nz, e);
-            if (f) atomicAdd(&sc->n_nonfinite, f);
+            if (c >= 0x7f800000u) atomicAdd(&sc->n_nonfinite, 1ull);
         }
     }
 };
@@ -555,6 +558,7 @@ static void clear_scalars(nnc_ctx *ctx) {
     memset(&z, 0, sizeof(z));
     z.min_ord = 0xffffffffu;
     z.min_nz_ord = 0xffffffffu;
+    z.amin_nz_m1 = 0xffffffffu;
     *ctx->h_scal = z;
     NNC_CUDA(cudaMemcpyAsync(ctx->d_scal, ctx->h_scal, sizeof(DevScalars), cudaMemcpyHostToDevice, ctx->stream));
 }

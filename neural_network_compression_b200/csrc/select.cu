@@ -148,70 +148,112 @@ void hist_edges_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *h
 
 // ---------------------------------------------------------------------------------------------
 // order-preserving non-zero compaction, single pass, decoupled look-back
-constexpr int CP_THREADS = 256;
-constexpr int CP_ROWS = 16;                         // rows of 32 per warp
-constexpr int CP_TILE = CP_THREADS * CP_ROWS;       // 4096 elements
+//
+// A tile is 8192 consecutive elements; warp w of the CTA owns elements [512 w, 512 (w+1)) of it as 4 rows of
+// 128 (one float4 per lane and row), so survivors keep their order: (row, lane, component) is element order.
+constexpr int CP_THREADS = 512;
+constexpr int CP_WARPS = CP_THREADS / 32;
+constexpr int CP_ROWS = 4;
+constexpr int CP_TILE = CP_THREADS * CP_ROWS * 4;  // 8192 elements
 constexpr unsigned long long CP_FLAG_AGG = 1ull << 62;
 constexpr unsigned long long CP_FLAG_PFX = 2ull << 62;
 constexpr unsigned long long CP_VAL_MASK = (1ull << 62) - 1;
 
-__global__ void __launch_bounds__(CP_THREADS) compact_kernel(const float *w, int64_t n, float *out,
-                                                             unsigned long long *state, unsigned int *ticket,
-                                                             unsigned long long *total_out) {
+// exclusive prefix of the tile: sum of the survivor counts of all earlier tiles (warp-parallel look-back)
+__device__ __forceinline__ unsigned long long cp_lookback(unsigned long long *state, unsigned int tile, unsigned long long tot) {
+    const int lane = lane_id();
+    if (tile == 0) {
+        if (lane == 0) st_volatile_u64(&state[0], CP_FLAG_PFX | tot);
+        return 0;
+    }
+    if (lane == 0) st_volatile_u64(&state[tile], CP_FLAG_AGG | tot);
+    unsigned long long excl = 0;
+    long long p = (long long)tile - 1;
+    for (;;) {
+        const long long idx = p - lane;
+        unsigned long long v = CP_FLAG_PFX;  // tiles before the first contribute 0 and end the walk
+        if (idx >= 0) {
+            do {
+                v = ld_volatile_u64(&state[idx]);
+            } while ((v >> 62) == 0);
+        }
+        const unsigned pfx = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+        const int stop = pfx ? __ffs(pfx) - 1 : 32;  // nearest predecessor that already holds an inclusive prefix
+        unsigned long long c = lane <= stop ? (v & CP_VAL_MASK) : 0ull;
+        c = warp_sum_ull(c);
+        excl += c;
+        if (pfx) break;
+        p -= 32;
+    }
+    if (lane == 0) st_volatile_u64(&state[tile], CP_FLAG_PFX | (excl + tot));
+    return excl;
+}
+
+__global__ void __launch_bounds__(CP_THREADS, 2) compact_kernel(const float *w, int64_t n, int vec_ok, float *out,
+                                                                unsigned long long *state, unsigned int *ticket,
+                                                                unsigned long long *total_out) {
     __shared__ unsigned int s_tile;
-    __shared__ int s_warp_cnt[CP_THREADS / 32];
+    __shared__ int s_warp_cnt[CP_WARPS];
     __shared__ unsigned long long s_base;
     const int64_t n_tiles = (n + CP_TILE - 1) / CP_TILE;
     const int lane = lane_id(), wid = warp_id();
+    const uint32_t lt = (1u << lane) - 1u;
     for (;;) {
         if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
         __syncthreads();
         const unsigned int tile = s_tile;
         if ((int64_t)tile >= n_tiles) break;
-        const int64_t warp_base = (int64_t)tile * CP_TILE + (int64_t)wid * (32 * CP_ROWS);
-        float x[CP_ROWS];
-        uint32_t bal[CP_ROWS];
-        int wcnt = 0;
+        const int64_t warp_base = (int64_t)tile * CP_TILE + (int64_t)wid * (128 * CP_ROWS);
+        float4 x[CP_ROWS];
 #pragma unroll
         for (int r = 0; r < CP_ROWS; ++r) {
-            int64_t i = warp_base + r * 32 + lane;
-            x[r] = i < n ? ld_stream_f1(w + i) : 0.f;
+            const int64_t i = warp_base + r * 128 + lane * 4;
+            if (vec_ok && i + 4 <= n) {
+                x[r] = ld_stream_f4(w + i);
+            } else {
+                x[r].x = i < n ? w[i] : 0.f;
+                x[r].y = i + 1 < n ? w[i + 1] : 0.f;
+                x[r].z = i + 2 < n ? w[i + 2] : 0.f;
+                x[r].w = i + 3 < n ? w[i + 3] : 0.f;
+            }
         }
+        // per lane and row: survivors (NaN != 0 is true: NaNs survive, like numpy), exclusive offsets in the warp
+        int off[CP_ROWS], wcnt = 0;
 #pragma unroll
         for (int r = 0; r < CP_ROWS; ++r) {
-            bal[r] = __ballot_sync(0xffffffffu, x[r] != 0.f);  // NaN != 0 is true: NaNs survive, like numpy
-            wcnt += __popc(bal[r]);
+            const int c = (x[r].x != 0.f) + (x[r].y != 0.f) + (x[r].z != 0.f) + (x[r].w != 0.f);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            off[r] = wcnt + incl - c;
+            wcnt += __shfl_sync(0xffffffffu, incl, 31);
         }
+        (void)lt;
         if (lane == 0) s_warp_cnt[wid] = wcnt;
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (wid == 0) {
             unsigned long long tot = 0;
-            for (int i = 0; i < CP_THREADS / 32; ++i) tot += s_warp_cnt[i];
-            unsigned long long excl = 0;
-            if (tile == 0) {
-                st_volatile_u64(&state[0], CP_FLAG_PFX | tot);
-            } else {
-                st_volatile_u64(&state[tile], CP_FLAG_AGG | tot);
-                for (int64_t p = (int64_t)tile - 1; p >= 0; --p) {
-                    unsigned long long s;
-                    do {
-                        s = ld_volatile_u64(&state[p]);
-                    } while ((s >> 62) == 0);
-                    excl += s & CP_VAL_MASK;
-                    if ((s >> 62) == 2) break;
-                }
-                st_volatile_u64(&state[tile], CP_FLAG_PFX | (excl + tot));
+#pragma unroll
+            for (int i = 0; i < CP_WARPS; ++i) tot += s_warp_cnt[i];
+            const unsigned long long excl = cp_lookback(state, tile, tot);
+            if (lane == 0) {
+                s_base = excl;
+                if ((int64_t)tile == n_tiles - 1) *total_out = excl + tot;
             }
-            s_base = excl;
-            if ((int64_t)tile == n_tiles - 1) *total_out = excl + tot;
         }
         __syncthreads();
         unsigned long long base = s_base;
         for (int i = 0; i < wid; ++i) base += s_warp_cnt[i];
 #pragma unroll
         for (int r = 0; r < CP_ROWS; ++r) {
-            if (x[r] != 0.f) out[base + __popc(bal[r] & ((1u << lane) - 1u))] = x[r];
-            base += __popc(bal[r]);
+            float *dst = out + base + off[r];
+            if (x[r].x != 0.f) *dst++ = x[r].x;
+            if (x[r].y != 0.f) *dst++ = x[r].y;
+            if (x[r].z != 0.f) *dst++ = x[r].z;
+            if (x[r].w != 0.f) *dst++ = x[r].w;
         }
         __syncthreads();  // s_tile / s_warp_cnt reuse
     }
@@ -223,8 +265,9 @@ int64_t compact_ordered_device(nnc_ctx *ctx, const float *d_w, int64_t n, float 
     NNC_CUDA(cudaMemsetAsync(state, 0, sizeof(unsigned long long) * (n_tiles + 2), ctx->stream));
     unsigned int *ticket = reinterpret_cast<unsigned int *>(state + n_tiles);
     unsigned long long *total = state + n_tiles + 1;
-    int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, n_tiles);
-    NNC_LAUNCH(ctx, compact_kernel, grid, CP_THREADS, 0, d_w, n, d_out, state, ticket, total);
+    int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 2, n_tiles);
+    int vec_ok = (reinterpret_cast<uintptr_t>(d_w) & 15u) == 0;
+    NNC_LAUNCH(ctx, compact_kernel, grid, CP_THREADS, 0, d_w, n, vec_ok, d_out, state, ticket, total);
     unsigned long long h = 0;
     NNC_CUDA(cudaMemcpyAsync(&h, total, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     NNC_CUDA(cudaStreamSynchronize(ctx->stream));
