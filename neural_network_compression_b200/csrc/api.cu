@@ -622,19 +622,19 @@ int nnc_kmeans1d_f32(nnc_ctx *ctx, const float *w, int64_t n, const float *init,
         linspace_f32(ord2f(sc.min_ord), ord2f(sc.max_ord), k, lin.data());
         init = lin.data();
     }
-    LloydResult lr = lloyd_run(ctx, h, init, max_iter, tol, c_final.data(), c_emit.data());
+    LloydResult lr = lloyd_run(ctx, h, init, max_iter, tol, c_final.data(), c_emit.data(), hist);
     // 4. final E-step in original order
     volatile float xlo = ord2f(sc.min_ord) - sc.mean, xhi = ord2f(sc.max_ord) - sc.mean;
     const float xabs = fmaxf(fabsf(xlo), fabsf(xhi));
     double inertia = NAN;
-    const bool want_emit = labels || ris || packed || hist || (info && (flags & NNC_KM_INERTIA));
+    const bool want_emit = labels || ris || packed || (info && (flags & NNC_KM_INERTIA));
     if (want_emit) {
         Staged sl, sr, sp;
         if (labels) sl = stage_out(ctx, labels, sizeof(int32_t) * (size_t)n);
         if (ris) sr = stage_out(ctx, ris, sizeof(float) * (size_t)n);
         if (packed) sp = stage_out(ctx, packed, (size_t)((n * (int64_t)bits + 7) / 8));
         emit_device(ctx, d_w, n, c_emit.data(), c_final.data(), k, sc.mean, xabs, xlo, xhi, nullptr, static_cast<int32_t *>(sl.dev),
-                    static_cast<float *>(sr.dev), static_cast<uint8_t *>(sp.dev), bits, hist,
+                    static_cast<float *>(sr.dev), static_cast<uint8_t *>(sp.dev), bits, nullptr,
                     (info && (flags & NNC_KM_INERTIA)) ? &inertia : nullptr);
         prof_mark(ctx, "emit");
         stage_finish(ctx, sl);

@@ -16,8 +16,14 @@
 
 namespace nnc {
 
-constexpr int EM_LUT = 16384;      // buckets of the label look-up table over [x'_min, x'_max]
-constexpr uint16_t EM_SLOW = 0x8000;  // LUT entry: bit 15 set -> low bits = first candidate region, resolve by search
+constexpr int EM_LUT = 16384;       // coarse buckets of the label look-up table over [x'_min, x'_max]
+constexpr int EM_SUB = 32;          // fine buckets per coarse bucket (second level, only for buckets holding a boundary)
+constexpr int EM_FINE = EM_LUT * EM_SUB;
+constexpr int EM_DMAX = 512;        // coarse buckets that get a second-level table
+// LUT entry (16 bit): 00 | cluster id        the whole bucket lies in one SAFE region
+//                     01 | table index       second-level table (first level only)
+//                     10 | region            resolve by search starting at that region (boundary or ZONE inside)
+constexpr uint32_t EM_SLOW = 0x8000, EM_L2 = 0x4000;
 
 struct EmitDevice {
     RegionTable tab;
@@ -28,16 +34,24 @@ struct EmitDevice {
     unsigned long long inertia_q;      // fixed-point sum of fl32 squared distances
     int rid[2 * TB_KMAX + 2];          // cluster id of a SAFE region, -1 for a ZONE
     int zid;                           // cluster id of the value 0.0 (the pruned weights)
-    float lut_lo, lut_scale;           // bucket(x') = clamp(int((x' - lut_lo) * lut_scale), 0, EM_LUT - 1)
-    alignas(16) uint32_t lut_cnt[EM_LUT];  // breakpoints per bucket (scratch of the table kernel)
+    float lut_lo, lut_scale;           // fine bucket(x') = min(int((x' - lut_lo) * lut_scale), EM_FINE - 1)
+    alignas(16) uint32_t lut_cnt[EM_LUT];  // boundaries per coarse bucket (scratch of the table kernel)
+    alignas(16) uint16_t lut_rlo[EM_LUT];  // region of the first x' of every coarse bucket (scratch)
+    alignas(16) uint16_t lut_did[EM_LUT];  // dense index of a bucket that holds boundaries (scratch)
+    alignas(16) uint32_t sub_cnt[EM_DMAX * EM_SUB];
     alignas(16) uint16_t lut[EM_LUT];
+    alignas(16) uint16_t lut2[EM_DMAX * EM_SUB];
 };
 
 // Monotone non-decreasing in xc: float subtraction, multiplication by a non-negative scale, truncation and the
 // clamp all preserve order, so "bucket(T) < b  =>  T < every x' of bucket b" and "bucket(T) > b  =>  T > ...".
-__device__ __forceinline__ int lut_bucket(float xc, float lo, float scale) {
-    int b = __float2int_rz(fmul(fsub(xc, lo), scale));
-    return min(max(b, 0), EM_LUT - 1);
+__device__ __forceinline__ int lut_fine(float xc, float lo, float scale) {
+    return (int)min((unsigned)__float2int_rz(fmul(fsub(xc, lo), scale)), (unsigned)(EM_FINE - 1));
+}
+__device__ __forceinline__ int lut_fine_clamped(float xc, float lo, float scale) {  // for thresholds outside the data range
+    const float t = fmul(fsub(xc, lo), scale);
+    if (!(t > 0.f)) return 0;
+    return (int)min((unsigned)__float2int_rz(t), (unsigned)(EM_FINE - 1));
 }
 
 // region of xc: number of breakpoints rstart[1..R-1] that are <= xc, scanning upwards from region r0
@@ -56,25 +70,56 @@ __global__ void __launch_bounds__(TB_THREADS) emit_table_kernel(EmitDevice *ed, 
     const int R = T.R, tid = threadIdx.x;
     for (int r = tid; r < R; r += TB_THREADS) ed->rid[r] = T.rJ1[r] == T.rJ2[r] ? T.down[T.rJ1[r]] : -1;
     for (int b = tid; b < EM_LUT; b += TB_THREADS) ed->lut_cnt[b] = 0;
+    for (int i = tid; i < EM_DMAX * EM_SUB; i += TB_THREADS) ed->sub_cnt[i] = 0;
     __syncthreads();
-    for (int r = 1 + tid; r < R; r += TB_THREADS) atomicAdd(&ed->lut_cnt[lut_bucket(T.rstart[r], lut_lo, lut_scale)], 1u);
+    for (int r = 1 + tid; r < R; r += TB_THREADS) atomicAdd(&ed->lut_cnt[lut_fine_clamped(T.rstart[r], lut_lo, lut_scale) / EM_SUB], 1u);
     __syncthreads();
-    // exclusive scan of the bucket counts: region of the first x' of every bucket
+    // exclusive scans over the coarse buckets: boundaries before the bucket (-> region of its first x') and
+    // buckets holding boundaries before it (-> dense index)
     constexpr int PER = EM_LUT / TB_THREADS;
-    uint32_t loc[PER], sum = 0;
+    uint32_t loc[PER], sum = 0, dsum = 0;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         loc[i] = ed->lut_cnt[tid * PER + i];
         sum += loc[i];
+        dsum += loc[i] != 0;
     }
     uint32_t incl = block_scan_incl<uint32_t>(sum, [](uint32_t a, uint32_t b) { return a + b; }, s_scan);
-    uint32_t run = incl - sum;
+    uint32_t dincl = block_scan_incl<uint32_t>(dsum, [](uint32_t a, uint32_t b) { return a + b; }, s_scan);
+    uint32_t run = incl - sum, drun = dincl - dsum;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         const int b = tid * PER + i;
         const int rid = ed->rid[run];
-        ed->lut[b] = (loc[i] == 0 && rid >= 0) ? (uint16_t)rid : (uint16_t)(EM_SLOW | run);
+        uint32_t e;
+        if (loc[i] == 0)
+            e = rid >= 0 ? (uint32_t)rid : (EM_SLOW | run);
+        else
+            e = drun < (uint32_t)EM_DMAX ? (EM_L2 | drun) : (EM_SLOW | run);
+        ed->lut[b] = (uint16_t)e;
+        ed->lut_rlo[b] = (uint16_t)run;
+        ed->lut_did[b] = (uint16_t)(loc[i] != 0 && drun < (uint32_t)EM_DMAX ? drun : 0xffffu);
         run += loc[i];
+        drun += loc[i] != 0;
+    }
+    __syncthreads();
+    // second level: boundaries per fine bucket of the buckets that have a table
+    for (int r = 1 + tid; r < R; r += TB_THREADS) {
+        const int f = lut_fine_clamped(T.rstart[r], lut_lo, lut_scale);
+        const uint32_t did = ed->lut_did[f / EM_SUB];
+        if (did != 0xffffu) atomicAdd(&ed->sub_cnt[did * EM_SUB + (f % EM_SUB)], 1u);
+    }
+    __syncthreads();
+    for (int b = tid; b < EM_LUT; b += TB_THREADS) {
+        const uint32_t did = ed->lut_did[b];
+        if (did == 0xffffu) continue;
+        uint32_t r = ed->lut_rlo[b];
+        for (int f = 0; f < EM_SUB; ++f) {
+            const uint32_t c = ed->sub_cnt[did * EM_SUB + f];
+            const int rid = ed->rid[r];
+            ed->lut2[did * EM_SUB + f] = (uint16_t)((c == 0 && rid >= 0) ? (uint32_t)rid : (EM_SLOW | r));
+            r += c;
+        }
     }
     if (tid == 0) {  // label of the pruned weights (value 0.0)
         const float x0 = fsub(0.f, mean);
@@ -86,11 +131,12 @@ __global__ void __launch_bounds__(TB_THREADS) emit_table_kernel(EmitDevice *ed, 
     }
 }
 
-constexpr int EM_THREADS = 256;
+constexpr int EM_THREADS = 512;
 constexpr int EM_PER = 8;  // weights per thread
 
 struct EmitSmem {
     alignas(16) uint16_t lut[EM_LUT];
+    alignas(16) uint16_t lut2[EM_DMAX * EM_SUB];
     float start[2 * TB_KMAX + 2];
     int rid[2 * TB_KMAX + 2];
     float val[TB_KMAX];
@@ -98,18 +144,23 @@ struct EmitSmem {
     unsigned long long red[EM_THREADS / 32];
 };
 
-template <bool VEC, bool INERTIA>
-__global__ void __launch_bounds__(EM_THREADS) emit_kernel(const float *__restrict__ w, int64_t n, EmitDevice *ed, float mean,
+// BITS: compile-time width of a packed code (8), or 0 for the run-time width `bits`
+template <bool VEC, bool INERTIA, int BITS>
+__global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__restrict__ w, int64_t n, EmitDevice *ed, float mean,
                                                           double inertia_scale, int32_t *labels, float *ris,
-                                                          uint8_t *packed, int bits, int want_hist) {
+                                                          uint8_t *packed, int bits_rt, int want_hist) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EmitSmem &S = *reinterpret_cast<EmitSmem *>(smem_raw);
     const RegionTable &T = ed->tab;
     const int R = T.R, k = T.k;
+    const int bits = BITS ? BITS : bits_rt;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(ed->lut);
         uint4 *dst = reinterpret_cast<uint4 *>(S.lut);
         for (int i = threadIdx.x; i < EM_LUT * 2 / 16; i += EM_THREADS) dst[i] = src[i];
+        src = reinterpret_cast<const uint4 *>(ed->lut2);
+        dst = reinterpret_cast<uint4 *>(S.lut2);
+        for (int i = threadIdx.x; i < EM_DMAX * EM_SUB * 2 / 16; i += EM_THREADS) dst[i] = src[i];
     }
     for (int i = threadIdx.x; i <= R; i += EM_THREADS) S.start[i] = T.rstart[i];
     for (int i = threadIdx.x; i < R; i += EM_THREADS) S.rid[i] = ed->rid[i];
@@ -120,7 +171,6 @@ __global__ void __launch_bounds__(EM_THREADS) emit_kernel(const float *__restric
     __syncthreads();
     const int zid = ed->zid;
     const float lut_lo = ed->lut_lo, lut_scale = ed->lut_scale;
-    const float zval = S.val[zid];
 
     unsigned long long inert = 0;
     unsigned int zcount = 0;
@@ -139,29 +189,51 @@ __global__ void __launch_bounds__(EM_THREADS) emit_kernel(const float *__restric
 #pragma unroll
             for (int j = 0; j < EM_PER; ++j) x[j] = j < cnt ? w[base + j] : 0.f;
         }
+        // phase 1, branch free: LUT entry of every element (pruned weights take the known label of 0.0)
         int id[EM_PER];
+        uint32_t slow = 0;
 #pragma unroll
         for (int j = 0; j < EM_PER; ++j) {
-            if (x[j] == 0.f) {  // pruned weight (or padding): one known label, counted in a register
-                id[j] = zid;
-                zcount += j < cnt;
-            } else {
-                const float xc = fsub(x[j], mean);
-                const uint32_t e = S.lut[lut_bucket(xc, lut_lo, lut_scale)];
-                int lab = (int)e;
-                if (e & EM_SLOW) {
-                    const int r = region_from(S.start, R, (int)(e & (EM_SLOW - 1)), xc);
-                    lab = S.rid[r];
-                    if (lab < 0) lab = T.down[zone_argmin(xc, T.dv, T.dcn, T.down, T.rJ2[r], T.rJ1[r])];
+            const bool zero = x[j] == 0.f;
+            const int f = lut_fine(fsub(x[j], mean), lut_lo, lut_scale);
+            uint32_t e = S.lut[f / EM_SUB];
+            if (e & EM_L2) e = S.lut2[(e & (EM_L2 - 1)) * EM_SUB + (f % EM_SUB)];
+            e = zero ? (uint32_t)zid : e;
+            id[j] = (int)e;
+            slow |= (e >> 15) << j;
+            zcount += zero;
+        }
+        // phase 2: the few elements whose fine bucket holds a region boundary or a zone (one pass per thread)
+        while (slow) {
+            const int j = __ffs(slow) - 1;
+            slow &= slow - 1;
+            float xj = x[0];
+#pragma unroll
+            for (int q = 1; q < EM_PER; ++q) xj = q == j ? x[q] : xj;
+            int ej = id[0];
+#pragma unroll
+            for (int q = 1; q < EM_PER; ++q) ej = q == j ? id[q] : ej;
+            const float xc = fsub(xj, mean);
+            const int r = region_from(S.start, R, ej & (int)(EM_L2 - 1), xc);
+            int lab = S.rid[r];
+            if (lab < 0) lab = T.down[zone_argmin(xc, T.dv, T.dcn, T.down, T.rJ2[r], T.rJ1[r])];
+#pragma unroll
+            for (int q = 0; q < EM_PER; ++q) id[q] = q == j ? lab : id[q];
+        }
+        if (want_hist) {
+#pragma unroll
+            for (int j = 0; j < EM_PER; ++j)
+                if (x[j] != 0.f) atomicAdd(&S.hist[id[j]], 1u);  // NaN never gets here (rejected upstream)
+        }
+        if (INERTIA) {
+#pragma unroll
+            for (int j = 0; j < EM_PER; ++j) {
+                if (j < cnt) {
+                    // distance to the centroid in centred space, as sklearn's _inertia_dense computes it
+                    const float t = fsub(fsub(x[j], mean), ed->cfin[id[j]]);
+                    const float d2 = fmul(t, t);
+                    inert += (unsigned long long)__double2ll_rn(__dmul_rn((double)d2, inertia_scale));
                 }
-                id[j] = lab;
-                if (want_hist) atomicAdd(&S.hist[lab], 1u);
-            }
-            if (INERTIA && j < cnt) {
-                // distance to the centroid in centred space, as sklearn's _inertia_dense computes it
-                const float t = fsub(fsub(x[j], mean), ed->cfin[id[j]]);
-                const float d2 = fmul(t, t);
-                inert += (unsigned long long)__double2ll_rn(__dmul_rn((double)d2, inertia_scale));
             }
         }
         if (labels) {
@@ -181,44 +253,51 @@ __global__ void __launch_bounds__(EM_THREADS) emit_kernel(const float *__restric
             }
         }
         if (packed) {
-            // 8 codes -> `bits` bytes, little-endian bit stream
-            unsigned long long lo64 = 0, hi64 = 0;
-#pragma unroll
-            for (int j = 0; j < EM_PER; ++j) {
-                const unsigned long long v = j < cnt ? (unsigned long long)(uint32_t)id[j] : 0ull;
-                const int sh = j * bits;
-                if (sh < 64) {
-                    lo64 |= v << sh;
-                    if (sh + bits > 64) hi64 |= v >> (64 - sh);
-                } else {
-                    hi64 |= v << (sh - 64);
-                }
-            }
-            const int64_t byte0 = chunk * bits;
-            uint8_t *dst = packed + byte0;
-            const bool full = byte0 + bits <= total_bytes;
-            if (VEC && full && bits == 8) {
-                *reinterpret_cast<unsigned long long *>(dst) = lo64;
-            } else if (VEC && full && bits == 4) {
-                *reinterpret_cast<uint32_t *>(dst) = (uint32_t)lo64;
-            } else if (VEC && full && bits == 2) {
-                *reinterpret_cast<uint16_t *>(dst) = (uint16_t)lo64;
-            } else if (VEC && full && bits == 16) {
-                reinterpret_cast<unsigned long long *>(dst)[0] = lo64;
-                reinterpret_cast<unsigned long long *>(dst)[1] = hi64;
+            if (BITS == 8 && VEC && cnt == EM_PER) {
+                const uint32_t lo = (uint32_t)id[0] | ((uint32_t)id[1] << 8) | ((uint32_t)id[2] << 16) | ((uint32_t)id[3] << 24);
+                const uint32_t hi = (uint32_t)id[4] | ((uint32_t)id[5] << 8) | ((uint32_t)id[6] << 16) | ((uint32_t)id[7] << 24);
+                *reinterpret_cast<uint2 *>(packed + base) = make_uint2(lo, hi);
             } else {
-                for (int b = 0; b < bits; ++b) {
-                    if (byte0 + b < total_bytes) dst[b] = (uint8_t)(b < 8 ? (lo64 >> (8 * b)) : (hi64 >> (8 * (b - 8))));
+                // 8 codes -> `bits` bytes, little-endian bit stream
+                unsigned long long lo64 = 0, hi64 = 0;
+#pragma unroll
+                for (int j = 0; j < EM_PER; ++j) {
+                    const unsigned long long v = j < cnt ? (unsigned long long)(uint32_t)id[j] : 0ull;
+                    const int sh = j * bits;
+                    if (sh < 64) {
+                        lo64 |= v << sh;
+                        if (sh + bits > 64) hi64 |= v >> (64 - sh);
+                    } else {
+                        hi64 |= v << (sh - 64);
+                    }
+                }
+                const int64_t byte0 = chunk * bits;
+                uint8_t *dst = packed + byte0;
+                const bool full = byte0 + bits <= total_bytes;
+                if (VEC && full && bits == 8) {
+                    *reinterpret_cast<unsigned long long *>(dst) = lo64;
+                } else if (VEC && full && bits == 4) {
+                    *reinterpret_cast<uint32_t *>(dst) = (uint32_t)lo64;
+                } else if (VEC && full && bits == 2) {
+                    *reinterpret_cast<uint16_t *>(dst) = (uint16_t)lo64;
+                } else if (VEC && full && bits == 16) {
+                    reinterpret_cast<unsigned long long *>(dst)[0] = lo64;
+                    reinterpret_cast<unsigned long long *>(dst)[1] = hi64;
+                } else {
+                    for (int b = 0; b < bits; ++b) {
+                        if (byte0 + b < total_bytes) dst[b] = (uint8_t)(b < 8 ? (lo64 >> (8 * b)) : (hi64 >> (8 * (b - 8))));
+                    }
                 }
             }
         }
     }
-    (void)zval;
     if (INERTIA) {
         inert = warp_sum_ull(inert);
         if (lane_id() == 0 && inert) atomicAdd(&ed->inertia_q, inert);
     }
     if (want_hist) {
+        // the thread that handled the last chunk counted its padding as zeros: take it back
+        if ((n_chunks - 1) % stride == (int64_t)blockIdx.x * EM_THREADS + threadIdx.x) zcount -= (unsigned int)(n_chunks * EM_PER - n);
         unsigned long long z = warp_sum_ull((unsigned long long)zcount);
         if (lane_id() == 0) S.red[warp_id()] = z;
         __syncthreads();
@@ -230,6 +309,19 @@ __global__ void __launch_bounds__(EM_THREADS) emit_kernel(const float *__restric
         for (int i = threadIdx.x; i < k; i += EM_THREADS)
             if (S.hist[i]) atomicAdd(&ed->hist[i], (unsigned long long)S.hist[i]);
     }
+}
+
+template <bool VEC, bool INERTIA, int BITS>
+static void emit_launch(nnc_ctx *ctx, int grid, const float *d_w, int64_t n, EmitDevice *ed, float mean, double inertia_scale,
+                        int32_t *d_labels, float *d_ris, uint8_t *d_packed, int bits, int want_hist) {
+    static bool configured = false;
+    if (!configured) {
+        NNC_CUDA(cudaFuncSetAttribute(emit_kernel<VEC, INERTIA, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(EmitSmem)));
+        configured = true;
+    }
+    NNC_LAUNCH(ctx, (emit_kernel<VEC, INERTIA, BITS>), grid, EM_THREADS, sizeof(EmitSmem), d_w, n, ed, mean, inertia_scale,
+               d_labels, d_ris, d_packed, bits, want_hist);
 }
 
 void emit_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *h_centred, const float *h_centred_final, int k,
@@ -273,7 +365,7 @@ void emit_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *h_centr
         xhi = xabs;
     }
     volatile float span = xhi - xlo;
-    float lut_scale = span > 0.f ? (float)((double)EM_LUT / (double)span * (1.0 - 1e-6)) : 0.f;
+    float lut_scale = span > 0.f ? (float)((double)EM_FINE / (double)span * (1.0 - 1e-6)) : 0.f;
     if (!isfinite(lut_scale)) lut_scale = 0.f;
     NNC_LAUNCH(ctx, emit_table_kernel, 1, TB_THREADS, 0, ed, k, xabs, mean, xlo, lut_scale);
     const bool vec = ((reinterpret_cast<uintptr_t>(d_w) & 15u) == 0) &&
@@ -281,29 +373,19 @@ void emit_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *h_centr
                      (!d_ris || (reinterpret_cast<uintptr_t>(d_ris) & 15u) == 0) &&
                      (!d_packed || (reinterpret_cast<uintptr_t>(d_packed) & 15u) == 0);
     const int64_t n_chunks = (n + EM_PER - 1) / EM_PER;
-    const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 4, (n_chunks + EM_THREADS - 1) / EM_THREADS);
-    const size_t smem = sizeof(EmitSmem);
+    const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 2, (n_chunks + EM_THREADS - 1) / EM_THREADS);
     const int want_hist = h_hist ? 1 : 0;
-    static bool configured = false;
-    if (!configured) {
-        NNC_CUDA(cudaFuncSetAttribute(emit_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NNC_CUDA(cudaFuncSetAttribute(emit_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NNC_CUDA(cudaFuncSetAttribute(emit_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NNC_CUDA(cudaFuncSetAttribute(emit_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    const bool b8 = bits == 8 && d_packed;
     if (vec && h_inertia)
-        NNC_LAUNCH(ctx, (emit_kernel<true, true>), grid, EM_THREADS, smem, d_w, n, ed, mean, inertia_scale, d_labels, d_ris,
-                   d_packed, bits, want_hist);
+        emit_launch<true, true, 0>(ctx, grid, d_w, n, ed, mean, inertia_scale, d_labels, d_ris, d_packed, bits, want_hist);
+    else if (vec && b8)
+        emit_launch<true, false, 8>(ctx, grid, d_w, n, ed, mean, inertia_scale, d_labels, d_ris, d_packed, bits, want_hist);
     else if (vec)
-        NNC_LAUNCH(ctx, (emit_kernel<true, false>), grid, EM_THREADS, smem, d_w, n, ed, mean, inertia_scale, d_labels, d_ris,
-                   d_packed, bits, want_hist);
+        emit_launch<true, false, 0>(ctx, grid, d_w, n, ed, mean, inertia_scale, d_labels, d_ris, d_packed, bits, want_hist);
     else if (h_inertia)
-        NNC_LAUNCH(ctx, (emit_kernel<false, true>), grid, EM_THREADS, smem, d_w, n, ed, mean, inertia_scale, d_labels, d_ris,
-                   d_packed, bits, want_hist);
+        emit_launch<false, true, 0>(ctx, grid, d_w, n, ed, mean, inertia_scale, d_labels, d_ris, d_packed, bits, want_hist);
     else
-        NNC_LAUNCH(ctx, (emit_kernel<false, false>), grid, EM_THREADS, smem, d_w, n, ed, mean, inertia_scale, d_labels, d_ris,
-                   d_packed, bits, want_hist);
+        emit_launch<false, false, 0>(ctx, grid, d_w, n, ed, mean, inertia_scale, d_labels, d_ris, d_packed, bits, want_hist);
     if (h_hist || h_inertia) {
         std::vector<unsigned long long> hh(k + 1);
         if (h_hist) NNC_CUDA(cudaMemcpyAsync(hh.data(), ed->hist, sizeof(unsigned long long) * k, cudaMemcpyDeviceToHost, ctx->stream));

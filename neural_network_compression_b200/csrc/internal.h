@@ -189,8 +189,9 @@ struct LloydHandle {
     void *d_ptile = nullptr, *d_samp = nullptr;
     int64_t n_tiles = 0;
 };
+// h_hist (optional, k entries): code histogram of the final labelling, counted on the sorted survivors
 LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max_iter, double tol_rel,
-                      float *h_centred_final, float *h_centred_emit);
+                      float *h_centred_final, float *h_centred_emit, int64_t *h_hist);
 
 // emit.cu : final E-step over the tensor in original order
 // h_centred: centroids the labels are taken against; h_centred_final (optional): final centroids (codebook

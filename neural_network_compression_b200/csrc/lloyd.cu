@@ -50,6 +50,8 @@ struct LloydDevice : LloydHeader {
     // centroids (centred space) by cluster id
     float c[TB_KMAX];
     float c_emit[TB_KMAX];
+    float c_save[TB_KMAX];
+    long long hist[TB_KMAX];  // code histogram of the final labelling (ll_count_kernel)
     RegionTable tab;
     long long rpos[2 * TB_KMAX + 2];
     long long rsum[2 * TB_KMAX + 2];
@@ -703,11 +705,46 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
     }
 }
 
+// ---- final labelling histogram ---------------------------------------------------------------------
+// After the loop has stopped, the labels the emission pass will produce are those of the E-step against c_emit.
+// Their per-cluster counts follow from one more table / search / zone round on the sorted survivors -- far
+// cheaper than histogramming n labels in the streaming emission kernel.
+__global__ void __launch_bounds__(TB_KMAX) ll_final_begin_kernel(LloydDevice *st) {
+    const int tid = threadIdx.x;
+    if (tid < st->k) {
+        st->c_save[tid] = st->c[tid];
+        st->c[tid] = st->c_emit[tid];
+        st->hist[tid] = 0;
+    }
+    __syncthreads();
+    if (tid == 0) st->done = 0;
+}
+
+__global__ void __launch_bounds__(TB_THREADS) ll_count_kernel(LloydDevice *st) {
+    __shared__ long long Wd[TB_KMAX];
+    const RegionTable &T = st->tab;
+    const int tid = threadIdx.x, k = st->k, m = T.m, R = T.R;
+    if (tid < m) Wd[tid] = st->zW[tid];
+    __syncthreads();
+    for (int r = tid; r < R; r += TB_THREADS) {
+        if (T.rJ1[r] != T.rJ2[r]) continue;
+        const long long c = st->rpos[r + 1] - st->rpos[r];
+        if (c > 0) Wd[T.rJ1[r]] += c;  // (J, J) occurs in at most one region
+    }
+    __syncthreads();
+    if (tid == 0 && st->n0 > 0) Wd[zone_argmin(fsub(0.f, st->mean), T.dv, T.dcn, T.down, 0, m - 1)] += st->n0;
+    __syncthreads();
+    if (tid < m) st->hist[T.down[tid]] = Wd[tid];
+    if (tid < k) st->c[tid] = st->c_save[tid];
+    __syncthreads();
+    if (tid == 0) st->done = 1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------
 LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max_iter, double tol_rel,
-                      float *h_centred_final, float *h_centred_emit) {
+                      float *h_centred_final, float *h_centred_emit, int64_t *h_hist) {
     const int k = h.k;
     if (k < 1 || k > TB_KMAX) NNC_FAIL(NNC_ERR_UNSUPPORTED, "k-means: k = %d outside [1, %d]", k, TB_KMAX);
     static bool configured = false;
@@ -781,6 +818,15 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
     NNC_CUDA(cudaMemcpyAsync(h_centred_emit, st->c_emit, sizeof(float) * k, cudaMemcpyDeviceToHost, ctx->stream));
     float tol_h = 0.f;
     NNC_CUDA(cudaMemcpyAsync(&tol_h, &st->tol, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_hist) {
+        NNC_LAUNCH(ctx, ll_final_begin_kernel, 1, TB_KMAX, 0, st);
+        NNC_LAUNCH(ctx, ll_table_kernel, 1, TB_THREADS, 0, st);
+        NNC_LAUNCH(ctx, ll_search_kernel, search_grid, 256, 0, st, h.d_sorted, samp, ptile);
+        NNC_LAUNCH(ctx, ll_zone_kernel, zone_grid, 256, 0, st, h.d_sorted);
+        NNC_LAUNCH(ctx, ll_count_kernel, 1, TB_THREADS, 0, st);
+        static_assert(sizeof(long long) == sizeof(int64_t), "histogram element size");
+        NNC_CUDA(cudaMemcpyAsync(h_hist, st->hist, sizeof(int64_t) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     NNC_CUDA(cudaStreamSynchronize(ctx->stream));
     prof_mark(ctx, "lloyd_iters");
     if (getenv("NNC_LLOYD_LOG")) {

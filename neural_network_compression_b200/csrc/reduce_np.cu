@@ -28,7 +28,6 @@ namespace nnc {
 
 constexpr int NP_TILE_MAX = 4096;
 constexpr int NP_THREADS = 256;
-constexpr int NP_HEAP = 128;  // heap slots of a tile's sub-tree (depth <= 6)
 
 static inline int64_t half_down(int64_t s) {
     int64_t n2 = s / 2;
@@ -74,45 +73,46 @@ struct BlockAux {  // shared scratch for visitor epilogues
     uint32_t o[4][NP_THREADS / 32];
 };
 
-// pass 1 of pruning / nnc_stats: term = x; side: fp64 sum, sum of squares, non-finite count.
+// pass 1 of pruning / nnc_stats: term = x; side: sum and sum of squares as an ESTIMATE of the std (float32 over
+// the 16 elements a thread sees of a tile, float64 across tiles: relative error ~1e-7, the speculation band is
+// 1.5e-5 wide).
 struct VisitStats {
     DevScalars *sc;
     double s = 0.0, s2 = 0.0;
-    unsigned long long bad = 0;
+    float ts = 0.f, ts2 = 0.f;
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ float4 load4(const float *p) const { return ld_stream_f4(p); }
     __device__ __forceinline__ float load1(const float *p) const { return ld_stream_f1(p); }
     __device__ __forceinline__ float one(float x) {
-        double xd = (double)x;
-        s += xd;
-        s2 = fma(xd, xd, s2);
-        bad += !isfinite(x);
+        ts += x;
+        ts2 = fmaf(x, x, ts2);
         return x;
     }
     __device__ __forceinline__ float4 visit4(int64_t, const float *, float4 x) {
         return make_float4(one(x.x), one(x.y), one(x.z), one(x.w));
     }
     __device__ __forceinline__ float visit1(int64_t, const float *, float x) { return one(x); }
+    __device__ __forceinline__ void end_tile() {
+        s += (double)ts;
+        s2 += (double)ts2;
+        ts = 0.f;
+        ts2 = 0.f;
+    }
     __device__ void finish(BlockAux &aux) {
         double a = warp_sum_d(s), b = warp_sum_d(s2);
-        unsigned long long c = warp_sum_ull(bad);
         if (lane_id() == 0) {
             aux.d[0][warp_id()] = a;
             aux.d[1][warp_id()] = b;
-            aux.u[0][warp_id()] = c;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
             double ta = 0, tb = 0;
-            unsigned long long tc = 0;
             for (int i = 0; i < NP_THREADS / 32; i++) {
                 ta += aux.d[0][i];
                 tb += aux.d[1][i];
-                tc += aux.u[0][i];
             }
             atomicAdd(&sc->sum_d, ta);
             atomicAdd(&sc->sumsq_d, tb);
-            if (tc) atomicAdd(&sc->n_nonfinite, tc);
         }
     }
 };
@@ -132,6 +132,7 @@ struct VisitCenSq {
         return make_float4(one(x.x), one(x.y), one(x.z), one(x.w));
     }
     __device__ __forceinline__ float visit1(int64_t, const float *, float x) { return one(x); }
+    __device__ __forceinline__ void end_tile() {}
     __device__ void finish(BlockAux &) {}
 };
 
@@ -204,6 +205,7 @@ struct VisitCenSqApply {
         mask[g] = (uint8_t)m;
         return r;
     }
+    __device__ __forceinline__ void end_tile() {}
     __device__ void finish(BlockAux &aux) {
         unsigned long long c = warp_sum_ull(pruned);
         if (lane_id() == 0) aux.u[0][warp_id()] = c;
@@ -239,6 +241,7 @@ struct VisitQuant {
         return make_float4(one(x.x), one(x.y), one(x.z), one(x.w));
     }
     __device__ __forceinline__ float visit1(int64_t, const float *, float x) { return one(x); }
+    __device__ __forceinline__ void end_tile() {}
     __device__ void finish(BlockAux &aux) {
         // a thread sees at most 2^32 / 4 elements only for absurd grids; the per-thread count fits 32 bits
         float a = warp_min_f(mn), b = warp_max_f(mx);
@@ -276,110 +279,177 @@ struct VisitQuant {
 };
 
 // ---------------------------------------------------------------------------------------------
-// The tree kernel: one tile (= one depth-`depth` subtree of NumPy's recursion) per loop iteration.
+// The tree kernel: one tile (= one depth-`depth` subtree of NumPy's recursion, 2041..4096 elements) per loop
+// iteration.
+//   stage   coalesced 128-bit loads, the visitor's term of every element goes to shared memory; the tile is
+//           stored with 8 floats of padding per 128 so that the strided leaf reads below are conflict free
+//   leaves  8 lanes per depth-5 node of the tile's sub-tree: NumPy's 8 strided accumulators per leaf (a node
+//           that is still > 128 elements splits once more into two leaves)
+//   fold    warp 0 folds the <= 32 node values up the sub-tree while the other warps stage the next tile
 // ---------------------------------------------------------------------------------------------
+constexpr int NP_TILE_SMEM = NP_TILE_MAX + (NP_TILE_MAX >> 7) * 8 + 16;
+
+__device__ __forceinline__ int np_pad(int e) { return e + ((e >> 7) << 3); }
+
+// sum of the leaf [o, o + s) of the staged tile in NumPy's order; called by the 8 lanes j = 0..7 of a group,
+// every lane returns the leaf's value.  s <= 128, o a multiple of 8.
+__device__ __forceinline__ float np_leaf_sum(const float *tile, int o, int s, int j) {
+    float r = 0.f;
+    const int rows = s >> 3;  // full rows of 8 consecutive elements
+    // row i lives at pA[8 i] before the leaf crosses a multiple of 128 and at pA[8 i + 8] after it (the padding
+    // grows by 8 there; a row never straddles the crossing because o is a multiple of 8)
+    const float *pA = tile + np_pad(o + j);
+    const int istar = (128 - (o & 127)) >> 3;
+    if (rows > 0) {
+        r = pA[0];
+#pragma unroll
+        for (int i = 1; i < 16; ++i) {
+            const float *q = i >= istar ? pA + 8 : pA;
+            if (i < rows) r = fadd(r, q[8 * i]);
+        }
+    }
+    // the 8 lanes of the group only: groups of one warp may be in different branches
+    const unsigned gmask = 0xffu << (threadIdx.x & 24);
+    r = fadd(r, __shfl_xor_sync(gmask, r, 1));
+    r = fadd(r, __shfl_xor_sync(gmask, r, 2));
+    r = fadd(r, __shfl_xor_sync(gmask, r, 4));
+    if (rows > 0) {
+        for (int i = rows << 3; i < s; ++i) r = fadd(r, tile[np_pad(o + i)]);
+    } else {  // n < 8: plain sequential sum starting from 0
+        r = 0.f;
+        for (int i = 0; i < s; ++i) r = fadd(r, tile[np_pad(o + i)]);
+    }
+    return r;
+}
+
+// Per-tile description of the tree (it only depends on n), filled once per reduction by one thread per tile:
+// offset and size of the tile, for each of the 32 depth-5 path groups the node it sums
+//   desc = o | s << 13 | h << 21 | mine << 27     (o, s: offset / size inside the tile; h: heap slot of the value;
+//                                                   mine: this group is the one that stores it)
+// and the bit mask of the internal heap nodes h < 32 (size > 128: value = left + right).
+struct NpTileDesc {
+    long long off;
+    int sz;
+    uint32_t internal;
+    uint32_t grp[32];
+};
+
+__global__ void np_tiles_kernel(int64_t n, int depth, NpTileDesc *desc) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (1u << depth)) return;
+    int64_t off;
+    int sz;
+    np_tile_root(n, depth, t, off, sz);
+    NpTileDesc d;
+    d.off = off;
+    d.sz = sz;
+    d.internal = 0;
+    for (int g = 0; g < 32; ++g) {
+        int o = 0, s = sz, h = 1;
+        bool mine = true, leaf = false;
+        for (int lvl = 4; lvl >= 0; --lvl) {
+            if (!leaf && s > 128) {
+                d.internal |= 1u << h;
+                int n2 = s >> 1;
+                n2 -= n2 & 7;
+                if ((g >> lvl) & 1) {
+                    o += n2;
+                    s -= n2;
+                    h = 2 * h + 1;
+                } else {
+                    s = n2;
+                    h = 2 * h;
+                }
+            } else {
+                leaf = true;  // h stays the leaf's own heap slot; it belongs to its leftmost descendant group
+                if ((g >> lvl) & 1) mine = false;
+            }
+        }
+        d.grp[g] = (uint32_t)o | ((uint32_t)s << 13) | ((uint32_t)h << 21) | ((mine ? 1u : 0u) << 27);
+    }
+    desc[t] = d;
+}
+
 template <class V>
-__global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, int64_t n, int depth, int vec_ok,
-                                                             float *partials, V v) {
-    __shared__ __align__(16) float tile[NP_TILE_MAX + 8];
-    __shared__ float heap_val[NP_HEAP];
-    __shared__ short node_off[NP_HEAP];
-    __shared__ short node_sz[NP_HEAP];
-    __shared__ unsigned char leaf_list[NP_HEAP];
-    __shared__ int n_leaves;
+__global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, int depth, int vec_ok,
+                                                             const NpTileDesc *__restrict__ desc, float *partials, V v) {
+    __shared__ __align__(16) float tile[NP_TILE_SMEM];
+    __shared__ float heap_val[2][64];
     __shared__ BlockAux aux;
 
     v.begin();
     const uint32_t num_tiles = 1u << depth;
-    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int64_t off;
-        int sz;
-        np_tile_root(n, depth, t, off, sz);
-        if (threadIdx.x == 0) n_leaves = 0;
-        // ---- load + visit: global -> terms in shared memory
+    const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;
+    int buf = 0;
+    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, buf ^= 1) {
+        const int64_t off = desc[t].off;
+        const int sz = desc[t].sz;
+        const uint32_t gd = desc[t].grp[grp];
+        // ---- stage + visit: global -> terms in shared memory
         const float *src = a + off;
         if (vec_ok) {
-            int nvec = sz >> 2;
-            for (int i = threadIdx.x; i < nvec; i += NP_THREADS) {
-                float4 x = v.load4(src + 4 * i);
-                float4 r = v.visit4(off + 4 * i, src + 4 * i, x);
-                *reinterpret_cast<float4 *>(&tile[4 * i]) = r;
+            const int nvec = sz >> 2;
+            constexpr int NV = NP_TILE_MAX / 4 / NP_THREADS;
+            float4 x[NV];
+#pragma unroll
+            for (int r = 0; r < NV; ++r) {  // all loads first: the in-place visitor's stores would otherwise fence them
+                const int i = r * NP_THREADS + threadIdx.x;
+                if (i < nvec) x[r] = v.load4(src + 4 * i);
             }
-            for (int i = (nvec << 2) + threadIdx.x; i < sz; i += NP_THREADS) tile[i] = v.visit1(off + i, src + i, v.load1(src + i));
+#pragma unroll
+            for (int r = 0; r < NV; ++r) {
+                const int i = r * NP_THREADS + threadIdx.x;
+                if (i < nvec) {
+                    float4 y = v.visit4(off + 4 * i, src + 4 * i, x[r]);
+                    *reinterpret_cast<float4 *>(&tile[np_pad(4 * i)]) = y;
+                }
+            }
+            for (int i = (nvec << 2) + threadIdx.x; i < sz; i += NP_THREADS)
+                tile[np_pad(i)] = v.visit1(off + i, src + i, v.load1(src + i));
         } else {
-            for (int i = threadIdx.x; i < sz; i += NP_THREADS) tile[i] = v.visit1(off + i, src + i, v.load1(src + i));
+            for (int i = threadIdx.x; i < sz; i += NP_THREADS) tile[np_pad(i)] = v.visit1(off + i, src + i, v.load1(src + i));
         }
-        __syncthreads();  // n_leaves = 0 visible; tile complete
-        // ---- node table of this tile's sub-tree (heap indexing, root = 1)
+        v.end_tile();
+        __syncthreads();  // tile complete (also: warp 0 finished folding the tile before the previous one)
+        // ---- leaves: the 8 lanes of group `grp` sum the node described by gd
         {
-            int h = threadIdx.x;
-            if (h >= 1 && h < NP_HEAP) {
-                int e = 31 - __clz(h);
-                int o = 0, s = sz;
-                bool ok = true;
-                for (int lvl = e - 1; lvl >= 0; --lvl) {
-                    if (s <= 128) {
-                        ok = false;
-                        break;
-                    }
-                    int n2 = s / 2;
-                    n2 -= n2 % 8;
-                    if ((h >> lvl) & 1) {
-                        o += n2;
-                        s -= n2;
-                    } else {
-                        s = n2;
-                    }
-                }
-                node_off[h] = (short)o;
-                node_sz[h] = ok ? (short)s : (short)0;
-                if (ok && s <= 128) {
-                    int slot = atomicAdd(&n_leaves, 1);
-                    leaf_list[slot] = (unsigned char)h;
-                }
+            const int o = gd & 8191, s = (gd >> 13) & 255, h = (gd >> 21) & 63;
+            float val;
+            if (s == 128 && (o & 127) == 0) {  // the common case: a full, aligned leaf -- no address arithmetic
+                const float *p = tile + np_pad(o) + j;
+                val = p[0];
+#pragma unroll
+                for (int i = 1; i < 16; ++i) val = fadd(val, p[8 * i]);
+                const unsigned gmask = 0xffu << (threadIdx.x & 24);
+                val = fadd(val, __shfl_xor_sync(gmask, val, 1));
+                val = fadd(val, __shfl_xor_sync(gmask, val, 2));
+                val = fadd(val, __shfl_xor_sync(gmask, val, 4));
+            } else if (s > 128) {  // a depth-5 node that splits once more: two leaves
+                int n2 = s >> 1;
+                n2 -= n2 & 7;
+                const float l = np_leaf_sum(tile, o, n2, j);
+                const float r = np_leaf_sum(tile, o + n2, s - n2, j);
+                val = fadd(l, r);
+            } else {
+                val = np_leaf_sum(tile, o, s, j);
             }
+            if (j == 0 && (gd >> 27)) heap_val[buf][h] = val;
         }
-        __syncthreads();
-        // ---- leaves: 8 lanes per leaf, NumPy's 8 strided accumulators
-        {
-            const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;
-            const int nl = n_leaves;
-            for (int base = 0; base < nl; base += NP_THREADS / 8) {
-                int li = base + grp;
-                bool valid = li < nl;
-                int h = valid ? leaf_list[li] : 0;
-                int o = valid ? node_off[h] : 0;
-                int s = valid ? node_sz[h] : 0;
-                float r = 0.f;
-                if (s >= 8) {
-                    int lim = s - (s & 7);
-                    r = tile[o + j];
-                    for (int i = 8; i < lim; i += 8) r = fadd(r, tile[o + i + j]);
-                }
-                r = fadd(r, __shfl_xor_sync(0xffffffffu, r, 1));
-                r = fadd(r, __shfl_xor_sync(0xffffffffu, r, 2));
-                r = fadd(r, __shfl_xor_sync(0xffffffffu, r, 4));
-                if (valid && j == 0) {
-                    if (s >= 8) {
-                        for (int i = s - (s & 7); i < s; ++i) r = fadd(r, tile[o + i]);
-                    } else {  // n < 8: plain sequential sum starting from 0
-                        r = 0.f;
-                        for (int i = 0; i < s; ++i) r = fadd(r, tile[o + i]);
-                    }
-                    heap_val[h] = r;
-                }
+        __syncthreads();  // node values visible; the tile buffer may be overwritten
+        // ---- fold (warp 0): internal nodes take left + right, level by level
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            const uint32_t internal = desc[t].internal;
+#pragma unroll
+            for (int lvl = 4; lvl >= 0; --lvl) {
+                const int h = (1 << lvl) + lane;
+                if (lane < (1 << lvl) && ((internal >> h) & 1u)) heap_val[buf][h] = fadd(heap_val[buf][2 * h], heap_val[buf][2 * h + 1]);
+                __syncwarp();
             }
+            if (lane == 0) partials[t] = heap_val[buf][1];
         }
-        __syncthreads();
-        // ---- fold the sub-tree bottom-up
-        for (int lvl = 5; lvl >= 0; --lvl) {
-            int h = threadIdx.x;
-            if (h >= (1 << lvl) && h < (2 << lvl) && node_sz[h] > 128) heap_val[h] = fadd(heap_val[2 * h], heap_val[2 * h + 1]);
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) partials[t] = heap_val[1];
-        __syncthreads();  // tile / tables are reused by the next iteration
     }
+    __syncthreads();
     v.finish(aux);
 }
 
@@ -548,7 +618,9 @@ template <class V>
 static void run_tree(nnc_ctx *ctx, const float *d_w, int64_t n, V v, const FinArgs &fa) {
     NpPlan p = np_plan(n);
     float *partials = arena_alloc_t<float>(ctx, 2 * (size_t)p.num_tiles);
-    NNC_LAUNCH(ctx, np_tree_kernel<V>, tree_grid(ctx, p), NP_THREADS, 0, d_w, n, p.depth, aligned16(d_w) ? 1 : 0, partials,
+    NpTileDesc *desc = arena_alloc_t<NpTileDesc>(ctx, p.num_tiles);
+    NNC_LAUNCH(ctx, np_tiles_kernel, (p.num_tiles + 127) / 128, 128, 0, n, p.depth, desc);
+    NNC_LAUNCH(ctx, np_tree_kernel<V>, tree_grid(ctx, p), NP_THREADS, 0, d_w, p.depth, aligned16(d_w) ? 1 : 0, desc, partials,
                v);
     NNC_LAUNCH(ctx, np_final_kernel, 1, 1024, 0, partials, p.num_tiles, ctx->d_scal, fa);
 }

@@ -149,12 +149,12 @@ void hist_edges_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *h
 // ---------------------------------------------------------------------------------------------
 // order-preserving non-zero compaction, single pass, decoupled look-back
 //
-// A tile is 8192 consecutive elements; warp w of the CTA owns elements [512 w, 512 (w+1)) of it as 4 rows of
+// A tile is 4096 consecutive elements; warp w of the CTA owns elements [512 w, 512 (w+1)) of it as 4 rows of
 // 128 (one float4 per lane and row), so survivors keep their order: (row, lane, component) is element order.
-constexpr int CP_THREADS = 512;
+constexpr int CP_THREADS = 256;
 constexpr int CP_WARPS = CP_THREADS / 32;
 constexpr int CP_ROWS = 4;
-constexpr int CP_TILE = CP_THREADS * CP_ROWS * 4;  // 8192 elements
+constexpr int CP_TILE = CP_THREADS * CP_ROWS * 4;  // 4096 elements
 constexpr unsigned long long CP_FLAG_AGG = 1ull << 62;
 constexpr unsigned long long CP_FLAG_PFX = 2ull << 62;
 constexpr unsigned long long CP_VAL_MASK = (1ull << 62) - 1;
@@ -189,7 +189,7 @@ __device__ __forceinline__ unsigned long long cp_lookback(unsigned long long *st
     return excl;
 }
 
-__global__ void __launch_bounds__(CP_THREADS, 2) compact_kernel(const float *w, int64_t n, int vec_ok, float *out,
+__global__ void __launch_bounds__(CP_THREADS, 5) compact_kernel(const float *w, int64_t n, int vec_ok, float *out,
                                                                 unsigned long long *state, unsigned int *ticket,
                                                                 unsigned long long *total_out) {
     __shared__ unsigned int s_tile;
@@ -265,7 +265,7 @@ int64_t compact_ordered_device(nnc_ctx *ctx, const float *d_w, int64_t n, float 
     NNC_CUDA(cudaMemsetAsync(state, 0, sizeof(unsigned long long) * (n_tiles + 2), ctx->stream));
     unsigned int *ticket = reinterpret_cast<unsigned int *>(state + n_tiles);
     unsigned long long *total = state + n_tiles + 1;
-    int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 2, n_tiles);
+    int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 5, n_tiles);
     int vec_ok = (reinterpret_cast<uintptr_t>(d_w) & 15u) == 0;
     NNC_LAUNCH(ctx, compact_kernel, grid, CP_THREADS, 0, d_w, n, vec_ok, d_out, state, ticket, total);
     unsigned long long h = 0;
