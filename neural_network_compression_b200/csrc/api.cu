@@ -591,7 +591,7 @@ int nnc_kmeans1d_f32(nnc_ctx *ctx, const float *w, int64_t n, const float *init,
     const float *d_w = static_cast<const float *>(sw.dev);
     prof_mark(ctx, "h2d");
     // 1. mean (NumPy pairwise), min/max, survivor count
-    quant_prologue(ctx, d_w, n, nullptr);
+    const QuantPrologue qp = quant_prologue(ctx, d_w, n);
     read_scalars(ctx);
     prof_mark(ctx, "prologue");
     const DevScalars sc = *ctx->h_scal;
@@ -602,8 +602,7 @@ int nnc_kmeans1d_f32(nnc_ctx *ctx, const float *w, int64_t n, const float *init,
     float *buf_b = arena_alloc_t<float>(ctx, (size_t)std::max<int64_t>(n_nz, 1));
     const float *d_sorted = buf_a;
     if (n_nz > 0) {
-        int64_t c = compact_ordered_device(ctx, d_w, n, buf_a);
-        if (c != n_nz) NNC_FAIL(NNC_ERR_INTERNAL, "compaction kept %lld of %lld survivors", (long long)c, (long long)n_nz);
+        compact_tiles_device(ctx, d_w, qp, buf_a);
         prof_mark(ctx, "compact");
         d_sorted = radix_sort_f32(ctx, buf_a, buf_b, n_nz, sc.amin_nz_m1 + 1u, sc.amax_bits);
         prof_mark(ctx, "sort");

@@ -77,6 +77,7 @@ struct BlockAux {  // shared scratch for visitor epilogues
 // the 16 elements a thread sees of a tile, float64 across tiles: relative error ~1e-7, the speculation band is
 // 1.5e-5 wide).
 struct VisitStats {
+    static constexpr bool kTileCount = false;
     DevScalars *sc;
     double s = 0.0, s2 = 0.0;
     float ts = 0.f, ts2 = 0.f;
@@ -119,6 +120,7 @@ struct VisitStats {
 
 // plain centred squares (nnc_stats second pass, non-speculative prune fallback)
 struct VisitCenSq {
+    static constexpr bool kTileCount = false;
     DevScalars *sc;
     float mean;
     __device__ __forceinline__ void begin() { mean = sc->mean; }
@@ -138,6 +140,7 @@ struct VisitCenSq {
 
 // pass 2 of pruning: centred squares + speculative apply (see file header).
 struct VisitCenSqApply {
+    static constexpr bool kTileCount = false;
     DevScalars *sc;
     float *w;            // in place
     uint8_t *mask;
@@ -221,10 +224,17 @@ struct VisitCenSqApply {
 // k-means prologue: term = x (-> mean); side: min / max, non-zero count, range of |x| bit patterns over the
 // non-zero elements (the radix-sort key range), non-finite detection (|x| bits >= 0x7f800000).
 struct VisitQuant {
+    static constexpr bool kTileCount = true;  // the kernel also records the non-zero count of every tile
     DevScalars *sc;
+    unsigned int *tile_counts;
     float mn = INFINITY, mx = -INFINITY;
     uint32_t amax = 0u, amin_m1 = 0xffffffffu;
-    unsigned int nz = 0;
+    unsigned int nz = 0, nz_before = 0;
+    __device__ __forceinline__ unsigned int take_tile_count() {
+        const unsigned int c = nz - nz_before;
+        nz_before = nz;
+        return c;
+    }
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ float4 load4(const float *p) const { return ld_stream_f4(p); }
     __device__ __forceinline__ float load1(const float *p) const { return ld_stream_f1(p); }
@@ -375,9 +385,14 @@ __global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, int
                                                              const NpTileDesc *__restrict__ desc, float *partials, V v) {
     __shared__ __align__(16) float tile[NP_TILE_SMEM];
     __shared__ float heap_val[2][64];
+    __shared__ unsigned int s_cnt[2];
     __shared__ BlockAux aux;
 
     v.begin();
+    if (V::kTileCount) {
+        if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+    }
     const uint32_t num_tiles = 1u << depth;
     const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;
     int buf = 0;
@@ -410,6 +425,10 @@ __global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, int
             for (int i = threadIdx.x; i < sz; i += NP_THREADS) tile[np_pad(i)] = v.visit1(off + i, src + i, v.load1(src + i));
         }
         v.end_tile();
+        if constexpr (V::kTileCount) {
+            const unsigned int c = (unsigned int)warp_sum_i((int)v.take_tile_count());
+            if (lane_id() == 0 && c) atomicAdd(&s_cnt[buf], c);
+        }
         __syncthreads();  // tile complete (also: warp 0 finished folding the tile before the previous one)
         // ---- leaves: the 8 lanes of group `grp` sum the node described by gd
         {
@@ -447,6 +466,12 @@ __global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, int
                 __syncwarp();
             }
             if (lane == 0) partials[t] = heap_val[buf][1];
+        }
+        if constexpr (V::kTileCount) {
+            if (threadIdx.x == 64) {  // s_cnt[buf] is next touched two iterations (two barriers) from here
+                v.tile_counts[t] = s_cnt[buf];
+                s_cnt[buf] = 0;
+            }
         }
     }
     __syncthreads();
@@ -615,7 +640,7 @@ static int tree_grid(nnc_ctx *ctx, const NpPlan &p) {
 }
 
 template <class V>
-static void run_tree(nnc_ctx *ctx, const float *d_w, int64_t n, V v, const FinArgs &fa) {
+static NpTileDesc *run_tree(nnc_ctx *ctx, const float *d_w, int64_t n, V v, const FinArgs &fa) {
     NpPlan p = np_plan(n);
     float *partials = arena_alloc_t<float>(ctx, 2 * (size_t)p.num_tiles);
     NpTileDesc *desc = arena_alloc_t<NpTileDesc>(ctx, p.num_tiles);
@@ -623,6 +648,7 @@ static void run_tree(nnc_ctx *ctx, const float *d_w, int64_t n, V v, const FinAr
     NNC_LAUNCH(ctx, np_tree_kernel<V>, tree_grid(ctx, p), NP_THREADS, 0, d_w, p.depth, aligned16(d_w) ? 1 : 0, desc, partials,
                v);
     NNC_LAUNCH(ctx, np_final_kernel, 1, 1024, 0, partials, p.num_tiles, ctx->d_scal, fa);
+    return desc;
 }
 
 static void clear_scalars(nnc_ctx *ctx) {
@@ -646,11 +672,117 @@ void np_stats(nnc_ctx *ctx, const float *d_w, int64_t n) {
     run_tree(ctx, d_w, n, v2, FinArgs{FIN_VAR, n, 0.0, 0, 1});
 }
 
-void quant_prologue(nnc_ctx *ctx, const float *d_w, int64_t n, float *) {
+QuantPrologue quant_prologue(nnc_ctx *ctx, const float *d_w, int64_t n) {
     clear_scalars(ctx);
+    QuantPrologue q;
+    q.num_tiles = np_plan(n).num_tiles;
+    q.tile_counts = arena_alloc_t<unsigned int>(ctx, q.num_tiles);
     VisitQuant v;
     v.sc = ctx->d_scal;
-    run_tree(ctx, d_w, n, v, FinArgs{FIN_MEAN, n, 0.0, 0, 1});
+    v.tile_counts = q.tile_counts;
+    q.tile_desc = run_tree(ctx, d_w, n, v, FinArgs{FIN_MEAN, n, 0.0, 0, 1});
+    return q;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Survivor compaction over the tiles of the prologue: the per-tile non-zero counts are already known, so the tile
+// bases are one small scan and the scatter is a pure streaming pass (no inter-CTA dependency).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const unsigned int *counts, uint32_t num_tiles, unsigned long long *base) {
+    __shared__ unsigned long long s_warp[32];
+    const uint32_t per = (num_tiles + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = min(num_tiles, threadIdx.x * per), hi = min(num_tiles, lo + per);
+    unsigned long long sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) sum += counts[i];
+    // block inclusive scan
+    const int lane = lane_id(), w = warp_id();
+    unsigned long long incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        unsigned long long x = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += t;
+        }
+        s_warp[lane] = x;
+    }
+    __syncthreads();
+    if (w > 0) incl += s_warp[w - 1];
+    unsigned long long run = incl - sum;
+    for (uint32_t i = lo; i < hi; ++i) {
+        base[i] = run;
+        run += counts[i];
+    }
+    if (threadIdx.x == blockDim.x - 1) base[num_tiles] = incl;
+}
+
+__global__ void __launch_bounds__(NP_THREADS) tile_compact_kernel(const float *__restrict__ w, int vec_ok,
+                                                                   const NpTileDesc *__restrict__ desc, uint32_t num_tiles,
+                                                                   const unsigned long long *__restrict__ base,
+                                                                   float *__restrict__ out) {
+    __shared__ int s_warp_cnt[2][NP_THREADS / 32];
+    const int lane = lane_id(), wid = warp_id();
+    int buf = 0;
+    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, buf ^= 1) {
+        const int64_t off = desc[t].off;
+        const int sz = desc[t].sz;
+        // warp `wid` owns elements [512 wid, 512 (wid + 1)) of the tile as 4 rows of 128: (row, lane, component) is
+        // element order, so the survivors keep their order
+        const float *src = w + off;
+        float4 x[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int e = wid * 512 + r * 128 + lane * 4;
+            if (vec_ok && e + 4 <= sz) {
+                x[r] = ld_stream_f4(src + e);
+            } else {
+                x[r].x = e < sz ? src[e] : 0.f;
+                x[r].y = e + 1 < sz ? src[e + 1] : 0.f;
+                x[r].z = e + 2 < sz ? src[e + 2] : 0.f;
+                x[r].w = e + 3 < sz ? src[e + 3] : 0.f;
+            }
+        }
+        int offr[4], wcnt = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int c = (x[r].x != 0.f) + (x[r].y != 0.f) + (x[r].z != 0.f) + (x[r].w != 0.f);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int tt = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += tt;
+            }
+            offr[r] = wcnt + incl - c;
+            wcnt += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) s_warp_cnt[buf][wid] = wcnt;
+        __syncthreads();  // the other buffer is free again: every warp passed the barrier of the previous tile
+        unsigned long long b = base[t];
+        for (int i = 0; i < wid; ++i) b += s_warp_cnt[buf][i];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float *dst = out + b + offr[r];
+            if (x[r].x != 0.f) *dst++ = x[r].x;
+            if (x[r].y != 0.f) *dst++ = x[r].y;
+            if (x[r].z != 0.f) *dst++ = x[r].z;
+            if (x[r].w != 0.f) *dst++ = x[r].w;
+        }
+    }
+}
+
+void compact_tiles_device(nnc_ctx *ctx, const float *d_w, const QuantPrologue &q, float *d_out) {
+    unsigned long long *base = arena_alloc_t<unsigned long long>(ctx, (size_t)q.num_tiles + 1);
+    NNC_LAUNCH(ctx, tile_scan_kernel, 1, 1024, 0, q.tile_counts, q.num_tiles, base);
+    const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, q.num_tiles);
+    NNC_LAUNCH(ctx, tile_compact_kernel, grid, NP_THREADS, 0, d_w, aligned16(d_w) ? 1 : 0,
+               static_cast<const NpTileDesc *>(q.tile_desc), q.num_tiles, base, d_out);
 }
 
 void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth, int thr_mode, uint8_t *d_mask) {

@@ -5,12 +5,11 @@
 // samples, so the B200 path sorts the surviving (non-zero) weights ONCE and turns each Lloyd iteration into
 // boundary searches (lloyd.cu).  This file is that one-time sort.
 //
-// Algorithm (Adinets & Merrill, "Onesweep"): one upfront kernel builds the four 8-bit digit histograms; each
-// of the four passes then reads a tile of keys once, ranks it in shared memory (warp-level match_any
-// multisplit, stable), resolves the tile's global digit offsets with a decoupled look-back over per-tile
-// digit counts, and scatters the tile-sorted keys.  Traffic: 4 B read for the histograms + 4 x (4 B read +
-// 4 B write) per key.  Floats are mapped to order-preserving uint32 on the first read and back on the last
-// write.
+// Algorithm: least-significant-digit radix sort with 9-bit digits over range-compressed keys (three passes
+// for a pruned Gaussian layer).  Each pass is count -> base -> scatter (see "pass structure" below): 12 B of
+// traffic per key and pass, and no inter-CTA dependency (a decoupled look-back "onesweep" variant was measured
+// first and was bound by the look-back latency, not by HBM).  Floats are mapped to keys on the first read and
+// back on the last write.
 #include <algorithm>
 
 #include "common.cuh"
@@ -47,209 +46,188 @@ struct RsPlan {
     int width[RS_MAX_PASSES];
 };
 
-constexpr unsigned long long RS_VAL_MASK = (1ull << 54) - 1;
-__device__ __forceinline__ unsigned long long rs_pack(unsigned flag, unsigned epoch, unsigned long long v) {
-    return ((unsigned long long)flag << 62) | ((unsigned long long)(epoch & 0xffu) << 54) | (v & RS_VAL_MASK);
-}
+// ---- pass structure --------------------------------------------------------------------------------------
+// The keys are cut into C contiguous chunks of whole tiles (8192 keys), one per resident CTA.  Per pass:
+//   count    CTA c histograms the pass digit over its chunk                          (read 4 B/key)
+//   base     one CTA turns the C x radix chunk histograms into the global start of every (chunk, digit) run
+//   scatter  CTA c walks its chunk tile by tile: stable ranking inside the tile (warp-level match_any
+//            multisplit), tile staged in digit order in shared memory, coalesced scatter; the running
+//            (chunk, digit) cursors live in shared memory                                (read + write 4 B/key)
+// No CTA ever waits for another one (no decoupled look-back): every kernel is a plain streaming pass.
+constexpr int RS_MAX_CHUNKS = 1024;
 
-// ---- upfront histograms of all digits ----------------------------------------------------------------
-__global__ void __launch_bounds__(512) rs_hist_kernel(const uint32_t *in, int64_t n, int vec_ok, RsKeyMap km, RsPlan plan,
-                                                      unsigned long long *ghist /*[passes][RS_RADIX]*/) {
-    __shared__ uint32_t h[RS_MAX_PASSES][RS_RADIX];
-    for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_RADIX; i += blockDim.x) (&h[0][0])[i] = 0;
+template <bool IN_FLOAT>
+__global__ void __launch_bounds__(RS_THREADS) rs_count_kernel(const uint32_t *__restrict__ in, int64_t n, int vec_ok,
+                                                              int64_t tiles_per_chunk, int shift, int width, RsKeyMap km,
+                                                              uint32_t *chunk_hist /*[C][RS_RADIX]*/) {
+    __shared__ uint32_t h[RS_RADIX];
+    h[threadIdx.x] = 0;
     __syncthreads();
+    const uint32_t dmask = (1u << width) - 1u;
+    const int64_t lo = (int64_t)blockIdx.x * tiles_per_chunk * RS_TILE;
+    const int64_t hi = min(n, lo + tiles_per_chunk * RS_TILE);
     auto one = [&](uint32_t bits) {
-        const uint32_t k = rs_key(bits, km);
-#pragma unroll
-        for (int p = 0; p < RS_MAX_PASSES; ++p)
-            if (p < plan.passes) atomicAdd(&h[p][(k >> plan.shift[p]) & ((1u << plan.width[p]) - 1u)], 1u);
+        const uint32_t k = IN_FLOAT ? rs_key(bits, km) : bits;
+        atomicAdd(&h[(k >> shift) & dmask], 1u);
     };
-    int64_t nvec = vec_ok ? (n >> 2) : 0;
-    // per-CTA counts stay below 2^32: each CTA sees at most n / gridDim + slack keys (n < 2^40 / grid)
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-        uint4 v = ld_stream_u4(in + 4 * i);
-        one(v.x);
-        one(v.y);
-        one(v.z);
-        one(v.w);
-    }
-    for (int64_t i = (nvec << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x)
-        one(in[i]);
-    __syncthreads();
-    for (int i = threadIdx.x; i < plan.passes * RS_RADIX; i += blockDim.x) {
-        uint32_t c = (&h[0][0])[i];
-        if (c) atomicAdd(&ghist[i], (unsigned long long)c);
-    }
-}
-
-// exclusive scan of each digit histogram -> global base offset of every digit value
-__global__ void __launch_bounds__(RS_RADIX) rs_scan_kernel(unsigned long long *ghist /*[passes][RS_RADIX] in place*/, int passes) {
-    __shared__ unsigned long long s[RS_RADIX];
-    for (int p = 0; p < passes; ++p) {
-        s[threadIdx.x] = ghist[p * RS_RADIX + threadIdx.x];
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long run = 0;
-            for (int i = 0; i < RS_RADIX; ++i) {
-                unsigned long long c = s[i];
-                s[i] = run;
-                run += c;
-            }
+    if (vec_ok) {  // lo is a multiple of 8192 keys: 16-byte aligned whenever the base is
+        const int64_t nvec = (hi - lo) >> 2;
+        const uint32_t *p = in + lo;
+        for (int64_t i = threadIdx.x; i < nvec; i += RS_THREADS) {
+            uint4 v = ld_stream_u4(p + 4 * i);
+            one(v.x);
+            one(v.y);
+            one(v.z);
+            one(v.w);
         }
-        __syncthreads();
-        ghist[p * RS_RADIX + threadIdx.x] = s[threadIdx.x];
-        __syncthreads();
+        for (int64_t i = lo + (nvec << 2) + threadIdx.x; i < hi; i += RS_THREADS) one(in[i]);
+    } else {
+        for (int64_t i = lo + threadIdx.x; i < hi; i += RS_THREADS) one(in[i]);
+    }
+    __syncthreads();
+    chunk_hist[(size_t)blockIdx.x * RS_RADIX + threadIdx.x] = h[threadIdx.x];
+}
+
+// chunk_hist[c][d] (counts)  ->  chunk_base[c][d] = keys with a smaller digit + keys with digit d in earlier chunks
+__global__ void __launch_bounds__(RS_RADIX) rs_base_kernel(const uint32_t *chunk_hist, int chunks, unsigned long long *chunk_base) {
+    __shared__ unsigned long long s_warp[RS_RADIX / 32];
+    const int d = threadIdx.x, lane = lane_id(), w = warp_id();
+    unsigned long long tot = 0;
+    for (int c = 0; c < chunks; ++c) tot += chunk_hist[(size_t)c * RS_RADIX + d];
+    unsigned long long incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    unsigned long long add = 0;
+    for (int i = 0; i < w; ++i) add += s_warp[i];
+    unsigned long long run = incl - tot + add;  // keys with a smaller digit
+    for (int c = 0; c < chunks; ++c) {
+        chunk_base[(size_t)c * RS_RADIX + d] = run;
+        run += chunk_hist[(size_t)c * RS_RADIX + d];
     }
 }
 
-// ---- one onesweep pass -------------------------------------------------------------------------------
 struct RsSmem {
     uint32_t keys[RS_TILE];
     uint32_t warp_hist[RS_WARPS][RS_RADIX];
     uint32_t tile_start[RS_RADIX];
-    unsigned long long gbase[RS_RADIX];
+    unsigned long long run[RS_RADIX];    // next output position of every digit for this chunk
+    unsigned long long gbase[RS_RADIX];  // run[d] - tile_start[d] of the tile being scattered
     uint32_t warp_tot[RS_WARPS];
-    uint32_t tile;
 };
 
 template <bool IN_FLOAT, bool OUT_FLOAT>
-__global__ void __launch_bounds__(RS_THREADS) rs_pass_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
-                                                             int64_t n, int shift, int width, RsKeyMap km,
-                                                             const unsigned long long *__restrict__ digit_base,
-                                                             unsigned long long *state, unsigned int *ticket,
-                                                             unsigned epoch) {
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
+                                                                int64_t n, int64_t tiles_per_chunk, int shift, int width,
+                                                                RsKeyMap km, const unsigned long long *__restrict__ chunk_base) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RsSmem &s = *reinterpret_cast<RsSmem *>(smem_raw);
     const int lane = lane_id(), wid = warp_id();
     const uint32_t dmask = (1u << width) - 1u;
     const int radix = 1 << width;
-
-    if (threadIdx.x == 0) s.tile = atomicAdd(ticket, 1u);
-    for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&s.warp_hist[0][0])[i] = 0;
-    __syncthreads();
-    const uint32_t tile = s.tile;
-    const int64_t tile_base = (int64_t)tile * RS_TILE;
-    const int valid = (int)min((int64_t)RS_TILE, n - tile_base);
-
-    // ---- load (warp-striped: item i of lane l is element i*32 + l of the warp's 512-key chunk)
-    uint32_t key[RS_ITEMS];
-    const int64_t wbase = tile_base + wid * (32 * RS_ITEMS);
-#pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        int64_t idx = wbase + i * 32 + lane;
-        uint32_t k = 0xffffffffu;  // padding: all digit bits set, sorts last in every pass
-        if (idx < n) {
-            k = __ldg(in + idx);
-            if (IN_FLOAT) k = rs_key(k, km);
-        }
-        key[i] = k;
-    }
-    // ---- stable ranking inside the warp: match_any multisplit with warp-private digit counters
-    uint32_t rank[RS_ITEMS];
-    uint32_t *wh = s.warp_hist[wid];
     const uint32_t lt = (1u << lane) - 1u;
+    s.run[threadIdx.x] = chunk_base[(size_t)blockIdx.x * RS_RADIX + threadIdx.x];
+    const int64_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
+    const int64_t t0 = (int64_t)blockIdx.x * tiles_per_chunk, t1 = min(n_tiles, t0 + tiles_per_chunk);
+    for (int64_t tile = t0; tile < t1; ++tile) {
+        for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX / 4; i += RS_THREADS)
+            reinterpret_cast<uint4 *>(&s.warp_hist[0][0])[i] = make_uint4(0, 0, 0, 0);
+        const int64_t tile_base = tile * RS_TILE;
+        const int valid = (int)min((int64_t)RS_TILE, n - tile_base);
+        // ---- load (warp-striped: item i of lane l is element i*32 + l of the warp's 512-key chunk)
+        uint32_t key[RS_ITEMS];
+        const int64_t wbase = tile_base + wid * (32 * RS_ITEMS);
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        uint32_t d = (key[i] >> shift) & dmask;
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
-        uint32_t before = wh[d];
-        __syncwarp();
-        if ((peers & lt) == 0) wh[d] = before + __popc(peers);  // lowest peer lane updates the counter
-        __syncwarp();
-        rank[i] = before + __popc(peers & lt);
-    }
-    __syncthreads();
-    // ---- per-digit exclusive scan over warps; tile digit totals (thread d owns digit d)
-    uint32_t tot = 0;
-    {
-        const int d = threadIdx.x;
-        if (d < radix) {
-#pragma unroll
-            for (int w = 0; w < RS_WARPS; ++w) {
-                uint32_t c = s.warp_hist[w][d];
-                s.warp_hist[w][d] = tot;
-                tot += c;
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            int64_t idx = wbase + i * 32 + lane;
+            uint32_t k = 0xffffffffu;  // padding: all digit bits set, sorts last in every pass
+            if (idx < n) {
+                k = __ldg(in + idx);
+                if (IN_FLOAT) k = rs_key(k, km);
             }
+            key[i] = k;
         }
-        // exclusive scan of the digit totals -> position of each digit's run in tile order
-        uint32_t incl = tot;
+        __syncthreads();  // counters cleared; the previous tile's scatter has finished reading s.keys / s.gbase
+        // ---- stable ranking inside the warp: match_any multisplit with warp-private digit counters
+        uint32_t rank[RS_ITEMS];
+        uint32_t *wh = s.warp_hist[wid];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            uint32_t d = (key[i] >> shift) & dmask;
+            uint32_t peers = __match_any_sync(0xffffffffu, d);
+            uint32_t before = wh[d];
+            __syncwarp();
+            if ((peers & lt) == 0) wh[d] = before + __popc(peers);  // lowest peer lane updates the counter
+            __syncwarp();
+            rank[i] = before + __popc(peers & lt);
         }
-        if (lane == 31) s.warp_tot[wid] = incl;
-        s.tile_start[d] = incl - tot;  // warp-local exclusive; fixed up after the barrier
-    }
-    __syncthreads();
-    {
-        const int d = threadIdx.x;
-        uint32_t add = 0;
-        for (int w = 0; w < wid; ++w) add += s.warp_tot[w];
-        const uint32_t start = s.tile_start[d] + add;
-        if (d < radix) {
-            // ---- decoupled look-back for this digit
+        __syncthreads();
+        // ---- per-digit exclusive scan over warps; tile digit totals (thread d owns digit d)
+        {
+            const int d = threadIdx.x;
+            uint32_t tot = 0;
+            if (d < radix) {
+#pragma unroll
+                for (int w = 0; w < RS_WARPS; ++w) {
+                    uint32_t c = s.warp_hist[w][d];
+                    s.warp_hist[w][d] = tot;
+                    tot += c;
+                }
+            }
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s.warp_tot[wid] = incl;
+            __syncthreads();
+            uint32_t add = 0;
+            for (int w = 0; w < wid; ++w) add += s.warp_tot[w];
+            const uint32_t start = incl - tot + add;  // position of the digit's run in tile order
+            s.tile_start[d] = start;
             unsigned long long real = tot;
             if (d == radix - 1) real -= (unsigned long long)(RS_TILE - valid);  // exclude padding
-            unsigned long long excl = 0;
-            unsigned long long *my = state + (size_t)tile * RS_RADIX + d;
-            if (tile == 0) {
-                st_volatile_u64(my, rs_pack(2u, epoch, real));
-            } else {
-                st_volatile_u64(my, rs_pack(1u, epoch, real));
-                for (int64_t p = (int64_t)tile - 1; p >= 0; --p) {
-                    const unsigned long long *q = state + (size_t)p * RS_RADIX + d;
-                    unsigned long long v;
-                    unsigned flag;
-                    do {
-                        v = ld_volatile_u64(q);
-                        flag = (unsigned)(v >> 62);
-                        if (((v >> 54) & 0xffu) != (epoch & 0xffu)) flag = 0;  // stale word from an earlier pass
-                    } while (flag == 0);
-                    excl += v & RS_VAL_MASK;
-                    if (flag == 2u) break;
-                }
-                st_volatile_u64(my, rs_pack(2u, epoch, excl + real));
-            }
-            s.gbase[d] = digit_base[d] + excl - start;
+            const unsigned long long r = s.run[d];
+            s.gbase[d] = r - start;
+            s.run[d] = r + real;
         }
-        __syncthreads();  // every thread has read the warp-local tile_start of its digit
-        s.tile_start[d] = start;
-    }
-    __syncthreads();
-    // ---- tile-order placement in shared memory
+        __syncthreads();
+        // ---- tile-order placement in shared memory
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        uint32_t d = (key[i] >> shift) & dmask;
-        s.keys[s.tile_start[d] + s.warp_hist[wid][d] + rank[i]] = key[i];
-    }
-    __syncthreads();
-    // ---- coalesced scatter
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            uint32_t d = (key[i] >> shift) & dmask;
+            s.keys[s.tile_start[d] + s.warp_hist[wid][d] + rank[i]] = key[i];
+        }
+        __syncthreads();
+        // ---- coalesced scatter
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        int p = threadIdx.x + j * RS_THREADS;
-        if (p < valid) {
-            uint32_t k = s.keys[p];
-            uint32_t d = (k >> shift) & dmask;
-            uint32_t v = OUT_FLOAT ? rs_unkey(k, km) : k;
-            out[s.gbase[d] + p] = v;
+        for (int j = 0; j < RS_ITEMS; ++j) {
+            int p = threadIdx.x + j * RS_THREADS;
+            if (p < valid) {
+                uint32_t k = s.keys[p];
+                uint32_t d = (k >> shift) & dmask;
+                uint32_t v = OUT_FLOAT ? rs_unkey(k, km) : k;
+                out[s.gbase[d] + p] = v;
+            }
         }
     }
 }
 
 template <bool A, bool B>
-static void launch_pass(nnc_ctx *ctx, const uint32_t *in, uint32_t *out, int64_t n, int shift, int width, RsKeyMap km,
-                        const unsigned long long *digit_base, unsigned long long *state, unsigned int *ticket,
-                        unsigned epoch) {
+static void launch_scatter(nnc_ctx *ctx, int chunks, const uint32_t *in, uint32_t *out, int64_t n, int64_t tiles_per_chunk,
+                           int shift, int width, RsKeyMap km, const unsigned long long *chunk_base) {
     static bool configured = false;
     if (!configured) {
-        NNC_CUDA(cudaFuncSetAttribute(rs_pass_kernel<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        NNC_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
         configured = true;
     }
-    const int64_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
-    NNC_LAUNCH(ctx, (rs_pass_kernel<A, B>), (unsigned)n_tiles, RS_THREADS, sizeof(RsSmem), in, out, n, shift, width, km,
-               digit_base, state, ticket, epoch);
+    NNC_LAUNCH(ctx, (rs_scatter_kernel<A, B>), chunks, RS_THREADS, sizeof(RsSmem), in, out, n, tiles_per_chunk, shift, width, km,
+               chunk_base);
 }
 
 // Sorts the n non-zero floats in d_a ascending, using d_b as the other half of the ping-pong.  amin / amax: smallest
@@ -272,28 +250,30 @@ float *radix_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n, uint32_t 
         at += wd;
     }
     const int64_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
-    unsigned long long *ghist = arena_alloc_t<unsigned long long>(ctx, RS_MAX_PASSES * RS_RADIX + 4);
-    unsigned int *tickets = reinterpret_cast<unsigned int *>(ghist + RS_MAX_PASSES * RS_RADIX);
-    unsigned long long *state = arena_alloc_t<unsigned long long>(ctx, (size_t)n_tiles * RS_RADIX);
-    NNC_CUDA(cudaMemsetAsync(ghist, 0, sizeof(unsigned long long) * (RS_MAX_PASSES * RS_RADIX + 4), ctx->stream));
-    NNC_CUDA(cudaMemsetAsync(state, 0, sizeof(unsigned long long) * (size_t)n_tiles * RS_RADIX, ctx->stream));
+    const int64_t want_chunks = std::min<int64_t>(RS_MAX_CHUNKS, (int64_t)ctx->sm_count * 2);
+    const int64_t tiles_per_chunk = (n_tiles + want_chunks - 1) / want_chunks;
+    const int chunks = (int)((n_tiles + tiles_per_chunk - 1) / tiles_per_chunk);
+    uint32_t *chunk_hist = arena_alloc_t<uint32_t>(ctx, (size_t)chunks * RS_RADIX);
+    unsigned long long *chunk_base = arena_alloc_t<unsigned long long>(ctx, (size_t)chunks * RS_RADIX);
     uint32_t *a = reinterpret_cast<uint32_t *>(d_a), *b = reinterpret_cast<uint32_t *>(d_b);
-    int vec_ok = (reinterpret_cast<uintptr_t>(d_a) & 15u) == 0;
-    int hgrid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 4, (n / 4 + 511) / 512 + 1);
-    NNC_LAUNCH(ctx, rs_hist_kernel, hgrid, 512, 0, a, n, vec_ok, km, plan, ghist);
-    NNC_LAUNCH(ctx, rs_scan_kernel, 1, RS_RADIX, 0, ghist, plan.passes);
     uint32_t *src = a, *dst = b;
     for (int p = 0; p < plan.passes; ++p) {
         const bool first = p == 0, last = p == plan.passes - 1;
-        const unsigned long long *base = ghist + (size_t)p * RS_RADIX;
-        if (first && last)
-            launch_pass<true, true>(ctx, src, dst, n, plan.shift[p], plan.width[p], km, base, state, tickets + p, p + 1);
-        else if (first)
-            launch_pass<true, false>(ctx, src, dst, n, plan.shift[p], plan.width[p], km, base, state, tickets + p, p + 1);
-        else if (last)
-            launch_pass<false, true>(ctx, src, dst, n, plan.shift[p], plan.width[p], km, base, state, tickets + p, p + 1);
+        const int sh = plan.shift[p], wd = plan.width[p];
+        const int vec_ok = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+        if (first)
+            NNC_LAUNCH(ctx, rs_count_kernel<true>, chunks, RS_THREADS, 0, src, n, vec_ok, tiles_per_chunk, sh, wd, km, chunk_hist);
         else
-            launch_pass<false, false>(ctx, src, dst, n, plan.shift[p], plan.width[p], km, base, state, tickets + p, p + 1);
+            NNC_LAUNCH(ctx, rs_count_kernel<false>, chunks, RS_THREADS, 0, src, n, vec_ok, tiles_per_chunk, sh, wd, km, chunk_hist);
+        NNC_LAUNCH(ctx, rs_base_kernel, 1, RS_RADIX, 0, chunk_hist, chunks, chunk_base);
+        if (first && last)
+            launch_scatter<true, true>(ctx, chunks, src, dst, n, tiles_per_chunk, sh, wd, km, chunk_base);
+        else if (first)
+            launch_scatter<true, false>(ctx, chunks, src, dst, n, tiles_per_chunk, sh, wd, km, chunk_base);
+        else if (last)
+            launch_scatter<false, true>(ctx, chunks, src, dst, n, tiles_per_chunk, sh, wd, km, chunk_base);
+        else
+            launch_scatter<false, false>(ctx, chunks, src, dst, n, tiles_per_chunk, sh, wd, km, chunk_base);
         std::swap(src, dst);
     }
     return reinterpret_cast<float *>(src);
