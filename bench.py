@@ -306,14 +306,13 @@ def run_b200(args):
 def kernel_bytes(name, n, n_nz):
     """Algorithmic bytes one launch of `name` moves."""
     table = {
-        "np_tree_kernel<V>": 4.0 * n,                       # read once (the apply pass adds 5 B/weight: see DESIGN)
-        "(rs_pass_kernel<A, B>)": 8.0 * n_nz,               # read + write every key
-        "rs_hist_kernel": 4.0 * n_nz,
-        "compact_kernel": 4.0 * n + 4.0 * n_nz,
-        "emit_kernel<true>": 4.0 * n + BITS / 8.0 * n,
-        "emit_kernel<false>": 4.0 * n + BITS / 8.0 * n,
+        "np_tree_kernel<V>": (4.0 + 4.0 + 9.0) * n / 3.0,   # 3 launches per step: mean (4), var+apply (9), k-means prologue (4)
+        "(rs_scatter_kernel<A, B>)": 8.0 * n_nz,            # read + write every key
+        "rs_count_kernel<true>": 4.0 * n_nz,
+        "rs_count_kernel<false>": 4.0 * n_nz,
+        "tile_compact_kernel": 4.0 * n + 4.0 * n_nz,
+        "(emit_kernel<VEC, INERTIA, BITS>)": 4.0 * n + BITS / 8.0 * n,
         "ll_tilesum_kernel": 4.0 * n_nz,
-        "minmax_kernel": 4.0 * n,
     }
     return table.get(name, 0.0)
 
@@ -321,6 +320,8 @@ def kernel_bytes(name, n, n_nz):
 def run_e2e(args, torch, U, n_local, rank, world, dist, dev):
     steps = max(1, min(args.steps, args.e2e_steps))
     host = torch.empty(n_local, dtype=torch.float32).pin_memory()
+    out_mask = torch.empty(n_local, dtype=torch.uint8).pin_memory()
+    out_packed = torch.empty(n_local * BITS // 8, dtype=torch.uint8).pin_memory()
     src = (torch.randn(n_local, generator=torch.Generator().manual_seed(SEED + 100 + rank)) * SIGMA) if n_local <= (1 << 26) else None
     total = 0.0
     h2d = d2h = 0
@@ -336,20 +337,21 @@ def run_e2e(args, torch, U, n_local, rank, world, dist, dev):
             dist.barrier()
         t0 = time.perf_counter()
         arr = host.numpy()
-        mask, km = U.compress_weight(arr, QUALITY, True, BITS, MODE)
+        mask, km = U.compress_weight(arr, QUALITY, True, BITS, MODE, update_weights=False, out_mask=out_mask.numpy(),
+                                     out_packed=out_packed.numpy())
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if i > 0:
             total += dt
-        # prune: w in + (w, mask) out; quantize: w in + packed out (+ k centroids, histogram)
-        h2d = 2 * 4 * n_local
-        d2h = 4 * n_local + n_local + km.packed_codes.nbytes + 4 * km.n_clusters + 8 * km.n_clusters
+        # one fused call: w in; mask + packed codes (+ k centroids, histogram) out
+        h2d = 4 * n_local
+        d2h = n_local + km.packed_codes.nbytes + 4 * km.n_clusters + 8 * km.n_clusters
     if dist is not None:
         t = torch.tensor([total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total = float(t.item())
     return {"value": args.n * steps / total, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "steps": steps, "ms_per_step": 1e3 * total / steps, "api": "utility.compress_weight(numpy float32 in pinned host memory)"}
+            "steps": steps, "ms_per_step": 1e3 * total / steps, "api": "utility.compress_weight(pinned host ndarray, update_weights=False, pinned out_mask/out_packed) -> nnc_compress_f32"}
 
 
 def main():

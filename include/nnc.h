@@ -127,6 +127,15 @@ int nnc_kmeans1d_f32(nnc_ctx *ctx, const float *w, int64_t n, const float *init,
                      int flags, float *centers, float *centred, int32_t *labels, float *ris, uint8_t *packed, int bits,
                      int64_t *hist, nnc_kmeans_info *info);
 
+/* prune_weigth followed by the k-means weight sharing of the pruned tensor, keeping only the compressed form
+ * (mask, codebook, packed codes, histogram): what Trainer._prune_parameters + Trainer.quantize do to one tensor
+ * (trainer.py:177-193, :42-72).  A host tensor is copied to the device once; write_back == 0 skips copying the
+ * pruned weights back to a HOST `w` (a device-resident `w` is always pruned in place).  Arguments as in
+ * nnc_prune_f32 and nnc_kmeans1d_f32. */
+int nnc_compress_f32(nnc_ctx *ctx, float *w, int64_t n, double threshold, int std_smooth, int threshold_mode, int write_back,
+                     uint8_t *mask, double *thr_out, int64_t *n_pruned_out, const float *init, int k, int max_iter, double tol,
+                     int flags, float *centers, float *centred, uint8_t *packed, int bits, int64_t *hist, nnc_kmeans_info *info);
+
 /* E-step / emission only: labels[i] = first argmin_j fl(c_j^2 + fl(-2 x'_i) c_j), x' = fl(w - mean),
  * c = centred[k] (the sklearn label rule, _k_means_lloyd.pyx:196-213).  values[k] (optional) are
  * the codebook entries written to `ris`. */

@@ -33,6 +33,7 @@ EXPORTS = [
     "nnc_compact_nonzero_f32", "nnc_minmax_f32", "nnc_hist_edges_f32", "nnc_weight_cdf_f32", "nnc_gather_f32",
     "nnc_kmeans1d_f32", "nnc_assign_f32", "nnc_unpack_gather_f32", "nnc_grad_segsum_f32", "nnc_ctx_set_comm",
     "nnc_ctx_set_kernel_timing", "nnc_last_kernel_times", "nnc_ctx_total_launches",
+    "nnc_compress_f32",
 ]
 
 
@@ -96,6 +97,8 @@ def lib():
         L.nnc_weight_cdf_f32.argtypes = [vp, vp, i64, i32, vp, vp]
         L.nnc_gather_f32.argtypes = [vp, vp, i64, vp, i32, vp]
         L.nnc_kmeans1d_f32.argtypes = [vp, vp, i64, vp, i32, i32, f64, i32, vp, vp, vp, vp, vp, i32, vp, P(KMeansInfo)]
+        L.nnc_compress_f32.argtypes = [vp, vp, i64, f64, i32, i32, i32, vp, P(f64), P(i64), vp, i32, i32, f64, i32, vp, vp, vp, i32,
+                                       vp, P(KMeansInfo)]
         L.nnc_assign_f32.argtypes = [vp, vp, i64, vp, i32, f32, vp, vp, vp, vp, i32, vp, P(f64)]
         L.nnc_unpack_gather_f32.argtypes = [vp, vp, i64, i32, vp, i32, vp]
         L.nnc_grad_segsum_f32.argtypes = [vp, vp, vp, i64, i32, i32, vp]

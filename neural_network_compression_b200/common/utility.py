@@ -339,34 +339,78 @@ def _init_space(buf: _Buf, ctx: N.Context, bits: int, mode: str, cdfs):
     raise Exception(" error mode not found")
 
 
-def compress_weight(original_weigth, threshold=0.25, std_smooth=True, bits=4, mode="linear", with_cdf=True):
+def compress_weight(original_weigth, threshold=0.25, std_smooth=True, bits=4, mode="linear", with_cdf=True,
+                    update_weights=True, out_mask=None, out_packed=None):
     """The whole compression of one tensor as Trainer._prune_parameters + Trainer.quantize apply it
-    (trainer.py:177-193, :42-72): std-threshold prune IN PLACE, then k-means weight sharing of the pruned tensor,
-    keeping only the compressed representation -- the boolean mask, the codebook, the packed n-bit cluster
-    indices and their histogram -- instead of the dense de-quantised tensor and int32 labels.
+    (trainer.py:177-193, :42-72): std-threshold prune, then k-means weight sharing of the pruned tensor, keeping
+    only the compressed representation -- the boolean mask, the codebook, the packed n-bit cluster indices and
+    their histogram -- instead of the dense de-quantised tensor and int32 labels.
+
+    update_weights=True keeps prune_weigth's contract (the argument is pruned IN PLACE).  With a host array and
+    update_weights=False the pruned weights are not copied back (the caller is about to replace them with the
+    codebook values anyway): the tensor crosses the bus once.  out_mask / out_packed: optional preallocated
+    (e.g. pinned) uint8 output buffers for host arrays.
 
     Returns (mask, KMeansResult); `KMeansResult.labels_` is None (decode with `dequantize`)."""
-    mask = prune_weigth(original_weigth, threshold, std_smooth)
-    buf = _Buf(original_weigth, "original_weigth")
+    buf = _Buf(original_weigth, "original_weigth", writable=True)
     if buf.n < (2 ** bits) + 1:
+        mask = prune_weigth(original_weigth, threshold, std_smooth)
         print("not enough bits:", buf.n, " vs ", 2 ** bits)
         return mask, None
     ctx = _ctx_for(buf)
-    prune_prof, _ = ctx.last_profile()
-    cdfs = None
-    if mode == "density" and with_cdf:
-        cdfs = get_weight_distribution(original_weigth, skip_zeros=True)
-    space = None if mode == "linear" else np.asarray(_init_space(buf, ctx, bits, mode, cdfs), dtype=np.float32)
+    if mode != "linear":
+        # density / forgy initialise from the PRUNED tensor: prune first, then the reference's init, then k-means
+        mask = prune_weigth(original_weigth, threshold, std_smooth)
+        prune_prof, _ = ctx.last_profile()
+        cdfs = get_weight_distribution(original_weigth, skip_zeros=True) if (mode == "density" and with_cdf) else None
+        buf = _Buf(original_weigth, "original_weigth")
+        space = np.asarray(_init_space(buf, ctx, bits, mode, cdfs), dtype=np.float32)
+        try:
+            _, res = _kmeans_device(buf, ctx, space, want_labels=False, want_ris=False, want_packed=True, want_inertia=False)
+        except N.NncError as e:
+            if e.code == N.NNC_ERR_NONFINITE:
+                raise ValueError("Input X contains NaN or infinity.") from None
+            raise
+        for name, ms in prune_prof.items():
+            res.profile["prune." + name] = ms
+        return mask, res
+    # linear init needs only min / max of the pruned tensor, which the k-means prologue measures: one fused call
+    k = 2 ** bits
+    cbits = index_bits(k)
+    thr_mode = 1 if isinstance(threshold, np.float64) else 0
+    mask = out_mask if out_mask is not None else buf.empty(buf.n, np.uint8)
+    packed = out_packed if out_packed is not None else buf.empty((buf.n * cbits + 7) // 8, np.uint8)
+    centers = np.empty(k, dtype=np.float32)
+    centred = np.empty(k, dtype=np.float32)
+    hist = np.empty(k, dtype=np.int64)
+    info = N.KMeansInfo()
+    thr_out, n_pruned = C.c_double(), C.c_int64()
     try:
-        _, res = _kmeans_device(buf, ctx, space, want_labels=False, want_ris=False, want_packed=True, want_inertia=False,
-                                linear_k=2 ** bits)
+        N.check(N.lib().nnc_compress_f32(ctx.handle, buf.ptr, buf.n, float(threshold), int(bool(std_smooth)), thr_mode,
+                                         int(bool(update_weights)), N.ptr(mask), C.byref(thr_out), C.byref(n_pruned), None, k,
+                                         300, 1e-4, N.NNC_KM_INIT_LINEAR, N.ptr(centers), N.ptr(centred), N.ptr(packed), cbits,
+                                         N.ptr(hist), C.byref(info)))
     except N.NncError as e:
         if e.code == N.NNC_ERR_NONFINITE:
             raise ValueError("Input X contains NaN or infinity.") from None
         raise
-    for name, ms in prune_prof.items():
-        res.profile["prune." + name] = ms
-    return mask, res
+    if update_weights:
+        buf.finish()
+    prune_weigth.last_threshold = thr_out.value
+    prune_weigth.last_pruned = n_pruned.value
+    prof, launches = ctx.last_profile()
+    prof["launches"] = launches
+    res = KMeansResult(
+        cluster_centers_=centers.reshape(-1, 1), labels_=None, n_iter_=info.n_iter, inertia_=info.inertia,
+        packed_codes=packed, code_bits=cbits, code_histogram=hist, centred_centers=centred, mean=np.float32(info.mean),
+        strict_convergence=bool(info.strict), n_relocations=info.n_relocations, n_nonzero=info.n_nonzero,
+        tol_=float(info.tol), profile=prof)
+    if buf.kind == "torch":
+        import torch
+
+        mask = mask.view(torch.bool) if mask.dtype == torch.uint8 else mask
+        return mask.reshape(buf.shape), res
+    return mask.view(np.bool_).reshape(buf.shape), res
 
 
 def assign_codes(weights, kmeans: KMeansResult, want_labels=True, want_packed=True):

@@ -574,22 +574,19 @@ int nnc_gather_f32(nnc_ctx *ctx, const float *w, int64_t n, const int64_t *idx, 
 }
 
 // ---- k-means ---------------------------------------------------------------------------------------------
-int nnc_kmeans1d_f32(nnc_ctx *ctx, const float *w, int64_t n, const float *init, int k, int max_iter, double tol,
-                     int flags, float *centers, float *centred, int32_t *labels, float *ris, uint8_t *packed, int bits,
-                     int64_t *hist, nnc_kmeans_info *info) {
-    NNC_TRY
-    Call call(ctx);
+// The k-means pipeline on a device-resident tensor (prologue -> compaction -> sort -> Lloyd -> emission); shared by
+// nnc_kmeans1d_f32 and nnc_compress_f32.  Output pointers are the caller's (host or device); w is a device pointer.
+static void kmeans_on_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *init, int k, int max_iter, double tol,
+                             int flags, float *centers, float *centred, int32_t *labels, float *ris, uint8_t *packed, int bits,
+                             int64_t *hist, nnc_kmeans_info *info) {
     const bool init_linear = (flags & NNC_KM_INIT_LINEAR) != 0;
-    if (!w || (!init && !init_linear) || n <= 0 || k <= 0 || max_iter < 1 || tol < 0)
-        NNC_FAIL(NNC_ERR_BAD_ARG, "nnc_kmeans1d_f32: bad argument (n = %lld, k = %d, max_iter = %d)", (long long)n, k, max_iter);
+    if ((!init && !init_linear) || n <= 0 || k <= 0 || max_iter < 1 || tol < 0)
+        NNC_FAIL(NNC_ERR_BAD_ARG, "k-means: bad argument (n = %lld, k = %d, max_iter = %d)", (long long)n, k, max_iter);
     if (k > NNC_KMAX) NNC_FAIL(NNC_ERR_UNSUPPORTED, "k = %d exceeds NNC_KMAX = %d", k, NNC_KMAX);
     if ((int64_t)k > n) NNC_FAIL(NNC_ERR_NOT_ENOUGH, "n_samples=%lld should be >= n_clusters=%d.", (long long)n, k);
     if (!init_linear)
         for (int j = 0; j < k; ++j)
             if (!isfinite(init[j])) NNC_FAIL(NNC_ERR_NONFINITE, "initial centroid %d is not finite", j);
-    Staged sw = stage_in(ctx, w, sizeof(float) * (size_t)n);
-    const float *d_w = static_cast<const float *>(sw.dev);
-    prof_mark(ctx, "h2d");
     // 1. mean (NumPy pairwise), min/max, survivor count
     const QuantPrologue qp = quant_prologue(ctx, d_w, n);
     read_scalars(ctx);
@@ -659,6 +656,42 @@ int nnc_kmeans1d_f32(nnc_ctx *ctx, const float *w, int64_t n, const float *init,
         info->inertia = inertia;
         info->n_nonzero = n_nz;
     }
+}
+
+int nnc_kmeans1d_f32(nnc_ctx *ctx, const float *w, int64_t n, const float *init, int k, int max_iter, double tol,
+                     int flags, float *centers, float *centred, int32_t *labels, float *ris, uint8_t *packed, int bits,
+                     int64_t *hist, nnc_kmeans_info *info) {
+    NNC_TRY
+    Call call(ctx);
+    if (!w || n <= 0) NNC_FAIL(NNC_ERR_BAD_ARG, "nnc_kmeans1d_f32: empty input");
+    Staged sw = stage_in(ctx, w, sizeof(float) * (size_t)n);
+    prof_mark(ctx, "h2d");
+    kmeans_on_device(ctx, static_cast<const float *>(sw.dev), n, init, k, max_iter, tol, flags, centers, centred, labels, ris,
+                     packed, bits, hist, info);
+    call.finish();
+    NNC_CATCH
+}
+
+// Prune + quantize in one call (Trainer._prune_parameters then Trainer.quantize on one tensor, trainer.py:177-193,
+// :42-72): a host tensor crosses the bus once.
+int nnc_compress_f32(nnc_ctx *ctx, float *w, int64_t n, double threshold, int std_smooth, int threshold_mode, int write_back,
+                     uint8_t *mask, double *thr_out, int64_t *n_pruned_out, const float *init, int k, int max_iter, double tol,
+                     int flags, float *centers, float *centred, uint8_t *packed, int bits, int64_t *hist, nnc_kmeans_info *info) {
+    NNC_TRY
+    Call call(ctx);
+    if (!w || !mask || n <= 0) NNC_FAIL(NNC_ERR_BAD_ARG, "nnc_compress_f32: null buffer or empty input");
+    Staged sw = stage_inout(ctx, w, sizeof(float) * (size_t)n);
+    Staged sm = stage_out(ctx, mask, (size_t)n);
+    prof_mark(ctx, "h2d");
+    float *d_w = static_cast<float *>(sw.dev);
+    prune_device(ctx, d_w, n, threshold, std_smooth, threshold_mode, static_cast<uint8_t *>(sm.dev));
+    if (write_back) stage_finish(ctx, sw);  // a device-resident tensor was pruned in place already
+    stage_finish(ctx, sm);
+    read_scalars(ctx);
+    prof_mark(ctx, "prune_d2h");
+    if (thr_out) *thr_out = ctx->h_scal->thr;
+    if (n_pruned_out) *n_pruned_out = (int64_t)ctx->h_scal->n_pruned;
+    kmeans_on_device(ctx, d_w, n, init, k, max_iter, tol, flags, centers, centred, nullptr, nullptr, packed, bits, hist, info);
     call.finish();
     NNC_CATCH
 }

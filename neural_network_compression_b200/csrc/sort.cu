@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t *
         }
         __syncthreads();  // counters cleared; the previous tile's scatter has finished reading s.keys / s.gbase
         // ---- stable ranking inside the warp: match_any multisplit with warp-private digit counters
+        // (an atomicAdd-by-the-leader variant was measured slower than this read / write pair)
         uint32_t rank[RS_ITEMS];
         uint32_t *wh = s.warp_hist[wid];
 #pragma unroll
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t *
         }
         __syncthreads();
         // ---- per-digit exclusive scan over warps; tile digit totals (thread d owns digit d)
+        // (folding the run start into warp_hist here, to save one gather in the placement below, measured slower)
         {
             const int d = threadIdx.x;
             uint32_t tot = 0;

@@ -357,3 +357,31 @@ def test_label_rule_stress(U, offset, sigma):
         assert np.array_equal(labels, expect), (k, int((labels != expect).sum()))
         assert np.array_equal(hist, np.bincount(expect, minlength=k))
         assert np.array_equal(O.unpack_codes(packed, w.size, U.index_bits(k)), expect)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused prune + quantize (compress_weight) against the two separate reference steps
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,bits", [("linear", 8), ("linear", 4), ("density", 2), ("forgy", 5)])
+def test_compress_weight_matches_separate_steps(U, mode, bits):
+    w = D.gaussian(400 * 1000, seed=91).reshape(400, 1000)
+    a, b = w.copy(), w.copy()
+    np.random.seed(5)
+    mask, km = U.compress_weight(a, 1, True, bits, mode)
+    mask_ref = U.prune_weigth(b, 1, True)
+    assert np.array_equal(mask, mask_ref) and a.tobytes() == b.tobytes()
+    cdfs = U.get_weight_distribution(b, skip_zeros=True) if mode == "density" else None
+    np.random.seed(5)
+    ris, km_ref = U.get_quantized_weight(b, bits, mode, cdfs)
+    assert km.cluster_centers_.tobytes() == km_ref.cluster_centers_.tobytes()
+    assert km.n_iter_ == km_ref.n_iter_ and km.code_bits == km_ref.code_bits
+    assert np.array_equal(km.packed_codes, km_ref.packed_codes)
+    assert np.array_equal(km.code_histogram, km_ref.code_histogram)
+    assert U.dequantize(km.packed_codes, w.size, km.code_bits, km.cluster_centers_).reshape(w.shape).tobytes() == ris.tobytes()
+    # host array, no write-back: same compressed output, the argument keeps its original values
+    c = w.copy()
+    np.random.seed(5)
+    mask2, km2 = U.compress_weight(c, 1, True, bits, mode, update_weights=False)
+    if mode == "linear":
+        assert c.tobytes() == w.tobytes()
+    assert np.array_equal(mask2, mask_ref) and np.array_equal(km2.packed_codes, km_ref.packed_codes)
