@@ -201,6 +201,13 @@ static void kfold(nnc_ctx *ctx) {  // after a stream synchronize: fold this call
     ctx->kused = 0;
 }
 
+void comm_allreduce(nnc_ctx *ctx, int64_t *d_buf, int count, int op) {
+    if (ctx->world <= 1 || count <= 0) return;
+    if (!ctx->allreduce) NNC_FAIL(NNC_ERR_COMM, "multi-rank context without an all-reduce callback");
+    const int rc = ctx->allreduce(ctx->allreduce_user, d_buf, count, op, ctx->stream);
+    if (rc != 0) NNC_FAIL(NNC_ERR_COMM, "all-reduce callback failed (%d)", rc);
+}
+
 void read_scalars(nnc_ctx *ctx) {
     NNC_CUDA(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, ctx->stream));
     NNC_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -150,6 +150,10 @@ void klaunch_end(nnc_ctx *ctx);
 
 void read_scalars(nnc_ctx *ctx);  // D2H of DevScalars + stream sync
 
+// In-place all-reduce of `count` int64 values in device memory over the ranks of the context (no-op for one rank).
+// op: 0 sum, 1 min, 2 max.  Enqueued on the context's stream through the host's callback.
+void comm_allreduce(nnc_ctx *ctx, int64_t *d_buf, int count, int op);
+
 // ---- kernels' host entry points (one per .cu file) ----------------------------------------------
 // reduce_np.cu
 struct NpPlan {

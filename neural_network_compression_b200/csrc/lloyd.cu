@@ -38,6 +38,8 @@ __host__ __device__ __forceinline__ long long llmax2(long long a, long long b) {
 
 struct LloydHeader {
     int k, max_iter, fixed_exp, pad0;
+    int rank, world;
+    unsigned long long *cand;  // relocation candidates [world][k][2] (see ll_update_kernel phase 1)
     long long n, n_nz, n0, n_tiles;
     float mean, tol, xabs_max, pad1;
     double scale, tol_rel;
@@ -59,6 +61,13 @@ struct LloydDevice : LloydHeader {
     long long zW[TB_KMAX], zS[TB_KMAX], zmin[TB_KMAX], zmax[TB_KMAX];
     // per-id partials (pre-relocation) of the previous iteration: label-equality proxy
     long long Wprev[TB_KMAX], Sprev[TB_KMAX];
+    // state handed between the phases of the update kernel when they run as separate launches (multi-GPU: the
+    // per-cluster partials and the relocation candidates are all-reduced between the phases)
+    long long gW[TB_KMAX], gS[TB_KMAX];        // per distinct index: count, fixed-point sum (contiguous: one all-reduce)
+    long long gfirst[TB_KMAX], glast[TB_KMAX]; // local member cursors per distinct index
+    long long idW[TB_KMAX], idS[TB_KMAX];      // per cluster id, before relocation
+    int empt_s[TB_KMAX];
+    int zdi_s, n_empty_s, same_s, pad3;
     // control
     int iter, done, strict, n_reloc, n_iter, pad2;
     // per-iteration log (diagnostics): zone elements, zone groups, distinct centroids, empty clusters
@@ -127,6 +136,15 @@ __global__ void __launch_bounds__(1024) ll_scan_kernel(const long long *tsum, lo
 // ---------------------------------------------------------------------------------------------
 // init: centre the initial centroids, tolerance from exact integer moments
 // ---------------------------------------------------------------------------------------------
+// the zero run of this rank joins its exact moments (same 31-bit split as ll_tilesum_kernel)
+__global__ void ll_moments_kernel(LloydDevice *st) {
+    const long long q0 = fixed_q(fsub(0.f, st->mean), st->scale);
+    const unsigned long long qq = (unsigned long long)(q0 * q0);
+    st->s1 += st->n0 * q0;
+    st->s2_lo += (unsigned long long)st->n0 * (qq & 0x7fffffffull);
+    st->s2_hi += (unsigned long long)st->n0 * (qq >> 31);
+}
+
 __global__ void ll_init_kernel(LloydDevice *st, const float *init) {
     const int tid = threadIdx.x;
     if (tid < st->k) {
@@ -135,11 +153,9 @@ __global__ void ll_init_kernel(LloydDevice *st, const float *init) {
         st->Sprev[tid] = 0;
     }
     if (tid == 0) {
-        // zero run joins the moments
-        long long q0 = fixed_q(fsub(0.f, st->mean), st->scale);
-        __int128 s1 = (__int128)st->s1 + (__int128)st->n0 * q0;
-        unsigned __int128 s2 = ((unsigned __int128)st->s2_hi << 31) + st->s2_lo +
-                               (unsigned __int128)st->n0 * (unsigned __int128)((unsigned long long)(q0 * q0));
+        // s1 / s2 cover all n samples of all ranks (ll_moments_kernel added the zero runs, then the all-reduce)
+        __int128 s1 = (__int128)st->s1;
+        unsigned __int128 s2 = ((unsigned __int128)st->s2_hi << 31) + st->s2_lo;
         unsigned __int128 num = (unsigned __int128)st->n * s2 - (unsigned __int128)(s1 * s1);
         double numd = __dadd_rn(__dmul_rn((double)(unsigned long long)(num >> 64), 18446744073709551616.0),
                                 (double)(unsigned long long)num);
@@ -409,11 +425,16 @@ struct UpdateSmem {
     int red_i[32], red_id[32];
     uint32_t rk_d2[32], rk_gap[32], rk_ord[32];
     int rk_who[32];
-    int n_empty, zdi, same, winner, stop_reloc;
+    int n_empty, zdi, same, winner, stop_reloc;  // stop_reloc: scratch of the convergence step
     long long zero_left;
 };
 
-__global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, const float *__restrict__ ks) {
+// Phases (run in one launch on a single GPU, as three launches with an all-reduce in between otherwise):
+//   0  local per-distinct-index counts / sums / member cursors (+ the zero run)            -> gW, gS  [all-reduce]
+//   1  per cluster id, label-equality proxy, empty clusters, LOCAL farthest candidates       -> cand    [all-gather]
+//   2  merge the candidates, relocate, average, centre shift, convergence
+__global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, const float *__restrict__ ks, int phase_lo,
+                                                               int phase_hi) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     UpdateSmem &U = *reinterpret_cast<UpdateSmem *>(smem_raw);
     if (st->done) return;
@@ -421,6 +442,27 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
     const int tid = threadIdx.x, k = st->k, m = T.m, R = T.R;
     const float mean = st->mean;
     const double scale = st->scale;
+    const float x0 = fsub(0.f, mean);
+    if (phase_lo > 0) {  // resume: reload what the previous launch left (gW / gS now hold the global sums)
+        if (tid < m) {
+            U.Wd[tid] = st->gW[tid];
+            U.Sd[tid] = st->gS[tid];
+            U.first[tid] = st->gfirst[tid];
+            U.last[tid] = st->glast[tid];
+        }
+        if (tid < k) {
+            U.W[tid] = st->idW[tid];
+            U.S[tid] = st->idS[tid];
+            U.empt[tid] = st->empt_s[tid];
+        }
+        if (tid == 0) {
+            U.zdi = st->zdi_s;
+            U.n_empty = st->n_empty_s;
+            U.same = st->same_s;
+        }
+        __syncthreads();
+    }
+    if (phase_lo == 0) {
     // ---- 1. per distinct index: zone partials + SAFE regions
     if (tid < m) {
         U.Wd[tid] = st->zW[tid];
@@ -446,7 +488,6 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
     }
     __syncthreads();
     // ---- 2. zero run: label of x'_0 = fl(0 - mean) over all distinct centroids
-    const float x0 = fsub(0.f, mean);
     if (st->n0 > 0) {
         float d = INFINITY;
         int id = 0x7fffffff, di = -1;
@@ -490,6 +531,20 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
         U.zdi = -1;
     }
     __syncthreads();
+    if (phase_hi == 0) {
+        if (tid < TB_KMAX) {
+            st->gW[tid] = tid < m ? U.Wd[tid] : 0;
+            st->gS[tid] = tid < m ? U.Sd[tid] : 0;
+        }
+        if (tid < m) {
+            st->gfirst[tid] = U.first[tid];
+            st->glast[tid] = U.last[tid];
+        }
+        if (tid == 0) st->zdi_s = U.zdi;
+        return;
+    }
+    }  // phase 0
+    if (phase_lo <= 1) {
     // ---- 3. per cluster id
     if (tid < m) {
         U.W[T.down[tid]] = U.Wd[tid];
@@ -549,12 +604,10 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
             }
         };
         refresh();
-        if (tid == 0) {
-            U.zero_left = st->n0;
-            U.stop_reloc = 0;
-        }
+        if (tid == 0) U.zero_left = st->n0;
         __syncthreads();
         const FarKey kz = far_key(x0, U.zdi >= 0 ? T.dv[U.zdi] : 0.f);
+        unsigned long long *my_cand = st->cand + (size_t)st->rank * k * 2;
         int n_done = 0;
         for (int pop = 0; pop < n_empty; ++pop) {
             // best head of this thread: 0 = left, 1 = right, 2 = zero run
@@ -603,19 +656,18 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
                     }
                 }
                 U.winner = owner;
-                // np.max(distances) == 0 -> relocation is skipped altogether (_k_means_common.pyx:192-195)
-                if (pop == 0 && (owner < 0 || best.d2 == 0u)) U.stop_reloc = 1;
             }
             __syncthreads();
-            if (U.stop_reloc || U.winner < 0) break;
+            if (U.winner < 0) break;  // this rank has no sample left
             if (tid == U.winner) {
+                // candidate = (dist^2, ulp gap | x', old cluster id + 1): the local list comes out in descending order
+                const FarKey kk = who == 0 ? kl : (who == 1 ? kr : kz);
+                const int old_id = who == 2 ? T.down[U.zdi] : T.down[tid];
+                my_cand[2 * pop] = ((unsigned long long)kk.d2 << 32) | kk.gap;
+                my_cand[2 * pop + 1] = ((unsigned long long)kk.ordx << 32) | (unsigned)(old_id + 1);
                 if (who == 2) {
-                    U.far_x[pop] = x0;
-                    U.far_old[pop] = T.down[U.zdi];
                     U.zero_left -= 1;
                 } else {
-                    U.far_x[pop] = who == 0 ? xl : xr;
-                    U.far_old[pop] = T.down[tid];
                     // advance the cursor to the next member of this distinct index
                     if (who == 0) {
                         do {
@@ -633,16 +685,74 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
             __syncthreads();
         }
         __syncthreads();
-        if (tid == 0 && !U.stop_reloc) {
-            for (int i = 0; i < n_done; ++i) {
-                const int nw = U.empt[i], od = U.far_old[i];
-                const long long q = fixed_q(U.far_x[i], scale);
-                U.S[od] -= q;
-                U.S[nw] = q;
-                U.W[nw] = 1;
-                U.W[od] -= 1;
+        // unused slots of this rank, and (before the all-gather) every slot of the other ranks, hold zeros
+        for (int i = tid; i < st->world * k; i += TB_THREADS) {
+            const int r = i / k, j = i - r * k;
+            if (r != st->rank || j >= n_done) {
+                st->cand[2 * (size_t)i] = 0;
+                st->cand[2 * (size_t)i + 1] = 0;
             }
-            st->n_reloc += n_done;
+        }
+        __syncthreads();
+    }
+    if (phase_hi == 1) {
+        if (tid < k) {
+            st->idW[tid] = U.W[tid];
+            st->idS[tid] = U.S[tid];
+            st->empt_s[tid] = U.empt[tid];
+        }
+        if (tid == 0) {
+            st->n_empty_s = U.n_empty;
+            st->same_s = U.same;
+        }
+        return;
+    }
+    }  // phase 1
+    // ---- 5b. relocation: the n_empty farthest samples over all ranks (every rank's list is already in descending
+    // order: a W-way merge by one thread), moved to the empty clusters in ascending id order
+    if (U.n_empty > 0) {
+        __threadfence_block();
+        if (tid == 0) {
+            const int n_empty = U.n_empty, world = st->world;
+            int cur[64];
+            for (int r = 0; r < world; ++r) cur[r] = 0;
+            int n_done = 0;
+            bool skip = false;
+            for (int i = 0; i < n_empty; ++i) {
+                int br = -1;
+                unsigned long long ba = 0, bb = 0;
+                for (int r = 0; r < world; ++r) {
+                    if (cur[r] >= k) continue;
+                    const unsigned long long a = st->cand[2 * ((size_t)r * k + cur[r])], b = st->cand[2 * ((size_t)r * k + cur[r]) + 1];
+                    if ((b & 0xffffffffull) == 0) continue;  // list exhausted
+                    if (br < 0 || a > ba || (a == ba && (b >> 32) > (bb >> 32))) {
+                        br = r;
+                        ba = a;
+                        bb = b;
+                    }
+                }
+                if (br < 0) break;
+                // np.max(distances) == 0 -> relocation is skipped altogether (_k_means_common.pyx:192-195)
+                if (i == 0 && (ba >> 32) == 0ull) {
+                    skip = true;
+                    break;
+                }
+                cur[br]++;
+                U.far_x[i] = ord2f((uint32_t)(bb >> 32));
+                U.far_old[i] = (int)(bb & 0xffffffffull) - 1;
+                n_done = i + 1;
+            }
+            if (!skip) {
+                for (int i = 0; i < n_done; ++i) {
+                    const int nw = U.empt[i], od = U.far_old[i];
+                    const long long q = fixed_q(U.far_x[i], scale);
+                    U.S[od] -= q;
+                    U.S[nw] = q;
+                    U.W[nw] = 1;
+                    U.W[od] -= 1;
+                }
+                st->n_reloc += n_done;
+            }
         }
         __syncthreads();
     }
@@ -784,6 +894,11 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
     hs.xabs_max = xabs;
     hs.scale = scale;
     hs.tol_rel = tol_rel;
+    const int world = ctx->world;
+    if (world > 64) NNC_FAIL(NNC_ERR_UNSUPPORTED, "k-means: at most 64 ranks");
+    hs.rank = ctx->rank;
+    hs.world = world;
+    hs.cand = arena_alloc_t<unsigned long long>(ctx, (size_t)world * k * 2);
     NNC_CUDA(cudaMemsetAsync(st, 0, sizeof(LloydDevice), ctx->stream));
     NNC_CUDA(cudaMemcpyAsync(static_cast<LloydHeader *>(st), &hs, sizeof(hs), cudaMemcpyHostToDevice, ctx->stream));
     NNC_CUDA(cudaMemcpyAsync(d_init, h_init, sizeof(float) * k, cudaMemcpyHostToDevice, ctx->stream));
@@ -792,6 +907,8 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         NNC_LAUNCH(ctx, ll_tilesum_kernel, grid, 256, 0, h.d_sorted, h.n_nz, mean, scale, tsum, samp, st);
     }
     NNC_LAUNCH(ctx, ll_scan_kernel, 1, 1024, 0, tsum, n_tiles, ptile, st);
+    NNC_LAUNCH(ctx, ll_moments_kernel, 1, 1, 0, st);
+    comm_allreduce(ctx, reinterpret_cast<int64_t *>(&st->s1), 3, 0);  // s1, s2_lo, s2_hi are consecutive
     NNC_LAUNCH(ctx, ll_init_kernel, 1, TB_KMAX, 0, st, d_init);
     prof_mark(ctx, "lloyd_prep");
 
@@ -807,7 +924,16 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
             NNC_LAUNCH(ctx, ll_table_kernel, 1, TB_THREADS, 0, st);
             NNC_LAUNCH(ctx, ll_search_kernel, search_grid, 256, 0, st, h.d_sorted, samp, ptile);
             NNC_LAUNCH(ctx, ll_zone_kernel, zone_grid, 256, 0, st, h.d_sorted);
-            NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted);
+            if (world == 1) {
+                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 0, 2);
+            } else {
+                // exact integer partials: the sums are identical on every rank and for every rank count
+                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 0, 0);
+                comm_allreduce(ctx, reinterpret_cast<int64_t *>(st->gW), 2 * TB_KMAX, 0);  // gW, gS
+                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 1, 1);
+                comm_allreduce(ctx, reinterpret_cast<int64_t *>(hs.cand), world * k * 2, 0);  // all-gather by sum
+                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 2, 2);
+            }
         }
         NNC_CUDA(cudaMemcpyAsync(&ctl, &st->iter, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
         NNC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -824,6 +950,7 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         NNC_LAUNCH(ctx, ll_search_kernel, search_grid, 256, 0, st, h.d_sorted, samp, ptile);
         NNC_LAUNCH(ctx, ll_zone_kernel, zone_grid, 256, 0, st, h.d_sorted);
         NNC_LAUNCH(ctx, ll_count_kernel, 1, TB_THREADS, 0, st);
+        comm_allreduce(ctx, reinterpret_cast<int64_t *>(st->hist), k, 0);
         static_assert(sizeof(long long) == sizeof(int64_t), "histogram element size");
         NNC_CUDA(cudaMemcpyAsync(h_hist, st->hist, sizeof(int64_t) * k, cudaMemcpyDeviceToHost, ctx->stream));
     }
