@@ -153,9 +153,16 @@ int nnc_grad_segsum_f32(nnc_ctx *ctx, const float *grad, const void *codes, int6
                         double *out);
 
 /* ---- multi-GPU (one process per GPU; contiguous shards of the flattened tensor) ------------ */
-/* The library does not own a communicator.  The host supplies an all-reduce callback that sums
- * `count` int64 values (DEVICE buffer, in place) across ranks on `stream`; all exchanged
- * quantities are integers, so the result is bit-identical for any rank count. */
+/* The library does not own a communicator.  The host supplies an all-reduce callback that reduces
+ * `count` int64 values (DEVICE buffer, in place; op 0 sum, 1 min, 2 max) across ranks on `stream`;
+ * all exchanged quantities are integers, so the result is bit-identical for any rank count.
+ * With world > 1, nnc_stats_f32 / nnc_prune_f32 / nnc_kmeans1d_f32 / nnc_compress_f32 take THIS RANK'S
+ * slice of the flattened tensor (`n` = its length), which must be the slice nnc_shard_range assigns:
+ * shards are aligned to the tiles of NumPy's pairwise-summation tree so that the float32 mean / std
+ * are bit-exact for any rank count.  Per-rank outputs (mask, codes, labels) cover the slice; scalars,
+ * centroids and histograms are global and identical on every rank.  Only the seeded/explicit and
+ * linear initialisations are supported on shards (density's CDF helpers stay single-rank). */
+int nnc_shard_range(int64_t n, int rank, int world, int64_t *begin, int64_t *end);
 typedef int (*nnc_allreduce_i64_fn)(void *user, int64_t *dev_buf, int count, int op /*0 sum,1 min,2 max*/,
                                     void *cuda_stream);
 int nnc_ctx_set_comm(nnc_ctx *ctx, int rank, int world, nnc_allreduce_i64_fn fn, void *user);

@@ -33,7 +33,7 @@ EXPORTS = [
     "nnc_compact_nonzero_f32", "nnc_minmax_f32", "nnc_hist_edges_f32", "nnc_weight_cdf_f32", "nnc_gather_f32",
     "nnc_kmeans1d_f32", "nnc_assign_f32", "nnc_unpack_gather_f32", "nnc_grad_segsum_f32", "nnc_ctx_set_comm",
     "nnc_ctx_set_kernel_timing", "nnc_last_kernel_times", "nnc_ctx_total_launches",
-    "nnc_compress_f32",
+    "nnc_compress_f32", "nnc_shard_range",
 ]
 
 
@@ -58,6 +58,35 @@ class KMeansInfo(C.Structure):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p)
+
+
+def shard_range(n: int, rank: int, world: int):
+    """[begin, end) of the flattened n-element tensor that `rank` of `world` owns (reduction-tile aligned)."""
+    b, e = C.c_int64(), C.c_int64()
+    check(lib().nnc_shard_range(int(n), int(rank), int(world), C.byref(b), C.byref(e)))
+    return b.value, e.value
+
+
+class _DevView:
+    """A raw device pointer dressed as __cuda_array_interface__ so that torch can wrap it without a copy."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+def torch_allreduce(group=None):
+    """An all-reduce callback for Context.set_comm built on torch.distributed (NCCL on GPU boxes)."""
+    import torch
+    import torch.distributed as dist
+
+    ops = {0: dist.ReduceOp.SUM, 1: dist.ReduceOp.MIN, 2: dist.ReduceOp.MAX}
+
+    def allreduce(ptr, count, op, stream):
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+            t = torch.as_tensor(_DevView(ptr, count), device="cuda")
+            dist.all_reduce(t, op=ops[op], group=group)
+
+    return allreduce
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -105,6 +134,7 @@ def lib():
         L.nnc_ctx_set_kernel_timing.argtypes = [vp, i32]
         L.nnc_last_kernel_times.argtypes = [vp, P(C.c_char_p)]
         L.nnc_ctx_total_launches.argtypes = [vp, P(i64)]
+        L.nnc_shard_range.argtypes = [i64, i32, i32, P(i64), P(i64)]
         L.nnc_ctx_set_comm.argtypes = [vp, i32, i32, ALLREDUCE_FN, vp]
         for name in EXPORTS:
             fn = getattr(L, name)

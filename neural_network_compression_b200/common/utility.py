@@ -22,7 +22,7 @@ from .. import _native as N
 
 __all__ = [
     "prune_weigth", "apply_mask", "get_weight_distribution", "get_quantized_weight", "KMeansResult",
-    "compress_weight", "nonzero_weights", "weight_stats", "assign_codes", "dequantize", "cluster_gradient_sum", "index_bits",
+    "compress_weight", "init_distributed", "shard_range", "nonzero_weights", "weight_stats", "assign_codes", "dequantize", "cluster_gradient_sum", "index_bits",
 ]
 
 
@@ -82,6 +82,22 @@ class _Buf:
             tdt = {np.uint8: torch.uint8, np.int32: torch.int32, np.float32: torch.float32, np.bool_: torch.bool}[dtype]
             return torch.empty(int(n), dtype=tdt, device=self.arr.device)
         return np.empty(int(n), dtype=dtype)
+
+
+def init_distributed(group=None, device=None):
+    """Multi-GPU: one process per GPU.  Installs a torch.distributed all-reduce on this process's context; from then
+    on prune_weigth / get_quantized_weight / compress_weight take THIS RANK'S slice (see `shard_range`) of the
+    flattened tensor and return per-slice masks / codes with global thresholds, centroids and histograms."""
+    import torch.distributed as dist
+
+    ctx = N.default_context(device)
+    ctx.set_comm(dist.get_rank(group), dist.get_world_size(group), N.torch_allreduce(group))
+    return ctx
+
+
+def shard_range(n: int, rank: int, world: int):
+    """[begin, end) of the flattened n-element tensor owned by `rank` (aligned to NumPy's summation tree tiles)."""
+    return N.shard_range(n, rank, world)
 
 
 def _ctx_for(buf: _Buf) -> N.Context:

@@ -256,6 +256,35 @@ struct Call {  // RAII: device selection, arena reset, launch accounting, profil
     }
 };
 
+// Establishes the shard of this call: one rank owns everything; otherwise the ranks agree on the global element
+// count (all-reduce) and every rank must hold exactly the slice nnc_shard_range assigns to it.
+static void shard_setup(nnc_ctx *ctx, int64_t n_local) {
+    if (ctx->world <= 1) {
+        ctx->sh.n_global = n_local;
+        ctx->sh.begin = 0;
+        ctx->sh.t0 = 0;
+        ctx->sh.t1 = n_local > 0 ? np_plan(n_local).num_tiles : 0;
+        return;
+    }
+    int64_t *d = arena_alloc_t<int64_t>(ctx, 1);
+    NNC_CUDA(cudaMemcpyAsync(d, &n_local, sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    comm_allreduce(ctx, d, 1, 0);
+    int64_t n_global = 0;
+    NNC_CUDA(cudaMemcpyAsync(&n_global, d, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    NNC_CUDA(cudaStreamSynchronize(ctx->stream));
+    int64_t b = 0, e = 0;
+    uint32_t t0 = 0, t1 = 0;
+    if (n_global <= 0) NNC_FAIL(NNC_ERR_BAD_ARG, "sharded call on an empty tensor");
+    np_shard_range(n_global, ctx->rank, ctx->world, &b, &e, &t0, &t1);
+    if (e - b != n_local)
+        NNC_FAIL(NNC_ERR_BAD_ARG, "rank %d of %d holds %lld elements of a %lld-element tensor; nnc_shard_range assigns [%lld, %lld)",
+                 ctx->rank, ctx->world, (long long)n_local, (long long)n_global, (long long)b, (long long)e);
+    ctx->sh.n_global = n_global;
+    ctx->sh.begin = b;
+    ctx->sh.t0 = t0;
+    ctx->sh.t1 = t1;
+}
+
 }  // namespace nnc
 
 using namespace nnc;
@@ -399,6 +428,14 @@ int nnc_last_kernel_times(nnc_ctx *ctx, const char **out) {
     NNC_CATCH
 }
 
+int nnc_shard_range(int64_t n, int rank, int world, int64_t *begin, int64_t *end) {
+    NNC_TRY
+    if (n <= 0 || world < 1 || rank < 0 || rank >= world || !begin || !end)
+        NNC_FAIL(NNC_ERR_BAD_ARG, "nnc_shard_range: n = %lld, rank %d / world %d", (long long)n, rank, world);
+    np_shard_range(n, rank, world, begin, end, nullptr, nullptr);
+    NNC_CATCH
+}
+
 int nnc_ctx_set_comm(nnc_ctx *ctx, int rank, int world, nnc_allreduce_i64_fn fn, void *user) {
     NNC_TRY
     if (!ctx || world < 1 || rank < 0 || rank >= world || (world > 1 && !fn))
@@ -415,6 +452,7 @@ int nnc_stats_f32(nnc_ctx *ctx, const float *w, int64_t n, float *mean_out, floa
     NNC_TRY
     Call call(ctx);
     if (!w || n <= 0) NNC_FAIL(NNC_ERR_BAD_ARG, "nnc_stats_f32: w = %p, n = %lld", (const void *)w, (long long)n);
+    shard_setup(ctx, n);
     Staged sw = stage_in(ctx, w, sizeof(float) * (size_t)n);
     np_stats(ctx, static_cast<const float *>(sw.dev), n);
     prof_mark(ctx, "stats");
@@ -437,6 +475,7 @@ int nnc_prune_f32(nnc_ctx *ctx, float *w, int64_t n, double threshold, int std_s
         call.finish();
         return NNC_OK;
     }
+    shard_setup(ctx, n);
     Staged sw = stage_inout(ctx, w, sizeof(float) * (size_t)n);
     Staged sm = stage_out(ctx, mask, (size_t)n);
     prof_mark(ctx, "h2d");
@@ -586,11 +625,13 @@ int nnc_gather_f32(nnc_ctx *ctx, const float *w, int64_t n, const int64_t *idx, 
 static void kmeans_on_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *init, int k, int max_iter, double tol,
                              int flags, float *centers, float *centred, int32_t *labels, float *ris, uint8_t *packed, int bits,
                              int64_t *hist, nnc_kmeans_info *info) {
+    // n: elements of this rank's shard; n_global: of the whole tensor (they coincide on one rank)
     const bool init_linear = (flags & NNC_KM_INIT_LINEAR) != 0;
+    const int64_t n_global = ctx->sh.n_global;
     if ((!init && !init_linear) || n <= 0 || k <= 0 || max_iter < 1 || tol < 0)
         NNC_FAIL(NNC_ERR_BAD_ARG, "k-means: bad argument (n = %lld, k = %d, max_iter = %d)", (long long)n, k, max_iter);
     if (k > NNC_KMAX) NNC_FAIL(NNC_ERR_UNSUPPORTED, "k = %d exceeds NNC_KMAX = %d", k, NNC_KMAX);
-    if ((int64_t)k > n) NNC_FAIL(NNC_ERR_NOT_ENOUGH, "n_samples=%lld should be >= n_clusters=%d.", (long long)n, k);
+    if ((int64_t)k > n_global) NNC_FAIL(NNC_ERR_NOT_ENOUGH, "n_samples=%lld should be >= n_clusters=%d.", (long long)n_global, k);
     if (!init_linear)
         for (int j = 0; j < k; ++j)
             if (!isfinite(init[j])) NNC_FAIL(NNC_ERR_NONFINITE, "initial centroid %d is not finite", j);
@@ -600,7 +641,7 @@ static void kmeans_on_device(nnc_ctx *ctx, const float *d_w, int64_t n, const fl
     prof_mark(ctx, "prologue");
     const DevScalars sc = *ctx->h_scal;
     if (sc.n_nonfinite) NNC_FAIL(NNC_ERR_NONFINITE, "Input X contains NaN or infinity.");
-    const int64_t n_nz = (int64_t)sc.n_nz;
+    const int64_t n_nz = (int64_t)(ctx->world > 1 ? sc.n_nz_local : sc.n_nz);  // of this shard
     // 2. survivors -> sorted
     float *buf_a = arena_alloc_t<float>(ctx, (size_t)std::max<int64_t>(n_nz, 1));
     float *buf_b = arena_alloc_t<float>(ctx, (size_t)std::max<int64_t>(n_nz, 1));
@@ -616,7 +657,7 @@ static void kmeans_on_device(nnc_ctx *ctx, const float *d_w, int64_t n, const fl
     h.d_sorted = d_sorted;
     h.n_nz = n_nz;
     h.n0 = n - n_nz;
-    h.n = n;
+    h.n = n_global;
     h.k = k;
     h.mean = sc.mean;
     std::vector<float> c_final(k), c_emit(k), lin;
@@ -661,7 +702,7 @@ static void kmeans_on_device(nnc_ctx *ctx, const float *d_w, int64_t n, const fl
         info->mean = sc.mean;
         info->tol = lr.tol;
         info->inertia = inertia;
-        info->n_nonzero = n_nz;
+        info->n_nonzero = (int64_t)sc.n_nz;
     }
 }
 
@@ -671,6 +712,7 @@ int nnc_kmeans1d_f32(nnc_ctx *ctx, const float *w, int64_t n, const float *init,
     NNC_TRY
     Call call(ctx);
     if (!w || n <= 0) NNC_FAIL(NNC_ERR_BAD_ARG, "nnc_kmeans1d_f32: empty input");
+    shard_setup(ctx, n);
     Staged sw = stage_in(ctx, w, sizeof(float) * (size_t)n);
     prof_mark(ctx, "h2d");
     kmeans_on_device(ctx, static_cast<const float *>(sw.dev), n, init, k, max_iter, tol, flags, centers, centred, labels, ris,
@@ -687,6 +729,7 @@ int nnc_compress_f32(nnc_ctx *ctx, float *w, int64_t n, double threshold, int st
     NNC_TRY
     Call call(ctx);
     if (!w || !mask || n <= 0) NNC_FAIL(NNC_ERR_BAD_ARG, "nnc_compress_f32: null buffer or empty input");
+    shard_setup(ctx, n);
     Staged sw = stage_inout(ctx, w, sizeof(float) * (size_t)n);
     Staged sm = stage_out(ctx, mask, (size_t)n);
     prof_mark(ctx, "h2d");

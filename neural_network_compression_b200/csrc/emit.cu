@@ -386,6 +386,8 @@ void emit_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *h_centr
         emit_launch<false, true, 0>(ctx, grid, d_w, n, ed, mean, inertia_scale, d_labels, d_ris, d_packed, bits, want_hist);
     else
         emit_launch<false, false, 0>(ctx, grid, d_w, n, ed, mean, inertia_scale, d_labels, d_ris, d_packed, bits, want_hist);
+    if (h_inertia) comm_allreduce(ctx, reinterpret_cast<int64_t *>(&ed->inertia_q), 1, 0);
+    if (h_hist) comm_allreduce(ctx, reinterpret_cast<int64_t *>(ed->hist), k, 0);
     if (h_hist || h_inertia) {
         std::vector<unsigned long long> hh(k + 1);
         if (h_hist) NNC_CUDA(cudaMemcpyAsync(hh.data(), ed->hist, sizeof(unsigned long long) * k, cudaMemcpyDeviceToHost, ctx->stream));

@@ -58,7 +58,8 @@ struct DevScalars {
     uint32_t amax_bits;               // largest |x| bit pattern (>= 0x7f800000: a NaN or infinity is present)
     uint32_t amin_nz_m1;              // smallest non-zero |x| bit pattern, minus one (0xffffffff: all zero)
     float fmin_all, fmax_all;         // float min / max over all elements (scratch; folded into min_ord / max_ord)
-    unsigned long long n_nz;          // non-zero count (also the compaction cursor)
+    unsigned long long n_nz;          // non-zero count (global once the ranks have exchanged)
+    unsigned long long n_nz_local;    // ... of this rank's shard
     int pad_;
 };
 
@@ -101,7 +102,11 @@ struct nnc_ctx {
     std::string prof_names;
     int64_t launches = 0;       // kernels launched by the current / last call
     int64_t last_launches = 0;
-    // multi-GPU
+    // multi-GPU: shard of the current call (set by shard_setup at the entry point)
+    struct {
+        int64_t n_global = 0, begin = 0;
+        uint32_t t0 = 0, t1 = 0;
+    } sh;
     int rank = 0, world = 1;
     nnc_allreduce_i64_fn allreduce = nullptr;
     void *allreduce_user = nullptr;
@@ -156,6 +161,7 @@ void comm_allreduce(nnc_ctx *ctx, int64_t *d_buf, int count, int op);
 
 // ---- kernels' host entry points (one per .cu file) ----------------------------------------------
 // reduce_np.cu
+void np_shard_range(int64_t n, int rank, int world, int64_t *begin, int64_t *end, uint32_t *t0, uint32_t *t1);
 struct NpPlan {
     int depth;
     uint32_t num_tiles;

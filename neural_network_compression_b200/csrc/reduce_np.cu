@@ -48,7 +48,7 @@ NpPlan np_plan(int64_t n) {
 }
 size_t np_partials_bytes(const NpPlan &p) { return sizeof(float) * 2 * (size_t)p.num_tiles; }
 
-__device__ __forceinline__ void np_tile_root(int64_t n, int depth, uint32_t t, int64_t &off, int &sz) {
+__host__ __device__ __forceinline__ void np_tile_root(int64_t n, int depth, uint32_t t, int64_t &off, int &sz) {
     int64_t o = 0, s = n;
     for (int lvl = depth - 1; lvl >= 0; --lvl) {
         int64_t n2 = s / 2;
@@ -380,9 +380,11 @@ __global__ void np_tiles_kernel(int64_t n, int depth, NpTileDesc *desc) {
     desc[t] = d;
 }
 
+// a: this rank's shard (elements [shard_begin, ...) of the flattened tensor); tiles [t0, t1) belong to it
 template <class V>
-__global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, int depth, int vec_ok,
-                                                             const NpTileDesc *__restrict__ desc, float *partials, V v) {
+__global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, uint32_t t0, uint32_t t1, int64_t shard_begin,
+                                                             int vec_ok, const NpTileDesc *__restrict__ desc, float *partials,
+                                                             V v) {
     __shared__ __align__(16) float tile[NP_TILE_SMEM];
     __shared__ float heap_val[2][64];
     __shared__ unsigned int s_cnt[2];
@@ -393,11 +395,10 @@ __global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, int
         if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
         __syncthreads();
     }
-    const uint32_t num_tiles = 1u << depth;
     const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;
     int buf = 0;
-    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, buf ^= 1) {
-        const int64_t off = desc[t].off;
+    for (uint32_t t = t0 + blockIdx.x; t < t1; t += gridDim.x, buf ^= 1) {
+        const int64_t off = desc[t].off - shard_begin;  // offset inside the shard
         const int sz = desc[t].sz;
         const uint32_t gd = desc[t].grp[grp];
         // ---- stage + visit: global -> terms in shared memory
@@ -633,20 +634,113 @@ __global__ void __launch_bounds__(256) mask_apply_kernel(float *w, const uint8_t
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline bool aligned4(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
 
-static int tree_grid(nnc_ctx *ctx, const NpPlan &p) {
+// ---- sharding: a rank owns a contiguous range of the reduction tree's tiles ----------------------------------
+void np_shard_range(int64_t n, int rank, int world, int64_t *begin, int64_t *end, uint32_t *t0_out, uint32_t *t1_out) {
+    const NpPlan p = np_plan(n);
+    uint32_t t0 = 0, t1 = p.num_tiles;
+    if (world > 1) {
+        if (p.num_tiles >= (uint32_t)world) {
+            t0 = (uint32_t)((uint64_t)p.num_tiles * rank / world);
+            t1 = (uint32_t)((uint64_t)p.num_tiles * (rank + 1) / world);
+        } else {  // too small to cut: rank 0 owns everything
+            t0 = rank == 0 ? 0 : p.num_tiles;
+            t1 = p.num_tiles;
+        }
+    }
+    int64_t off0 = n, off1 = n;
+    int sz;
+    if (t0 < p.num_tiles) np_tile_root(n, p.depth, t0, off0, sz);
+    if (t1 < p.num_tiles) np_tile_root(n, p.depth, t1, off1, sz);
+    *begin = off0;
+    *end = off1;
+    if (t0_out) *t0_out = t0;
+    if (t1_out) *t1_out = t1;
+}
+
+// ---- scalar exchange between ranks (all integers on the wire; doubles travel as per-rank slots) -------------------
+enum { EX_NONE = 0, EX_STATS = 1, EX_PRUNE = 2, EX_QUANT = 3 };
+
+__global__ void scal_pack_kernel(DevScalars *sc, long long *buf, int mode, int rank, int world) {
+    if (mode == EX_STATS) {
+        for (int r = 0; r < world; ++r) {
+            buf[r] = r == rank ? __double_as_longlong(sc->sum_d) : 0;
+            buf[world + r] = r == rank ? __double_as_longlong(sc->sumsq_d) : 0;
+        }
+    } else if (mode == EX_PRUNE) {
+        buf[0] = (long long)sc->n_pruned;
+        buf[1] = (long long)sc->band_dropped;
+    } else if (mode == EX_QUANT) {
+        sc->n_nz_local = sc->n_nz;
+        buf[0] = (long long)sc->n_nz;
+        buf[1] = (long long)sc->n_nonfinite;
+        // second buffer (max): minima travel complemented
+        buf[8] = (long long)sc->max_ord;
+        buf[9] = (long long)(0xffffffffu - sc->min_ord);
+        buf[10] = (long long)sc->amax_bits;
+        buf[11] = (long long)(0xffffffffu - sc->amin_nz_m1);
+    }
+}
+__global__ void scal_unpack_kernel(DevScalars *sc, const long long *buf, int mode, int world) {
+    if (mode == EX_STATS) {
+        double a = 0.0, b = 0.0;
+        for (int r = 0; r < world; ++r) {  // rank order: every rank gets the same double
+            a += __longlong_as_double(buf[r]);
+            b += __longlong_as_double(buf[world + r]);
+        }
+        sc->sum_d = a;
+        sc->sumsq_d = b;
+    } else if (mode == EX_PRUNE) {
+        sc->n_pruned = (unsigned long long)buf[0];
+        sc->band_dropped = (unsigned long long)buf[1];
+    } else if (mode == EX_QUANT) {
+        sc->n_nz = (unsigned long long)buf[0];
+        sc->n_nonfinite = (unsigned long long)buf[1];
+        sc->max_ord = (uint32_t)buf[8];
+        sc->min_ord = 0xffffffffu - (uint32_t)buf[9];
+        sc->amax_bits = (uint32_t)buf[10];
+        sc->amin_nz_m1 = 0xffffffffu - (uint32_t)buf[11];
+    }
+}
+
+static void exchange_scalars(nnc_ctx *ctx, int mode) {
+    if (ctx->world <= 1 || mode == EX_NONE) return;
+    const int world = ctx->world;
+    long long *buf = arena_alloc_t<long long>(ctx, std::max(16, 2 * world));
+    NNC_LAUNCH(ctx, scal_pack_kernel, 1, 1, 0, ctx->d_scal, buf, mode, ctx->rank, world);
+    if (mode == EX_STATS) {
+        comm_allreduce(ctx, reinterpret_cast<int64_t *>(buf), 2 * world, 0);
+    } else if (mode == EX_PRUNE) {
+        comm_allreduce(ctx, reinterpret_cast<int64_t *>(buf), 2, 0);
+    } else {
+        comm_allreduce(ctx, reinterpret_cast<int64_t *>(buf), 2, 0);
+        comm_allreduce(ctx, reinterpret_cast<int64_t *>(buf + 8), 4, 2);
+    }
+    NNC_LAUNCH(ctx, scal_unpack_kernel, 1, 1, 0, ctx->d_scal, buf, mode, world);
+}
+
+static int tree_grid(nnc_ctx *ctx, uint32_t tiles) {
     int64_t g = (int64_t)ctx->sm_count * 8;
-    if ((int64_t)p.num_tiles < g) g = p.num_tiles;
+    if ((int64_t)tiles < g) g = tiles;
     return (int)g;
 }
 
+// One reduction over the whole (possibly sharded) tensor: tile descriptors for the GLOBAL n, this rank's tiles
+// reduced here, the float32 tile partials all-gathered bit for bit (sum of int64 words, the other ranks' slots are
+// zero), and the fold done redundantly -- and therefore identically -- on every rank.
 template <class V>
-static NpTileDesc *run_tree(nnc_ctx *ctx, const float *d_w, int64_t n, V v, const FinArgs &fa) {
+static NpTileDesc *run_tree(nnc_ctx *ctx, const float *d_w, V v, const FinArgs &fa, int exchange_mode) {
+    const int64_t n = ctx->sh.n_global;
     NpPlan p = np_plan(n);
-    float *partials = arena_alloc_t<float>(ctx, 2 * (size_t)p.num_tiles);
+    float *partials = arena_alloc_t<float>(ctx, 2 * (size_t)p.num_tiles + 2);
     NpTileDesc *desc = arena_alloc_t<NpTileDesc>(ctx, p.num_tiles);
     NNC_LAUNCH(ctx, np_tiles_kernel, (p.num_tiles + 127) / 128, 128, 0, n, p.depth, desc);
-    NNC_LAUNCH(ctx, np_tree_kernel<V>, tree_grid(ctx, p), NP_THREADS, 0, d_w, p.depth, aligned16(d_w) ? 1 : 0, desc, partials,
-               v);
+    if (ctx->world > 1) NNC_CUDA(cudaMemsetAsync(partials, 0, sizeof(float) * (2 * (size_t)p.num_tiles + 2), ctx->stream));
+    const uint32_t t0 = ctx->sh.t0, t1 = ctx->sh.t1;
+    if (t1 > t0)
+        NNC_LAUNCH(ctx, np_tree_kernel<V>, tree_grid(ctx, t1 - t0), NP_THREADS, 0, d_w, t0, t1, ctx->sh.begin,
+                   aligned16(d_w) ? 1 : 0, desc, partials, v);
+    if (ctx->world > 1) comm_allreduce(ctx, reinterpret_cast<int64_t *>(partials), (int)((p.num_tiles + 1) / 2), 0);
+    exchange_scalars(ctx, exchange_mode);
     NNC_LAUNCH(ctx, np_final_kernel, 1, 1024, 0, partials, p.num_tiles, ctx->d_scal, fa);
     return desc;
 }
@@ -665,22 +759,26 @@ void np_stats(nnc_ctx *ctx, const float *d_w, int64_t n) {
     clear_scalars(ctx);
     VisitStats v1;
     v1.sc = ctx->d_scal;
-    run_tree(ctx, d_w, n, v1, FinArgs{FIN_MEAN, n, 0.0, 0, 1});
+    const int64_t ng = ctx->sh.n_global;
+    (void)n;
+    run_tree(ctx, d_w, v1, FinArgs{FIN_MEAN, ng, 0.0, 0, 1}, EX_NONE);
     VisitCenSq v2;
     v2.sc = ctx->d_scal;
     v2.mean = 0.f;
-    run_tree(ctx, d_w, n, v2, FinArgs{FIN_VAR, n, 0.0, 0, 1});
+    run_tree(ctx, d_w, v2, FinArgs{FIN_VAR, ng, 0.0, 0, 1}, EX_NONE);
 }
 
 QuantPrologue quant_prologue(nnc_ctx *ctx, const float *d_w, int64_t n) {
     clear_scalars(ctx);
     QuantPrologue q;
-    q.num_tiles = np_plan(n).num_tiles;
+    const int64_t ng = ctx->sh.n_global;
+    (void)n;
+    q.num_tiles = np_plan(ng).num_tiles;
     q.tile_counts = arena_alloc_t<unsigned int>(ctx, q.num_tiles);
     VisitQuant v;
     v.sc = ctx->d_scal;
     v.tile_counts = q.tile_counts;
-    q.tile_desc = run_tree(ctx, d_w, n, v, FinArgs{FIN_MEAN, n, 0.0, 0, 1});
+    q.tile_desc = run_tree(ctx, d_w, v, FinArgs{FIN_MEAN, ng, 0.0, 0, 1}, EX_QUANT);
     return q;
 }
 
@@ -723,15 +821,17 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const unsigned int *cou
     if (threadIdx.x == blockDim.x - 1) base[num_tiles] = incl;
 }
 
+// w: this rank's shard; desc / base: the shard's tiles (descriptor offsets are global: shard_begin is subtracted)
 __global__ void __launch_bounds__(NP_THREADS) tile_compact_kernel(const float *__restrict__ w, int vec_ok,
                                                                    const NpTileDesc *__restrict__ desc, uint32_t num_tiles,
+                                                                   int64_t shard_begin,
                                                                    const unsigned long long *__restrict__ base,
                                                                    float *__restrict__ out) {
     __shared__ int s_warp_cnt[2][NP_THREADS / 32];
     const int lane = lane_id(), wid = warp_id();
     int buf = 0;
     for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, buf ^= 1) {
-        const int64_t off = desc[t].off;
+        const int64_t off = desc[t].off - shard_begin;
         const int sz = desc[t].sz;
         // warp `wid` owns elements [512 wid, 512 (wid + 1)) of the tile as 4 rows of 128: (row, lane, component) is
         // element order, so the survivors keep their order
@@ -778,11 +878,13 @@ __global__ void __launch_bounds__(NP_THREADS) tile_compact_kernel(const float *_
 }
 
 void compact_tiles_device(nnc_ctx *ctx, const float *d_w, const QuantPrologue &q, float *d_out) {
-    unsigned long long *base = arena_alloc_t<unsigned long long>(ctx, (size_t)q.num_tiles + 1);
-    NNC_LAUNCH(ctx, tile_scan_kernel, 1, 1024, 0, q.tile_counts, q.num_tiles, base);
-    const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, q.num_tiles);
+    const uint32_t t0 = ctx->sh.t0, tiles = ctx->sh.t1 - ctx->sh.t0;
+    if (tiles == 0) return;
+    unsigned long long *base = arena_alloc_t<unsigned long long>(ctx, (size_t)tiles + 1);
+    NNC_LAUNCH(ctx, tile_scan_kernel, 1, 1024, 0, q.tile_counts + t0, tiles, base);
+    const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, tiles);
     NNC_LAUNCH(ctx, tile_compact_kernel, grid, NP_THREADS, 0, d_w, aligned16(d_w) ? 1 : 0,
-               static_cast<const NpTileDesc *>(q.tile_desc), q.num_tiles, base, d_out);
+               static_cast<const NpTileDesc *>(q.tile_desc) + t0, tiles, ctx->sh.begin, base, d_out);
 }
 
 void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth, int thr_mode, uint8_t *d_mask) {
@@ -793,13 +895,15 @@ void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth,
         double thr = thr_mode == 0 ? (double)(float)q : q;
         NNC_LAUNCH(ctx, set_thr_kernel, 1, 1, 0, ctx->d_scal, thr);
         NNC_LAUNCH(ctx, prune_apply_kernel, ew_grid, 256, 0, d_w, d_mask, n, ctx->d_scal, vec_ok, 0);
+        exchange_scalars(ctx, EX_PRUNE);
         prof_mark(ctx, "apply");
         return;
     }
     // pass 1: NumPy mean + fp64 estimate of the std -> speculation band
     VisitStats v1;
     v1.sc = ctx->d_scal;
-    run_tree(ctx, d_w, n, v1, FinArgs{FIN_PRUNE1, n, q, thr_mode, 1});
+    const int64_t ng = ctx->sh.n_global;
+    run_tree(ctx, d_w, v1, FinArgs{FIN_PRUNE1, ng, q, thr_mode, 1}, EX_STATS);
     prof_mark(ctx, "mean");
     // pass 2: NumPy var/std/threshold + speculative apply
     unsigned long long cap = (unsigned long long)std::max<int64_t>(65536, n / 256);
@@ -814,9 +918,10 @@ void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth,
     v2.side_cap = cap;
     v2.mask_vec_ok = aligned4(d_mask) ? 1 : 0;
     v2.mean = v2.lo = v2.hi = 0.f;
-    run_tree(ctx, d_w, n, v2, FinArgs{FIN_PRUNE2, n, q, thr_mode, 1});
+    run_tree(ctx, d_w, v2, FinArgs{FIN_PRUNE2, ng, q, thr_mode, 1}, EX_NONE);
     prof_mark(ctx, "var+apply");
     NNC_LAUNCH(ctx, prune_fixup_kernel, 64, 256, 0, d_w, d_mask, side_idx, side_val, cap, ctx->d_scal);
+    exchange_scalars(ctx, EX_PRUNE);
     prof_mark(ctx, "fixup");
     read_scalars(ctx);
     const DevScalars &s = *ctx->h_scal;
@@ -828,6 +933,9 @@ void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth,
         if (s.spec_failed && s.thr < s.band_lo && s.n_pruned > 0)
             NNC_FAIL(NNC_ERR_INTERNAL, "prune: exact threshold %.9g below speculation band [%.9g, %.9g]", s.thr, s.band_lo,
                      s.band_hi);
+        if (ctx->world > 1)  // n_pruned is already a global count: the resolve pass would add local counts to it
+            NNC_FAIL(NNC_ERR_INTERNAL, "prune: speculation band missed on a sharded tensor (thr %.9g, band [%.9g, %.9g])", s.thr,
+                     s.band_lo, s.band_hi);
         NNC_LAUNCH(ctx, prune_apply_kernel, ew_grid, 256, 0, d_w, d_mask, n, ctx->d_scal, vec_ok, 1);
         prof_mark(ctx, "resolve");
         read_scalars(ctx);

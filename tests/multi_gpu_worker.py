@@ -1,0 +1,68 @@
+"""Worker of the multi-GPU parity test: launched by torchrun, one rank per GPU.
+
+Every rank builds the same full tensor, keeps the slice `shard_range` assigns to it, runs the sharded path and
+compares with the single-rank result it computes itself on its own GPU (a second, rank-less context)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from neural_network_compression_b200 import _native as N
+    from neural_network_compression_b200.common import utility as U
+
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else (1 << 22) + 12345
+    failures = []
+    for bits, seed in ((8, 1), (4, 2), (2, 3)):
+        g = torch.Generator(device="cuda").manual_seed(1000 + seed)
+        full = torch.empty(n, device="cuda").normal_(0.0, 0.02, generator=g)
+        full[::9] = 0.0
+        # ---- single-rank reference on this GPU
+        N._tls.ctx = {}
+        ref_w = full.clone()
+        ref_mask, ref_km = U.compress_weight(ref_w, 1.0, True, bits, "linear")
+        ref_thr = U.prune_weigth.last_threshold
+        ref_ris, ref_full_km = U.get_quantized_weight(ref_w, bits, "linear")
+        # ---- sharded
+        N._tls.ctx = {}
+        U.init_distributed()
+        b, e = U.shard_range(n, rank, world)
+        mine = full[b:e].clone()
+        mask, km = U.compress_weight(mine, 1.0, True, bits, "linear")
+        ok = True
+        ok &= U.prune_weigth.last_threshold == ref_thr
+        ok &= bool(torch.equal(mask, ref_mask[b:e])) and bool(torch.equal(mine, ref_w[b:e]))
+        ok &= km.cluster_centers_.tobytes() == ref_km.cluster_centers_.tobytes()
+        ok &= km.n_iter_ == ref_km.n_iter_ and km.n_relocations == ref_km.n_relocations
+        ok &= bool(np.array_equal(km.code_histogram, ref_km.code_histogram))
+        per = km.code_bits
+        if (b * per) % 8 == 0:
+            ok &= bool(torch.equal(km.packed_codes, ref_km.packed_codes[b * per // 8: (e * per + 7) // 8]))
+        # the reference-signature helper on the shard: labels / ris of the slice, inertia global
+        ris, km2 = U.get_quantized_weight(mine, bits, "linear")
+        ok &= bool(torch.equal(km2.labels_, ref_full_km.labels_[b:e])) and bool(torch.equal(ris, ref_ris[b:e]))
+        ok &= km2.inertia_ == ref_full_km.inertia_
+        # np.std of the sharded tensor
+        m, v, s = U.weight_stats(full[b:e].clone())
+        ok &= (m, v, s) == tuple(np.float32(x) for x in (np.mean(full.cpu().numpy()), np.var(full.cpu().numpy()), np.std(full.cpu().numpy())))
+        if not ok:
+            failures.append((bits, rank))
+        print("rank %d bits %d iters %d reloc %d thr %.9g %s" % (rank, bits, km.n_iter_, km.n_relocations, ref_thr, "OK" if ok else "MISMATCH"), flush=True)
+    t = torch.tensor([len(failures)], device="cuda")
+    dist.all_reduce(t)
+    dist.destroy_process_group()
+    if int(t.item()):
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()

@@ -385,3 +385,24 @@ def test_compress_weight_matches_separate_steps(U, mode, bits):
     if mode == "linear":
         assert c.tobytes() == w.tobytes()
     assert np.array_equal(mask2, mask_ref) and np.array_equal(km2.packed_codes, km_ref.packed_codes)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# multi-GPU: sharded run == single-rank run, bit for bit (needs >= 2 GPUs; the driver's 1-GPU box skips it)
+# ---------------------------------------------------------------------------------------------------------
+def test_sharded_equals_single_rank():
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if ngpu < 4 else 4
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multi_gpu_worker.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", worker], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("OK") == 3 * world and "MISMATCH" not in r.stdout
