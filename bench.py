@@ -27,6 +27,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
 
 import numpy as np  # noqa: E402
 
@@ -47,7 +49,7 @@ def env_int(name, default):
 # clocks
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -61,12 +63,15 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock over the samples taken between the two wall-clock times (the timed region)."""
+        import datetime
+
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -82,6 +87,10 @@ class ClockSampler:
                 if len(f) < 9:
                     continue
                 try:
+                    if t_begin is not None:
+                        ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                        if ts < t_begin - 0.02 or ts > t_end + 0.02:
+                            continue
                     sm.append(float(f[1]))
                     out["sm_max_mhz"] = float(f[2])
                 except ValueError:
@@ -93,8 +102,7 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            busy = [x for x in sm if x >= 0.5 * max(sm)] or sm
-            out["sm_mhz"] = statistics.median(busy)
+            out["sm_mhz"] = statistics.median(sm)
             out["samples"] = len(sm)
         out["reasons"] = sorted(reasons)
         return out
@@ -159,6 +167,10 @@ def workload_config(args, world):
 # CUDA arm
 # ---------------------------------------------------------------------------------------------------------
 def run_b200(args):
+    # libraries (NCCL's version banner, ...) may write to stdout: rank 0's JSON line goes to the real stdout, the
+    # rest of the run sees stderr there
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
 
     from neural_network_compression_b200 import _native as N
@@ -175,7 +187,10 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ctx = N.default_context(local)
-    n_local = args.n // world
+    if world > 1:
+        U.init_distributed(device=local)
+    lo, hi = U.shard_range(args.n, rank, world)  # contiguous slice of the flattened layer owned by this rank
+    n_local = hi - lo
     K, W = args.steps, args.warmup
 
     def barrier():
@@ -198,24 +213,34 @@ def run_b200(args):
         mask, km = U.compress_weight(t, QUALITY, True, BITS, MODE)
         return mask, km
 
-    # ---- warm-up
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()  # running well before the timed region: nvidia-smi needs a moment to deliver its first sample
+    # ---- warm-up (the last warm-up step runs with every kernel bracketed by events: it names the dominant kernel
+    # and gives the per-kernel breakdown; the timed region then brackets only that kernel, so that the event
+    # overhead -- two records per launch -- stays out of `value`)
     done = 0
     refill(min(pool, W))
+    warm_ktimes = {}
     for i in range(W):
         if i and i % pool == 0:
             refill(min(pool, W - i))
+        if i == W - 1:
+            ctx.set_kernel_timing(True)
         step(bufs[i % pool])
+    warm_ktimes = {name: [c, ms] for name, (c, ms) in ctx.last_kernel_times().items()}
+    hbm = {name: v for name, v in warm_ktimes.items() if kernel_bytes(name, 1.0, 0.3) > 0}  # streaming kernels only
+    dom_name = max(hbm.items(), key=lambda kv: kv[1][1])[0] if hbm else None
+    dom_filter = dom_name.strip("()").split("<")[0] if dom_name else None
     # ---- timed region: K steps in chunks of `pool` fresh tensors
-    clocks = ClockSampler(local)
-    ctx.set_kernel_timing(True)
+    ctx.set_kernel_timing(True, dom_filter)
     launches0 = ctx.total_launches()
     total_ms = 0.0
     n_iters = []
     launches = 0
     ktimes = {}
     phases = {}
-    if rank == 0:
-        clocks.start()
+    t_region0 = time.time()
     while done < K:
         cnt = min(pool, K - done)
         refill(cnt)
@@ -233,7 +258,8 @@ def run_b200(args):
         barrier()
         total_ms += ev0.elapsed_time(ev1)
         done += cnt
-    clk = clocks.stop() if rank == 0 else None
+    t_region1 = time.time()
+    clk = clocks.stop(t_region0, t_region1) if rank == 0 else None
     ktimes = {name: [c, ms] for name, (c, ms) in ctx.last_kernel_times().items()}
     launches = ctx.total_launches() - launches0
     ctx.set_kernel_timing(False)
@@ -260,10 +286,9 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    survivors = km.n_nonzero
-    s_frac = survivors / float(n_local)
-    dom = max(ktimes.items(), key=lambda kv: kv[1][1]) if ktimes else (None, (1, 0.0))
-    dom_name, (dom_cnt, dom_ms) = dom
+    survivors = km.n_nonzero / world  # n_nonzero is the global count
+    s_frac = km.n_nonzero / float(args.n)
+    dom_cnt, dom_ms = ktimes.get(dom_name, (1, 0.0))
     kbytes = kernel_bytes(dom_name, n_local, survivors)
     avg_ms = dom_ms / max(dom_cnt, 1)
     achieved = kbytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
@@ -285,7 +310,8 @@ def run_b200(args):
         "n_iter": n_iters,
         "survivor_fraction": s_frac,
         "phase_ms_per_step": {kname: ms / K for kname, ms in sorted(phases.items())},
-        "kernel_ms_per_step": {kname: v[1] / K for kname, v in sorted(ktimes.items(), key=lambda kv: -kv[1][1])},
+        "kernel_ms_per_step": {kname: v[1] for kname, v in sorted(warm_ktimes.items(), key=lambda kv: -kv[1][1])},
+        "kernel_ms_note": "per-kernel CUDA-event times of the last warm-up step; the roofline kernel is timed inside the timed region",
     }
     if e2e is not None:
         line["e2e"] = e2e
@@ -297,7 +323,7 @@ def run_b200(args):
             "sample": "2^%d-weight tensor of the same distribution, same pipeline to convergence (%d Lloyd iterations, %.1f s), "
                       "scalar C restatement of numpy/sklearn float32 arithmetic" % (int(np.log2(args.cpu_sample)), it_cpu, t_cpu),
         }
-    print(json.dumps(line), flush=True)
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
     return 0

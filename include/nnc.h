@@ -65,10 +65,11 @@ int nnc_timer_stop(nnc_ctx *ctx, float *ms_out);
 int nnc_last_profile(nnc_ctx *ctx, float *ms_out, int cap, int *n_out, const char **names_out,
                      int64_t *launches_out);
 
-/* Benchmarks: when on, every kernel launch is bracketed by CUDA events on the context's stream;
+/* Benchmarks: when on, every kernel launch (or only those whose kernel name contains `name_filter`, when it
+ * is not NULL / empty) is bracketed by CUDA events on the context's stream;
  * nnc_last_kernel_times returns "kernel:launches:total_ms;..." accumulated since the last
  * nnc_ctx_set_kernel_timing call.  nnc_ctx_total_launches: kernels launched over the context's lifetime. */
-int nnc_ctx_set_kernel_timing(nnc_ctx *ctx, int on);
+int nnc_ctx_set_kernel_timing(nnc_ctx *ctx, int on, const char *name_filter);
 int nnc_last_kernel_times(nnc_ctx *ctx, const char **out);
 int nnc_ctx_total_launches(nnc_ctx *ctx, int64_t *out);
 
@@ -163,6 +164,11 @@ int nnc_grad_segsum_f32(nnc_ctx *ctx, const float *grad, const void *codes, int6
  * centroids and histograms are global and identical on every rank.  Only the seeded/explicit and
  * linear initialisations are supported on shards (density's CDF helpers stay single-rank). */
 int nnc_shard_range(int64_t n, int rank, int world, int64_t *begin, int64_t *end);
+/* Preferred transport: the library's own NCCL communicator (libnccl.so.2 bound at run time).  Rank 0 calls
+ * nnc_comm_unique_id, the host ships the 128 bytes to every rank (any side channel), all ranks call
+ * nnc_ctx_init_nccl.  All-reduces are then enqueued natively on the context's stream (no host callback). */
+int nnc_comm_unique_id(char *out128);
+int nnc_ctx_init_nccl(nnc_ctx *ctx, const char *id128, int rank, int world);
 typedef int (*nnc_allreduce_i64_fn)(void *user, int64_t *dev_buf, int count, int op /*0 sum,1 min,2 max*/,
                                     void *cuda_stream);
 int nnc_ctx_set_comm(nnc_ctx *ctx, int rank, int world, nnc_allreduce_i64_fn fn, void *user);

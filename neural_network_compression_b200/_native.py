@@ -33,7 +33,7 @@ EXPORTS = [
     "nnc_compact_nonzero_f32", "nnc_minmax_f32", "nnc_hist_edges_f32", "nnc_weight_cdf_f32", "nnc_gather_f32",
     "nnc_kmeans1d_f32", "nnc_assign_f32", "nnc_unpack_gather_f32", "nnc_grad_segsum_f32", "nnc_ctx_set_comm",
     "nnc_ctx_set_kernel_timing", "nnc_last_kernel_times", "nnc_ctx_total_launches",
-    "nnc_compress_f32", "nnc_shard_range",
+    "nnc_compress_f32", "nnc_shard_range", "nnc_comm_unique_id", "nnc_ctx_init_nccl",
 ]
 
 
@@ -58,6 +58,12 @@ class KMeansInfo(C.Structure):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p)
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    check(lib().nnc_comm_unique_id(buf))
+    return buf.raw
 
 
 def shard_range(n: int, rank: int, world: int):
@@ -131,10 +137,12 @@ def lib():
         L.nnc_assign_f32.argtypes = [vp, vp, i64, vp, i32, f32, vp, vp, vp, vp, i32, vp, P(f64)]
         L.nnc_unpack_gather_f32.argtypes = [vp, vp, i64, i32, vp, i32, vp]
         L.nnc_grad_segsum_f32.argtypes = [vp, vp, vp, i64, i32, i32, vp]
-        L.nnc_ctx_set_kernel_timing.argtypes = [vp, i32]
+        L.nnc_ctx_set_kernel_timing.argtypes = [vp, i32, C.c_char_p]
         L.nnc_last_kernel_times.argtypes = [vp, P(C.c_char_p)]
         L.nnc_ctx_total_launches.argtypes = [vp, P(i64)]
         L.nnc_shard_range.argtypes = [i64, i32, i32, P(i64), P(i64)]
+        L.nnc_comm_unique_id.argtypes = [C.c_char_p]
+        L.nnc_ctx_init_nccl.argtypes = [vp, C.c_char_p, i32, i32]
         L.nnc_ctx_set_comm.argtypes = [vp, i32, i32, ALLREDUCE_FN, vp]
         for name in EXPORTS:
             fn = getattr(L, name)
@@ -200,8 +208,8 @@ class Context:
             out[kname] = out.get(kname, 0.0) + buf[i]
         return out, launches.value
 
-    def set_kernel_timing(self, on: bool):
-        check(lib().nnc_ctx_set_kernel_timing(self._h, int(bool(on))))
+    def set_kernel_timing(self, on: bool, name_filter: str | None = None):
+        check(lib().nnc_ctx_set_kernel_timing(self._h, int(bool(on)), name_filter.encode() if name_filter else None))
 
     def total_launches(self) -> int:
         v = C.c_int64()
@@ -218,6 +226,11 @@ class Context:
                 name, cnt, ms = item.rsplit(":", 2)
                 out[name] = (int(cnt), float(ms))
         return out
+
+    def init_nccl(self, unique_id: bytes, rank: int, world: int):
+        """The library's own NCCL communicator (all-reduces enqueued natively on the context's stream)."""
+        assert len(unique_id) == 128
+        check(lib().nnc_ctx_init_nccl(self._h, unique_id, int(rank), int(world)))
 
     def set_comm(self, rank: int, world: int, allreduce):
         """allreduce(dev_ptr: int, count: int, op: int, stream: int) -> None sums/mins/maxes int64 in place."""

@@ -91,7 +91,19 @@ def init_distributed(group=None, device=None):
     import torch.distributed as dist
 
     ctx = N.default_context(device)
-    ctx.set_comm(dist.get_rank(group), dist.get_world_size(group), N.torch_allreduce(group))
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        return ctx
+    # preferred: the library's own NCCL communicator, bootstrapped through the existing process group
+    try:
+        box = [N.nccl_unique_id() if rank == 0 else None]
+    except N.NncError:
+        box = [None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if box[0] is not None:
+        ctx.init_nccl(box[0], rank, world)
+    else:  # no loadable libnccl: all-reduce through torch.distributed (slower: one host callback per exchange)
+        ctx.set_comm(rank, world, N.torch_allreduce(group))
     return ctx
 
 

@@ -4,6 +4,7 @@
 // Boundary being replaced (reference, Python): neural_network_compression/common/utility.py
 //   prune_weigth :134-163, get_weight_distribution :334-392, get_quantized_weight :172-240
 // and the inline NumPy of common/trainer.py:55-60 (survivor selection) and :195-206 (mask re-apply).
+#include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
 
@@ -201,8 +202,48 @@ static void kfold(nnc_ctx *ctx) {  // after a stream synchronize: fold this call
     ctx->kused = 0;
 }
 
+// ---- NCCL, bound at run time (dlopen: the library is the one PyTorch already loaded, or the system's) ------------
+// Only what is needed: unique id, communicator, int64 all-reduce.  Constants as in nccl.h (2.x ABI).
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUniqueIdBytes, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi *nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.lib ? &api : nullptr;
+    tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) return nullptr;
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.lib, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.lib, "ncclAllReduce"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce) {
+        api.lib = nullptr;
+        return nullptr;
+    }
+    return &api;
+}
+
 void comm_allreduce(nnc_ctx *ctx, int64_t *d_buf, int count, int op) {
     if (ctx->world <= 1 || count <= 0) return;
+    if (ctx->nccl_comm) {
+        NcclApi *api = nccl_api();
+        const int nccl_op = op == 0 ? 0 /* ncclSum */ : (op == 1 ? 3 /* ncclMin */ : 2 /* ncclMax */);
+        const int rc = api->AllReduce(d_buf, d_buf, (size_t)count, 4 /* ncclInt64 */, nccl_op, ctx->nccl_comm, ctx->stream);
+        if (rc != 0) NNC_FAIL(NNC_ERR_COMM, "ncclAllReduce: %s", api->GetErrorString ? api->GetErrorString(rc) : "error");
+        return;
+    }
     if (!ctx->allreduce) NNC_FAIL(NNC_ERR_COMM, "multi-rank context without an all-reduce callback");
     const int rc = ctx->allreduce(ctx->allreduce_user, d_buf, count, op, ctx->stream);
     if (rc != 0) NNC_FAIL(NNC_ERR_COMM, "all-reduce callback failed (%d)", rc);
@@ -343,6 +384,10 @@ void nnc_ctx_destroy(nnc_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->nccl_comm) {
+        NcclApi *api = nccl_api();
+        if (api) api->CommDestroy(ctx->nccl_comm);
+    }
     for (void *p : ctx->overflow) cudaFree(p);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->d_scal) cudaFree(ctx->d_scal);
@@ -400,10 +445,11 @@ int nnc_last_profile(nnc_ctx *ctx, float *ms_out, int cap, int *n_out, const cha
     NNC_CATCH
 }
 
-int nnc_ctx_set_kernel_timing(nnc_ctx *ctx, int on) {
+int nnc_ctx_set_kernel_timing(nnc_ctx *ctx, int on, const char *name_filter) {
     NNC_TRY
     if (!ctx) NNC_FAIL(NNC_ERR_BAD_ARG, "null context");
     ctx->ktime = on != 0;
+    ctx->kfilter = name_filter ? name_filter : "";
     ctx->kacc_names.clear();
     ctx->kacc_ms.clear();
     ctx->kacc_cnt.clear();
@@ -425,6 +471,34 @@ int nnc_last_kernel_times(nnc_ctx *ctx, const char **out) {
         ctx->ktimes += line;
     }
     *out = ctx->ktimes.c_str();
+    NNC_CATCH
+}
+
+int nnc_comm_unique_id(char *out128) {
+    NNC_TRY
+    if (!out128) NNC_FAIL(NNC_ERR_BAD_ARG, "null argument");
+    NcclApi *api = nccl_api();
+    if (!api) NNC_FAIL(NNC_ERR_COMM, "libnccl.so.2 could not be loaded");
+    const int rc = api->GetUniqueId(out128);
+    if (rc != 0) NNC_FAIL(NNC_ERR_COMM, "ncclGetUniqueId failed (%d)", rc);
+    NNC_CATCH
+}
+
+int nnc_ctx_init_nccl(nnc_ctx *ctx, const char *id128, int rank, int world) {
+    NNC_TRY
+    if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) NNC_FAIL(NNC_ERR_BAD_ARG, "nnc_ctx_init_nccl: bad argument");
+    NcclApi *api = nccl_api();
+    if (!api) NNC_FAIL(NNC_ERR_COMM, "libnccl.so.2 could not be loaded");
+    NNC_CUDA(cudaSetDevice(ctx->device));
+    NcclUniqueIdBytes id;
+    memcpy(id.internal, id128, sizeof(id.internal));
+    void *comm = nullptr;
+    const int rc = api->CommInitRank(&comm, world, id, rank);
+    if (rc != 0) NNC_FAIL(NNC_ERR_COMM, "ncclCommInitRank: %s", api->GetErrorString ? api->GetErrorString(rc) : "error");
+    if (ctx->nccl_comm) api->CommDestroy(ctx->nccl_comm);
+    ctx->nccl_comm = comm;
+    ctx->rank = rank;
+    ctx->world = world;
     NNC_CATCH
 }
 

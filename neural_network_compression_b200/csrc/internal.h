@@ -11,6 +11,10 @@
 
 #include "../../include/nnc.h"
 
+struct NcclUniqueIdBytes {  // ncclUniqueId (nccl.h: 128 opaque bytes), passed by value to ncclCommInitRank
+    char internal[128];
+};
+
 namespace nnc {
 
 void set_error(const char *fmt, ...);
@@ -86,6 +90,7 @@ struct nnc_ctx {
     bool user_stream = false;
     // optional per-kernel CUDA-event timing (benchmarks): one event pair per launch, folded by kernel name
     bool ktime = false;
+    std::string kfilter;  // when not empty: only launches whose kernel name contains it are timed
     std::vector<cudaEvent_t> kev;
     std::vector<const char *> knames;
     size_t kused = 0;
@@ -108,6 +113,7 @@ struct nnc_ctx {
         uint32_t t0 = 0, t1 = 0;
     } sh;
     int rank = 0, world = 1;
+    void *nccl_comm = nullptr;  // ncclComm_t when the library owns a communicator (nnc_ctx_init_nccl)
     nnc_allreduce_i64_fn allreduce = nullptr;
     void *allreduce_user = nullptr;
 };
@@ -146,10 +152,11 @@ void klaunch_end(nnc_ctx *ctx);
 
 #define NNC_LAUNCH(ctx, kernel, grid, block, smem, ...)                 \
     do {                                                                \
-        if ((ctx)->ktime) nnc::klaunch_begin((ctx), #kernel);           \
+        const bool _kt = (ctx)->ktime && ((ctx)->kfilter.empty() || strstr(#kernel, (ctx)->kfilter.c_str())); \
+        if (_kt) nnc::klaunch_begin((ctx), #kernel);                    \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
         (ctx)->launches++;                                              \
-        if ((ctx)->ktime) nnc::klaunch_end((ctx));                      \
+        if (_kt) nnc::klaunch_end((ctx));                               \
         NNC_CUDA(cudaGetLastError());                                   \
     } while (0)
 
