@@ -159,6 +159,8 @@ def workload_config(args, world):
         "workload": "synthetic 2^%d-weight fp32 layer N(0,0.02^2), std-threshold prune q=1.0 (bimodal post-prune), "
                     "8-bit linear-init k-means to convergence, packed 8-bit codes + histogram out" % int(np.log2(args.n)),
         "n_weights": args.n, "bits": BITS, "init": MODE, "quality": QUALITY, "shards": world,
+        "exchange": "none (one rank)" if world == 1 else "per-iteration (count, sum) all-reduce inside the Lloyd update kernel over "
+                    "NVLink peer memory; NCCL int64 all-reduces for the reduction-tree partials and scalars",
         "l2": "every step reads a fresh %.1f GiB tensor (> 126 MB L2); no flush needed" % (args.n * 4 / world / 2 ** 30),
     }
 

@@ -167,6 +167,12 @@ int nnc_shard_range(int64_t n, int rank, int world, int64_t *begin, int64_t *end
 /* Preferred transport: the library's own NCCL communicator (libnccl.so.2 bound at run time).  Rank 0 calls
  * nnc_comm_unique_id, the host ships the 128 bytes to every rank (any side channel), all ranks call
  * nnc_ctx_init_nccl.  All-reduces are then enqueued natively on the context's stream (no host callback). */
+/* Optional, one box: peer mailboxes for the Lloyd loop.  Every rank creates one (64-byte CUDA IPC handle out),
+ * the host all-gathers the handles (rank order, world x 64 bytes) and every rank connects.  The per-iteration
+ * exchanges of nnc_kmeans1d_f32 / nnc_compress_f32 then happen INSIDE the update kernel over NVLink peer memory
+ * instead of two NCCL calls and two extra launches per iteration. */
+int nnc_peer_mailbox_create(nnc_ctx *ctx, int world, char *handle_out64);
+int nnc_peer_mailbox_connect(nnc_ctx *ctx, const char *handles, int rank, int world);
 int nnc_comm_unique_id(char *out128);
 int nnc_ctx_init_nccl(nnc_ctx *ctx, const char *id128, int rank, int world);
 typedef int (*nnc_allreduce_i64_fn)(void *user, int64_t *dev_buf, int count, int op /*0 sum,1 min,2 max*/,

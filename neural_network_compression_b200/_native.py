@@ -34,6 +34,7 @@ EXPORTS = [
     "nnc_kmeans1d_f32", "nnc_assign_f32", "nnc_unpack_gather_f32", "nnc_grad_segsum_f32", "nnc_ctx_set_comm",
     "nnc_ctx_set_kernel_timing", "nnc_last_kernel_times", "nnc_ctx_total_launches",
     "nnc_compress_f32", "nnc_shard_range", "nnc_comm_unique_id", "nnc_ctx_init_nccl",
+    "nnc_peer_mailbox_create", "nnc_peer_mailbox_connect",
 ]
 
 
@@ -141,6 +142,8 @@ def lib():
         L.nnc_last_kernel_times.argtypes = [vp, P(C.c_char_p)]
         L.nnc_ctx_total_launches.argtypes = [vp, P(i64)]
         L.nnc_shard_range.argtypes = [i64, i32, i32, P(i64), P(i64)]
+        L.nnc_peer_mailbox_create.argtypes = [vp, i32, C.c_char_p]
+        L.nnc_peer_mailbox_connect.argtypes = [vp, C.c_char_p, i32, i32]
         L.nnc_comm_unique_id.argtypes = [C.c_char_p]
         L.nnc_ctx_init_nccl.argtypes = [vp, C.c_char_p, i32, i32]
         L.nnc_ctx_set_comm.argtypes = [vp, i32, i32, ALLREDUCE_FN, vp]
@@ -165,6 +168,7 @@ class Context:
         check(lib().nnc_ctx_create(int(device), C.byref(self._h)))
         self.device = int(device)
         self._comm_cb = None
+        self.peer_exchange = False  # True once the in-kernel peer-memory exchange is connected
 
     @property
     def handle(self):
@@ -231,6 +235,17 @@ class Context:
         """The library's own NCCL communicator (all-reduces enqueued natively on the context's stream)."""
         assert len(unique_id) == 128
         check(lib().nnc_ctx_init_nccl(self._h, unique_id, int(rank), int(world)))
+
+    def peer_mailbox_create(self, world: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(lib().nnc_peer_mailbox_create(self._h, int(world), buf))
+        return buf.raw
+
+    def peer_mailbox_connect(self, handles: bytes | None, rank: int, world: int):
+        """handles: the world x 64 bytes of all ranks' mailboxes in rank order, or None to disconnect."""
+        assert handles is None or len(handles) == 64 * world
+        check(lib().nnc_peer_mailbox_connect(self._h, handles, int(rank), int(world)))
+        self.peer_exchange = handles is not None
 
     def set_comm(self, rank: int, world: int, allreduce):
         """allreduce(dev_ptr: int, count: int, op: int, stream: int) -> None sums/mins/maxes int64 in place."""

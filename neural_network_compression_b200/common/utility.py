@@ -84,7 +84,7 @@ class _Buf:
         return np.empty(int(n), dtype=dtype)
 
 
-def init_distributed(group=None, device=None):
+def init_distributed(group=None, device=None, peer_exchange=True):
     """Multi-GPU: one process per GPU.  Installs a torch.distributed all-reduce on this process's context; from then
     on prune_weigth / get_quantized_weight / compress_weight take THIS RANK'S slice (see `shard_range`) of the
     flattened tensor and return per-slice masks / codes with global thresholds, centroids and histograms."""
@@ -104,6 +104,25 @@ def init_distributed(group=None, device=None):
         ctx.init_nccl(box[0], rank, world)
     else:  # no loadable libnccl: all-reduce through torch.distributed (slower: one host callback per exchange)
         ctx.set_comm(rank, world, N.torch_allreduce(group))
+    # one box: peer mailboxes, so that the per-iteration exchanges of the Lloyd loop run inside its update kernel
+    if peer_exchange and world <= 16:
+        try:
+            mine = ctx.peer_mailbox_create(world)
+        except N.NncError:
+            mine = None
+        handles = [None] * world
+        dist.all_gather_object(handles, mine, group=group)
+        ok = False
+        if all(h is not None for h in handles):
+            try:
+                ctx.peer_mailbox_connect(b"".join(handles), rank, world)
+                ok = True
+            except N.NncError:
+                ok = False
+        oks = [None] * world
+        dist.all_gather_object(oks, ok, group=group)
+        if not all(oks):  # all or nothing: a half-connected box would dead-lock the in-kernel exchange
+            ctx.peer_mailbox_connect(None, rank, world)
     return ctx
 
 

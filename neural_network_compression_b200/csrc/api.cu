@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "peer.cuh"
 
 namespace nnc {
 
@@ -388,6 +389,9 @@ void nnc_ctx_destroy(nnc_ctx *ctx) {
         NcclApi *api = nccl_api();
         if (api) api->CommDestroy(ctx->nccl_comm);
     }
+    for (int r = 0; r < 16; ++r)
+        if (ctx->peer_mail[r] && ctx->peer_mail[r] != ctx->peer_local) cudaIpcCloseMemHandle(ctx->peer_mail[r]);
+    if (ctx->peer_local) cudaFree(ctx->peer_local);
     for (void *p : ctx->overflow) cudaFree(p);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->d_scal) cudaFree(ctx->d_scal);
@@ -499,6 +503,47 @@ int nnc_ctx_init_nccl(nnc_ctx *ctx, const char *id128, int rank, int world) {
     ctx->nccl_comm = comm;
     ctx->rank = rank;
     ctx->world = world;
+    NNC_CATCH
+}
+
+int nnc_peer_mailbox_create(nnc_ctx *ctx, int world, char *handle_out64) {
+    NNC_TRY
+    if (!ctx || !handle_out64 || world < 2 || world > PEER_MAX_WORLD) NNC_FAIL(NNC_ERR_BAD_ARG, "nnc_peer_mailbox_create: world = %d", world);
+    NNC_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->peer_local) NNC_FAIL(NNC_ERR_BAD_ARG, "the context already has a mailbox");
+    const size_t bytes = peer_mailbox_bytes(world);
+    NNC_CUDA(cudaMalloc(&ctx->peer_local, bytes));
+    NNC_CUDA(cudaMemset(ctx->peer_local, 0, bytes));
+    NNC_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t hdl;
+    NNC_CUDA(cudaIpcGetMemHandle(&hdl, ctx->peer_local));
+    static_assert(sizeof(hdl) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle_out64, &hdl, sizeof(hdl));
+    NNC_CATCH
+}
+
+int nnc_peer_mailbox_connect(nnc_ctx *ctx, const char *handles, int rank, int world) {
+    NNC_TRY
+    if (ctx && !handles) {  // disconnect: back to NCCL exchanges
+        ctx->peer_enabled = false;
+        return NNC_OK;
+    }
+    if (!ctx || !ctx->peer_local || world < 2 || world > PEER_MAX_WORLD || rank < 0 || rank >= world)
+        NNC_FAIL(NNC_ERR_BAD_ARG, "nnc_peer_mailbox_connect: bad argument");
+    NNC_CUDA(cudaSetDevice(ctx->device));
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            ctx->peer_mail[r] = ctx->peer_local;
+            continue;
+        }
+        cudaIpcMemHandle_t hdl;
+        memcpy(&hdl, handles + (size_t)r * sizeof(hdl), sizeof(hdl));
+        void *p = nullptr;
+        NNC_CUDA(cudaIpcOpenMemHandle(&p, hdl, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_mail[r] = p;
+    }
+    ctx->peer_enabled = true;
+    ctx->peer_seq = 0;
     NNC_CATCH
 }
 

@@ -114,6 +114,11 @@ struct nnc_ctx {
     } sh;
     int rank = 0, world = 1;
     void *nccl_comm = nullptr;  // ncclComm_t when the library owns a communicator (nnc_ctx_init_nccl)
+    // peer mailboxes for the in-kernel exchanges of the Lloyd loop (peer.cuh; nnc_peer_mailbox_create / _connect)
+    bool peer_enabled = false;
+    void *peer_local = nullptr;
+    void *peer_mail[16] = {nullptr};
+    unsigned long long peer_seq = 0;
     nnc_allreduce_i64_fn allreduce = nullptr;
     void *allreduce_user = nullptr;
 };

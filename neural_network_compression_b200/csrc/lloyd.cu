@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "peer.cuh"
 #include "table.cuh"
 
 namespace nnc {
@@ -67,7 +68,8 @@ struct LloydDevice : LloydHeader {
     long long gfirst[TB_KMAX], glast[TB_KMAX]; // local member cursors per distinct index
     long long idW[TB_KMAX], idS[TB_KMAX];      // per cluster id, before relocation
     int empt_s[TB_KMAX];
-    int zdi_s, n_empty_s, same_s, pad3;
+    int zdi_s, n_empty_s, same_s, comm_error;
+    long long xbuf[2 * TB_KMAX];  // staging of the in-kernel peer exchange
     // control
     int iter, done, strict, n_reloc, n_iter, pad2;
     // per-iteration log (diagnostics): zone elements, zone groups, distinct centroids, empty clusters
@@ -433,8 +435,10 @@ struct UpdateSmem {
 //   0  local per-distinct-index counts / sums / member cursors (+ the zero run)            -> gW, gS  [all-reduce]
 //   1  per cluster id, label-equality proxy, empty clusters, LOCAL farthest candidates       -> cand    [all-gather]
 //   2  merge the candidates, relocate, average, centre shift, convergence
+// With a peer mailbox (pc.enabled, multi-GPU) the three phases run in ONE launch and the two exchanges happen inside
+// the kernel over NVLink peer memory (peer.cuh).
 __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, const float *__restrict__ ks, int phase_lo,
-                                                               int phase_hi) {
+                                                               int phase_hi, PeerComm pc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     UpdateSmem &U = *reinterpret_cast<UpdateSmem *>(smem_raw);
     if (st->done) return;
@@ -443,6 +447,7 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
     const float mean = st->mean;
     const double scale = st->scale;
     const float x0 = fsub(0.f, mean);
+    unsigned long long xseq = pc.enabled ? *peer_counter(pc) : 0ull;  // exchanges executed so far (same on every rank)
     if (phase_lo > 0) {  // resume: reload what the previous launch left (gW / gS now hold the global sums)
         if (tid < m) {
             U.Wd[tid] = st->gW[tid];
@@ -542,6 +547,19 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
         }
         if (tid == 0) st->zdi_s = U.zdi;
         return;
+    }
+    if (pc.enabled) {  // fused all-reduce of the exact per-distinct-index (count, sum) over the ranks
+        if (tid < m) {
+            st->xbuf[tid] = U.Wd[tid];
+            st->xbuf[m + tid] = U.Sd[tid];
+        }
+        __syncthreads();
+        if (!peer_allreduce_sum(pc, st->xbuf, 2 * m, ++xseq) && tid == 0) st->comm_error = 1;
+        if (tid < m) {
+            U.Wd[tid] = st->xbuf[tid];
+            U.Sd[tid] = st->xbuf[m + tid];
+        }
+        __syncthreads();
     }
     }  // phase 0
     if (phase_lo <= 1) {
@@ -707,7 +725,17 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
         }
         return;
     }
+    if (pc.enabled && U.n_empty > 0) {  // fused all-gather of the candidate lists (n_empty is the same on every rank)
+        const int cnt = 2 * U.n_empty;
+        unsigned long long *mine = st->cand + (size_t)st->rank * k * 2;
+        for (int i = tid; i < cnt; i += TB_THREADS) st->xbuf[i] = (long long)mine[i];
+        __syncthreads();
+        if (!peer_allgather(pc, reinterpret_cast<const unsigned long long *>(st->xbuf), cnt, st->cand, (size_t)k * 2, ++xseq) &&
+            tid == 0)
+            st->comm_error = 1;
+    }
     }  // phase 1
+    if (pc.enabled && tid == 0) *peer_counter(pc) = xseq;
     // ---- 5b. relocation: the n_empty farthest samples over all ranks (every rank's list is already in descending
     // order: a W-way merge by one thread), moved to the empty clusters in ascending id order
     if (U.n_empty > 0) {
@@ -924,15 +952,23 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
             NNC_LAUNCH(ctx, ll_table_kernel, 1, TB_THREADS, 0, st);
             NNC_LAUNCH(ctx, ll_search_kernel, search_grid, 256, 0, st, h.d_sorted, samp, ptile);
             NNC_LAUNCH(ctx, ll_zone_kernel, zone_grid, 256, 0, st, h.d_sorted);
+            PeerComm pc;
+            memset(&pc, 0, sizeof(pc));
             if (world == 1) {
-                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 0, 2);
+                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 0, 2, pc);
+            } else if (ctx->peer_enabled && 2 * k <= PEER_WORDS) {
+                pc.enabled = 1;
+                pc.rank = ctx->rank;
+                pc.world = world;
+                for (int r = 0; r < world; ++r) pc.mail[r] = static_cast<unsigned long long *>(ctx->peer_mail[r]);
+                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 0, 2, pc);
             } else {
                 // exact integer partials: the sums are identical on every rank and for every rank count
-                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 0, 0);
+                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 0, 0, pc);
                 comm_allreduce(ctx, reinterpret_cast<int64_t *>(st->gW), 2 * TB_KMAX, 0);  // gW, gS
-                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 1, 1);
+                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 1, 1, pc);
                 comm_allreduce(ctx, reinterpret_cast<int64_t *>(hs.cand), world * k * 2, 0);  // all-gather by sum
-                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 2, 2);
+                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 2, 2, pc);
             }
         }
         NNC_CUDA(cudaMemcpyAsync(&ctl, &st->iter, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
@@ -940,6 +976,11 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         if (ctl.done || launched >= max_iter) break;
     }
     if (!ctl.done) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: loop ended without a stop decision (iter %d)", ctl.iter);
+    if (world > 1 && ctx->peer_enabled) {
+        int comm_error = 0;
+        NNC_CUDA(cudaMemcpy(&comm_error, &st->comm_error, sizeof(int), cudaMemcpyDeviceToHost));
+        if (comm_error) NNC_FAIL(NNC_ERR_COMM, "k-means: a rank did not arrive at an in-kernel peer exchange (time-out)");
+    }
     NNC_CUDA(cudaMemcpyAsync(h_centred_final, st->c, sizeof(float) * k, cudaMemcpyDeviceToHost, ctx->stream));
     NNC_CUDA(cudaMemcpyAsync(h_centred_emit, st->c_emit, sizeof(float) * k, cudaMemcpyDeviceToHost, ctx->stream));
     float tol_h = 0.f;

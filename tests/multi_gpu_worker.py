@@ -34,7 +34,8 @@ def main():
         ref_ris, ref_full_km = U.get_quantized_weight(ref_w, bits, "linear")
         # ---- sharded
         N._tls.ctx = {}
-        U.init_distributed()
+        # bits 4 runs over NCCL all-reduces between the update phases, the others over the in-kernel peer exchange
+        dctx = U.init_distributed(peer_exchange=(bits != 4))
         b, e = U.shard_range(n, rank, world)
         mine = full[b:e].clone()
         mask, km = U.compress_weight(mine, 1.0, True, bits, "linear")
@@ -56,7 +57,8 @@ def main():
         ok &= (m, v, s) == tuple(np.float32(x) for x in (np.mean(full.cpu().numpy()), np.var(full.cpu().numpy()), np.std(full.cpu().numpy())))
         if not ok:
             failures.append((bits, rank))
-        print("rank %d bits %d iters %d reloc %d thr %.9g %s" % (rank, bits, km.n_iter_, km.n_relocations, ref_thr, "OK" if ok else "MISMATCH"), flush=True)
+        print("rank %d bits %d iters %d reloc %d thr %.9g peer_exchange=%s %s" % (rank, bits, km.n_iter_, km.n_relocations, ref_thr,
+                                                                                    dctx.peer_exchange, "OK" if ok else "MISMATCH"), flush=True)
     t = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(t)
     dist.destroy_process_group()
