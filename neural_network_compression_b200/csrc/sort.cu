@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(RS_RADIX) rs_base_kernel(const uint32_t *chunk
 }
 
 struct RsSmem {
+    alignas(16) uint32_t stage[RS_TILE];  // next tile's raw keys, filled by cp.async while the current tile is processed
     uint32_t keys[RS_TILE];
     uint32_t warp_hist[RS_WARPS][RS_RADIX];
     uint32_t tile_start[RS_RADIX];
@@ -121,7 +122,7 @@ struct RsSmem {
 };
 
 template <bool IN_FLOAT, bool OUT_FLOAT>
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
+__global__ void __launch_bounds__(RS_THREADS, 2) rs_scatter_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
                                                                 int64_t n, int64_t tiles_per_chunk, int shift, int width,
                                                                 RsKeyMap km, const unsigned long long *__restrict__ chunk_base) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -133,36 +134,74 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t *
     s.run[threadIdx.x] = chunk_base[(size_t)blockIdx.x * RS_RADIX + threadIdx.x];
     const int64_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
     const int64_t t0 = (int64_t)blockIdx.x * tiles_per_chunk, t1 = min(n_tiles, t0 + tiles_per_chunk);
+    const bool src_aligned = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+    // Asynchronous tile fetch (cp.async, 16 B per thread and copy): the fetch of tile t + 1 is in flight while
+    // tile t is ranked and scattered -- without it the pass waited on the key loads of every tile (ncu:
+    // long-scoreboard stalls on the first use of the keys, 45 % of the samples).
+    auto fetch = [&](int64_t tile) {
+        const int64_t tile_base = tile * RS_TILE;
+        if (src_aligned && tile_base + RS_TILE <= n) {
+#pragma unroll
+            for (int c = 0; c < RS_TILE / 4 / RS_THREADS; ++c) {
+                const int chunk = c * RS_THREADS + threadIdx.x;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s.stage[4 * chunk]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(in + tile_base + 4 * chunk) : "memory");
+            }
+        } else {  // the last, partial tile (or an unaligned source): plain loads
+            for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS) s.stage[i] = tile_base + i < n ? in[tile_base + i] : 0xffffffffu;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (t0 < t1) fetch(t0);
     for (int64_t tile = t0; tile < t1; ++tile) {
-        for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX / 4; i += RS_THREADS)
-            reinterpret_cast<uint4 *>(&s.warp_hist[0][0])[i] = make_uint4(0, 0, 0, 0);
         const int64_t tile_base = tile * RS_TILE;
         const int valid = (int)min((int64_t)RS_TILE, n - tile_base);
-        // ---- load (warp-striped: item i of lane l is element i*32 + l of the warp's 512-key chunk)
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // the staged tile is complete and visible
+        // ---- keys to registers (warp-striped: item i of lane l is element i*32 + l of the warp's 512-key chunk)
         uint32_t key[RS_ITEMS];
-        const int64_t wbase = tile_base + wid * (32 * RS_ITEMS);
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
-            int64_t idx = wbase + i * 32 + lane;
-            uint32_t k = 0xffffffffu;  // padding: all digit bits set, sorts last in every pass
-            if (idx < n) {
-                k = __ldg(in + idx);
+            const int e = wid * (32 * RS_ITEMS) + i * 32 + lane;
+            uint32_t k = s.stage[e];
+            if (e < valid) {
                 if (IN_FLOAT) k = rs_key(k, km);
+            } else {
+                k = 0xffffffffu;  // padding: all digit bits set, sorts last in every pass
             }
             key[i] = k;
         }
-        __syncthreads();  // counters cleared; the previous tile's scatter has finished reading s.keys / s.gbase
-        // ---- stable ranking inside the warp: match_any multisplit with warp-private digit counters
-        // (an atomicAdd-by-the-leader variant was measured slower than this read / write pair)
+        for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX / 4; i += RS_THREADS)
+            reinterpret_cast<uint4 *>(&s.warp_hist[0][0])[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();  // stage consumed, counters cleared, previous tile's scatter finished
+        if (tile + 1 < t1) fetch(tile + 1);
+        // ---- stable ranking inside the warp with warp-private digit counters.
+        // rank = (keys of the warp's earlier items with this digit) + (lower lanes of this item with this digit).
+        // __match_any_sync would give the second term directly, but on sm_100 it costs ~60 cycles per warp
+        // instruction when the 32 digits are mostly distinct (scripts/micro/matchany.cu) -- it alone made the pass
+        // 15 k cycles per tile.  With 512 bins two lanes of an item rarely share a digit, so collisions are
+        // DETECTED with the counter word itself -- every lane stores its lane id into the tag byte of its digit's
+        // word, then reads the word back: a lane whose tag did not survive shares its digit with another lane --
+        // and only those digit groups are resolved with ballots.  word = count (low 16 bits) | tag (top byte).
         uint32_t rank[RS_ITEMS];
         uint32_t *wh = s.warp_hist[wid];
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
-            uint32_t d = (key[i] >> shift) & dmask;
-            uint32_t peers = __match_any_sync(0xffffffffu, d);
-            uint32_t before = wh[d];
+            const uint32_t d = (key[i] >> shift) & dmask;
+            reinterpret_cast<volatile uint8_t *>(&wh[d])[3] = (uint8_t)lane;
             __syncwarp();
-            if ((peers & lt) == 0) wh[d] = before + __popc(peers);  // lowest peer lane updates the counter
+            const uint32_t word = reinterpret_cast<volatile uint32_t *>(wh)[d];
+            uint32_t peers = 1u << lane;
+            uint32_t unresolved = __ballot_sync(0xffffffffu, (word >> 24) != (uint32_t)lane);
+            while (unresolved) {  // one round per digit shared by several lanes (about one per item on average)
+                const int ld = __ffs(unresolved) - 1;
+                const uint32_t dl = __shfl_sync(0xffffffffu, d, ld);
+                const uint32_t grp = __ballot_sync(0xffffffffu, d == dl);
+                if (d == dl) peers = grp;
+                unresolved &= ~grp;
+            }
+            const uint32_t before = word & 0xffffu;
+            if ((peers & lt) == 0) reinterpret_cast<volatile uint16_t *>(&wh[d])[0] = (uint16_t)(before + __popc(peers));
             __syncwarp();
             rank[i] = before + __popc(peers & lt);
         }
@@ -175,7 +214,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t *
             if (d < radix) {
 #pragma unroll
                 for (int w = 0; w < RS_WARPS; ++w) {
-                    uint32_t c = s.warp_hist[w][d];
+                    uint32_t c = s.warp_hist[w][d] & 0xffffu;  // count; the top byte is the ranking's lane tag
                     s.warp_hist[w][d] = tot;
                     tot += c;
                 }
