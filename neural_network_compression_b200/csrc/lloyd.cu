@@ -119,20 +119,8 @@ __global__ void __launch_bounds__(256) ll_tilesum_kernel(const float *__restrict
 __global__ void __launch_bounds__(1024) ll_scan_kernel(const long long *tsum, long long n_tiles, long long *ptile,
                                                        LloydDevice *st) {
     __shared__ long long s_warp[32];
-    const long long per = (n_tiles + blockDim.x - 1) / blockDim.x;
-    const long long lo = llmin2(n_tiles, threadIdx.x * per), hi = llmin2(n_tiles, lo + per);
-    long long sum = 0;
-    for (long long i = lo; i < hi; ++i) sum += tsum[i];
-    long long incl = block_scan_incl<long long>(sum, [](long long a, long long b) { return a + b; }, s_warp);
-    long long run = incl - sum;
-    for (long long i = lo; i < hi; ++i) {
-        ptile[i] = run;
-        run += tsum[i];
-    }
-    if (threadIdx.x == blockDim.x - 1) {
-        ptile[n_tiles] = incl;
-        st->total_q = incl;
-    }
+    const long long total = cta_exclusive_scan<long long, long long>(tsum, n_tiles, ptile, s_warp);
+    if (threadIdx.x == 0) st->total_q = total;
 }
 
 // ---------------------------------------------------------------------------------------------

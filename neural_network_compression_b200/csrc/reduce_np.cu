@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "table.cuh"
 
 namespace nnc {
 
@@ -788,37 +789,7 @@ QuantPrologue quant_prologue(nnc_ctx *ctx, const float *d_w, int64_t n) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) tile_scan_kernel(const unsigned int *counts, uint32_t num_tiles, unsigned long long *base) {
     __shared__ unsigned long long s_warp[32];
-    const uint32_t per = (num_tiles + blockDim.x - 1) / blockDim.x;
-    const uint32_t lo = min(num_tiles, threadIdx.x * per), hi = min(num_tiles, lo + per);
-    unsigned long long sum = 0;
-    for (uint32_t i = lo; i < hi; ++i) sum += counts[i];
-    // block inclusive scan
-    const int lane = lane_id(), w = warp_id();
-    unsigned long long incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-        unsigned long long x = s_warp[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long t = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += t;
-        }
-        s_warp[lane] = x;
-    }
-    __syncthreads();
-    if (w > 0) incl += s_warp[w - 1];
-    unsigned long long run = incl - sum;
-    for (uint32_t i = lo; i < hi; ++i) {
-        base[i] = run;
-        run += counts[i];
-    }
-    if (threadIdx.x == blockDim.x - 1) base[num_tiles] = incl;
+    cta_exclusive_scan<unsigned int, unsigned long long>(counts, (long long)num_tiles, base, s_warp);
 }
 
 // w: this rank's shard; desc / base: the shard's tiles (descriptor offsets are global: shard_begin is subtracted)

@@ -90,6 +90,38 @@ __device__ __forceinline__ T block_scan_incl(T v, Op op, T *s_warp /*[32]*/) {
     return v;
 }
 
+// Exclusive scan of in[0, n) into out[0, n] (out[n] = total) by ONE CTA of 1024 threads: rounds of 8192 consecutive
+// elements (8 per thread, coalesced), a block scan per round, the carry kept in a register.
+template <class TIn, class TOut>
+__device__ __forceinline__ TOut cta_exclusive_scan(const TIn *__restrict__ in, long long n, TOut *__restrict__ out, TOut *s_warp /*[32]*/) {
+    constexpr int PER = 8;
+    TOut carry = 0;
+    for (long long base = 0; base < n; base += (long long)blockDim.x * PER) {
+        const long long i0 = base + (long long)threadIdx.x * PER;
+        TOut v[PER], sum = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            v[j] = i0 + j < n ? (TOut)in[i0 + j] : (TOut)0;
+            sum += v[j];
+        }
+        TOut incl = block_scan_incl<TOut>(sum, [](TOut a, TOut b) { return a + b; }, s_warp);
+        TOut run = carry + incl - sum;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            if (i0 + j < n) out[i0 + j] = run;
+            run += v[j];
+        }
+        // total of the round = inclusive value of the last thread
+        __shared__ TOut s_total;
+        if (threadIdx.x == blockDim.x - 1) s_total = incl;
+        __syncthreads();
+        carry += s_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry;
+    return carry;
+}
+
 struct TableScratch {
     unsigned long long keys[TB_KMAX];
     double a[TB_KMAX];
