@@ -193,12 +193,25 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_scatter_kernel(const uint32_
             const uint32_t word = reinterpret_cast<volatile uint32_t *>(wh)[d];
             uint32_t peers = 1u << lane;
             uint32_t unresolved = __ballot_sync(0xffffffffu, (word >> 24) != (uint32_t)lane);
-            while (unresolved) {  // one round per digit shared by several lanes (about one per item on average)
-                const int ld = __ffs(unresolved) - 1;
-                const uint32_t dl = __shfl_sync(0xffffffffu, d, ld);
-                const uint32_t grp = __ballot_sync(0xffffffffu, d == dl);
-                if (d == dl) peers = grp;
-                unresolved &= ~grp;
+            if (__popc(unresolved) > 6) {
+                // many lanes share digits (the most significant digit of a bell-shaped layer): one ballot per digit
+                // bit gives every lane its peer set at a fixed cost
+                peers = 0xffffffffu;
+#pragma unroll
+                for (int b = 0; b < 9; ++b) {
+                    if (b < width) {
+                        const uint32_t v = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+                        peers &= ((d >> b) & 1u) ? v : ~v;
+                    }
+                }
+            } else {
+                while (unresolved) {  // one round per digit shared by several lanes (about one per item when digits are uniform)
+                    const int ld = __ffs(unresolved) - 1;
+                    const uint32_t dl = __shfl_sync(0xffffffffu, d, ld);
+                    const uint32_t grp = __ballot_sync(0xffffffffu, d == dl);
+                    if (d == dl) peers = grp;
+                    unresolved &= ~grp;
+                }
             }
             const uint32_t before = word & 0xffffu;
             if ((peers & lt) == 0) reinterpret_cast<volatile uint16_t *>(&wh[d])[0] = (uint16_t)(before + __popc(peers));
