@@ -300,7 +300,9 @@ def run_b200(args):
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "roofline": {
-            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": NCU_TRAFFIC.get(dom_name, [None])[0] if world == 1 and args.n == (1 << 30) else None,
+            "traffic_source": NCU_TRAFFIC.get(dom_name, [None, None])[1],
             "kernel": dom_name, "kernel_launches_per_step": dom_cnt / K, "kernel_ms_per_launch": avg_ms,
             "kernel_algorithmic_bytes_per_launch": kbytes, "peak_source": peak_src,
             "step_algorithmic_bytes_per_weight": step_bytes,
@@ -329,6 +331,11 @@ def run_b200(args):
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` capture of the dominant
+# kernel on this workload (2^30 weights, 1 GPU): average of the three passes in profiles/r1_summary.md section 3
+NCU_TRAFFIC = {"(rs_scatter_kernel<A, B>)": [3.135e9, "profiles/r1_summary.md section 3 (gpurun_out/prof_r1_scatter.ncu-rep)"]}
 
 
 def kernel_bytes(name, n, n_nz):
