@@ -194,6 +194,10 @@ struct QuantPrologue {
 QuantPrologue quant_prologue(nnc_ctx *ctx, const float *d_w, int64_t n);
 void compact_tiles_device(nnc_ctx *ctx, const float *d_w, const QuantPrologue &q, float *d_out);
 
+// scan.cu : multi-CTA exclusive scans (out[n] = total)
+void exclusive_scan_i64(nnc_ctx *ctx, const long long *d_in, long long n, long long *d_out);
+void exclusive_scan_u32_u64(nnc_ctx *ctx, const unsigned int *d_in, long long n, unsigned long long *d_out);
+
 // select.cu : min/max, edge histogram, ordered compaction, gather
 void minmax_device(nnc_ctx *ctx, const float *d_w, int64_t n, int skip_zeros, float *mn, float *mx, int64_t *cnt);
 void hist_edges_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *h_edges, int n_edges, int skip_zeros,

@@ -115,13 +115,8 @@ __global__ void __launch_bounds__(256) ll_tilesum_kernel(const float *__restrict
     }
 }
 
-// exclusive scan of tile sums -> ptile[0..T]; single CTA
-__global__ void __launch_bounds__(1024) ll_scan_kernel(const long long *tsum, long long n_tiles, long long *ptile,
-                                                       LloydDevice *st) {
-    __shared__ long long s_warp[32];
-    const long long total = cta_exclusive_scan<long long, long long>(tsum, n_tiles, ptile, s_warp);
-    if (threadIdx.x == 0) st->total_q = total;
-}
+// total_q = ptile[n_tiles] (the exclusive scan of the tile sums is exclusive_scan_i64, scan.cu)
+__global__ void ll_total_kernel(const long long *ptile, long long n_tiles, LloydDevice *st) { st->total_q = ptile[n_tiles]; }
 
 // ---------------------------------------------------------------------------------------------
 // init: centre the initial centroids, tolerance from exact integer moments
@@ -218,15 +213,17 @@ __device__ __forceinline__ void warp_boundary_search(const float *__restrict__ k
     const long long tile = lo - 1;
     const long long base = tile * LL_TS;
     long long cnt = 0, acc = 0;
-#pragma unroll 4
+    float xv[LL_TS / 32];
+#pragma unroll
+    for (int j = 0; j < LL_TS / 32; ++j) {  // all 32 loads in flight before the first use
+        const long long i = base + j * 32 + lane;
+        xv[j] = i < n_nz ? ks[i] : INFINITY;
+    }
+#pragma unroll
     for (int j = 0; j < LL_TS / 32; ++j) {
-        long long i = base + j * 32 + lane;
-        bool p = false;
-        if (i < n_nz) {
-            float xc = fsub(ks[i], mean);
-            p = xc < t;
-            if (p) acc += fixed_q(xc, scale);
-        }
+        const float xc = fsub(xv[j], mean);
+        const bool p = xc < t;  // padding is +inf: never counted
+        if (p) acc += fixed_q(xc, scale);
         cnt += __popc(__ballot_sync(0xffffffffu, p));
     }
     acc = warp_sum_ll(acc);
@@ -922,7 +919,8 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         int grid = (int)std::min<long long>((long long)ctx->sm_count * 8, (n_tiles + 7) / 8);
         NNC_LAUNCH(ctx, ll_tilesum_kernel, grid, 256, 0, h.d_sorted, h.n_nz, mean, scale, tsum, samp, st);
     }
-    NNC_LAUNCH(ctx, ll_scan_kernel, 1, 1024, 0, tsum, n_tiles, ptile, st);
+    exclusive_scan_i64(ctx, tsum, n_tiles, ptile);
+    NNC_LAUNCH(ctx, ll_total_kernel, 1, 1, 0, ptile, n_tiles, st);
     NNC_LAUNCH(ctx, ll_moments_kernel, 1, 1, 0, st);
     comm_allreduce(ctx, reinterpret_cast<int64_t *>(&st->s1), 3, 0);  // s1, s2_lo, s2_hi are consecutive
     NNC_LAUNCH(ctx, ll_init_kernel, 1, TB_KMAX, 0, st, d_init);

@@ -787,11 +787,6 @@ QuantPrologue quant_prologue(nnc_ctx *ctx, const float *d_w, int64_t n) {
 // Survivor compaction over the tiles of the prologue: the per-tile non-zero counts are already known, so the tile
 // bases are one small scan and the scatter is a pure streaming pass (no inter-CTA dependency).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) tile_scan_kernel(const unsigned int *counts, uint32_t num_tiles, unsigned long long *base) {
-    __shared__ unsigned long long s_warp[32];
-    cta_exclusive_scan<unsigned int, unsigned long long>(counts, (long long)num_tiles, base, s_warp);
-}
-
 // w: this rank's shard; desc / base: the shard's tiles (descriptor offsets are global: shard_begin is subtracted)
 __global__ void __launch_bounds__(NP_THREADS) tile_compact_kernel(const float *__restrict__ w, int vec_ok,
                                                                    const NpTileDesc *__restrict__ desc, uint32_t num_tiles,
@@ -852,7 +847,7 @@ void compact_tiles_device(nnc_ctx *ctx, const float *d_w, const QuantPrologue &q
     const uint32_t t0 = ctx->sh.t0, tiles = ctx->sh.t1 - ctx->sh.t0;
     if (tiles == 0) return;
     unsigned long long *base = arena_alloc_t<unsigned long long>(ctx, (size_t)tiles + 1);
-    NNC_LAUNCH(ctx, tile_scan_kernel, 1, 1024, 0, q.tile_counts + t0, tiles, base);
+    exclusive_scan_u32_u64(ctx, q.tile_counts + t0, (long long)tiles, base);
     const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, tiles);
     NNC_LAUNCH(ctx, tile_compact_kernel, grid, NP_THREADS, 0, d_w, aligned16(d_w) ? 1 : 0,
                static_cast<const NpTileDesc *>(q.tile_desc) + t0, tiles, ctx->sh.begin, base, d_out);

@@ -298,7 +298,9 @@ float *radix_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n, uint32_t 
     plan.passes = (keybits + 8) / 9;
     for (int p = 0, at = 0; p < RS_MAX_PASSES; ++p) {
         int left = plan.passes - p;
-        int wd = p < plan.passes ? (keybits - at + left - 1) / left : 0;
+        // narrower digits first: the most significant digit of a bell-shaped layer is the skewed one, and a wider
+        // digit there means fewer lanes of a warp item sharing a bin
+        int wd = p < plan.passes ? (keybits - at) / left : 0;
         plan.shift[p] = at;
         plan.width[p] = wd;
         at += wd;
