@@ -8,6 +8,7 @@
 // bins are folded in CTA order by a second tiny kernel.  The result is therefore deterministic for a given
 // (n, grid) and within a few float64 ulps of the exactly rounded sum.
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 #include "internal.h"
@@ -55,18 +56,34 @@ __device__ __forceinline__ int load_code1(const void *codes, int bits, int64_t i
     return (int)((v >> (bit & 7)) & ((1u << bits) - 1u));
 }
 
+// WARP_PRIV (k <= 1024): every warp owns a private copy of the bins and adds with NATIVE 32-bit shared-memory
+// atomics -- the fixed-point value q (|q| < 2^43) is split as q = hi * 2^22 + lo, lo in [0, 2^22): a warp adds at most
+// 512 values per tile, so neither half can overflow 32 bits.  (A 64-bit shared-memory atomicAdd compiles to a
+// compare-and-swap spin loop, ATOMS.CAST.SPIN.64, which collapses when one code dominates.)  Otherwise: one set of
+// 64-bit bins per CTA.
+constexpr int SG_WARPS = SG_THREADS / 32;
+constexpr int SG_QBITS_PRIV = 43, SG_SPLIT = 22;
+
+template <bool WARP_PRIV>
 __global__ void __launch_bounds__(SG_THREADS) segsum_kernel(const float *__restrict__ grad, const void *__restrict__ codes,
                                                             int64_t n, int bits, int k, int vec_ok, double *partial,
                                                             unsigned long long *bad_codes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    long long *s_bin = reinterpret_cast<long long *>(smem_raw);
-    double *s_dbl = reinterpret_cast<double *>(s_bin + k);
+    double *s_dbl = reinterpret_cast<double *>(smem_raw);                                // [k]
+    long long *s_bin = reinterpret_cast<long long *>(s_dbl + k);                          // !WARP_PRIV: [k]
+    uint32_t *s_lo = reinterpret_cast<uint32_t *>(s_dbl + k);                             // WARP_PRIV: [SG_WARPS][k]
+    int32_t *s_hi = reinterpret_cast<int32_t *>(s_lo + (size_t)SG_WARPS * k);             // WARP_PRIV: [SG_WARPS][k]
     __shared__ float s_max[SG_THREADS / 32];
     __shared__ float s_tile_max;
-    for (int i = threadIdx.x; i < k; i += SG_THREADS) {
-        s_bin[i] = 0;
-        s_dbl[i] = 0.0;
+    for (int i = threadIdx.x; i < k; i += SG_THREADS) s_dbl[i] = 0.0;
+    if (WARP_PRIV) {
+        for (int i = threadIdx.x; i < 2 * SG_WARPS * k; i += SG_THREADS) s_lo[i] = 0;
+    } else {
+        for (int i = threadIdx.x; i < k; i += SG_THREADS) s_bin[i] = 0;
     }
+    uint32_t *my_lo = s_lo + (size_t)warp_id() * k;
+    int32_t *my_hi = s_hi + (size_t)warp_id() * k;
+    constexpr int QBITS = WARP_PRIV ? SG_QBITS_PRIV : 50;
     __syncthreads();
     const int64_t n_tiles = (n + SG_TILE - 1) / SG_TILE;
     unsigned long long bad = 0;
@@ -109,45 +126,69 @@ __global__ void __launch_bounds__(SG_THREADS) segsum_kernel(const float *__restr
         }
         __syncthreads();
         const float tmax = s_tile_max;
-        // |g| < 2^E ; q = rint(g * 2^(50-E)) < 2^50 ; 4096 of them < 2^62
+        // |g| < 2^E ; q = rint(g * 2^(QBITS-E)), |q| < 2^QBITS
         int E = 0;
         if (tmax > 0.f) E = (int)((__float_as_uint(tmax) >> 23) & 0xffu) - 126;  // ilogb + 1 (denormals: E = -126)
         if (tmax > 0.f && tmax < 1.17549435e-38f) E = -126;
-        const double scale = ldexp(1.0, 50 - E);
+        const double scale = ldexp(1.0, QBITS - E);
 #pragma unroll
         for (int v = 0; v < SG_VEC; ++v) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int code = c[v][j];
                 long long q = code >= 0 ? __double2ll_rn(__dmul_rn((double)g[v][j], scale)) : 0;
-                // warp aggregation of the most populated code in the warp, individual atomics for the rest
-                uint32_t peers = __match_any_sync(0xffffffffu, code);
-                int sz = __popc(peers);
-                int best = sz;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+                // Shared-memory integer atomics commute, so any order gives the same bins.  A code that many lanes of
+                // the warp share (the cluster of the pruned zeros holds 2/3 of a pruned layer) would serialise on one
+                // address: up to two such groups are summed with shuffles first (leader = lowest remaining lane),
+                // the rest goes through individual atomics.  (__match_any_sync costs ~60 cycles per warp instruction
+                // on sm_100 when the 32 values are mostly distinct: scripts/micro/matchany.cu.)
+                unsigned remaining = __ballot_sync(0xffffffffu, code >= 0);
                 bool done = code < 0;
-                if (best >= 4) {
-                    unsigned cand = __ballot_sync(0xffffffffu, sz == best && code >= 0);
-                    if (cand) {
-                        int leader = __ffs(cand) - 1;
-                        int Lc = __shfl_sync(0xffffffffu, code, leader);
-                        long long s = warp_sum_ll(code == Lc ? q : 0);
-                        if (lane_id() == leader) atomicAdd((unsigned long long *)&s_bin[Lc], (unsigned long long)s);
-                        if (code == Lc) done = true;
+#pragma unroll
+                for (int round = 0; round < 2; ++round) {
+                    if (remaining == 0) break;
+                    const int leader = __ffs(remaining) - 1;
+                    const int Lc = __shfl_sync(0xffffffffu, code, leader);
+                    const unsigned grp = __ballot_sync(0xffffffffu, !done && code == Lc);
+                    if (__popc(grp) < 4) break;
+                    const long long sgrp = warp_sum_ll((grp >> lane_id()) & 1u ? q : 0);
+                    if (lane_id() == leader) {
+                        if (WARP_PRIV) {
+                            atomicAdd(&my_lo[Lc], (uint32_t)(sgrp & ((1ll << SG_SPLIT) - 1)));
+                            atomicAdd(&my_hi[Lc], (int32_t)(sgrp >> SG_SPLIT));
+                        } else {
+                            atomicAdd((unsigned long long *)&s_bin[Lc], (unsigned long long)sgrp);
+                        }
+                    }
+                    if ((grp >> lane_id()) & 1u) done = true;
+                    remaining &= ~grp;
+                }
+                if (!done) {
+                    if (WARP_PRIV) {
+                        atomicAdd(&my_lo[code], (uint32_t)(q & ((1ll << SG_SPLIT) - 1)));
+                        atomicAdd(&my_hi[code], (int32_t)(q >> SG_SPLIT));
+                    } else {
+                        atomicAdd((unsigned long long *)&s_bin[code], (unsigned long long)q);
                     }
                 }
-                if (!done) atomicAdd((unsigned long long *)&s_bin[code], (unsigned long long)q);
             }
         }
         __syncthreads();
-        const double inv = ldexp(1.0, E - 50);
+        const double inv = ldexp(1.0, E - QBITS);
         for (int i = threadIdx.x; i < k; i += SG_THREADS) {
-            long long b = s_bin[i];
-            if (b) {
-                s_dbl[i] = __dadd_rn(s_dbl[i], __dmul_rn((double)b, inv));
+            long long b = 0;
+            if (WARP_PRIV) {
+#pragma unroll
+                for (int w = 0; w < SG_WARPS; ++w) {
+                    b += ((long long)s_hi[(size_t)w * k + i] << SG_SPLIT) + (long long)s_lo[(size_t)w * k + i];
+                    s_hi[(size_t)w * k + i] = 0;
+                    s_lo[(size_t)w * k + i] = 0;
+                }
+            } else {
+                b = s_bin[i];
                 s_bin[i] = 0;
             }
+            if (b) s_dbl[i] = __dadd_rn(s_dbl[i], __dmul_rn((double)b, inv));
         }
         __syncthreads();
     }
@@ -168,24 +209,52 @@ void grad_segsum_device(nnc_ctx *ctx, const float *d_grad, const void *d_codes, 
                         double *h_out) {
     if (k < 1 || k > 65536) NNC_FAIL(NNC_ERR_UNSUPPORTED, "segsum: k = %d outside [1, 65536]", k);
     if (bits < 0 || bits > 16) NNC_FAIL(NNC_ERR_BAD_ARG, "segsum: bits = %d outside [0, 16]", bits);
-    if (16 * (size_t)k > 200 * 1024) NNC_FAIL(NNC_ERR_UNSUPPORTED, "segsum: k = %d does not fit shared memory", k);
+    const bool priv = k <= 1024;
+    if (!priv && 16 * (size_t)k > 200 * 1024) NNC_FAIL(NNC_ERR_UNSUPPORTED, "segsum: k = %d does not fit shared memory", k);
     const int64_t n_tiles = (n + SG_TILE - 1) / SG_TILE;
     const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 4, n_tiles);
     double *partial = arena_alloc_t<double>(ctx, (size_t)grid * k);
     double *d_out = arena_alloc_t<double>(ctx, k);
     unsigned long long *bad = arena_alloc_t<unsigned long long>(ctx, 1);
     NNC_CUDA(cudaMemsetAsync(bad, 0, sizeof(unsigned long long), ctx->stream));
-    const size_t smem = 16 * (size_t)k;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        NNC_CUDA(cudaFuncSetAttribute(segsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    const size_t smem = priv ? (8 + 8 * (size_t)SG_WARPS) * k : 16 * (size_t)k;
+    static size_t configured[2] = {0, 0};
+    if (smem > 48 * 1024 && smem > configured[priv]) {
+        if (priv)
+            NNC_CUDA(cudaFuncSetAttribute(segsum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else
+            NNC_CUDA(cudaFuncSetAttribute(segsum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[priv] = smem;
     }
     const int vec_ok = ((reinterpret_cast<uintptr_t>(d_grad) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_codes) & 15u) == 0) &&
                        (bits == 0 || bits == 4 || bits == 8 || bits == 16 || bits == 2 || bits == 1 || true);
-    NNC_LAUNCH(ctx, segsum_kernel, grid, SG_THREADS, smem, d_grad, d_codes, n, bits, k, vec_ok, partial, bad);
+    if (priv)
+        NNC_LAUNCH(ctx, segsum_kernel<true>, grid, SG_THREADS, smem, d_grad, d_codes, n, bits, k, vec_ok, partial, bad);
+    else
+        NNC_LAUNCH(ctx, segsum_kernel<false>, grid, SG_THREADS, smem, d_grad, d_codes, n, bits, k, vec_ok, partial, bad);
     NNC_LAUNCH(ctx, segsum_final_kernel, (k + 127) / 128, 128, 0, partial, grid, k, d_out);
     unsigned long long h_bad = 0;
+    if (ctx->world > 1) {
+        // every rank's k partial sums travel as bit patterns in its own slot (the other slots are zero, so the integer
+        // all-reduce is an all-gather); they are added in rank order on the host: the same double on every rank
+        const int world = ctx->world;
+        double *slots = arena_alloc_t<double>(ctx, (size_t)world * k);
+        NNC_CUDA(cudaMemsetAsync(slots, 0, sizeof(double) * (size_t)world * k, ctx->stream));
+        NNC_CUDA(cudaMemcpyAsync(slots + (size_t)ctx->rank * k, d_out, sizeof(double) * k, cudaMemcpyDeviceToDevice, ctx->stream));
+        comm_allreduce(ctx, reinterpret_cast<int64_t *>(slots), world * k, 0);
+        comm_allreduce(ctx, reinterpret_cast<int64_t *>(bad), 1, 0);
+        std::vector<double> all((size_t)world * k);
+        NNC_CUDA(cudaMemcpyAsync(all.data(), slots, sizeof(double) * (size_t)world * k, cudaMemcpyDeviceToHost, ctx->stream));
+        NNC_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(h_bad), cudaMemcpyDeviceToHost, ctx->stream));
+        NNC_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (h_bad) NNC_FAIL(NNC_ERR_BAD_ARG, "segsum: %llu codes >= k = %d", h_bad, k);
+        for (int j = 0; j < k; ++j) {
+            double acc = 0.0;
+            for (int r = 0; r < world; ++r) acc += all[(size_t)r * k + j];
+            h_out[j] = acc;
+        }
+        return;
+    }
     NNC_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * k, cudaMemcpyDeviceToHost, ctx->stream));
     NNC_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(h_bad), cudaMemcpyDeviceToHost, ctx->stream));
     NNC_CUDA(cudaStreamSynchronize(ctx->stream));

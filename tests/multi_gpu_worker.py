@@ -52,6 +52,12 @@ def main():
         ris, km2 = U.get_quantized_weight(mine, bits, "linear")
         ok &= bool(torch.equal(km2.labels_, ref_full_km.labels_[b:e])) and bool(torch.equal(ris, ref_ris[b:e]))
         ok &= km2.inertia_ == ref_full_km.inertia_
+        # trained-quantization gradient sum over the shards == over the whole tensor (same grid-independent tolerance)
+        gg = torch.empty(n, device="cuda").normal_(0.0, 1e-3, generator=g)
+        gs = U.cluster_gradient_sum(gg[b:e].clone(), km2.labels_, km2.n_clusters)
+        full_sum = torch.zeros(km2.n_clusters, dtype=torch.float64, device="cuda").index_add_(0, ref_full_km.labels_.long(), gg.double())
+        mag = torch.zeros(km2.n_clusters, dtype=torch.float64, device="cuda").index_add_(0, ref_full_km.labels_.long(), gg.double().abs())
+        ok &= bool(np.all(np.abs(gs - full_sum.cpu().numpy()) <= 1e-13 * mag.cpu().numpy() + 1e-300))
         # np.std of the sharded tensor
         m, v, s = U.weight_stats(full[b:e].clone())
         ok &= (m, v, s) == tuple(np.float32(x) for x in (np.mean(full.cpu().numpy()), np.var(full.cpu().numpy()), np.std(full.cpu().numpy())))
