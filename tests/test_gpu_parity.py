@@ -406,3 +406,47 @@ def test_sharded_equals_single_rank():
                         "--master-addr", "127.0.0.1", "--master-port", "29517", worker], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("OK") == 3 * world and "MISMATCH" not in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Trainer drivers on a device-resident torch model (trainer.py:177-206, :42-72) against the NumPy flow on the oracle
+# ---------------------------------------------------------------------------------------------------------
+def test_compressor_lenet300_matches_reference_flow(U):
+    import torch
+
+    from neural_network_compression_b200.common.trainer import Compressor
+    from neural_network_compression_b200.neural_networks import LeNet300100
+
+    torch.manual_seed(0)
+    net = LeNet300100().cuda()
+    host = {name: [p.detach().cpu().numpy().copy() for p in (layer.weight, layer.bias)] for name, layer in net.get_config().items()}
+    comp = Compressor(net, net.layers_to_prune_with_threshold())
+    # pruned_train step: prune, (optimizer step), re-apply
+    comp._prune_parameters(True)
+    thresholds = {"dense1": (1, 0.1), "dense2": (1, 0.1), "out": (0.5, 0)}
+    for name, layer in net.get_config().items():
+        w, b = host[name]
+        mw = O.prune_weigth(w, thresholds[name][0])
+        mb = O.prune_weigth(b, thresholds[name][1])
+        zw, zb = comp.pruned_indexes_by_layer[layer]
+        assert np.array_equal(zw.cpu().numpy(), mw) and np.array_equal(zb.cpu().numpy(), mb)
+        assert layer.weight.detach().cpu().numpy().tobytes() == w.tobytes()
+    with torch.no_grad():
+        for layer in net.get_config().values():
+            layer.weight.add_(0.001)  # an "optimizer step" that revives pruned weights
+    comp._reset_pruned_parameters()
+    for name, layer in net.get_config().items():
+        zw, _ = comp.pruned_indexes_by_layer[layer]
+        assert bool((layer.weight.detach()[zw] == 0).all())
+        host[name][0] = layer.weight.detach().cpu().numpy().copy()
+    # quantize: 2-bit density with the CDF of the non-zero weights (main.py:96-105)
+    fitted = comp.quantize(True, 2, "density")
+    for name, layer in net.get_config().items():
+        for p, h, km in zip((layer.weight, layer.bias), host[name], fitted[layer]):
+            nz = h.ravel()[h.ravel() != 0]
+            cdfs = O.get_weight_distribution(nz)
+            space = O.init_centroids(h, 2, "density", cdfs)
+            det = O.kmeans1d(h, space, mode=O.MODE_DET)
+            expect = det.cluster_centers_[det.labels_].reshape(h.shape)
+            assert km.cluster_centers_.tobytes() == det.cluster_centers_.tobytes()
+            assert p.detach().cpu().numpy().tobytes() == expect.tobytes()
