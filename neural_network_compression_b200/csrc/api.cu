@@ -741,8 +741,9 @@ int nnc_gather_f32(nnc_ctx *ctx, const float *w, int64_t n, const int64_t *idx, 
 // ---- k-means ---------------------------------------------------------------------------------------------
 // The k-means pipeline on a device-resident tensor (prologue -> compaction -> sort -> Lloyd -> emission); shared by
 // nnc_kmeans1d_f32 and nnc_compress_f32.  Output pointers are the caller's (host or device); w is a device pointer.
-static void kmeans_on_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *init, int k, int max_iter, double tol,
-                             int flags, float *centers, float *centred, int32_t *labels, float *ris, uint8_t *packed, int bits,
+// nz_bound: an upper bound of the non-zero count of the shard when the caller knows one (-1: none), sizes the buffers.
+static void kmeans_on_device(nnc_ctx *ctx, const float *d_w, int64_t n, int64_t nz_bound, const float *init, int k, int max_iter,
+                             double tol, int flags, float *centers, float *centred, int32_t *labels, float *ris, uint8_t *packed, int bits,
                              int64_t *hist, nnc_kmeans_info *info) {
     // n: elements of this rank's shard; n_global: of the whole tensor (they coincide on one rank)
     const bool init_linear = (flags & NNC_KM_INIT_LINEAR) != 0;
@@ -754,20 +755,20 @@ static void kmeans_on_device(nnc_ctx *ctx, const float *d_w, int64_t n, const fl
     if (!init_linear)
         for (int j = 0; j < k; ++j)
             if (!isfinite(init[j])) NNC_FAIL(NNC_ERR_NONFINITE, "initial centroid %d is not finite", j);
-    // 1. mean (NumPy pairwise), min/max, survivor count
-    const QuantPrologue qp = quant_prologue(ctx, d_w, n);
+    // 1. mean (NumPy pairwise), min/max, key range, survivor count -- and the survivors, compacted in the same read
+    const int64_t cap = std::max<int64_t>(1, std::min<int64_t>(n, nz_bound >= 0 ? nz_bound : n));
+    float *buf_a = arena_alloc_t<float>(ctx, (size_t)cap);
+    float *buf_b = arena_alloc_t<float>(ctx, (size_t)cap);
+    quant_prologue(ctx, d_w, n, buf_a, cap);
     read_scalars(ctx);
     prof_mark(ctx, "prologue");
     const DevScalars sc = *ctx->h_scal;
     if (sc.n_nonfinite) NNC_FAIL(NNC_ERR_NONFINITE, "Input X contains NaN or infinity.");
     const int64_t n_nz = (int64_t)(ctx->world > 1 ? sc.n_nz_local : sc.n_nz);  // of this shard
+    if (n_nz > cap) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: %lld survivors exceed the reserved %lld", (long long)n_nz, (long long)cap);
     // 2. survivors -> sorted
-    float *buf_a = arena_alloc_t<float>(ctx, (size_t)std::max<int64_t>(n_nz, 1));
-    float *buf_b = arena_alloc_t<float>(ctx, (size_t)std::max<int64_t>(n_nz, 1));
     const float *d_sorted = buf_a;
     if (n_nz > 0) {
-        compact_tiles_device(ctx, d_w, qp, buf_a);
-        prof_mark(ctx, "compact");
         d_sorted = radix_sort_f32(ctx, buf_a, buf_b, n_nz, sc.amin_nz_m1 + 1u, sc.amax_bits);
         prof_mark(ctx, "sort");
     }
@@ -834,7 +835,7 @@ int nnc_kmeans1d_f32(nnc_ctx *ctx, const float *w, int64_t n, const float *init,
     shard_setup(ctx, n);
     Staged sw = stage_in(ctx, w, sizeof(float) * (size_t)n);
     prof_mark(ctx, "h2d");
-    kmeans_on_device(ctx, static_cast<const float *>(sw.dev), n, init, k, max_iter, tol, flags, centers, centred, labels, ris,
+    kmeans_on_device(ctx, static_cast<const float *>(sw.dev), n, -1, init, k, max_iter, tol, flags, centers, centred, labels, ris,
                      packed, bits, hist, info);
     call.finish();
     NNC_CATCH
@@ -860,7 +861,9 @@ int nnc_compress_f32(nnc_ctx *ctx, float *w, int64_t n, double threshold, int st
     prof_mark(ctx, "prune_d2h");
     if (thr_out) *thr_out = ctx->h_scal->thr;
     if (n_pruned_out) *n_pruned_out = (int64_t)ctx->h_scal->n_pruned;
-    kmeans_on_device(ctx, d_w, n, init, k, max_iter, tol, flags, centers, centred, nullptr, nullptr, packed, bits, hist, info);
+    // every pruned element is a zero now: on one rank n - n_pruned bounds the survivors (on several, n_pruned is global)
+    const int64_t nz_bound = ctx->world == 1 ? n - (int64_t)ctx->h_scal->n_pruned : -1;
+    kmeans_on_device(ctx, d_w, n, nz_bound, init, k, max_iter, tol, flags, centers, centred, nullptr, nullptr, packed, bits, hist, info);
     call.finish();
     NNC_CATCH
 }

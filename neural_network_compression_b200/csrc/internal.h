@@ -183,16 +183,9 @@ size_t np_partials_bytes(const NpPlan &p);
 void np_stats(nnc_ctx *ctx, const float *d_w, int64_t n);  // fills mean/var/std_ in d_scal (2 passes)
 void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth, int thr_mode, uint8_t *d_mask);
 void mask_apply_device(nnc_ctx *ctx, float *d_w, const uint8_t *d_mask, int64_t n);
-// k-means prologue: NumPy mean + min/max + non-zero count + |x| key range (DevScalars), and the non-zero count
-// of every tile of the reduction tree, which compact_tiles_device turns into an order-preserving compaction
-// (flat[flat != 0], trainer.py:55-59) without any inter-CTA dependency.
-struct QuantPrologue {
-    uint32_t num_tiles = 0;
-    const void *tile_desc = nullptr;    // NpTileDesc[num_tiles]
-    unsigned int *tile_counts = nullptr;
-};
-QuantPrologue quant_prologue(nnc_ctx *ctx, const float *d_w, int64_t n);
-void compact_tiles_device(nnc_ctx *ctx, const float *d_w, const QuantPrologue &q, float *d_out);
+// k-means prologue: NumPy mean + min/max + non-zero count + |x| key range (DevScalars), and the non-zero elements
+// themselves written densely (unordered) into d_out -- one read of the tensor.
+void quant_prologue(nnc_ctx *ctx, const float *d_w, int64_t n, float *d_out, int64_t capacity);
 
 // scan.cu : multi-CTA exclusive scans (out[n] = total)
 void exclusive_scan_i64(nnc_ctx *ctx, const long long *d_in, long long n, long long *d_out);

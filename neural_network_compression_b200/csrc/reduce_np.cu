@@ -79,6 +79,7 @@ struct BlockAux {  // shared scratch for visitor epilogues
 // 1.5e-5 wide).
 struct VisitStats {
     static constexpr bool kTileCount = false;
+    static constexpr bool kCompact = false;
     DevScalars *sc;
     double s = 0.0, s2 = 0.0;
     float ts = 0.f, ts2 = 0.f;
@@ -122,6 +123,7 @@ struct VisitStats {
 // plain centred squares (nnc_stats second pass, non-speculative prune fallback)
 struct VisitCenSq {
     static constexpr bool kTileCount = false;
+    static constexpr bool kCompact = false;
     DevScalars *sc;
     float mean;
     __device__ __forceinline__ void begin() { mean = sc->mean; }
@@ -142,6 +144,7 @@ struct VisitCenSq {
 // pass 2 of pruning: centred squares + speculative apply (see file header).
 struct VisitCenSqApply {
     static constexpr bool kTileCount = false;
+    static constexpr bool kCompact = false;
     DevScalars *sc;
     float *w;            // in place
     uint8_t *mask;
@@ -225,9 +228,12 @@ struct VisitCenSqApply {
 // k-means prologue: term = x (-> mean); side: min / max, non-zero count, range of |x| bit patterns over the
 // non-zero elements (the radix-sort key range), non-finite detection (|x| bits >= 0x7f800000).
 struct VisitQuant {
-    static constexpr bool kTileCount = true;  // the kernel also records the non-zero count of every tile
+    static constexpr bool kTileCount = false;
+    static constexpr bool kCompact = true;  // the kernel also writes the non-zero elements of every tile to `out`
     DevScalars *sc;
-    unsigned int *tile_counts;
+    float *out;                       // survivors, dense, in no particular tile order (they are sorted next)
+    unsigned long long *cursor;       // next free slot of `out`
+    unsigned long long capacity;
     float mn = INFINITY, mx = -INFINITY;
     uint32_t amax = 0u, amin_m1 = 0xffffffffu;
     unsigned int nz = 0, nz_before = 0;
@@ -389,11 +395,17 @@ __global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, uin
     __shared__ __align__(16) float tile[NP_TILE_SMEM];
     __shared__ float heap_val[2][64];
     __shared__ unsigned int s_cnt[2];
+    __shared__ unsigned long long s_base[2];
+    extern __shared__ __align__(16) unsigned char np_dyn_smem[];  // kCompact: float s_out[2][NP_TILE_MAX] (32 KB)
+    float(*s_out)[NP_TILE_MAX] = reinterpret_cast<float(*)[NP_TILE_MAX]>(np_dyn_smem);
     __shared__ BlockAux aux;
 
     v.begin();
-    if (V::kTileCount) {
-        if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    if (V::kTileCount || V::kCompact) {
+        if (threadIdx.x < 2) {
+            s_cnt[threadIdx.x] = 0;
+            s_base[threadIdx.x] = 0;
+        }
         __syncthreads();
     }
     const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;
@@ -432,6 +444,16 @@ __global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, uin
             if (lane_id() == 0 && c) atomicAdd(&s_cnt[buf], c);
         }
         __syncthreads();  // tile complete (also: warp 0 finished folding the tile before the previous one)
+        if constexpr (V::kCompact) {
+            // flush the previous tile's survivors: its stage, count and global base are complete since the barrier
+            const int pb = buf ^ 1;
+            const unsigned int c = s_cnt[pb];
+            if (c) {
+                const unsigned long long b = s_base[pb];
+                if (b + c <= v.capacity)
+                    for (unsigned int i = threadIdx.x; i < c; i += NP_THREADS) v.out[b + i] = s_out[pb][i];
+            }
+        }
         // ---- leaves: the 8 lanes of group `grp` sum the node described by gd
         {
             const int o = gd & 8191, s = (gd >> 13) & 255, h = (gd >> 21) & 63;
@@ -456,6 +478,46 @@ __global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, uin
             }
             if (j == 0 && (gd >> 27)) heap_val[buf][h] = val;
         }
+        if constexpr (V::kCompact) {
+            // survivors of the tile, straight from the staged tile (term == value for this visitor), compacted into
+            // the shared-memory stage s_out[buf]: a warp takes the 512 elements [512 w, 512 (w + 1)), counts, and
+            // reserves its slots of the stage with one shared-memory atomic (warp order inside the tile is arbitrary --
+            // the consumer is a sort).
+            const int lane = lane_id(), wbase_e = warp_id() * 512;
+            float4 xs[4];
+            int cnt = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int e = wbase_e + r * 128 + lane * 4;
+                xs[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e < sz) xs[r] = *reinterpret_cast<const float4 *>(&tile[np_pad(e)]);
+                if (e + 3 >= sz) {  // tail of the (globally last) tile: mask what lies beyond it
+                    if (e + 1 >= sz) xs[r].y = 0.f;
+                    if (e + 2 >= sz) xs[r].z = 0.f;
+                    if (e + 3 >= sz) xs[r].w = 0.f;
+                    if (e >= sz) xs[r].x = 0.f;
+                }
+                cnt += (xs[r].x != 0.f) + (xs[r].y != 0.f) + (xs[r].z != 0.f) + (xs[r].w != 0.f);
+            }
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int tt = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += tt;
+            }
+            const int wtot = __shfl_sync(0xffffffffu, incl, 31);
+            unsigned int wb = 0;
+            if (lane == 0 && wtot) wb = atomicAdd(&s_cnt[buf], (unsigned int)wtot);
+            wb = __shfl_sync(0xffffffffu, wb, 0);
+            float *dst = s_out[buf] + wb + (incl - cnt);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (xs[r].x != 0.f) *dst++ = xs[r].x;
+                if (xs[r].y != 0.f) *dst++ = xs[r].y;
+                if (xs[r].z != 0.f) *dst++ = xs[r].z;
+                if (xs[r].w != 0.f) *dst++ = xs[r].w;
+            }
+        }
         __syncthreads();  // node values visible; the tile buffer may be overwritten
         // ---- fold (warp 0): internal nodes take left + right, level by level
         if (threadIdx.x < 32) {
@@ -469,14 +531,23 @@ __global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, uin
             }
             if (lane == 0) partials[t] = heap_val[buf][1];
         }
-        if constexpr (V::kTileCount) {
-            if (threadIdx.x == 64) {  // s_cnt[buf] is next touched two iterations (two barriers) from here
-                v.tile_counts[t] = s_cnt[buf];
-                s_cnt[buf] = 0;
+        if constexpr (V::kCompact) {
+            // one global atomic per tile reserves the output slots; the copy stage -> global happens after the next
+            // barrier (the next tile's "tile complete"), so the atomic's latency is off the critical path
+            if (threadIdx.x == 64) {
+                s_base[buf] = s_cnt[buf] ? atomicAdd(v.cursor, (unsigned long long)s_cnt[buf]) : 0ull;
+                s_cnt[buf ^ 1] = 0;  // flushed above, before this tile's second barrier; reused by the next tile
             }
         }
     }
     __syncthreads();
+    if constexpr (V::kCompact) {  // the last tile of this CTA
+        const int pb = buf ^ 1;
+        const unsigned int c = s_cnt[pb];
+        const unsigned long long b = s_base[pb];
+        if (b + c <= v.capacity)
+            for (unsigned int i = threadIdx.x; i < c; i += NP_THREADS) v.out[b + i] = s_out[pb][i];
+    }
     v.finish(aux);
 }
 
@@ -737,8 +808,16 @@ static NpTileDesc *run_tree(nnc_ctx *ctx, const float *d_w, V v, const FinArgs &
     NNC_LAUNCH(ctx, np_tiles_kernel, (p.num_tiles + 127) / 128, 128, 0, n, p.depth, desc);
     if (ctx->world > 1) NNC_CUDA(cudaMemsetAsync(partials, 0, sizeof(float) * (2 * (size_t)p.num_tiles + 2), ctx->stream));
     const uint32_t t0 = ctx->sh.t0, t1 = ctx->sh.t1;
+    const size_t dyn = V::kCompact ? 2 * sizeof(float) * NP_TILE_MAX : 0;
+    if (V::kCompact) {
+        static bool configured = false;
+        if (!configured) {
+            NNC_CUDA(cudaFuncSetAttribute(np_tree_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            configured = true;
+        }
+    }
     if (t1 > t0)
-        NNC_LAUNCH(ctx, np_tree_kernel<V>, tree_grid(ctx, t1 - t0), NP_THREADS, 0, d_w, t0, t1, ctx->sh.begin,
+        NNC_LAUNCH(ctx, np_tree_kernel<V>, tree_grid(ctx, t1 - t0), NP_THREADS, dyn, d_w, t0, t1, ctx->sh.begin,
                    aligned16(d_w) ? 1 : 0, desc, partials, v);
     if (ctx->world > 1) comm_allreduce(ctx, reinterpret_cast<int64_t *>(partials), (int)((p.num_tiles + 1) / 2), 0);
     exchange_scalars(ctx, exchange_mode);
@@ -769,88 +848,20 @@ void np_stats(nnc_ctx *ctx, const float *d_w, int64_t n) {
     run_tree(ctx, d_w, v2, FinArgs{FIN_VAR, ng, 0.0, 0, 1}, EX_NONE);
 }
 
-QuantPrologue quant_prologue(nnc_ctx *ctx, const float *d_w, int64_t n) {
+// mean (NumPy tree), min / max, key range, non-zero count -- and the survivors themselves, compacted into d_out
+// (capacity elements) in the same read of the tensor.
+void quant_prologue(nnc_ctx *ctx, const float *d_w, int64_t n, float *d_out, int64_t capacity) {
     clear_scalars(ctx);
-    QuantPrologue q;
-    const int64_t ng = ctx->sh.n_global;
     (void)n;
-    q.num_tiles = np_plan(ng).num_tiles;
-    q.tile_counts = arena_alloc_t<unsigned int>(ctx, q.num_tiles);
+    const int64_t ng = ctx->sh.n_global;
+    unsigned long long *cursor = arena_alloc_t<unsigned long long>(ctx, 1);
+    NNC_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), ctx->stream));
     VisitQuant v;
     v.sc = ctx->d_scal;
-    v.tile_counts = q.tile_counts;
-    q.tile_desc = run_tree(ctx, d_w, v, FinArgs{FIN_MEAN, ng, 0.0, 0, 1}, EX_QUANT);
-    return q;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Survivor compaction over the tiles of the prologue: the per-tile non-zero counts are already known, so the tile
-// bases are one small scan and the scatter is a pure streaming pass (no inter-CTA dependency).
-// ---------------------------------------------------------------------------------------------
-// w: this rank's shard; desc / base: the shard's tiles (descriptor offsets are global: shard_begin is subtracted)
-__global__ void __launch_bounds__(NP_THREADS) tile_compact_kernel(const float *__restrict__ w, int vec_ok,
-                                                                   const NpTileDesc *__restrict__ desc, uint32_t num_tiles,
-                                                                   int64_t shard_begin,
-                                                                   const unsigned long long *__restrict__ base,
-                                                                   float *__restrict__ out) {
-    __shared__ int s_warp_cnt[2][NP_THREADS / 32];
-    const int lane = lane_id(), wid = warp_id();
-    int buf = 0;
-    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, buf ^= 1) {
-        const int64_t off = desc[t].off - shard_begin;
-        const int sz = desc[t].sz;
-        // warp `wid` owns elements [512 wid, 512 (wid + 1)) of the tile as 4 rows of 128: (row, lane, component) is
-        // element order, so the survivors keep their order
-        const float *src = w + off;
-        float4 x[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int e = wid * 512 + r * 128 + lane * 4;
-            if (vec_ok && e + 4 <= sz) {
-                x[r] = ld_stream_f4(src + e);
-            } else {
-                x[r].x = e < sz ? src[e] : 0.f;
-                x[r].y = e + 1 < sz ? src[e + 1] : 0.f;
-                x[r].z = e + 2 < sz ? src[e + 2] : 0.f;
-                x[r].w = e + 3 < sz ? src[e + 3] : 0.f;
-            }
-        }
-        int offr[4], wcnt = 0;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int c = (x[r].x != 0.f) + (x[r].y != 0.f) + (x[r].z != 0.f) + (x[r].w != 0.f);
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int tt = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += tt;
-            }
-            offr[r] = wcnt + incl - c;
-            wcnt += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (lane == 0) s_warp_cnt[buf][wid] = wcnt;
-        __syncthreads();  // the other buffer is free again: every warp passed the barrier of the previous tile
-        unsigned long long b = base[t];
-        for (int i = 0; i < wid; ++i) b += s_warp_cnt[buf][i];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            float *dst = out + b + offr[r];
-            if (x[r].x != 0.f) *dst++ = x[r].x;
-            if (x[r].y != 0.f) *dst++ = x[r].y;
-            if (x[r].z != 0.f) *dst++ = x[r].z;
-            if (x[r].w != 0.f) *dst++ = x[r].w;
-        }
-    }
-}
-
-void compact_tiles_device(nnc_ctx *ctx, const float *d_w, const QuantPrologue &q, float *d_out) {
-    const uint32_t t0 = ctx->sh.t0, tiles = ctx->sh.t1 - ctx->sh.t0;
-    if (tiles == 0) return;
-    unsigned long long *base = arena_alloc_t<unsigned long long>(ctx, (size_t)tiles + 1);
-    exclusive_scan_u32_u64(ctx, q.tile_counts + t0, (long long)tiles, base);
-    const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, tiles);
-    NNC_LAUNCH(ctx, tile_compact_kernel, grid, NP_THREADS, 0, d_w, aligned16(d_w) ? 1 : 0,
-               static_cast<const NpTileDesc *>(q.tile_desc) + t0, tiles, ctx->sh.begin, base, d_out);
+    v.out = d_out;
+    v.cursor = cursor;
+    v.capacity = (unsigned long long)capacity;
+    run_tree(ctx, d_w, v, FinArgs{FIN_MEAN, ng, 0.0, 0, 1}, EX_QUANT);
 }
 
 void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth, int thr_mode, uint8_t *d_mask) {
