@@ -767,14 +767,23 @@ static void kmeans_on_device(nnc_ctx *ctx, const float *d_w, int64_t n, int64_t 
     const int64_t n_nz = (int64_t)(ctx->world > 1 ? sc.n_nz_local : sc.n_nz);  // of this shard
     if (n_nz > cap) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: %lld survivors exceed the reserved %lld", (long long)n_nz, (long long)cap);
     // 2. survivors -> sorted
+    // (a large narrow-range layer: as (value, multiplicity) runs from a key histogram, khist.cu; otherwise radix sort)
     const float *d_sorted = buf_a;
+    SortedRuns runs;
     if (n_nz > 0) {
-        d_sorted = radix_sort_f32(ctx, buf_a, buf_b, n_nz, sc.amin_nz_m1 + 1u, sc.amax_bits);
+        if (hist_sort_applicable(n_nz, sc.amin_nz_m1 + 1u, sc.amax_bits)) {
+            runs = hist_sort_f32(ctx, buf_a, buf_b, n_nz, sc.amin_nz_m1 + 1u, sc.amax_bits);
+            d_sorted = runs.val;
+        } else {
+            d_sorted = radix_sort_f32(ctx, buf_a, buf_b, n_nz, sc.amin_nz_m1 + 1u, sc.amax_bits);
+        }
         prof_mark(ctx, "sort");
     }
     // 3. Lloyd iterations on the sorted survivors + the zero run
     LloydHandle h;
     h.d_sorted = d_sorted;
+    h.d_cnt = runs.cnt;
+    h.n_ent = runs.n_ent;
     h.n_nz = n_nz;
     h.n0 = n - n_nz;
     h.n = n_global;

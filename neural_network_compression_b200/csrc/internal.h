@@ -201,6 +201,15 @@ void gather_device(nnc_ctx *ctx, const float *d_w, int64_t n, const int64_t *h_i
 // sort.cu : onesweep LSD radix sort of float32 keys; returns pointer to the sorted buffer (d_a or d_b)
 float *radix_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n, uint32_t amin, uint32_t amax);
 
+// khist.cu : the sorted survivors as ascending (distinct value, multiplicity) runs from a full-resolution key histogram
+struct SortedRuns {
+    const float *val = nullptr;
+    const uint32_t *cnt = nullptr;
+    int64_t n_ent = 0;
+};
+bool hist_sort_applicable(int64_t n, uint32_t amin, uint32_t amax);
+SortedRuns hist_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n, uint32_t amin, uint32_t amax);
+
 // lloyd.cu
 struct LloydResult {
     int n_iter, strict, n_reloc, fixed_exp;
@@ -209,7 +218,9 @@ struct LloydResult {
 struct LloydDevice;  // opaque device-side state
 struct LloydHandle {
     LloydDevice *d_state = nullptr;
-    const float *d_sorted = nullptr;
+    const float *d_sorted = nullptr;    // surviving weights ascending: one entry per sample, or (d_cnt) per distinct value
+    const uint32_t *d_cnt = nullptr;    // multiplicity of every entry (nullptr: one sample per entry)
+    int64_t n_ent = 0;                  // entries (with d_cnt only; otherwise n_nz)
     int64_t n_nz = 0, n0 = 0, n = 0;
     int k = 0;
     float mean = 0.f;

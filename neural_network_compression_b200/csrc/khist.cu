@@ -1,0 +1,429 @@
+// khist.cu -- the sorted survivors as (distinct value, multiplicity) runs, built WITHOUT a comparison or LSD sort.
+//
+// The Lloyd kernels (lloyd.cu) only need the surviving weights as an ascending sequence with multiplicities.  For a
+// large pruned layer the survivors occupy a narrow |x| bit range -- 26 bits of rank-image key for a pruned
+// N(0, sigma^2) layer (sort.cu: RsKeyMap) -- while there are hundreds of millions of them, so the multiset is
+// smaller as a full-resolution key histogram than as a sorted array.  This file builds that histogram:
+//
+//   count     per-chunk histograms of the key's HIGH digit (key >> 15)                       read  4 B/key
+//   scatter   NON-stable partition by the high digit (shared-memory atomics rank the keys;
+//             the tile is staged in digit order and written out in coalesced runs)           read + write 4 B/key
+//   hist      one CTA per bucket: 2^15-bin shared-memory histogram of the LOW 15 bits        read  4 B/key
+//             -> dense H[2^keybits] (uint32)                                                 write 4 B/bin
+//   compact   non-empty bins -> (value, count) entries in key order = ascending value        read H, write 8 B/entry
+//
+// 16 B of traffic per key + 12..16 B per histogram bin, against 36 B per key (+ 4 for the tile sums) of the
+// three-pass radix sort -- and none of it needs a stable ranking, which is what made the LSD scatter pass
+// shared-memory bound.  Keys-only data: equal keys are indistinguishable, so the result is exactly the sorted array
+// run-length encoded.  The path is taken when the histogram is not larger than the data (see hist_sort_applicable);
+// small or wide-range tensors keep the radix sort.
+//
+// Reference context: this replaces, together with lloyd.cu, the n x k distance evaluations of
+// sklearn/cluster/_k_means_lloyd.pyx:196-213 that neural_network_compression/common/utility.py:237-238 runs.
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace nnc {
+
+constexpr int KH_LOW = 15;                // low key bits resolved in shared memory
+constexpr int KH_BINS = 1 << KH_LOW;      // 32768 bins = 128 KB of shared memory
+constexpr int KH_MAX_HB = 12;             // high digit: at most 4096 buckets (keybits <= 27)
+constexpr int KH_THREADS = 512;
+constexpr int KH_ITEMS = 16;
+constexpr int KH_TILE = KH_THREADS * KH_ITEMS;  // 8192 keys per scatter tile
+constexpr int KH_CHUNK = 1 << 18;               // keys per work item of the histogram kernel
+constexpr int KH_HT = 1024;                     // bins per compaction tile
+
+struct KhKeyMap {  // same rank image as sort.cu's RsKeyMap
+    uint32_t amin, range;
+};
+__device__ __forceinline__ uint32_t kh_key(uint32_t bits, KhKeyMap km) {
+    const uint32_t m = (bits & 0x7fffffffu) - km.amin;
+    return (bits & 0x80000000u) ? km.range - m : km.range + 1u + m;
+}
+__device__ __forceinline__ uint32_t kh_unkey(uint32_t key, KhKeyMap km) {
+    return key <= km.range ? ((km.range - key + km.amin) | 0x80000000u) : (key - km.range - 1u + km.amin);
+}
+
+// ---- count: chunk_hist[c][d] = keys of chunk c whose high digit is d ---------------------------------------
+__global__ void __launch_bounds__(KH_THREADS) kh_count_kernel(const uint32_t *__restrict__ in, int64_t n, int64_t tiles_per_chunk,
+                                                              int nb, KhKeyMap km, uint32_t *__restrict__ chunk_hist) {
+    extern __shared__ uint32_t kh_h[];
+    for (int i = threadIdx.x; i < nb; i += KH_THREADS) kh_h[i] = 0;
+    __syncthreads();
+    const int64_t lo = (int64_t)blockIdx.x * tiles_per_chunk * KH_TILE;
+    const int64_t hi = min(n, lo + tiles_per_chunk * KH_TILE);
+    auto one = [&](uint32_t bits) { atomicAdd(&kh_h[kh_key(bits, km) >> KH_LOW], 1u); };
+    if ((reinterpret_cast<uintptr_t>(in) & 15u) == 0) {  // lo is a multiple of 8192 keys
+        const int64_t nvec = (hi - lo) >> 2;
+        const uint32_t *p = in + lo;
+        for (int64_t i = threadIdx.x; i < nvec; i += KH_THREADS) {
+            uint4 v = ld_stream_u4(p + 4 * i);
+            one(v.x);
+            one(v.y);
+            one(v.z);
+            one(v.w);
+        }
+        for (int64_t i = lo + (nvec << 2) + threadIdx.x; i < hi; i += KH_THREADS) one(in[i]);
+    } else {
+        for (int64_t i = lo + threadIdx.x; i < hi; i += KH_THREADS) one(in[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += KH_THREADS) chunk_hist[(size_t)blockIdx.x * nb + i] = kh_h[i];
+}
+
+// ---- base: bucket starts, per-chunk write cursors, work items of the histogram kernel -----------------------
+// one thread per digit: crel[c][d] = keys of digit d in the chunks before c, tot[d] = keys of digit d
+__global__ void __launch_bounds__(128) kh_crel_kernel(const uint32_t *__restrict__ chunk_hist, int chunks, int nb,
+                                                      uint32_t *__restrict__ crel_lo, uint32_t *__restrict__ crel_hi,
+                                                      unsigned long long *__restrict__ tot) {
+    const int d = blockIdx.x * 128 + threadIdx.x;
+    if (d >= nb) return;
+    unsigned long long r = 0;
+#pragma unroll 8
+    for (int c = 0; c < chunks; ++c) {
+        const uint32_t v = chunk_hist[(size_t)c * nb + d];
+        crel_lo[(size_t)c * nb + d] = (uint32_t)r;
+        crel_hi[(size_t)c * nb + d] = (uint32_t)(r >> 32);
+        r += v;
+    }
+    tot[d] = r;
+}
+
+// bucket_off[d] = keys with a smaller high digit (bucket_off[nb] = n); item_off[d] = work items (KH_CHUNK keys each)
+// of the buckets before d
+__global__ void __launch_bounds__(1024) kh_base_kernel(const unsigned long long *__restrict__ tot, int nb,
+                                                       unsigned long long *__restrict__ bucket_off, uint32_t *__restrict__ item_off) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned int s_iwarp[32];
+    const int per = (nb + 1023) / 1024;  // digits per thread (consecutive)
+    const int d0 = threadIdx.x * per;
+    unsigned long long sum = 0;
+    unsigned int items = 0;
+    for (int j = 0; j < per; ++j) {
+        const int d = d0 + j;
+        const unsigned long long t = d < nb ? tot[d] : 0ull;
+        sum += t;
+        items += (unsigned int)((t + KH_CHUNK - 1) / KH_CHUNK);
+    }
+    const int lane = lane_id(), w = warp_id();
+    unsigned long long incl = sum;
+    unsigned int iincl = items;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        unsigned int ti = __shfl_up_sync(0xffffffffu, iincl, o);
+        if (lane >= o) {
+            incl += t;
+            iincl += ti;
+        }
+    }
+    if (lane == 31) {
+        s_warp[w] = incl;
+        s_iwarp[w] = iincl;
+    }
+    __syncthreads();
+    unsigned long long add = 0;
+    unsigned int iadd = 0;
+    for (int i = 0; i < w; ++i) {
+        add += s_warp[i];
+        iadd += s_iwarp[i];
+    }
+    unsigned long long run = incl - sum + add;
+    unsigned int irun = iincl - items + iadd;
+    for (int j = 0; j < per; ++j) {
+        const int d = d0 + j;
+        if (d < nb) {
+            bucket_off[d] = run;
+            item_off[d] = irun;
+            const unsigned long long t = tot[d];
+            run += t;
+            irun += (unsigned int)((t + KH_CHUNK - 1) / KH_CHUNK);
+        }
+    }
+    if (threadIdx.x == 1023) {
+        bucket_off[nb] = run;
+        item_off[nb] = irun;
+    }
+}
+
+// ---- scatter: non-stable partition by the high digit --------------------------------------------------------
+// Shared memory (dynamic): stage[KH_TILE] | keys[KH_TILE] | hist[nb] | gbase[nb] (u64) | run[nb] (u64)
+__global__ void __launch_bounds__(KH_THREADS, 2) kh_scatter_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int64_t n,
+                                                                int64_t tiles_per_chunk, int nb, KhKeyMap km,
+                                                                const unsigned long long *__restrict__ bucket_off,
+                                                                const uint32_t *__restrict__ crel_lo, const uint32_t *__restrict__ crel_hi) {
+    extern __shared__ __align__(16) unsigned char kh_smem[];
+    uint32_t *stage = reinterpret_cast<uint32_t *>(kh_smem);
+    uint32_t *keys = stage + KH_TILE;
+    unsigned long long *gbase = reinterpret_cast<unsigned long long *>(keys + KH_TILE);
+    unsigned long long *run = gbase + nb;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(run + nb);
+    __shared__ uint32_t s_warp[KH_THREADS / 32];
+    const int lane = lane_id(), wid = warp_id();
+    for (int d = threadIdx.x; d < nb; d += KH_THREADS)
+        run[d] = bucket_off[d] + (((unsigned long long)crel_hi[(size_t)blockIdx.x * nb + d] << 32) | crel_lo[(size_t)blockIdx.x * nb + d]);
+    const int64_t n_tiles = (n + KH_TILE - 1) / KH_TILE;
+    const int64_t t0 = (int64_t)blockIdx.x * tiles_per_chunk, t1 = min(n_tiles, t0 + tiles_per_chunk);
+    const bool src_aligned = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+    const int per = (nb + KH_THREADS - 1) / KH_THREADS;  // bins per thread in the scan (consecutive bins)
+    auto fetch = [&](int64_t tile) {
+        const int64_t tile_base = tile * KH_TILE;
+        if (src_aligned && tile_base + KH_TILE <= n) {
+#pragma unroll
+            for (int c = 0; c < KH_TILE / 4 / KH_THREADS; ++c) {
+                const int chunk = c * KH_THREADS + threadIdx.x;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&stage[4 * chunk]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(in + tile_base + 4 * chunk) : "memory");
+            }
+        } else {
+            for (int i = threadIdx.x; i < KH_TILE; i += KH_THREADS) stage[i] = tile_base + i < n ? in[tile_base + i] : 0u;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (t0 < t1) fetch(t0);
+    for (int64_t tile = t0; tile < t1; ++tile) {
+        const int64_t tile_base = tile * KH_TILE;
+        const int valid = (int)min((int64_t)KH_TILE, n - tile_base);
+        for (int d = threadIdx.x; d < nb; d += KH_THREADS) hist[d] = 0;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // staged tile complete, counters cleared, previous tile's write-out finished
+        uint32_t key[KH_ITEMS];
+        uint32_t rank[KH_ITEMS];
+#pragma unroll
+        for (int i = 0; i < KH_ITEMS; ++i) {
+            const int e = i * KH_THREADS + threadIdx.x;
+            key[i] = kh_key(stage[e], km);
+        }
+#pragma unroll
+        for (int i = 0; i < KH_ITEMS; ++i) {
+            const int e = i * KH_THREADS + threadIdx.x;
+            rank[i] = e < valid ? atomicAdd(&hist[key[i] >> KH_LOW], 1u) : 0u;
+        }
+        __syncthreads();  // stage consumed, counts complete
+        if (tile + 1 < t1) fetch(tile + 1);
+        // exclusive scan of the digit counts (thread t owns bins [t * per, t * per + per))
+        {
+            const int b0 = threadIdx.x * per;
+            uint32_t loc = 0;
+            for (int j = 0; j < per; ++j)
+                if (b0 + j < nb) loc += hist[b0 + j];
+            uint32_t incl = loc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_warp[wid] = incl;
+            __syncthreads();
+            uint32_t add = 0;
+            for (int w2 = 0; w2 < wid; ++w2) add += s_warp[w2];
+            uint32_t start = incl - loc + add;
+            for (int j = 0; j < per; ++j) {
+                const int d = b0 + j;
+                if (d < nb) {
+                    const uint32_t c = hist[d];
+                    hist[d] = start;  // position of the digit's run in the staged tile
+                    const unsigned long long r = run[d];
+                    gbase[d] = r - start;
+                    run[d] = r + c;
+                    start += c;
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < KH_ITEMS; ++i) {
+            const int e = i * KH_THREADS + threadIdx.x;
+            if (e < valid) keys[hist[key[i] >> KH_LOW] + rank[i]] = key[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < KH_ITEMS; ++j) {
+            const int p = threadIdx.x + j * KH_THREADS;
+            if (p < valid) {
+                const uint32_t k = keys[p];
+                out[gbase[k >> KH_LOW] + p] = k;
+            }
+        }
+    }
+}
+
+// ---- hist: low-digit histogram of one work item (<= KH_CHUNK keys of one bucket) in shared memory -----------
+// IN_FLOAT: the input is the raw survivor array (no partition pass ran: keybits <= KH_LOW, one bucket).
+template <bool IN_FLOAT>
+__global__ void __launch_bounds__(1024) kh_hist_kernel(const uint32_t *__restrict__ in, int nb, int low_bins, KhKeyMap km,
+                                                       const unsigned long long *__restrict__ bucket_off,
+                                                       const uint32_t *__restrict__ item_off, uint32_t *__restrict__ H) {
+    extern __shared__ uint32_t kh_bins[];
+    const uint32_t item = blockIdx.x;
+    if (item >= item_off[nb]) return;
+    int lo = 0, hi = nb;  // largest bucket b with item_off[b] <= item (empty buckets own no items)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (item_off[mid] <= item)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    const int b = lo;
+    const uint32_t items_b = item_off[b + 1] - item_off[b];
+    const unsigned long long beg = bucket_off[b] + (unsigned long long)(item - item_off[b]) * KH_CHUNK;
+    const unsigned long long end = min(bucket_off[b + 1], beg + KH_CHUNK);
+    for (int i = threadIdx.x; i < low_bins; i += 1024) kh_bins[i] = 0;
+    __syncthreads();
+    const uint32_t lmask = (uint32_t)low_bins - 1u;
+    auto one = [&](uint32_t v) {
+        const uint32_t k = IN_FLOAT ? kh_key(v, km) : v;
+        atomicAdd(&kh_bins[k & lmask], 1u);
+    };
+    // head up to the first 16-byte boundary, vector body, tail
+    const uint32_t *p = in + beg;
+    const unsigned long long cnt = end - beg;
+    unsigned long long head = ((16u - (unsigned)(reinterpret_cast<uintptr_t>(p) & 15u)) & 15u) >> 2;
+    if (head > cnt) head = cnt;
+    if (threadIdx.x < head) one(p[threadIdx.x]);
+    const unsigned long long nvec = (cnt - head) >> 2;
+    const uint32_t *pv = p + head;
+    for (unsigned long long i = threadIdx.x; i < nvec; i += 1024) {
+        const uint4 v = ld_stream_u4(pv + 4 * i);
+        one(v.x);
+        one(v.y);
+        one(v.z);
+        one(v.w);
+    }
+    for (unsigned long long i = head + (nvec << 2) + threadIdx.x; i < cnt; i += 1024) one(p[i]);
+    __syncthreads();
+    uint32_t *Hb = H + ((size_t)b << KH_LOW);
+    if (items_b == 1) {
+        for (int i = threadIdx.x; i < low_bins; i += 1024) {
+            const uint32_t c = kh_bins[i];
+            if (c) Hb[i] = c;
+        }
+    } else {  // a bucket larger than one work item: merge the partial histograms
+        for (int i = threadIdx.x; i < low_bins; i += 1024) {
+            const uint32_t c = kh_bins[i];
+            if (c) atomicAdd(&Hb[i], c);
+        }
+    }
+}
+
+// ---- compact: non-empty bins -> (value, count) entries ---------------------------------------------------------
+__global__ void __launch_bounds__(KH_HT) kh_tilecount_kernel(const uint32_t *__restrict__ H, uint32_t *__restrict__ tnz) {
+    __shared__ int s_warp[KH_HT / 32];
+    const uint32_t c = H[(size_t)blockIdx.x * KH_HT + threadIdx.x];
+    const int nzw = __popc(__ballot_sync(0xffffffffu, c != 0));
+    if (lane_id() == 0) s_warp[warp_id()] = nzw;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < KH_HT / 32; ++w) t += s_warp[w];
+        tnz[blockIdx.x] = (uint32_t)t;
+    }
+}
+
+__global__ void __launch_bounds__(KH_HT) kh_compact_kernel(const uint32_t *__restrict__ H, const unsigned long long *__restrict__ toff,
+                                                           KhKeyMap km, float *__restrict__ val, uint32_t *__restrict__ cnt) {
+    __shared__ int s_warp[KH_HT / 32];
+    const uint32_t key = blockIdx.x * KH_HT + threadIdx.x;
+    const uint32_t c = H[key];
+    const unsigned bal = __ballot_sync(0xffffffffu, c != 0);
+    if (lane_id() == 0) s_warp[warp_id()] = __popc(bal);
+    __syncthreads();
+    if (c) {
+        int before = __popc(bal & ((1u << lane_id()) - 1u));
+        for (int w = 0; w < warp_id(); ++w) before += s_warp[w];
+        const unsigned long long at = toff[blockIdx.x] + (unsigned long long)before;
+        val[at] = __uint_as_float(kh_unkey(key, km));
+        cnt[at] = c;
+    }
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------------
+static int kh_keybits(uint32_t amin, uint32_t amax) {
+    const unsigned long long span = 2ull * (unsigned long long)(amax - amin) + 2ull;  // number of distinct keys
+    int keybits = 1;
+    while ((1ull << keybits) < span) keybits++;
+    return keybits;
+}
+
+bool hist_sort_applicable(int64_t n, uint32_t amin, uint32_t amax) {
+    if (n <= 1 || amax < amin || n >= (1ll << 40)) return false;
+    const int keybits = kh_keybits(amin, amax);
+    if (keybits > KH_LOW + KH_MAX_HB) return false;
+    const char *env = getenv("NNC_SORT_PATH");  // tests / experiments: "hist" or "radix"
+    if (env && !strcmp(env, "hist")) return true;
+    if (env && !strcmp(env, "radix")) return false;
+    // the histogram costs about three sweeps of 4 B per BIN on top of 16 B per key; the radix sort 40 B per key
+    return n >= (1ll << keybits) / 2;
+}
+
+SortedRuns hist_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n, uint32_t amin, uint32_t amax) {
+    const int keybits = kh_keybits(amin, amax);
+    if (keybits > KH_LOW + KH_MAX_HB) NNC_FAIL(NNC_ERR_INTERNAL, "histogram path: %d key bits", keybits);
+    KhKeyMap km{amin, amax - amin};
+    const int hb = std::max(0, keybits - KH_LOW);
+    const int nb = 1 << hb;
+    const int low_bins = 1 << std::min(keybits, KH_LOW);
+    const size_t n_bins = (size_t)1 << keybits;
+    static bool configured = false;
+    if (!configured) {
+        NNC_CUDA(cudaFuncSetAttribute(kh_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KH_BINS * 4));
+        NNC_CUDA(cudaFuncSetAttribute(kh_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KH_BINS * 4));
+        NNC_CUDA(cudaFuncSetAttribute(kh_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      KH_TILE * 8 + (1 << KH_MAX_HB) * 20));
+        configured = true;
+    }
+    uint32_t *H = arena_alloc_t<uint32_t>(ctx, std::max<size_t>(n_bins, KH_HT));
+    NNC_CUDA(cudaMemsetAsync(H, 0, sizeof(uint32_t) * std::max<size_t>(n_bins, KH_HT), ctx->stream));
+    unsigned long long *bucket_off = arena_alloc_t<unsigned long long>(ctx, (size_t)nb + 1);
+    uint32_t *item_off = arena_alloc_t<uint32_t>(ctx, (size_t)nb + 1);
+    const uint32_t *a = reinterpret_cast<const uint32_t *>(d_a);
+    uint32_t *b = reinterpret_cast<uint32_t *>(d_b);
+    const int max_items = (int)std::min<int64_t>(n / KH_CHUNK + nb, (int64_t)1 << 30);
+    if (hb > 0) {
+        const int64_t n_tiles = (n + KH_TILE - 1) / KH_TILE;
+        const int64_t want_chunks = std::min<int64_t>(1024, (int64_t)ctx->sm_count * 2);
+        const int64_t tiles_per_chunk = (n_tiles + want_chunks - 1) / want_chunks;
+        const int chunks = (int)((n_tiles + tiles_per_chunk - 1) / tiles_per_chunk);
+        uint32_t *chunk_hist = arena_alloc_t<uint32_t>(ctx, (size_t)chunks * nb);
+        uint32_t *crel_lo = arena_alloc_t<uint32_t>(ctx, (size_t)chunks * nb);
+        uint32_t *crel_hi = arena_alloc_t<uint32_t>(ctx, (size_t)chunks * nb);
+        unsigned long long *tot = arena_alloc_t<unsigned long long>(ctx, (size_t)nb);
+        NNC_LAUNCH(ctx, kh_count_kernel, chunks, KH_THREADS, nb * 4, a, n, tiles_per_chunk, nb, km, chunk_hist);
+        NNC_LAUNCH(ctx, kh_crel_kernel, (nb + 127) / 128, 128, 0, chunk_hist, chunks, nb, crel_lo, crel_hi, tot);
+        NNC_LAUNCH(ctx, kh_base_kernel, 1, 1024, 0, tot, nb, bucket_off, item_off);
+        NNC_LAUNCH(ctx, kh_scatter_kernel, chunks, KH_THREADS, KH_TILE * 8 + nb * 20, a, b, n, tiles_per_chunk, nb, km, bucket_off,
+                   crel_lo, crel_hi);
+        NNC_LAUNCH(ctx, kh_hist_kernel<false>, max_items, 1024, low_bins * 4, b, nb, low_bins, km, bucket_off, item_off, H);
+    } else {
+        const unsigned long long h_off[2] = {0ull, (unsigned long long)n};
+        const uint32_t h_items[2] = {0u, (uint32_t)((n + KH_CHUNK - 1) / KH_CHUNK)};
+        NNC_CUDA(cudaMemcpyAsync(bucket_off, h_off, sizeof(h_off), cudaMemcpyHostToDevice, ctx->stream));
+        NNC_CUDA(cudaMemcpyAsync(item_off, h_items, sizeof(h_items), cudaMemcpyHostToDevice, ctx->stream));
+        NNC_CUDA(cudaStreamSynchronize(ctx->stream));  // the two host arrays are on this frame
+        NNC_LAUNCH(ctx, kh_hist_kernel<true>, (int)h_items[1], 1024, low_bins * 4, a, 1, low_bins, km, bucket_off, item_off, H);
+    }
+    // non-empty bins -> entries; the survivor buffers are dead from here on and take the entries
+    const long long n_htiles = (long long)(std::max<size_t>(n_bins, KH_HT) / KH_HT);
+    uint32_t *tnz = arena_alloc_t<uint32_t>(ctx, (size_t)n_htiles + 1);
+    unsigned long long *toff = arena_alloc_t<unsigned long long>(ctx, (size_t)n_htiles + 2);
+    NNC_LAUNCH(ctx, kh_tilecount_kernel, (int)n_htiles, KH_HT, 0, H, tnz);
+    exclusive_scan_u32_u64(ctx, tnz, n_htiles, toff);
+    NNC_LAUNCH(ctx, kh_compact_kernel, (int)n_htiles, KH_HT, 0, H, toff, km, d_a, b);
+    unsigned long long n_ent = 0;
+    NNC_CUDA(cudaMemcpyAsync(&n_ent, toff + n_htiles, sizeof(n_ent), cudaMemcpyDeviceToHost, ctx->stream));
+    NNC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_ent == 0 || (int64_t)n_ent > n) NNC_FAIL(NNC_ERR_INTERNAL, "histogram path: %llu entries for %lld keys", n_ent, (long long)n);
+    SortedRuns r;
+    r.val = d_a;
+    r.cnt = b;
+    r.n_ent = (int64_t)n_ent;
+    return r;
+}
+
+}  // namespace nnc

@@ -41,7 +41,10 @@ struct LloydHeader {
     int k, max_iter, fixed_exp, pad0;
     int rank, world;
     unsigned long long *cand;  // relocation candidates [world][k][2] (see ll_update_kernel phase 1)
-    long long n, n_nz, n0, n_tiles;
+    long long n, n_nz, n0, n_tiles;  // n_nz: surviving ELEMENTS of this shard (sum of the entry counts)
+    long long n_ent;                 // entries of the sorted array (= n_nz when every entry counts once)
+    const unsigned int *cnt;         // multiplicity of every entry (nullptr: all ones)
+    const long long *ctile;          // exclusive prefix of the entry counts at tile granularity (with cnt only)
     float mean, tol, xabs_max, pad1;
     double scale, tol_rel;
 };
@@ -56,7 +59,8 @@ struct LloydDevice : LloydHeader {
     float c_save[TB_KMAX];
     long long hist[TB_KMAX];  // code histogram of the final labelling (ll_count_kernel)
     RegionTable tab;
-    long long rpos[2 * TB_KMAX + 2];
+    long long rpos[2 * TB_KMAX + 2];  // entries before every region boundary
+    long long rcnt[2 * TB_KMAX + 2];  // elements before every region boundary (= rpos without multiplicities)
     long long rsum[2 * TB_KMAX + 2];
     // zone partials per distinct index
     long long zW[TB_KMAX], zS[TB_KMAX], zmin[TB_KMAX], zmax[TB_KMAX];
@@ -80,34 +84,39 @@ struct LloydDevice : LloydHeader {
 // ---------------------------------------------------------------------------------------------
 // prep: per-tile sums of q, samples, moments
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ll_tilesum_kernel(const float *__restrict__ ks, long long n_nz, float mean,
-                                                         double scale, long long *tsum, float *samp, LloydDevice *st) {
-    const long long n_tiles = (n_nz + LL_TS - 1) / LL_TS;
+__global__ void __launch_bounds__(256) ll_tilesum_kernel(const float *__restrict__ ks, const unsigned int *__restrict__ cnt,
+                                                         long long n_ent, float mean, double scale, long long *tsum,
+                                                         long long *tcnt, float *samp, LloydDevice *st) {
+    const long long n_tiles = (n_ent + LL_TS - 1) / LL_TS;
     const int wpb = blockDim.x >> 5;
     long long s1 = 0;
-    unsigned long long s2lo = 0, s2hi = 0;
+    unsigned __int128 s2 = 0;  // sum of count * q^2 (q^2 < 2^61, count < 2^32)
     for (long long t = blockIdx.x * (long long)wpb + warp_id(); t < n_tiles; t += (long long)gridDim.x * wpb) {
         long long base = t * LL_TS;
-        long long acc = 0;
+        long long acc = 0, cacc = 0;
 #pragma unroll 4
         for (int j = 0; j < LL_TS / 32; ++j) {
             long long i = base + j * 32 + lane_id();
-            if (i < n_nz) {
+            if (i < n_ent) {
                 float x = ks[i];
+                const long long c = cnt ? (long long)cnt[i] : 1ll;
                 long long q = fixed_q(fsub(x, mean), scale);
-                acc += q;
-                unsigned long long qq = (unsigned long long)(q * q);
-                s2lo += qq & 0x7fffffffull;
-                s2hi += qq >> 31;
+                acc += q * c;
+                cacc += c;
+                s2 += (unsigned __int128)(unsigned long long)(q * q) * (unsigned long long)c;
                 if (j == 0 && lane_id() == 0) samp[t] = x;
             }
         }
         acc = warp_sum_ll(acc);
         if (lane_id() == 0) tsum[t] = acc;
+        if (tcnt) {
+            cacc = warp_sum_ll(cacc);
+            if (lane_id() == 0) tcnt[t] = cacc;
+        }
         s1 += acc;  // every lane holds the warp total; only lane 0 contributes below
     }
-    s2lo = warp_sum_ull(s2lo);
-    s2hi = warp_sum_ull(s2hi);
+    unsigned long long s2lo = warp_sum_ull((unsigned long long)(s2 & 0x7fffffffull));
+    unsigned long long s2hi = warp_sum_ull((unsigned long long)(s2 >> 31));
     if (lane_id() == 0) {
         atomicAdd((unsigned long long *)&st->s1, (unsigned long long)s1);
         atomicAdd(&st->s2_lo, s2lo);
@@ -174,17 +183,20 @@ __global__ void __launch_bounds__(TB_THREADS) ll_table_kernel(LloydDevice *st) {
     if (tid == 0) {
         const int R = st->tab.R;
         st->rpos[0] = 0;
+        st->rcnt[0] = 0;
         st->rsum[0] = 0;
-        st->rpos[R] = st->n_nz;
+        st->rpos[R] = st->n_ent;
+        st->rcnt[R] = st->n_nz;
         st->rsum[R] = st->total_q;
     }
 }
 
-// number of sorted survivors with fl(x - mean) < t, and the sum of q over them; one warp per boundary
-__device__ __forceinline__ void warp_boundary_search(const float *__restrict__ ks, const float *__restrict__ samp,
-                                                     const long long *__restrict__ ptile, long long n_nz,
+// entries / elements of the sorted survivors with fl(x - mean) < t, and the sum of q over them; one warp per boundary
+__device__ __forceinline__ void warp_boundary_search(const float *__restrict__ ks, const unsigned int *__restrict__ cnt,
+                                                     const float *__restrict__ samp, const long long *__restrict__ ptile,
+                                                     const long long *__restrict__ ctile, long long n_ent,
                                                      long long n_tiles, float mean, double scale, float t,
-                                                     long long &pos_out, long long &sum_out) {
+                                                     long long &pos_out, long long &cnt_out, long long &sum_out) {
     const int lane = lane_id();
     long long lo = 0, hi = n_tiles;  // first tile whose first key fails the predicate lies in [lo, hi]
     while (lo < hi) {
@@ -207,27 +219,34 @@ __device__ __forceinline__ void warp_boundary_search(const float *__restrict__ k
     }
     if (lo == 0) {
         pos_out = 0;
+        cnt_out = 0;
         sum_out = 0;
         return;
     }
     const long long tile = lo - 1;
     const long long base = tile * LL_TS;
-    long long cnt = 0, acc = 0;
+    long long npos = 0, acc = 0, cacc = 0;
     float xv[LL_TS / 32];
+    unsigned int cv[LL_TS / 32];
 #pragma unroll
     for (int j = 0; j < LL_TS / 32; ++j) {  // all 32 loads in flight before the first use
         const long long i = base + j * 32 + lane;
-        xv[j] = i < n_nz ? ks[i] : INFINITY;
+        xv[j] = i < n_ent ? ks[i] : INFINITY;
+        cv[j] = (cnt && i < n_ent) ? cnt[i] : 1u;
     }
 #pragma unroll
     for (int j = 0; j < LL_TS / 32; ++j) {
         const float xc = fsub(xv[j], mean);
         const bool p = xc < t;  // padding is +inf: never counted
-        if (p) acc += fixed_q(xc, scale);
-        cnt += __popc(__ballot_sync(0xffffffffu, p));
+        if (p) {
+            acc += fixed_q(xc, scale) * (long long)cv[j];
+            cacc += cv[j];
+        }
+        npos += __popc(__ballot_sync(0xffffffffu, p));
     }
     acc = warp_sum_ll(acc);
-    pos_out = base + cnt;
+    pos_out = base + npos;
+    cnt_out = cnt ? ctile[tile] + warp_sum_ll(cacc) : pos_out;
     sum_out = ptile[tile] + acc;
 }
 
@@ -238,23 +257,32 @@ __global__ void __launch_bounds__(256) ll_search_kernel(LloydDevice *st, const f
     const int nb = st->tab.R - 1;  // boundaries 1 .. R-1
     const int wpb = blockDim.x >> 5;
     for (int r = 1 + blockIdx.x * wpb + warp_id(); r <= nb; r += gridDim.x * wpb) {
-        long long pos, sum;
-        warp_boundary_search(ks, samp, ptile, st->n_nz, st->n_tiles, st->mean, st->scale, st->tab.rstart[r], pos, sum);
+        long long pos, cn, sum;
+        warp_boundary_search(ks, st->cnt, samp, ptile, st->ctile, st->n_ent, st->n_tiles, st->mean, st->scale, st->tab.rstart[r],
+                             pos, cn, sum);
         if (lane_id() == 0) {
             st->rpos[r] = pos;
+            st->rcnt[r] = cn;
             st->rsum[r] = sum;
         }
     }
 }
 
+struct ZoneSmem {
+    long long zpre[2 * TB_KMAX + 2];
+    long long s_warp[32];
+    unsigned long long sW[TB_KMAX];
+    long long sS[TB_KMAX];
+    long long sMin[TB_KMAX];
+    long long sMax[TB_KMAX];
+};
+
 __global__ void __launch_bounds__(256) ll_zone_kernel(LloydDevice *st, const float *__restrict__ ks) {
     if (st->done) return;
-    __shared__ long long zpre[2 * TB_KMAX + 2];
-    __shared__ long long s_warp[32];
-    __shared__ unsigned int sW[TB_KMAX];
-    __shared__ long long sS[TB_KMAX];
-    __shared__ long long sMin[TB_KMAX];
-    __shared__ long long sMax[TB_KMAX];
+    extern __shared__ __align__(16) unsigned char zone_smem_raw[];
+    ZoneSmem &Z_ = *reinterpret_cast<ZoneSmem *>(zone_smem_raw);
+    long long *zpre = Z_.zpre, *s_warp = Z_.s_warp, *sS = Z_.sS, *sMin = Z_.sMin, *sMax = Z_.sMax;
+    unsigned long long *sW = Z_.sW;
     const RegionTable &T = st->tab;
     const int R = T.R, m = T.m;
     if (R <= 1) return;
@@ -293,11 +321,12 @@ __global__ void __launch_bounds__(256) ll_zone_kernel(LloydDevice *st, const flo
     const float mean = st->mean;
     const double scale = st->scale;
     const int lane = lane_id();
+    const unsigned int *__restrict__ ecnt = st->cnt;
     for (long long eb = e0; eb < e1; eb += blockDim.x) {  // e1 - e0 is a multiple of blockDim.x or ends at Z: uniform trips
         long long e = eb + threadIdx.x;
         bool valid = e < e1;
         int di = -1;
-        long long q = 0, p = 0;
+        long long q = 0, p = 0, c = 0;
         if (valid) {
             int lo = 0, hi = R;  // largest r with zpre[r] <= e: the non-empty zone that holds e
             while (hi - lo > 1) {
@@ -311,7 +340,8 @@ __global__ void __launch_bounds__(256) ll_zone_kernel(LloydDevice *st, const flo
             p = st->rpos[r] + (e - zpre[r]);
             float xc = fsub(ks[p], mean);
             di = zone_argmin(xc, T.dv, T.dcn, T.down, T.rJ2[r], T.rJ1[r]);
-            q = fixed_q(xc, scale);
+            c = ecnt ? (long long)ecnt[p] : 1ll;
+            q = fixed_q(xc, scale) * c;
         }
         unsigned active = __ballot_sync(0xffffffffu, valid);
         while (active) {
@@ -320,10 +350,11 @@ __global__ void __launch_bounds__(256) ll_zone_kernel(LloydDevice *st, const flo
             bool mine = valid && di == L;
             unsigned grp = __ballot_sync(0xffffffffu, mine);
             long long sq = warp_sum_ll(mine ? q : 0);
+            long long sc = ecnt ? warp_sum_ll(mine ? c : 0) : (long long)__popc(grp);
             long long pf = __shfl_sync(0xffffffffu, p, __ffs(grp) - 1);
             long long pl = __shfl_sync(0xffffffffu, p, 31 - __clz(grp));
             if (lane == leader) {
-                atomicAdd(&sW[L], (unsigned)__popc(grp));
+                atomicAdd(&sW[L], (unsigned long long)sc);
                 atomicAdd((unsigned long long *)&sS[L], (unsigned long long)sq);
                 atomicMin(&sMin[L], pf);
                 atomicMax(&sMax[L], pl);
@@ -334,7 +365,7 @@ __global__ void __launch_bounds__(256) ll_zone_kernel(LloydDevice *st, const flo
     __syncthreads();
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
         if (sW[i]) {
-            atomicAdd((unsigned long long *)&st->zW[i], (unsigned long long)sW[i]);
+            atomicAdd((unsigned long long *)&st->zW[i], sW[i]);
             atomicAdd((unsigned long long *)&st->zS[i], (unsigned long long)sS[i]);
             atomicMin(&st->zmin[i], sMin[i]);
             atomicMax(&st->zmax[i], sMax[i]);
@@ -470,7 +501,7 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
         const int di = T.rJ1[r];
         long long lo = st->rpos[r], hi = st->rpos[r + 1];
         if (hi > lo) {
-            U.Wd[di] += hi - lo;  // (J, J) occurs in at most one region: no conflicts
+            U.Wd[di] += st->rcnt[r + 1] - st->rcnt[r];  // (J, J) occurs in at most one region: no conflicts
             U.Sd[di] += st->rsum[r + 1] - st->rsum[r];
             U.first[di] = llmin2(U.first[di], lo);
             U.last[di] = llmax2(U.last[di], hi - 1);
@@ -582,6 +613,11 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
         // Thread di owns both cursors of distinct index di; the owner of the zero run's cluster also owns
         // the zero run (a third head).
         long long pl = -1, pr = -2;  // empty stream when pl > pr
+        // an entry stands for cnt identical samples: the cursors pop them one by one (reml / remr: samples left in
+        // the entry under the left / right cursor; when the cursors meet, the left one owns what is left)
+        unsigned long long reml = 0, remr = 0;
+        const unsigned int *__restrict__ ecnt = st->cnt;
+        auto cnt_at = [&](long long p) -> unsigned long long { return ecnt ? (unsigned long long)ecnt[p] : 1ull; };
         float cown = 0.f;
         FarKey kl{0, 0, 0}, kr{0, 0, 0};
         float xl = 0.f, xr = 0.f;
@@ -591,6 +627,8 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
             if (U.last[tid] >= U.first[tid] && U.last[tid] >= 0) {
                 pl = U.first[tid];
                 pr = U.last[tid];
+                reml = cnt_at(pl);
+                remr = cnt_at(pr);
             }
         }
         auto refresh = [&]() {
@@ -671,17 +709,29 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
                 if (who == 2) {
                     U.zero_left -= 1;
                 } else {
-                    // advance the cursor to the next member of this distinct index
+                    // take one sample of the entry; when it is used up, advance the cursor to the next member of this
+                    // distinct index
                     if (who == 0) {
-                        do {
-                            ++pl;
-                        } while (pl <= pr && label_at(st, ks, pl) != tid);
+                        if (reml > 1) {
+                            reml -= 1;
+                        } else {
+                            do {
+                                ++pl;
+                            } while (pl <= pr && label_at(st, ks, pl) != tid);
+                            if (pl <= pr) reml = pl == pr ? remr : cnt_at(pl);
+                            refresh();
+                        }
                     } else {
-                        do {
-                            --pr;
-                        } while (pr >= pl && label_at(st, ks, pr) != tid);
+                        if (remr > 1) {
+                            remr -= 1;
+                        } else {
+                            do {
+                                --pr;
+                            } while (pr >= pl && label_at(st, ks, pr) != tid);
+                            if (pr > pl) remr = cnt_at(pr);
+                            refresh();
+                        }
                     }
-                    refresh();
                 }
             }
             n_done = pop + 1;
@@ -851,7 +901,7 @@ __global__ void __launch_bounds__(TB_THREADS) ll_count_kernel(LloydDevice *st) {
     __syncthreads();
     for (int r = tid; r < R; r += TB_THREADS) {
         if (T.rJ1[r] != T.rJ2[r]) continue;
-        const long long c = st->rpos[r + 1] - st->rpos[r];
+        const long long c = st->rcnt[r + 1] - st->rcnt[r];
         if (c > 0) Wd[T.rJ1[r]] += c;  // (J, J) occurs in at most one region
     }
     __syncthreads();
@@ -873,14 +923,18 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
     static bool configured = false;
     if (!configured) {
         NNC_CUDA(cudaFuncSetAttribute(ll_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateSmem)));
+        NNC_CUDA(cudaFuncSetAttribute(ll_zone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZoneSmem)));
         configured = true;
     }
     LloydDevice *st = arena_alloc_t<LloydDevice>(ctx, 1);
     h.d_state = st;
-    const long long n_tiles = (h.n_nz + LL_TS - 1) / LL_TS;
+    const long long n_ent = h.d_cnt ? h.n_ent : h.n_nz;  // entries of the sorted array
+    const long long n_tiles = (n_ent + LL_TS - 1) / LL_TS;
     h.n_tiles = n_tiles;
     long long *tsum = arena_alloc_t<long long>(ctx, n_tiles + 1);
     long long *ptile = arena_alloc_t<long long>(ctx, n_tiles + 2);
+    long long *tcnt = h.d_cnt ? arena_alloc_t<long long>(ctx, n_tiles + 1) : nullptr;
+    long long *ctile = h.d_cnt ? arena_alloc_t<long long>(ctx, n_tiles + 2) : nullptr;
     float *samp = arena_alloc_t<float>(ctx, n_tiles + 1);
     float *d_init = arena_alloc_t<float>(ctx, k);
     h.d_ptile = ptile;
@@ -901,6 +955,9 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
     hs.fixed_exp = E;
     hs.n = h.n;
     hs.n_nz = h.n_nz;
+    hs.n_ent = n_ent;
+    hs.cnt = h.d_cnt;
+    hs.ctile = ctile;
     hs.n0 = h.n0;
     hs.n_tiles = n_tiles;
     hs.mean = mean;
@@ -917,9 +974,10 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
     NNC_CUDA(cudaMemcpyAsync(d_init, h_init, sizeof(float) * k, cudaMemcpyHostToDevice, ctx->stream));
     if (n_tiles > 0) {
         int grid = (int)std::min<long long>((long long)ctx->sm_count * 8, (n_tiles + 7) / 8);
-        NNC_LAUNCH(ctx, ll_tilesum_kernel, grid, 256, 0, h.d_sorted, h.n_nz, mean, scale, tsum, samp, st);
+        NNC_LAUNCH(ctx, ll_tilesum_kernel, grid, 256, 0, h.d_sorted, h.d_cnt, n_ent, mean, scale, tsum, tcnt, samp, st);
     }
     exclusive_scan_i64(ctx, tsum, n_tiles, ptile);
+    if (ctile) exclusive_scan_i64(ctx, tcnt, n_tiles, ctile);
     NNC_LAUNCH(ctx, ll_total_kernel, 1, 1, 0, ptile, n_tiles, st);
     NNC_LAUNCH(ctx, ll_moments_kernel, 1, 1, 0, st);
     comm_allreduce(ctx, reinterpret_cast<int64_t *>(&st->s1), 3, 0);  // s1, s2_lo, s2_hi are consecutive
@@ -937,7 +995,7 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         for (int b = 0; b < batch && launched < max_iter; ++b, ++launched) {
             NNC_LAUNCH(ctx, ll_table_kernel, 1, TB_THREADS, 0, st);
             NNC_LAUNCH(ctx, ll_search_kernel, search_grid, 256, 0, st, h.d_sorted, samp, ptile);
-            NNC_LAUNCH(ctx, ll_zone_kernel, zone_grid, 256, 0, st, h.d_sorted);
+            NNC_LAUNCH(ctx, ll_zone_kernel, zone_grid, 256, sizeof(ZoneSmem), st, h.d_sorted);
             PeerComm pc;
             memset(&pc, 0, sizeof(pc));
             if (world == 1) {
@@ -975,7 +1033,7 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         NNC_LAUNCH(ctx, ll_final_begin_kernel, 1, TB_KMAX, 0, st);
         NNC_LAUNCH(ctx, ll_table_kernel, 1, TB_THREADS, 0, st);
         NNC_LAUNCH(ctx, ll_search_kernel, search_grid, 256, 0, st, h.d_sorted, samp, ptile);
-        NNC_LAUNCH(ctx, ll_zone_kernel, zone_grid, 256, 0, st, h.d_sorted);
+        NNC_LAUNCH(ctx, ll_zone_kernel, zone_grid, 256, sizeof(ZoneSmem), st, h.d_sorted);
         NNC_LAUNCH(ctx, ll_count_kernel, 1, TB_THREADS, 0, st);
         comm_allreduce(ctx, reinterpret_cast<int64_t *>(st->hist), k, 0);
         static_assert(sizeof(long long) == sizeof(int64_t), "histogram element size");

@@ -272,6 +272,67 @@ def test_kmeans_edge_cases(U):
     _check_kmeans(U, w, 4, "linear")
 
 
+# ---------------------------------------------------------------------------------------------------------
+# key-histogram path (csrc/khist.cu): the sorted survivors as (value, multiplicity) runs.  Chosen by the library
+# for large narrow-range layers; forced here (NNC_SORT_PATH=hist) on tensors the oracle finishes in seconds.
+# ---------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def hist_path(monkeypatch):
+    monkeypatch.setenv("NNC_SORT_PATH", "hist")
+
+
+@pytest.mark.parametrize("bits,mode", [(5, "forgy"), (8, "linear"), (3, "density"), (8, "density"), (1, "linear"), (4, "linear")])
+def test_kmeans_hist_path_pruned_gaussian(U, hist_path, bits, mode):
+    w = D.gaussian(300 * 1000, seed=77).reshape(300, 1000)
+    O.prune_weigth(w, 1)
+    _check_kmeans(U, w, bits, mode)
+
+
+def test_kmeans_hist_path_multiplicities(U, hist_path):
+    rng = np.random.RandomState(5)
+    # a coarse grid: every distinct value occurs hundreds of times (entries with large counts, wide key range)
+    w = (np.round(rng.randn(400 * 1000) * 40) / 1024).astype(np.float32)
+    _check_kmeans(U, w, 4, "linear")
+    _check_kmeans(U, w, 5, "forgy", seed=2)
+    # fewer distinct values than clusters: relocation pops samples out of multi-count entries
+    vals = np.sort(((0.5 + 1.5 * rng.rand(20)) * rng.choice([-1.0, 1.0], size=20)).astype(np.float32))
+    w = vals[rng.randint(0, 20, size=100 * 1000)]
+    _check_kmeans(U, w, 5, "linear")
+    _check_kmeans(U, w, 6, "forgy", seed=1)
+    # narrow positive range: the whole key fits the shared-memory histogram (no partition pass)
+    w = (1.0 + rng.rand(500 * 1000) * 2.0 ** -11).astype(np.float32)
+    _check_kmeans(U, w, 4, "linear")
+    # ... two narrow lobes of opposite sign, zeros in between
+    w = ((1.0 + rng.rand(300 * 1000) * 2.0 ** -12) * rng.choice([-1.0, 1.0, 0.0], size=300 * 1000)).astype(np.float32)
+    _check_kmeans(U, w, 3, "linear")
+    _check_kmeans(U, w, 8, "linear")
+
+
+def test_kmeans_hist_path_4m(U, hist_path):
+    # several work items per bucket region, partition pass over many tiles
+    w = D.gaussian(1 << 22, seed=11)
+    O.prune_weigth(w, 1)
+    _check_kmeans(U, w, 8, "linear", check_ref32=False)
+    _check_kmeans(U, w, 4, "linear", check_ref32=False)
+
+
+def test_kmeans_hist_path_equals_radix_path(U, monkeypatch):
+    # the two representations of the sorted survivors give the same fit, bit for bit, on a tensor whose largest
+    # bucket spans several histogram work items (a near-constant lobe)
+    rng = np.random.RandomState(9)
+    g = D.gaussian(1 << 21, seed=3)
+    O.prune_weigth(g, 1)  # survivors |x| > 0.02: with the lobe at 0.5 the key range stays within 27 bits
+    w = np.concatenate([g, (0.5 + rng.rand(3 << 20) * 2.0 ** -9).astype(np.float32)])
+    rng.shuffle(w)
+    out = {}
+    for path in ("radix", "hist"):
+        monkeypatch.setenv("NNC_SORT_PATH", path)
+        ris, km = U.get_quantized_weight(w, 6, "linear")
+        out[path] = (ris.tobytes(), km.cluster_centers_.tobytes(), km.n_iter_, km.packed_codes.tobytes(), km.code_histogram.tobytes(),
+                     km.inertia_, km.n_relocations)
+    assert out["radix"] == out["hist"]
+
+
 def test_kmeans_errors(U):
     w = D.gaussian(1000, seed=2)
     with pytest.raises(Exception, match="error mode not found"):
