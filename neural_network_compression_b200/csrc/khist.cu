@@ -207,7 +207,29 @@ __global__ void __launch_bounds__(KH_THREADS, 2) kh_scatter_kernel(const uint32_
         __syncthreads();  // stage consumed, counts complete
         if (tile + 1 < t1) fetch(tile + 1);
         // exclusive scan of the digit counts (thread t owns bins [t * per, t * per + per))
-        {
+        if (per == 4) {  // 2048 buckets: 128-bit shared-memory accesses (consecutive 16-byte pieces: conflict free)
+            const int b0 = threadIdx.x * 4;
+            uint4 c = *reinterpret_cast<const uint4 *>(&hist[b0]);
+            const uint32_t loc = c.x + c.y + c.z + c.w;
+            uint32_t incl = loc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_warp[wid] = incl;
+            ulonglong2 r01 = *reinterpret_cast<const ulonglong2 *>(&run[b0]);
+            ulonglong2 r23 = *reinterpret_cast<const ulonglong2 *>(&run[b0 + 2]);
+            __syncthreads();
+            uint32_t add = 0;
+            for (int w2 = 0; w2 < wid; ++w2) add += s_warp[w2];
+            const uint32_t s0 = incl - loc + add, s1 = s0 + c.x, s2 = s1 + c.y, s3 = s2 + c.z;
+            *reinterpret_cast<uint4 *>(&hist[b0]) = make_uint4(s0, s1, s2, s3);
+            *reinterpret_cast<ulonglong2 *>(&gbase[b0]) = make_ulonglong2(r01.x - s0, r01.y - s1);
+            *reinterpret_cast<ulonglong2 *>(&gbase[b0 + 2]) = make_ulonglong2(r23.x - s2, r23.y - s3);
+            *reinterpret_cast<ulonglong2 *>(&run[b0]) = make_ulonglong2(r01.x + c.x, r01.y + c.y);
+            *reinterpret_cast<ulonglong2 *>(&run[b0 + 2]) = make_ulonglong2(r23.x + c.z, r23.y + c.w);
+        } else {
             const int b0 = threadIdx.x * per;
             uint32_t loc = 0;
             for (int j = 0; j < per; ++j)
@@ -258,8 +280,10 @@ __global__ void __launch_bounds__(KH_THREADS, 2) kh_scatter_kernel(const uint32_
 template <bool IN_FLOAT>
 __global__ void __launch_bounds__(1024) kh_hist_kernel(const uint32_t *__restrict__ in, int nb, int low_bins, KhKeyMap km,
                                                        const unsigned long long *__restrict__ bucket_off,
-                                                       const uint32_t *__restrict__ item_off, uint32_t *__restrict__ H) {
+                                                       const uint32_t *__restrict__ item_off, uint32_t *__restrict__ H,
+                                                       uint32_t *__restrict__ tnz) {
     extern __shared__ uint32_t kh_bins[];
+    __shared__ uint32_t s_tnz[KH_BINS / KH_HT];
     const uint32_t item = blockIdx.x;
     if (item >= item_off[nb]) return;
     int lo = 0, hi = nb;  // largest bucket b with item_off[b] <= item (empty buckets own no items)
@@ -300,10 +324,19 @@ __global__ void __launch_bounds__(1024) kh_hist_kernel(const uint32_t *__restric
     __syncthreads();
     uint32_t *Hb = H + ((size_t)b << KH_LOW);
     if (items_b == 1) {
-        for (int i = threadIdx.x; i < low_bins; i += 1024) {
-            const uint32_t c = kh_bins[i];
+        // the bucket is complete: its bins go out together with the non-empty count of every 1024-bin compaction tile
+        const int tiles_b = max(low_bins, KH_HT) / KH_HT;
+        if (threadIdx.x < KH_BINS / KH_HT) s_tnz[threadIdx.x] = 0;
+        __syncthreads();
+        for (int j = 0; j < tiles_b; ++j) {
+            const int i = j * KH_HT + threadIdx.x;
+            const uint32_t c = i < low_bins ? kh_bins[i] : 0u;
             if (c) Hb[i] = c;
+            const int nzw = __popc(__ballot_sync(0xffffffffu, c != 0));
+            if (lane_id() == 0 && nzw) atomicAdd(&s_tnz[j], (uint32_t)nzw);
         }
+        __syncthreads();
+        if (threadIdx.x < tiles_b) tnz[(size_t)b * (KH_BINS / KH_HT) + threadIdx.x] = s_tnz[threadIdx.x];
     } else {  // a bucket larger than one work item: merge the partial histograms
         for (int i = threadIdx.x; i < low_bins; i += 1024) {
             const uint32_t c = kh_bins[i];
@@ -313,33 +346,62 @@ __global__ void __launch_bounds__(1024) kh_hist_kernel(const uint32_t *__restric
 }
 
 // ---- compact: non-empty bins -> (value, count) entries ---------------------------------------------------------
-__global__ void __launch_bounds__(KH_HT) kh_tilecount_kernel(const uint32_t *__restrict__ H, uint32_t *__restrict__ tnz) {
+// buckets merged from several work items (atomics): their tile counts are taken once the bucket is complete
+__global__ void __launch_bounds__(KH_HT) kh_tilecount_kernel(const uint32_t *__restrict__ H, const uint32_t *__restrict__ item_off,
+                                                             int tiles_per_bucket, uint32_t *__restrict__ tnz) {
     __shared__ int s_warp[KH_HT / 32];
-    const uint32_t c = H[(size_t)blockIdx.x * KH_HT + threadIdx.x];
-    const int nzw = __popc(__ballot_sync(0xffffffffu, c != 0));
-    if (lane_id() == 0) s_warp[warp_id()] = nzw;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int w = 0; w < KH_HT / 32; ++w) t += s_warp[w];
-        tnz[blockIdx.x] = (uint32_t)t;
+    const int b = blockIdx.x;
+    if (item_off[b + 1] - item_off[b] <= 1) return;  // empty (counts stay 0) or counted by the histogram kernel
+    for (int j = 0; j < tiles_per_bucket; ++j) {
+        const size_t tile = (size_t)b * tiles_per_bucket + j;
+        const uint32_t c = H[tile * KH_HT + threadIdx.x];
+        const int nzw = __popc(__ballot_sync(0xffffffffu, c != 0));
+        if (lane_id() == 0) s_warp[warp_id()] = nzw;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < KH_HT / 32; ++w) t += s_warp[w];
+            tnz[tile] = (uint32_t)t;
+        }
+        __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(KH_HT) kh_compact_kernel(const uint32_t *__restrict__ H, const unsigned long long *__restrict__ toff,
-                                                           KhKeyMap km, float *__restrict__ val, uint32_t *__restrict__ cnt) {
-    __shared__ int s_warp[KH_HT / 32];
-    const uint32_t key = blockIdx.x * KH_HT + threadIdx.x;
-    const uint32_t c = H[key];
-    const unsigned bal = __ballot_sync(0xffffffffu, c != 0);
-    if (lane_id() == 0) s_warp[warp_id()] = __popc(bal);
+// one CTA per 1024-bin tile, four bins per thread
+__global__ void __launch_bounds__(KH_HT / 4) kh_compact_kernel(const uint32_t *__restrict__ H, const uint32_t *__restrict__ tnz,
+                                                               const unsigned long long *__restrict__ toff, KhKeyMap km,
+                                                               float *__restrict__ val, uint32_t *__restrict__ cnt) {
+    __shared__ int s_warp[KH_HT / 128];
+    if (tnz[blockIdx.x] == 0) return;
+    const uint32_t key0 = blockIdx.x * KH_HT + threadIdx.x * 4;
+    const uint4 c = *reinterpret_cast<const uint4 *>(H + key0);
+    const int mine = (c.x != 0) + (c.y != 0) + (c.z != 0) + (c.w != 0);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane_id() >= o) incl += t;
+    }
+    if (lane_id() == 31) s_warp[warp_id()] = incl;
     __syncthreads();
-    if (c) {
-        int before = __popc(bal & ((1u << lane_id()) - 1u));
-        for (int w = 0; w < warp_id(); ++w) before += s_warp[w];
-        const unsigned long long at = toff[blockIdx.x] + (unsigned long long)before;
-        val[at] = __uint_as_float(kh_unkey(key, km));
-        cnt[at] = c;
+    int before = incl - mine;
+    for (int w = 0; w < warp_id(); ++w) before += s_warp[w];
+    unsigned long long at = toff[blockIdx.x] + (unsigned long long)before;
+    if (c.x) {
+        val[at] = __uint_as_float(kh_unkey(key0, km));
+        cnt[at++] = c.x;
+    }
+    if (c.y) {
+        val[at] = __uint_as_float(kh_unkey(key0 + 1, km));
+        cnt[at++] = c.y;
+    }
+    if (c.z) {
+        val[at] = __uint_as_float(kh_unkey(key0 + 2, km));
+        cnt[at++] = c.z;
+    }
+    if (c.w) {
+        val[at] = __uint_as_float(kh_unkey(key0 + 3, km));
+        cnt[at++] = c.w;
     }
 }
 
@@ -385,6 +447,10 @@ SortedRuns hist_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n, uint32
     const uint32_t *a = reinterpret_cast<const uint32_t *>(d_a);
     uint32_t *b = reinterpret_cast<uint32_t *>(d_b);
     const int max_items = (int)std::min<int64_t>(n / KH_CHUNK + nb, (int64_t)1 << 30);
+    const long long n_htiles = (long long)(std::max<size_t>(n_bins, KH_HT) / KH_HT);
+    const int tiles_per_bucket = (int)(n_htiles / nb);  // 32 with a partition pass, max(low_bins, 1024) / 1024 without
+    uint32_t *tnz = arena_alloc_t<uint32_t>(ctx, (size_t)n_htiles + 1);
+    NNC_CUDA(cudaMemsetAsync(tnz, 0, sizeof(uint32_t) * ((size_t)n_htiles + 1), ctx->stream));
     if (hb > 0) {
         const int64_t n_tiles = (n + KH_TILE - 1) / KH_TILE;
         const int64_t want_chunks = std::min<int64_t>(1024, (int64_t)ctx->sm_count * 2);
@@ -399,22 +465,20 @@ SortedRuns hist_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n, uint32
         NNC_LAUNCH(ctx, kh_base_kernel, 1, 1024, 0, tot, nb, bucket_off, item_off);
         NNC_LAUNCH(ctx, kh_scatter_kernel, chunks, KH_THREADS, KH_TILE * 8 + nb * 20, a, b, n, tiles_per_chunk, nb, km, bucket_off,
                    crel_lo, crel_hi);
-        NNC_LAUNCH(ctx, kh_hist_kernel<false>, max_items, 1024, low_bins * 4, b, nb, low_bins, km, bucket_off, item_off, H);
+        NNC_LAUNCH(ctx, kh_hist_kernel<false>, max_items, 1024, low_bins * 4, b, nb, low_bins, km, bucket_off, item_off, H, tnz);
     } else {
         const unsigned long long h_off[2] = {0ull, (unsigned long long)n};
         const uint32_t h_items[2] = {0u, (uint32_t)((n + KH_CHUNK - 1) / KH_CHUNK)};
         NNC_CUDA(cudaMemcpyAsync(bucket_off, h_off, sizeof(h_off), cudaMemcpyHostToDevice, ctx->stream));
         NNC_CUDA(cudaMemcpyAsync(item_off, h_items, sizeof(h_items), cudaMemcpyHostToDevice, ctx->stream));
         NNC_CUDA(cudaStreamSynchronize(ctx->stream));  // the two host arrays are on this frame
-        NNC_LAUNCH(ctx, kh_hist_kernel<true>, (int)h_items[1], 1024, low_bins * 4, a, 1, low_bins, km, bucket_off, item_off, H);
+        NNC_LAUNCH(ctx, kh_hist_kernel<true>, (int)h_items[1], 1024, low_bins * 4, a, 1, low_bins, km, bucket_off, item_off, H, tnz);
     }
     // non-empty bins -> entries; the survivor buffers are dead from here on and take the entries
-    const long long n_htiles = (long long)(std::max<size_t>(n_bins, KH_HT) / KH_HT);
-    uint32_t *tnz = arena_alloc_t<uint32_t>(ctx, (size_t)n_htiles + 1);
     unsigned long long *toff = arena_alloc_t<unsigned long long>(ctx, (size_t)n_htiles + 2);
-    NNC_LAUNCH(ctx, kh_tilecount_kernel, (int)n_htiles, KH_HT, 0, H, tnz);
+    NNC_LAUNCH(ctx, kh_tilecount_kernel, nb, KH_HT, 0, H, item_off, tiles_per_bucket, tnz);
     exclusive_scan_u32_u64(ctx, tnz, n_htiles, toff);
-    NNC_LAUNCH(ctx, kh_compact_kernel, (int)n_htiles, KH_HT, 0, H, toff, km, d_a, b);
+    NNC_LAUNCH(ctx, kh_compact_kernel, (int)n_htiles, KH_HT / 4, 0, H, tnz, toff, km, d_a, b);
     unsigned long long n_ent = 0;
     NNC_CUDA(cudaMemcpyAsync(&n_ent, toff + n_htiles, sizeof(n_ent), cudaMemcpyDeviceToHost, ctx->stream));
     NNC_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -76,6 +76,8 @@ struct LloydDevice : LloydHeader {
     long long xbuf[2 * TB_KMAX];  // staging of the in-kernel peer exchange
     // control
     int iter, done, strict, n_reloc, n_iter, pad2;
+    unsigned int gbar;  // arrival counter of the grid barrier (ll_loop_kernel)
+    int gbail;          // a CTA gave up waiting at the grid barrier
     // per-iteration log (diagnostics): zone elements, zone groups, distinct centroids, empty clusters
     long long logZ[LL_LOG];
     int logG[LL_LOG], logM[LL_LOG], logE[LL_LOG];
@@ -169,9 +171,7 @@ __global__ void ll_init_kernel(LloydDevice *st, const float *init) {
 // ---------------------------------------------------------------------------------------------
 // per-iteration kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TB_THREADS) ll_table_kernel(LloydDevice *st) {
-    __shared__ TableScratch S;
-    if (st->done) return;
+__device__ void table_phase(LloydDevice *st, TableScratch &S) {
     build_region_table(st->c, st->k, st->xabs_max, &st->tab, S);
     const int tid = threadIdx.x;
     if (tid < st->k) {
@@ -189,6 +189,11 @@ __global__ void __launch_bounds__(TB_THREADS) ll_table_kernel(LloydDevice *st) {
         st->rcnt[R] = st->n_nz;
         st->rsum[R] = st->total_q;
     }
+}
+__global__ void __launch_bounds__(TB_THREADS) ll_table_kernel(LloydDevice *st) {
+    __shared__ TableScratch S;
+    if (st->done) return;
+    table_phase(st, S);
 }
 
 // entries / elements of the sorted survivors with fl(x - mean) < t, and the sum of q over them; one warp per boundary
@@ -226,23 +231,27 @@ __device__ __forceinline__ void warp_boundary_search(const float *__restrict__ k
     const long long tile = lo - 1;
     const long long base = tile * LL_TS;
     long long npos = 0, acc = 0, cacc = 0;
-    float xv[LL_TS / 32];
-    unsigned int cv[LL_TS / 32];
+    constexpr int HALF = LL_TS / 64;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {  // two rounds of 16 loads per lane in flight (64 registers per thread in the loop kernel)
+        float xv[HALF];
+        unsigned int cv[HALF];
 #pragma unroll
-    for (int j = 0; j < LL_TS / 32; ++j) {  // all 32 loads in flight before the first use
-        const long long i = base + j * 32 + lane;
-        xv[j] = i < n_ent ? ks[i] : INFINITY;
-        cv[j] = (cnt && i < n_ent) ? cnt[i] : 1u;
-    }
-#pragma unroll
-    for (int j = 0; j < LL_TS / 32; ++j) {
-        const float xc = fsub(xv[j], mean);
-        const bool p = xc < t;  // padding is +inf: never counted
-        if (p) {
-            acc += fixed_q(xc, scale) * (long long)cv[j];
-            cacc += cv[j];
+        for (int j = 0; j < HALF; ++j) {
+            const long long i = base + (h * HALF + j) * 32 + lane;
+            xv[j] = i < n_ent ? ks[i] : INFINITY;
+            cv[j] = (cnt && i < n_ent) ? cnt[i] : 1u;
         }
-        npos += __popc(__ballot_sync(0xffffffffu, p));
+#pragma unroll
+        for (int j = 0; j < HALF; ++j) {
+            const float xc = fsub(xv[j], mean);
+            const bool p = xc < t;  // padding is +inf: never counted
+            if (p) {
+                acc += fixed_q(xc, scale) * (long long)cv[j];
+                cacc += cv[j];
+            }
+            npos += __popc(__ballot_sync(0xffffffffu, p));
+        }
     }
     acc = warp_sum_ll(acc);
     pos_out = base + npos;
@@ -250,13 +259,12 @@ __device__ __forceinline__ void warp_boundary_search(const float *__restrict__ k
     sum_out = ptile[tile] + acc;
 }
 
-__global__ void __launch_bounds__(256) ll_search_kernel(LloydDevice *st, const float *__restrict__ ks,
-                                                        const float *__restrict__ samp,
-                                                        const long long *__restrict__ ptile) {
-    if (st->done) return;
+__device__ __forceinline__ void search_phase(LloydDevice *st, const float *__restrict__ ks, const float *__restrict__ samp,
+                                             const long long *__restrict__ ptile) {
     const int nb = st->tab.R - 1;  // boundaries 1 .. R-1
     const int wpb = blockDim.x >> 5;
-    for (int r = 1 + blockIdx.x * wpb + warp_id(); r <= nb; r += gridDim.x * wpb) {
+    // warps of different CTAs take consecutive boundaries: the work spreads over all SMs
+    for (int r = 1 + warp_id() * gridDim.x + blockIdx.x; r <= nb; r += gridDim.x * wpb) {
         long long pos, cn, sum;
         warp_boundary_search(ks, st->cnt, samp, ptile, st->ctile, st->n_ent, st->n_tiles, st->mean, st->scale, st->tab.rstart[r],
                              pos, cn, sum);
@@ -266,6 +274,12 @@ __global__ void __launch_bounds__(256) ll_search_kernel(LloydDevice *st, const f
             st->rsum[r] = sum;
         }
     }
+}
+__global__ void __launch_bounds__(256) ll_search_kernel(LloydDevice *st, const float *__restrict__ ks,
+                                                        const float *__restrict__ samp,
+                                                        const long long *__restrict__ ptile) {
+    if (st->done) return;
+    search_phase(st, ks, samp, ptile);
 }
 
 struct ZoneSmem {
@@ -277,10 +291,7 @@ struct ZoneSmem {
     long long sMax[TB_KMAX];
 };
 
-__global__ void __launch_bounds__(256) ll_zone_kernel(LloydDevice *st, const float *__restrict__ ks) {
-    if (st->done) return;
-    extern __shared__ __align__(16) unsigned char zone_smem_raw[];
-    ZoneSmem &Z_ = *reinterpret_cast<ZoneSmem *>(zone_smem_raw);
+__device__ void zone_phase(LloydDevice *st, const float *__restrict__ ks, ZoneSmem &Z_) {
     long long *zpre = Z_.zpre, *s_warp = Z_.s_warp, *sS = Z_.sS, *sMin = Z_.sMin, *sMax = Z_.sMax;
     unsigned long long *sW = Z_.sW;
     const RegionTable &T = st->tab;
@@ -372,6 +383,11 @@ __global__ void __launch_bounds__(256) ll_zone_kernel(LloydDevice *st, const flo
         }
     }
 }
+__global__ void __launch_bounds__(256) ll_zone_kernel(LloydDevice *st, const float *__restrict__ ks) {
+    if (st->done) return;
+    extern __shared__ __align__(16) unsigned char zone_smem_raw[];
+    zone_phase(st, ks, *reinterpret_cast<ZoneSmem *>(zone_smem_raw));
+}
 
 // ---- update ------------------------------------------------------------------------------------
 // NumPy pairwise sum of a small float32 array (numpy/_core/src/umath/loops_utils.h.src), single thread.
@@ -416,13 +432,13 @@ __device__ __forceinline__ FarKey far_key(float xc, float c) {
 }
 
 // label (distinct index) of the sorted survivor at position p, from the region table + searched positions
-__device__ int label_at(const LloydDevice *st, const float *ks, long long p) {
+__device__ int label_at(const LloydDevice *st, const long long *rpos, const float *ks, long long p) {
     const RegionTable &T = st->tab;
     const int R = T.R;
     int lo = 0, hi = R;  // largest r with rpos[r] <= p
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
-        if (st->rpos[mid] <= p)
+        if (rpos[mid] <= p)
             lo = mid;
         else
             hi = mid;
@@ -445,6 +461,7 @@ struct UpdateSmem {
     int rk_who[32];
     int n_empty, zdi, same, winner, stop_reloc;  // stop_reloc: scratch of the convergence step
     long long zero_left;
+    long long rpos[2 * TB_KMAX + 2];  // copy of the region positions for the relocation cursors (label_at)
 };
 
 // Phases (run in one launch on a single GPU, as three launches with an all-reduce in between otherwise):
@@ -453,11 +470,8 @@ struct UpdateSmem {
 //   2  merge the candidates, relocate, average, centre shift, convergence
 // With a peer mailbox (pc.enabled, multi-GPU) the three phases run in ONE launch and the two exchanges happen inside
 // the kernel over NVLink peer memory (peer.cuh).
-__global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, const float *__restrict__ ks, int phase_lo,
-                                                               int phase_hi, PeerComm pc) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    UpdateSmem &U = *reinterpret_cast<UpdateSmem *>(smem_raw);
-    if (st->done) return;
+__device__ void update_phase(LloydDevice *st, const float *__restrict__ ks, int phase_lo, int phase_hi, const PeerComm &pc,
+                             UpdateSmem &U) {
     const RegionTable &T = st->tab;
     const int tid = threadIdx.x, k = st->k, m = T.m, R = T.R;
     const float mean = st->mean;
@@ -644,6 +658,8 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
                 }
             }
         };
+        for (int r = tid; r <= R; r += TB_THREADS) U.rpos[r] = st->rpos[r];
+        __syncthreads();
         refresh();
         if (tid == 0) U.zero_left = st->n0;
         __syncthreads();
@@ -717,7 +733,7 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
                         } else {
                             do {
                                 ++pl;
-                            } while (pl <= pr && label_at(st, ks, pl) != tid);
+                            } while (pl <= pr && label_at(st, U.rpos, ks, pl) != tid);
                             if (pl <= pr) reml = pl == pr ? remr : cnt_at(pl);
                             refresh();
                         }
@@ -727,7 +743,7 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
                         } else {
                             do {
                                 --pr;
-                            } while (pr >= pl && label_at(st, ks, pr) != tid);
+                            } while (pr >= pl && label_at(st, U.rpos, ks, pr) != tid);
                             if (pr > pl) remr = cnt_at(pr);
                             refresh();
                         }
@@ -877,12 +893,18 @@ __global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, 
         }
     }
 }
+__global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, const float *__restrict__ ks, int phase_lo,
+                                                               int phase_hi, PeerComm pc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (st->done) return;
+    update_phase(st, ks, phase_lo, phase_hi, pc, *reinterpret_cast<UpdateSmem *>(smem_raw));
+}
 
 // ---- final labelling histogram ---------------------------------------------------------------------
 // After the loop has stopped, the labels the emission pass will produce are those of the E-step against c_emit.
 // Their per-cluster counts follow from one more table / search / zone round on the sorted survivors -- far
 // cheaper than histogramming n labels in the streaming emission kernel.
-__global__ void __launch_bounds__(TB_KMAX) ll_final_begin_kernel(LloydDevice *st) {
+__device__ void final_begin_phase(LloydDevice *st, int clear_done) {
     const int tid = threadIdx.x;
     if (tid < st->k) {
         st->c_save[tid] = st->c[tid];
@@ -890,11 +912,11 @@ __global__ void __launch_bounds__(TB_KMAX) ll_final_begin_kernel(LloydDevice *st
         st->hist[tid] = 0;
     }
     __syncthreads();
-    if (tid == 0) st->done = 0;
+    if (tid == 0 && clear_done) st->done = 0;  // the per-phase kernels skip their work while `done` is set
 }
+__global__ void __launch_bounds__(TB_KMAX) ll_final_begin_kernel(LloydDevice *st) { final_begin_phase(st, 1); }
 
-__global__ void __launch_bounds__(TB_THREADS) ll_count_kernel(LloydDevice *st) {
-    __shared__ long long Wd[TB_KMAX];
+__device__ void count_phase(LloydDevice *st, long long *Wd /*[TB_KMAX], shared*/) {
     const RegionTable &T = st->tab;
     const int tid = threadIdx.x, k = st->k, m = T.m, R = T.R;
     if (tid < m) Wd[tid] = st->zW[tid];
@@ -911,6 +933,90 @@ __global__ void __launch_bounds__(TB_THREADS) ll_count_kernel(LloydDevice *st) {
     if (tid < k) st->c[tid] = st->c_save[tid];
     __syncthreads();
     if (tid == 0) st->done = 1;
+}
+__global__ void __launch_bounds__(TB_THREADS) ll_count_kernel(LloydDevice *st) {
+    __shared__ long long Wd[TB_KMAX];
+    count_phase(st, Wd);
+}
+
+// ---- the whole loop in ONE launch -------------------------------------------------------------------------------
+// Launched cooperatively with one CTA per SM (all resident).  Per iteration: CTA 0 builds the region table; all CTAs
+// search the region boundaries; all CTAs evaluate the zones; CTA 0 updates the centroids (with the in-kernel peer
+// exchange on several GPUs) and, unless the loop has stopped, builds the next table right away -- three grid barriers
+// per iteration, no launch boundary, no host round trip until the loop has converged.  The code histogram of the final
+// labelling (one more table / search / zone round) runs in the same launch.
+//
+// Grid barrier: every CTA's thread 0 publishes its arrival with a release-ordered atomic and spins with acquire loads
+// until all CTAs of the current epoch have arrived; the surrounding __syncthreads extend the ordering to the whole
+// CTA (the acquire invalidates the SM's L1, so the plain loads of the next phase see the other CTAs' stores).
+// A CTA that waits for more than a few seconds gives up and raises *bail (checked by the host): the kernel then runs
+// through without waiting instead of hanging the device.
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &epoch, volatile int *bail) {
+    __syncthreads();
+    epoch += 1;
+    if (threadIdx.x == 0 && !*bail) {
+        const unsigned int target = epoch * gridDim.x;
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        unsigned int v;
+        long long spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if (++spins > (1ll << 23)) {
+                *bail = 1;
+                break;
+            }
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+union LoopSmem {
+    TableScratch tb;
+    ZoneSmem zn;
+    UpdateSmem up;
+    long long wd[TB_KMAX];
+};
+
+__global__ void __launch_bounds__(TB_THREADS, 1) ll_loop_kernel(LloydDevice *st, const float *__restrict__ ks,
+                                                               const float *__restrict__ samp,
+                                                               const long long *__restrict__ ptile, int max_iter, int want_hist,
+                                                               PeerComm pc) {
+    extern __shared__ __align__(16) unsigned char loop_smem_raw[];
+    LoopSmem &S = *reinterpret_cast<LoopSmem *>(loop_smem_raw);
+    unsigned int epoch = 0;
+    unsigned int *bar = &st->gbar;
+    volatile int *bail = &st->gbail;
+    const volatile int *done = &st->done;
+    if (blockIdx.x == 0) table_phase(st, S.tb);
+    grid_barrier(bar, epoch, bail);
+    int stopped = 0;
+    for (int it = 0; it < max_iter && !stopped; ++it) {
+        search_phase(st, ks, samp, ptile);
+        grid_barrier(bar, epoch, bail);
+        zone_phase(st, ks, S.zn);
+        grid_barrier(bar, epoch, bail);
+        if (blockIdx.x == 0) {
+            update_phase(st, ks, 0, 2, pc, S.up);
+            __syncthreads();
+            if (!*done) table_phase(st, S.tb);
+        }
+        grid_barrier(bar, epoch, bail);
+        stopped = *done || *bail;  // `done` is only written by the update phase: stable until every CTA has read it
+    }
+    if (!want_hist || !stopped || *bail) return;
+    // code histogram of the final labelling (`done` stays set: nobody reads it from here on)
+    if (blockIdx.x == 0) {
+        final_begin_phase(st, 0);
+        __syncthreads();
+        table_phase(st, S.tb);
+    }
+    grid_barrier(bar, epoch, bail);
+    search_phase(st, ks, samp, ptile);
+    grid_barrier(bar, epoch, bail);
+    zone_phase(st, ks, S.zn);
+    grid_barrier(bar, epoch, bail);
+    if (blockIdx.x == 0) count_phase(st, S.wd);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -987,37 +1093,67 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
     struct Ctl {
         int iter, done, strict, n_reloc, n_iter, pad;
     } ctl;
-    const int batch = 8;
     const int search_grid = std::max(1, std::min(ctx->sm_count * 2, (2 * k + 7) / 8));
     const int zone_grid = ctx->sm_count * 2;
-    int launched = 0;
-    for (;;) {
-        for (int b = 0; b < batch && launched < max_iter; ++b, ++launched) {
-            NNC_LAUNCH(ctx, ll_table_kernel, 1, TB_THREADS, 0, st);
-            NNC_LAUNCH(ctx, ll_search_kernel, search_grid, 256, 0, st, h.d_sorted, samp, ptile);
-            NNC_LAUNCH(ctx, ll_zone_kernel, zone_grid, 256, sizeof(ZoneSmem), st, h.d_sorted);
-            PeerComm pc;
-            memset(&pc, 0, sizeof(pc));
-            if (world == 1) {
-                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 0, 2, pc);
-            } else if (ctx->peer_enabled && 2 * k <= PEER_WORDS) {
-                pc.enabled = 1;
-                pc.rank = ctx->rank;
-                pc.world = world;
-                for (int r = 0; r < world; ++r) pc.mail[r] = static_cast<unsigned long long *>(ctx->peer_mail[r]);
-                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 0, 2, pc);
-            } else {
-                // exact integer partials: the sums are identical on every rank and for every rank count
-                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 0, 0, pc);
-                comm_allreduce(ctx, reinterpret_cast<int64_t *>(st->gW), 2 * TB_KMAX, 0);  // gW, gS
-                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 1, 1, pc);
-                comm_allreduce(ctx, reinterpret_cast<int64_t *>(hs.cand), world * k * 2, 0);  // all-gather by sum
-                NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 2, 2, pc);
-            }
+    const bool peer = world > 1 && ctx->peer_enabled && 2 * k <= PEER_WORDS;
+    const bool one_launch = (world == 1 || peer) && !getenv("NNC_LLOYD_MULTI_LAUNCH");
+    PeerComm pc;
+    memset(&pc, 0, sizeof(pc));
+    if (peer) {
+        pc.enabled = 1;
+        pc.rank = ctx->rank;
+        pc.world = world;
+        for (int r = 0; r < world; ++r) pc.mail[r] = static_cast<unsigned long long *>(ctx->peer_mail[r]);
+    }
+    bool hist_done = false;
+    if (one_launch) {
+        static bool loop_configured = false;
+        if (!loop_configured) {
+            NNC_CUDA(cudaFuncSetAttribute(ll_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LoopSmem)));
+            loop_configured = true;
         }
+        const float *ks_arg = h.d_sorted;
+        const float *samp_arg = samp;
+        const long long *ptile_arg = ptile;
+        int max_iter_arg = max_iter, want_hist = h_hist ? 1 : 0;
+        void *args[] = {&st, &ks_arg, &samp_arg, &ptile_arg, &max_iter_arg, &want_hist, &pc};
+        const bool kt = ctx->ktime && (ctx->kfilter.empty() || strstr("ll_loop_kernel", ctx->kfilter.c_str()));
+        if (kt) klaunch_begin(ctx, "ll_loop_kernel");
+        NNC_CUDA(cudaLaunchCooperativeKernel((const void *)ll_loop_kernel, dim3(ctx->sm_count), dim3(TB_THREADS), args, sizeof(LoopSmem),
+                                             ctx->stream));
+        ctx->launches++;
+        if (kt) klaunch_end(ctx);
         NNC_CUDA(cudaMemcpyAsync(&ctl, &st->iter, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
         NNC_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctl.done || launched >= max_iter) break;
+        hist_done = h_hist != nullptr;
+    } else {
+        const int batch = 8;
+        int launched = 0;
+        for (;;) {
+            for (int b = 0; b < batch && launched < max_iter; ++b, ++launched) {
+                NNC_LAUNCH(ctx, ll_table_kernel, 1, TB_THREADS, 0, st);
+                NNC_LAUNCH(ctx, ll_search_kernel, search_grid, 256, 0, st, h.d_sorted, samp, ptile);
+                NNC_LAUNCH(ctx, ll_zone_kernel, zone_grid, 256, sizeof(ZoneSmem), st, h.d_sorted);
+                if (world == 1 || peer) {
+                    NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 0, 2, pc);
+                } else {
+                    // exact integer partials: the sums are identical on every rank and for every rank count
+                    NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 0, 0, pc);
+                    comm_allreduce(ctx, reinterpret_cast<int64_t *>(st->gW), 2 * TB_KMAX, 0);  // gW, gS
+                    NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 1, 1, pc);
+                    comm_allreduce(ctx, reinterpret_cast<int64_t *>(hs.cand), world * k * 2, 0);  // all-gather by sum
+                    NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 2, 2, pc);
+                }
+            }
+            NNC_CUDA(cudaMemcpyAsync(&ctl, &st->iter, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
+            NNC_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (ctl.done || launched >= max_iter) break;
+        }
+    }
+    if (one_launch) {
+        int bail = 0;
+        NNC_CUDA(cudaMemcpy(&bail, &st->gbail, sizeof(int), cudaMemcpyDeviceToHost));
+        if (bail) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: the grid barrier of the loop kernel timed out (iter %d)", ctl.iter);
     }
     if (!ctl.done) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: loop ended without a stop decision (iter %d)", ctl.iter);
     if (world > 1 && ctx->peer_enabled) {
@@ -1030,11 +1166,13 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
     float tol_h = 0.f;
     NNC_CUDA(cudaMemcpyAsync(&tol_h, &st->tol, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (h_hist) {
-        NNC_LAUNCH(ctx, ll_final_begin_kernel, 1, TB_KMAX, 0, st);
-        NNC_LAUNCH(ctx, ll_table_kernel, 1, TB_THREADS, 0, st);
-        NNC_LAUNCH(ctx, ll_search_kernel, search_grid, 256, 0, st, h.d_sorted, samp, ptile);
-        NNC_LAUNCH(ctx, ll_zone_kernel, zone_grid, 256, sizeof(ZoneSmem), st, h.d_sorted);
-        NNC_LAUNCH(ctx, ll_count_kernel, 1, TB_THREADS, 0, st);
+        if (!hist_done) {
+            NNC_LAUNCH(ctx, ll_final_begin_kernel, 1, TB_KMAX, 0, st);
+            NNC_LAUNCH(ctx, ll_table_kernel, 1, TB_THREADS, 0, st);
+            NNC_LAUNCH(ctx, ll_search_kernel, search_grid, 256, 0, st, h.d_sorted, samp, ptile);
+            NNC_LAUNCH(ctx, ll_zone_kernel, zone_grid, 256, sizeof(ZoneSmem), st, h.d_sorted);
+            NNC_LAUNCH(ctx, ll_count_kernel, 1, TB_THREADS, 0, st);
+        }
         comm_allreduce(ctx, reinterpret_cast<int64_t *>(st->hist), k, 0);
         static_assert(sizeof(long long) == sizeof(int64_t), "histogram element size");
         NNC_CUDA(cudaMemcpyAsync(h_hist, st->hist, sizeof(int64_t) * k, cudaMemcpyDeviceToHost, ctx->stream));
