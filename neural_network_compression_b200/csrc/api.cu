@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <exception>
@@ -742,9 +743,11 @@ int nnc_gather_f32(nnc_ctx *ctx, const float *w, int64_t n, const int64_t *idx, 
 // The k-means pipeline on a device-resident tensor (prologue -> compaction -> sort -> Lloyd -> emission); shared by
 // nnc_kmeans1d_f32 and nnc_compress_f32.  Output pointers are the caller's (host or device); w is a device pointer.
 // nz_bound: an upper bound of the non-zero count of the shard when the caller knows one (-1: none), sizes the buffers.
+// prefilled: the prologue already ran fused with the pruning pass (prune_device with a QuantFuse): the survivors are in
+// prefilled (capacity n) and DevScalars holds the prologue's results.
 static void kmeans_on_device(nnc_ctx *ctx, const float *d_w, int64_t n, int64_t nz_bound, const float *init, int k, int max_iter,
                              double tol, int flags, float *centers, float *centred, int32_t *labels, float *ris, uint8_t *packed, int bits,
-                             int64_t *hist, nnc_kmeans_info *info) {
+                             int64_t *hist, nnc_kmeans_info *info, float *prefilled = nullptr) {
     // n: elements of this rank's shard; n_global: of the whole tensor (they coincide on one rank)
     const bool init_linear = (flags & NNC_KM_INIT_LINEAR) != 0;
     const int64_t n_global = ctx->sh.n_global;
@@ -757,15 +760,18 @@ static void kmeans_on_device(nnc_ctx *ctx, const float *d_w, int64_t n, int64_t 
             if (!isfinite(init[j])) NNC_FAIL(NNC_ERR_NONFINITE, "initial centroid %d is not finite", j);
     // 1. mean (NumPy pairwise), min/max, key range, survivor count -- and the survivors, compacted in the same read
     const int64_t cap = std::max<int64_t>(1, std::min<int64_t>(n, nz_bound >= 0 ? nz_bound : n));
-    float *buf_a = arena_alloc_t<float>(ctx, (size_t)cap);
+    float *buf_a = prefilled ? prefilled : arena_alloc_t<float>(ctx, (size_t)cap);
     float *buf_b = arena_alloc_t<float>(ctx, (size_t)cap);
-    quant_prologue(ctx, d_w, n, buf_a, cap);
-    read_scalars(ctx);
-    prof_mark(ctx, "prologue");
+    if (!prefilled) {
+        quant_prologue(ctx, d_w, n, buf_a, cap);
+        read_scalars(ctx);
+        prof_mark(ctx, "prologue");
+    }
     const DevScalars sc = *ctx->h_scal;
     if (sc.n_nonfinite) NNC_FAIL(NNC_ERR_NONFINITE, "Input X contains NaN or infinity.");
     const int64_t n_nz = (int64_t)(ctx->world > 1 ? sc.n_nz_local : sc.n_nz);  // of this shard
-    if (n_nz > cap) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: %lld survivors exceed the reserved %lld", (long long)n_nz, (long long)cap);
+    if (n_nz > (prefilled ? n : cap))
+        NNC_FAIL(NNC_ERR_INTERNAL, "k-means: %lld survivors exceed the reserved %lld", (long long)n_nz, (long long)cap);
     // 2. survivors -> sorted
     // (a large narrow-range layer: as (value, multiplicity) runs from a key histogram, khist.cu; otherwise radix sort)
     const float *d_sorted = buf_a;
@@ -863,7 +869,13 @@ int nnc_compress_f32(nnc_ctx *ctx, float *w, int64_t n, double threshold, int st
     Staged sm = stage_out(ctx, mask, (size_t)n);
     prof_mark(ctx, "h2d");
     float *d_w = static_cast<float *>(sw.dev);
-    prune_device(ctx, d_w, n, threshold, std_smooth, threshold_mode, static_cast<uint8_t *>(sm.dev));
+    // with the std-scaled threshold the k-means prologue of the pruned tensor rides on the apply pass (one sweep less)
+    QuantFuse fuse;
+    if (std_smooth && !getenv("NNC_NO_FUSE")) {
+        fuse.out = arena_alloc_t<float>(ctx, (size_t)n);
+        fuse.capacity = n;
+    }
+    prune_device(ctx, d_w, n, threshold, std_smooth, threshold_mode, static_cast<uint8_t *>(sm.dev), fuse.out ? &fuse : nullptr);
     if (write_back) stage_finish(ctx, sw);  // a device-resident tensor was pruned in place already
     stage_finish(ctx, sm);
     read_scalars(ctx);
@@ -872,7 +884,8 @@ int nnc_compress_f32(nnc_ctx *ctx, float *w, int64_t n, double threshold, int st
     if (n_pruned_out) *n_pruned_out = (int64_t)ctx->h_scal->n_pruned;
     // every pruned element is a zero now: on one rank n - n_pruned bounds the survivors (on several, n_pruned is global)
     const int64_t nz_bound = ctx->world == 1 ? n - (int64_t)ctx->h_scal->n_pruned : -1;
-    kmeans_on_device(ctx, d_w, n, nz_bound, init, k, max_iter, tol, flags, centers, centred, nullptr, nullptr, packed, bits, hist, info);
+    kmeans_on_device(ctx, d_w, n, nz_bound, init, k, max_iter, tol, flags, centers, centred, nullptr, nullptr, packed, bits, hist, info,
+                     fuse.done ? fuse.out : nullptr);
     call.finish();
     NNC_CATCH
 }

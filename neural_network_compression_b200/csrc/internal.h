@@ -60,6 +60,7 @@ struct DevScalars {
     uint32_t min_ord, max_ord;        // ordered-uint min / max over all elements
     uint32_t min_nz_ord, max_nz_ord;  // ... over non-zero elements
     uint32_t amax_bits;               // largest |x| bit pattern (>= 0x7f800000: a NaN or infinity is present)
+    uint32_t amax_all;                // ... over ALL elements of the tensor the statistics pass read (VisitStats)
     uint32_t amin_nz_m1;              // smallest non-zero |x| bit pattern, minus one (0xffffffff: all zero)
     float fmin_all, fmax_all;         // float min / max over all elements (scratch; folded into min_ord / max_ord)
     unsigned long long n_nz;          // non-zero count (global once the ranks have exchanged)
@@ -181,7 +182,16 @@ struct NpPlan {
 NpPlan np_plan(int64_t n);
 size_t np_partials_bytes(const NpPlan &p);
 void np_stats(nnc_ctx *ctx, const float *d_w, int64_t n);  // fills mean/var/std_ in d_scal (2 passes)
-void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth, int thr_mode, uint8_t *d_mask);
+// fuse (nnc_compress_f32): the k-means prologue of the PRUNED tensor rides on the apply pass -- survivors compacted
+// into fuse->out, mean / min / max / key range / survivor count left in DevScalars exactly as quant_prologue would
+// leave them.  fuse->done tells whether that happened (not for a hard threshold or when the speculation failed).
+struct QuantFuse {
+    float *out = nullptr;
+    int64_t capacity = 0;
+    bool done = false;
+};
+void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth, int thr_mode, uint8_t *d_mask,
+                  QuantFuse *fuse = nullptr);
 void mask_apply_device(nnc_ctx *ctx, float *d_w, const uint8_t *d_mask, int64_t n);
 // k-means prologue: NumPy mean + min/max + non-zero count + |x| key range (DevScalars), and the non-zero elements
 // themselves written densely (unordered) into d_out -- one read of the tensor.

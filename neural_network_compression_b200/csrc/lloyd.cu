@@ -81,6 +81,7 @@ struct LloydDevice : LloydHeader {
     // per-iteration log (diagnostics): zone elements, zone groups, distinct centroids, empty clusters
     long long logZ[LL_LOG];
     int logG[LL_LOG], logM[LL_LOG], logE[LL_LOG];
+    unsigned int logT[LL_LOG][4];  // loop kernel: ns spent in search / zone / update / table (+ their barriers) per iteration
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -991,17 +992,34 @@ __global__ void __launch_bounds__(TB_THREADS, 1) ll_loop_kernel(LloydDevice *st,
     if (blockIdx.x == 0) table_phase(st, S.tb);
     grid_barrier(bar, epoch, bail);
     int stopped = 0;
+    auto now = []() {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+    };
+    const bool logger = blockIdx.x == 0 && threadIdx.x == 0;
     for (int it = 0; it < max_iter && !stopped; ++it) {
+        const unsigned long long t0 = logger ? now() : 0ull;
         search_phase(st, ks, samp, ptile);
         grid_barrier(bar, epoch, bail);
+        const unsigned long long t1 = logger ? now() : 0ull;
         zone_phase(st, ks, S.zn);
         grid_barrier(bar, epoch, bail);
+        const unsigned long long t2 = logger ? now() : 0ull;
+        unsigned long long t3 = 0;
         if (blockIdx.x == 0) {
             update_phase(st, ks, 0, 2, pc, S.up);
             __syncthreads();
+            t3 = logger ? now() : 0ull;
             if (!*done) table_phase(st, S.tb);
         }
         grid_barrier(bar, epoch, bail);
+        if (logger && it < LL_LOG) {
+            st->logT[it][0] = (unsigned int)(t1 - t0);
+            st->logT[it][1] = (unsigned int)(t2 - t1);
+            st->logT[it][2] = (unsigned int)(t3 - t2);
+            st->logT[it][3] = (unsigned int)(now() - t3);
+        }
         stopped = *done || *bail;  // `done` is only written by the update phase: stable until every CTA has read it
     }
     if (!want_hist || !stopped || *bail) return;
@@ -1187,9 +1205,12 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         NNC_CUDA(cudaMemcpy(g.data(), st->logG, sizeof(int) * cnt, cudaMemcpyDeviceToHost));
         NNC_CUDA(cudaMemcpy(mm.data(), st->logM, sizeof(int) * cnt, cudaMemcpyDeviceToHost));
         NNC_CUDA(cudaMemcpy(ee.data(), st->logE, sizeof(int) * cnt, cudaMemcpyDeviceToHost));
+        std::vector<unsigned int> tt(4 * (size_t)cnt);
+        NNC_CUDA(cudaMemcpy(tt.data(), st->logT, sizeof(unsigned int) * 4 * cnt, cudaMemcpyDeviceToHost));
         for (int i = 0; i < cnt; ++i)
-            fprintf(stderr, "[nnc lloyd] iter %d zone_elems %lld (%.3f%% of survivors) groups %d distinct %d empty %d\n", i, z[i],
-                    h.n_nz ? 100.0 * (double)z[i] / (double)h.n_nz : 0.0, g[i], mm[i], ee[i]);
+            fprintf(stderr, "[nnc lloyd] iter %d zone_elems %lld (%.3f%% of survivors) groups %d distinct %d empty %d | us: search %.1f zone %.1f update %.1f table %.1f\n", i, z[i],
+                    h.n_nz ? 100.0 * (double)z[i] / (double)h.n_nz : 0.0, g[i], mm[i], ee[i], tt[4 * i] * 1e-3, tt[4 * i + 1] * 1e-3,
+                    tt[4 * i + 2] * 1e-3, tt[4 * i + 3] * 1e-3);
     }
     LloydResult r;
     r.n_iter = ctl.n_iter;

@@ -79,16 +79,19 @@ struct BlockAux {  // shared scratch for visitor epilogues
 // 1.5e-5 wide).
 struct VisitStats {
     static constexpr bool kTileCount = false;
+    static constexpr bool kSecondTree = false;
     static constexpr bool kCompact = false;
     DevScalars *sc;
     double s = 0.0, s2 = 0.0;
     float ts = 0.f, ts2 = 0.f;
+    uint32_t amax = 0u;  // largest |x| bit pattern (the fused compress path takes its key range and NaN check from it)
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ float4 load4(const float *p) const { return ld_stream_f4(p); }
     __device__ __forceinline__ float load1(const float *p) const { return ld_stream_f1(p); }
     __device__ __forceinline__ float one(float x) {
         ts += x;
         ts2 = fmaf(x, x, ts2);
+        amax = max(amax, __float_as_uint(x) & 0x7fffffffu);
         return x;
     }
     __device__ __forceinline__ float4 visit4(int64_t, const float *, float4 x) {
@@ -103,19 +106,24 @@ struct VisitStats {
     }
     __device__ void finish(BlockAux &aux) {
         double a = warp_sum_d(s), b = warp_sum_d(s2);
+        const uint32_t m = warp_max_u(amax);
         if (lane_id() == 0) {
             aux.d[0][warp_id()] = a;
             aux.d[1][warp_id()] = b;
+            aux.o[0][warp_id()] = m;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
             double ta = 0, tb = 0;
+            uint32_t tm = 0;
             for (int i = 0; i < NP_THREADS / 32; i++) {
                 ta += aux.d[0][i];
                 tb += aux.d[1][i];
+                tm = max(tm, aux.o[0][i]);
             }
             atomicAdd(&sc->sum_d, ta);
             atomicAdd(&sc->sumsq_d, tb);
+            atomicMax(&sc->amax_all, tm);
         }
     }
 };
@@ -123,6 +131,7 @@ struct VisitStats {
 // plain centred squares (nnc_stats second pass, non-speculative prune fallback)
 struct VisitCenSq {
     static constexpr bool kTileCount = false;
+    static constexpr bool kSecondTree = false;
     static constexpr bool kCompact = false;
     DevScalars *sc;
     float mean;
@@ -144,6 +153,7 @@ struct VisitCenSq {
 // pass 2 of pruning: centred squares + speculative apply (see file header).
 struct VisitCenSqApply {
     static constexpr bool kTileCount = false;
+    static constexpr bool kSecondTree = false;
     static constexpr bool kCompact = false;
     DevScalars *sc;
     float *w;            // in place
@@ -229,6 +239,7 @@ struct VisitCenSqApply {
 // non-zero elements (the radix-sort key range), non-finite detection (|x| bits >= 0x7f800000).
 struct VisitQuant {
     static constexpr bool kTileCount = false;
+    static constexpr bool kSecondTree = false;
     static constexpr bool kCompact = true;  // the kernel also writes the non-zero elements of every tile to `out`
     DevScalars *sc;
     float *out;                       // survivors, dense, in no particular tile order (they are sorted next)
@@ -291,6 +302,172 @@ struct VisitQuant {
             atomicMin(&sc->amin_nz_m1, d);
             if (e) atomicAdd(&sc->n_nz, e);
             if (c >= 0x7f800000u) atomicAdd(&sc->n_nonfinite, 1ull);
+        }
+    }
+};
+
+// plain term = x (re-reduction of single tiles, see VisitApplyQuant)
+struct VisitPlain {
+    static constexpr bool kTileCount = false;
+    static constexpr bool kSecondTree = false;
+    static constexpr bool kCompact = false;
+    __device__ __forceinline__ void begin() {}
+    __device__ __forceinline__ float4 load4(const float *p) const { return *reinterpret_cast<const float4 *>(p); }
+    __device__ __forceinline__ float load1(const float *p) const { return *p; }
+    __device__ __forceinline__ float4 visit4(int64_t, const float *, float4 x) { return x; }
+    __device__ __forceinline__ float visit1(int64_t, const float *, float x) { return x; }
+    __device__ __forceinline__ void end_tile() {}
+    __device__ void finish(BlockAux &) {}
+};
+
+static __device__ __noinline__ void band_append(DevScalars *sc, long long *side_idx, float *side_val, unsigned long long side_cap,
+                                                long long g, float x) {
+    unsigned long long slot = atomicAdd(&sc->band_count, 1ull);
+    if (slot < side_cap) {
+        side_idx[slot] = g;
+        side_val[slot] = x;
+    } else {
+        atomicAdd(&sc->band_dropped, 1ull);
+    }
+}
+
+// pass 2 of pruning FUSED with the k-means prologue (nnc_compress_f32): besides VisitCenSqApply's work the same read
+// produces what VisitQuant would get from another sweep over the PRUNED tensor --
+//   second tree   NumPy's pairwise sum of the pruned values (-> X.mean of KMeans.fit, _kmeans.py:1486)
+//   compaction    the survivors, written densely to `out`
+//   scalars       min / max, |x| key range and count of the survivors.
+// Elements inside the speculation band are not decided yet: they are left out of the compaction and the scalars
+// (prune_fixup_kernel adds the ones that survive) and their tile is put on a list instead of delivering its
+// second-tree partial; the few listed tiles are re-reduced from the final tensor afterwards (VisitPlain).
+struct VisitApplyQuant {
+    static constexpr bool kTileCount = false;
+    static constexpr bool kSecondTree = true;
+    static constexpr bool kCompact = true;
+    DevScalars *sc;
+    float *w;  // in place
+    uint8_t *mask;
+    long long *side_idx;
+    float *side_val;
+    unsigned long long side_cap;
+    int mask_vec_ok;
+    float *out;  // survivors
+    unsigned long long *cursor;
+    unsigned long long capacity;
+    float *partials2;           // second tree: one partial per tile
+    uint32_t *dirty_list;       // tiles whose partial has to be recomputed
+    unsigned int *dirty_count;
+    float mean, lo, hi;
+    unsigned int pruned = 0;  // per thread: far below 2^32
+    float mn = INFINITY, mx = -INFINITY;
+    bool dirty = false;
+    __device__ __forceinline__ void begin() {
+        mean = sc->mean;
+        lo = (float)sc->band_lo;
+        hi = (float)sc->band_hi;
+    }
+    __device__ __forceinline__ float4 load4(const float *p) const { return *reinterpret_cast<const float4 *>(p); }
+    __device__ __forceinline__ float load1(const float *p) const { return *p; }
+    __device__ __forceinline__ bool take_dirty() {
+        const bool d = dirty;
+        dirty = false;
+        return d;
+    }
+    // an element inside the band: decided later with the exact threshold (rare: ~1e-5 of the elements).  A free
+    // function on purpose: a non-inlined MEMBER would take `this` and push the whole visitor into local memory.
+    __device__ __forceinline__ void band(int64_t g, float x) {
+        dirty = true;
+        band_append(sc, side_idx, side_val, side_cap, g, x);
+    }
+    __device__ __forceinline__ float4 visit4(int64_t g, const float *, float4 x, float4 &second) {
+        const float a0 = fabsf(x.x), a1 = fabsf(x.y), a2 = fabsf(x.z), a3 = fabsf(x.w);
+        const bool p0 = a0 < lo, p1 = a1 < lo, p2 = a2 < lo, p3 = a3 < lo;
+        float4 o = make_float4(p0 ? 0.f : x.x, p1 ? 0.f : x.y, p2 ? 0.f : x.z, p3 ? 0.f : x.w);  // the pruned tensor, band kept
+        second = o;
+        // in band: lo <= |x| < hi (a NaN is in neither set: it stays, final)
+        const bool b0 = !p0 && a0 < hi, b1 = !p1 && a1 < hi, b2 = !p2 && a2 < hi, b3 = !p3 && a3 < hi;
+        float4 sv = o;  // values that join min / max (fminf / fmaxf skip the NaN standing for an undecided element)
+        if (b0 | b1 | b2 | b3) {
+            if (b0) {
+                band(g, x.x);
+                second.x = 0.f;
+                sv.x = NAN;
+            }
+            if (b1) {
+                band(g + 1, x.y);
+                second.y = 0.f;
+                sv.y = NAN;
+            }
+            if (b2) {
+                band(g + 2, x.z);
+                second.z = 0.f;
+                sv.z = NAN;
+            }
+            if (b3) {
+                band(g + 3, x.w);
+                second.w = 0.f;
+                sv.w = NAN;
+            }
+        }
+        mn = fminf(fminf(mn, sv.x), fminf(sv.y, fminf(sv.z, sv.w)));
+        mx = fmaxf(fmaxf(mx, sv.x), fmaxf(sv.y, fmaxf(sv.z, sv.w)));
+        const uint32_t mm = (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)p2 << 16) | ((uint32_t)p3 << 24);
+        pruned += (unsigned int)p0 + (unsigned int)p1 + (unsigned int)p2 + (unsigned int)p3;
+        if (mm) *reinterpret_cast<float4 *>(w + g) = o;
+        if (mask_vec_ok) {
+            *reinterpret_cast<uint32_t *>(mask + g) = mm;
+        } else {
+            mask[g] = (uint8_t)p0;
+            mask[g + 1] = (uint8_t)p1;
+            mask[g + 2] = (uint8_t)p2;
+            mask[g + 3] = (uint8_t)p3;
+        }
+        const float t0 = fsub(x.x, mean), t1 = fsub(x.y, mean), t2 = fsub(x.z, mean), t3 = fsub(x.w, mean);
+        return make_float4(fmul(t0, t0), fmul(t1, t1), fmul(t2, t2), fmul(t3, t3));
+    }
+    __device__ __forceinline__ float visit1(int64_t g, const float *, float x, float &second) {
+        const float a = fabsf(x);
+        const bool p = a < lo;
+        const float o = p ? 0.f : x;
+        second = o;
+        if (!p && a < hi) {
+            band(g, x);
+            second = 0.f;
+        } else {
+            mn = fminf(mn, o);
+            mx = fmaxf(mx, o);
+        }
+        if (p) {
+            w[g] = 0.f;
+            pruned++;
+        }
+        mask[g] = (uint8_t)p;
+        const float t = fsub(x, mean);
+        return fmul(t, t);
+    }
+    __device__ __forceinline__ void end_tile() {}
+    __device__ void finish(BlockAux &aux) {
+        float a = warp_min_f(mn), b = warp_max_f(mx);
+        unsigned long long pc = warp_sum_ull((unsigned long long)pruned);
+        if (lane_id() == 0) {
+            aux.o[0][warp_id()] = __float_as_uint(a);
+            aux.o[1][warp_id()] = __float_as_uint(b);
+            aux.u[1][warp_id()] = pc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long pt = pc;
+            for (int i = 1; i < NP_THREADS / 32; i++) {
+                a = fminf(a, __uint_as_float(aux.o[0][i]));
+                b = fmaxf(b, __uint_as_float(aux.o[1][i]));
+                pt += aux.u[1][i];
+            }
+            if (a == 0.f) a = 0.f;  // -0.0 -> +0.0: canonical ordered image
+            if (b == 0.f) b = 0.f;
+            if (a <= b) {
+                atomicMin(&sc->min_ord, f2ord(a));
+                atomicMax(&sc->max_ord, f2ord(b));
+            }
+            if (pt) atomicAdd(&sc->n_pruned, pt);
         }
     }
 };
@@ -387,30 +564,66 @@ __global__ void np_tiles_kernel(int64_t n, int depth, NpTileDesc *desc) {
     desc[t] = d;
 }
 
-// a: this rank's shard (elements [shard_begin, ...) of the flattened tensor); tiles [t0, t1) belong to it
+// value of the node `gd` of the staged tile `tl` (NumPy order); called by the 8 lanes j = 0..7 of a group
+__device__ __forceinline__ float np_node_value(const float *tl, uint32_t gd, int j) {
+    const int o = gd & 8191, s = (gd >> 13) & 255;
+    float val;
+    if (s == 128 && (o & 127) == 0) {  // the common case: a full, aligned leaf -- no address arithmetic
+        const float *p = tl + np_pad(o) + j;
+        val = p[0];
+#pragma unroll
+        for (int i = 1; i < 16; ++i) val = fadd(val, p[8 * i]);
+        const unsigned gmask = 0xffu << (threadIdx.x & 24);
+        val = fadd(val, __shfl_xor_sync(gmask, val, 1));
+        val = fadd(val, __shfl_xor_sync(gmask, val, 2));
+        val = fadd(val, __shfl_xor_sync(gmask, val, 4));
+    } else if (s > 128) {  // a depth-5 node that splits once more: two leaves
+        int n2 = s >> 1;
+        n2 -= n2 & 7;
+        const float l = np_leaf_sum(tl, o, n2, j);
+        const float r = np_leaf_sum(tl, o + n2, s - n2, j);
+        val = fadd(l, r);
+    } else {
+        val = np_leaf_sum(tl, o, s, j);
+    }
+    return val;
+}
+
+// a: this rank's shard (elements [shard_begin, ...) of the flattened tensor); tiles [t0, t1) belong to it -- or, with a
+// tile list, the tiles tile_list[0, *list_count).
+// Dynamic shared memory: kCompact: float s_out[2][NP_TILE_MAX] (32 KB); kSecondTree: float tile2[NP_TILE_SMEM] after it.
 template <class V>
-__global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, uint32_t t0, uint32_t t1, int64_t shard_begin,
+__global__ void __launch_bounds__(NP_THREADS, V::kSecondTree ? 3 : 4) np_tree_kernel(const float *a, uint32_t t0, uint32_t t1, int64_t shard_begin,
                                                              int vec_ok, const NpTileDesc *__restrict__ desc, float *partials,
+                                                             const uint32_t *__restrict__ tile_list, const unsigned int *list_count,
                                                              V v) {
     __shared__ __align__(16) float tile[NP_TILE_SMEM];
     __shared__ float heap_val[2][64];
-    __shared__ unsigned int s_cnt[2];
+    __shared__ float heap_val2[V::kSecondTree ? 2 : 1][64];
+    __shared__ unsigned int s_cnt[2];   // survivors staged so far in s_out[b]
+    __shared__ unsigned int s_fcnt[2];  // ... of the completed tile in s_out[b], waiting to be flushed to s_base[b]
     __shared__ unsigned long long s_base[2];
-    extern __shared__ __align__(16) unsigned char np_dyn_smem[];  // kCompact: float s_out[2][NP_TILE_MAX] (32 KB)
+    __shared__ int s_dirty[2];
+    extern __shared__ __align__(16) unsigned char np_dyn_smem[];
     float(*s_out)[NP_TILE_MAX] = reinterpret_cast<float(*)[NP_TILE_MAX]>(np_dyn_smem);
+    float *tile2 = reinterpret_cast<float *>(np_dyn_smem) + (V::kCompact ? 2 * NP_TILE_MAX : 0);
     __shared__ BlockAux aux;
 
     v.begin();
     if (V::kTileCount || V::kCompact) {
         if (threadIdx.x < 2) {
             s_cnt[threadIdx.x] = 0;
+            s_fcnt[threadIdx.x] = 0;
             s_base[threadIdx.x] = 0;
+            s_dirty[threadIdx.x] = 0;
         }
         __syncthreads();
     }
     const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;
     int buf = 0;
-    for (uint32_t t = t0 + blockIdx.x; t < t1; t += gridDim.x, buf ^= 1) {
+    const uint32_t n_mine = tile_list ? *list_count : t1 - t0;
+    for (uint32_t it = blockIdx.x; it < n_mine; it += gridDim.x, buf ^= 1) {
+        const uint32_t t = tile_list ? tile_list[it] : t0 + it;
         const int64_t off = desc[t].off - shard_begin;  // offset inside the shard
         const int sz = desc[t].sz;
         const uint32_t gd = desc[t].grp[grp];
@@ -425,29 +638,88 @@ __global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, uin
                 const int i = r * NP_THREADS + threadIdx.x;
                 if (i < nvec) x[r] = v.load4(src + 4 * i);
             }
+            if constexpr (V::kSecondTree) {
+                float4 y2[NV];
+                int cnt = 0;
 #pragma unroll
-            for (int r = 0; r < NV; ++r) {
-                const int i = r * NP_THREADS + threadIdx.x;
-                if (i < nvec) {
-                    float4 y = v.visit4(off + 4 * i, src + 4 * i, x[r]);
-                    *reinterpret_cast<float4 *>(&tile[np_pad(4 * i)]) = y;
+                for (int r = 0; r < NV; ++r) {
+                    const int i = r * NP_THREADS + threadIdx.x;
+                    y2[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i < nvec) {
+                        float4 y = v.visit4(off + 4 * i, src + 4 * i, x[r], y2[r]);
+                        *reinterpret_cast<float4 *>(&tile[np_pad(4 * i)]) = y;
+                        *reinterpret_cast<float4 *>(&tile2[np_pad(4 * i)]) = y2[r];
+                    }
+                    cnt += (y2[r].x != 0.f) + (y2[r].y != 0.f) + (y2[r].z != 0.f) + (y2[r].w != 0.f);
+                }
+                // survivors straight from the registers into the shared-memory stage s_out[buf] (any order: they are
+                // sorted next): one warp scan and one shared-memory atomic per warp and tile
+                const int lane = lane_id();
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int tt = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += tt;
+                }
+                unsigned int wb = 0;
+                if (lane == 31 && incl) wb = atomicAdd(&s_cnt[buf], (unsigned int)incl);
+                wb = __shfl_sync(0xffffffffu, wb, 31);
+                float *dst = s_out[buf] + wb + (incl - cnt);
+#pragma unroll
+                for (int r = 0; r < NV; ++r) {
+                    if (y2[r].x != 0.f) *dst++ = y2[r].x;
+                    if (y2[r].y != 0.f) *dst++ = y2[r].y;
+                    if (y2[r].z != 0.f) *dst++ = y2[r].z;
+                    if (y2[r].w != 0.f) *dst++ = y2[r].w;
+                }
+                for (int i = (nvec << 2) + threadIdx.x; i < sz; i += NP_THREADS) {  // ragged end of the last tile
+                    float y2s;
+                    tile[np_pad(i)] = v.visit1(off + i, src + i, v.load1(src + i), y2s);
+                    tile2[np_pad(i)] = y2s;
+                    if (y2s != 0.f) s_out[buf][atomicAdd(&s_cnt[buf], 1u)] = y2s;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < NV; ++r) {
+                    const int i = r * NP_THREADS + threadIdx.x;
+                    if (i < nvec) {
+                        float4 y = v.visit4(off + 4 * i, src + 4 * i, x[r]);
+                        *reinterpret_cast<float4 *>(&tile[np_pad(4 * i)]) = y;
+                    }
+                }
+                for (int i = (nvec << 2) + threadIdx.x; i < sz; i += NP_THREADS)
+                    tile[np_pad(i)] = v.visit1(off + i, src + i, v.load1(src + i));
+            }
+        } else {
+            for (int i = threadIdx.x; i < sz; i += NP_THREADS) {
+                if constexpr (V::kSecondTree) {
+                    float y2s;
+                    tile[np_pad(i)] = v.visit1(off + i, src + i, v.load1(src + i), y2s);
+                    tile2[np_pad(i)] = y2s;
+                    if (y2s != 0.f) s_out[buf][atomicAdd(&s_cnt[buf], 1u)] = y2s;
+                } else {
+                    tile[np_pad(i)] = v.visit1(off + i, src + i, v.load1(src + i));
                 }
             }
-            for (int i = (nvec << 2) + threadIdx.x; i < sz; i += NP_THREADS)
-                tile[np_pad(i)] = v.visit1(off + i, src + i, v.load1(src + i));
-        } else {
-            for (int i = threadIdx.x; i < sz; i += NP_THREADS) tile[np_pad(i)] = v.visit1(off + i, src + i, v.load1(src + i));
         }
         v.end_tile();
         if constexpr (V::kTileCount) {
             const unsigned int c = (unsigned int)warp_sum_i((int)v.take_tile_count());
             if (lane_id() == 0 && c) atomicAdd(&s_cnt[buf], c);
         }
+        if constexpr (V::kSecondTree) {
+            if (v.take_dirty()) s_dirty[buf] = 1;
+        }
         __syncthreads();  // tile complete (also: warp 0 finished folding the tile before the previous one)
+        if constexpr (V::kSecondTree) {
+            // the other buffer's flag: warp 0 read it (fold of the previous tile) before arriving at the barrier above, and
+            // the next tile's staging sets it again only after the barrier below
+            if (threadIdx.x == 96) s_dirty[buf ^ 1] = 0;
+        }
         if constexpr (V::kCompact) {
             // flush the previous tile's survivors: its stage, count and global base are complete since the barrier
             const int pb = buf ^ 1;
-            const unsigned int c = s_cnt[pb];
+            const unsigned int c = s_fcnt[pb];
             if (c) {
                 const unsigned long long b = s_base[pb];
                 if (b + c <= v.capacity)
@@ -456,33 +728,20 @@ __global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, uin
         }
         // ---- leaves: the 8 lanes of group `grp` sum the node described by gd
         {
-            const int o = gd & 8191, s = (gd >> 13) & 255, h = (gd >> 21) & 63;
-            float val;
-            if (s == 128 && (o & 127) == 0) {  // the common case: a full, aligned leaf -- no address arithmetic
-                const float *p = tile + np_pad(o) + j;
-                val = p[0];
-#pragma unroll
-                for (int i = 1; i < 16; ++i) val = fadd(val, p[8 * i]);
-                const unsigned gmask = 0xffu << (threadIdx.x & 24);
-                val = fadd(val, __shfl_xor_sync(gmask, val, 1));
-                val = fadd(val, __shfl_xor_sync(gmask, val, 2));
-                val = fadd(val, __shfl_xor_sync(gmask, val, 4));
-            } else if (s > 128) {  // a depth-5 node that splits once more: two leaves
-                int n2 = s >> 1;
-                n2 -= n2 & 7;
-                const float l = np_leaf_sum(tile, o, n2, j);
-                const float r = np_leaf_sum(tile, o + n2, s - n2, j);
-                val = fadd(l, r);
-            } else {
-                val = np_leaf_sum(tile, o, s, j);
-            }
+            const int h = (gd >> 21) & 63;
+            const float val = np_node_value(tile, gd, j);
             if (j == 0 && (gd >> 27)) heap_val[buf][h] = val;
+            if constexpr (V::kSecondTree) {
+                const float val2 = np_node_value(tile2, gd, j);
+                if (j == 0 && (gd >> 27)) heap_val2[buf][h] = val2;
+            }
         }
-        if constexpr (V::kCompact) {
-            // survivors of the tile, straight from the staged tile (term == value for this visitor), compacted into
-            // the shared-memory stage s_out[buf]: a warp takes the 512 elements [512 w, 512 (w + 1)), counts, and
+        if constexpr (V::kCompact && !V::kSecondTree) {
+            // survivors of the tile, straight from the staged values (the terms themselves for this visitor), compacted
+            // into the shared-memory stage s_out[buf]: a warp takes the 512 elements [512 w, 512 (w + 1)), counts, and
             // reserves its slots of the stage with one shared-memory atomic (warp order inside the tile is arbitrary --
-            // the consumer is a sort).
+            // the consumer is a sort).  (The fused visitor compacts from its registers while staging.)
+            const float *vals = tile;
             const int lane = lane_id(), wbase_e = warp_id() * 512;
             float4 xs[4];
             int cnt = 0;
@@ -490,7 +749,7 @@ __global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, uin
             for (int r = 0; r < 4; ++r) {
                 const int e = wbase_e + r * 128 + lane * 4;
                 xs[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (e < sz) xs[r] = *reinterpret_cast<const float4 *>(&tile[np_pad(e)]);
+                if (e < sz) xs[r] = *reinterpret_cast<const float4 *>(&vals[np_pad(e)]);
                 if (e + 3 >= sz) {  // tail of the (globally last) tile: mask what lies beyond it
                     if (e + 1 >= sz) xs[r].y = 0.f;
                     if (e + 2 >= sz) xs[r].z = 0.f;
@@ -518,7 +777,7 @@ __global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, uin
                 if (xs[r].w != 0.f) *dst++ = xs[r].w;
             }
         }
-        __syncthreads();  // node values visible; the tile buffer may be overwritten
+        __syncthreads();  // node values visible; the tile buffers may be overwritten
         // ---- fold (warp 0): internal nodes take left + right, level by level
         if (threadIdx.x < 32) {
             const int lane = threadIdx.x;
@@ -526,24 +785,37 @@ __global__ void __launch_bounds__(NP_THREADS) np_tree_kernel(const float *a, uin
 #pragma unroll
             for (int lvl = 4; lvl >= 0; --lvl) {
                 const int h = (1 << lvl) + lane;
-                if (lane < (1 << lvl) && ((internal >> h) & 1u)) heap_val[buf][h] = fadd(heap_val[buf][2 * h], heap_val[buf][2 * h + 1]);
+                if (lane < (1 << lvl) && ((internal >> h) & 1u)) {
+                    heap_val[buf][h] = fadd(heap_val[buf][2 * h], heap_val[buf][2 * h + 1]);
+                    if constexpr (V::kSecondTree) heap_val2[buf][h] = fadd(heap_val2[buf][2 * h], heap_val2[buf][2 * h + 1]);
+                }
                 __syncwarp();
             }
-            if (lane == 0) partials[t] = heap_val[buf][1];
+            if (lane == 0) {
+                partials[t] = heap_val[buf][1];
+                if constexpr (V::kSecondTree) {
+                    if (s_dirty[buf])  // holds undecided elements: re-reduced from the final tensor later
+                        v.dirty_list[atomicAdd(v.dirty_count, 1u)] = t;
+                    else
+                        v.partials2[t] = heap_val2[buf][1];
+                }
+            }
         }
         if constexpr (V::kCompact) {
             // one global atomic per tile reserves the output slots; the copy stage -> global happens after the next
             // barrier (the next tile's "tile complete"), so the atomic's latency is off the critical path
             if (threadIdx.x == 64) {
-                s_base[buf] = s_cnt[buf] ? atomicAdd(v.cursor, (unsigned long long)s_cnt[buf]) : 0ull;
-                s_cnt[buf ^ 1] = 0;  // flushed above, before this tile's second barrier; reused by the next tile
+                const unsigned int c = s_cnt[buf];
+                s_base[buf] = c ? atomicAdd(v.cursor, (unsigned long long)c) : 0ull;
+                s_fcnt[buf] = c;  // read by the flush after the next tile's first barrier
+                s_cnt[buf] = 0;   // next written by the tile after next, which starts after the next tile's second barrier
             }
         }
     }
     __syncthreads();
     if constexpr (V::kCompact) {  // the last tile of this CTA
         const int pb = buf ^ 1;
-        const unsigned int c = s_cnt[pb];
+        const unsigned int c = s_fcnt[pb];
         const unsigned long long b = s_base[pb];
         if (b + c <= v.capacity)
             for (unsigned int i = threadIdx.x; i < c; i += NP_THREADS) v.out[b + i] = s_out[pb][i];
@@ -613,9 +885,11 @@ __global__ void __launch_bounds__(1024) np_final_kernel(float *partials, uint32_
     }
 }
 
-// Decide the band elements with the exact threshold.
+// Decide the band elements with the exact threshold.  With `out` (fused k-means prologue, VisitApplyQuant) the decided
+// values also join the prologue's statistics and the survivors are appended to the compacted array.
 __global__ void prune_fixup_kernel(float *w, uint8_t *mask, const long long *side_idx, const float *side_val,
-                                   unsigned long long cap, DevScalars *sc) {
+                                   unsigned long long cap, DevScalars *sc, float *out, unsigned long long *cursor,
+                                   unsigned long long capacity) {
     unsigned long long cnt = sc->band_count;
     if (cnt > cap) cnt = cap;
     float thr_f = f32_ceil_of(sc->thr);
@@ -623,14 +897,42 @@ __global__ void prune_fixup_kernel(float *w, uint8_t *mask, const long long *sid
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < cnt;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         long long g = side_idx[i];
-        if (fabsf(side_val[i]) < thr_f) {
+        float x = side_val[i];
+        const bool p = fabsf(x) < thr_f;
+        if (p) {
             w[g] = 0.f;
             mask[g] = 1;
             pruned++;
+            x = 0.f;
+        }
+        if (out) {
+            if (x == 0.f) x = 0.f;  // canonical zero
+            atomicMin(&sc->min_ord, f2ord(x));
+            atomicMax(&sc->max_ord, f2ord(x));
+            const uint32_t ab = __float_as_uint(x) & 0x7fffffffu;
+            if (ab != 0u) {
+                atomicMax(&sc->amax_bits, ab);
+                atomicMin(&sc->amin_nz_m1, ab - 1u);
+                atomicAdd(&sc->n_nz, 1ull);
+                const unsigned long long at = atomicAdd(cursor, 1ull);
+                if (at < capacity) out[at] = x;
+            }
         }
     }
     pruned = warp_sum_ull(pruned);
     if (lane_id() == 0 && pruned) atomicAdd(&sc->n_pruned, pruned);
+}
+
+// Fused k-means prologue (VisitApplyQuant): the scalars the apply pass did not track per element.  Every survivor has
+// |x| >= band_lo and |x| <= the largest |x| of the original tensor (statistics pass), which is all the sort needs (any
+// enclosing key range is valid); the survivor count is the compaction cursor.
+__global__ void quant_scalars_kernel(DevScalars *sc, const unsigned long long *cursor) {
+    sc->n_nz = *cursor;
+    const float lo = (float)sc->band_lo;
+    const uint32_t lo_m1 = lo > 0.f ? __float_as_uint(lo) - 1u : 0u;
+    sc->amin_nz_m1 = min(sc->amin_nz_m1, lo_m1);
+    sc->amax_bits = max(sc->amax_bits, sc->amax_all);
+    if (sc->amax_all >= 0x7f800000u) sc->n_nonfinite = 1ull;
 }
 
 // Plain elementwise apply with a known threshold (std_smooth = False, and the safe fallback).
@@ -808,7 +1110,7 @@ static NpTileDesc *run_tree(nnc_ctx *ctx, const float *d_w, V v, const FinArgs &
     NNC_LAUNCH(ctx, np_tiles_kernel, (p.num_tiles + 127) / 128, 128, 0, n, p.depth, desc);
     if (ctx->world > 1) NNC_CUDA(cudaMemsetAsync(partials, 0, sizeof(float) * (2 * (size_t)p.num_tiles + 2), ctx->stream));
     const uint32_t t0 = ctx->sh.t0, t1 = ctx->sh.t1;
-    const size_t dyn = V::kCompact ? 2 * sizeof(float) * NP_TILE_MAX : 0;
+    const size_t dyn = (V::kCompact ? 2 * sizeof(float) * NP_TILE_MAX : 0) + (V::kSecondTree ? sizeof(float) * NP_TILE_SMEM : 0);
     if (V::kCompact) {
         static bool configured = false;
         if (!configured) {
@@ -818,7 +1120,7 @@ static NpTileDesc *run_tree(nnc_ctx *ctx, const float *d_w, V v, const FinArgs &
     }
     if (t1 > t0)
         NNC_LAUNCH(ctx, np_tree_kernel<V>, tree_grid(ctx, t1 - t0), NP_THREADS, dyn, d_w, t0, t1, ctx->sh.begin,
-                   aligned16(d_w) ? 1 : 0, desc, partials, v);
+                   aligned16(d_w) ? 1 : 0, desc, partials, (const uint32_t *)nullptr, (const unsigned int *)nullptr, v);
     if (ctx->world > 1) comm_allreduce(ctx, reinterpret_cast<int64_t *>(partials), (int)((p.num_tiles + 1) / 2), 0);
     exchange_scalars(ctx, exchange_mode);
     NNC_LAUNCH(ctx, np_final_kernel, 1, 1024, 0, partials, p.num_tiles, ctx->d_scal, fa);
@@ -864,8 +1166,9 @@ void quant_prologue(nnc_ctx *ctx, const float *d_w, int64_t n, float *d_out, int
     run_tree(ctx, d_w, v, FinArgs{FIN_MEAN, ng, 0.0, 0, 1}, EX_QUANT);
 }
 
-void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth, int thr_mode, uint8_t *d_mask) {
+void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth, int thr_mode, uint8_t *d_mask, QuantFuse *fuse) {
     clear_scalars(ctx);
+    if (fuse) fuse->done = false;
     const int vec_ok = aligned16(d_w) && aligned4(d_mask);
     const int ew_grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 16, (n / 4 + 255) / 256 + 1);
     if (!std_smooth) {
@@ -886,6 +1189,47 @@ void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth,
     unsigned long long cap = (unsigned long long)std::max<int64_t>(65536, n / 256);
     long long *side_idx = arena_alloc_t<long long>(ctx, cap);
     float *side_val = arena_alloc_t<float>(ctx, cap);
+    unsigned long long *cursor = nullptr;
+    if (fuse && fuse->out) {
+        // pass 2 fused with the k-means prologue of the pruned tensor (VisitApplyQuant)
+        const NpPlan p = np_plan(ng);
+        float *partials2 = arena_alloc_t<float>(ctx, 2 * (size_t)p.num_tiles + 2);
+        uint32_t *dirty_list = arena_alloc_t<uint32_t>(ctx, (size_t)p.num_tiles);
+        unsigned long long *ctr = arena_alloc_t<unsigned long long>(ctx, 2);  // survivor cursor, dirty-tile count
+        NNC_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        if (ctx->world > 1) NNC_CUDA(cudaMemsetAsync(partials2, 0, sizeof(float) * (2 * (size_t)p.num_tiles + 2), ctx->stream));
+        cursor = ctr;
+        unsigned int *dirty_count = reinterpret_cast<unsigned int *>(ctr + 1);
+        VisitApplyQuant v2;
+        v2.sc = ctx->d_scal;
+        v2.w = d_w;
+        v2.mask = d_mask;
+        v2.side_idx = side_idx;
+        v2.side_val = side_val;
+        v2.side_cap = cap;
+        v2.mask_vec_ok = aligned4(d_mask) ? 1 : 0;
+        v2.out = fuse->out;
+        v2.cursor = cursor;
+        v2.capacity = (unsigned long long)fuse->capacity;
+        v2.partials2 = partials2;
+        v2.dirty_list = dirty_list;
+        v2.dirty_count = dirty_count;
+        v2.mean = v2.lo = v2.hi = 0.f;
+        NpTileDesc *desc = run_tree(ctx, d_w, v2, FinArgs{FIN_PRUNE2, ng, q, thr_mode, 1}, EX_NONE);
+        prof_mark(ctx, "var+apply");
+        NNC_LAUNCH(ctx, prune_fixup_kernel, 64, 256, 0, d_w, d_mask, side_idx, side_val, cap, ctx->d_scal, fuse->out, cursor,
+                   (unsigned long long)fuse->capacity);
+        NNC_LAUNCH(ctx, quant_scalars_kernel, 1, 1, 0, ctx->d_scal, cursor);
+        // tiles that held undecided elements: their partial of the second tree from the final tensor
+        NNC_LAUNCH(ctx, np_tree_kernel<VisitPlain>, std::max(1, std::min<int>(ctx->sm_count * 4, (int)std::min<uint32_t>(p.num_tiles, 1u << 20))),
+                   NP_THREADS, 0, d_w, 0u, 0u, ctx->sh.begin, aligned16(d_w) ? 1 : 0, desc, partials2, (const uint32_t *)dirty_list,
+                   (const unsigned int *)dirty_count, VisitPlain{});
+        exchange_scalars(ctx, EX_PRUNE);
+        if (ctx->world > 1) comm_allreduce(ctx, reinterpret_cast<int64_t *>(partials2), (int)((p.num_tiles + 1) / 2), 0);
+        exchange_scalars(ctx, EX_QUANT);
+        NNC_LAUNCH(ctx, np_final_kernel, 1, 1024, 0, partials2, p.num_tiles, ctx->d_scal, FinArgs{FIN_MEAN, ng, 0.0, 0, 1});
+        prof_mark(ctx, "fixup");
+    } else {
     VisitCenSqApply v2;
     v2.sc = ctx->d_scal;
     v2.w = d_w;
@@ -897,11 +1241,14 @@ void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth,
     v2.mean = v2.lo = v2.hi = 0.f;
     run_tree(ctx, d_w, v2, FinArgs{FIN_PRUNE2, ng, q, thr_mode, 1}, EX_NONE);
     prof_mark(ctx, "var+apply");
-    NNC_LAUNCH(ctx, prune_fixup_kernel, 64, 256, 0, d_w, d_mask, side_idx, side_val, cap, ctx->d_scal);
+    NNC_LAUNCH(ctx, prune_fixup_kernel, 64, 256, 0, d_w, d_mask, side_idx, side_val, cap, ctx->d_scal, (float *)nullptr,
+               (unsigned long long *)nullptr, 0ull);
     exchange_scalars(ctx, EX_PRUNE);
     prof_mark(ctx, "fixup");
+    }
     read_scalars(ctx);
     const DevScalars &s = *ctx->h_scal;
+    if (fuse && fuse->out) fuse->done = !(s.spec_failed || s.band_dropped);
     if (s.spec_failed || s.band_dropped) {
         // Either the exact threshold left the speculation band (non-finite or badly scaled data) or the side
         // list overflowed.  Everything that is still non-zero is re-decided with the exact threshold.  This is

@@ -448,6 +448,26 @@ def test_compress_weight_matches_separate_steps(U, mode, bits):
     assert np.array_equal(mask2, mask_ref) and np.array_equal(km2.packed_codes, km_ref.packed_codes)
 
 
+@pytest.mark.parametrize("n,q", [(1 << 22, 1.0), ((1 << 22) + 12345, 0.5), (3 * 1000 * 1000 + 1, 2.0), (70001, 1.0), (1 << 20, 0.0)])
+def test_compress_weight_fused_prologue_large(U, n, q, monkeypatch):
+    # the k-means prologue rides on the pruning pass (reduce_np.cu: VisitApplyQuant): enough elements for the speculation
+    # band to be populated, ragged tile sizes, a threshold of zero (nothing pruned); against the unfused library path
+    w = D.gaussian(n, seed=n % 1013)
+    a, b = w.copy(), w.copy()
+    mask, km = U.compress_weight(a, q, True, 6, "linear")
+    monkeypatch.setenv("NNC_NO_FUSE", "1")
+    mask_ref, km_ref = U.compress_weight(b, q, True, 6, "linear")
+    w_np = w.copy()
+    mask_np = D.prune_np(w_np, q)
+    assert np.array_equal(mask, mask_np) and a.tobytes() == w_np.tobytes()
+    assert np.array_equal(mask, mask_ref) and a.tobytes() == b.tobytes()
+    assert km.mean == km_ref.mean == np.float32(np.mean(w_np))
+    assert km.cluster_centers_.tobytes() == km_ref.cluster_centers_.tobytes()
+    assert km.n_iter_ == km_ref.n_iter_ and km.n_nonzero == km_ref.n_nonzero == int(np.count_nonzero(w_np))
+    assert np.array_equal(km.packed_codes, km_ref.packed_codes)
+    assert np.array_equal(km.code_histogram, km_ref.code_histogram)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # multi-GPU: sharded run == single-rank run, bit for bit (needs >= 2 GPUs; the driver's 1-GPU box skips it)
 # ---------------------------------------------------------------------------------------------------------
