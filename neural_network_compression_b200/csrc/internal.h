@@ -166,6 +166,17 @@ void klaunch_end(nnc_ctx *ctx);
         NNC_CUDA(cudaGetLastError());                                   \
     } while (0)
 
+// the same with an explicit name for the per-kernel timing (template kernels: one name per instantiation)
+#define NNC_LAUNCH_AS(ctx, name, kernel, grid, block, smem, ...)         \
+    do {                                                                \
+        const bool _kt = (ctx)->ktime && ((ctx)->kfilter.empty() || strstr((name), (ctx)->kfilter.c_str())); \
+        if (_kt) nnc::klaunch_begin((ctx), (name));                     \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+        (ctx)->launches++;                                              \
+        if (_kt) nnc::klaunch_end((ctx));                               \
+        NNC_CUDA(cudaGetLastError());                                   \
+    } while (0)
+
 void read_scalars(nnc_ctx *ctx);  // D2H of DevScalars + stream sync
 
 // In-place all-reduce of `count` int64 values in device memory over the ranks of the context (no-op for one rank).

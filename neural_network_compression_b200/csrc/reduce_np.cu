@@ -78,6 +78,7 @@ struct BlockAux {  // shared scratch for visitor epilogues
 // the 16 elements a thread sees of a tile, float64 across tiles: relative error ~1e-7, the speculation band is
 // 1.5e-5 wide).
 struct VisitStats {
+    static constexpr const char *kName = "np_tree_kernel<VisitStats>";
     static constexpr bool kTileCount = false;
     static constexpr bool kSecondTree = false;
     static constexpr bool kCompact = false;
@@ -130,6 +131,7 @@ struct VisitStats {
 
 // plain centred squares (nnc_stats second pass, non-speculative prune fallback)
 struct VisitCenSq {
+    static constexpr const char *kName = "np_tree_kernel<VisitCenSq>";
     static constexpr bool kTileCount = false;
     static constexpr bool kSecondTree = false;
     static constexpr bool kCompact = false;
@@ -152,6 +154,7 @@ struct VisitCenSq {
 
 // pass 2 of pruning: centred squares + speculative apply (see file header).
 struct VisitCenSqApply {
+    static constexpr const char *kName = "np_tree_kernel<VisitCenSqApply>";
     static constexpr bool kTileCount = false;
     static constexpr bool kSecondTree = false;
     static constexpr bool kCompact = false;
@@ -238,6 +241,7 @@ struct VisitCenSqApply {
 // k-means prologue: term = x (-> mean); side: min / max, non-zero count, range of |x| bit patterns over the
 // non-zero elements (the radix-sort key range), non-finite detection (|x| bits >= 0x7f800000).
 struct VisitQuant {
+    static constexpr const char *kName = "np_tree_kernel<VisitQuant>";
     static constexpr bool kTileCount = false;
     static constexpr bool kSecondTree = false;
     static constexpr bool kCompact = true;  // the kernel also writes the non-zero elements of every tile to `out`
@@ -308,6 +312,7 @@ struct VisitQuant {
 
 // plain term = x (re-reduction of single tiles, see VisitApplyQuant)
 struct VisitPlain {
+    static constexpr const char *kName = "np_tree_kernel<VisitPlain>";
     static constexpr bool kTileCount = false;
     static constexpr bool kSecondTree = false;
     static constexpr bool kCompact = false;
@@ -340,6 +345,7 @@ static __device__ __noinline__ void band_append(DevScalars *sc, long long *side_
 // (prune_fixup_kernel adds the ones that survive) and their tile is put on a list instead of delivering its
 // second-tree partial; the few listed tiles are re-reduced from the final tensor afterwards (VisitPlain).
 struct VisitApplyQuant {
+    static constexpr const char *kName = "np_tree_kernel<VisitApplyQuant>";
     static constexpr bool kTileCount = false;
     static constexpr bool kSecondTree = true;
     static constexpr bool kCompact = true;
@@ -1119,7 +1125,7 @@ static NpTileDesc *run_tree(nnc_ctx *ctx, const float *d_w, V v, const FinArgs &
         }
     }
     if (t1 > t0)
-        NNC_LAUNCH(ctx, np_tree_kernel<V>, tree_grid(ctx, t1 - t0), NP_THREADS, dyn, d_w, t0, t1, ctx->sh.begin,
+        NNC_LAUNCH_AS(ctx, V::kName, np_tree_kernel<V>, tree_grid(ctx, t1 - t0), NP_THREADS, dyn, d_w, t0, t1, ctx->sh.begin,
                    aligned16(d_w) ? 1 : 0, desc, partials, (const uint32_t *)nullptr, (const unsigned int *)nullptr, v);
     if (ctx->world > 1) comm_allreduce(ctx, reinterpret_cast<int64_t *>(partials), (int)((p.num_tiles + 1) / 2), 0);
     exchange_scalars(ctx, exchange_mode);
@@ -1221,7 +1227,7 @@ void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth,
                    (unsigned long long)fuse->capacity);
         NNC_LAUNCH(ctx, quant_scalars_kernel, 1, 1, 0, ctx->d_scal, cursor);
         // tiles that held undecided elements: their partial of the second tree from the final tensor
-        NNC_LAUNCH(ctx, np_tree_kernel<VisitPlain>, std::max(1, std::min<int>(ctx->sm_count * 4, (int)std::min<uint32_t>(p.num_tiles, 1u << 20))),
+        NNC_LAUNCH_AS(ctx, VisitPlain::kName, np_tree_kernel<VisitPlain>, std::max(1, std::min<int>(ctx->sm_count * 4, (int)std::min<uint32_t>(p.num_tiles, 1u << 20))),
                    NP_THREADS, 0, d_w, 0u, 0u, ctx->sh.begin, aligned16(d_w) ? 1 : 0, desc, partials2, (const uint32_t *)dirty_list,
                    (const unsigned int *)dirty_count, VisitPlain{});
         exchange_scalars(ctx, EX_PRUNE);
