@@ -177,9 +177,9 @@ __global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__rest
     const int64_t n_chunks = (n + EM_PER - 1) / EM_PER;
     const int64_t total_bytes = (n * bits + 7) / 8;
     const int64_t stride = (int64_t)gridDim.x * EM_THREADS;
-    for (int64_t chunk = (int64_t)blockIdx.x * EM_THREADS + threadIdx.x; chunk < n_chunks; chunk += stride) {
+    // the loads of the next chunk are issued before the current one is processed: 64 B per thread in flight
+    auto load_chunk = [&](int64_t chunk, float *x) {
         const int64_t base = chunk * EM_PER;
-        float x[EM_PER];
         const int cnt = (int)min((int64_t)EM_PER, n - base);
         if (VEC && cnt == EM_PER) {
             float4 a = ld_stream_f4(w + base), b = ld_stream_f4(w + base + 4);
@@ -189,6 +189,19 @@ __global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__rest
 #pragma unroll
             for (int j = 0; j < EM_PER; ++j) x[j] = j < cnt ? w[base + j] : 0.f;
         }
+    };
+    float xn[EM_PER];
+    {
+        const int64_t first = (int64_t)blockIdx.x * EM_THREADS + threadIdx.x;
+        if (first < n_chunks) load_chunk(first, xn);
+    }
+    for (int64_t chunk = (int64_t)blockIdx.x * EM_THREADS + threadIdx.x; chunk < n_chunks; chunk += stride) {
+        const int64_t base = chunk * EM_PER;
+        float x[EM_PER];
+        const int cnt = (int)min((int64_t)EM_PER, n - base);
+#pragma unroll
+        for (int j = 0; j < EM_PER; ++j) x[j] = xn[j];
+        if (chunk + stride < n_chunks) load_chunk(chunk + stride, xn);
         // phase 1, branch free: LUT entry of every element (pruned weights take the known label of 0.0)
         int id[EM_PER];
         uint32_t slow = 0;

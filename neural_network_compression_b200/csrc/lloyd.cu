@@ -59,6 +59,7 @@ struct LloydDevice : LloydHeader {
     float c_save[TB_KMAX];
     long long hist[TB_KMAX];  // code histogram of the final labelling (ll_count_kernel)
     RegionTable tab;
+    int perm[TB_KMAX];                // sorted order of the centroids at the previous table build
     long long rpos[2 * TB_KMAX + 2];  // entries before every region boundary
     long long rcnt[2 * TB_KMAX + 2];  // elements before every region boundary (= rpos without multiplicities)
     long long rsum[2 * TB_KMAX + 2];
@@ -173,7 +174,7 @@ __global__ void ll_init_kernel(LloydDevice *st, const float *init) {
 // per-iteration kernels
 // ---------------------------------------------------------------------------------------------
 __device__ void table_phase(LloydDevice *st, TableScratch &S) {
-    build_region_table(st->c, st->k, st->xabs_max, &st->tab, S);
+    build_region_table(st->c, st->k, st->xabs_max, &st->tab, S, st->perm);
     const int tid = threadIdx.x;
     if (tid < st->k) {
         st->zW[tid] = 0;
@@ -460,6 +461,7 @@ struct UpdateSmem {
     int red_i[32], red_id[32];
     uint32_t rk_d2[32], rk_gap[32], rk_ord[32];
     int rk_who[32];
+    long long red_w[32];
     int n_empty, zdi, same, winner, stop_reloc;  // stop_reloc: scratch of the convergence step
     long long zero_left;
     long long rpos[2 * TB_KMAX + 2];  // copy of the region positions for the relocation cursors (label_at)
@@ -839,11 +841,37 @@ __device__ void update_phase(LloydDevice *st, const float *__restrict__ ks, int 
     // ---- 6. averages (_average_centers), shift (_center_shift)
     if (tid < k) U.raw[tid] = (float)__ddiv_rn((double)U.S[tid], scale);
     __syncthreads();
-    if (tid == 0) {
-        int amax = 0;
-        for (int j = 1; j < k; ++j)
-            if (U.W[j] > U.W[amax]) amax = j;
-        U.winner = amax;
+    {   // argmax of the counts, lowest id on ties (np.argmax): block reduction
+        long long bw = tid < k ? U.W[tid] : -1;
+        int bi = tid < k ? tid : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const long long ow = __shfl_xor_sync(0xffffffffu, bw, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ow > bw || (ow == bw && oi < bi)) {
+                bw = ow;
+                bi = oi;
+            }
+        }
+        if (lane_id() == 0) {
+            U.red_w[warp_id()] = bw;
+            U.red_i[warp_id()] = bi;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            bw = U.red_w[tid];
+            bi = U.red_i[tid];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const long long ow = __shfl_xor_sync(0xffffffffu, bw, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ow > bw || (ow == bw && oi < bi)) {
+                    bw = ow;
+                    bi = oi;
+                }
+            }
+            if (tid == 0) U.winner = bi;
+        }
     }
     __syncthreads();
     if (tid < k) {
@@ -961,13 +989,15 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &ep
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         unsigned int v;
         long long spins = 0;
-        do {
+        for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-            if (++spins > (1ll << 23)) {
+            if (v >= target) break;
+            if (++spins > (1ll << 22)) {
                 *bail = 1;
                 break;
             }
-        } while (v < target);
+            __nanosleep(64);  // 148 pollers on one line: leave the L2 slice room for the arrivals
+        }
     }
     __syncthreads();
 }
@@ -1022,6 +1052,15 @@ __global__ void __launch_bounds__(TB_THREADS, 1) ll_loop_kernel(LloydDevice *st,
         }
         stopped = *done || *bail;  // `done` is only written by the update phase: stable until every CTA has read it
     }
+    if (logger) {  // cost of the bare grid barrier (diagnostics)
+        const unsigned long long tb = now();
+        st->logT[LL_LOG - 1][0] = (unsigned int)tb;
+    }
+    grid_barrier(bar, epoch, bail);
+    grid_barrier(bar, epoch, bail);
+    grid_barrier(bar, epoch, bail);
+    grid_barrier(bar, epoch, bail);
+    if (logger) st->logT[LL_LOG - 1][1] = (unsigned int)now();
     if (!want_hist || !stopped || *bail) return;
     // code histogram of the final labelling (`done` stays set: nobody reads it from here on)
     if (blockIdx.x == 0) {
@@ -1207,6 +1246,9 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         NNC_CUDA(cudaMemcpy(ee.data(), st->logE, sizeof(int) * cnt, cudaMemcpyDeviceToHost));
         std::vector<unsigned int> tt(4 * (size_t)cnt);
         NNC_CUDA(cudaMemcpy(tt.data(), st->logT, sizeof(unsigned int) * 4 * cnt, cudaMemcpyDeviceToHost));
+        unsigned int tb[2];
+        NNC_CUDA(cudaMemcpy(tb, st->logT[LL_LOG - 1], sizeof(tb), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[nnc lloyd] four bare grid barriers: %.2f us\n", (tb[1] - tb[0]) * 1e-3);
         for (int i = 0; i < cnt; ++i)
             fprintf(stderr, "[nnc lloyd] iter %d zone_elems %lld (%.3f%% of survivors) groups %d distinct %d empty %d | us: search %.1f zone %.1f update %.1f table %.1f\n", i, z[i],
                     h.n_nz ? 100.0 * (double)z[i] / (double)h.n_nz : 0.0, g[i], mm[i], ee[i], tt[4 * i] * 1e-3, tt[4 * i + 1] * 1e-3,

@@ -185,7 +185,10 @@ struct TableScratch {
 
 // Build the table for centroids c[0..k) (centred space).  Must be called by all TB_THREADS threads of a CTA.
 // xabs_max: max |x'| over the data.
-static __device__ void build_region_table(const float *c, int k, float xabs_max, RegionTable *T, TableScratch &S) {
+// perm (optional, k ints in global memory, zero-initialised): the sorted order of the previous call.  Centroids
+// rarely change their order between Lloyd iterations: when the previous order still sorts them the bitonic network
+// (36 barriers for 256 centroids) is skipped.
+static __device__ void build_region_table(const float *c, int k, float xabs_max, RegionTable *T, TableScratch &S, int *perm = nullptr) {
     const int tid = threadIdx.x;
     // ---- 1. sort (value, id)
     int P = 32;
@@ -195,11 +198,27 @@ static __device__ void build_region_table(const float *c, int k, float xabs_max,
         cv = c[tid];
         if (cv == 0.f) cv = 0.f;  // -0.0 -> +0.0 (identical distances)
     }
-    if (tid < P) S.keys[tid] = tid < k ? (((unsigned long long)f2ord(cv) << 32) | (unsigned)tid) : ~0ull;
     // max |c|
     float cm = tid < k ? fabsf(cv) : 0.f;
     cm = warp_max_f(cm);
     if (lane_id() == 0) S.warp_f[warp_id()] = cm;
+    bool sorted = false;
+    if (perm) {
+        unsigned long long key = ~0ull;
+        if (tid < k) {
+            const int pi = perm[tid];
+            float pv = c[pi];
+            if (pv == 0.f) pv = 0.f;
+            key = ((unsigned long long)f2ord(pv) << 32) | (unsigned)pi;
+        }
+        if (tid < P) S.keys[tid] = key;
+        __syncthreads();
+        // strictly increasing (value, id) keys over distinct ids = the sorted order
+        const bool ok = tid + 1 < k ? S.keys[tid] < S.keys[tid + 1] : true;
+        sorted = __syncthreads_and(ok) != 0;
+    }
+    if (!sorted) {
+    if (tid < P) S.keys[tid] = tid < k ? (((unsigned long long)f2ord(cv) << 32) | (unsigned)tid) : ~0ull;
     __syncthreads();
     for (int size = 2; size <= P; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -216,6 +235,8 @@ static __device__ void build_region_table(const float *c, int k, float xabs_max,
             }
             __syncthreads();
         }
+    }
+    if (perm && tid < k) perm[tid] = (int)(S.keys[tid] & 0xffffffffu);
     }
     float M = xabs_max;
     for (int i = 0; i < TB_THREADS / 32; ++i) M = fmaxf(M, S.warp_f[i]);
