@@ -31,7 +31,8 @@
 
 namespace nnc {
 
-constexpr int LL_TS = 1024;  // sorted-array tile
+constexpr int LL_TS = 512;   // sorted-array tile (one round of 16 loads per lane in the boundary search)
+constexpr int LL_TOP = 2048; // entries of the shared-memory top level of the tile-sample index (loop kernel)
 constexpr int LL_LOG = 304;  // per-iteration diagnostics kept for the first LL_LOG iterations
 
 __host__ __device__ __forceinline__ long long llmin2(long long a, long long b) { return a < b ? a : b; }
@@ -198,21 +199,59 @@ __global__ void __launch_bounds__(TB_THREADS) ll_table_kernel(LloydDevice *st) {
     table_phase(st, S);
 }
 
-// entries / elements of the sorted survivors with fl(x - mean) < t, and the sum of q over them; one warp per boundary
-__device__ __forceinline__ void warp_boundary_search(const float *__restrict__ ks, const unsigned int *__restrict__ cnt,
-                                                     const float *__restrict__ samp, const long long *__restrict__ ptile,
-                                                     const long long *__restrict__ ctile, long long n_ent,
-                                                     long long n_tiles, float mean, double scale, float t,
-                                                     long long &pos_out, long long &cnt_out, long long &sum_out) {
+// entries / elements of the sorted survivors with fl(x - mean) < t, and the sum of q over them; one warp per boundary.
+// top (optional, shared memory): top[i] = samp[i * top_step], i < top_n -- the first, coarse level of the search without a
+// trip to L2.
+struct SearchConst {  // per-launch constants of the search (hoisted out of the iterations by the loop kernel)
+    const float *ks;
+    const unsigned int *cnt;
+    const float *samp;
+    const long long *ptile, *ctile;
+    long long n_ent, n_tiles;
+    float mean;
+    double scale;
+    const float *top;
+    long long top_step;
+    int top_n;
+};
+
+__device__ __forceinline__ void warp_boundary_search(const SearchConst &C, float t, long long &pos_out, long long &cnt_out,
+                                                     long long &sum_out) {
     const int lane = lane_id();
-    long long lo = 0, hi = n_tiles;  // first tile whose first key fails the predicate lies in [lo, hi]
+    const float mean = C.mean;
+    long long lo = 0, hi = C.n_tiles;  // first tile whose first key fails the predicate lies in [lo, hi]
+    if (C.top) {  // coarse level: number of top samples that satisfy the predicate (they are a prefix)
+        int a = 0, b = C.top_n;  // first top index failing lies in [a, b]
+        while (a < b) {
+            const int span = b - a, step = (span + 31) >> 5;
+            const int cs = a + lane * step;
+            const int last = min(cs + step, b) - 1;
+            const bool p = cs < b ? (fsub(C.top[last], mean) < t) : false;
+            const int c = __popc(__ballot_sync(0xffffffffu, p));
+            const int na = min(a + c * step, b);
+            if (na >= b) {
+                a = b;
+                break;
+            }
+            b = min(na + step, b) - 1;
+            a = na;
+        }
+        // top samples 0 .. a-1 satisfy the predicate, sample a (if any) fails
+        if (a == 0) {
+            lo = 0;
+            hi = 0;
+        } else {
+            lo = (long long)(a - 1) * C.top_step + 1;  // tile (a-1)*step satisfies: the first failing tile is after it
+            hi = a < C.top_n ? (long long)a * C.top_step : C.n_tiles;
+        }
+    }
     while (lo < hi) {
         long long span = hi - lo;
         long long step = (span + 31) >> 5;
         long long cs = lo + (long long)lane * step;  // chunk start
         bool inr = cs < hi;
         long long last = llmin2(cs + step, hi) - 1;
-        bool p = inr ? (fsub(samp[last], mean) < t) : false;
+        bool p = inr ? (fsub(C.samp[last], mean) < t) : false;
         unsigned b = __ballot_sync(0xffffffffu, p);
         int c = __popc(b);
         long long nlo = llmin2(lo + (long long)c * step, hi);
@@ -232,44 +271,42 @@ __device__ __forceinline__ void warp_boundary_search(const float *__restrict__ k
     }
     const long long tile = lo - 1;
     const long long base = tile * LL_TS;
+    // the tile's prefixes and its entries: all loads in flight together
+    const long long psum = C.ptile[tile];
+    const long long pcnt = C.cnt ? C.ctile[tile] : 0;
     long long npos = 0, acc = 0, cacc = 0;
-    constexpr int HALF = LL_TS / 64;
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {  // two rounds of 16 loads per lane in flight (64 registers per thread in the loop kernel)
-        float xv[HALF];
-        unsigned int cv[HALF];
+    constexpr int PER = LL_TS / 32;
+    float xv[PER];
+    unsigned int cv[PER];
 #pragma unroll
-        for (int j = 0; j < HALF; ++j) {
-            const long long i = base + (h * HALF + j) * 32 + lane;
-            xv[j] = i < n_ent ? ks[i] : INFINITY;
-            cv[j] = (cnt && i < n_ent) ? cnt[i] : 1u;
-        }
+    for (int j = 0; j < PER; ++j) {
+        const long long i = base + j * 32 + lane;
+        xv[j] = i < C.n_ent ? C.ks[i] : INFINITY;
+        cv[j] = (C.cnt && i < C.n_ent) ? C.cnt[i] : 1u;
+    }
 #pragma unroll
-        for (int j = 0; j < HALF; ++j) {
-            const float xc = fsub(xv[j], mean);
-            const bool p = xc < t;  // padding is +inf: never counted
-            if (p) {
-                acc += fixed_q(xc, scale) * (long long)cv[j];
-                cacc += cv[j];
-            }
-            npos += __popc(__ballot_sync(0xffffffffu, p));
+    for (int j = 0; j < PER; ++j) {
+        const float xc = fsub(xv[j], mean);
+        const bool p = xc < t;  // padding is +inf: never counted
+        if (p) {
+            acc += fixed_q(xc, C.scale) * (long long)cv[j];
+            cacc += cv[j];
         }
+        npos += __popc(__ballot_sync(0xffffffffu, p));
     }
     acc = warp_sum_ll(acc);
     pos_out = base + npos;
-    cnt_out = cnt ? ctile[tile] + warp_sum_ll(cacc) : pos_out;
-    sum_out = ptile[tile] + acc;
+    cnt_out = C.cnt ? pcnt + warp_sum_ll(cacc) : pos_out;
+    sum_out = psum + acc;
 }
 
-__device__ __forceinline__ void search_phase(LloydDevice *st, const float *__restrict__ ks, const float *__restrict__ samp,
-                                             const long long *__restrict__ ptile) {
+__device__ __forceinline__ void search_phase(LloydDevice *st, const SearchConst &C) {
     const int nb = st->tab.R - 1;  // boundaries 1 .. R-1
     const int wpb = blockDim.x >> 5;
     // warps of different CTAs take consecutive boundaries: the work spreads over all SMs
     for (int r = 1 + warp_id() * gridDim.x + blockIdx.x; r <= nb; r += gridDim.x * wpb) {
         long long pos, cn, sum;
-        warp_boundary_search(ks, st->cnt, samp, ptile, st->ctile, st->n_ent, st->n_tiles, st->mean, st->scale, st->tab.rstart[r],
-                             pos, cn, sum);
+        warp_boundary_search(C, st->tab.rstart[r], pos, cn, sum);
         if (lane_id() == 0) {
             st->rpos[r] = pos;
             st->rcnt[r] = cn;
@@ -277,11 +314,27 @@ __device__ __forceinline__ void search_phase(LloydDevice *st, const float *__res
         }
     }
 }
+__device__ __forceinline__ SearchConst search_const(const LloydDevice *st, const float *ks, const float *samp, const long long *ptile) {
+    SearchConst C;
+    C.ks = ks;
+    C.cnt = st->cnt;
+    C.samp = samp;
+    C.ptile = ptile;
+    C.ctile = st->ctile;
+    C.n_ent = st->n_ent;
+    C.n_tiles = st->n_tiles;
+    C.mean = st->mean;
+    C.scale = st->scale;
+    C.top = nullptr;
+    C.top_step = 1;
+    C.top_n = 0;
+    return C;
+}
 __global__ void __launch_bounds__(256) ll_search_kernel(LloydDevice *st, const float *__restrict__ ks,
                                                         const float *__restrict__ samp,
                                                         const long long *__restrict__ ptile) {
     if (st->done) return;
-    search_phase(st, ks, samp, ptile);
+    search_phase(st, search_const(st, ks, samp, ptile));
 }
 
 struct ZoneSmem {
@@ -1015,6 +1068,14 @@ __global__ void __launch_bounds__(TB_THREADS, 1) ll_loop_kernel(LloydDevice *st,
                                                                PeerComm pc) {
     extern __shared__ __align__(16) unsigned char loop_smem_raw[];
     LoopSmem &S = *reinterpret_cast<LoopSmem *>(loop_smem_raw);
+    __shared__ float s_top[LL_TOP];
+    SearchConst C = search_const(st, ks, samp, ptile);
+    if (C.n_tiles > 64) {  // top level of the tile-sample index in shared memory (the samples never change)
+        C.top_step = (C.n_tiles + LL_TOP - 1) / LL_TOP;
+        C.top_n = (int)((C.n_tiles + C.top_step - 1) / C.top_step);
+        for (int i = threadIdx.x; i < C.top_n; i += blockDim.x) s_top[i] = samp[(long long)i * C.top_step];
+        C.top = s_top;
+    }
     unsigned int epoch = 0;
     unsigned int *bar = &st->gbar;
     volatile int *bail = &st->gbail;
@@ -1030,7 +1091,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) ll_loop_kernel(LloydDevice *st,
     const bool logger = blockIdx.x == 0 && threadIdx.x == 0;
     for (int it = 0; it < max_iter && !stopped; ++it) {
         const unsigned long long t0 = logger ? now() : 0ull;
-        search_phase(st, ks, samp, ptile);
+        search_phase(st, C);
         grid_barrier(bar, epoch, bail);
         const unsigned long long t1 = logger ? now() : 0ull;
         zone_phase(st, ks, S.zn);
@@ -1069,7 +1130,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) ll_loop_kernel(LloydDevice *st,
         table_phase(st, S.tb);
     }
     grid_barrier(bar, epoch, bail);
-    search_phase(st, ks, samp, ptile);
+    search_phase(st, C);
     grid_barrier(bar, epoch, bail);
     zone_phase(st, ks, S.zn);
     grid_barrier(bar, epoch, bail);
