@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(256) ll_search_kernel(LloydDevice *st, const f
 }
 
 struct ZoneSmem {
+    long long rp[2 * TB_KMAX + 2];  // copy of the region positions (the per-element lookup stays on chip)
     long long zpre[2 * TB_KMAX + 2];
     long long s_warp[32];
     unsigned long long sW[TB_KMAX];
@@ -352,9 +353,12 @@ __device__ void zone_phase(LloydDevice *st, const float *__restrict__ ks, ZoneSm
     const RegionTable &T = st->tab;
     const int R = T.R, m = T.m;
     if (R <= 1) return;
-    // prefix of zone sizes over the regions (SAFE regions count 0): chunked scan by the 256 threads
+    // prefix of zone sizes over the regions (SAFE regions count 0): chunked scan by the threads of the CTA
     {
-        auto zsize = [&](int r) -> long long { return T.rJ1[r] > T.rJ2[r] ? st->rpos[r + 1] - st->rpos[r] : 0ll; };
+        long long *rp = Z_.rp;
+        for (int r = threadIdx.x; r <= R; r += blockDim.x) rp[r] = st->rpos[r];
+        __syncthreads();
+        auto zsize = [&](int r) -> long long { return T.rJ1[r] > T.rJ2[r] ? rp[r + 1] - rp[r] : 0ll; };
         const int per = (R + blockDim.x - 1) / blockDim.x;
         const int lo = min(R, (int)threadIdx.x * per), hi = min(R, lo + per);
         long long sum = 0;
@@ -403,7 +407,7 @@ __device__ void zone_phase(LloydDevice *st, const float *__restrict__ ks, ZoneSm
                     hi = mid;
             }
             const int r = lo;
-            p = st->rpos[r] + (e - zpre[r]);
+            p = Z_.rp[r] + (e - zpre[r]);
             float xc = fsub(ks[p], mean);
             di = zone_argmin(xc, T.dv, T.dcn, T.down, T.rJ2[r], T.rJ1[r]);
             c = ecnt ? (long long)ecnt[p] : 1ll;
@@ -759,16 +763,22 @@ __device__ void update_phase(LloydDevice *st, const float *__restrict__ ks, int 
                 U.rk_who[warp_id()] = owner;
             }
             __syncthreads();
-            if (tid == 0) {
-                for (int w = 1; w < TB_THREADS / 32; ++w) {
-                    FarKey ob{U.rk_d2[w], U.rk_gap[w], U.rk_ord[w]};
-                    int oo = U.rk_who[w];
+            if (tid < 32) {  // warp 0 folds the 32 warp winners (same order relation: a total order, so any tree gives the same winner)
+                best = FarKey{U.rk_d2[tid], U.rk_gap[tid], U.rk_ord[tid]};
+                owner = U.rk_who[tid];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    FarKey ob;
+                    ob.d2 = __shfl_xor_sync(0xffffffffu, best.d2, o);
+                    ob.gap = __shfl_xor_sync(0xffffffffu, best.gap, o);
+                    ob.ordx = __shfl_xor_sync(0xffffffffu, best.ordx, o);
+                    int oo = __shfl_xor_sync(0xffffffffu, owner, o);
                     if (oo >= 0 && (owner < 0 || far_before(ob, best) || (!far_before(best, ob) && oo < owner))) {
                         best = ob;
                         owner = oo;
                     }
                 }
-                U.winner = owner;
+                if (tid == 0) U.winner = owner;
             }
             __syncthreads();
             if (U.winner < 0) break;  // this rank has no sample left
