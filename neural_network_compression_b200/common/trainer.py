@@ -86,3 +86,23 @@ class Compressor:
                 models.append(kmeans)
             fitted[layer] = models
         return fitted
+
+    @torch.no_grad()
+    def trained_quantization_step(self, fitted, learning_rate: float) -> None:
+        """The fine-tuning step of Deep Compression's trained quantization, which the reference describes but leaves
+        unimplemented (papers/lat/report.tex:149-158): the gradient of a shared weight is the sum of the gradients of
+        the weights that carry its index, dL/dC_k = sum_ij dL/dW_ij 1(I_ij = k) (report.tex:152); the codebook takes a
+        plain SGD step and the layer is re-materialised from the unchanged packed indices.
+
+        fitted: what quantize() returned; every parameter must hold its loss gradient in .grad."""
+        for layer, models in fitted.items():
+            for params, kmeans in zip(_layer_params(layer), models):
+                if kmeans is None or params.grad is None:
+                    continue
+                k, bits = kmeans.n_clusters, kmeans.code_bits
+                grad = params.grad.contiguous().view(-1)
+                g = utility.cluster_gradient_sum(grad, kmeans.packed_codes, k, bits)  # float64[k], exact per tile
+                centers = (kmeans.cluster_centers_.astype("float64").ravel() - learning_rate * g).astype("float32")
+                kmeans.cluster_centers_ = centers.reshape(-1, 1)
+                params.data.copy_(utility.dequantize(kmeans.packed_codes, params.numel(), bits, centers).view_as(params))
+

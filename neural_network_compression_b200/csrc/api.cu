@@ -62,6 +62,8 @@ void arena_reset(nnc_ctx *ctx) {
     }
     ctx->ws_off = 0;
     ctx->call_bytes = 0;
+    ctx->desc_n = -1;
+    ctx->desc_ptr = nullptr;
 }
 
 void arena_reserve(nnc_ctx *ctx, size_t bytes) {

@@ -842,6 +842,26 @@ struct FinArgs {
 
 __device__ __forceinline__ float f32_ceil_of(double d) { return __double2float_ru(d); }
 
+// First stage of the fold for big trees: every CTA folds 1024 consecutive partials -- a complete sub-tree of the
+// (complete, binary) fold, so the additions are exactly the ones the one-CTA fold below would do.
+__global__ void __launch_bounds__(512) np_fold1024_kernel(const float *__restrict__ partials, float *__restrict__ out) {
+    __shared__ float a[1024], b[512];
+    const float *src = partials + (size_t)blockIdx.x * 1024;
+    a[threadIdx.x] = src[threadIdx.x];
+    a[threadIdx.x + 512] = src[threadIdx.x + 512];
+    __syncthreads();
+    float *s = a, *d = b;
+    for (int len = 1024; len > 1; len >>= 1) {
+        const int half = len >> 1;
+        if ((int)threadIdx.x < half) d[threadIdx.x] = fadd(s[2 * threadIdx.x], s[2 * threadIdx.x + 1]);
+        __syncthreads();
+        float *t = s;
+        s = d;
+        d = t;
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = s[0];
+}
+
 __global__ void __launch_bounds__(1024) np_final_kernel(float *partials, uint32_t count, DevScalars *sc, FinArgs fa) {
     float *src = partials, *dst = partials + count;
     for (uint32_t len = count; len > 1; len >>= 1) {
@@ -1098,6 +1118,17 @@ static void exchange_scalars(nnc_ctx *ctx, int mode) {
     NNC_LAUNCH(ctx, scal_unpack_kernel, 1, 1, 0, ctx->d_scal, buf, mode, world);
 }
 
+// fold of the tile partials (+ scalar epilogue): two stages for big trees
+static void launch_final(nnc_ctx *ctx, float *partials, uint32_t count, const FinArgs &fa) {
+    if (count >= 4096) {  // count is a power of two
+        float *stage = partials + count;
+        NNC_LAUNCH(ctx, np_fold1024_kernel, count / 1024, 512, 0, partials, stage);
+        NNC_LAUNCH(ctx, np_final_kernel, 1, 1024, 0, stage, count / 1024, ctx->d_scal, fa);
+    } else {
+        NNC_LAUNCH(ctx, np_final_kernel, 1, 1024, 0, partials, count, ctx->d_scal, fa);
+    }
+}
+
 static int tree_grid(nnc_ctx *ctx, uint32_t tiles) {
     int64_t g = (int64_t)ctx->sm_count * 8;
     if ((int64_t)tiles < g) g = tiles;
@@ -1112,8 +1143,13 @@ static NpTileDesc *run_tree(nnc_ctx *ctx, const float *d_w, V v, const FinArgs &
     const int64_t n = ctx->sh.n_global;
     NpPlan p = np_plan(n);
     float *partials = arena_alloc_t<float>(ctx, 2 * (size_t)p.num_tiles + 2);
-    NpTileDesc *desc = arena_alloc_t<NpTileDesc>(ctx, p.num_tiles);
-    NNC_LAUNCH(ctx, np_tiles_kernel, (p.num_tiles + 127) / 128, 128, 0, n, p.depth, desc);
+    NpTileDesc *desc = static_cast<NpTileDesc *>(ctx->desc_ptr);
+    if (ctx->desc_n != n || !desc) {  // the descriptors only depend on n: built once per call
+        desc = arena_alloc_t<NpTileDesc>(ctx, p.num_tiles);
+        NNC_LAUNCH(ctx, np_tiles_kernel, (p.num_tiles + 127) / 128, 128, 0, n, p.depth, desc);
+        ctx->desc_n = n;
+        ctx->desc_ptr = desc;
+    }
     if (ctx->world > 1) NNC_CUDA(cudaMemsetAsync(partials, 0, sizeof(float) * (2 * (size_t)p.num_tiles + 2), ctx->stream));
     const uint32_t t0 = ctx->sh.t0, t1 = ctx->sh.t1;
     const size_t dyn = (V::kCompact ? 2 * sizeof(float) * NP_TILE_MAX : 0) + (V::kSecondTree ? sizeof(float) * NP_TILE_SMEM : 0);
@@ -1129,7 +1165,7 @@ static NpTileDesc *run_tree(nnc_ctx *ctx, const float *d_w, V v, const FinArgs &
                    aligned16(d_w) ? 1 : 0, desc, partials, (const uint32_t *)nullptr, (const unsigned int *)nullptr, v);
     if (ctx->world > 1) comm_allreduce(ctx, reinterpret_cast<int64_t *>(partials), (int)((p.num_tiles + 1) / 2), 0);
     exchange_scalars(ctx, exchange_mode);
-    NNC_LAUNCH(ctx, np_final_kernel, 1, 1024, 0, partials, p.num_tiles, ctx->d_scal, fa);
+    launch_final(ctx, partials, p.num_tiles, fa);
     return desc;
 }
 
@@ -1233,7 +1269,7 @@ void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth,
         exchange_scalars(ctx, EX_PRUNE);
         if (ctx->world > 1) comm_allreduce(ctx, reinterpret_cast<int64_t *>(partials2), (int)((p.num_tiles + 1) / 2), 0);
         exchange_scalars(ctx, EX_QUANT);
-        NNC_LAUNCH(ctx, np_final_kernel, 1, 1024, 0, partials2, p.num_tiles, ctx->d_scal, FinArgs{FIN_MEAN, ng, 0.0, 0, 1});
+        launch_final(ctx, partials2, p.num_tiles, FinArgs{FIN_MEAN, ng, 0.0, 0, 1});
         prof_mark(ctx, "fixup");
     } else {
     VisitCenSqApply v2;

@@ -531,3 +531,39 @@ def test_compressor_lenet300_matches_reference_flow(U):
             expect = det.cluster_centers_[det.labels_].reshape(h.shape)
             assert km.cluster_centers_.tobytes() == det.cluster_centers_.tobytes()
             assert p.detach().cpu().numpy().tobytes() == expect.tobytes()
+
+
+def test_trained_quantization_step_matches_numpy(U):
+    # Deep Compression's codebook fine-tuning (report.tex:149-153): centroid gradient = per-cluster sum of the weight
+    # gradients; SGD step on the codebook; layer re-materialised from the packed indices
+    import torch
+
+    from neural_network_compression_b200.common.trainer import Compressor
+    from neural_network_compression_b200.neural_networks import LeNet300100
+
+    torch.manual_seed(1)
+    net = LeNet300100().cuda()
+    comp = Compressor(net, net.layers_to_prune_with_threshold())
+    comp._prune_parameters(True)
+    fitted = comp.quantize(False, 4, "linear")
+    before = {}
+    for layer, models in fitted.items():
+        for p, km in zip((layer.weight, layer.bias), models):
+            p.grad = torch.randn_like(p) * 1e-2
+            if km is not None:
+                before[p] = (km.cluster_centers_.copy(), km.labels_.cpu().numpy())
+    lr = 0.05
+    comp.trained_quantization_step(fitted, lr)
+    checked = 0
+    for layer, models in fitted.items():
+        for p, km in zip((layer.weight, layer.bias), models):
+            if km is None:
+                continue
+            centers0, labels = before[p]
+            g = np.bincount(labels, weights=p.grad.cpu().numpy().ravel().astype(np.float64), minlength=km.n_clusters)
+            expect = (centers0.astype(np.float64).ravel() - lr * g).astype(np.float32)
+            np.testing.assert_allclose(km.cluster_centers_.ravel(), expect, rtol=1e-6, atol=1e-9)
+            assert p.detach().cpu().numpy().ravel().tobytes() == km.cluster_centers_.ravel()[labels].tobytes()
+            checked += 1
+    assert checked >= 5
+
