@@ -21,6 +21,8 @@
 //           go to a side list and are decided by a fix-up kernel once the exact threshold is known.
 #include <math.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "internal.h"
 #include "table.cuh"
@@ -639,25 +641,36 @@ __global__ void __launch_bounds__(NP_THREADS, V::kSecondTree ? 3 : 4) np_tree_ke
             const int nvec = sz >> 2;
             constexpr int NV = NP_TILE_MAX / 4 / NP_THREADS;
             float4 x[NV];
-#pragma unroll
-            for (int r = 0; r < NV; ++r) {  // all loads first: the in-place visitor's stores would otherwise fence them
-                const int i = r * NP_THREADS + threadIdx.x;
-                if (i < nvec) x[r] = v.load4(src + 4 * i);
-            }
             if constexpr (V::kSecondTree) {
                 float4 y2[NV];
                 int cnt = 0;
+                // element 4 i of the tile lives at tile[np_pad(4 i)]; i = r * NP_THREADS + tid, and 4 * NP_THREADS is a
+                // multiple of 128, so the padded index advances by a constant per r
+                constexpr int RSTRIDE = 4 * NP_THREADS + ((4 * NP_THREADS) >> 7) * 8;
+                const int sidx0 = np_pad(4 * (int)threadIdx.x);
+                auto stage = [&](auto full_c) {
+                    constexpr bool FULL = decltype(full_c)::value;  // a complete 4096-element tile: no bounds checks
 #pragma unroll
-                for (int r = 0; r < NV; ++r) {
-                    const int i = r * NP_THREADS + threadIdx.x;
-                    y2[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (i < nvec) {
-                        float4 y = v.visit4(off + 4 * i, src + 4 * i, x[r], y2[r]);
-                        *reinterpret_cast<float4 *>(&tile[np_pad(4 * i)]) = y;
-                        *reinterpret_cast<float4 *>(&tile2[np_pad(4 * i)]) = y2[r];
+                    for (int r = 0; r < NV; ++r) {  // all loads first: the in-place stores would otherwise fence them
+                        const int i = r * NP_THREADS + threadIdx.x;
+                        if (FULL || i < nvec) x[r] = v.load4(src + 4 * i);
                     }
-                    cnt += (y2[r].x != 0.f) + (y2[r].y != 0.f) + (y2[r].z != 0.f) + (y2[r].w != 0.f);
-                }
+#pragma unroll
+                    for (int r = 0; r < NV; ++r) {
+                        const int i = r * NP_THREADS + threadIdx.x;
+                        y2[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (FULL || i < nvec) {
+                            float4 y = v.visit4(off + 4 * i, src + 4 * i, x[r], y2[r]);
+                            *reinterpret_cast<float4 *>(&tile[sidx0 + r * RSTRIDE]) = y;
+                            *reinterpret_cast<float4 *>(&tile2[sidx0 + r * RSTRIDE]) = y2[r];
+                        }
+                        cnt += (y2[r].x != 0.f) + (y2[r].y != 0.f) + (y2[r].z != 0.f) + (y2[r].w != 0.f);
+                    }
+                };
+                if (sz == NP_TILE_MAX)
+                    stage(std::true_type{});
+                else
+                    stage(std::false_type{});
                 // survivors straight from the registers into the shared-memory stage s_out[buf] (any order: they are
                 // sorted next): one warp scan and one shared-memory atomic per warp and tile
                 const int lane = lane_id();
@@ -685,6 +698,11 @@ __global__ void __launch_bounds__(NP_THREADS, V::kSecondTree ? 3 : 4) np_tree_ke
                     if (y2s != 0.f) s_out[buf][atomicAdd(&s_cnt[buf], 1u)] = y2s;
                 }
             } else {
+#pragma unroll
+                for (int r = 0; r < NV; ++r) {  // all loads first: the in-place visitor's stores would otherwise fence them
+                    const int i = r * NP_THREADS + threadIdx.x;
+                    if (i < nvec) x[r] = v.load4(src + 4 * i);
+                }
 #pragma unroll
                 for (int r = 0; r < NV; ++r) {
                     const int i = r * NP_THREADS + threadIdx.x;
