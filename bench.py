@@ -49,6 +49,10 @@ def env_int(name, default):
 # clocks
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML in a background thread (two light
+    queries every 10 ms); an `nvidia-smi -lms` child process was measured to stall kernel launches for milliseconds
+    per query on some boxes, which showed up as idle gaps between the kernels of a step.  Falls back to nvidia-smi
+    when NVML is not importable."""
     QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -57,13 +61,54 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.samples = []  # (wall time, sm MHz, reasons bit mask)
+        self.max_mhz = None
+        self._stop = False
+
+    def _nvml_loop(self, nv, handle):
+        while not self._stop:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.samples.append((time.time(), float(mhz), int(reasons)))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        if os.environ.get("NNC_BENCH_NO_CLOCKS"):
+            return
+        try:
+            import threading
+
+            import pynvml as nv
+
+            nv.nvmlInit()
+            # NVML enumerates all GPUs of the box; CUDA_VISIBLE_DEVICES may remap the CUDA ordinal
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self._nv = nv
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "20"],
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -73,6 +118,27 @@ class ClockSampler:
         import datetime
 
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            nv = self._nv
+            names = (("hw_slowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                     ("hw_thermal_slowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                     ("sw_thermal_slowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                     ("sw_power_cap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))
+            sel = [s for s in self.samples if t_begin is None or (t_begin - 0.02 <= s[0] <= t_end + 0.02)]
+            reasons = set()
+            for _, _, mask in sel:
+                for nm, bit in names:
+                    if mask & bit:
+                        reasons.add(nm)
+            if sel:
+                out["sm_mhz"] = statistics.median(s[1] for s in sel)
+                out["samples"] = len(sel)
+            out["sm_max_mhz"] = self.max_mhz
+            out["reasons"] = sorted(reasons)
+            out["source"] = "nvml"
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -89,7 +155,7 @@ class ClockSampler:
                 try:
                     if t_begin is not None:
                         ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                        if ts < t_begin - 0.02 or ts > t_end + 0.02:
+                        if ts < t_begin - 0.05 or ts > t_end + 0.05:
                             continue
                     sm.append(float(f[1]))
                     out["sm_max_mhz"] = float(f[2])
@@ -105,6 +171,7 @@ class ClockSampler:
             out["sm_mhz"] = statistics.median(sm)
             out["samples"] = len(sm)
         out["reasons"] = sorted(reasons)
+        out["source"] = "nvidia-smi"
         return out
 
 
@@ -239,6 +306,7 @@ def run_b200(args):
     launches0 = ctx.total_launches()
     total_ms = 0.0
     n_iters = []
+    step_ms = []
     launches = 0
     ktimes = {}
     phases = {}
@@ -250,8 +318,10 @@ def run_b200(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(torch.cuda.current_stream())
         for i in range(cnt):
+            t_s = time.perf_counter()
             mask, km = step(bufs[i])
-            # accounting only (host side, after the call returned)
+            # accounting only (host side, after the call returned; every call ends with a stream synchronize)
+            step_ms.append(1e3 * (time.perf_counter() - t_s))
             n_iters.append(km.n_iter_)
             for kname, ms in km.profile.items():
                 if kname != "launches":
@@ -312,6 +382,7 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "clocks": clk,
         "n_iter": n_iters,
+        "ms_each_step_host_clock": [round(v, 3) for v in step_ms],
         "survivor_fraction": s_frac,
         "phase_ms_per_step": {kname: ms / K for kname, ms in sorted(phases.items())},
         "kernel_ms_per_step": {kname: v[1] for kname, v in sorted(warm_ktimes.items(), key=lambda kv: -kv[1][1])},

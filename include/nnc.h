@@ -132,7 +132,9 @@ int nnc_kmeans1d_f32(nnc_ctx *ctx, const float *w, int64_t n, const float *init,
  * (mask, codebook, packed codes, histogram): what Trainer._prune_parameters + Trainer.quantize do to one tensor
  * (trainer.py:177-193, :42-72).  A host tensor is copied to the device once; write_back == 0 skips copying the
  * pruned weights back to a HOST `w` (a device-resident `w` is always pruned in place).  Arguments as in
- * nnc_prune_f32 and nnc_kmeans1d_f32. */
+ * nnc_prune_f32 and nnc_kmeans1d_f32.  With std_smooth the k-means prologue of the pruned tensor (sklearn's centring
+ * mean, survivor compaction, min / max) rides on the pruning pass: two sweeps of the tensor before the clustering
+ * instead of three.  Results are bit-identical to nnc_prune_f32 followed by nnc_kmeans1d_f32. */
 int nnc_compress_f32(nnc_ctx *ctx, float *w, int64_t n, double threshold, int std_smooth, int threshold_mode, int write_back,
                      uint8_t *mask, double *thr_out, int64_t *n_pruned_out, const float *init, int k, int max_iter, double tol,
                      int flags, float *centers, float *centred, uint8_t *packed, int bits, int64_t *hist, nnc_kmeans_info *info);

@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(1024) kh_hist_kernel(const uint32_t *__restric
         for (int j = 0; j < tiles_b; ++j) {
             const int i = j * KH_HT + threadIdx.x;
             const uint32_t c = i < low_bins ? kh_bins[i] : 0u;
-            if (c) Hb[i] = c;
+            if (i < low_bins) Hb[i] = c;  // every bin, zeros included: the bucket needs no clearing beforehand
             const int nzw = __popc(__ballot_sync(0xffffffffu, c != 0));
             if (lane_id() == 0 && nzw) atomicAdd(&s_tnz[j], (uint32_t)nzw);
         }
@@ -343,6 +343,15 @@ __global__ void __launch_bounds__(1024) kh_hist_kernel(const uint32_t *__restric
             if (c) atomicAdd(&Hb[i], c);
         }
     }
+}
+
+// clears the bins of the buckets that are NOT written in full by one work item (empty ones, and the ones merged with
+// atomics) -- a fraction of the 4 B/bin a memset of all of H would cost
+__global__ void __launch_bounds__(1024) kh_zero_kernel(uint32_t *__restrict__ H, const uint32_t *__restrict__ item_off) {
+    const int b = blockIdx.x;
+    if (item_off[b + 1] - item_off[b] == 1) return;
+    uint4 *p = reinterpret_cast<uint4 *>(H + ((size_t)b << KH_LOW));
+    for (int i = threadIdx.x; i < KH_BINS / 4; i += 1024) p[i] = make_uint4(0, 0, 0, 0);
 }
 
 // ---- compact: non-empty bins -> (value, count) entries ---------------------------------------------------------
@@ -441,7 +450,7 @@ SortedRuns hist_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n, uint32
         configured = true;
     }
     uint32_t *H = arena_alloc_t<uint32_t>(ctx, std::max<size_t>(n_bins, KH_HT));
-    NNC_CUDA(cudaMemsetAsync(H, 0, sizeof(uint32_t) * std::max<size_t>(n_bins, KH_HT), ctx->stream));
+    if (hb == 0) NNC_CUDA(cudaMemsetAsync(H, 0, sizeof(uint32_t) * std::max<size_t>(n_bins, KH_HT), ctx->stream));
     unsigned long long *bucket_off = arena_alloc_t<unsigned long long>(ctx, (size_t)nb + 1);
     uint32_t *item_off = arena_alloc_t<uint32_t>(ctx, (size_t)nb + 1);
     const uint32_t *a = reinterpret_cast<const uint32_t *>(d_a);
@@ -465,6 +474,7 @@ SortedRuns hist_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n, uint32
         NNC_LAUNCH(ctx, kh_base_kernel, 1, 1024, 0, tot, nb, bucket_off, item_off);
         NNC_LAUNCH(ctx, kh_scatter_kernel, chunks, KH_THREADS, KH_TILE * 8 + nb * 20, a, b, n, tiles_per_chunk, nb, km, bucket_off,
                    crel_lo, crel_hi);
+        NNC_LAUNCH(ctx, kh_zero_kernel, nb, 1024, 0, H, item_off);
         NNC_LAUNCH(ctx, kh_hist_kernel<false>, max_items, 1024, low_bins * 4, b, nb, low_bins, km, bucket_off, item_off, H, tnz);
     } else {
         const unsigned long long h_off[2] = {0ull, (unsigned long long)n};

@@ -20,6 +20,7 @@
 //   update  (1 CTA)   per-cluster counts and sums (SAFE regions via prefix differences + zone partials +
 //                     the zero run), empty-cluster relocation, averages, centre shift, convergence test
 // Per-cluster sums are exact integers, so the result does not depend on reduction order or sharding.
+#include <stddef.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -1218,9 +1219,12 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
     NNC_LAUNCH(ctx, ll_init_kernel, 1, TB_KMAX, 0, st, d_init);
     prof_mark(ctx, "lloyd_prep");
 
-    struct Ctl {
+    struct Ctl {  // mirrors LloydDevice from `iter` on: one read-back brings the loop's outcome and the barrier bail-out flag
         int iter, done, strict, n_reloc, n_iter, pad;
+        unsigned int gbar;
+        int gbail;
     } ctl;
+    static_assert(offsetof(LloydDevice, gbail) - offsetof(LloydDevice, iter) == offsetof(Ctl, gbail), "Ctl mirrors LloydDevice");
     const int search_grid = std::max(1, std::min(ctx->sm_count * 2, (2 * k + 7) / 8));
     const int zone_grid = ctx->sm_count * 2;
     const bool peer = world > 1 && ctx->peer_enabled && 2 * k <= PEER_WORDS;
@@ -1278,11 +1282,7 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
             if (ctl.done || launched >= max_iter) break;
         }
     }
-    if (one_launch) {
-        int bail = 0;
-        NNC_CUDA(cudaMemcpy(&bail, &st->gbail, sizeof(int), cudaMemcpyDeviceToHost));
-        if (bail) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: the grid barrier of the loop kernel timed out (iter %d)", ctl.iter);
-    }
+    if (one_launch && ctl.gbail) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: the grid barrier of the loop kernel timed out (iter %d)", ctl.iter);
     if (!ctl.done) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: loop ended without a stop decision (iter %d)", ctl.iter);
     if (world > 1 && ctx->peer_enabled) {
         int comm_error = 0;
