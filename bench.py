@@ -296,7 +296,10 @@ def run_b200(args):
             refill(min(pool, W - i))
         if i == W - 1:
             ctx.set_kernel_timing(True)
-        step(bufs[i % pool])
+        # same binding pattern as the timed loop: the previous step's outputs stay alive during the next call, so the
+        # torch caching allocator holds two sets of output buffers before the timing starts (a first-time cudaMalloc of
+        # the second set used to land in the second timed step: +10..30 ms)
+        mask, km = step(bufs[i % pool])
     warm_ktimes = {name: [c, ms] for name, (c, ms) in ctx.last_kernel_times().items()}
     hbm = {name: v for name, v in warm_ktimes.items() if kernel_bytes(name, 1.0, 0.3) > 0}  # streaming kernels only
     dom_name = max(hbm.items(), key=lambda kv: kv[1][1])[0] if hbm else None
