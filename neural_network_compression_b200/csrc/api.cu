@@ -21,6 +21,11 @@ namespace nnc {
 
 static thread_local char g_err[512] = "";
 
+bool debug_sync() {
+    static const bool on = getenv("NNC_DEBUG_SYNC") != nullptr;
+    return on;
+}
+
 void set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

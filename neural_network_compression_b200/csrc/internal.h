@@ -18,6 +18,7 @@ struct NcclUniqueIdBytes {  // ncclUniqueId (nccl.h: 128 opaque bytes), passed b
 namespace nnc {
 
 void set_error(const char *fmt, ...);
+bool debug_sync();  // NNC_DEBUG_SYNC: synchronize and check after every kernel launch (fault localisation)
 
 struct Error {
     int code;
@@ -166,6 +167,10 @@ void klaunch_end(nnc_ctx *ctx);
         (ctx)->launches++;                                              \
         if (_kt) nnc::klaunch_end((ctx));                               \
         NNC_CUDA(cudaGetLastError());                                   \
+        if (nnc::debug_sync()) {                                        \
+            cudaError_t _se = cudaStreamSynchronize((ctx)->stream);     \
+            if (_se != cudaSuccess) NNC_FAIL(NNC_ERR_CUDA, "kernel %s failed: %s", #kernel, cudaGetErrorString(_se)); \
+        }                                                               \
     } while (0)
 
 // the same with an explicit name for the per-kernel timing (template kernels: one name per instantiation)

@@ -519,7 +519,6 @@ struct UpdateSmem {
     int red_i[32], red_id[32];
     uint32_t rk_d2[32], rk_gap[32], rk_ord[32];
     int rk_who[32];
-    long long red_w[32];
     int n_empty, zdi, same, winner, stop_reloc;  // stop_reloc: scratch of the convergence step
     long long zero_left;
     long long rpos[2 * TB_KMAX + 2];  // copy of the region positions for the relocation cursors (label_at)
@@ -764,22 +763,17 @@ __device__ void update_phase(LloydDevice *st, const float *__restrict__ ks, int 
                 U.rk_who[warp_id()] = owner;
             }
             __syncthreads();
-            if (tid < 32) {  // warp 0 folds the 32 warp winners (same order relation: a total order, so any tree gives the same winner)
-                best = FarKey{U.rk_d2[tid], U.rk_gap[tid], U.rk_ord[tid]};
-                owner = U.rk_who[tid];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    FarKey ob;
-                    ob.d2 = __shfl_xor_sync(0xffffffffu, best.d2, o);
-                    ob.gap = __shfl_xor_sync(0xffffffffu, best.gap, o);
-                    ob.ordx = __shfl_xor_sync(0xffffffffu, best.ordx, o);
-                    int oo = __shfl_xor_sync(0xffffffffu, owner, o);
+            if (tid == 0) {  // fold of the warp winners: only the first ceil(m / 32) warps own streams
+                const int nw = (m + 31) >> 5;
+                for (int w = 1; w < nw; ++w) {
+                    FarKey ob{U.rk_d2[w], U.rk_gap[w], U.rk_ord[w]};
+                    int oo = U.rk_who[w];
                     if (oo >= 0 && (owner < 0 || far_before(ob, best) || (!far_before(best, ob) && oo < owner))) {
                         best = ob;
                         owner = oo;
                     }
                 }
-                if (tid == 0) U.winner = owner;
+                U.winner = owner;
             }
             __syncthreads();
             if (U.winner < 0) break;  // this rank has no sample left
@@ -905,37 +899,14 @@ __device__ void update_phase(LloydDevice *st, const float *__restrict__ ks, int 
     // ---- 6. averages (_average_centers), shift (_center_shift)
     if (tid < k) U.raw[tid] = (float)__ddiv_rn((double)U.S[tid], scale);
     __syncthreads();
-    {   // argmax of the counts, lowest id on ties (np.argmax): block reduction
-        long long bw = tid < k ? U.W[tid] : -1;
-        int bi = tid < k ? tid : 0x7fffffff;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const long long ow = __shfl_xor_sync(0xffffffffu, bw, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ow > bw || (ow == bw && oi < bi)) {
-                bw = ow;
-                bi = oi;
-            }
-        }
-        if (lane_id() == 0) {
-            U.red_w[warp_id()] = bw;
-            U.red_i[warp_id()] = bi;
-        }
-        __syncthreads();
-        if (tid < 32) {
-            bw = U.red_w[tid];
-            bi = U.red_i[tid];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const long long ow = __shfl_xor_sync(0xffffffffu, bw, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ow > bw || (ow == bw && oi < bi)) {
-                    bw = ow;
-                    bi = oi;
-                }
-            }
-            if (tid == 0) U.winner = bi;
-        }
+    // argmax of the counts, lowest id on ties (np.argmax).  One thread, on purpose: a block reduction of (count, id)
+    // pairs with long long shuffles here made the per-phase kernels (ll_update_kernel) fault with "misaligned address"
+    // on sm_100a while the identical code inside ll_loop_kernel ran -- not understood, so the plain loop stays.
+    if (tid == 0) {
+        int amax = 0;
+        for (int j = 1; j < k; ++j)
+            if (U.W[j] > U.W[amax]) amax = j;
+        U.winner = amax;
     }
     __syncthreads();
     if (tid < k) {
@@ -986,11 +957,11 @@ __device__ void update_phase(LloydDevice *st, const float *__restrict__ ks, int 
         }
     }
 }
-__global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, const float *__restrict__ ks, int phase_lo,
-                                                               int phase_hi, PeerComm pc) {
+template <int PHASE_LO, int PHASE_HI>
+__global__ void __launch_bounds__(TB_THREADS) ll_update_kernel(LloydDevice *st, const float *__restrict__ ks, PeerComm pc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (st->done) return;
-    update_phase(st, ks, phase_lo, phase_hi, pc, *reinterpret_cast<UpdateSmem *>(smem_raw));
+    update_phase(st, ks, PHASE_LO, PHASE_HI, pc, *reinterpret_cast<UpdateSmem *>(smem_raw));
 }
 
 // ---- final labelling histogram ---------------------------------------------------------------------
@@ -1157,7 +1128,10 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
     if (k < 1 || k > TB_KMAX) NNC_FAIL(NNC_ERR_UNSUPPORTED, "k-means: k = %d outside [1, %d]", k, TB_KMAX);
     static bool configured = false;
     if (!configured) {
-        NNC_CUDA(cudaFuncSetAttribute(ll_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateSmem)));
+        NNC_CUDA(cudaFuncSetAttribute(ll_update_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateSmem)));
+        NNC_CUDA(cudaFuncSetAttribute(ll_update_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateSmem)));
+        NNC_CUDA(cudaFuncSetAttribute(ll_update_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateSmem)));
+        NNC_CUDA(cudaFuncSetAttribute(ll_update_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateSmem)));
         NNC_CUDA(cudaFuncSetAttribute(ll_zone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZoneSmem)));
         configured = true;
     }
@@ -1228,7 +1202,10 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
     const int search_grid = std::max(1, std::min(ctx->sm_count * 2, (2 * k + 7) / 8));
     const int zone_grid = ctx->sm_count * 2;
     const bool peer = world > 1 && ctx->peer_enabled && 2 * k <= PEER_WORDS;
-    const bool one_launch = (world == 1 || peer) && !getenv("NNC_LLOYD_MULTI_LAUNCH");
+    // NNC_LLOYD_MULTI_LAUNCH: one launch per phase (the path taken when no peer mailbox is available);
+    // NNC_LLOYD_SPLIT: additionally the update in its three launches with the all-reduces in between (no-ops on one rank)
+    const bool split_update = getenv("NNC_LLOYD_SPLIT") != nullptr;
+    const bool one_launch = (world == 1 || peer) && !getenv("NNC_LLOYD_MULTI_LAUNCH") && !split_update;
     PeerComm pc;
     memset(&pc, 0, sizeof(pc));
     if (peer) {
@@ -1266,15 +1243,15 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
                 NNC_LAUNCH(ctx, ll_table_kernel, 1, TB_THREADS, 0, st);
                 NNC_LAUNCH(ctx, ll_search_kernel, search_grid, 256, 0, st, h.d_sorted, samp, ptile);
                 NNC_LAUNCH(ctx, ll_zone_kernel, zone_grid, 256, sizeof(ZoneSmem), st, h.d_sorted);
-                if (world == 1 || peer) {
-                    NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 0, 2, pc);
+                if ((world == 1 || peer) && !split_update) {
+                    NNC_LAUNCH(ctx, (ll_update_kernel<0, 2>), 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, pc);
                 } else {
                     // exact integer partials: the sums are identical on every rank and for every rank count
-                    NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 0, 0, pc);
+                    NNC_LAUNCH(ctx, (ll_update_kernel<0, 0>), 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, pc);
                     comm_allreduce(ctx, reinterpret_cast<int64_t *>(st->gW), 2 * TB_KMAX, 0);  // gW, gS
-                    NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 1, 1, pc);
+                    NNC_LAUNCH(ctx, (ll_update_kernel<1, 1>), 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, pc);
                     comm_allreduce(ctx, reinterpret_cast<int64_t *>(hs.cand), world * k * 2, 0);  // all-gather by sum
-                    NNC_LAUNCH(ctx, ll_update_kernel, 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, 2, 2, pc);
+                    NNC_LAUNCH(ctx, (ll_update_kernel<2, 2>), 1, TB_THREADS, sizeof(UpdateSmem), st, h.d_sorted, pc);
                 }
             }
             NNC_CUDA(cudaMemcpyAsync(&ctl, &st->iter, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));

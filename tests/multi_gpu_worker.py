@@ -40,31 +40,42 @@ def main():
         mine = full[b:e].clone()
         mask, km = U.compress_weight(mine, 1.0, True, bits, "linear")
         ok = True
-        ok &= U.prune_weigth.last_threshold == ref_thr
-        ok &= bool(torch.equal(mask, ref_mask[b:e])) and bool(torch.equal(mine, ref_w[b:e]))
-        ok &= km.cluster_centers_.tobytes() == ref_km.cluster_centers_.tobytes()
-        ok &= km.n_iter_ == ref_km.n_iter_ and km.n_relocations == ref_km.n_relocations
-        ok &= bool(np.array_equal(km.code_histogram, ref_km.code_histogram))
+        bad = []
+
+        def check(name, cond):
+            nonlocal ok
+            if not cond:
+                bad.append(name)
+                ok = False
+
+        check("thr", U.prune_weigth.last_threshold == ref_thr)
+        check("mask", bool(torch.equal(mask, ref_mask[b:e])) and bool(torch.equal(mine, ref_w[b:e])))
+        check("mean %r %r" % (km.mean, ref_km.mean), km.mean == ref_km.mean)
+        check("n_nonzero %r %r" % (km.n_nonzero, ref_km.n_nonzero), km.n_nonzero == ref_km.n_nonzero)
+        check("centers", km.cluster_centers_.tobytes() == ref_km.cluster_centers_.tobytes())
+        check("iters %r %r" % ((km.n_iter_, km.n_relocations), (ref_km.n_iter_, ref_km.n_relocations)),
+              km.n_iter_ == ref_km.n_iter_ and km.n_relocations == ref_km.n_relocations)
+        check("hist", bool(np.array_equal(km.code_histogram, ref_km.code_histogram)))
         per = km.code_bits
         if (b * per) % 8 == 0:
-            ok &= bool(torch.equal(km.packed_codes, ref_km.packed_codes[b * per // 8: (e * per + 7) // 8]))
+            check("packed", bool(torch.equal(km.packed_codes, ref_km.packed_codes[b * per // 8: (e * per + 7) // 8])))
         # the reference-signature helper on the shard: labels / ris of the slice, inertia global
         ris, km2 = U.get_quantized_weight(mine, bits, "linear")
-        ok &= bool(torch.equal(km2.labels_, ref_full_km.labels_[b:e])) and bool(torch.equal(ris, ref_ris[b:e]))
-        ok &= km2.inertia_ == ref_full_km.inertia_
+        check("labels2", bool(torch.equal(km2.labels_, ref_full_km.labels_[b:e])) and bool(torch.equal(ris, ref_ris[b:e])))
+        check("inertia2", km2.inertia_ == ref_full_km.inertia_)
         # trained-quantization gradient sum over the shards == over the whole tensor (same grid-independent tolerance)
         gg = torch.empty(n, device="cuda").normal_(0.0, 1e-3, generator=g)
         gs = U.cluster_gradient_sum(gg[b:e].clone(), km2.labels_, km2.n_clusters)
         full_sum = torch.zeros(km2.n_clusters, dtype=torch.float64, device="cuda").index_add_(0, ref_full_km.labels_.long(), gg.double())
         mag = torch.zeros(km2.n_clusters, dtype=torch.float64, device="cuda").index_add_(0, ref_full_km.labels_.long(), gg.double().abs())
-        ok &= bool(np.all(np.abs(gs - full_sum.cpu().numpy()) <= 1e-13 * mag.cpu().numpy() + 1e-300))
+        check("gradsum", bool(np.all(np.abs(gs - full_sum.cpu().numpy()) <= 1e-13 * mag.cpu().numpy() + 1e-300)))
         # np.std of the sharded tensor
         m, v, s = U.weight_stats(full[b:e].clone())
-        ok &= (m, v, s) == tuple(np.float32(x) for x in (np.mean(full.cpu().numpy()), np.var(full.cpu().numpy()), np.std(full.cpu().numpy())))
+        check("stats", (m, v, s) == tuple(np.float32(x) for x in (np.mean(full.cpu().numpy()), np.var(full.cpu().numpy()), np.std(full.cpu().numpy()))))
         if not ok:
             failures.append((bits, rank))
         print("rank %d bits %d iters %d reloc %d thr %.9g peer_exchange=%s %s" % (rank, bits, km.n_iter_, km.n_relocations, ref_thr,
-                                                                                    dctx.peer_exchange, "OK" if ok else "MISMATCH"), flush=True)
+                                                                                    dctx.peer_exchange, "OK" if ok else "MISMATCH " + "; ".join(bad)), flush=True)
     t = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(t)
     dist.destroy_process_group()

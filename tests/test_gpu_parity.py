@@ -333,6 +333,25 @@ def test_kmeans_hist_path_equals_radix_path(U, monkeypatch):
     assert out["radix"] == out["hist"]
 
 
+@pytest.mark.parametrize("env", ["NNC_LLOYD_MULTI_LAUNCH", "NNC_LLOYD_SPLIT"])
+@pytest.mark.parametrize("bits,mode", [(4, "linear"), (8, "linear"), (5, "forgy")])
+def test_kmeans_per_phase_launch_paths(U, monkeypatch, env, bits, mode):
+    # the Lloyd loop as one launch per phase / with the update split in its three launches (the multi-rank path without a
+    # peer mailbox: all-reduces between the launches, no-ops on one rank) gives the same fit as the one-launch loop
+    w = D.gaussian(300 * 1000, seed=5)
+    w[::9] = 0.0
+    O.prune_weigth(w, 1)
+    np.random.seed(3)
+    ris0, km0 = U.get_quantized_weight(w, bits, mode)
+    monkeypatch.setenv(env, "1")
+    np.random.seed(3)
+    ris1, km1 = U.get_quantized_weight(w, bits, mode)
+    assert km1.n_iter_ == km0.n_iter_ and km1.n_relocations == km0.n_relocations
+    assert km1.cluster_centers_.tobytes() == km0.cluster_centers_.tobytes()
+    assert ris1.tobytes() == ris0.tobytes() and np.array_equal(km1.code_histogram, km0.code_histogram)
+    assert km1.inertia_ == km0.inertia_
+
+
 def test_kmeans_errors(U):
     w = D.gaussian(1000, seed=2)
     with pytest.raises(Exception, match="error mode not found"):
