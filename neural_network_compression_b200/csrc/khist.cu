@@ -35,7 +35,7 @@ constexpr int KH_MAX_HB = 12;             // high digit: at most 4096 buckets (k
 constexpr int KH_THREADS = 512;
 constexpr int KH_ITEMS = 16;
 constexpr int KH_TILE = KH_THREADS * KH_ITEMS;  // 8192 keys per scatter tile
-constexpr int KH_CHUNK = 1 << 18;               // keys per work item of the histogram kernel
+constexpr int KH_CHUNK = 1 << 20;               // keys per work item of the histogram kernel (a pruned Gaussian layer at 2^30: ~260 K keys per bucket, one item each)
 constexpr int KH_HT = 1024;                     // bins per compaction tile
 
 struct KhKeyMap {  // same rank image as sort.cu's RsKeyMap
@@ -313,14 +313,35 @@ __global__ void __launch_bounds__(1024) kh_hist_kernel(const uint32_t *__restric
     if (threadIdx.x < head) one(p[threadIdx.x]);
     const unsigned long long nvec = (cnt - head) >> 2;
     const uint32_t *pv = p + head;
-    for (unsigned long long i = threadIdx.x; i < nvec; i += 1024) {
+    unsigned long long i = threadIdx.x;
+    for (; i + 3 * 1024 < nvec; i += 4 * 1024) {  // four 16-byte loads in flight per thread (one CTA per SM: 64 KB in flight)
+        const uint4 v0 = ld_stream_u4(pv + 4 * i), v1 = ld_stream_u4(pv + 4 * (i + 1024));
+        const uint4 v2 = ld_stream_u4(pv + 4 * (i + 2048)), v3 = ld_stream_u4(pv + 4 * (i + 3072));
+        one(v0.x);
+        one(v0.y);
+        one(v0.z);
+        one(v0.w);
+        one(v1.x);
+        one(v1.y);
+        one(v1.z);
+        one(v1.w);
+        one(v2.x);
+        one(v2.y);
+        one(v2.z);
+        one(v2.w);
+        one(v3.x);
+        one(v3.y);
+        one(v3.z);
+        one(v3.w);
+    }
+    for (; i < nvec; i += 1024) {
         const uint4 v = ld_stream_u4(pv + 4 * i);
         one(v.x);
         one(v.y);
         one(v.z);
         one(v.w);
     }
-    for (unsigned long long i = head + (nvec << 2) + threadIdx.x; i < cnt; i += 1024) one(p[i]);
+    for (unsigned long long j = head + (nvec << 2) + threadIdx.x; j < cnt; j += 1024) one(p[j]);
     __syncthreads();
     uint32_t *Hb = H + ((size_t)b << KH_LOW);
     if (items_b == 1) {
