@@ -410,8 +410,8 @@ def run_b200(args):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` captures on this workload
 # (2^30 weights, 1 GPU; profiles/r1_summary.md)
 NCU_TRAFFIC = {
-    "np_tree_kernel<VisitApplyQuant>": [11.01e9, "profiles/r1_summary.md section 3 (gpurun_out/prof_r1_fused.ncu-rep)"],
-    "kh_scatter_kernel": [3.84e9, "profiles/r1_summary.md section 3 (gpurun_out/prof_r1_kh.ncu-rep)"],
+    "np_tree_kernel<VisitApplyQuant>": [11.01e9, "profiles/r1_summary.md section 3 (ncu --set full capture prof_r1_final.ncu-rep: dram__bytes_read.sum 4.333 GB + dram__bytes_write.sum 6.674 GB)"],
+    "kh_scatter_kernel": [3.84e9, "profiles/r1_summary.md section 3 (prof_r1_final.ncu-rep: 1.962 GB read + 1.880 GB written)"],
     "(rs_scatter_kernel<A, B>)": [3.135e9, "profiles/r1_summary.md (gpurun_out/prof_r1_scatter.ncu-rep)"],
 }
 
