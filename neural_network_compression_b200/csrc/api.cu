@@ -108,6 +108,20 @@ bool is_device_ptr(const void *p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+void func_dyn_smem(nnc_ctx *ctx, const void *fn, size_t bytes) {
+    if (bytes <= 48 * 1024) return;  // the default limit already covers it
+    for (auto &e : ctx->func_smem) {
+        if (e.first == fn) {
+            if (e.second >= bytes) return;
+            NNC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            e.second = bytes;
+            return;
+        }
+    }
+    NNC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    ctx->func_smem.emplace_back(fn, bytes);
+}
+
 Staged stage_in(nnc_ctx *ctx, const void *p, size_t bytes) {
     Staged s;
     s.bytes = bytes;

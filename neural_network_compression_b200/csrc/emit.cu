@@ -327,12 +327,7 @@ __global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__rest
 template <bool VEC, bool INERTIA, int BITS>
 static void emit_launch(nnc_ctx *ctx, int grid, const float *d_w, int64_t n, EmitDevice *ed, float mean, double inertia_scale,
                         int32_t *d_labels, float *d_ris, uint8_t *d_packed, int bits, int want_hist) {
-    static bool configured = false;
-    if (!configured) {
-        NNC_CUDA(cudaFuncSetAttribute(emit_kernel<VEC, INERTIA, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(EmitSmem)));
-        configured = true;
-    }
+    func_dyn_smem(ctx, (const void *)emit_kernel<VEC, INERTIA, BITS>, sizeof(EmitSmem));
     NNC_LAUNCH(ctx, (emit_kernel<VEC, INERTIA, BITS>), grid, EM_THREADS, sizeof(EmitSmem), d_w, n, ed, mean, inertia_scale,
                d_labels, d_ris, d_packed, bits, want_hist);
 }

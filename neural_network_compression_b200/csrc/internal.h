@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/nnc.h"
@@ -125,6 +126,8 @@ struct nnc_ctx {
     unsigned long long peer_seq = 0;
     nnc_allreduce_i64_fn allreduce = nullptr;
     void *allreduce_user = nullptr;
+    // kernels whose dynamic shared-memory limit has been raised ON THIS CONTEXT'S DEVICE (the attribute is per device)
+    std::vector<std::pair<const void *, size_t>> func_smem;
 };
 
 namespace nnc {
@@ -139,6 +142,11 @@ T *arena_alloc_t(nnc_ctx *ctx, size_t count) {
 }
 
 bool is_device_ptr(const void *p);
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize >= bytes for `fn` on the context's device; set once per context (and again
+// when a larger size is asked for).  The attribute is per DEVICE: a process-wide flag would leave the kernels of a second
+// GPU at the 48 KB default.
+void func_dyn_smem(nnc_ctx *ctx, const void *fn, size_t bytes);
 
 // Stages a caller buffer: device pointers pass through, host pointers get an arena copy.
 struct Staged {

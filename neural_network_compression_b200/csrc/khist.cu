@@ -462,14 +462,9 @@ SortedRuns hist_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n, uint32
     const int nb = 1 << hb;
     const int low_bins = 1 << std::min(keybits, KH_LOW);
     const size_t n_bins = (size_t)1 << keybits;
-    static bool configured = false;
-    if (!configured) {
-        NNC_CUDA(cudaFuncSetAttribute(kh_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KH_BINS * 4));
-        NNC_CUDA(cudaFuncSetAttribute(kh_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KH_BINS * 4));
-        NNC_CUDA(cudaFuncSetAttribute(kh_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      KH_TILE * 8 + (1 << KH_MAX_HB) * 20));
-        configured = true;
-    }
+    func_dyn_smem(ctx, (const void *)kh_hist_kernel<true>, KH_BINS * 4);
+    func_dyn_smem(ctx, (const void *)kh_hist_kernel<false>, KH_BINS * 4);
+    func_dyn_smem(ctx, (const void *)kh_scatter_kernel, KH_TILE * 8 + (1 << KH_MAX_HB) * 20);
     uint32_t *H = arena_alloc_t<uint32_t>(ctx, std::max<size_t>(n_bins, KH_HT));
     if (hb == 0) NNC_CUDA(cudaMemsetAsync(H, 0, sizeof(uint32_t) * std::max<size_t>(n_bins, KH_HT), ctx->stream));
     unsigned long long *bucket_off = arena_alloc_t<unsigned long long>(ctx, (size_t)nb + 1);

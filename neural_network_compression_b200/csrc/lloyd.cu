@@ -25,67 +25,9 @@
 
 #include <algorithm>
 
-#include "common.cuh"
-#include "internal.h"
-#include "peer.cuh"
-#include "table.cuh"
+#include "lloyd_shared.cuh"
 
 namespace nnc {
-
-constexpr int LL_TS = 512;   // sorted-array tile (one round of 16 loads per lane in the boundary search)
-constexpr int LL_TOP = 2048; // entries of the shared-memory top level of the tile-sample index (loop kernel)
-constexpr int LL_LOG = 304;  // per-iteration diagnostics kept for the first LL_LOG iterations
-
-__host__ __device__ __forceinline__ long long llmin2(long long a, long long b) { return a < b ? a : b; }
-__host__ __device__ __forceinline__ long long llmax2(long long a, long long b) { return a > b ? a : b; }
-
-struct LloydHeader {
-    int k, max_iter, fixed_exp, pad0;
-    int rank, world;
-    unsigned long long *cand;  // relocation candidates [world][k][2] (see ll_update_kernel phase 1)
-    long long n, n_nz, n0, n_tiles;  // n_nz: surviving ELEMENTS of this shard (sum of the entry counts)
-    long long n_ent;                 // entries of the sorted array (= n_nz when every entry counts once)
-    const unsigned int *cnt;         // multiplicity of every entry (nullptr: all ones)
-    const long long *ctile;          // exclusive prefix of the entry counts at tile granularity (with cnt only)
-    float mean, tol, xabs_max, pad1;
-    double scale, tol_rel;
-};
-struct LloydDevice : LloydHeader {
-    // exact moments of q over all n samples (for the tolerance)
-    long long s1;
-    unsigned long long s2_lo, s2_hi;
-    long long total_q;  // sum of q over the sorted survivors
-    // centroids (centred space) by cluster id
-    float c[TB_KMAX];
-    float c_emit[TB_KMAX];
-    float c_save[TB_KMAX];
-    long long hist[TB_KMAX];  // code histogram of the final labelling (ll_count_kernel)
-    RegionTable tab;
-    int perm[TB_KMAX];                // sorted order of the centroids at the previous table build
-    long long rpos[2 * TB_KMAX + 2];  // entries before every region boundary
-    long long rcnt[2 * TB_KMAX + 2];  // elements before every region boundary (= rpos without multiplicities)
-    long long rsum[2 * TB_KMAX + 2];
-    // zone partials per distinct index
-    long long zW[TB_KMAX], zS[TB_KMAX], zmin[TB_KMAX], zmax[TB_KMAX];
-    // per-id partials (pre-relocation) of the previous iteration: label-equality proxy
-    long long Wprev[TB_KMAX], Sprev[TB_KMAX];
-    // state handed between the phases of the update kernel when they run as separate launches (multi-GPU: the
-    // per-cluster partials and the relocation candidates are all-reduced between the phases)
-    long long gW[TB_KMAX], gS[TB_KMAX];        // per distinct index: count, fixed-point sum (contiguous: one all-reduce)
-    long long gfirst[TB_KMAX], glast[TB_KMAX]; // local member cursors per distinct index
-    long long idW[TB_KMAX], idS[TB_KMAX];      // per cluster id, before relocation
-    int empt_s[TB_KMAX];
-    int zdi_s, n_empty_s, same_s, comm_error;
-    long long xbuf[2 * TB_KMAX];  // staging of the in-kernel peer exchange
-    // control
-    int iter, done, strict, n_reloc, n_iter, pad2;
-    unsigned int gbar;  // arrival counter of the grid barrier (ll_loop_kernel)
-    int gbail;          // a CTA gave up waiting at the grid barrier
-    // per-iteration log (diagnostics): zone elements, zone groups, distinct centroids, empty clusters
-    long long logZ[LL_LOG];
-    int logG[LL_LOG], logM[LL_LOG], logE[LL_LOG];
-    unsigned int logT[LL_LOG][4];  // loop kernel: ns spent in search / zone / update / table (+ their barriers) per iteration
-};
 
 // ---------------------------------------------------------------------------------------------
 // prep: per-tile sums of q, samples, moments
@@ -200,107 +142,6 @@ __global__ void __launch_bounds__(TB_THREADS) ll_table_kernel(LloydDevice *st) {
     table_phase(st, S);
 }
 
-// entries / elements of the sorted survivors with fl(x - mean) < t, and the sum of q over them; one warp per boundary.
-// top (optional, shared memory): top[i] = samp[i * top_step], i < top_n -- the first, coarse level of the search without a
-// trip to L2.
-struct SearchConst {  // per-launch constants of the search (hoisted out of the iterations by the loop kernel)
-    const float *ks;
-    const unsigned int *cnt;
-    const float *samp;
-    const long long *ptile, *ctile;
-    long long n_ent, n_tiles;
-    float mean;
-    double scale;
-    const float *top;
-    long long top_step;
-    int top_n;
-};
-
-__device__ __forceinline__ void warp_boundary_search(const SearchConst &C, float t, long long &pos_out, long long &cnt_out,
-                                                     long long &sum_out) {
-    const int lane = lane_id();
-    const float mean = C.mean;
-    long long lo = 0, hi = C.n_tiles;  // first tile whose first key fails the predicate lies in [lo, hi]
-    if (C.top) {  // coarse level: number of top samples that satisfy the predicate (they are a prefix)
-        int a = 0, b = C.top_n;  // first top index failing lies in [a, b]
-        while (a < b) {
-            const int span = b - a, step = (span + 31) >> 5;
-            const int cs = a + lane * step;
-            const int last = min(cs + step, b) - 1;
-            const bool p = cs < b ? (fsub(C.top[last], mean) < t) : false;
-            const int c = __popc(__ballot_sync(0xffffffffu, p));
-            const int na = min(a + c * step, b);
-            if (na >= b) {
-                a = b;
-                break;
-            }
-            b = min(na + step, b) - 1;
-            a = na;
-        }
-        // top samples 0 .. a-1 satisfy the predicate, sample a (if any) fails
-        if (a == 0) {
-            lo = 0;
-            hi = 0;
-        } else {
-            lo = (long long)(a - 1) * C.top_step + 1;  // tile (a-1)*step satisfies: the first failing tile is after it
-            hi = a < C.top_n ? (long long)a * C.top_step : C.n_tiles;
-        }
-    }
-    while (lo < hi) {
-        long long span = hi - lo;
-        long long step = (span + 31) >> 5;
-        long long cs = lo + (long long)lane * step;  // chunk start
-        bool inr = cs < hi;
-        long long last = llmin2(cs + step, hi) - 1;
-        bool p = inr ? (fsub(C.samp[last], mean) < t) : false;
-        unsigned b = __ballot_sync(0xffffffffu, p);
-        int c = __popc(b);
-        long long nlo = llmin2(lo + (long long)c * step, hi);
-        long long nhi = llmin2(nlo + step, hi) - 1;
-        if (nlo >= hi) {
-            lo = hi;
-            break;
-        }
-        lo = nlo;
-        hi = nhi;
-    }
-    if (lo == 0) {
-        pos_out = 0;
-        cnt_out = 0;
-        sum_out = 0;
-        return;
-    }
-    const long long tile = lo - 1;
-    const long long base = tile * LL_TS;
-    // the tile's prefixes and its entries: all loads in flight together
-    const long long psum = C.ptile[tile];
-    const long long pcnt = C.cnt ? C.ctile[tile] : 0;
-    long long npos = 0, acc = 0, cacc = 0;
-    constexpr int PER = LL_TS / 32;
-    float xv[PER];
-    unsigned int cv[PER];
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        const long long i = base + j * 32 + lane;
-        xv[j] = i < C.n_ent ? C.ks[i] : INFINITY;
-        cv[j] = (C.cnt && i < C.n_ent) ? C.cnt[i] : 1u;
-    }
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        const float xc = fsub(xv[j], mean);
-        const bool p = xc < t;  // padding is +inf: never counted
-        if (p) {
-            acc += fixed_q(xc, C.scale) * (long long)cv[j];
-            cacc += cv[j];
-        }
-        npos += __popc(__ballot_sync(0xffffffffu, p));
-    }
-    acc = warp_sum_ll(acc);
-    pos_out = base + npos;
-    cnt_out = C.cnt ? pcnt + warp_sum_ll(cacc) : pos_out;
-    sum_out = psum + acc;
-}
-
 __device__ __forceinline__ void search_phase(LloydDevice *st, const SearchConst &C) {
     const int nb = st->tab.R - 1;  // boundaries 1 .. R-1
     const int wpb = blockDim.x >> 5;
@@ -314,22 +155,6 @@ __device__ __forceinline__ void search_phase(LloydDevice *st, const SearchConst 
             st->rsum[r] = sum;
         }
     }
-}
-__device__ __forceinline__ SearchConst search_const(const LloydDevice *st, const float *ks, const float *samp, const long long *ptile) {
-    SearchConst C;
-    C.ks = ks;
-    C.cnt = st->cnt;
-    C.samp = samp;
-    C.ptile = ptile;
-    C.ctile = st->ctile;
-    C.n_ent = st->n_ent;
-    C.n_tiles = st->n_tiles;
-    C.mean = st->mean;
-    C.scale = st->scale;
-    C.top = nullptr;
-    C.top_step = 1;
-    C.top_n = 0;
-    return C;
 }
 __global__ void __launch_bounds__(256) ll_search_kernel(LloydDevice *st, const float *__restrict__ ks,
                                                         const float *__restrict__ samp,
@@ -450,47 +275,6 @@ __global__ void __launch_bounds__(256) ll_zone_kernel(LloydDevice *st, const flo
 }
 
 // ---- update ------------------------------------------------------------------------------------
-// NumPy pairwise sum of a small float32 array (numpy/_core/src/umath/loops_utils.h.src), single thread.
-__device__ float np_pairwise_small(const float *a, int n) {
-    if (n < 8) {
-        float r = 0.f;
-        for (int i = 0; i < n; ++i) r = fadd(r, a[i]);
-        return r;
-    }
-    if (n <= 128) {
-        float r[8];
-        for (int j = 0; j < 8; ++j) r[j] = a[j];
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8)
-            for (int j = 0; j < 8; ++j) r[j] = fadd(r[j], a[i + j]);
-        float res = fadd(fadd(fadd(r[0], r[1]), fadd(r[2], r[3])), fadd(fadd(r[4], r[5]), fadd(r[6], r[7])));
-        for (; i < n; ++i) res = fadd(res, a[i]);
-        return res;
-    }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return fadd(np_pairwise_small(a, n2), np_pairwise_small(a + n2, n - n2));
-}
-
-struct FarKey {  // priority of a relocation candidate: larger is farther
-    uint32_t d2, gap, ordx;
-};
-__device__ __forceinline__ bool far_before(const FarKey &a, const FarKey &b) {
-    if (a.d2 != b.d2) return a.d2 > b.d2;
-    if (a.gap != b.gap) return a.gap > b.gap;
-    return a.ordx > b.ordx;
-}
-__device__ __forceinline__ FarKey far_key(float xc, float c) {
-    float t = fsub(xc, c);
-    float d2 = fmul(t, t);
-    FarKey k;
-    k.d2 = __float_as_uint(d2);
-    uint32_t ox = f2ord(xc), oc = f2ord(c);
-    k.gap = ox > oc ? ox - oc : oc - ox;
-    k.ordx = ox;
-    return k;
-}
-
 // label (distinct index) of the sorted survivor at position p, from the region table + searched positions
 __device__ int label_at(const LloydDevice *st, const long long *rpos, const float *ks, long long p) {
     const RegionTable &T = st->tab;
@@ -1126,15 +910,11 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
                       float *h_centred_final, float *h_centred_emit, int64_t *h_hist) {
     const int k = h.k;
     if (k < 1 || k > TB_KMAX) NNC_FAIL(NNC_ERR_UNSUPPORTED, "k-means: k = %d outside [1, %d]", k, TB_KMAX);
-    static bool configured = false;
-    if (!configured) {
-        NNC_CUDA(cudaFuncSetAttribute(ll_update_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateSmem)));
-        NNC_CUDA(cudaFuncSetAttribute(ll_update_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateSmem)));
-        NNC_CUDA(cudaFuncSetAttribute(ll_update_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateSmem)));
-        NNC_CUDA(cudaFuncSetAttribute(ll_update_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateSmem)));
-        NNC_CUDA(cudaFuncSetAttribute(ll_zone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZoneSmem)));
-        configured = true;
-    }
+    func_dyn_smem(ctx, (const void *)ll_update_kernel<0, 2>, sizeof(UpdateSmem));
+    func_dyn_smem(ctx, (const void *)ll_update_kernel<0, 0>, sizeof(UpdateSmem));
+    func_dyn_smem(ctx, (const void *)ll_update_kernel<1, 1>, sizeof(UpdateSmem));
+    func_dyn_smem(ctx, (const void *)ll_update_kernel<2, 2>, sizeof(UpdateSmem));
+    func_dyn_smem(ctx, (const void *)ll_zone_kernel, sizeof(ZoneSmem));
     LloydDevice *st = arena_alloc_t<LloydDevice>(ctx, 1);
     h.d_state = st;
     const long long n_ent = h.d_cnt ? h.n_ent : h.n_nz;  // entries of the sorted array
@@ -1216,11 +996,7 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
     }
     bool hist_done = false;
     if (one_launch) {
-        static bool loop_configured = false;
-        if (!loop_configured) {
-            NNC_CUDA(cudaFuncSetAttribute(ll_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LoopSmem)));
-            loop_configured = true;
-        }
+        func_dyn_smem(ctx, (const void *)ll_loop_kernel, sizeof(LoopSmem));
         const float *ks_arg = h.d_sorted;
         const float *samp_arg = samp;
         const long long *ptile_arg = ptile;

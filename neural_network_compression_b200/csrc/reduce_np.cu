@@ -1171,13 +1171,7 @@ static NpTileDesc *run_tree(nnc_ctx *ctx, const float *d_w, V v, const FinArgs &
     if (ctx->world > 1) NNC_CUDA(cudaMemsetAsync(partials, 0, sizeof(float) * (2 * (size_t)p.num_tiles + 2), ctx->stream));
     const uint32_t t0 = ctx->sh.t0, t1 = ctx->sh.t1;
     const size_t dyn = (V::kCompact ? 2 * sizeof(float) * NP_TILE_MAX : 0) + (V::kSecondTree ? sizeof(float) * NP_TILE_SMEM : 0);
-    if (V::kCompact) {
-        static bool configured = false;
-        if (!configured) {
-            NNC_CUDA(cudaFuncSetAttribute(np_tree_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            configured = true;
-        }
-    }
+    if (V::kCompact) func_dyn_smem(ctx, (const void *)np_tree_kernel<V>, dyn);
     if (t1 > t0)
         NNC_LAUNCH_AS(ctx, V::kName, np_tree_kernel<V>, tree_grid(ctx, t1 - t0), NP_THREADS, dyn, d_w, t0, t1, ctx->sh.begin,
                    aligned16(d_w) ? 1 : 0, desc, partials, (const uint32_t *)nullptr, (const unsigned int *)nullptr, v);

@@ -224,14 +224,7 @@ void grad_segsum_device(nnc_ctx *ctx, const float *d_grad, const void *d_codes, 
     unsigned long long *bad = arena_alloc_t<unsigned long long>(ctx, 1);
     NNC_CUDA(cudaMemsetAsync(bad, 0, sizeof(unsigned long long), ctx->stream));
     const size_t smem = priv ? (8 + 8 * (size_t)SG_WARPS) * k : 16 * (size_t)k;
-    static size_t configured[2] = {0, 0};
-    if (smem > 48 * 1024 && smem > configured[priv]) {
-        if (priv)
-            NNC_CUDA(cudaFuncSetAttribute(segsum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else
-            NNC_CUDA(cudaFuncSetAttribute(segsum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[priv] = smem;
-    }
+    func_dyn_smem(ctx, priv ? (const void *)segsum_kernel<true> : (const void *)segsum_kernel<false>, smem);
     const int vec_ok = ((reinterpret_cast<uintptr_t>(d_grad) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_codes) & 15u) == 0) &&
                        (bits == 0 || bits == 4 || bits == 8 || bits == 16 || bits == 2 || bits == 1 || true);
     if (priv)

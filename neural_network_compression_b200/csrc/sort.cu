@@ -275,11 +275,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_scatter_kernel(const uint32_
 template <bool A, bool B>
 static void launch_scatter(nnc_ctx *ctx, int chunks, const uint32_t *in, uint32_t *out, int64_t n, int64_t tiles_per_chunk,
                            int shift, int width, RsKeyMap km, const unsigned long long *chunk_base) {
-    static bool configured = false;
-    if (!configured) {
-        NNC_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
-        configured = true;
-    }
+    func_dyn_smem(ctx, (const void *)rs_scatter_kernel<A, B>, sizeof(RsSmem));
     NNC_LAUNCH(ctx, (rs_scatter_kernel<A, B>), chunks, RS_THREADS, sizeof(RsSmem), in, out, n, tiles_per_chunk, shift, width, km,
                chunk_base);
 }

@@ -28,18 +28,20 @@ namespace nnc {
 constexpr int TB_KMAX = 1024;
 constexpr int TB_THREADS = 1024;
 
-struct RegionTable {
+template <int KM>
+struct RegionTableT {
     int k;   // clusters
     int m;   // distinct centroid values
     int R;   // regions = 2m - 1 (region r covers x' in [rstart[r], rstart[r+1]))
     int pad_;
-    float dv[TB_KMAX];      // distinct centroid values, ascending
-    float dcn[TB_KMAX];     // fl(dv * dv)
-    int down[TB_KMAX];      // owner id = lowest cluster id with that value
-    float rstart[2 * TB_KMAX + 2];  // rstart[0] = -inf, rstart[R] = +inf
-    short rJ2[2 * TB_KMAX + 2];     // candidates of region r: distinct indices rJ2[r] .. rJ1[r]
-    short rJ1[2 * TB_KMAX + 2];
+    float dv[KM];      // distinct centroid values, ascending
+    float dcn[KM];     // fl(dv * dv)
+    int down[KM];      // owner id = lowest cluster id with that value
+    float rstart[2 * KM + 2];  // rstart[0] = -inf, rstart[R] = +inf
+    short rJ2[2 * KM + 2];     // candidates of region r: distinct indices rJ2[r] .. rJ1[r]
+    short rJ1[2 * KM + 2];
 };
+using RegionTable = RegionTableT<TB_KMAX>;
 
 __device__ __forceinline__ float f32_nextup(float f) {
     if (f != f || f == INFINITY) return f;
@@ -171,24 +173,27 @@ __global__ void __launch_bounds__(1024) scan_chunk_apply_kernel(const TIn *__res
     }
 }
 
-struct TableScratch {
-    unsigned long long keys[TB_KMAX];
-    double a[TB_KMAX];
-    double b[TB_KMAX];
+template <int KM>
+struct TableScratchT {
+    unsigned long long keys[KM];
+    double a[KM];
+    double b[KM];
     double warp_d[32];
     int warp_i[32];
     float warp_f[32];
-    int flag[TB_KMAX];
-    float tlo[TB_KMAX];
-    float thi[TB_KMAX];
+    int flag[KM];
+    float tlo[KM];
+    float thi[KM];
 };
+using TableScratch = TableScratchT<TB_KMAX>;
 
 // Build the table for centroids c[0..k) (centred space).  Must be called by all TB_THREADS threads of a CTA.
 // xabs_max: max |x'| over the data.
 // perm (optional, k ints in global memory, zero-initialised): the sorted order of the previous call.  Centroids
 // rarely change their order between Lloyd iterations: when the previous order still sorts them the bitonic network
 // (36 barriers for 256 centroids) is skipped.
-static __device__ void build_region_table(const float *c, int k, float xabs_max, RegionTable *T, TableScratch &S, int *perm = nullptr) {
+template <class RT, class TS>
+static __device__ void build_region_table(const float *c, int k, float xabs_max, RT *T, TS &S, int *perm = nullptr) {
     const int tid = threadIdx.x;
     // ---- 1. sort (value, id)
     int P = 32;

@@ -91,4 +91,8 @@ def kmeans_cases(big=True):
         w = gaussian(2048 * 2048).reshape(2048, 2048)  # config 3 at a quarter of the size (oracle time)
         prune_np(w, 1.0)
         out.append(("c3_2048x2048_forgy5", w, 5, "forgy", 0))
+        # config 4 (the benchmark's own type) at 2^22 weights: N(0, 0.02^2), std-prune q = 1, 8-bit linear
+        w = gaussian(1 << 22, seed=2024)
+        prune_np(w, 1.0)
+        out.append(("c4_4m_linear8", w, 8, "linear", 0))
     return out
