@@ -176,45 +176,98 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------
-# CPU arms (oracle = test infrastructure; used here only as the timed baseline)
+# CPU arms.  Preferred: the library calls the reference's helpers make (NumPy for prune_weigth, utility.py:159-162;
+# scikit-learn's KMeans with the reference's arguments, utility.py:237-239) -- "reference".  Without an importable
+# scikit-learn: the C restatement under oracle/ (test infrastructure; used here only as the timed baseline) -- "port".
 # ---------------------------------------------------------------------------------------------------------
-def cpu_pipeline(n_sample, threads):
-    """prune + 8-bit linear k-means of an n_sample-weight tensor of the same distribution with the CPU
-    restatement of the reference (oracle/nnc_oracle.c).  Returns (seconds, n_iter)."""
+CPU_THREADS_CAP = 16  # the same thread count in every run of a round (BENCH and SCALE boxes differ in core count)
+
+
+def cpu_threads():
+    return max(1, min(CPU_THREADS_CAP, os.cpu_count() or 1))
+
+
+def cpu_tensor(n_sample):
+    return (np.random.RandomState(SEED).randn(n_sample) * SIGMA).astype(np.float32)
+
+
+def cpu_pipeline_sklearn(w, threads, bits=BITS, quality=QUALITY):
+    """The reference's own sequence of library calls on `w` (pruned in place).  Returns (seconds, n_iter)."""
+    import warnings
+
+    from sklearn.cluster import KMeans
+    from threadpoolctl import threadpool_limits
+
+    with threadpool_limits(limits=threads), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        t0 = time.perf_counter()
+        thr = np.std(w) * quality                      # utility.py:159
+        mask = np.abs(w) < thr                          # utility.py:161
+        w[mask] = 0                                     # utility.py:162
+        space = np.linspace(np.min(w), np.max(w), num=2 ** bits)  # utility.py:206-209
+        km = KMeans(n_clusters=len(space), init=space.reshape(-1, 1), n_init=1, algorithm="lloyd").fit(w.reshape(-1, 1))  # :237-238
+        ris = km.cluster_centers_[km.labels_].reshape(w.shape)  # utility.py:239
+        dt = time.perf_counter() - t0
+    del ris
+    return dt, int(km.n_iter_)
+
+
+def cpu_pipeline_port(w, threads):
     from oracle import oracle as O
 
     O.set_threads(threads)
-    w = (np.random.RandomState(SEED).randn(n_sample) * SIGMA).astype(np.float32)
     t0 = time.perf_counter()
     O.prune_weigth(w, QUALITY)
     space = O.init_centroids(w, BITS, MODE)
     km = O.kmeans1d(w, space, mode=O.MODE_DET if threads > 1 else O.MODE_REF32)
     O.pack_codes(km.labels_, BITS)
-    dt = time.perf_counter() - t0
-    return dt, km.n_iter_
+    return time.perf_counter() - t0, km.n_iter_
+
+
+def cpu_pipeline(n_sample, threads):
+    """prune + 8-bit linear k-means to convergence of an n_sample-weight tensor of the workload's distribution on the
+    host.  Returns (seconds, n_iter, kind, engine)."""
+    w = cpu_tensor(n_sample)
+    try:
+        import sklearn
+
+        dt, it = cpu_pipeline_sklearn(w, threads)
+        return dt, it, "reference", "numpy %s + scikit-learn %s KMeans(init=linspace, n_init=1, algorithm='lloyd'): the calls of utility.py:159-162, 206-209, 237-239" % (np.__version__, sklearn.__version__)
+    except ImportError:
+        dt, it = cpu_pipeline_port(w, threads)
+        return dt, it, "port", "oracle/nnc_oracle.c (C restatement, pthreads)"
+
+
+def cpu_sample_text(n_sample, n_iter, seconds):
+    return ("a 2^%d-weight tensor of the workload's distribution (NOT the 2^30 layer: the reference needs ~2 min per Lloyd iteration "
+            "there), same pipeline to convergence: %d Lloyd iterations, %.1f s" % (int(np.log2(n_sample)), n_iter, seconds))
 
 
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
+    threads = cpu_threads()
     n_sample = args.cpu_sample
     times = []
-    n_iter = 0
+    n_iter, kind, engine = 0, "port", ""
     for i in range(args.warmup + args.steps):
-        dt, n_iter = cpu_pipeline(n_sample, cores)
+        dt, n_iter, kind, engine = cpu_pipeline(n_sample, threads)
         if i >= args.warmup:
             times.append(dt)
     total = sum(times)
     value = n_sample * len(times) / total
-    sample = "2^%d-weight N(0,0.02^2) tensor, same pipeline to convergence (%d Lloyd iterations)" % (int(np.log2(n_sample)), n_iter)
+    cfg = workload_config(args, args.gpus)
+    # this arm times a SAMPLE of the workload: say so where the driver compares configs
+    cfg["n_weights_timed"] = n_sample
+    cfg["sampled"] = True
+    cfg["workload"] += " -- CPU arm: timed on a 2^%d-weight sample of the same distribution" % int(np.log2(n_sample))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "engine": engine,
+                         "sample": cpu_sample_text(n_sample, n_iter, total / len(times))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -271,12 +324,25 @@ def run_b200(args):
     # ---- inputs: one fresh tensor per step (pruning is in place), generated on the device before timing
     pool = min(K + W, args.pool)
     gen = torch.Generator(device=dev)
-    gen.manual_seed(SEED + rank)
     bufs = [torch.empty(n_local, dtype=torch.float32, device=dev) for _ in range(pool)]
+    # The GLOBAL tensor of a step is the same for every rank count: it is generated in fixed chunks of 2^22 weights, each
+    # from its own Philox seed (step, chunk); a rank fills the part of its slice that every chunk covers.  Results
+    # (threshold, centroids, n_iter, code histogram, code checksum -> `result_hash`) must then agree across N = 1/2/4/8.
+    CH = 1 << 22
+    chunk_tmp = torch.empty(CH, dtype=torch.float32, device=dev)
+    fills = [0]
+
+    def fill(buf, tensor_index):
+        for c in range(lo // CH, (hi - 1) // CH + 1):
+            gen.manual_seed((SEED * 1000003 + tensor_index) * 4099 + c)
+            chunk_tmp.normal_(0.0, SIGMA, generator=gen)
+            g0, g1 = max(lo, c * CH), min(hi, (c + 1) * CH)
+            buf[g0 - lo:g1 - lo].copy_(chunk_tmp[g0 - c * CH:g1 - c * CH])
 
     def refill(count):
         for b in bufs[:count]:
-            b.normal_(0.0, SIGMA, generator=gen)
+            fill(b, fills[0])
+            fills[0] += 1
 
     def step(t):
         mask, km = U.compress_weight(t, QUALITY, True, BITS, MODE)
@@ -344,6 +410,9 @@ def run_b200(args):
         total_ms = float(t.item())
     value = args.n * K / (total_ms * 1e-3)
 
+    # ---- result hash of the LAST timed step (shard independent: the driver compares it across N)
+    result = result_hash(torch, dist, dev, lo, hi, mask, km, U.prune_weigth.last_threshold, U.prune_weigth.last_pruned, n_iters)
+
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -368,12 +437,15 @@ def run_b200(args):
     avg_ms = dom_ms / max(dom_cnt, 1)
     achieved = kbytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     step_bytes = 13.0 + 4.0 + BITS / 8.0 + 52.0 * s_frac  # prune 13 + quantize 4 + b/8 + 52 s
+    moved_bytes = 4.0 + 9.0 + 4.0 * s_frac + 16.0 * s_frac + 0.5 + 4.0 + BITS / 8.0  # stats, fused apply, histogram path, emission
+    floor_bytes = 13.0 + 8.0 + BITS / 8.0
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            # static value from the committed ncu capture of this kernel on this workload, NOT measured in this run
             "traffic": NCU_TRAFFIC.get(dom_name, [None])[0] if world == 1 and args.n == (1 << 30) else None,
             "traffic_source": NCU_TRAFFIC.get(dom_name, [None, None])[1],
             "kernel": dom_name, "kernel_launches_per_step": dom_cnt / K, "kernel_ms_per_launch": avg_ms,
@@ -381,7 +453,15 @@ def run_b200(args):
             "step_algorithmic_bytes_per_weight": step_bytes,
             "step_achieved_gbs": step_bytes * args.n / world / (total_ms / K * 1e-3) / 1e9,
             "step_frac": step_bytes * args.n / world / (total_ms / K * 1e-3) / 1e9 / peak,
+            # the same step against the bytes the pipeline actually moves (the sort of SURVEY 8d is
+            # replaced by a key histogram) and against the algorithm-independent floor (prune 13 + quantize 8 + b/8)
+            "step_frac_by_bytes": {
+                "prescribed_34.5": step_bytes * args.n / world / (total_ms / K * 1e-3) / 1e9 / peak,
+                "moved_%.1f" % moved_bytes: moved_bytes * args.n / world / (total_ms / K * 1e-3) / 1e9 / peak,
+                "floor_%.1f" % floor_bytes: floor_bytes * args.n / world / (total_ms / K * 1e-3) / 1e9 / peak,
+            },
         },
+        "result_hash": result,
         "gpu_launches": int(launches),
         "clocks": clk,
         "n_iter": n_iters,
@@ -394,17 +474,44 @@ def run_b200(args):
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu:
-        cores = 1
-        t_cpu, it_cpu = cpu_pipeline(args.cpu_sample, cores)
-        line["cpu_baseline"] = {
-            "value": args.cpu_sample / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "2^%d-weight tensor of the same distribution, same pipeline to convergence (%d Lloyd iterations, %.1f s), "
-                      "scalar C restatement of numpy/sklearn float32 arithmetic" % (int(np.log2(args.cpu_sample)), it_cpu, t_cpu),
-        }
+        threads = cpu_threads()
+        t_cpu, it_cpu, kind, engine = cpu_pipeline(args.cpu_sample, threads)
+        line["cpu_baseline"] = {"value": args.cpu_sample / t_cpu, "unit": UNIT, "cores": threads, "kind": kind, "engine": engine,
+                                "sample": cpu_sample_text(args.cpu_sample, it_cpu, t_cpu)}
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def result_hash(torch, dist, dev, lo, hi, mask, km, thr, n_pruned, n_iters):
+    """CRC over everything a caller gets back, in a form that does not depend on how the tensor was sharded: the global
+    scalars and codebook as they are, the per-element outputs (mask, packed codes) through position-weighted checksums
+    summed over the ranks (int64 arithmetic modulo 2^64)."""
+    import struct
+    import zlib
+
+    codes = km.packed_codes
+    sums = torch.zeros(4, dtype=torch.int64, device=dev)
+    step = 1 << 26
+    for b0 in range(0, hi - lo, step):
+        b1 = min(hi - lo, b0 + step)
+        wgt = (torch.arange(lo + b0, lo + b1, device=dev, dtype=torch.int64) % 65521) + 1
+        c = codes[b0:b1].to(torch.int64)
+        m = mask.reshape(-1)[b0:b1].to(torch.int64)
+        sums[0] += (c * wgt).sum()
+        sums[1] += c.sum()
+        sums[2] += (m * wgt).sum()
+        sums[3] += m.sum()
+    if dist is not None:
+        dist.all_reduce(sums)
+    sums = [int(v) for v in sums.cpu().tolist()]
+    blob = struct.pack("<dq", float(thr), int(n_pruned)) + np.ascontiguousarray(km.cluster_centers_).tobytes() + \
+        np.ascontiguousarray(km.code_histogram).tobytes() + struct.pack("<%dq" % len(n_iters), *n_iters) + struct.pack("<4q", *sums)
+    return {"crc32": "%08x" % (zlib.crc32(blob) & 0xffffffff), "threshold": float(thr), "n_pruned": int(n_pruned),
+            "centroids_crc32": "%08x" % (zlib.crc32(np.ascontiguousarray(km.cluster_centers_).tobytes()) & 0xffffffff),
+            "histogram_crc32": "%08x" % (zlib.crc32(np.ascontiguousarray(km.code_histogram).tobytes()) & 0xffffffff),
+            "codes_weighted_sum": sums[0], "codes_sum": sums[1], "mask_weighted_sum": sums[2], "mask_sum": sums[3]}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` captures on this workload
@@ -482,7 +589,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=1 << 30, help="total weights over all ranks")
     ap.add_argument("--pool", type=int, default=8, help="distinct input tensors kept resident")
-    ap.add_argument("--cpu-sample", type=int, default=1 << 21)
+    ap.add_argument("--cpu-sample", type=int, default=1 << 22, help="weights of the sample the CPU arms time")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -109,7 +109,7 @@ bool is_device_ptr(const void *p) {
 }
 
 void func_dyn_smem(nnc_ctx *ctx, const void *fn, size_t bytes) {
-    if (bytes <= 48 * 1024) return;  // the default limit already covers it
+    // (no shortcut for small sizes: the 48 KB default limit covers static + dynamic shared memory together)
     for (auto &e : ctx->func_smem) {
         if (e.first == fn) {
             if (e.second >= bytes) return;

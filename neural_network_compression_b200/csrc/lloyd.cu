@@ -967,10 +967,15 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
     }
     exclusive_scan_i64(ctx, tsum, n_tiles, ptile);
     if (ctile) exclusive_scan_i64(ctx, tcnt, n_tiles, ctile);
-    NNC_LAUNCH(ctx, ll_total_kernel, 1, 1, 0, ptile, n_tiles, st);
-    NNC_LAUNCH(ctx, ll_moments_kernel, 1, 1, 0, st);
-    comm_allreduce(ctx, reinterpret_cast<int64_t *>(&st->s1), 3, 0);  // s1, s2_lo, s2_hi are consecutive
-    NNC_LAUNCH(ctx, ll_init_kernel, 1, TB_KMAX, 0, st, d_init);
+    const bool peer = world > 1 && ctx->peer_enabled && 2 * k <= PEER_WORDS;
+    // the cluster kernel (lloyd_fast.cu) folds the scalar prologue (total, moments, their all-reduce, init) into its start
+    const bool fast = lloyd_fast_applicable(k) && (world == 1 || peer) && !getenv("NNC_LLOYD_MULTI_LAUNCH") && !getenv("NNC_LLOYD_SPLIT");
+    if (!fast) {
+        NNC_LAUNCH(ctx, ll_total_kernel, 1, 1, 0, ptile, n_tiles, st);
+        NNC_LAUNCH(ctx, ll_moments_kernel, 1, 1, 0, st);
+        comm_allreduce(ctx, reinterpret_cast<int64_t *>(&st->s1), 3, 0);  // s1, s2_lo, s2_hi are consecutive
+        NNC_LAUNCH(ctx, ll_init_kernel, 1, TB_KMAX, 0, st, d_init);
+    }
     prof_mark(ctx, "lloyd_prep");
 
     struct Ctl {  // mirrors LloydDevice from `iter` on: one read-back brings the loop's outcome and the barrier bail-out flag
@@ -981,7 +986,6 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
     static_assert(offsetof(LloydDevice, gbail) - offsetof(LloydDevice, iter) == offsetof(Ctl, gbail), "Ctl mirrors LloydDevice");
     const int search_grid = std::max(1, std::min(ctx->sm_count * 2, (2 * k + 7) / 8));
     const int zone_grid = ctx->sm_count * 2;
-    const bool peer = world > 1 && ctx->peer_enabled && 2 * k <= PEER_WORDS;
     // NNC_LLOYD_MULTI_LAUNCH: one launch per phase (the path taken when no peer mailbox is available);
     // NNC_LLOYD_SPLIT: additionally the update in its three launches with the all-reduces in between (no-ops on one rank)
     const bool split_update = getenv("NNC_LLOYD_SPLIT") != nullptr;
@@ -995,7 +999,15 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         for (int r = 0; r < world; ++r) pc.mail[r] = static_cast<unsigned long long *>(ctx->peer_mail[r]);
     }
     bool hist_done = false;
-    if (one_launch) {
+    if (fast) {
+        const bool kt = ctx->ktime && (ctx->kfilter.empty() || strstr("ll_fast_kernel", ctx->kfilter.c_str()));
+        if (kt) klaunch_begin(ctx, "ll_fast_kernel");
+        lloyd_fast_launch(ctx, st, h.d_sorted, samp, ptile, d_init, h_hist ? 1 : 0, pc);
+        if (kt) klaunch_end(ctx);
+        NNC_CUDA(cudaMemcpyAsync(&ctl, &st->iter, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
+        NNC_CUDA(cudaStreamSynchronize(ctx->stream));
+        hist_done = h_hist != nullptr;
+    } else if (one_launch) {
         func_dyn_smem(ctx, (const void *)ll_loop_kernel, sizeof(LoopSmem));
         const float *ks_arg = h.d_sorted;
         const float *samp_arg = samp;
@@ -1035,7 +1047,7 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
             if (ctl.done || launched >= max_iter) break;
         }
     }
-    if (one_launch && ctl.gbail) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: the grid barrier of the loop kernel timed out (iter %d)", ctl.iter);
+    if (!fast && one_launch && ctl.gbail) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: the grid barrier of the loop kernel timed out (iter %d)", ctl.iter);
     if (!ctl.done) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: loop ended without a stop decision (iter %d)", ctl.iter);
     if (world > 1 && ctx->peer_enabled) {
         int comm_error = 0;
@@ -1073,6 +1085,11 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         unsigned int tb[2];
         NNC_CUDA(cudaMemcpy(tb, st->logT[LL_LOG - 1], sizeof(tb), cudaMemcpyDeviceToHost));
         fprintf(stderr, "[nnc lloyd] four bare grid barriers: %.2f us\n", (tb[1] - tb[0]) * 1e-3);
+        long long zp[4], up[8];
+        NNC_CUDA(cudaMemcpy(zp, st->logZ + LL_LOG - 16, sizeof(zp), cudaMemcpyDeviceToHost));
+        NNC_CUDA(cudaMemcpy(up, st->logZ + LL_LOG - 32, sizeof(up), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[nnc lloyd] zone profile (cycles): prefix %lld elements %lld flush %lld\n", zp[1], zp[2], zp[3]);
+        fprintf(stderr, "[nnc lloyd] update profile (cycles): safe %lld zero-run %lld per-id+empties %lld reloc %lld average %lld conv %lld end %lld\n", up[1], up[2], up[3], up[4], up[5], up[6], up[7]);
         for (int i = 0; i < cnt; ++i)
             fprintf(stderr, "[nnc lloyd] iter %d zone_elems %lld (%.3f%% of survivors) groups %d distinct %d empty %d | us: search %.1f zone %.1f update %.1f table %.1f\n", i, z[i],
                     h.n_nz ? 100.0 * (double)z[i] / (double)h.n_nz : 0.0, g[i], mm[i], ee[i], tt[4 * i] * 1e-3, tt[4 * i + 1] * 1e-3,

@@ -1,0 +1,943 @@
+// lloyd_fast.cu -- the Lloyd loop as ONE thread-block cluster with its whole state in shared memory.
+//
+// Same arithmetic as lloyd.cu (which restates sklearn's _kmeans_single_lloyd / lloyd_iter_chunked_dense /
+// _relocate_empty_clusters_dense / _average_centers / _center_shift, sklearn/cluster/_kmeans.py:630-758,
+// _k_means_lloyd.pyx:23-218, _k_means_common.pyx:167-311, reached through KMeans(...).fit in
+// neural_network_compression/common/utility.py:237-238) -- bit-identical results, checked against the cooperative
+// loop kernel and the oracle.  What changes is where the iteration state lives and how the CTAs synchronise.
+//
+// An iteration on the sorted survivors is latency, not bandwidth: <= 2(m-1) boundary searches (three dependent memory
+// round trips each), ~0.01 % of the entries evaluated with the float32 label rule, and a k-element update.  The
+// cooperative kernel (ll_loop_kernel) spends ~43 us per iteration on that: the region table, the searched positions
+// and the per-cluster partials live in global memory (every phase starts with dependent L2 round trips), CTA 0 runs
+// the serial phases, and three software grid barriers of 1.6 us separate the phases.  Here:
+//   * one cluster of LF_CL CTAs x 1024 threads (256 warps >= the boundaries of a 256-cluster codebook);
+//   * every CTA builds the region table REDUNDANTLY in its own shared memory from its copy of the centroids
+//     (deterministic: identical tables, no broadcast of 14 KB);
+//   * searched positions and zone partials go to CTA 0's shared memory through distributed shared memory
+//     (st.shared::cluster / atom.shared::cluster, ~215 cycles) instead of L2;
+//   * phases are separated by the hardware cluster barrier (~380 cycles) instead of a spinning grid barrier;
+//   * CTA 0 updates the centroids out of shared memory only (with the NVLink peer exchange on several GPUs) and the
+//     other CTAs pull the k new centroids over DSMEM.
+// k <= LF_KMAX (512: 8-bit codebooks and the 257-centroid density init); larger k keeps ll_loop_kernel.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
+#include "lloyd_shared.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace nnc {
+
+constexpr int LF_KMAX = 512;
+constexpr int LF_CL = 8;  // CTAs per cluster (portable maximum)
+constexpr int LF_THREADS = 1024;
+constexpr int LF_R = 2 * LF_KMAX + 2;
+
+// scratch of np_pairwise_warp
+struct NpWarpScratch {
+    short off[16], len[16];
+    float val[16];
+};
+
+struct FastUpdate {  // scratch of the update step (CTA 0)
+    long long Wd[LF_KMAX], Sd[LF_KMAX];       // per distinct index
+    long long W[LF_KMAX], S[LF_KMAX];         // per cluster id
+    long long first[LF_KMAX], last[LF_KMAX];  // member cursors per distinct index
+    float raw[LF_KMAX], cnew[LF_KMAX], sq[LF_KMAX];
+    int empt[LF_KMAX];
+    float far_x[LF_KMAX];
+    int far_old[LF_KMAX];
+    float red_d[32];
+    int red_i[32], red_id[32];
+    uint32_t rk_d2[32], rk_gap[32], rk_ord[32];
+    int rk_who[32];
+    unsigned long long red_w[32];
+    NpWarpScratch np;
+    int n_empty, zdi, same, winner, stop, strict;
+    long long zero_left;
+};
+struct FastZone {
+    long long rp[LF_R];  // copy of CTA 0's region positions
+};
+struct FastSmem {
+    RegionTableT<LF_KMAX> tab;  // built redundantly by every CTA
+    float c[LF_KMAX];           // centred centroids by cluster id
+    int perm[LF_KMAX];          // sorted order of the previous table build
+    float top[LL_TOP];          // coarse level of the tile-sample index
+    int done, iter, strict, n_reloc, n_iter, comm_error;
+    union {
+        TableScratchT<LF_KMAX> tb;
+        FastUpdate up;
+        FastZone zn;
+    } u;
+    // searched region boundaries: only CTA 0's copy is used; the other CTAs write it through DSMEM
+    long long rpos[LF_R], rcnt[LF_R], rsum[LF_R];
+    // zone partials per distinct index of THIS CTA (CTA 0 pulls all of them in the update step)
+    unsigned long long zW[LF_KMAX];
+    long long zS[LF_KMAX], zmin[LF_KMAX], zmax[LF_KMAX];
+    long long Wprev[LF_KMAX], Sprev[LF_KMAX];
+    float c_emit[LF_KMAX];
+    long long xbuf[2 * LF_KMAX];  // staging of the peer exchange
+};
+
+struct FastConst {  // read once from the LloydDevice header
+    int k, rank, world, max_iter;
+    long long n, n_nz, n0, n_ent;
+    const unsigned int *cnt;
+    unsigned long long *cand;
+    float mean, xabs_max;
+    double scale;
+};
+
+// NumPy's pairwise float32 sum (numpy/_core/src/umath/loops_utils.h.src) of a[0, n), n <= 1024, by ONE WARP: the leaves
+// (<= 128 elements: 8 strided accumulators, combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the n % 8 tail) are
+// summed by groups of 8 lanes, four leaves at a time; lane 0 folds them up the recursion tree.  Bit-identical with
+// np_pairwise_small.  scratch: 16 shorts + 16 shorts + 16 floats.
+static __device__ int np_leaf_list(int o, int n, NpWarpScratch &W, int cnt) {
+    if (n <= 128) {
+        W.off[cnt] = (short)o;
+        W.len[cnt] = (short)n;
+        return cnt + 1;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    cnt = np_leaf_list(o, n2, W, cnt);
+    return np_leaf_list(o + n2, n - n2, W, cnt);
+}
+static __device__ float np_fold_leaves(int n, const NpWarpScratch &W, int &idx) {
+    if (n <= 128) return W.val[idx++];
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    const float l = np_fold_leaves(n2, W, idx);
+    const float r = np_fold_leaves(n - n2, W, idx);
+    return fadd(l, r);
+}
+__device__ float np_pairwise_warp(const float *a, int n, NpWarpScratch &W) {  // all 32 lanes of one warp; result in lane 0
+    const int lane = lane_id(), grp = lane >> 3, j = lane & 7;
+    int n_leaves = 0;
+    if (lane == 0) n_leaves = np_leaf_list(0, n, W, 0);
+    n_leaves = __shfl_sync(0xffffffffu, n_leaves, 0);
+    __syncwarp();
+    for (int l0 = 0; l0 < n_leaves; l0 += 4) {
+        const int l = l0 + grp;
+        float r = 0.f;
+        const bool have = l < n_leaves;
+        const int o = have ? W.off[l] : 0, sz = have ? W.len[l] : 0;
+        if (sz >= 8) {
+            r = a[o + j];
+            const int full = sz - (sz % 8);
+            for (int i = 8; i < full; i += 8) r = fadd(r, a[o + i + j]);
+        }
+        r = fadd(r, __shfl_xor_sync(0xffffffffu, r, 1));
+        r = fadd(r, __shfl_xor_sync(0xffffffffu, r, 2));
+        r = fadd(r, __shfl_xor_sync(0xffffffffu, r, 4));
+        if (have && j == 0) {
+            if (sz >= 8) {
+                for (int i = sz - (sz % 8); i < sz; ++i) r = fadd(r, a[o + i]);
+            } else {  // n < 8: plain sequential sum starting from 0
+                r = 0.f;
+                for (int i = 0; i < sz; ++i) r = fadd(r, a[o + i]);
+            }
+            W.val[l] = r;
+        }
+    }
+    __syncwarp();
+    float tot = 0.f;
+    if (lane == 0) {
+        int idx = 0;
+        tot = np_fold_leaves(n, W, idx);
+    }
+    return tot;
+}
+
+// label (distinct index) of the sorted survivor at position p
+__device__ __forceinline__ int fast_label_at(const FastSmem &S, const float *ks, float mean, long long p) {
+    const RegionTableT<LF_KMAX> &T = S.tab;
+    int lo = 0, hi = T.R;  // largest r with rpos[r] <= p
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (S.rpos[mid] <= p)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    if (T.rJ1[lo] == T.rJ2[lo]) return T.rJ1[lo];
+    return zone_argmin(fsub(ks[p], mean), T.dv, T.dcn, T.down, T.rJ2[lo], T.rJ1[lo]);
+}
+
+// ---- zone step: the float32 label rule for the few entries inside the zones.
+// Every CTA accumulates into ITS OWN partials (S.zW / zS / zmin / zmax, local shared-memory atomics); CTA 0 pulls the
+// eight partial sets over DSMEM in the update step.  (Remote atomics into CTA 0 -- generic-address 64-bit min / max on
+// another CTA's shared memory -- lost updates under contention on sm_100a and are not used.)
+//   small zones (<= LF_ZONE_WARP entries, the normal case: ~170 entries between two adjacent centroids): one warp per
+//       zone; two candidates keep their (count, sum) in registers, first / last member come from ballots;
+//   big zones (near-duplicate centroids after a relocation): chunks of LF_ZONE_WARP entries spread over all warps.
+constexpr int LF_ZONE_WARP = 2048;
+
+// one warp: entries [lo, hi) of region r, any number of candidates; accumulates into the CTA's partials
+__device__ __forceinline__ void fast_zone_generic(FastSmem &S, const FastConst &K, const SearchConst &C, const float *__restrict__ ks,
+                                                  int J2, int J1, long long lo, long long hi) {
+    const RegionTableT<LF_KMAX> &T = S.tab;
+    const int lane = lane_id();
+    const unsigned int *__restrict__ ecnt = K.cnt;
+    for (long long b = lo; b < hi; b += 32) {
+        const long long p = b + lane;
+        const bool valid = p < hi;
+        int di = -1;
+        long long q = 0, c = 0;
+        if (valid) {
+            const float xc = fsub(ks[p], K.mean);
+            di = zone_argmin(xc, T.dv, T.dcn, T.down, J2, J1);
+            c = ecnt ? (long long)ecnt[p] : 1ll;
+            q = fixed_qf(xc, C.scale_f, K.scale) * c;
+        }
+        unsigned active = __ballot_sync(0xffffffffu, valid);
+        while (active) {
+            const int leader = __ffs(active) - 1;
+            const int L = __shfl_sync(0xffffffffu, di, leader);
+            const bool mine = valid && di == L;
+            const unsigned grp = __ballot_sync(0xffffffffu, mine);
+            const long long sq = warp_sum_ll(mine ? q : 0);
+            const long long sc = ecnt ? warp_sum_ll(mine ? c : 0) : (long long)__popc(grp);
+            if (lane == leader) {
+                atomicAdd(&S.zW[L], (unsigned long long)sc);
+                atomicAdd((unsigned long long *)&S.zS[L], (unsigned long long)sq);
+                atomicMin(&S.zmin[L], b + (__ffs(grp) - 1));
+                atomicMax(&S.zmax[L], b + (31 - __clz(grp)));
+            }
+            active &= ~grp;
+        }
+    }
+}
+
+__device__ void fast_zone_step(FastSmem &S, FastSmem *S0, const FastConst &K, const SearchConst &C, const float *__restrict__ ks,
+                               int gw, long long *prof = nullptr) {
+    if (prof) prof[0] = clock64();
+    FastZone &Z = S.u.zn;
+    const RegionTableT<LF_KMAX> &T = S.tab;
+    const int R = T.R, tid = threadIdx.x, lane = lane_id();
+    if (R <= 1) return;
+    for (int r = tid; r <= R; r += LF_THREADS) Z.rp[r] = S0->rpos[r];
+    __syncthreads();
+    if (prof) prof[1] = clock64();
+    constexpr int NW = LF_CL * (LF_THREADS / 32);
+    const unsigned int *__restrict__ ecnt = K.cnt;
+    // is there a zone too large for one warp?  Every CTA looks at ALL regions (one per thread), so the whole cluster takes
+    // the same decision
+    int big = 0;
+    for (int r = tid; r < R; r += LF_THREADS) big |= (T.rJ1[r] > T.rJ2[r]) && (Z.rp[r + 1] - Z.rp[r] > LF_ZONE_WARP);
+    // zones are normally the ODD regions (SAFE and ZONE alternate): odd regions first, one per warp, then the even ones
+    // (zones only in degenerate layouts) -- a plain r = gw, gw + NW, ... would leave every second warp without work
+    for (int pass = 0; pass < 2; ++pass)
+    for (int r = 2 * gw + 1 - pass; r < R; r += 2 * NW) {
+        const int J2 = T.rJ2[r], J1 = T.rJ1[r];
+        if (J1 <= J2) continue;  // SAFE
+        const long long lo = Z.rp[r], hi = Z.rp[r + 1];
+        if (hi <= lo) continue;
+        if (hi - lo > LF_ZONE_WARP) continue;  // handled by all warps below
+        if (J1 != J2 + 1) {
+            fast_zone_generic(S, K, C, ks, J2, J1, lo, hi);
+            continue;
+        }
+        // two candidates a = J2 < b = J1: label b iff d_b < d_a, or d_b == d_a with the lower owner id
+        const float va = T.dv[J2], vb = T.dv[J1], na = T.dcn[J2], nb = T.dcn[J1];
+        const bool b_wins_ties = T.down[J1] < T.down[J2];
+        long long Wb = 0, Sb = 0, Wt = 0, St = 0;  // candidate b and both candidates together
+        long long fa = -1, la = -1, fb = -1, lb = -1;  // first / last member positions (uniform over the warp)
+        for (long long base = lo; base < hi; base += 128) {  // four rounds of 32 entries with all their loads in flight
+            float xv[4];
+            unsigned int cv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long p = base + 32 * j + lane;
+                const bool valid = p < hi;
+                xv[j] = valid ? ld_vol_f1(ks + p) : 0.f;
+                cv[j] = 1u;
+                if (ecnt && valid) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(cv[j]) : "l"(ecnt + p));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long b32 = base + 32 * j;
+                if (b32 >= hi) break;
+                const bool valid = b32 + lane < hi;
+                bool isb = false;
+                if (valid) {
+                    const float xc = fsub(xv[j], K.mean);
+                    const float m2x = fmul(-2.0f, xc);
+                    const float da = skl_dist(m2x, va, na), db = skl_dist(m2x, vb, nb);
+                    isb = db < da || (db == da && b_wins_ties);
+                    const long long c = (long long)cv[j];
+                    const long long q = fixed_qf(xc, C.scale_f, K.scale) * c;
+                    Wt += c;
+                    St += q;
+                    if (isb) {
+                        Wb += c;
+                        Sb += q;
+                    }
+                }
+                const unsigned mb = __ballot_sync(0xffffffffu, valid && isb);
+                const unsigned ma = __ballot_sync(0xffffffffu, valid && !isb);
+                if (ma) {
+                    if (fa < 0) fa = b32 + (__ffs(ma) - 1);
+                    la = b32 + (31 - __clz(ma));
+                }
+                if (mb) {
+                    if (fb < 0) fb = b32 + (__ffs(mb) - 1);
+                    lb = b32 + (31 - __clz(mb));
+                }
+            }
+        }
+        Wt = warp_sum_ll(Wt);
+        St = warp_sum_ll(St);
+        Wb = warp_sum_ll(Wb);
+        Sb = warp_sum_ll(Sb);
+        if (lane == 0) {
+            if (fa >= 0) {
+                atomicAdd(&S.zW[J2], (unsigned long long)(Wt - Wb));
+                atomicAdd((unsigned long long *)&S.zS[J2], (unsigned long long)(St - Sb));
+                atomicMin(&S.zmin[J2], fa);
+                atomicMax(&S.zmax[J2], la);
+            }
+            if (fb >= 0) {
+                atomicAdd(&S.zW[J1], (unsigned long long)Wb);
+                atomicAdd((unsigned long long *)&S.zS[J1], (unsigned long long)Sb);
+                atomicMin(&S.zmin[J1], fb);
+                atomicMax(&S.zmax[J1], lb);
+            }
+        }
+    }
+    if (prof) prof[2] = clock64();
+    // zones too large for one warp (rare): every warp of the cluster takes chunks of them
+    if (__syncthreads_or(big)) {
+        long long chunk0 = 0;  // chunks before the current region, counted identically by every warp
+        for (int r = 0; r < R; ++r) {
+            const int J2 = T.rJ2[r], J1 = T.rJ1[r];
+            if (J1 <= J2) continue;
+            const long long lo = Z.rp[r], hi = Z.rp[r + 1];
+            if (hi - lo <= LF_ZONE_WARP) continue;
+            const long long nch = (hi - lo + LF_ZONE_WARP - 1) / LF_ZONE_WARP;
+            long long c = (gw - chunk0 % NW + NW) % NW;  // first chunk of this region owned by this warp (global round robin)
+            for (; c < nch; c += NW) {
+                const long long b0 = lo + c * LF_ZONE_WARP;
+                fast_zone_generic(S, K, C, ks, J2, J1, b0, llmin2(hi, b0 + LF_ZONE_WARP));
+            }
+            chunk0 += nch;
+        }
+    }
+    if (prof) prof[3] = clock64();
+}
+
+// ---- update step (CTA 0 only; S is its own shared memory): per-cluster counts / sums, label-equality proxy, empty-cluster
+// relocation, averages, centre shift, convergence.  Mirrors update_phase of lloyd.cu statement by statement.
+__device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const FastConst &K, const float *__restrict__ ks,
+                                 const PeerComm &pc, unsigned long long &xseq, float tol, long long *prof = nullptr) {
+    FastUpdate &U = S.u.up;
+    if (prof) prof[0] = clock64();
+    const RegionTableT<LF_KMAX> &T = S.tab;
+    const int tid = threadIdx.x, k = K.k, m = T.m, R = T.R;
+    const float mean = K.mean;
+    const double scale = K.scale;
+    const float x0 = fsub(0.f, mean);
+    // ---- 1. per distinct index: zone partials of every CTA (pulled over DSMEM) + SAFE regions
+    if (tid < m) {
+        long long w = 0, sm = 0, mn = 0x7fffffffffffffffll, mx = -1;
+#pragma unroll
+        for (int cta = 0; cta < LF_CL; ++cta) {
+            const FastSmem *Sc = cluster.map_shared_rank(&S, cta);
+            w += (long long)Sc->zW[tid];
+            sm += Sc->zS[tid];
+            mn = llmin2(mn, Sc->zmin[tid]);
+            mx = llmax2(mx, Sc->zmax[tid]);
+        }
+        U.Wd[tid] = w;
+        U.Sd[tid] = sm;
+        U.first[tid] = mn;
+        U.last[tid] = mx;
+    }
+    if (tid < k) {
+        U.W[tid] = 0;
+        U.S[tid] = 0;
+    }
+    if (tid == 0) {
+        U.same = 1;
+        U.n_empty = 0;
+    }
+    __syncthreads();
+    for (int r = tid; r < R; r += LF_THREADS) {  // SAFE regions: positions [rpos[r], rpos[r+1]) carry one label
+        if (T.rJ1[r] != T.rJ2[r]) continue;
+        const int di = T.rJ1[r];
+        const long long lo = S.rpos[r], hi = S.rpos[r + 1];
+        if (hi > lo) {
+            U.Wd[di] += S.rcnt[r + 1] - S.rcnt[r];  // (J, J) occurs in at most one region: no conflicts
+            U.Sd[di] += S.rsum[r + 1] - S.rsum[r];
+            U.first[di] = llmin2(U.first[di], lo);
+            U.last[di] = llmax2(U.last[di], hi - 1);
+        }
+    }
+    __syncthreads();
+    if (prof) prof[1] = clock64();
+    // ---- 2. zero run: label of x'_0 = fl(0 - mean) over all distinct centroids
+    if (K.n0 > 0) {
+        if (warp_id() == 0) {  // argmin by (d, owner id) over the m distinct centroids: one warp, strided
+            float d = INFINITY;
+            int id = 0x7fffffff, di = -1;
+            const float m2x = fmul(-2.0f, x0);
+            for (int i = lane_id(); i < m; i += 32) {
+                const float di_d = skl_dist(m2x, T.dv[i], T.dcn[i]);
+                const int di_id = T.down[i];
+                if (di_d < d || (di_d == d && di_id < id)) {
+                    d = di_d;
+                    id = di_id;
+                    di = i;
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const float d2 = __shfl_xor_sync(0xffffffffu, d, o);
+                const int id2 = __shfl_xor_sync(0xffffffffu, id, o);
+                const int di2 = __shfl_xor_sync(0xffffffffu, di, o);
+                if (d2 < d || (d2 == d && id2 < id)) {
+                    d = d2;
+                    id = id2;
+                    di = di2;
+                }
+            }
+            if (lane_id() == 0) {
+                U.zdi = di;
+                const long long q0 = fixed_q(x0, scale);
+                U.Wd[di] += K.n0;
+                U.Sd[di] += K.n0 * q0;
+            }
+        }
+        __syncthreads();
+    } else {
+        if (tid == 0) U.zdi = -1;
+        __syncthreads();
+    }
+    if (pc.enabled) {  // fused all-reduce of the exact per-distinct-index (count, sum) over the ranks
+        if (tid < m) {
+            S.xbuf[tid] = U.Wd[tid];
+            S.xbuf[m + tid] = U.Sd[tid];
+        }
+        __syncthreads();
+        if (!peer_allreduce_sum(pc, S.xbuf, 2 * m, ++xseq) && tid == 0) S.comm_error = 1;
+        if (tid < m) {
+            U.Wd[tid] = S.xbuf[tid];
+            U.Sd[tid] = S.xbuf[m + tid];
+        }
+        __syncthreads();
+    }
+    if (prof) prof[2] = clock64();
+    // ---- 3. per cluster id
+    if (tid < m) {
+        U.W[T.down[tid]] = U.Wd[tid];
+        U.S[T.down[tid]] = U.Sd[tid];
+    }
+    __syncthreads();
+    // ---- 4. label-equality proxy: identical exact (count, sum) per cluster as in the previous iteration
+    int differs = 0;
+    if (tid < k) {
+        differs = (U.W[tid] != S.Wprev[tid]) || (U.S[tid] != S.Sprev[tid]);
+        S.Wprev[tid] = U.W[tid];
+        S.Sprev[tid] = U.S[tid];
+    }
+    const int any_differs = __syncthreads_or(differs);
+    // ---- 5. empty clusters (ascending id) and relocation
+    {
+        const int e = (tid < k) && (U.W[tid] == 0);
+        const int incl = block_scan_incl<int>(e, [](int a, int b) { return a + b; }, U.red_i);
+        if (e) U.empt[incl - 1] = tid;
+        if (tid == LF_THREADS - 1) U.n_empty = incl;
+        __syncthreads();
+    }
+    const int n_empty = U.n_empty;
+    if (prof) prof[3] = clock64();
+    if (n_empty > 0) {
+        // Streams of candidates: for every distinct index its members walked from the left end and from the right end
+        // (|x' - c| is V-shaped along a cluster's sorted members), plus the zero run.  The farthest remaining sample
+        // overall is always at the head of one of the streams; pop n_empty times.  Thread di owns both cursors of
+        // distinct index di; the owner of the zero run's cluster also owns the zero run (a third head).
+        long long pl = -1, pr = -2;  // empty stream when pl > pr
+        unsigned long long reml = 0, remr = 0;  // samples left in the entry under the left / right cursor
+        const unsigned int *__restrict__ ecnt = K.cnt;
+        auto cnt_at = [&](long long p) -> unsigned long long { return ecnt ? (unsigned long long)ecnt[p] : 1ull; };
+        float cown = 0.f;
+        FarKey kl{0, 0, 0}, kr{0, 0, 0};
+        float xl = 0.f, xr = 0.f;
+        bool has_l = false, has_r = false;
+        if (tid < m) {
+            cown = T.dv[tid];
+            if (U.last[tid] >= U.first[tid] && U.last[tid] >= 0) {
+                pl = U.first[tid];
+                pr = U.last[tid];
+                reml = cnt_at(pl);
+                remr = cnt_at(pr);
+            }
+        }
+        auto refresh = [&]() {
+            has_l = has_r = false;
+            if (tid < m && pl <= pr) {
+                xl = fsub(ks[pl], mean);
+                kl = far_key(xl, cown);
+                has_l = true;
+                if (pr > pl) {
+                    xr = fsub(ks[pr], mean);
+                    kr = far_key(xr, cown);
+                    has_r = true;
+                }
+            }
+        };
+        refresh();
+        if (tid == 0) U.zero_left = K.n0;
+        __syncthreads();
+        const FarKey kz = far_key(x0, U.zdi >= 0 ? T.dv[U.zdi] : 0.f);
+        unsigned long long *my_cand = K.cand + (size_t)K.rank * k * 2;
+        const int nw = (m + 31) >> 5;  // warps that own streams
+        int n_done = 0;
+        for (int pop = 0; pop < n_empty; ++pop) {
+            FarKey best{0, 0, 0};
+            int who = -1;  // best head of this thread: 0 = left, 1 = right, 2 = zero run
+            if (has_l) {
+                best = kl;
+                who = 0;
+            }
+            if (has_r && (who < 0 || far_before(kr, best))) {
+                best = kr;
+                who = 1;
+            }
+            if (tid == U.zdi && U.zero_left > 0 && (who < 0 || far_before(kz, best))) {
+                best = kz;
+                who = 2;
+            }
+            int owner = who >= 0 ? tid : -1;
+            if (warp_id() < nw) {
+                for (int o = 16; o > 0; o >>= 1) {
+                    FarKey ob;
+                    ob.d2 = __shfl_xor_sync(0xffffffffu, best.d2, o);
+                    ob.gap = __shfl_xor_sync(0xffffffffu, best.gap, o);
+                    ob.ordx = __shfl_xor_sync(0xffffffffu, best.ordx, o);
+                    const int oo = __shfl_xor_sync(0xffffffffu, owner, o);
+                    if (oo >= 0 && (owner < 0 || far_before(ob, best) || (!far_before(best, ob) && oo < owner))) {
+                        best = ob;
+                        owner = oo;
+                    }
+                }
+                if (lane_id() == 0) {
+                    U.rk_d2[warp_id()] = best.d2;
+                    U.rk_gap[warp_id()] = best.gap;
+                    U.rk_ord[warp_id()] = best.ordx;
+                    U.rk_who[warp_id()] = owner;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < nw; ++w) {
+                    const FarKey ob{U.rk_d2[w], U.rk_gap[w], U.rk_ord[w]};
+                    const int oo = U.rk_who[w];
+                    if (oo >= 0 && (owner < 0 || far_before(ob, best) || (!far_before(best, ob) && oo < owner))) {
+                        best = ob;
+                        owner = oo;
+                    }
+                }
+                U.winner = owner;
+            }
+            __syncthreads();
+            if (U.winner < 0) break;  // this rank has no sample left
+            if (tid == U.winner) {
+                // candidate = (dist^2, ulp gap | x', old cluster id + 1): the local list comes out in descending order
+                const FarKey kk = who == 0 ? kl : (who == 1 ? kr : kz);
+                const int old_id = who == 2 ? T.down[U.zdi] : T.down[tid];
+                my_cand[2 * pop] = ((unsigned long long)kk.d2 << 32) | kk.gap;
+                my_cand[2 * pop + 1] = ((unsigned long long)kk.ordx << 32) | (unsigned)(old_id + 1);
+                if (who == 2) {
+                    U.zero_left -= 1;
+                } else if (who == 0) {
+                    if (reml > 1) {
+                        reml -= 1;
+                    } else {
+                        do {
+                            ++pl;
+                        } while (pl <= pr && fast_label_at(S, ks, mean, pl) != tid);
+                        if (pl <= pr) reml = pl == pr ? remr : cnt_at(pl);
+                        refresh();
+                    }
+                } else {
+                    if (remr > 1) {
+                        remr -= 1;
+                    } else {
+                        do {
+                            --pr;
+                        } while (pr >= pl && fast_label_at(S, ks, mean, pr) != tid);
+                        if (pr > pl) remr = cnt_at(pr);
+                        refresh();
+                    }
+                }
+            }
+            n_done = pop + 1;
+            __syncthreads();
+        }
+        __syncthreads();
+        // unused slots of this rank, and (before the all-gather) every slot of the other ranks, hold zeros
+        for (int i = tid; i < K.world * k; i += LF_THREADS) {
+            const int r = i / k, j = i - r * k;
+            if (r != K.rank || j >= n_done) {
+                K.cand[2 * (size_t)i] = 0;
+                K.cand[2 * (size_t)i + 1] = 0;
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+        if (pc.enabled) {  // fused all-gather of the candidate lists (n_empty is the same on every rank)
+            const int cnt = 2 * n_empty;
+            const unsigned long long *mine = K.cand + (size_t)K.rank * k * 2;
+            for (int i = tid; i < cnt; i += LF_THREADS) S.xbuf[i] = (long long)mine[i];
+            __syncthreads();
+            if (!peer_allgather(pc, reinterpret_cast<const unsigned long long *>(S.xbuf), cnt, K.cand, (size_t)k * 2, ++xseq) &&
+                tid == 0)
+                S.comm_error = 1;
+        }
+        // ---- 5b. the n_empty farthest samples over all ranks (every rank's list is in descending order: a W-way merge by
+        // one thread), moved to the empty clusters in ascending id order
+        __syncthreads();
+        if (tid == 0) {
+            const int world = K.world;
+            int cur[64];
+            for (int r = 0; r < world; ++r) cur[r] = 0;
+            int n_moved = 0;
+            bool skip = false;
+            for (int i = 0; i < n_empty; ++i) {
+                int br = -1;
+                unsigned long long ba = 0, bb = 0;
+                for (int r = 0; r < world; ++r) {
+                    if (cur[r] >= k) continue;
+                    const unsigned long long a = K.cand[2 * ((size_t)r * k + cur[r])], b = K.cand[2 * ((size_t)r * k + cur[r]) + 1];
+                    if ((b & 0xffffffffull) == 0) continue;  // list exhausted
+                    if (br < 0 || a > ba || (a == ba && (b >> 32) > (bb >> 32))) {
+                        br = r;
+                        ba = a;
+                        bb = b;
+                    }
+                }
+                if (br < 0) break;
+                // np.max(distances) == 0 -> relocation is skipped altogether (_k_means_common.pyx:192-195)
+                if (i == 0 && (ba >> 32) == 0ull) {
+                    skip = true;
+                    break;
+                }
+                cur[br]++;
+                U.far_x[i] = ord2f((uint32_t)(bb >> 32));
+                U.far_old[i] = (int)(bb & 0xffffffffull) - 1;
+                n_moved = i + 1;
+            }
+            if (!skip) {
+                for (int i = 0; i < n_moved; ++i) {
+                    const int nwid = U.empt[i], od = U.far_old[i];
+                    const long long q = fixed_q(U.far_x[i], scale);
+                    U.S[od] -= q;
+                    U.S[nwid] = q;
+                    U.W[nwid] = 1;
+                    U.W[od] -= 1;
+                }
+                S.n_reloc += n_moved;
+            }
+        }
+        __syncthreads();
+    }
+    if (prof) prof[4] = clock64();
+    // ---- 6. averages (_average_centers), shift (_center_shift)
+    // S / 2^s == S * 2^-s exactly (a power-of-two scaling of the double image of S), without a float64 division
+    if (tid < k) U.raw[tid] = (float)__dmul_rn((double)U.S[tid], __ddiv_rn(1.0, scale));
+    // argmax of the counts, lowest id on ties (np.argmax): key = count << 10 | (1023 - id), count < 2^53
+    {
+        unsigned long long key = tid < k ? (((unsigned long long)U.W[tid] << 10) | (unsigned long long)(1023 - tid)) : 0ull;
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other > key ? other : key;
+        }
+        if (lane_id() == 0) U.red_w[warp_id()] = key;
+        __syncthreads();
+        if (tid == 0) {
+            const int nwk = (k + 31) >> 5;
+            for (int w = 1; w < nwk; ++w) key = U.red_w[w] > key ? U.red_w[w] : key;
+            U.winner = 1023 - (int)(key & 1023ull);
+        }
+        __syncthreads();
+    }
+    if (tid < k) {
+        const int amax = U.winner;
+        auto avg = [&](int j) { return fmul(U.raw[j], (float)__ddiv_rn(1.0, (double)U.W[j])); };
+        float cn;
+        if (U.W[tid] > 0)
+            cn = avg(tid);
+        else  // in-place ascending loop: rows below amax see its raw sum, rows above see its average
+            cn = amax < tid ? (U.W[amax] > 0 ? avg(amax) : U.raw[amax]) : U.raw[amax];
+        U.cnew[tid] = cn;
+        const float t = fsub(cn, S.c[tid]);
+        const float r = fmul(t, t);
+        // (float)sqrt((double)r) == the correctly rounded float32 sqrt: double rounding is innocuous for sqrt when the wide
+        // format has >= 2 * 24 + 2 bits (Figueroa)
+        const float sh = __fsqrt_rn(r);
+        U.sq[tid] = fmul(sh, sh);
+    }
+    __syncthreads();
+    if (prof) prof[5] = clock64();
+    // ---- 7. convergence (_kmeans.py:721-738)
+    if (warp_id() == 0) {
+        const float tot = np_pairwise_warp(U.sq, k, U.np);
+        int stop = 0, strict = 0;
+        if (!any_differs) {
+            stop = 1;
+            strict = 1;
+        } else if (tot <= tol) {
+            stop = 1;
+        }
+        if (tid == 0) {
+            U.strict = strict;
+            U.stop = stop;
+        }
+    }
+    __syncthreads();
+    if (prof) prof[6] = clock64();
+    {
+        const int strict = U.strict, stop = U.stop;
+        const int last_iter = S.iter + 1 >= K.max_iter;
+        if (tid < k) {
+            // labels of a strict stop belong to the centroids the E-step used; otherwise a final E-step with the new
+            // centroids follows (emit.cu)
+            if (stop || last_iter) S.c_emit[tid] = strict ? S.c[tid] : U.cnew[tid];
+        }
+        __syncthreads();
+        if (tid < k) S.c[tid] = U.cnew[tid];
+        if (tid == 0) {
+            S.iter += 1;
+            if (stop || last_iter) {
+                S.done = 1;
+                S.strict = strict;
+                S.n_iter = S.iter;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __cluster_dims__(LF_CL, 1, 1) __launch_bounds__(LF_THREADS, 1)
+    ll_fast_kernel(LloydDevice *st, const float *__restrict__ ks, const float *__restrict__ samp, const long long *__restrict__ ptile,
+                   const float *__restrict__ init, int want_hist, int want_log, PeerComm pc) {
+    extern __shared__ __align__(16) unsigned char fast_smem_raw[];
+    FastSmem &S = *reinterpret_cast<FastSmem *>(fast_smem_raw);
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned cta = cluster.block_rank();
+    FastSmem *S0 = cluster.map_shared_rank(&S, 0);
+    const int tid = threadIdx.x;
+    const int gw = (int)cta * (LF_THREADS / 32) + warp_id();  // warp index inside the cluster
+
+    FastConst K;
+    K.k = st->k;
+    K.rank = st->rank;
+    K.world = st->world;
+    K.max_iter = st->max_iter;
+    K.n = st->n;
+    K.n_nz = st->n_nz;
+    K.n0 = st->n0;
+    K.n_ent = st->n_ent;
+    K.cnt = st->cnt;
+    K.cand = st->cand;
+    K.mean = st->mean;
+    K.xabs_max = st->xabs_max;
+    K.scale = st->scale;
+    const int k = K.k;
+    SearchConst C = search_const(st, ks, samp, ptile);
+    if (C.n_tiles > 64) {  // top level of the tile-sample index in shared memory (the samples never change)
+        C.top_step = (C.n_tiles + LL_TOP - 1) / LL_TOP;
+        C.top_n = (int)((C.n_tiles + C.top_step - 1) / C.top_step);
+        for (int i = tid; i < C.top_n; i += LF_THREADS) S.top[i] = samp[(long long)i * C.top_step];
+        C.top = S.top;
+    }
+    const long long total_q = C.n_tiles > 0 ? ptile[C.n_tiles] : 0ll;
+    unsigned long long xseq = (pc.enabled && cta == 0) ? *peer_counter(pc) : 0ull;
+    // ---- init: centre the initial centroids; tolerance from the exact integer moments of all n samples
+    if (tid < k) {
+        S.c[tid] = fsub(init[tid], K.mean);  // init -= X_mean  (_kmeans.py:1493)
+        S.perm[tid] = 0;
+    }
+    if (tid == 0) {
+        S.done = 0;
+        S.iter = 0;
+        S.strict = 0;
+        S.n_reloc = 0;
+        S.n_iter = 0;
+        S.comm_error = 0;
+    }
+    float tol = 0.f;
+    if (cta == 0) {
+        if (tid < k) {
+            S.Wprev[tid] = -1;
+            S.Sprev[tid] = 0;
+        }
+        if (tid == 0) {  // this rank's moments: the sorted survivors (ll_tilesum_kernel) + its zero run
+            const long long q0 = fixed_q(fsub(0.f, K.mean), K.scale);
+            const unsigned long long qq = (unsigned long long)(q0 * q0);
+            S.xbuf[0] = st->s1 + K.n0 * q0;
+            S.xbuf[1] = (long long)(st->s2_lo + (unsigned long long)K.n0 * (qq & 0x7fffffffull));
+            S.xbuf[2] = (long long)(st->s2_hi + (unsigned long long)K.n0 * (qq >> 31));
+        }
+        __syncthreads();
+        if (pc.enabled) {
+            if (!peer_allreduce_sum(pc, S.xbuf, 3, ++xseq) && tid == 0) S.comm_error = 1;
+        }
+        if (tid == 0) {
+            const __int128 s1 = (__int128)S.xbuf[0];
+            const unsigned __int128 s2 = ((unsigned __int128)(unsigned long long)S.xbuf[2] << 31) + (unsigned long long)S.xbuf[1];
+            const unsigned __int128 num = (unsigned __int128)K.n * s2 - (unsigned __int128)(s1 * s1);
+            const double numd = __dadd_rn(__dmul_rn((double)(unsigned long long)(num >> 64), 18446744073709551616.0),
+                                          (double)(unsigned long long)num);
+            const double nd = (double)K.n;
+            const double var_d = __ddiv_rn(__ddiv_rn(numd, __dmul_rn(nd, nd)), __dmul_rn(K.scale, K.scale));
+            float t = fmul((float)var_d, (float)st->tol_rel);
+            if (st->tol_rel == 0.0) t = 0.f;
+            st->tol = t;
+            S.u.up.red_d[0] = t;
+        }
+        __syncthreads();
+        tol = S.u.up.red_d[0];
+        __syncthreads();
+    }
+    auto now = []() {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+    };
+    const bool logger = want_log && cta == 0 && tid == 0;
+
+    long long hint[LF_R / (LF_CL * (LF_THREADS / 32)) + 1];  // tile found last time for each boundary slot of this warp
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(hint) / sizeof(hint[0])); ++i) hint[i] = -1;
+
+    // one E-step against the centroids in S.c: table, boundary search, zones (results in CTA 0's exchange area)
+    auto e_step = [&](unsigned long long *tlog) {
+        build_region_table(S.c, k, K.xabs_max, &S.tab, S.u.tb, S.perm);
+        const int R = S.tab.R;
+        if (tid < S.tab.m) {
+            S.zW[tid] = 0;
+            S.zS[tid] = 0;
+            S.zmin[tid] = 0x7fffffffffffffffll;
+            S.zmax[tid] = -1;
+        }
+        if (cta == 0) {
+            if (tid == 0) {
+                S.rpos[0] = 0;
+                S.rcnt[0] = 0;
+                S.rsum[0] = 0;
+                S.rpos[R] = K.n_ent;
+                S.rcnt[R] = K.n_nz;
+                S.rsum[R] = total_q;
+            }
+        }
+        if (tlog) tlog[0] = now();
+        int trip = 0;
+        for (int r = 1 + gw; r < R; r += LF_CL * (LF_THREADS / 32), ++trip) {  // one warp per region boundary
+            long long pos, cn, sum;
+            warp_boundary_search(C, S.tab.rstart[r], pos, cn, sum, &hint[trip]);
+            if (lane_id() == 0) {
+                S0->rpos[r] = pos;
+                S0->rcnt[r] = cn;
+                S0->rsum[r] = sum;
+            }
+        }
+        cluster.sync();
+        if (tlog) tlog[1] = now();
+        long long zp[4];
+        fast_zone_step(S, S0, K, C, ks, gw, tlog ? zp : nullptr);
+        if (tlog && S.iter == 6)
+            for (int i = 0; i < 4; ++i) st->logZ[LL_LOG - 16 + i] = zp[i] - zp[0];
+        cluster.sync();
+        if (tlog) tlog[2] = now();
+    };
+
+    cluster.sync();  // every CTA's shared state is initialised before anybody writes into CTA 0's
+    int stopped = 0;
+    for (int it = 0; it < K.max_iter && !stopped; ++it) {
+        unsigned long long tl[5];
+        tl[4] = logger ? now() : 0ull;
+        e_step(logger ? tl : nullptr);
+        if (cta == 0) {
+            long long up[8];
+            const int it_now = S.iter;
+            fast_update_step(cluster, S, K, ks, pc, xseq, tol, logger ? up : nullptr);
+            if (logger && it_now == 6) {
+                up[7] = clock64();
+                for (int i = 0; i < 8; ++i) st->logZ[LL_LOG - 32 + i] = up[i] - up[0];
+            }
+        }
+        cluster.sync();
+        if (cta != 0) {  // pull the new centroids and the stop decision from CTA 0
+            if (tid < k) S.c[tid] = S0->c[tid];
+            if (tid == 0) S.done = S0->done;
+            __syncthreads();
+        }
+        stopped = S.done;
+        if (logger && it < LL_LOG) {
+            st->logT[it][3] = (unsigned int)(tl[0] - tl[4]);      // table
+            st->logT[it][0] = (unsigned int)(tl[1] - tl[0]);      // search (+ barrier)
+            st->logT[it][1] = (unsigned int)(tl[2] - tl[1]);      // zone (+ barrier)
+            st->logT[it][2] = (unsigned int)(now() - tl[2]);      // update (+ barrier, pull)
+        }
+    }
+    // results of the loop (CTA 0 holds them)
+    if (cta == 0) {
+        if (tid < k) {
+            st->c[tid] = S.c[tid];
+            st->c_emit[tid] = S.c_emit[tid];
+        }
+        if (tid == 0) {
+            st->iter = S.iter;
+            st->done = S.done;
+            st->strict = S.strict;
+            st->n_reloc = S.n_reloc;
+            st->n_iter = S.n_iter;
+            st->comm_error = S.comm_error;
+        }
+    }
+    if (want_hist && stopped) {
+        // code histogram of the final labelling: one more E-step against c_emit, counts only
+        cluster.sync();  // CTA 0 has written the results above before its S.c changes
+        if (tid < k) S.c[tid] = S0->c_emit[tid];
+        __syncthreads();
+        e_step(nullptr);
+        if (cta == 0) {
+            long long *Wd = S.u.up.Wd;
+            const RegionTableT<LF_KMAX> &T = S.tab;
+            const int m = T.m, R = T.R;
+            if (tid < k) st->hist[tid] = 0;
+            if (tid < m) {
+                long long w = 0;
+                for (int c2 = 0; c2 < LF_CL; ++c2) w += (long long)cluster.map_shared_rank(&S, c2)->zW[tid];
+                Wd[tid] = w;
+            }
+            __syncthreads();
+            for (int r = tid; r < R; r += LF_THREADS) {
+                if (T.rJ1[r] != T.rJ2[r]) continue;
+                const long long c = S.rcnt[r + 1] - S.rcnt[r];
+                if (c > 0) Wd[T.rJ1[r]] += c;  // (J, J) occurs in at most one region
+            }
+            __syncthreads();
+            if (tid == 0 && K.n0 > 0) Wd[zone_argmin(fsub(0.f, K.mean), T.dv, T.dcn, T.down, 0, m - 1)] += K.n0;
+            __syncthreads();
+            if (tid < m) st->hist[T.down[tid]] = Wd[tid];
+        }
+    }
+    if (pc.enabled && cta == 0 && tid == 0) *peer_counter(pc) = xseq;
+    cluster.sync();  // no CTA exits while another may still access its shared memory
+}
+
+bool lloyd_fast_applicable(int k) { return k >= 1 && k <= LF_KMAX && !getenv("NNC_LLOYD_NO_CLUSTER"); }
+
+// Launches the cluster loop; `st` has its header, moments (s1 / s2 of the sorted survivors) and candidate buffer set.
+void lloyd_fast_launch(nnc_ctx *ctx, LloydDevice *st, const float *d_sorted, const float *samp, const long long *ptile,
+                       const float *d_init, int want_hist, const PeerComm &pc) {
+    func_dyn_smem(ctx, (const void *)ll_fast_kernel, sizeof(FastSmem));
+    const int want_log = getenv("NNC_LLOYD_LOG") ? 1 : 0;
+    NNC_LAUNCH(ctx, ll_fast_kernel, LF_CL, LF_THREADS, sizeof(FastSmem), st, d_sorted, samp, ptile, d_init, want_hist, want_log, pc);
+}
+
+}  // namespace nnc

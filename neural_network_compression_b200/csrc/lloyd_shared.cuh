@@ -80,13 +80,33 @@ struct SearchConst {  // per-launch constants of the search (hoisted out of the 
     const float *top;
     long long top_step;
     int top_n;
+    int vec_ok;     // ks / cnt 16-byte aligned: the tile scan uses 128-bit loads
+    float scale_f;  // 2^(30-E) as a float (0: not representable, use `scale`)
 };
 
-__device__ __forceinline__ void warp_boundary_search(const SearchConst &C, float t, long long &pos_out, long long &cnt_out,
-                                                     long long &sum_out) {
+// fixed-point image without float64 arithmetic: x' * 2^s is exact in float32 (a power-of-two scaling below 2^30), so
+// rint of the float product equals rint of the double product.  scale_f = 2^s as a float, or 0 when 2^s is not a normal
+// float (absurd data ranges): then the float64 expression is used.
+__device__ __forceinline__ long long fixed_qf(float xc, float scale_f, double scale) {
+    return scale_f != 0.f ? (long long)__float2int_rn(__fmul_rn(xc, scale_f)) : fixed_q(xc, scale);
+}
+__device__ __forceinline__ float4 ld_vol_f4(const float *p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_vol_u4(const unsigned int *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// first tile whose first key FAILS the predicate fl(key - mean) < t (n_tiles when none fails): 32-ary search over the
+// shared-memory top level, then over the tile samples
+__device__ __forceinline__ long long warp_locate_tile(const SearchConst &C, float t) {
     const int lane = lane_id();
     const float mean = C.mean;
-    long long lo = 0, hi = C.n_tiles;  // first tile whose first key fails the predicate lies in [lo, hi]
+    long long lo = 0, hi = C.n_tiles;  // the answer lies in [lo, hi]
     if (C.top) {  // coarse level: number of top samples that satisfy the predicate (they are a prefix)
         int a = 0, b = C.top_n;  // first top index failing lies in [a, b]
         while (a < b) {
@@ -130,6 +150,69 @@ __device__ __forceinline__ void warp_boundary_search(const SearchConst &C, float
         lo = nlo;
         hi = nhi;
     }
+    return lo;
+}
+
+__device__ __forceinline__ float ld_vol_f1(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ long long ld_vol_s64(const long long *p) {
+    long long v;
+    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// entries / elements of the sorted survivors with fl(x - mean) < t, and the sum of q over them; one warp per boundary.
+// hint (optional, one per boundary slot of the calling warp, -1 initially): the answer of warp_locate_tile of the previous
+// call for this boundary.  Boundaries move little between Lloyd iterations: the hinted tile is loaded SPECULATIVELY
+// together with the two tile samples that bracket it; when they still bracket t (almost always) the search is ONE memory
+// round trip instead of four.  All loads are volatile asm so that they are issued before the first use (the compiler
+// otherwise sinks every load to its use: 16 serialised round trips).
+__device__ __forceinline__ void warp_boundary_search(const SearchConst &C, float t, long long &pos_out, long long &cnt_out,
+                                                     long long &sum_out, long long *hint = nullptr) {
+    const int lane = lane_id();
+    const float mean = C.mean;
+    float4 a0, a1, a2, a3;
+    uint4 c0 = make_uint4(1u, 1u, 1u, 1u), c1 = c0, c2 = c0, c3 = c0;
+    long long psum = 0, pcnt = 0;
+    auto full_tile = [&](long long tile) { return C.vec_ok && tile >= 0 && (tile + 1) * LL_TS <= C.n_ent; };
+    auto load_tile = [&](long long tile) {  // a complete, 16-byte aligned tile: 128-bit loads, all in flight
+        const long long base = tile * LL_TS;
+        const float *pk = C.ks + base + 4 * lane;
+        a0 = ld_vol_f4(pk);
+        a1 = ld_vol_f4(pk + 128);
+        a2 = ld_vol_f4(pk + 256);
+        a3 = ld_vol_f4(pk + 384);
+        if (C.cnt) {
+            const unsigned int *pc = C.cnt + base + 4 * lane;
+            c0 = ld_vol_u4(pc);
+            c1 = ld_vol_u4(pc + 128);
+            c2 = ld_vol_u4(pc + 256);
+            c3 = ld_vol_u4(pc + 384);
+            pcnt = ld_vol_s64(C.ctile + tile);
+        }
+        psum = ld_vol_s64(C.ptile + tile);
+    };
+    long long lo = -1;
+    bool loaded = false;
+    if (hint) {
+        const long long g = *hint;
+        if (g >= 0 && g <= C.n_tiles) {
+            const bool spec = g >= 1 && full_tile(g - 1);
+            if (spec) load_tile(g - 1);
+            const float below = g > 0 ? ld_vol_f1(C.samp + (g - 1)) : -INFINITY;
+            const float at = g < C.n_tiles ? ld_vol_f1(C.samp + g) : INFINITY;
+            const bool ok = (g == 0 || fsub(below, mean) < t) && (g == C.n_tiles || !(fsub(at, mean) < t));
+            if (ok) {
+                lo = g;
+                loaded = spec;
+            }
+        }
+    }
+    if (lo < 0) lo = warp_locate_tile(C, t);
+    if (hint) *hint = lo;
     if (lo == 0) {
         pos_out = 0;
         cnt_out = 0;
@@ -138,29 +221,42 @@ __device__ __forceinline__ void warp_boundary_search(const SearchConst &C, float
     }
     const long long tile = lo - 1;
     const long long base = tile * LL_TS;
-    // the tile's prefixes and its entries: all loads in flight together
-    const long long psum = C.ptile[tile];
-    const long long pcnt = C.cnt ? C.ctile[tile] : 0;
-    long long npos = 0, acc = 0, cacc = 0;
-    constexpr int PER = LL_TS / 32;
-    float xv[PER];
-    unsigned int cv[PER];
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        const long long i = base + j * 32 + lane;
-        xv[j] = i < C.n_ent ? C.ks[i] : INFINITY;
-        cv[j] = (C.cnt && i < C.n_ent) ? C.cnt[i] : 1u;
+    int npos = 0;
+    long long acc = 0, cacc = 0;
+    if (!loaded && full_tile(tile)) {
+        load_tile(tile);
+        loaded = true;
     }
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        const float xc = fsub(xv[j], mean);
-        const bool p = xc < t;  // padding is +inf: never counted
-        if (p) {
-            acc += fixed_q(xc, C.scale) * (long long)cv[j];
-            cacc += cv[j];
+    if (loaded) {
+        auto one = [&](float x, unsigned int c) {
+            const float xc = fsub(x, mean);
+            if (xc < t) {
+                acc += fixed_qf(xc, C.scale_f, C.scale) * (long long)c;
+                cacc += c;
+                npos += 1;
+            }
+        };
+        one(a0.x, c0.x); one(a0.y, c0.y); one(a0.z, c0.z); one(a0.w, c0.w);
+        one(a1.x, c1.x); one(a1.y, c1.y); one(a1.z, c1.z); one(a1.w, c1.w);
+        one(a2.x, c2.x); one(a2.y, c2.y); one(a2.z, c2.z); one(a2.w, c2.w);
+        one(a3.x, c3.x); one(a3.y, c3.y); one(a3.z, c3.z); one(a3.w, c3.w);
+    } else {  // the last (partial) tile, or an unaligned array
+        psum = C.ptile[tile];
+        if (C.cnt) pcnt = C.ctile[tile];
+        for (int j = 0; j < LL_TS / 32; ++j) {
+            const long long i = base + j * 32 + lane;
+            if (i < C.n_ent) {
+                const float xc = fsub(C.ks[i], mean);
+                if (xc < t) {
+                    const unsigned int c = C.cnt ? C.cnt[i] : 1u;
+                    acc += fixed_qf(xc, C.scale_f, C.scale) * (long long)c;
+                    cacc += c;
+                    npos += 1;
+                }
+            }
         }
-        npos += __popc(__ballot_sync(0xffffffffu, p));
     }
+    npos = warp_sum_i(npos);
     acc = warp_sum_ll(acc);
     pos_out = base + npos;
     cnt_out = C.cnt ? pcnt + warp_sum_ll(cacc) : pos_out;
@@ -181,6 +277,9 @@ __device__ __forceinline__ SearchConst search_const(const LloydDevice *st, const
     C.top = nullptr;
     C.top_step = 1;
     C.top_n = 0;
+    C.vec_ok = ((reinterpret_cast<uintptr_t>(ks) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(st->cnt) & 15u) == 0);
+    const int sh = 30 - st->fixed_exp;
+    C.scale_f = (sh >= -126 && sh <= 127) ? __int_as_float((sh + 127) << 23) : 0.f;
     return C;
 }
 // NumPy pairwise sum of a small float32 array (numpy/_core/src/umath/loops_utils.h.src), single thread.
@@ -223,5 +322,10 @@ __device__ __forceinline__ FarKey far_key(float xc, float c) {
     k.ordx = ox;
     return k;
 }
+
+// lloyd_fast.cu: the loop as one thread-block cluster with its state in shared memory (k <= 512)
+bool lloyd_fast_applicable(int k);
+void lloyd_fast_launch(nnc_ctx *ctx, LloydDevice *st, const float *d_sorted, const float *samp, const long long *ptile,
+                       const float *d_init, int want_hist, const PeerComm &pc);
 
 }  // namespace nnc

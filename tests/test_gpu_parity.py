@@ -352,6 +352,27 @@ def test_kmeans_per_phase_launch_paths(U, monkeypatch, env, bits, mode):
     assert km1.inertia_ == km0.inertia_
 
 
+@pytest.mark.parametrize("bits,mode", [(2, "density"), (4, "linear"), (8, "linear"), (8, "density"), (5, "forgy"), (9, "linear")])
+def test_kmeans_cluster_loop_equals_cooperative_loop(U, monkeypatch, bits, mode):
+    # lloyd_fast.cu (one thread-block cluster, state in shared memory) against lloyd.cu's cooperative one-launch loop:
+    # same fit bit for bit, relocation iterations included (8-bit linear / density on pruned data empty dozens of
+    # clusters at once); 9 bits = 512 clusters is the largest codebook of the cluster path
+    w = D.gaussian(300 * 1000, seed=6)
+    O.prune_weigth(w, 1)
+    cdfs = U.get_weight_distribution(w, skip_zeros=True) if mode == "density" else None
+    np.random.seed(4)
+    ris0, km0 = U.get_quantized_weight(w, bits, mode, cdfs)
+    monkeypatch.setenv("NNC_LLOYD_NO_CLUSTER", "1")
+    np.random.seed(4)
+    ris1, km1 = U.get_quantized_weight(w, bits, mode, cdfs)
+    assert km1.n_iter_ == km0.n_iter_ and km1.n_relocations == km0.n_relocations and km1.strict_convergence == km0.strict_convergence
+    assert km1.cluster_centers_.tobytes() == km0.cluster_centers_.tobytes()
+    assert km1.tol_ == km0.tol_
+    assert ris1.tobytes() == ris0.tobytes() and np.array_equal(km1.code_histogram, km0.code_histogram)
+    if bits == 8:
+        assert km0.n_relocations > 0
+
+
 def test_kmeans_errors(U):
     w = D.gaussian(1000, seed=2)
     with pytest.raises(Exception, match="error mode not found"):
