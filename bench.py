@@ -544,7 +544,7 @@ def kernel_bytes(name, n, n_nz):
 def run_e2e(args, torch, U, n_local, rank, world, dist, dev):
     steps = max(1, min(args.steps, args.e2e_steps))
     host = torch.empty(n_local, dtype=torch.float32).pin_memory()
-    out_mask = torch.empty(n_local, dtype=torch.uint8).pin_memory()
+    out_mask = torch.empty((n_local + 7) // 8, dtype=torch.uint8).pin_memory()  # the 1-bit mask of the compressed-layer format
     out_packed = torch.empty(n_local * BITS // 8, dtype=torch.uint8).pin_memory()
     src = (torch.randn(n_local, generator=torch.Generator().manual_seed(SEED + 100 + rank)) * SIGMA) if n_local <= (1 << 26) else None
     total = 0.0
@@ -563,7 +563,7 @@ def run_e2e(args, torch, U, n_local, rank, world, dist, dev):
         t0 = time.perf_counter()
         arr = host.numpy()
         mask, km = U.compress_weight(arr, QUALITY, True, BITS, MODE, update_weights=False, out_mask=out_mask.numpy(),
-                                     out_packed=out_packed.numpy())
+                                     out_packed=out_packed.numpy(), mask_bits=True)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if os.environ.get("NNC_BENCH_VERBOSE"):
@@ -572,13 +572,14 @@ def run_e2e(args, torch, U, n_local, rank, world, dist, dev):
             total += dt
         # one fused call: w in; mask + packed codes (+ k centroids, histogram) out
         h2d = 4 * n_local
-        d2h = n_local + km.packed_codes.nbytes + 4 * km.n_clusters + 8 * km.n_clusters
+        d2h = (n_local + 7) // 8 + km.packed_codes.nbytes + 4 * km.n_clusters + 8 * km.n_clusters
     if dist is not None:
         t = torch.tensor([total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total = float(t.item())
     return {"value": args.n * steps / total, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "steps": steps, "ms_per_step": 1e3 * total / steps, "api": "utility.compress_weight(pinned host ndarray, update_weights=False, pinned out_mask/out_packed) -> nnc_compress_f32"}
+            "steps": steps, "ms_per_step": 1e3 * total / steps, "api": "utility.compress_weight(pinned host ndarray, update_weights=False, pinned out_mask/out_packed, mask_bits=True) -> nnc_compress_f32: "
+                   "float32 weights in; the compressed layer out (1-bit mask, packed 8-bit codes, codebook, histogram)"}
 
 
 def main():

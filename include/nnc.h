@@ -118,6 +118,8 @@ typedef struct {
 
 #define NNC_KM_INERTIA 1     /* also compute KMeans.inertia_ (costs arithmetic in the emission pass) */
 #define NNC_KM_INIT_LINEAR 2 /* init = np.linspace(w.min(), w.max(), k) in float32 (utility.py:206-209); `init` may be NULL */
+#define NNC_KM_MASK_BITS 4   /* nnc_compress_f32: `mask` receives ceil(n/8) bytes, bit i of byte i/8 (the 1-bit mask of the
+                              * compressed-layer format) instead of one byte per weight */
 
 /* KMeans(n_clusters=k, init=init, n_init=1, algorithm="lloyd", max_iter, tol).fit(w.reshape(-1,1)).
  * Outputs (any may be NULL): centers[k] = cluster_centers_; centred[k] = centres in sklearn's
@@ -149,6 +151,10 @@ int nnc_assign_f32(nnc_ctx *ctx, const float *w, int64_t n, const float *centred
 /* Codebook de-quantisation: out[i] = values[code_i] from packed n-bit codes. */
 int nnc_unpack_gather_f32(nnc_ctx *ctx, const uint8_t *packed, int64_t n, int bits, const float *values, int k,
                           float *out);
+
+/* 0/1 bytes -> bits (bit i of byte i/8 = src[i] != 0): packs a pruning mask (the reference keeps it as a NumPy bool array,
+ * common/trainer.py:25,192) for the compressed-layer format of common/storage.py. */
+int nnc_pack_bits_u8(nnc_ctx *ctx, const uint8_t *src, int64_t n, uint8_t *dst_bits);
 
 /* Trained-quantization gradient sum (papers/lat/report.tex:152): out[j] = sum_i grad[i] * [code_i == j].
  * codes: packed n-bit stream when bits > 0, int32 labels when bits == 0. */

@@ -25,6 +25,7 @@ NNC_ERR_COMM = 7
 NNC_KMAX = 1024
 NNC_KM_INERTIA = 1
 NNC_KM_INIT_LINEAR = 2
+NNC_KM_MASK_BITS = 4
 
 # every symbol include/nnc.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -34,7 +35,7 @@ EXPORTS = [
     "nnc_kmeans1d_f32", "nnc_assign_f32", "nnc_unpack_gather_f32", "nnc_grad_segsum_f32", "nnc_ctx_set_comm",
     "nnc_ctx_set_kernel_timing", "nnc_last_kernel_times", "nnc_ctx_total_launches",
     "nnc_compress_f32", "nnc_shard_range", "nnc_comm_unique_id", "nnc_ctx_init_nccl",
-    "nnc_peer_mailbox_create", "nnc_peer_mailbox_connect",
+    "nnc_peer_mailbox_create", "nnc_peer_mailbox_connect", "nnc_pack_bits_u8",
 ]
 
 
@@ -138,6 +139,7 @@ def lib():
         L.nnc_assign_f32.argtypes = [vp, vp, i64, vp, i32, f32, vp, vp, vp, vp, i32, vp, P(f64)]
         L.nnc_unpack_gather_f32.argtypes = [vp, vp, i64, i32, vp, i32, vp]
         L.nnc_grad_segsum_f32.argtypes = [vp, vp, vp, i64, i32, i32, vp]
+        L.nnc_pack_bits_u8.argtypes = [vp, vp, i64, vp]
         L.nnc_ctx_set_kernel_timing.argtypes = [vp, i32, C.c_char_p]
         L.nnc_last_kernel_times.argtypes = [vp, P(C.c_char_p)]
         L.nnc_ctx_total_launches.argtypes = [vp, P(i64)]

@@ -23,6 +23,7 @@ from .. import _native as N
 __all__ = [
     "prune_weigth", "apply_mask", "get_weight_distribution", "get_quantized_weight", "KMeansResult",
     "compress_weight", "init_distributed", "shard_range", "nonzero_weights", "weight_stats", "assign_codes", "dequantize", "cluster_gradient_sum", "index_bits",
+    "pack_mask_bits",
 ]
 
 
@@ -194,6 +195,29 @@ def apply_mask(weights, mask):
     N.check(N.lib().nnc_mask_apply_f32(ctx.handle, buf.ptr, N.ptr(m), buf.n))
     buf.finish()
     return weights
+
+
+def pack_mask_bits(mask):
+    """The pruning mask as bits (bit i of byte i // 8 = mask.flat[i]): the 1-bit mask of the compressed-layer format
+    (common/storage.py).  Host bool / uint8 arrays and device tensors; the result lives where the input lives."""
+    if N.is_torch(mask):
+        import torch
+
+        m = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.contiguous()
+        n = m.numel()
+        out = torch.empty((n + 7) // 8, dtype=torch.uint8, device=m.device)
+        ctx = N.default_context(N.device_of(m))
+        if m.is_cuda:
+            ctx.set_stream(torch.cuda.current_stream(m.device).cuda_stream)
+    else:
+        m = np.ascontiguousarray(mask)
+        m = m.view(np.uint8) if m.dtype == np.bool_ else m.astype(np.uint8)
+        n = m.size
+        out = np.empty((n + 7) // 8, dtype=np.uint8)
+        ctx = N.default_context(None)
+        ctx.set_stream(None)
+    N.check(N.lib().nnc_pack_bits_u8(ctx.handle, N.ptr(m), n, N.ptr(out)))
+    return out
 
 
 def weight_stats(w):
@@ -387,7 +411,7 @@ def _init_space(buf: _Buf, ctx: N.Context, bits: int, mode: str, cdfs):
 
 
 def compress_weight(original_weigth, threshold=0.25, std_smooth=True, bits=4, mode="linear", with_cdf=True,
-                    update_weights=True, out_mask=None, out_packed=None):
+                    update_weights=True, out_mask=None, out_packed=None, mask_bits=False):
     """The whole compression of one tensor as Trainer._prune_parameters + Trainer.quantize apply it
     (trainer.py:177-193, :42-72): std-threshold prune, then k-means weight sharing of the pruned tensor, keeping
     only the compressed representation -- the boolean mask, the codebook, the packed n-bit cluster indices and
@@ -398,6 +422,10 @@ def compress_weight(original_weigth, threshold=0.25, std_smooth=True, bits=4, mo
     codebook values anyway): the tensor crosses the bus once.  out_mask / out_packed: optional preallocated
     (e.g. pinned) uint8 output buffers for host arrays.
 
+    mask_bits=True (linear init only): the mask comes back bit-packed -- ceil(n / 8) uint8, bit i of byte i // 8, the
+    layout of common/storage.py -- instead of one bool per weight: a compressed layer then leaves the device as
+    n * (bits + 1) / 8 bytes.
+
     Returns (mask, KMeansResult); `KMeansResult.labels_` is None (decode with `dequantize`)."""
     buf = _Buf(original_weigth, "original_weigth", writable=True)
     if buf.n < (2 ** bits) + 1:
@@ -406,6 +434,8 @@ def compress_weight(original_weigth, threshold=0.25, std_smooth=True, bits=4, mo
         return mask, None
     ctx = _ctx_for(buf)
     if mode != "linear":
+        if mask_bits:
+            raise ValueError("mask_bits=True needs mode='linear' (the fused call); pack other masks with pack_mask_bits")
         # density / forgy initialise from the PRUNED tensor: prune first, then the reference's init, then k-means
         mask = prune_weigth(original_weigth, threshold, std_smooth)
         prune_prof, _ = ctx.last_profile()
@@ -425,7 +455,7 @@ def compress_weight(original_weigth, threshold=0.25, std_smooth=True, bits=4, mo
     k = 2 ** bits
     cbits = index_bits(k)
     thr_mode = 1 if isinstance(threshold, np.float64) else 0
-    mask = out_mask if out_mask is not None else buf.empty(buf.n, np.uint8)
+    mask = out_mask if out_mask is not None else buf.empty((buf.n + 7) // 8 if mask_bits else buf.n, np.uint8)
     packed = out_packed if out_packed is not None else buf.empty((buf.n * cbits + 7) // 8, np.uint8)
     centers = np.empty(k, dtype=np.float32)
     centred = np.empty(k, dtype=np.float32)
@@ -435,7 +465,7 @@ def compress_weight(original_weigth, threshold=0.25, std_smooth=True, bits=4, mo
     try:
         N.check(N.lib().nnc_compress_f32(ctx.handle, buf.ptr, buf.n, float(threshold), int(bool(std_smooth)), thr_mode,
                                          int(bool(update_weights)), N.ptr(mask), C.byref(thr_out), C.byref(n_pruned), None, k,
-                                         300, 1e-4, N.NNC_KM_INIT_LINEAR, N.ptr(centers), N.ptr(centred), N.ptr(packed), cbits,
+                                         300, 1e-4, N.NNC_KM_INIT_LINEAR | (N.NNC_KM_MASK_BITS if mask_bits else 0), N.ptr(centers), N.ptr(centred), N.ptr(packed), cbits,
                                          N.ptr(hist), C.byref(info)))
     except N.NncError as e:
         if e.code == N.NNC_ERR_NONFINITE:
@@ -452,6 +482,8 @@ def compress_weight(original_weigth, threshold=0.25, std_smooth=True, bits=4, mo
         packed_codes=packed, code_bits=cbits, code_histogram=hist, centred_centers=centred, mean=np.float32(info.mean),
         strict_convergence=bool(info.strict), n_relocations=info.n_relocations, n_nonzero=info.n_nonzero,
         tol_=float(info.tol), profile=prof)
+    if mask_bits:
+        return mask, res
     if buf.kind == "torch":
         import torch
 

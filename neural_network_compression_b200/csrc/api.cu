@@ -887,7 +887,17 @@ int nnc_compress_f32(nnc_ctx *ctx, float *w, int64_t n, double threshold, int st
     if (!w || !mask || n <= 0) NNC_FAIL(NNC_ERR_BAD_ARG, "nnc_compress_f32: null buffer or empty input");
     shard_setup(ctx, n);
     Staged sw = stage_inout(ctx, w, sizeof(float) * (size_t)n);
-    Staged sm = stage_out(ctx, mask, (size_t)n);
+    // NNC_KM_MASK_BITS: `mask` receives ceil(n / 8) bytes (bit i of byte i / 8), the byte mask stays in the workspace
+    const bool mask_bits = (flags & NNC_KM_MASK_BITS) != 0;
+    Staged sm;
+    uint8_t *d_mask_bytes = nullptr;
+    if (mask_bits) {
+        d_mask_bytes = arena_alloc_t<uint8_t>(ctx, (size_t)n);
+        sm = stage_out(ctx, mask, (size_t)((n + 7) / 8));
+    } else {
+        sm = stage_out(ctx, mask, (size_t)n);
+        d_mask_bytes = static_cast<uint8_t *>(sm.dev);
+    }
     prof_mark(ctx, "h2d");
     float *d_w = static_cast<float *>(sw.dev);
     // with the std-scaled threshold the k-means prologue of the pruned tensor rides on the apply pass (one sweep less)
@@ -896,8 +906,9 @@ int nnc_compress_f32(nnc_ctx *ctx, float *w, int64_t n, double threshold, int st
         fuse.out = arena_alloc_t<float>(ctx, (size_t)n);
         fuse.capacity = n;
     }
-    prune_device(ctx, d_w, n, threshold, std_smooth, threshold_mode, static_cast<uint8_t *>(sm.dev), fuse.out ? &fuse : nullptr);
+    prune_device(ctx, d_w, n, threshold, std_smooth, threshold_mode, d_mask_bytes, fuse.out ? &fuse : nullptr);
     if (write_back) stage_finish(ctx, sw);  // a device-resident tensor was pruned in place already
+    if (mask_bits) pack_bits_device(ctx, d_mask_bytes, n, static_cast<uint8_t *>(sm.dev));
     stage_finish(ctx, sm);
     read_scalars(ctx);
     prof_mark(ctx, "prune_d2h");
@@ -944,6 +955,20 @@ int nnc_unpack_gather_f32(nnc_ctx *ctx, const uint8_t *packed, int64_t n, int bi
     unpack_gather_device(ctx, static_cast<const uint8_t *>(sp.dev), n, bits, values, k, static_cast<float *>(so.dev));
     prof_mark(ctx, "unpack");
     stage_finish(ctx, so);
+    NNC_CUDA(cudaStreamSynchronize(ctx->stream));
+    call.finish();
+    NNC_CATCH
+}
+
+int nnc_pack_bits_u8(nnc_ctx *ctx, const uint8_t *src, int64_t n, uint8_t *dst_bits) {
+    NNC_TRY
+    Call call(ctx);
+    if (!src || !dst_bits || n <= 0) NNC_FAIL(NNC_ERR_BAD_ARG, "nnc_pack_bits_u8: bad argument");
+    Staged ss = stage_in(ctx, src, (size_t)n);
+    Staged sd = stage_out(ctx, dst_bits, (size_t)((n + 7) / 8));
+    pack_bits_device(ctx, static_cast<const uint8_t *>(ss.dev), n, static_cast<uint8_t *>(sd.dev));
+    prof_mark(ctx, "pack_bits");
+    stage_finish(ctx, sd);
     NNC_CUDA(cudaStreamSynchronize(ctx->stream));
     call.finish();
     NNC_CATCH

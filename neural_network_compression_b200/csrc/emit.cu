@@ -426,6 +426,40 @@ __global__ void __launch_bounds__(256) unpack_gather_kernel(const uint8_t *__res
     }
 }
 
+// 0/1 bytes -> bits (bit i of byte i / 8 = byte i != 0): the 1-bit pruning mask of the compressed-layer format
+// (common/storage.py).  A thread packs 16 mask bytes (one 128-bit load) into two output bytes.
+__global__ void __launch_bounds__(256) pack_bits_kernel(const uint8_t *__restrict__ src, int64_t n, uint8_t *__restrict__ dst, int vec_ok) {
+    const int64_t n16 = vec_ok ? n >> 4 : 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(src + 16 * i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t out = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t b = w[j];
+            b = (b | (b >> 1) | (b >> 2) | (b >> 3) | (b >> 4) | (b >> 5) | (b >> 6) | (b >> 7)) & 0x01010101u;  // byte != 0
+            out |= (((b * 0x10204080u) >> 28) & 0xfu) << (4 * j);  // gather the four flag bits
+        }
+        *reinterpret_cast<uint16_t *>(dst + 2 * i) = (uint16_t)out;
+    }
+    // tail (and the whole array when it is not 16-byte aligned): one output byte per thread
+    const int64_t b0 = n16 * 2, nb = (n + 7) >> 3;
+    for (int64_t b = b0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t out = 0;
+        for (int j = 0; j < 8; ++j) {
+            const int64_t e = 8 * b + j;
+            if (e < n && src[e]) out |= 1u << j;
+        }
+        dst[b] = (uint8_t)out;
+    }
+}
+
+void pack_bits_device(nnc_ctx *ctx, const uint8_t *d_src, int64_t n, uint8_t *d_dst) {
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(d_src) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_dst) & 1u) == 0);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 16, (n / 16 + 255) / 256 + 1));
+    NNC_LAUNCH(ctx, pack_bits_kernel, grid, 256, 0, d_src, n, d_dst, vec_ok);
+}
+
 void unpack_gather_device(nnc_ctx *ctx, const uint8_t *d_packed, int64_t n, int bits, const float *h_values, int k,
                           float *d_out) {
     if (bits < 1 || bits > 16) NNC_FAIL(NNC_ERR_BAD_ARG, "unpack: bits = %d outside [1, 16]", bits);

@@ -128,6 +128,7 @@ struct nnc_ctx {
     void *allreduce_user = nullptr;
     // kernels whose dynamic shared-memory limit has been raised ON THIS CONTEXT'S DEVICE (the attribute is per device)
     std::vector<std::pair<const void *, size_t>> func_smem;
+    int fast_cluster = 0;  // CTAs per cluster of the Lloyd cluster kernel on this device (0: not decided yet)
 };
 
 namespace nnc {
@@ -275,6 +276,7 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
 void emit_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *h_centred, const float *h_centred_final, int k,
                  float mean, float xabs, float xlo, float xhi, const float *h_values, int32_t *d_labels, float *d_ris, uint8_t *d_packed, int bits,
                  int64_t *h_hist, double *h_inertia);
+void pack_bits_device(nnc_ctx *ctx, const uint8_t *d_src, int64_t n, uint8_t *d_dst);
 void unpack_gather_device(nnc_ctx *ctx, const uint8_t *d_packed, int64_t n, int bits, const float *h_values, int k,
                           float *d_out);
 // segsum.cu

@@ -1085,7 +1085,9 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         unsigned int tb[2];
         NNC_CUDA(cudaMemcpy(tb, st->logT[LL_LOG - 1], sizeof(tb), cudaMemcpyDeviceToHost));
         fprintf(stderr, "[nnc lloyd] four bare grid barriers: %.2f us\n", (tb[1] - tb[0]) * 1e-3);
-        long long zp[4], up[8];
+        long long zp[4], up[8], tb2 = 0;
+        NNC_CUDA(cudaMemcpy(&tb2, st->logZ + LL_LOG - 40, sizeof(tb2), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[nnc lloyd] second (warm) table build in the same iteration: %.2f us\n", tb2 * 1e-3);
         NNC_CUDA(cudaMemcpy(zp, st->logZ + LL_LOG - 16, sizeof(zp), cudaMemcpyDeviceToHost));
         NNC_CUDA(cudaMemcpy(up, st->logZ + LL_LOG - 32, sizeof(up), cudaMemcpyDeviceToHost));
         fprintf(stderr, "[nnc lloyd] zone profile (cycles): prefix %lld elements %lld flush %lld\n", zp[1], zp[2], zp[3]);

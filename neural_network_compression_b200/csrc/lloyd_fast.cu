@@ -30,8 +30,7 @@ namespace cg = cooperative_groups;
 namespace nnc {
 
 constexpr int LF_KMAX = 512;
-constexpr int LF_CL = 8;  // CTAs per cluster (portable maximum)
-constexpr int LF_THREADS = 1024;
+constexpr int LF_CL_MAX = 16;  // CTAs per cluster: 16 (non-portable size, one GPC) x 512 threads, or 8 x 1024
 constexpr int LF_R = 2 * LF_KMAX + 2;
 
 // scratch of np_pairwise_warp
@@ -176,7 +175,7 @@ __device__ __forceinline__ int fast_label_at(const FastSmem &S, const float *ks,
 constexpr int LF_ZONE_WARP = 2048;
 
 // one warp: entries [lo, hi) of region r, any number of candidates; accumulates into the CTA's partials
-__device__ __forceinline__ void fast_zone_generic(FastSmem &S, const FastConst &K, const SearchConst &C, const float *__restrict__ ks,
+__device__ __noinline__ void fast_zone_generic(FastSmem &S, const FastConst &K, const SearchConst &C, const float *__restrict__ ks,
                                                   int J2, int J1, long long lo, long long hi) {
     const RegionTableT<LF_KMAX> &T = S.tab;
     const int lane = lane_id();
@@ -212,21 +211,21 @@ __device__ __forceinline__ void fast_zone_generic(FastSmem &S, const FastConst &
 }
 
 __device__ void fast_zone_step(FastSmem &S, FastSmem *S0, const FastConst &K, const SearchConst &C, const float *__restrict__ ks,
-                               int gw, long long *prof = nullptr) {
+                               int gw, int NW, long long *prof = nullptr) {
+    const int NT = blockDim.x;
     if (prof) prof[0] = clock64();
     FastZone &Z = S.u.zn;
     const RegionTableT<LF_KMAX> &T = S.tab;
     const int R = T.R, tid = threadIdx.x, lane = lane_id();
     if (R <= 1) return;
-    for (int r = tid; r <= R; r += LF_THREADS) Z.rp[r] = S0->rpos[r];
+    for (int r = tid; r <= R; r += NT) Z.rp[r] = S0->rpos[r];
     __syncthreads();
     if (prof) prof[1] = clock64();
-    constexpr int NW = LF_CL * (LF_THREADS / 32);
     const unsigned int *__restrict__ ecnt = K.cnt;
     // is there a zone too large for one warp?  Every CTA looks at ALL regions (one per thread), so the whole cluster takes
     // the same decision
     int big = 0;
-    for (int r = tid; r < R; r += LF_THREADS) big |= (T.rJ1[r] > T.rJ2[r]) && (Z.rp[r + 1] - Z.rp[r] > LF_ZONE_WARP);
+    for (int r = tid; r < R; r += NT) big |= (T.rJ1[r] > T.rJ2[r]) && (Z.rp[r + 1] - Z.rp[r] > LF_ZONE_WARP);
     // zones are normally the ODD regions (SAFE and ZONE alternate): odd regions first, one per warp, then the even ones
     // (zones only in degenerate layouts) -- a plain r = gw, gw + NW, ... would leave every second warp without work
     for (int pass = 0; pass < 2; ++pass)
@@ -333,6 +332,7 @@ __device__ void fast_zone_step(FastSmem &S, FastSmem *S0, const FastConst &K, co
 __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const FastConst &K, const float *__restrict__ ks,
                                  const PeerComm &pc, unsigned long long &xseq, float tol, long long *prof = nullptr) {
     FastUpdate &U = S.u.up;
+    const int NT = blockDim.x, n_cta = (int)cluster.num_blocks();
     if (prof) prof[0] = clock64();
     const RegionTableT<LF_KMAX> &T = S.tab;
     const int tid = threadIdx.x, k = K.k, m = T.m, R = T.R;
@@ -342,14 +342,32 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
     // ---- 1. per distinct index: zone partials of every CTA (pulled over DSMEM) + SAFE regions
     if (tid < m) {
         long long w = 0, sm = 0, mn = 0x7fffffffffffffffll, mx = -1;
+        // one array at a time, its n_cta loads in flight together (volatile: the compiler must not chain them)
+        long long v[LF_CL_MAX];
 #pragma unroll
-        for (int cta = 0; cta < LF_CL; ++cta) {
-            const FastSmem *Sc = cluster.map_shared_rank(&S, cta);
-            w += (long long)Sc->zW[tid];
-            sm += Sc->zS[tid];
-            mn = llmin2(mn, Sc->zmin[tid]);
-            mx = llmax2(mx, Sc->zmax[tid]);
-        }
+        for (int cta = 0; cta < LF_CL_MAX; ++cta)
+            if (cta < n_cta) v[cta] = (long long)((const volatile FastSmem *)cluster.map_shared_rank(&S, cta))->zW[tid];
+#pragma unroll
+        for (int cta = 0; cta < LF_CL_MAX; ++cta)
+            if (cta < n_cta) w += v[cta];
+#pragma unroll
+        for (int cta = 0; cta < LF_CL_MAX; ++cta)
+            if (cta < n_cta) v[cta] = ((const volatile FastSmem *)cluster.map_shared_rank(&S, cta))->zS[tid];
+#pragma unroll
+        for (int cta = 0; cta < LF_CL_MAX; ++cta)
+            if (cta < n_cta) sm += v[cta];
+#pragma unroll
+        for (int cta = 0; cta < LF_CL_MAX; ++cta)
+            if (cta < n_cta) v[cta] = ((const volatile FastSmem *)cluster.map_shared_rank(&S, cta))->zmin[tid];
+#pragma unroll
+        for (int cta = 0; cta < LF_CL_MAX; ++cta)
+            if (cta < n_cta) mn = llmin2(mn, v[cta]);
+#pragma unroll
+        for (int cta = 0; cta < LF_CL_MAX; ++cta)
+            if (cta < n_cta) v[cta] = ((const volatile FastSmem *)cluster.map_shared_rank(&S, cta))->zmax[tid];
+#pragma unroll
+        for (int cta = 0; cta < LF_CL_MAX; ++cta)
+            if (cta < n_cta) mx = llmax2(mx, v[cta]);
         U.Wd[tid] = w;
         U.Sd[tid] = sm;
         U.first[tid] = mn;
@@ -364,7 +382,7 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
         U.n_empty = 0;
     }
     __syncthreads();
-    for (int r = tid; r < R; r += LF_THREADS) {  // SAFE regions: positions [rpos[r], rpos[r+1]) carry one label
+    for (int r = tid; r < R; r += NT) {  // SAFE regions: positions [rpos[r], rpos[r+1]) carry one label
         if (T.rJ1[r] != T.rJ2[r]) continue;
         const int di = T.rJ1[r];
         const long long lo = S.rpos[r], hi = S.rpos[r + 1];
@@ -447,7 +465,7 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
         const int e = (tid < k) && (U.W[tid] == 0);
         const int incl = block_scan_incl<int>(e, [](int a, int b) { return a + b; }, U.red_i);
         if (e) U.empt[incl - 1] = tid;
-        if (tid == LF_THREADS - 1) U.n_empty = incl;
+        if (tid == NT - 1) U.n_empty = incl;
         __syncthreads();
     }
     const int n_empty = U.n_empty;
@@ -578,7 +596,7 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
         }
         __syncthreads();
         // unused slots of this rank, and (before the all-gather) every slot of the other ranks, hold zeros
-        for (int i = tid; i < K.world * k; i += LF_THREADS) {
+        for (int i = tid; i < K.world * k; i += NT) {
             const int r = i / k, j = i - r * k;
             if (r != K.rank || j >= n_done) {
                 K.cand[2 * (size_t)i] = 0;
@@ -590,7 +608,7 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
         if (pc.enabled) {  // fused all-gather of the candidate lists (n_empty is the same on every rank)
             const int cnt = 2 * n_empty;
             const unsigned long long *mine = K.cand + (size_t)K.rank * k * 2;
-            for (int i = tid; i < cnt; i += LF_THREADS) S.xbuf[i] = (long long)mine[i];
+            for (int i = tid; i < cnt; i += NT) S.xbuf[i] = (long long)mine[i];
             __syncthreads();
             if (!peer_allgather(pc, reinterpret_cast<const unsigned long long *>(S.xbuf), cnt, K.cand, (size_t)k * 2, ++xseq) &&
                 tid == 0)
@@ -720,16 +738,20 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
     __syncthreads();
 }
 
-__global__ void __cluster_dims__(LF_CL, 1, 1) __launch_bounds__(LF_THREADS, 1)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
     ll_fast_kernel(LloydDevice *st, const float *__restrict__ ks, const float *__restrict__ samp, const long long *__restrict__ ptile,
                    const float *__restrict__ init, int want_hist, int want_log, PeerComm pc) {
     extern __shared__ __align__(16) unsigned char fast_smem_raw[];
     FastSmem &S = *reinterpret_cast<FastSmem *>(fast_smem_raw);
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned cta = cluster.block_rank();
+    const int n_cta = (int)cluster.num_blocks();
     FastSmem *S0 = cluster.map_shared_rank(&S, 0);
+    constexpr int NT = THREADS;
     const int tid = threadIdx.x;
-    const int gw = (int)cta * (LF_THREADS / 32) + warp_id();  // warp index inside the cluster
+    const int NW = n_cta * (NT / 32);                  // warps of the cluster
+    const int gw = (int)cta * (NT / 32) + warp_id();  // warp index inside the cluster
 
     FastConst K;
     K.k = st->k;
@@ -750,7 +772,7 @@ __global__ void __cluster_dims__(LF_CL, 1, 1) __launch_bounds__(LF_THREADS, 1)
     if (C.n_tiles > 64) {  // top level of the tile-sample index in shared memory (the samples never change)
         C.top_step = (C.n_tiles + LL_TOP - 1) / LL_TOP;
         C.top_n = (int)((C.n_tiles + C.top_step - 1) / C.top_step);
-        for (int i = tid; i < C.top_n; i += LF_THREADS) S.top[i] = samp[(long long)i * C.top_step];
+        for (int i = tid; i < C.top_n; i += NT) S.top[i] = samp[(long long)i * C.top_step];
         C.top = S.top;
     }
     const long long total_q = C.n_tiles > 0 ? ptile[C.n_tiles] : 0ll;
@@ -809,12 +831,20 @@ __global__ void __cluster_dims__(LF_CL, 1, 1) __launch_bounds__(LF_THREADS, 1)
     };
     const bool logger = want_log && cta == 0 && tid == 0;
 
-    long long hint[LF_R / (LF_CL * (LF_THREADS / 32)) + 1];  // tile found last time for each boundary slot of this warp
+    long long hint[10];  // tile found last time for each boundary slot of this warp (<= 1022 boundaries over >= 128 warps)
 #pragma unroll
-    for (int i = 0; i < (int)(sizeof(hint) / sizeof(hint[0])); ++i) hint[i] = -1;
+    for (int i = 0; i < 10; ++i) hint[i] = -1;
 
-    // one E-step against the centroids in S.c: table, boundary search, zones (results in CTA 0's exchange area)
-    auto e_step = [&](unsigned long long *tlog) {
+    cluster.sync();  // every CTA's shared state is initialised before anybody writes into CTA 0's
+    // One loop body for the Lloyd iterations AND the closing histogram round (one more E-step against c_emit, counts only):
+    // a second copy of the E-step would double the kernel's code, and this kernel is bound by instruction fetch as much as
+    // by memory latency (every phase is straight-line code executed once per iteration).
+    bool hist_round = false;
+    for (int it = 0;; ++it) {
+        unsigned long long tl[5];
+        const bool lg = logger && !hist_round;
+        tl[4] = lg ? now() : 0ull;
+        // ---- E-step against the centroids in S.c: table, boundary search, zones
         build_region_table(S.c, k, K.xabs_max, &S.tab, S.u.tb, S.perm);
         const int R = S.tab.R;
         if (tid < S.tab.m) {
@@ -823,108 +853,109 @@ __global__ void __cluster_dims__(LF_CL, 1, 1) __launch_bounds__(LF_THREADS, 1)
             S.zmin[tid] = 0x7fffffffffffffffll;
             S.zmax[tid] = -1;
         }
+        if (cta == 0 && tid == 0) {
+            S.rpos[0] = 0;
+            S.rcnt[0] = 0;
+            S.rsum[0] = 0;
+            S.rpos[R] = K.n_ent;
+            S.rcnt[R] = K.n_nz;
+            S.rsum[R] = total_q;
+        }
+        if (lg) tl[0] = now();
+        if (want_log > 1) {  // experiment: the same table build again, warm (instruction cache, shared memory state)
+            const unsigned long long w0 = now();
+            build_region_table(S.c, k, K.xabs_max, &S.tab, S.u.tb, S.perm);
+            if (lg && it == 6) st->logZ[LL_LOG - 40] = (long long)(now() - w0);
+            if (lg) tl[0] = now();
+        }
+        {
+            int trip = 0;
+#pragma unroll 1
+            for (int r = 1 + gw; r < R; r += NW, ++trip) {  // one warp per region boundary
+                long long pos, cn, sum;
+                warp_boundary_search(C, S.tab.rstart[r], pos, cn, sum, &hint[trip < 10 ? trip : 9]);
+                if (lane_id() == 0) {
+                    S0->rpos[r] = pos;
+                    S0->rcnt[r] = cn;
+                    S0->rsum[r] = sum;
+                }
+            }
+        }
+        cluster.sync();
+        if (lg) tl[1] = now();
+        {
+            long long zp[4];
+            fast_zone_step(S, S0, K, C, ks, gw, NW, lg ? zp : nullptr);
+            if (lg && S.iter == 6)
+                for (int i = 0; i < 4; ++i) st->logZ[LL_LOG - 16 + i] = zp[i] - zp[0];
+        }
+        cluster.sync();
+        if (lg) tl[2] = now();
+        // ---- M-step (CTA 0), or the counts of the closing round
         if (cta == 0) {
-            if (tid == 0) {
-                S.rpos[0] = 0;
-                S.rcnt[0] = 0;
-                S.rsum[0] = 0;
-                S.rpos[R] = K.n_ent;
-                S.rcnt[R] = K.n_nz;
-                S.rsum[R] = total_q;
-            }
-        }
-        if (tlog) tlog[0] = now();
-        int trip = 0;
-        for (int r = 1 + gw; r < R; r += LF_CL * (LF_THREADS / 32), ++trip) {  // one warp per region boundary
-            long long pos, cn, sum;
-            warp_boundary_search(C, S.tab.rstart[r], pos, cn, sum, &hint[trip]);
-            if (lane_id() == 0) {
-                S0->rpos[r] = pos;
-                S0->rcnt[r] = cn;
-                S0->rsum[r] = sum;
-            }
-        }
-        cluster.sync();
-        if (tlog) tlog[1] = now();
-        long long zp[4];
-        fast_zone_step(S, S0, K, C, ks, gw, tlog ? zp : nullptr);
-        if (tlog && S.iter == 6)
-            for (int i = 0; i < 4; ++i) st->logZ[LL_LOG - 16 + i] = zp[i] - zp[0];
-        cluster.sync();
-        if (tlog) tlog[2] = now();
-    };
-
-    cluster.sync();  // every CTA's shared state is initialised before anybody writes into CTA 0's
-    int stopped = 0;
-    for (int it = 0; it < K.max_iter && !stopped; ++it) {
-        unsigned long long tl[5];
-        tl[4] = logger ? now() : 0ull;
-        e_step(logger ? tl : nullptr);
-        if (cta == 0) {
-            long long up[8];
-            const int it_now = S.iter;
-            fast_update_step(cluster, S, K, ks, pc, xseq, tol, logger ? up : nullptr);
-            if (logger && it_now == 6) {
-                up[7] = clock64();
-                for (int i = 0; i < 8; ++i) st->logZ[LL_LOG - 32 + i] = up[i] - up[0];
+            if (!hist_round) {
+                long long up[8];
+                const int it_now = S.iter;
+                fast_update_step(cluster, S, K, ks, pc, xseq, tol, lg ? up : nullptr);
+                if (lg && it_now == 6) {
+                    up[7] = clock64();
+                    for (int i = 0; i < 8; ++i) st->logZ[LL_LOG - 32 + i] = up[i] - up[0];
+                }
+            } else {
+                long long *Wd = S.u.up.Wd;
+                const RegionTableT<LF_KMAX> &T = S.tab;
+                const int m = T.m;
+                if (tid < k) st->hist[tid] = 0;
+                if (tid < m) {
+                    long long w = 0;
+                    for (int c2 = 0; c2 < n_cta; ++c2) w += (long long)cluster.map_shared_rank(&S, c2)->zW[tid];
+                    Wd[tid] = w;
+                }
+                __syncthreads();
+                for (int r = tid; r < R; r += NT) {
+                    if (T.rJ1[r] != T.rJ2[r]) continue;
+                    const long long c = S.rcnt[r + 1] - S.rcnt[r];
+                    if (c > 0) Wd[T.rJ1[r]] += c;  // (J, J) occurs in at most one region
+                }
+                __syncthreads();
+                if (tid == 0 && K.n0 > 0) Wd[zone_argmin(fsub(0.f, K.mean), T.dv, T.dcn, T.down, 0, m - 1)] += K.n0;
+                __syncthreads();
+                if (tid < m) st->hist[T.down[tid]] = Wd[tid];
             }
         }
         cluster.sync();
-        if (cta != 0) {  // pull the new centroids and the stop decision from CTA 0
-            if (tid < k) S.c[tid] = S0->c[tid];
-            if (tid == 0) S.done = S0->done;
+        if (hist_round) break;
+        const int stopped = S0->done;
+        if (lg && it < LL_LOG) {
+            st->logT[it][3] = (unsigned int)(tl[0] - tl[4]);  // table
+            st->logT[it][0] = (unsigned int)(tl[1] - tl[0]);  // search (+ barrier)
+            st->logT[it][1] = (unsigned int)(tl[2] - tl[1]);  // zone (+ barrier)
+            st->logT[it][2] = (unsigned int)(now() - tl[2]);  // update (+ barrier)
+        }
+        if (!stopped) {  // pull the new centroids from CTA 0
+            if (cta != 0 && tid < k) S.c[tid] = S0->c[tid];
             __syncthreads();
+            continue;
         }
-        stopped = S.done;
-        if (logger && it < LL_LOG) {
-            st->logT[it][3] = (unsigned int)(tl[0] - tl[4]);      // table
-            st->logT[it][0] = (unsigned int)(tl[1] - tl[0]);      // search (+ barrier)
-            st->logT[it][1] = (unsigned int)(tl[2] - tl[1]);      // zone (+ barrier)
-            st->logT[it][2] = (unsigned int)(now() - tl[2]);      // update (+ barrier, pull)
+        // ---- the loop has stopped: results out (CTA 0 holds them)
+        if (cta == 0) {
+            if (tid < k) {
+                st->c[tid] = S.c[tid];
+                st->c_emit[tid] = S.c_emit[tid];
+            }
+            if (tid == 0) {
+                st->iter = S.iter;
+                st->done = S.done;
+                st->strict = S.strict;
+                st->n_reloc = S.n_reloc;
+                st->n_iter = S.n_iter;
+                st->comm_error = S.comm_error;
+            }
         }
-    }
-    // results of the loop (CTA 0 holds them)
-    if (cta == 0) {
-        if (tid < k) {
-            st->c[tid] = S.c[tid];
-            st->c_emit[tid] = S.c_emit[tid];
-        }
-        if (tid == 0) {
-            st->iter = S.iter;
-            st->done = S.done;
-            st->strict = S.strict;
-            st->n_reloc = S.n_reloc;
-            st->n_iter = S.n_iter;
-            st->comm_error = S.comm_error;
-        }
-    }
-    if (want_hist && stopped) {
-        // code histogram of the final labelling: one more E-step against c_emit, counts only
-        cluster.sync();  // CTA 0 has written the results above before its S.c changes
+        if (!want_hist) break;
+        hist_round = true;  // code histogram of the final labelling: the E-step once more, against c_emit
         if (tid < k) S.c[tid] = S0->c_emit[tid];
         __syncthreads();
-        e_step(nullptr);
-        if (cta == 0) {
-            long long *Wd = S.u.up.Wd;
-            const RegionTableT<LF_KMAX> &T = S.tab;
-            const int m = T.m, R = T.R;
-            if (tid < k) st->hist[tid] = 0;
-            if (tid < m) {
-                long long w = 0;
-                for (int c2 = 0; c2 < LF_CL; ++c2) w += (long long)cluster.map_shared_rank(&S, c2)->zW[tid];
-                Wd[tid] = w;
-            }
-            __syncthreads();
-            for (int r = tid; r < R; r += LF_THREADS) {
-                if (T.rJ1[r] != T.rJ2[r]) continue;
-                const long long c = S.rcnt[r + 1] - S.rcnt[r];
-                if (c > 0) Wd[T.rJ1[r]] += c;  // (J, J) occurs in at most one region
-            }
-            __syncthreads();
-            if (tid == 0 && K.n0 > 0) Wd[zone_argmin(fsub(0.f, K.mean), T.dv, T.dcn, T.down, 0, m - 1)] += K.n0;
-            __syncthreads();
-            if (tid < m) st->hist[T.down[tid]] = Wd[tid];
-        }
     }
     if (pc.enabled && cta == 0 && tid == 0) *peer_counter(pc) = xseq;
     cluster.sync();  // no CTA exits while another may still access its shared memory
@@ -933,11 +964,53 @@ __global__ void __cluster_dims__(LF_CL, 1, 1) __launch_bounds__(LF_THREADS, 1)
 bool lloyd_fast_applicable(int k) { return k >= 1 && k <= LF_KMAX && !getenv("NNC_LLOYD_NO_CLUSTER"); }
 
 // Launches the cluster loop; `st` has its header, moments (s1 / s2 of the sorted survivors) and candidate buffer set.
+// Preferred shape: ONE cluster of 16 CTAs x 512 threads (a non-portable cluster size: every GPC of a B200 has >= 16 SMs;
+// 128 registers per thread), else 8 x 1024 (64 registers).  NNC_LLOYD_CLUSTER=8|16 forces one.
+template <int THREADS>
+static cudaError_t fast_launch_shape(nnc_ctx *ctx, int n_cta, bool probe_only, LloydDevice *st, const float *d_sorted, const float *samp,
+                                     const long long *ptile, const float *d_init, int want_hist, int want_log, const PeerComm &pc) {
+    func_dyn_smem(ctx, (const void *)ll_fast_kernel<THREADS>, sizeof(FastSmem));
+    if (n_cta > 8) {
+        cudaError_t e = cudaFuncSetAttribute(ll_fast_kernel<THREADS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_cta);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = sizeof(FastSmem);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = n_cta;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (probe_only) {
+        int n_clusters = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n_clusters, ll_fast_kernel<THREADS>, &cfg);
+        if (e != cudaSuccess) return e;
+        return n_clusters >= 1 ? cudaSuccess : cudaErrorInvalidClusterSize;
+    }
+    return cudaLaunchKernelEx(&cfg, ll_fast_kernel<THREADS>, st, d_sorted, samp, ptile, d_init, want_hist, want_log, pc);
+}
+
 void lloyd_fast_launch(nnc_ctx *ctx, LloydDevice *st, const float *d_sorted, const float *samp, const long long *ptile,
                        const float *d_init, int want_hist, const PeerComm &pc) {
-    func_dyn_smem(ctx, (const void *)ll_fast_kernel, sizeof(FastSmem));
-    const int want_log = getenv("NNC_LLOYD_LOG") ? 1 : 0;
-    NNC_LAUNCH(ctx, ll_fast_kernel, LF_CL, LF_THREADS, sizeof(FastSmem), st, d_sorted, samp, ptile, d_init, want_hist, want_log, pc);
+    const int want_log = getenv("NNC_LLOYD_LOG") ? atoi(getenv("NNC_LLOYD_LOG")) : 0;
+    if (ctx->fast_cluster == 0) {  // decide once per context (= per device)
+        int want = 16;
+        if (const char *e = getenv("NNC_LLOYD_CLUSTER")) want = atoi(e) == 8 ? 8 : 16;
+        ctx->fast_cluster = 8;
+        if (want == 16 && fast_launch_shape<512>(ctx, 16, true, st, d_sorted, samp, ptile, d_init, want_hist, want_log, pc) == cudaSuccess)
+            ctx->fast_cluster = 16;
+        cudaGetLastError();
+    }
+    cudaError_t e = ctx->fast_cluster == 16
+                        ? fast_launch_shape<512>(ctx, 16, false, st, d_sorted, samp, ptile, d_init, want_hist, want_log, pc)
+                        : fast_launch_shape<1024>(ctx, 8, false, st, d_sorted, samp, ptile, d_init, want_hist, want_log, pc);
+    ctx->launches++;
+    if (e != cudaSuccess) NNC_FAIL(NNC_ERR_CUDA, "ll_fast_kernel launch (cluster of %d): %s", ctx->fast_cluster, cudaGetErrorString(e));
 }
 
 }  // namespace nnc

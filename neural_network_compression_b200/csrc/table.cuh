@@ -244,7 +244,7 @@ static __device__ void build_region_table(const float *c, int k, float xabs_max,
     if (perm && tid < k) perm[tid] = (int)(S.keys[tid] & 0xffffffffu);
     }
     float M = xabs_max;
-    for (int i = 0; i < TB_THREADS / 32; ++i) M = fmaxf(M, S.warp_f[i]);
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) M = fmaxf(M, S.warp_f[i]);
     // ---- 2. distinct values
     uint32_t myord = 0, prevord = 0;
     int myid = 0;
