@@ -582,6 +582,277 @@ def run_e2e(args, torch, U, n_local, rank, world, dist, dev):
                    "float32 weights in; the compressed layer out (1-bit mask, packed 8-bit codes, codebook, histogram)"}
 
 
+# ---------------------------------------------------------------------------------------------------------
+# the other configs of BASELINE.json (--config c1 | c2 | c3 | c5); the default (c4) is run_b200 above
+# ---------------------------------------------------------------------------------------------------------
+def run_config(args):
+    """C1 LeNet300-100 prune + 2-bit density k-means; C2 LeNet5 prune + 4-bit linear; C3 4096 x 4096 prune + 5-bit forgy
+    (seeded); C5 trained-quantization gradient sum (2^28 gradients, 256 clusters, shards over the ranks).  Same JSON
+    contract as the default config.  Inputs smaller than the L2 are followed by an L2 flush between the timed steps."""
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import torch
+
+    from neural_network_compression_b200 import _native as N
+    from neural_network_compression_b200.common import utility as U
+    from tests import _data as D
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        if args.config != "c5":
+            raise SystemExit("--config %s is a single-GPU configuration" % args.config)
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+        U.init_distributed(device=local)
+    ctx = N.default_context(local)
+    K, W = args.steps, args.warmup
+    cfgname = args.config
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    metric, unit = METRIC, UNIT
+    cpu = None
+    if cfgname in ("c1", "c2"):
+        model = D.lenet300_tensors() if cfgname == "c1" else D.lenet5_tensors()
+        bits, mode = (2, "density") if cfgname == "c1" else (4, "linear")
+        host, qs = [], []
+        for name, w, b, (qw, qb) in model:
+            host += [w, b]
+            qs += [qw, qb]
+        units = sum(t.size for t in host)
+        master = [torch.from_numpy(t).to(dev) for t in host]
+        work = {}
+
+        def prepare():
+            work["t"] = [m.clone() for m in master]
+
+        def step():
+            return U.compress_tensors(work["t"], qs, True, bits, mode)
+
+        def e2e_step():
+            return U.compress_tensors([t.copy() for t in host], qs, True, bits, mode)
+
+        h2d = 4 * units
+        d2h = units * (1 + 4 + 4)  # mask, ris (float32), labels (int32): what the reference's helpers return
+        workload = ("%s: every kernel and bias pruned with the trainer's thresholds, then %d-bit %s-init k-means, all "
+                    "tensors in one batched call (utility.compress_tensors)" %
+                    ("LeNet300-100 (784-300-100-10), 6 tensors" if cfgname == "c1" else "LeNet5 conv+dense layers, 8 tensors", bits, mode))
+        sfrac = 0.35
+        step_bytes = 13.0 + 4.0 + 4.0 + 4.0 + 52.0 * sfrac  # prune + quantize with dense ris and labels out
+
+        def cpu():
+            from oracle import oracle as O
+            import warnings
+
+            from sklearn.cluster import KMeans
+            from threadpoolctl import threadpool_limits
+
+            threads = cpu_threads()
+            ts = [t.copy() for t in host]
+            with threadpool_limits(limits=threads), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                t0 = time.perf_counter()
+                for t, q in zip(ts, qs):
+                    thr = np.std(t) * q
+                    m = np.abs(t) < thr
+                    t[m] = 0
+                    if t.size < 2 ** bits + 1:
+                        continue
+                    if mode == "density":
+                        flat = t.flatten()
+                        nz = np.delete(flat, np.nonzero(flat == 0)[0], axis=0)  # trainer.py:55-59
+                        space = O.init_centroids(t, bits, "density", O.get_weight_distribution(nz))  # utility.py:334-392, 210-223 (C restatement)
+                    else:
+                        space = np.linspace(np.min(t), np.max(t), num=2 ** bits)
+                    km = KMeans(n_clusters=len(space), init=space.reshape(-1, 1), n_init=1, algorithm="lloyd").fit(t.reshape(-1, 1))
+                    _ = km.cluster_centers_[km.labels_].reshape(t.shape)
+                dt = time.perf_counter() - t0
+            return dt, units, threads, "the whole model, to convergence (NumPy prune + scikit-learn KMeans per tensor; CDF / density init through the C restatement)"
+    elif cfgname == "c3":
+        w3 = D.gaussian(4096 * 4096, seed=1234).reshape(4096, 4096)
+        units = w3.size
+        master = torch.from_numpy(w3).to(dev)
+        work = {}
+
+        def prepare():
+            work["t"] = master.clone()
+
+        def step():
+            np.random.seed(0)
+            return U.compress_weight(work["t"], 1.0, True, 5, "forgy")
+
+        def e2e_step():
+            np.random.seed(0)
+            return U.compress_weight(w3.copy(), 1.0, True, 5, "forgy")
+
+        h2d, d2h = 4 * units, units + units * 5 // 8
+        workload = "synthetic 4096x4096 fp32 dense layer N(0,0.02^2), std-threshold prune q=1 + 5-bit forgy (np.random.seed(0)) k-means, mask + packed 5-bit codes out"
+        step_bytes = 13.0 + 4.0 + 5 / 8.0 + 52.0 * 0.317
+
+        def cpu():
+            import warnings
+
+            from sklearn.cluster import KMeans
+            from threadpoolctl import threadpool_limits
+
+            threads = cpu_threads()
+            t = w3.copy()
+            with threadpool_limits(limits=threads), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                t0 = time.perf_counter()
+                thr = np.std(t) * 1.0
+                t[np.abs(t) < thr] = 0
+                np.random.seed(0)
+                space = np.random.choice(t.flatten(), size=2 ** 5)  # utility.py:224-226
+                km = KMeans(n_clusters=len(space), init=space.reshape(-1, 1), n_init=1, algorithm="lloyd", max_iter=args.cpu_max_iter).fit(t.reshape(-1, 1))
+                dt = time.perf_counter() - t0
+            return dt, units, threads, "the whole tensor, k-means capped at %d of its ~227 Lloyd iterations (%d run): %.1f s" % (args.cpu_max_iter, km.n_iter_, dt)
+    else:  # c5
+        n_total = 1 << 28
+        n_local = n_total // world
+        units = n_total
+        metric, unit = "gradient elements/sec per-cluster segmented sum (256 clusters)", "elements/s"
+        g = torch.empty(n_local, device=dev).normal_(0, 1e-3, generator=torch.Generator(device=dev).manual_seed(7 + rank))
+        gen = torch.Generator(device=dev).manual_seed(8 + rank)
+        codes = torch.randint(0, 256, (n_local,), device=dev, generator=gen, dtype=torch.int32)
+        if args.c5_codes == "skewed":  # the code histogram of a pruned layer: 68 % of the weights in one cluster
+            codes = torch.where(torch.rand(n_local, device=dev, generator=gen) < 0.683, torch.full_like(codes, 126), codes)
+        packed = codes.to(torch.uint8)
+        ref = torch.zeros(256, dtype=torch.float64, device=dev).index_add_(0, codes.long(), g.double())
+        if dist is not None:
+            dist.all_reduce(ref)
+        del codes
+        g_host, p_host = None, None
+
+        def prepare():
+            pass
+
+        def step():
+            return U.cluster_gradient_sum(g, packed, 256, 8)
+
+        def e2e_step():
+            return U.cluster_gradient_sum(g_host, p_host, 256, 8)
+
+        h2d, d2h = 5 * n_local, 8 * 256
+        workload = "trained-quantization step: 2^28 fp32 gradients, 8-bit codes (%s histogram), per-cluster segmented sum, 256 clusters, contiguous shards" % args.c5_codes
+        step_bytes = 5.0
+
+        def cpu():
+            ns = 1 << 25
+            gs = (np.random.RandomState(7).randn(ns) * 1e-3).astype(np.float32)
+            cs = np.random.RandomState(8).randint(0, 256, size=ns)
+            t0 = time.perf_counter()
+            np.bincount(cs, weights=gs, minlength=256)
+            dt = time.perf_counter() - t0
+            return dt, ns, 1, "np.bincount(codes, weights=grad, minlength=256) on a 2^25-element sample (single threaded NumPy)"
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    out = None
+    for i in range(W):
+        prepare()
+        if i == W - 1:
+            ctx.set_kernel_timing(True)
+        out = step()
+    torch.cuda.synchronize()
+    ktimes = {}
+    # worker threads have their own contexts in the batched mode: kernel times come from this thread's context only
+    ktimes = {name: ms / max(c, 1) * c for name, (c, ms) in ctx.last_kernel_times().items()}
+    ctx.set_kernel_timing(False)
+    launches0 = ctx.total_launches()
+    total_ms = 0.0
+    t_region0 = time.time()
+    for i in range(K):
+        prepare()
+        if cfgname != "c5":
+            flush_buf.fill_(i & 0xff)  # L2 flush: the inputs are smaller than the 126 MB L2
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(torch.cuda.current_stream())
+        out = step()
+        ev1.record(torch.cuda.current_stream())
+        barrier()
+        total_ms += ev0.elapsed_time(ev1)
+    t_region1 = time.time()
+    clk = clocks.stop(t_region0, t_region1) if rank == 0 else None
+    launches = ctx.total_launches() - launches0
+    if dist is not None:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = units * K / (total_ms * 1e-3)
+    # end to end: host arrays in, host results out
+    e2e = None
+    if not args.no_e2e:
+        if cfgname == "c5":
+            g_host, p_host = g.cpu().numpy(), packed.cpu().numpy()
+        e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(K, args.e2e_steps))
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": units * n_e2e / dt, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e, "api": "the same public call on host (NumPy) arrays"}
+    check = None
+    if cfgname == "c5":
+        got = out
+        check = float(np.abs(got - ref.cpu().numpy()).max() / np.abs(ref.cpu().numpy()).max())
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    dom = max(ktimes.items(), key=lambda kv: kv[1])[0] if ktimes else None
+    per_rank_units = units / world
+    achieved = step_bytes * per_rank_units / (total_ms / K * 1e-3) / 1e9
+    line = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "name": cfgname, "units_per_step": units,
+                   "l2": "inputs > L2, no flush" if cfgname == "c5" else "256 MB written between timed steps (L2 flush)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "whole step" if cfgname != "c5" else "segsum_warp_kernel (+ fold)",
+                     "algorithmic_bytes_per_unit": step_bytes, "dominant_kernel_by_time": dom,
+                     "note": "latency bound at this size: tens of microsecond-scale launches per tensor" if cfgname in ("c1", "c2") else None},
+        "gpu_launches": int(launches), "clocks": clk,
+        "kernel_ms_last_warmup_step": {k2: v for k2, v in sorted(ktimes.items(), key=lambda kv: -kv[1])[:12]},
+    }
+    if check is not None:
+        line["max_rel_err_vs_float64_index_add"] = check
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu and cpu is not None:
+        dt, n_cpu, threads, sample = cpu()
+        line["cpu_baseline"] = {"value": n_cpu / dt, "unit": unit, "cores": threads, "kind": "reference", "sample": sample}
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -594,11 +865,16 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--config", default="c4", choices=["c1", "c2", "c3", "c4", "c5"], help="BASELINE.json configs; c4 (1B-weight layer) is the metric's")
+    ap.add_argument("--c5-codes", default="uniform", choices=["uniform", "skewed"])
+    ap.add_argument("--cpu-max-iter", type=int, default=30, help="c3: Lloyd iterations the CPU baseline is capped at")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.config != "c4":
+        return run_config(args)
     return run_b200(args)
 
 

@@ -23,7 +23,7 @@ from .. import _native as N
 __all__ = [
     "prune_weigth", "apply_mask", "get_weight_distribution", "get_quantized_weight", "KMeansResult",
     "compress_weight", "init_distributed", "shard_range", "nonzero_weights", "weight_stats", "assign_codes", "dequantize", "cluster_gradient_sum", "index_bits",
-    "pack_mask_bits",
+    "pack_mask_bits", "compress_tensors",
 ]
 
 
@@ -490,6 +490,114 @@ def compress_weight(original_weigth, threshold=0.25, std_smooth=True, bits=4, mo
         mask = mask.view(torch.bool) if mask.dtype == torch.uint8 else mask
         return mask.reshape(buf.shape), res
     return mask.view(np.bool_).reshape(buf.shape), res
+
+
+# ---------------------------------------------------------------------------------------------------------
+# batched many-small-tensor mode
+# ---------------------------------------------------------------------------------------------------------
+_pool = None
+_pool_streams = {}
+
+
+def _worker_stream(device):
+    """One CUDA stream per (worker thread, device), created on first use."""
+    import threading
+
+    import torch
+
+    key = (threading.get_ident(), device)
+    s = _pool_streams.get(key)
+    if s is None:
+        s = _pool_streams[key] = torch.cuda.Stream(device=device)
+    return s
+
+
+def compress_tensors(tensors, thresholds=None, std_smooth=True, bits=4, mode="linear", with_cdf=True, workers=8):
+    """All tensors of a model in ONE call: what the reference's loops do tensor by tensor (prune every kernel / bias,
+    trainer.py:177-193; then quantize every array of every layer, trainer.py:50-70), with the tensors processed
+    CONCURRENTLY -- every tensor's kernels run on a stream of their own (own context, own workspace), driven by a small
+    pool of host threads, so that launch latencies and the few host round trips of the per-tensor pipeline overlap
+    instead of adding up.  A LeNet has 6-8 tensors of 10 .. 627 200 weights: the call costs about as much as its largest
+    tensor.  Results are bit-identical to the per-tensor calls (each tensor runs exactly the same kernels).
+
+    tensors: float32 ndarrays / torch tensors (device tensors are pruned and read in place, as by prune_weigth).
+    thresholds: one pruning quality parameter per tensor, or None to skip pruning (already pruned model).
+    Returns [(mask or None, ris, kmeans or None)] in input order; a tensor with fewer than 2**bits + 1 elements comes back
+    unquantised with kmeans None, like get_quantized_weight (utility.py:202-204).
+    """
+    global _pool
+    from concurrent.futures import ThreadPoolExecutor
+
+    tensors = list(tensors)
+    if thresholds is not None and len(thresholds) != len(tensors):
+        raise ValueError("one threshold per tensor")
+    if mode == "forgy":
+        # np.random.choice draws from the global legacy RNG in layer order (utility.py:224-226): draw here, in order
+        forgy_idx = [np.random.randint(0, int(np.prod(tuple(t.shape))), size=2 ** bits).astype(np.int64)
+                     if int(np.prod(tuple(t.shape))) >= (2 ** bits) + 1 else None for t in tensors]
+    else:
+        forgy_idx = [None] * len(tensors)
+    if _pool is None:
+        _pool = ThreadPoolExecutor(max_workers=max(1, int(workers)), thread_name_prefix="nnc-batch")
+    producer = {}
+    if any(N.is_torch(t) and t.is_cuda for t in tensors):
+        import torch
+
+        for t in tensors:
+            if N.is_torch(t) and t.is_cuda and t.device.index not in producer:
+                producer[t.device.index] = torch.cuda.current_stream(t.device)
+
+    def one(i):
+        t = tensors[i]
+        on_dev = N.is_torch(t) and t.is_cuda
+
+        def work():
+            mask = None
+            if thresholds is not None:
+                mask = prune_weigth(t, thresholds[i], std_smooth)
+            n_elem = int(np.prod(tuple(t.shape)))
+            if n_elem < (2 ** bits) + 1:
+                print("not enough bits:", n_elem, " vs ", 2 ** bits)
+                return mask, t, None
+            if mode == "forgy":
+                buf = _Buf(t, "layer_weight")
+                ctx = _ctx_for(buf)
+                space = np.empty(forgy_idx[i].size, dtype=np.float32)
+                N.check(N.lib().nnc_gather_f32(ctx.handle, buf.ptr, buf.n, N.ptr(forgy_idx[i]), forgy_idx[i].size, N.ptr(space)))
+                ris, res = _kmeans_device(buf, ctx, space)
+                return mask, ris.reshape(buf.shape), res
+            cdfs = None
+            if mode == "density" and with_cdf:
+                try:
+                    cdfs = get_weight_distribution(t, skip_zeros=True)
+                except ValueError:  # an all-zero tensor has no survivors: the reference fails there as well
+                    raise
+            ris, res = get_quantized_weight(t, bits, mode, cdfs)
+            return mask, ris, res
+
+        if on_dev:
+            import torch
+
+            s = _worker_stream(t.device.index)
+            s.wait_stream(producer[t.device.index])
+            with torch.cuda.stream(s):
+                out = work()
+            return out, s
+        return work(), None
+
+    futures = [_pool.submit(one, i) for i in range(len(tensors))]
+    results = []
+    for f in futures:
+        out, s = f.result()
+        if s is not None:
+            prod = producer[s.device.index]
+            prod.wait_stream(s)
+            mask, ris, res = out
+            for x in (mask, ris, getattr(res, "labels_", None), getattr(res, "packed_codes", None)):
+                if N.is_torch(x) and x.is_cuda:
+                    x.record_stream(prod)  # allocated on the worker's stream, used on the caller's from here on
+        results.append(out)
+    return results
 
 
 def assign_codes(weights, kmeans: KMeansResult, want_labels=True, want_packed=True):

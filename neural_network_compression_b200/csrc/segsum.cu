@@ -203,6 +203,176 @@ __global__ void __launch_bounds__(SG_THREADS) segsum_kernel(const float *__restr
     if (lane_id() == 0 && bad) atomicAdd(bad_codes, bad);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// k <= 1024: one warp = one independent accumulator, no block barrier anywhere in the loop.
+//   * a warp takes tiles of 512 consecutive elements (16 per lane: four 128-bit gradient loads + their codes in flight);
+//   * fixed point WITHOUT float64: q = rint(g * 2^(43 - E)) is a power-of-two scaling, exact in float32, then one
+//     F2I.S64; 2^E bounds every |g| the warp has seen so far (running exponent: when a tile exceeds it the warp's bins are
+//     flushed and E grows -- a handful of times per launch);
+//   * the warp's private bins are exact 64-bit accumulators made of two NATIVE 32-bit shared-memory atomics: the low
+//     word wraps, its carry (old + x < old, from the returned value) rides on the add to the high word;
+//   * the most frequent code of the warp's first tile (the cluster of the pruned zeros holds 2/3 of a pruned layer) is
+//     summed in a register instead of serialising 20 lanes on one address;
+//   * flushes add bins * 2^(E - 43) in float64 into the WARP's own row of `partial` (one writer per row: a fixed order),
+//     and a second kernel folds the rows in row order: deterministic for a given (n, grid).
+// Exactness: elements below 2^-20 of the running bound lose bits below 2^(E - 44); everything else is summed exactly.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SW_QBITS = 43;
+constexpr int SW_TILE = 512;           // elements per warp tile
+constexpr int SW_FLUSH_TILES = 1024;   // bins are flushed at least this often: |high word| < 2^11 * 2^19 + carries < 2^31
+
+__global__ void __launch_bounds__(SG_THREADS) segsum_warp_kernel(const float *__restrict__ grad, const void *__restrict__ codes,
+                                                                 int64_t n, int bits, int k, int vec_ok, double *partial,
+                                                                 unsigned long long *bad_codes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = lane_id(), wid = warp_id();
+    uint32_t *my_lo = reinterpret_cast<uint32_t *>(smem_raw) + (size_t)wid * 2 * k;
+    int32_t *my_hi = reinterpret_cast<int32_t *>(my_lo + k);
+    for (int i = lane; i < 2 * k; i += 32) my_lo[i] = 0;
+    const int64_t gwarp = (int64_t)blockIdx.x * SG_WARPS + wid, n_warps = (int64_t)gridDim.x * SG_WARPS;
+    double *my_row = partial + (size_t)gwarp * k;
+    for (int i = lane; i < k; i += 32) my_row[i] = 0.0;
+    __syncwarp();
+    const int64_t n_tiles = (n + SW_TILE - 1) / SW_TILE;
+    int E = -200;          // 2^E bounds every |g| accumulated in the bins (none yet)
+    float scale_f = 0.f;   // 2^(SW_QBITS - E)
+    int hot = -2;          // code summed in a register (chosen at the warp's first tile)
+    long long hot_acc = 0;
+    int pending_tiles = 0;
+    unsigned long long bad = 0;
+    auto flush = [&]() {  // bins (and the hot register) -> this warp's float64 row; exact integers leave, doubles arrive
+        if (pending_tiles == 0) return;
+        __syncwarp();
+        const double inv = ldexp(1.0, E - SW_QBITS);
+        for (int i = lane; i < k; i += 32) {
+            const long long b = ((long long)my_hi[i] << 32) + (long long)my_lo[i];
+            if (b) {
+                my_row[i] = __dadd_rn(my_row[i], __dmul_rn((double)b, inv));
+                my_lo[i] = 0;
+                my_hi[i] = 0;
+            }
+        }
+        const long long h = warp_sum_ll(hot_acc);
+        if (lane == 0 && h) my_row[hot] = __dadd_rn(my_row[hot], __dmul_rn((double)h, inv));
+        hot_acc = 0;
+        pending_tiles = 0;
+        __syncwarp();
+    };
+    for (int64_t t = gwarp; t < n_tiles; t += n_warps) {
+        const int64_t base = t * SW_TILE;
+        float g[16];
+        int c[16];
+        if (vec_ok && base + SW_TILE <= n) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const int64_t e = base + (v * 32 + lane) * 4;
+                const float4 x = ld_stream_f4(grad + e);
+                g[4 * v] = x.x, g[4 * v + 1] = x.y, g[4 * v + 2] = x.z, g[4 * v + 3] = x.w;
+                int cc[4];
+                load_codes4(codes, bits, e >> 2, n, cc);
+                c[4 * v] = cc[0], c[4 * v + 1] = cc[1], c[4 * v + 2] = cc[2], c[4 * v + 3] = cc[3];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int64_t e = base + (j >> 2) * 128 + lane * 4 + (j & 3);
+                const bool in = e < n;
+                g[j] = in ? grad[e] : 0.f;
+                c[j] = in ? load_code1(codes, bits, e, n) : -1;
+            }
+        }
+        float mx = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (c[j] >= k) {
+                bad++;
+                c[j] = -1;
+            }
+            if (c[j] >= 0) mx = fmaxf(mx, fabsf(g[j]));
+        }
+        mx = warp_max_f(mx);
+        if (!(mx < INFINITY)) {  // a NaN / infinity: reported like an invalid code, never accumulated
+            bad += 1;
+            continue;
+        }
+        if (hot == -2) {  // first tile of this warp: the code most lanes see in their first element
+            const unsigned same = __match_any_sync(0xffffffffu, c[0]);
+            int votes = c[0] >= 0 ? __popc(same) : 0;
+            int best = votes, who = lane;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int ob = __shfl_xor_sync(0xffffffffu, best, o), ow = __shfl_xor_sync(0xffffffffu, who, o);
+                if (ob > best || (ob == best && ow < who)) {
+                    best = ob;
+                    who = ow;
+                }
+            }
+            hot = __shfl_sync(0xffffffffu, c[0], who);
+            if (best == 0) hot = -1;
+        }
+        if (mx > 0.f) {
+            int te = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 126;  // |g| < 2^te (denormals: -126)
+            if (te < -126) te = -126;
+            if (te > E) {  // the bound grows: what is in the bins was scaled with the old one
+                flush();
+                E = te + 1;
+                scale_f = __int_as_float((SW_QBITS - E + 127) << 23);  // SW_QBITS - E in [-85, 169]: clamp below
+                if (SW_QBITS - E > 127) scale_f = 0.f;
+            }
+        }
+        if (scale_f != 0.f) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int code = c[j];
+                if (code < 0) continue;
+                const long long q = __float2ll_rn(__fmul_rn(g[j], scale_f));
+                if (code == hot) {
+                    hot_acc += q;
+                } else {
+                    const uint32_t lo = (uint32_t)q;
+                    const uint32_t old = atomicAdd(&my_lo[code], lo);
+                    atomicAdd(&my_hi[code], (int32_t)(q >> 32) + (int32_t)(old + lo < old));
+                }
+            }
+        } else {  // bound below 2^-84: the float64 scaling (tiny gradients only)
+            const double sc = ldexp(1.0, SW_QBITS - E);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int code = c[j];
+                if (code < 0) continue;
+                const long long q = __double2ll_rn(__dmul_rn((double)g[j], sc));
+                if (code == hot) {
+                    hot_acc += q;
+                } else {
+                    const uint32_t lo = (uint32_t)q;
+                    const uint32_t old = atomicAdd(&my_lo[code], lo);
+                    atomicAdd(&my_hi[code], (int32_t)(q >> 32) + (int32_t)(old + lo < old));
+                }
+            }
+        }
+        if (++pending_tiles >= SW_FLUSH_TILES) flush();
+    }
+    flush();
+    bad = warp_sum_ull(bad);
+    if (lane == 0 && bad) atomicAdd(bad_codes, bad);
+}
+
+// rows of `partial` folded in row order: thread t of the bin's CTA adds rows t, t + 128, ... and the 128 partial sums are
+// combined by a fixed tree -- the same additions in the same order on every run
+__global__ void __launch_bounds__(128) segsum_fold_kernel(const double *__restrict__ partial, int64_t rows, int k, double *out) {
+    __shared__ double s[128];
+    const int j = blockIdx.x;
+    double acc = 0.0;
+    for (int64_t r = threadIdx.x; r < rows; r += 128) acc = __dadd_rn(acc, partial[(size_t)r * k + j]);
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s[threadIdx.x] = __dadd_rn(s[threadIdx.x], s[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[j] = s[0];
+}
+
 __global__ void segsum_final_kernel(const double *partial, int nblocks, int k, double *out) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= k) return;
@@ -217,21 +387,29 @@ void grad_segsum_device(nnc_ctx *ctx, const float *d_grad, const void *d_codes, 
     if (bits < 0 || bits > 16) NNC_FAIL(NNC_ERR_BAD_ARG, "segsum: bits = %d outside [0, 16]", bits);
     const bool priv = k <= 1024;
     if (!priv && 16 * (size_t)k > 200 * 1024) NNC_FAIL(NNC_ERR_UNSUPPORTED, "segsum: k = %d does not fit shared memory", k);
-    const int64_t n_tiles = (n + SG_TILE - 1) / SG_TILE;
-    const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 4, n_tiles);
-    double *partial = arena_alloc_t<double>(ctx, (size_t)grid * k);
     double *d_out = arena_alloc_t<double>(ctx, k);
     unsigned long long *bad = arena_alloc_t<unsigned long long>(ctx, 1);
     NNC_CUDA(cudaMemsetAsync(bad, 0, sizeof(unsigned long long), ctx->stream));
-    const size_t smem = priv ? (8 + 8 * (size_t)SG_WARPS) * k : 16 * (size_t)k;
-    func_dyn_smem(ctx, priv ? (const void *)segsum_kernel<true> : (const void *)segsum_kernel<false>, smem);
-    const int vec_ok = ((reinterpret_cast<uintptr_t>(d_grad) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_codes) & 15u) == 0) &&
-                       (bits == 0 || bits == 4 || bits == 8 || bits == 16 || bits == 2 || bits == 1 || true);
-    if (priv)
-        NNC_LAUNCH(ctx, segsum_kernel<true>, grid, SG_THREADS, smem, d_grad, d_codes, n, bits, k, vec_ok, partial, bad);
-    else
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(d_grad) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_codes) & 15u) == 0);
+    if (priv) {  // one independent accumulator per warp (segsum_warp_kernel)
+        const int64_t n_wtiles = (n + SW_TILE - 1) / SW_TILE;
+        const size_t smem = (size_t)SG_WARPS * 2 * k * sizeof(uint32_t);
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * per_sm, (n_wtiles + SG_WARPS - 1) / SG_WARPS));
+        const int64_t rows = (int64_t)grid * SG_WARPS;
+        double *partial = arena_alloc_t<double>(ctx, (size_t)rows * k);
+        func_dyn_smem(ctx, (const void *)segsum_warp_kernel, smem);
+        NNC_LAUNCH(ctx, segsum_warp_kernel, grid, SG_THREADS, smem, d_grad, d_codes, n, bits, k, vec_ok, partial, bad);
+        NNC_LAUNCH(ctx, segsum_fold_kernel, k, 128, 0, partial, rows, k, d_out);
+    } else {
+        const int64_t n_tiles = (n + SG_TILE - 1) / SG_TILE;
+        const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 4, n_tiles);
+        double *partial = arena_alloc_t<double>(ctx, (size_t)grid * k);
+        const size_t smem = 16 * (size_t)k;
+        func_dyn_smem(ctx, (const void *)segsum_kernel<false>, smem);
         NNC_LAUNCH(ctx, segsum_kernel<false>, grid, SG_THREADS, smem, d_grad, d_codes, n, bits, k, vec_ok, partial, bad);
-    NNC_LAUNCH(ctx, segsum_final_kernel, (k + 127) / 128, 128, 0, partial, grid, k, d_out);
+        NNC_LAUNCH(ctx, segsum_final_kernel, (k + 127) / 128, 128, 0, partial, grid, k, d_out);
+    }
     unsigned long long h_bad = 0;
     if (ctx->world > 1) {
         // every rank's k partial sums travel as bit patterns in its own slot (the other slots are zero, so the integer

@@ -373,6 +373,51 @@ def test_kmeans_cluster_loop_equals_cooperative_loop(U, monkeypatch, bits, mode)
         assert km0.n_relocations > 0
 
 
+@pytest.mark.parametrize("on_device", [False, True])
+def test_compress_tensors_batched_equals_per_tensor(U, on_device):
+    """all tensors of a model in one call (concurrent streams) == the per-tensor calls, bit for bit,
+    and == the oracle: LeNet300-100 with 2-bit density (config 1) and LeNet5 with 4-bit linear (config 2)."""
+    import torch
+
+    for tensors, bits, mode in ((D.lenet300_tensors(), 2, "density"), (D.lenet5_tensors(), 4, "linear"), (D.lenet5_tensors(), 3, "forgy")):
+        flat, qs = [], []
+        for name, w, b, (qw, qb) in tensors:
+            flat += [w, b]
+            qs += [qw, qb]
+        # reference flow per tensor through the single-tensor helpers
+        np.random.seed(11)
+        single = []
+        forgy_idx = [np.random.randint(0, t.size, size=2 ** bits) if t.size >= 2 ** bits + 1 else None for t in flat] if mode == "forgy" else None
+        for i, (t, q) in enumerate(zip(flat, qs)):
+            t = t.copy()
+            m = U.prune_weigth(t, q, True)
+            cdfs = U.get_weight_distribution(t, skip_zeros=True) if mode == "density" else None
+            if mode == "forgy":
+                if forgy_idx[i] is None:
+                    single.append((m, t, None))
+                    continue
+                space = t.ravel()[forgy_idx[i]]
+                det = O.kmeans1d(t, space, mode=O.MODE_DET)
+                single.append((m, det.cluster_centers_[det.labels_].reshape(t.shape), det))
+                continue
+            ris, km = U.get_quantized_weight(t, bits, mode, cdfs)
+            single.append((m, ris, km))
+        np.random.seed(11)
+        batch_in = [torch.from_numpy(t.copy()).cuda() if on_device else t.copy() for t in flat]
+        out = U.compress_tensors(batch_in, qs, True, bits, mode)
+        assert len(out) == len(flat)
+        for (m1, r1, k1), (m0, r0, k0), t_in in zip(out, single, batch_in):
+            to_np = (lambda x: x.cpu().numpy()) if on_device else (lambda x: x)
+            assert np.array_equal(to_np(m1), m0)
+            if k0 is None:
+                assert k1 is None
+                continue
+            assert to_np(r1).tobytes() == np.ascontiguousarray(r0).tobytes()
+            assert k1.cluster_centers_.tobytes() == k0.cluster_centers_.tobytes()
+            assert k1.n_iter_ == k0.n_iter_
+            assert np.array_equal(to_np(k1.labels_), k0.labels_)
+
+
 def test_kmeans_errors(U):
     w = D.gaussian(1000, seed=2)
     with pytest.raises(Exception, match="error mode not found"):
