@@ -171,6 +171,8 @@ class Context:
         self.device = int(device)
         self._comm_cb = None
         self.peer_exchange = False  # True once the in-kernel peer-memory exchange is connected
+        self.rank, self.world = 0, 1  # multi-GPU: set by init_nccl / set_comm
+        self.dist_group = None        # the torch.distributed group the ranks were taken from (utility.init_distributed)
 
     @property
     def handle(self):
@@ -237,6 +239,7 @@ class Context:
         """The library's own NCCL communicator (all-reduces enqueued natively on the context's stream)."""
         assert len(unique_id) == 128
         check(lib().nnc_ctx_init_nccl(self._h, unique_id, int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
 
     def peer_mailbox_create(self, world: int) -> bytes:
         buf = C.create_string_buffer(64)
@@ -266,6 +269,7 @@ class Context:
         else:
             self._comm_cb = C.cast(None, ALLREDUCE_FN)
         check(lib().nnc_ctx_set_comm(self._h, rank, world, self._comm_cb, None))
+        self.rank, self.world = int(rank), int(world)
 
 
 _tls = threading.local()

@@ -23,7 +23,7 @@ from .. import _native as N
 __all__ = [
     "prune_weigth", "apply_mask", "get_weight_distribution", "get_quantized_weight", "KMeansResult",
     "compress_weight", "init_distributed", "shard_range", "nonzero_weights", "weight_stats", "assign_codes", "dequantize", "cluster_gradient_sum", "index_bits",
-    "pack_mask_bits", "compress_tensors",
+    "pack_mask_bits", "compress_tensors", "sharded_weight_distribution", "sharded_forgy_init",
 ]
 
 
@@ -93,6 +93,7 @@ def init_distributed(group=None, device=None, peer_exchange=True):
 
     ctx = N.default_context(device)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ctx.dist_group = group
     if world == 1:
         return ctx
     # preferred: the library's own NCCL communicator, bootstrapped through the existing process group
@@ -242,6 +243,66 @@ def nonzero_weights(params):
     return out[: cnt.value]
 
 
+# ---- the same on a tensor sharded over the ranks (min / max all-reduce, 31-bin int64 all-reduce) ----------
+def sharded_weight_distribution(local_minmax, local_hist, allreduce):
+    """get_weight_distribution of a tensor whose slices live on several ranks; every rank gets the same result, equal to
+    the single-rank one.  The exchange logic is separated from the device calls so that it runs under any backend:
+        local_minmax() -> (min, max, count) of this rank's selected elements (count 0: no element)
+        local_hist(edges float32[32]) -> int64[31] counts of this rank's elements in the half-open bins
+        allreduce(np.ndarray, op) -> np.ndarray, op in "min" / "max" / "sum", elementwise over the ranks.
+    Restates utility.py:359-390 on the global counts (NumPy / SciPy do the 31-value CDF and its interpolation exactly
+    as in the reference)."""
+    from scipy.interpolate import interp1d
+
+    mn, mx, cnt = local_minmax()
+    big = np.float32(np.inf)
+    lo = allreduce(np.array([mn if cnt else big], dtype=np.float32), "min")[0]
+    hi = allreduce(np.array([mx if cnt else -big], dtype=np.float32), "max")[0]
+    total = int(allreduce(np.array([cnt], dtype=np.int64), "sum")[0])
+    if total == 0:
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")
+    steps = np.linspace(np.float32(lo), np.float32(hi), num=32)  # utility.py:365 (float32 under NumPy 2)
+    counts = allreduce(np.asarray(local_hist(steps), dtype=np.int64), "sum")
+    with np.errstate(invalid="ignore", divide="ignore"):
+        p = counts / counts.sum()          # :375
+        cdf = np.cumsum(p)                 # :377-385, a running float64 sum
+        cdf = cdf / cdf[-1]
+    x = steps[:-1]
+    xnew = np.linspace(x[0], x[30], num=300)  # :387
+    return xnew, interp1d(x, cdf)(xnew)       # :388-390
+
+
+def _torch_allreduce(ctx, device):
+    """allreduce(np array, op) over the ranks of the context's process group (NCCL needs device tensors)."""
+    import torch
+    import torch.distributed as dist
+
+    ops = {"min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX, "sum": dist.ReduceOp.SUM}
+    on_gpu = dist.get_backend(ctx.dist_group) == "nccl"
+
+    def allreduce(a, op):
+        t = torch.from_numpy(np.ascontiguousarray(a).copy())
+        if on_gpu:
+            t = t.cuda(device if device is not None else ctx.device)
+        dist.all_reduce(t, op=ops[op], group=ctx.dist_group)
+        return t.cpu().numpy()
+
+    return allreduce
+
+
+def sharded_forgy_init(idx_global, begin, end, local_gather, allreduce):
+    """np.random.choice(flat, size=k) on a sharded tensor (utility.py:224-226): every rank draws the same GLOBAL indices
+    from the global legacy RNG, the owner of an index supplies the value, the bit patterns are summed over the ranks
+    (one non-zero contribution each)."""
+    idx_global = np.asarray(idx_global, dtype=np.int64)
+    mine = (idx_global >= begin) & (idx_global < end)
+    bits = np.zeros(idx_global.size, dtype=np.int64)
+    if mine.any():
+        vals = np.asarray(local_gather(idx_global[mine] - begin), dtype=np.float32)
+        bits[mine] = vals.view(np.uint32).astype(np.int64)
+    return allreduce(bits, "sum").astype(np.uint32).view(np.float32)
+
+
 def get_weight_distribution(weight_matrix, skip_zeros: bool = False):
     """Restates utility.py:334-392: 31 half-open bins over linspace(min, max, 32), normalised cumulative sum,
     linear interpolation onto 300 points.  Returns (xnew float32[300], cdf float64[300]).
@@ -253,6 +314,19 @@ def get_weight_distribution(weight_matrix, skip_zeros: bool = False):
     if buf.n == 0:
         raise ValueError("zero-size array to reduction operation minimum which has no identity")
     ctx = _ctx_for(buf)
+    if ctx.world > 1:  # this rank's slice of a sharded tensor: global min / max and global 31-bin counts
+        def local_minmax():
+            mn, mx, cnt = C.c_float(), C.c_float(), C.c_int64()
+            N.check(N.lib().nnc_minmax_f32(ctx.handle, buf.ptr, buf.n, int(bool(skip_zeros)), C.byref(mn), C.byref(mx), C.byref(cnt)))
+            return np.float32(mn.value), np.float32(mx.value), cnt.value
+
+        def local_hist(edges):
+            edges = np.ascontiguousarray(edges, dtype=np.float32)
+            counts = np.empty(edges.size - 1, dtype=np.int64)
+            N.check(N.lib().nnc_hist_edges_f32(ctx.handle, buf.ptr, buf.n, N.ptr(edges), edges.size, int(bool(skip_zeros)), N.ptr(counts)))
+            return counts
+
+        return sharded_weight_distribution(local_minmax, local_hist, _torch_allreduce(ctx, buf.device))
     xnew = np.empty(300, dtype=np.float32)
     cdf = np.empty(300, dtype=np.float64)
     try:
@@ -363,10 +437,7 @@ def get_quantized_weight(layer_weight, bits=4, mode="linear", cdfs=None):
     elif mode == "forgy":
         buf = _Buf(layer_weight, "layer_weight")
         ctx = _ctx_for(buf)
-        # np.random.choice(flat, size=k) draws randint(0, n, k) from the global legacy RNG and indexes with it
-        idx = np.random.randint(0, buf.n, size=2 ** bits).astype(np.int64)
-        space = np.empty(idx.size, dtype=np.float32)
-        N.check(N.lib().nnc_gather_f32(ctx.handle, buf.ptr, buf.n, N.ptr(idx), idx.size, N.ptr(space)))
+        space = _forgy_space(buf, ctx, bits)
     elif mode == "kmeans++":
         # Outside the hot path: the reference's unseeded sklearn default.  The
         # seeding runs on the host through scikit-learn; the Lloyd iterations run on the device like every
@@ -392,6 +463,25 @@ def get_quantized_weight(layer_weight, bits=4, mode="linear", cdfs=None):
     return ris.reshape(buf.shape), res
 
 
+def _forgy_space(buf: _Buf, ctx: N.Context, bits: int):
+    """np.random.choice(flat, size=2**bits) (utility.py:224-226): draws randint(0, n, k) from the global legacy RNG and
+    indexes with it; on a sharded tensor n is the GLOBAL element count and the owners supply the values."""
+    def gather(idx):
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        out = np.empty(idx.size, dtype=np.float32)
+        N.check(N.lib().nnc_gather_f32(ctx.handle, buf.ptr, buf.n, N.ptr(idx), idx.size, N.ptr(out)))
+        return out
+
+    if ctx.world <= 1:
+        return gather(np.random.randint(0, buf.n, size=2 ** bits))
+    allreduce = _torch_allreduce(ctx, buf.device)
+    n_global = int(allreduce(np.array([buf.n], dtype=np.int64), "sum")[0])
+    begin, end = N.shard_range(n_global, ctx.rank, ctx.world)
+    if end - begin != buf.n:
+        raise ValueError("rank %d holds %d elements, shard_range assigns [%d, %d)" % (ctx.rank, buf.n, begin, end))
+    return sharded_forgy_init(np.random.randint(0, n_global, size=2 ** bits), begin, end, gather, allreduce)
+
+
 def _init_space(buf: _Buf, ctx: N.Context, bits: int, mode: str, cdfs):
     """Initial centroids for the deterministic / seeded modes (utility.py:206-226)."""
     if mode == "linear":
@@ -399,14 +489,15 @@ def _init_space(buf: _Buf, ctx: N.Context, bits: int, mode: str, cdfs):
         N.check(N.lib().nnc_minmax_f32(ctx.handle, buf.ptr, buf.n, 0, C.byref(mn), C.byref(mx), C.byref(cnt)))
         if cnt.value != buf.n:
             raise ValueError("Input X contains NaN.")
-        return np.linspace(np.float32(mn.value), np.float32(mx.value), num=2 ** bits)
+        lo, hi = np.float32(mn.value), np.float32(mx.value)
+        if ctx.world > 1:
+            allreduce = _torch_allreduce(ctx, buf.device)
+            lo, hi = allreduce(np.array([lo], np.float32), "min")[0], allreduce(np.array([hi], np.float32), "max")[0]
+        return np.linspace(lo, hi, num=2 ** bits)
     if mode == "density" and cdfs is not None:
         return _init_density(bits, cdfs)
     if mode == "forgy":
-        idx = np.random.randint(0, buf.n, size=2 ** bits).astype(np.int64)
-        space = np.empty(idx.size, dtype=np.float32)
-        N.check(N.lib().nnc_gather_f32(ctx.handle, buf.ptr, buf.n, N.ptr(idx), idx.size, N.ptr(space)))
-        return space
+        return _forgy_space(buf, ctx, bits)
     raise Exception(" error mode not found")
 
 
@@ -537,8 +628,14 @@ def compress_tensors(tensors, thresholds=None, std_smooth=True, bits=4, mode="li
                      if int(np.prod(tuple(t.shape))) >= (2 ** bits) + 1 else None for t in tensors]
     else:
         forgy_idx = [None] * len(tensors)
-    if _pool is None:
-        _pool = ThreadPoolExecutor(max_workers=max(1, int(workers)), thread_name_prefix="nnc-batch")
+    # one single-thread executor per worker slot; tensor i always goes to the same slot (largest tensors first, round
+    # robin), so that every slot's context keeps seeing the same sizes: its workspace arena reaches its high-water mark
+    # in the first call and is never regrown afterwards (a regrow is a cudaFree + cudaMalloc: a device-wide stall)
+    n_slots = max(1, min(int(workers), len(tensors)))
+    if _pool is None or len(_pool) < n_slots:
+        _pool = (_pool or []) + [ThreadPoolExecutor(max_workers=1, thread_name_prefix="nnc-batch") for _ in range(n_slots - len(_pool or []))]
+    order = sorted(range(len(tensors)), key=lambda i: -int(np.prod(tuple(tensors[i].shape))))
+    slot_of = {i: pos % n_slots for pos, i in enumerate(order)}
     producer = {}
     if any(N.is_torch(t) and t.is_cuda for t in tensors):
         import torch
@@ -585,9 +682,9 @@ def compress_tensors(tensors, thresholds=None, std_smooth=True, bits=4, mode="li
             return out, s
         return work(), None
 
-    futures = [_pool.submit(one, i) for i in range(len(tensors))]
+    futures = {i: _pool[slot_of[i]].submit(one, i) for i in order}
     results = []
-    for f in futures:
+    for f in (futures[i] for i in range(len(tensors))):
         out, s = f.result()
         if s is not None:
             prod = producer[s.device.index]

@@ -1085,9 +1085,17 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         unsigned int tb[2];
         NNC_CUDA(cudaMemcpy(tb, st->logT[LL_LOG - 1], sizeof(tb), cudaMemcpyDeviceToHost));
         fprintf(stderr, "[nnc lloyd] four bare grid barriers: %.2f us\n", (tb[1] - tb[0]) * 1e-3);
-        long long zp[4], up[8], tb2 = 0;
-        NNC_CUDA(cudaMemcpy(&tb2, st->logZ + LL_LOG - 40, sizeof(tb2), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[nnc lloyd] second (warm) table build in the same iteration: %.2f us\n", tb2 * 1e-3);
+        long long zp[4], up[8];
+        if (atoi(getenv("NNC_LLOYD_LOG")) > 1) {  // per-CTA time stamps of iteration 6 (cluster kernel)
+            unsigned long long sl[16 * 8];
+            NNC_CUDA(cudaMemcpy(sl, st->logZ, sizeof(sl), cudaMemcpyDeviceToHost));
+            for (int c = 0; c < 16; ++c)
+                if (sl[8 * c])
+                    fprintf(stderr, "[nnc lloyd] cta %2d ns: search %5lld | syncA %5lld | zone %5lld | syncB %5lld | update %5lld | syncC %5lld\n", c,
+                            (long long)(sl[8 * c + 1] - sl[8 * c]), (long long)(sl[8 * c + 2] - sl[8 * c + 1]),
+                            (long long)(sl[8 * c + 3] - sl[8 * c + 2]), (long long)(sl[8 * c + 4] - sl[8 * c + 3]),
+                            (long long)(sl[8 * c + 5] - sl[8 * c + 4]), (long long)(sl[8 * c + 6] - sl[8 * c + 5]));
+        }
         NNC_CUDA(cudaMemcpy(zp, st->logZ + LL_LOG - 16, sizeof(zp), cudaMemcpyDeviceToHost));
         NNC_CUDA(cudaMemcpy(up, st->logZ + LL_LOG - 32, sizeof(up), cudaMemcpyDeviceToHost));
         fprintf(stderr, "[nnc lloyd] zone profile (cycles): prefix %lld elements %lld flush %lld\n", zp[1], zp[2], zp[3]);

@@ -43,6 +43,10 @@ struct FastUpdate {  // scratch of the update step (CTA 0)
     long long Wd[LF_KMAX], Sd[LF_KMAX];       // per distinct index
     long long W[LF_KMAX], S[LF_KMAX];         // per cluster id
     long long first[LF_KMAX], last[LF_KMAX];  // member cursors per distinct index
+    // two-candidate zones gathered from the chunk slots: what a distinct index gets as the LEFT candidate (a) of the zone to
+    // its right and as the RIGHT candidate (b) of the zone to its left (a pair of candidates occurs in one region only)
+    long long aW[LF_KMAX], aS[LF_KMAX], af[LF_KMAX], al[LF_KMAX];
+    long long bW[LF_KMAX], bS[LF_KMAX], bf[LF_KMAX], bl[LF_KMAX];
     float raw[LF_KMAX], cnew[LF_KMAX], sq[LF_KMAX];
     int empt[LF_KMAX];
     float far_x[LF_KMAX];
@@ -52,12 +56,19 @@ struct FastUpdate {  // scratch of the update step (CTA 0)
     uint32_t rk_d2[32], rk_gap[32], rk_ord[32];
     int rk_who[32];
     unsigned long long red_w[32];
-    NpWarpScratch np;
     int n_empty, zdi, same, winner, stop, strict;
     long long zero_left;
 };
+constexpr int LF_CH = 128;      // entries per zone chunk (one warp: four rounds of 32 with all loads in flight)
+constexpr int LF_MAXCH = 1024;  // chunk slots in CTA 0 (two-candidate zones; more chunks take the generic path)
+struct ZoneSlot {               // result of one two-candidate chunk, written by exactly one warp of the cluster
+    long long Wb, Sb, Wt, St;   // (count, fixed-point sum) of candidate b and of both candidates
+    unsigned int ends;          // first / last member of a and of b as chunk offsets + 1 (0: none), one byte each
+    unsigned int pad;
+};
 struct FastZone {
     long long rp[LF_R];  // copy of CTA 0's region positions
+    int s_warp[32];
 };
 struct FastSmem {
     RegionTableT<LF_KMAX> tab;  // built redundantly by every CTA
@@ -75,10 +86,16 @@ struct FastSmem {
     // zone partials per distinct index of THIS CTA (CTA 0 pulls all of them in the update step)
     unsigned long long zW[LF_KMAX];
     long long zS[LF_KMAX], zmin[LF_KMAX], zmax[LF_KMAX];
+    NpWarpScratch np;         // leaf list of NumPy's pairwise sum over k values (built once) + its scratch
+    int np_leaves;
+    int cpre[LF_R];           // chunks of the zones before region r (SAFE regions: none); same numbers in every CTA
+    ZoneSlot slot[LF_MAXCH];  // CTA 0: per-chunk results of the two-candidate zones (remote plain stores, one writer each)
     long long Wprev[LF_KMAX], Sprev[LF_KMAX];
     float c_emit[LF_KMAX];
     long long xbuf[2 * LF_KMAX];  // staging of the peer exchange
 };
+
+static_assert(sizeof(FastSmem) <= 227 * 1024, "FastSmem must fit the 227 KB of shared memory a CTA can opt into");
 
 struct FastConst {  // read once from the LloydDevice header
     int k, rank, world, max_iter;
@@ -86,7 +103,7 @@ struct FastConst {  // read once from the LloydDevice header
     const unsigned int *cnt;
     unsigned long long *cand;
     float mean, xabs_max;
-    double scale;
+    double scale, inv_scale;  // 2^(30-E) and its (exact) reciprocal
 };
 
 // NumPy's pairwise float32 sum (numpy/_core/src/umath/loops_utils.h.src) of a[0, n), n <= 1024, by ONE WARP: the leaves
@@ -112,12 +129,14 @@ static __device__ float np_fold_leaves(int n, const NpWarpScratch &W, int &idx) 
     const float r = np_fold_leaves(n - n2, W, idx);
     return fadd(l, r);
 }
-__device__ float np_pairwise_warp(const float *a, int n, NpWarpScratch &W) {  // all 32 lanes of one warp; result in lane 0
+// n_leaves < 0: build the leaf list first (it only depends on n: callers with a fixed n build it once and pass the count)
+__device__ float np_pairwise_warp(const float *a, int n, NpWarpScratch &W, int n_leaves = -1) {  // one whole warp; result in lane 0
     const int lane = lane_id(), grp = lane >> 3, j = lane & 7;
-    int n_leaves = 0;
-    if (lane == 0) n_leaves = np_leaf_list(0, n, W, 0);
-    n_leaves = __shfl_sync(0xffffffffu, n_leaves, 0);
-    __syncwarp();
+    if (n_leaves < 0) {
+        if (lane == 0) n_leaves = np_leaf_list(0, n, W, 0);
+        n_leaves = __shfl_sync(0xffffffffu, n_leaves, 0);
+        __syncwarp();
+    }
     for (int l0 = 0; l0 < n_leaves; l0 += 4) {
         const int l = l0 + grp;
         float r = 0.f;
@@ -166,17 +185,19 @@ __device__ __forceinline__ int fast_label_at(const FastSmem &S, const float *ks,
 }
 
 // ---- zone step: the float32 label rule for the few entries inside the zones.
-// Every CTA accumulates into ITS OWN partials (S.zW / zS / zmin / zmax, local shared-memory atomics); CTA 0 pulls the
-// eight partial sets over DSMEM in the update step.  (Remote atomics into CTA 0 -- generic-address 64-bit min / max on
-// another CTA's shared memory -- lost updates under contention on sm_100a and are not used.)
-//   small zones (<= LF_ZONE_WARP entries, the normal case: ~170 entries between two adjacent centroids): one warp per
-//       zone; two candidates keep their (count, sum) in registers, first / last member come from ballots;
-//   big zones (near-duplicate centroids after a relocation): chunks of LF_ZONE_WARP entries spread over all warps.
-constexpr int LF_ZONE_WARP = 2048;
+// The zones are cut into chunks of LF_CH entries and the chunks are dealt round robin to ALL warps of the cluster (zones
+// between adjacent centroids hold 40 .. 900 entries: one warp per zone left most warps idle behind the largest ones).
+//   two-candidate zones (the normal case): (count, sum) of the two candidates in registers, first / last members from
+//       ballots; the chunk's result goes to ITS slot in CTA 0's shared memory with plain remote stores -- one writer per
+//       slot, no atomics (generic-address 64-bit atomics on another CTA's shared memory lost updates under contention on
+//       sm_100a and are not used anywhere);
+//   zones with more candidates (near-duplicate centroids after a relocation), and chunks beyond the slot array: the
+//       generic leader loop into THIS CTA's partials (local atomics), which CTA 0 pulls over DSMEM in the update step.
+__device__ __forceinline__ bool zone_is_generic(const RegionTableT<LF_KMAX> &T, int r) { return T.rJ1[r] > T.rJ2[r] + 1; }
 
-// one warp: entries [lo, hi) of region r, any number of candidates; accumulates into the CTA's partials
+// one warp: entries [lo, hi) of a region, any number of candidates; accumulates into the CTA's partials
 __device__ __noinline__ void fast_zone_generic(FastSmem &S, const FastConst &K, const SearchConst &C, const float *__restrict__ ks,
-                                                  int J2, int J1, long long lo, long long hi) {
+                                               int J2, int J1, long long lo, long long hi) {
     const RegionTableT<LF_KMAX> &T = S.tab;
     const int lane = lane_id();
     const unsigned int *__restrict__ ecnt = K.cnt;
@@ -210,81 +231,105 @@ __device__ __noinline__ void fast_zone_generic(FastSmem &S, const FastConst &K, 
     }
 }
 
-__device__ void fast_zone_step(FastSmem &S, FastSmem *S0, const FastConst &K, const SearchConst &C, const float *__restrict__ ks,
+// returns (uniform over the cluster) whether any chunk took the generic path, i.e. whether CTA 0 has partials to pull
+__device__ bool fast_zone_step(FastSmem &S, FastSmem *S0, const FastConst &K, const SearchConst &C, const float *__restrict__ ks,
                                int gw, int NW, long long *prof = nullptr) {
     const int NT = blockDim.x;
     if (prof) prof[0] = clock64();
     FastZone &Z = S.u.zn;
     const RegionTableT<LF_KMAX> &T = S.tab;
     const int R = T.R, tid = threadIdx.x, lane = lane_id();
-    if (R <= 1) return;
+    if (R <= 1) return false;
     for (int r = tid; r <= R; r += NT) Z.rp[r] = S0->rpos[r];
     __syncthreads();
+    // chunks per zone -> exclusive prefix over the regions (every CTA computes the same numbers)
+    int any_generic = 0;
+    {
+        const int per = (R + NT - 1) / NT;
+        const int lo = min(R, tid * per), hi = min(R, lo + per);
+        int sum = 0;
+        for (int r = lo; r < hi; ++r) {
+            const bool zone = T.rJ1[r] > T.rJ2[r];
+            const long long sz = zone ? Z.rp[r + 1] - Z.rp[r] : 0ll;
+            const long long nch = (sz + LF_CH - 1) / LF_CH;
+            sum += (int)llmin2(nch, 1ll << 24);
+            any_generic |= zone && sz > 0 && zone_is_generic(T, r);
+        }
+        const int incl = block_scan_incl<int>(sum, [](int a, int b) { return a + b; }, Z.s_warp);
+        int run = incl - sum;
+        for (int r = lo; r < hi; ++r) {
+            S.cpre[r] = run;
+            const bool zone = T.rJ1[r] > T.rJ2[r];
+            const long long sz = zone ? Z.rp[r + 1] - Z.rp[r] : 0ll;
+            run += (int)llmin2((sz + LF_CH - 1) / LF_CH, 1ll << 24);
+        }
+        if (tid == NT - 1) S.cpre[R] = incl;
+    }
+    any_generic = __syncthreads_or(any_generic);
+    const int NC = S.cpre[R];
+    if (NC > LF_MAXCH) any_generic = 1;
     if (prof) prof[1] = clock64();
     const unsigned int *__restrict__ ecnt = K.cnt;
-    // is there a zone too large for one warp?  Every CTA looks at ALL regions (one per thread), so the whole cluster takes
-    // the same decision
-    int big = 0;
-    for (int r = tid; r < R; r += NT) big |= (T.rJ1[r] > T.rJ2[r]) && (Z.rp[r + 1] - Z.rp[r] > LF_ZONE_WARP);
-    // zones are normally the ODD regions (SAFE and ZONE alternate): odd regions first, one per warp, then the even ones
-    // (zones only in degenerate layouts) -- a plain r = gw, gw + NW, ... would leave every second warp without work
-    for (int pass = 0; pass < 2; ++pass)
-    for (int r = 2 * gw + 1 - pass; r < R; r += 2 * NW) {
+#pragma unroll 1
+    for (int ch = gw; ch < NC; ch += NW) {
+        int lo_r = 0, hi_r = R;  // largest r with cpre[r] <= ch: the zone that holds the chunk
+        while (hi_r - lo_r > 1) {
+            const int mid = (lo_r + hi_r) >> 1;
+            if (S.cpre[mid] <= ch)
+                lo_r = mid;
+            else
+                hi_r = mid;
+        }
+        const int r = lo_r;
         const int J2 = T.rJ2[r], J1 = T.rJ1[r];
-        if (J1 <= J2) continue;  // SAFE
-        const long long lo = Z.rp[r], hi = Z.rp[r + 1];
-        if (hi <= lo) continue;
-        if (hi - lo > LF_ZONE_WARP) continue;  // handled by all warps below
-        if (J1 != J2 + 1) {
-            fast_zone_generic(S, K, C, ks, J2, J1, lo, hi);
+        const long long base = Z.rp[r] + (long long)(ch - S.cpre[r]) * LF_CH;
+        const long long hi = llmin2(Z.rp[r + 1], base + LF_CH);
+        if (J1 != J2 + 1 || ch >= LF_MAXCH) {
+            fast_zone_generic(S, K, C, ks, J2, J1, base, hi);
             continue;
         }
         // two candidates a = J2 < b = J1: label b iff d_b < d_a, or d_b == d_a with the lower owner id
         const float va = T.dv[J2], vb = T.dv[J1], na = T.dcn[J2], nb = T.dcn[J1];
         const bool b_wins_ties = T.down[J1] < T.down[J2];
-        long long Wb = 0, Sb = 0, Wt = 0, St = 0;  // candidate b and both candidates together
-        long long fa = -1, la = -1, fb = -1, lb = -1;  // first / last member positions (uniform over the warp)
-        for (long long base = lo; base < hi; base += 128) {  // four rounds of 32 entries with all their loads in flight
-            float xv[4];
-            unsigned int cv[4];
+        long long Wb = 0, Sb = 0, Wt = 0, St = 0;
+        float xv[4];
+        unsigned int cv[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const long long p = base + 32 * j + lane;
-                const bool valid = p < hi;
-                xv[j] = valid ? ld_vol_f1(ks + p) : 0.f;
-                cv[j] = 1u;
-                if (ecnt && valid) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(cv[j]) : "l"(ecnt + p));
+        for (int j = 0; j < 4; ++j) {  // all loads of the chunk in flight
+            const long long p = base + 32 * j + lane;
+            const bool valid = p < hi;
+            xv[j] = valid ? ld_vol_f1(ks + p) : 0.f;
+            cv[j] = 1u;
+            if (ecnt && valid) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(cv[j]) : "l"(ecnt + p));
+        }
+        int fa = 0, la = 0, fb = 0, lb = 0;  // chunk offsets + 1
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool valid = base + 32 * j + lane < hi;
+            bool isb = false;
+            if (valid) {
+                const float xc = fsub(xv[j], K.mean);
+                const float m2x = fmul(-2.0f, xc);
+                const float da = skl_dist(m2x, va, na), db = skl_dist(m2x, vb, nb);
+                isb = db < da || (db == da && b_wins_ties);
+                const long long c = (long long)cv[j];
+                const long long q = fixed_qf(xc, C.scale_f, K.scale) * c;
+                Wt += c;
+                St += q;
+                if (isb) {
+                    Wb += c;
+                    Sb += q;
+                }
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const long long b32 = base + 32 * j;
-                if (b32 >= hi) break;
-                const bool valid = b32 + lane < hi;
-                bool isb = false;
-                if (valid) {
-                    const float xc = fsub(xv[j], K.mean);
-                    const float m2x = fmul(-2.0f, xc);
-                    const float da = skl_dist(m2x, va, na), db = skl_dist(m2x, vb, nb);
-                    isb = db < da || (db == da && b_wins_ties);
-                    const long long c = (long long)cv[j];
-                    const long long q = fixed_qf(xc, C.scale_f, K.scale) * c;
-                    Wt += c;
-                    St += q;
-                    if (isb) {
-                        Wb += c;
-                        Sb += q;
-                    }
-                }
-                const unsigned mb = __ballot_sync(0xffffffffu, valid && isb);
-                const unsigned ma = __ballot_sync(0xffffffffu, valid && !isb);
-                if (ma) {
-                    if (fa < 0) fa = b32 + (__ffs(ma) - 1);
-                    la = b32 + (31 - __clz(ma));
-                }
-                if (mb) {
-                    if (fb < 0) fb = b32 + (__ffs(mb) - 1);
-                    lb = b32 + (31 - __clz(mb));
-                }
+            const unsigned mb = __ballot_sync(0xffffffffu, valid && isb);
+            const unsigned ma = __ballot_sync(0xffffffffu, valid && !isb);
+            if (ma) {
+                if (!fa) fa = 32 * j + __ffs(ma);
+                la = 32 * j + 32 - __clz(ma);
+            }
+            if (mb) {
+                if (!fb) fb = 32 * j + __ffs(mb);
+                lb = 32 * j + 32 - __clz(mb);
             }
         }
         Wt = warp_sum_ll(Wt);
@@ -292,45 +337,106 @@ __device__ void fast_zone_step(FastSmem &S, FastSmem *S0, const FastConst &K, co
         Wb = warp_sum_ll(Wb);
         Sb = warp_sum_ll(Sb);
         if (lane == 0) {
-            if (fa >= 0) {
-                atomicAdd(&S.zW[J2], (unsigned long long)(Wt - Wb));
-                atomicAdd((unsigned long long *)&S.zS[J2], (unsigned long long)(St - Sb));
-                atomicMin(&S.zmin[J2], fa);
-                atomicMax(&S.zmax[J2], la);
-            }
-            if (fb >= 0) {
-                atomicAdd(&S.zW[J1], (unsigned long long)Wb);
-                atomicAdd((unsigned long long *)&S.zS[J1], (unsigned long long)Sb);
-                atomicMin(&S.zmin[J1], fb);
-                atomicMax(&S.zmax[J1], lb);
-            }
+            ZoneSlot *sl = &S0->slot[ch];
+            sl->Wb = Wb;
+            sl->Sb = Sb;
+            sl->Wt = Wt;
+            sl->St = St;
+            sl->ends = (unsigned)fa | ((unsigned)la << 8) | ((unsigned)fb << 16) | ((unsigned)lb << 24);
         }
     }
     if (prof) prof[2] = clock64();
-    // zones too large for one warp (rare): every warp of the cluster takes chunks of them
-    if (__syncthreads_or(big)) {
-        long long chunk0 = 0;  // chunks before the current region, counted identically by every warp
-        for (int r = 0; r < R; ++r) {
-            const int J2 = T.rJ2[r], J1 = T.rJ1[r];
-            if (J1 <= J2) continue;
-            const long long lo = Z.rp[r], hi = Z.rp[r + 1];
-            if (hi - lo <= LF_ZONE_WARP) continue;
-            const long long nch = (hi - lo + LF_ZONE_WARP - 1) / LF_ZONE_WARP;
-            long long c = (gw - chunk0 % NW + NW) % NW;  // first chunk of this region owned by this warp (global round robin)
-            for (; c < nch; c += NW) {
-                const long long b0 = lo + c * LF_ZONE_WARP;
-                fast_zone_generic(S, K, C, ks, J2, J1, b0, llmin2(hi, b0 + LF_ZONE_WARP));
-            }
-            chunk0 += nch;
-        }
-    }
     if (prof) prof[3] = clock64();
+    return any_generic != 0;
+}
+
+// CTA 0: per distinct index (count, sum, first / last member) of the ZONE entries -> U.Wd / Sd / first / last, from the chunk
+// slots of the two-candidate zones and, when `pull`, from the generic partials of every CTA (DSMEM loads).
+__device__ void fast_gather_zones(cg::cluster_group &cluster, FastSmem &S, bool pull) {
+    FastUpdate &U = S.u.up;
+    const RegionTableT<LF_KMAX> &T = S.tab;
+    const int NT = blockDim.x, n_cta = (int)cluster.num_blocks(), tid = threadIdx.x, m = T.m, R = T.R;
+    for (int i = tid; i < m; i += NT) {
+        U.aW[i] = U.aS[i] = U.bW[i] = U.bS[i] = 0;
+        U.af[i] = U.bf[i] = 0x7fffffffffffffffll;
+        U.al[i] = U.bl[i] = -1;
+    }
+    __syncthreads();
+    for (int r = tid; r < R; r += NT) {
+        const int J2 = T.rJ2[r], J1 = T.rJ1[r];
+        if (J1 != J2 + 1) continue;
+        const int c0 = S.cpre[r], c1 = min(S.cpre[r + 1], LF_MAXCH);
+        if (c0 >= c1) continue;
+        const long long lo = S.rpos[r];
+        long long Wb = 0, Sb = 0, Wt = 0, St = 0, fa = 0x7fffffffffffffffll, la = -1, fb = 0x7fffffffffffffffll, lb = -1;
+        for (int c = c0; c < c1; ++c) {
+            const ZoneSlot &sl = S.slot[c];
+            Wb += sl.Wb;
+            Sb += sl.Sb;
+            Wt += sl.Wt;
+            St += sl.St;
+            const long long cb = lo + (long long)(c - c0) * LF_CH - 1;  // chunk base - 1: the ends are offsets + 1
+            const unsigned e = sl.ends;
+            if (e & 0xffu) {
+                fa = llmin2(fa, cb + (e & 0xffu));
+                la = cb + ((e >> 8) & 0xffu);
+            }
+            if ((e >> 16) & 0xffu) {
+                fb = llmin2(fb, cb + ((e >> 16) & 0xffu));
+                lb = cb + (e >> 24);
+            }
+        }
+        U.aW[J2] = Wt - Wb;
+        U.aS[J2] = St - Sb;
+        U.af[J2] = fa;
+        U.al[J2] = la;
+        U.bW[J1] = Wb;
+        U.bS[J1] = Sb;
+        U.bf[J1] = fb;
+        U.bl[J1] = lb;
+    }
+    __syncthreads();
+    for (int i = tid; i < m; i += NT) {
+        long long w = U.aW[i] + U.bW[i], sm = U.aS[i] + U.bS[i];
+        long long mn = llmin2(U.af[i], U.bf[i]), mx = llmax2(U.al[i], U.bl[i]);
+        if (pull) {  // generic chunks: every CTA's local partials, one array at a time with its loads in flight together
+            long long v[LF_CL_MAX];
+#pragma unroll
+            for (int cta = 0; cta < LF_CL_MAX; ++cta)
+                if (cta < n_cta) v[cta] = (long long)((const volatile FastSmem *)cluster.map_shared_rank(&S, cta))->zW[i];
+#pragma unroll
+            for (int cta = 0; cta < LF_CL_MAX; ++cta)
+                if (cta < n_cta) w += v[cta];
+#pragma unroll
+            for (int cta = 0; cta < LF_CL_MAX; ++cta)
+                if (cta < n_cta) v[cta] = ((const volatile FastSmem *)cluster.map_shared_rank(&S, cta))->zS[i];
+#pragma unroll
+            for (int cta = 0; cta < LF_CL_MAX; ++cta)
+                if (cta < n_cta) sm += v[cta];
+#pragma unroll
+            for (int cta = 0; cta < LF_CL_MAX; ++cta)
+                if (cta < n_cta) v[cta] = ((const volatile FastSmem *)cluster.map_shared_rank(&S, cta))->zmin[i];
+#pragma unroll
+            for (int cta = 0; cta < LF_CL_MAX; ++cta)
+                if (cta < n_cta) mn = llmin2(mn, v[cta]);
+#pragma unroll
+            for (int cta = 0; cta < LF_CL_MAX; ++cta)
+                if (cta < n_cta) v[cta] = ((const volatile FastSmem *)cluster.map_shared_rank(&S, cta))->zmax[i];
+#pragma unroll
+            for (int cta = 0; cta < LF_CL_MAX; ++cta)
+                if (cta < n_cta) mx = llmax2(mx, v[cta]);
+        }
+        U.Wd[i] = w;
+        U.Sd[i] = sm;
+        U.first[i] = mn;
+        U.last[i] = mx;
+    }
 }
 
 // ---- update step (CTA 0 only; S is its own shared memory): per-cluster counts / sums, label-equality proxy, empty-cluster
 // relocation, averages, centre shift, convergence.  Mirrors update_phase of lloyd.cu statement by statement.
 __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const FastConst &K, const float *__restrict__ ks,
-                                 const PeerComm &pc, unsigned long long &xseq, float tol, long long *prof = nullptr) {
+                                 const PeerComm &pc, unsigned long long &xseq, float tol, bool pull, long long *prof = nullptr) {
     FastUpdate &U = S.u.up;
     const int NT = blockDim.x, n_cta = (int)cluster.num_blocks();
     if (prof) prof[0] = clock64();
@@ -339,40 +445,8 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
     const float mean = K.mean;
     const double scale = K.scale;
     const float x0 = fsub(0.f, mean);
-    // ---- 1. per distinct index: zone partials of every CTA (pulled over DSMEM) + SAFE regions
-    if (tid < m) {
-        long long w = 0, sm = 0, mn = 0x7fffffffffffffffll, mx = -1;
-        // one array at a time, its n_cta loads in flight together (volatile: the compiler must not chain them)
-        long long v[LF_CL_MAX];
-#pragma unroll
-        for (int cta = 0; cta < LF_CL_MAX; ++cta)
-            if (cta < n_cta) v[cta] = (long long)((const volatile FastSmem *)cluster.map_shared_rank(&S, cta))->zW[tid];
-#pragma unroll
-        for (int cta = 0; cta < LF_CL_MAX; ++cta)
-            if (cta < n_cta) w += v[cta];
-#pragma unroll
-        for (int cta = 0; cta < LF_CL_MAX; ++cta)
-            if (cta < n_cta) v[cta] = ((const volatile FastSmem *)cluster.map_shared_rank(&S, cta))->zS[tid];
-#pragma unroll
-        for (int cta = 0; cta < LF_CL_MAX; ++cta)
-            if (cta < n_cta) sm += v[cta];
-#pragma unroll
-        for (int cta = 0; cta < LF_CL_MAX; ++cta)
-            if (cta < n_cta) v[cta] = ((const volatile FastSmem *)cluster.map_shared_rank(&S, cta))->zmin[tid];
-#pragma unroll
-        for (int cta = 0; cta < LF_CL_MAX; ++cta)
-            if (cta < n_cta) mn = llmin2(mn, v[cta]);
-#pragma unroll
-        for (int cta = 0; cta < LF_CL_MAX; ++cta)
-            if (cta < n_cta) v[cta] = ((const volatile FastSmem *)cluster.map_shared_rank(&S, cta))->zmax[tid];
-#pragma unroll
-        for (int cta = 0; cta < LF_CL_MAX; ++cta)
-            if (cta < n_cta) mx = llmax2(mx, v[cta]);
-        U.Wd[tid] = w;
-        U.Sd[tid] = sm;
-        U.first[tid] = mn;
-        U.last[tid] = mx;
-    }
+    // ---- 1. per distinct index: zone entries (chunk slots, generic partials) + SAFE regions
+    fast_gather_zones(cluster, S, pull);
     if (tid < k) {
         U.W[tid] = 0;
         U.S[tid] = 0;
@@ -393,45 +467,31 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
             U.last[di] = llmax2(U.last[di], hi - 1);
         }
     }
+    // ---- 2. zero run: the label of x'_0 = fl(0 - mean) is a region-table lookup -- the table is exact for every point of
+    // the line, not only for samples (one thread; the block argmin over all distinct centroids cost three barriers)
+    if (tid == NT - 1) {
+        int zdi = -1;
+        if (K.n0 > 0) {
+            int lo = 0, hi = R;  // largest r with rstart[r] <= x0 (rstart[0] = -inf)
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (T.rstart[mid] <= x0)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            zdi = T.rJ1[lo] == T.rJ2[lo] ? T.rJ1[lo] : zone_argmin(x0, T.dv, T.dcn, T.down, T.rJ2[lo], T.rJ1[lo]);
+        }
+        U.zdi = zdi;
+    }
     __syncthreads();
     if (prof) prof[1] = clock64();
-    // ---- 2. zero run: label of x'_0 = fl(0 - mean) over all distinct centroids
-    if (K.n0 > 0) {
-        if (warp_id() == 0) {  // argmin by (d, owner id) over the m distinct centroids: one warp, strided
-            float d = INFINITY;
-            int id = 0x7fffffff, di = -1;
-            const float m2x = fmul(-2.0f, x0);
-            for (int i = lane_id(); i < m; i += 32) {
-                const float di_d = skl_dist(m2x, T.dv[i], T.dcn[i]);
-                const int di_id = T.down[i];
-                if (di_d < d || (di_d == d && di_id < id)) {
-                    d = di_d;
-                    id = di_id;
-                    di = i;
-                }
-            }
-            for (int o = 16; o > 0; o >>= 1) {
-                const float d2 = __shfl_xor_sync(0xffffffffu, d, o);
-                const int id2 = __shfl_xor_sync(0xffffffffu, id, o);
-                const int di2 = __shfl_xor_sync(0xffffffffu, di, o);
-                if (d2 < d || (d2 == d && id2 < id)) {
-                    d = d2;
-                    id = id2;
-                    di = di2;
-                }
-            }
-            if (lane_id() == 0) {
-                U.zdi = di;
-                const long long q0 = fixed_q(x0, scale);
-                U.Wd[di] += K.n0;
-                U.Sd[di] += K.n0 * q0;
-            }
-        }
-        __syncthreads();
-    } else {
-        if (tid == 0) U.zdi = -1;
-        __syncthreads();
+    if (K.n0 > 0 && tid == U.zdi) {
+        const long long q0 = fixed_q(x0, scale);
+        U.Wd[tid] += K.n0;
+        U.Sd[tid] += K.n0 * q0;
     }
+    __syncthreads();
     if (pc.enabled) {  // fused all-reduce of the exact per-distinct-index (count, sum) over the ranks
         if (tid < m) {
             S.xbuf[tid] = U.Wd[tid];
@@ -664,7 +724,7 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
     if (prof) prof[4] = clock64();
     // ---- 6. averages (_average_centers), shift (_center_shift)
     // S / 2^s == S * 2^-s exactly (a power-of-two scaling of the double image of S), without a float64 division
-    if (tid < k) U.raw[tid] = (float)__dmul_rn((double)U.S[tid], __ddiv_rn(1.0, scale));
+    if (tid < k) U.raw[tid] = (float)__dmul_rn((double)U.S[tid], K.inv_scale);
     // argmax of the counts, lowest id on ties (np.argmax): key = count << 10 | (1023 - id), count < 2^53
     {
         unsigned long long key = tid < k ? (((unsigned long long)U.W[tid] << 10) | (unsigned long long)(1023 - tid)) : 0ull;
@@ -683,7 +743,13 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
     }
     if (tid < k) {
         const int amax = U.winner;
-        auto avg = [&](int j) { return fmul(U.raw[j], (float)__ddiv_rn(1.0, (double)U.W[j])); };
+        // (float)(1.0 / (double)W): for W < 2^24 (exact in float32) the float32 division gives the same value -- double
+        // rounding is innocuous for a quotient of float32 operands when the wide format has >= 2 * 24 + 2 bits
+        auto avg = [&](int j) {
+            const long long Wj = U.W[j];
+            const float rcp = Wj < (1ll << 24) ? __fdiv_rn(1.0f, (float)Wj) : (float)__ddiv_rn(1.0, (double)Wj);
+            return fmul(U.raw[j], rcp);
+        };
         float cn;
         if (U.W[tid] > 0)
             cn = avg(tid);
@@ -701,7 +767,7 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
     if (prof) prof[5] = clock64();
     // ---- 7. convergence (_kmeans.py:721-738)
     if (warp_id() == 0) {
-        const float tot = np_pairwise_warp(U.sq, k, U.np);
+        const float tot = np_pairwise_warp(U.sq, k, S.np, S.np_leaves);
         int stop = 0, strict = 0;
         if (!any_differs) {
             stop = 1;
@@ -767,6 +833,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     K.mean = st->mean;
     K.xabs_max = st->xabs_max;
     K.scale = st->scale;
+    K.inv_scale = __ddiv_rn(1.0, K.scale);
     const int k = K.k;
     SearchConst C = search_const(st, ks, samp, ptile);
     if (C.n_tiles > 64) {  // top level of the tile-sample index in shared memory (the samples never change)
@@ -783,6 +850,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         S.perm[tid] = 0;
     }
     if (tid == 0) {
+        S.np_leaves = np_leaf_list(0, k, S.np, 0);
         S.done = 0;
         S.iter = 0;
         S.strict = 0;
@@ -862,12 +930,9 @@ __global__ void __launch_bounds__(THREADS, 1)
             S.rsum[R] = total_q;
         }
         if (lg) tl[0] = now();
-        if (want_log > 1) {  // experiment: the same table build again, warm (instruction cache, shared memory state)
-            const unsigned long long w0 = now();
-            build_region_table(S.c, k, K.xabs_max, &S.tab, S.u.tb, S.perm);
-            if (lg && it == 6) st->logZ[LL_LOG - 40] = (long long)(now() - w0);
-            if (lg) tl[0] = now();
-        }
+        const bool stamp = want_log > 1 && tid == 0 && it == 6 && !hist_round;
+        unsigned long long *sl = reinterpret_cast<unsigned long long *>(st->logZ) + 8 * cta;  // [cta][8] ns stamps
+        if (stamp) sl[0] = now();
         {
             int trip = 0;
 #pragma unroll 1
@@ -881,22 +946,27 @@ __global__ void __launch_bounds__(THREADS, 1)
                 }
             }
         }
+        if (stamp) sl[1] = now();
         cluster.sync();
+        if (stamp) sl[2] = now();
         if (lg) tl[1] = now();
+        bool pull = false;
         {
             long long zp[4];
-            fast_zone_step(S, S0, K, C, ks, gw, NW, lg ? zp : nullptr);
+            pull = fast_zone_step(S, S0, K, C, ks, gw, NW, lg ? zp : nullptr);
             if (lg && S.iter == 6)
                 for (int i = 0; i < 4; ++i) st->logZ[LL_LOG - 16 + i] = zp[i] - zp[0];
         }
+        if (stamp) sl[3] = now();
         cluster.sync();
+        if (stamp) sl[4] = now();
         if (lg) tl[2] = now();
         // ---- M-step (CTA 0), or the counts of the closing round
         if (cta == 0) {
             if (!hist_round) {
                 long long up[8];
                 const int it_now = S.iter;
-                fast_update_step(cluster, S, K, ks, pc, xseq, tol, lg ? up : nullptr);
+                fast_update_step(cluster, S, K, ks, pc, xseq, tol, pull, lg ? up : nullptr);
                 if (lg && it_now == 6) {
                     up[7] = clock64();
                     for (int i = 0; i < 8; ++i) st->logZ[LL_LOG - 32 + i] = up[i] - up[0];
@@ -906,11 +976,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 const RegionTableT<LF_KMAX> &T = S.tab;
                 const int m = T.m;
                 if (tid < k) st->hist[tid] = 0;
-                if (tid < m) {
-                    long long w = 0;
-                    for (int c2 = 0; c2 < n_cta; ++c2) w += (long long)cluster.map_shared_rank(&S, c2)->zW[tid];
-                    Wd[tid] = w;
-                }
+                fast_gather_zones(cluster, S, pull);
                 __syncthreads();
                 for (int r = tid; r < R; r += NT) {
                     if (T.rJ1[r] != T.rJ2[r]) continue;
@@ -923,7 +989,9 @@ __global__ void __launch_bounds__(THREADS, 1)
                 if (tid < m) st->hist[T.down[tid]] = Wd[tid];
             }
         }
+        if (stamp) sl[5] = now();
         cluster.sync();
+        if (stamp) sl[6] = now();
         if (hist_round) break;
         const int stopped = S0->done;
         if (lg && it < LL_LOG) {

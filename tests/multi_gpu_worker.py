@@ -76,6 +76,32 @@ def main():
             failures.append((bits, rank))
         print("rank %d bits %d iters %d reloc %d thr %.9g peer_exchange=%s %s" % (rank, bits, km.n_iter_, km.n_relocations, ref_thr,
                                                                                     dctx.peer_exchange, "OK" if ok else "MISMATCH " + "; ".join(bad)), flush=True)
+    # density / forgy init on shards: global min / max + 31-bin histogram all-reduce, forgy owner gather
+    g = torch.Generator(device="cuda").manual_seed(77)
+    full = torch.empty(n, device="cuda").normal_(0.0, 0.02, generator=g)
+    for mode, bits in (("density", 2), ("forgy", 5)):
+        N._tls.ctx = {}
+        ref_w = full.clone()
+        np.random.seed(5)
+        ref_mask, ref_km = U.compress_weight(ref_w, 1.0, True, bits, mode)
+        N._tls.ctx = {}
+        dctx = U.init_distributed()
+        b, e = U.shard_range(n, rank, world)
+        mine = full[b:e].clone()
+        np.random.seed(5)
+        mask, km = U.compress_weight(mine, 1.0, True, bits, mode)
+        bad = []
+        if not bool(torch.equal(mask, ref_mask[b:e])):
+            bad.append("mask")
+        if km.cluster_centers_.tobytes() != ref_km.cluster_centers_.tobytes():
+            bad.append("centers")
+        if (km.n_iter_, km.n_relocations) != (ref_km.n_iter_, ref_km.n_relocations):
+            bad.append("iters %r %r" % ((km.n_iter_, km.n_relocations), (ref_km.n_iter_, ref_km.n_relocations)))
+        if not np.array_equal(km.code_histogram, ref_km.code_histogram):
+            bad.append("hist")
+        if bad:
+            failures.append((mode, rank))
+        print("rank %d %s-%d iters %d k %d %s" % (rank, mode, bits, km.n_iter_, km.n_clusters, "OK" if not bad else "MISMATCH " + "; ".join(bad)), flush=True)
     t = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(t)
     dist.destroy_process_group()

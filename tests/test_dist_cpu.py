@@ -57,7 +57,57 @@ def test_reference_arm_runs_on_rank0_only():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["e2e"]["h2d_bytes_per_step"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["value"] > 0
+
+
+INIT_WORKER = r"""
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from neural_network_compression_b200 import _native as N
+from neural_network_compression_b200.common import utility as U
+from oracle import oracle as O
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+ops = {"min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX, "sum": dist.ReduceOp.SUM}
+def allreduce(a, op):
+    t = torch.from_numpy(np.ascontiguousarray(a).copy()); dist.all_reduce(t, op=ops[op]); return t.numpy()
+ok = True
+for n, seed in ((300000, 5), (100003, 6)):
+    w = (np.random.RandomState(seed).randn(n) * 0.05).astype(np.float32)
+    w[np.abs(w) < 0.05] = 0                                   # a pruned layer: density init looks at the non-zeros only
+    b, e = N.shard_range(n, rank, world)
+    mine = w[b:e]
+    nz = mine[mine != 0]
+    # the exchange logic of utility.get_weight_distribution on shards, with NumPy standing in for the two device sweeps
+    def local_minmax():
+        return (nz.min(), nz.max(), nz.size) if nz.size else (np.float32(0), np.float32(0), 0)
+    def local_hist(edges):
+        return np.array([np.count_nonzero((nz >= edges[i]) & (nz < edges[i + 1])) for i in range(31)], dtype=np.int64)
+    xnew, cdf = U.sharded_weight_distribution(local_minmax, local_hist, allreduce)
+    ref = O.get_weight_distribution(w[w != 0])              # the single-rank restatement (pinned to the reference's goldens)
+    ok &= xnew.tobytes() == ref[0].tobytes() and cdf.tobytes() == ref[1].tobytes()
+    for bits in (2, 8):                                       # density init from the sharded CDF == from the whole tensor
+        ok &= U._init_density(bits, (xnew, cdf)).tobytes() == O.init_centroids(w, bits, "density", ref).tobytes()
+    # forgy: same global draws on every rank, owners supply the values
+    np.random.seed(3)
+    idx = np.random.randint(0, n, size=32)
+    space = U.sharded_forgy_init(idx, b, e, lambda local_idx: mine[local_idx], allreduce)
+    ok &= space.tobytes() == w[idx].tobytes()
+print("RANK", rank, "OK" if ok else "BAD", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+"""
+
+
+def test_density_and_forgy_init_on_shards_gloo(tmp_path):
+    """density init from an all-reduce of per-rank 31-bin histograms (+ min / max), forgy through an owner
+    gather: the exchange logic of utility.py under gloo on two CPU ranks equals the single-rank result bit for bit."""
+    w = tmp_path / "init_worker.py"
+    w.write_text(INIT_WORKER % ROOT)
+    r = _torchrun([str(w)])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("OK") == 2
 
 
 def test_shard_range_small_tensors():

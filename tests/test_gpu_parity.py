@@ -571,7 +571,7 @@ def test_sharded_equals_single_rank():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                         "--master-addr", "127.0.0.1", "--master-port", "29517", worker], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("OK") == 3 * world and "MISMATCH" not in r.stdout
+    assert r.stdout.count("OK") == 5 * world and "MISMATCH" not in r.stdout
 
 
 # ---------------------------------------------------------------------------------------------------------
