@@ -169,6 +169,21 @@ __device__ float np_pairwise_warp(const float *a, int n, NpWarpScratch &W, int n
     return tot;
 }
 
+// label (distinct index) of the sorted survivor at position p whose value x is already in a register
+__device__ __forceinline__ int fast_label_of(const FastSmem &S, float mean, long long p, float x) {
+    const RegionTableT<LF_KMAX> &T = S.tab;
+    int lo = 0, hi = T.R;  // largest r with rpos[r] <= p
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (S.rpos[mid] <= p)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    if (T.rJ1[lo] == T.rJ2[lo]) return T.rJ1[lo];
+    return zone_argmin(fsub(x, mean), T.dv, T.dcn, T.down, T.rJ2[lo], T.rJ1[lo]);
+}
+
 // label (distinct index) of the sorted survivor at position p
 __device__ __forceinline__ int fast_label_at(const FastSmem &S, const float *ks, float mean, long long p) {
     const RegionTableT<LF_KMAX> &T = S.tab;
@@ -633,21 +648,46 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
                     if (reml > 1) {
                         reml -= 1;
                     } else {
+                        // next member from the left: value and count of a candidate position are loaded together (one
+                        // round trip), the label check uses the loaded value
+                        float x = 0.f;
+                        unsigned long long c = 1ull;
                         do {
                             ++pl;
-                        } while (pl <= pr && fast_label_at(S, ks, mean, pl) != tid);
-                        if (pl <= pr) reml = pl == pr ? remr : cnt_at(pl);
-                        refresh();
+                            if (pl > pr) break;
+                            x = ks[pl];
+                            c = cnt_at(pl);
+                        } while (fast_label_of(S, mean, pl, x) != tid);
+                        has_l = false;
+                        if (pl <= pr) {
+                            reml = pl == pr ? remr : c;
+                            xl = fsub(x, mean);
+                            kl = far_key(xl, cown);
+                            has_l = true;
+                        }
+                        if (pl >= pr) has_r = false;  // the cursors met: the left one owns what is left
                     }
                 } else {
                     if (remr > 1) {
                         remr -= 1;
                     } else {
+                        float x = 0.f;
+                        unsigned long long c = 1ull;
                         do {
                             --pr;
-                        } while (pr >= pl && fast_label_at(S, ks, mean, pr) != tid);
-                        if (pr > pl) remr = cnt_at(pr);
-                        refresh();
+                            if (pr < pl) break;
+                            x = ks[pr];
+                            c = cnt_at(pr);
+                        } while (fast_label_of(S, mean, pr, x) != tid);
+                        has_r = false;
+                        if (pr > pl) {
+                            remr = c;
+                            xr = fsub(x, mean);
+                            kr = far_key(xr, cown);
+                            has_r = true;
+                        } else if (pr < pl) {
+                            has_l = false;
+                        }
                     }
                 }
             }

@@ -97,6 +97,7 @@ struct VisitStats {
         amax = max(amax, __float_as_uint(x) & 0x7fffffffu);
         return x;
     }
+    __device__ __forceinline__ float term(float x) const { return x; }
     __device__ __forceinline__ float4 visit4(int64_t, const float *, float4 x) {
         return make_float4(one(x.x), one(x.y), one(x.z), one(x.w));
     }
@@ -146,6 +147,7 @@ struct VisitCenSq {
         float t = fsub(x, mean);
         return fmul(t, t);
     }
+    __device__ __forceinline__ float term(float x) const { return one(x); }
     __device__ __forceinline__ float4 visit4(int64_t, const float *, float4 x) {
         return make_float4(one(x.x), one(x.y), one(x.z), one(x.w));
     }
@@ -177,6 +179,10 @@ struct VisitCenSqApply {
     // the kernel writes the memory it reads: no non-coherent path here
     __device__ __forceinline__ float4 load4(const float *p) const { return *reinterpret_cast<const float4 *>(p); }
     __device__ __forceinline__ float load1(const float *p) const { return *p; }
+    __device__ __forceinline__ float term(float x) const {
+        const float t = fsub(x, mean);
+        return fmul(t, t);
+    }
     __device__ __forceinline__ float one(int64_t g, float x, float &outv, uint32_t &m) {
         float t = fsub(x, mean);
         float a = fabsf(x);
@@ -262,6 +268,7 @@ struct VisitQuant {
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ float4 load4(const float *p) const { return ld_stream_f4(p); }
     __device__ __forceinline__ float load1(const float *p) const { return ld_stream_f1(p); }
+    __device__ __forceinline__ float term(float x) const { return x; }
     __device__ __forceinline__ float one(float x) {
         const uint32_t a = __float_as_uint(x) & 0x7fffffffu;
         amax = max(amax, a);
@@ -321,6 +328,7 @@ struct VisitPlain {
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ float4 load4(const float *p) const { return *reinterpret_cast<const float4 *>(p); }
     __device__ __forceinline__ float load1(const float *p) const { return *p; }
+    __device__ __forceinline__ float term(float x) const { return x; }
     __device__ __forceinline__ float4 visit4(int64_t, const float *, float4 x) { return x; }
     __device__ __forceinline__ float visit1(int64_t, const float *, float x) { return x; }
     __device__ __forceinline__ void end_tile() {}
@@ -380,6 +388,13 @@ struct VisitApplyQuant {
         dirty = false;
         return d;
     }
+    // tree 1: centred squares; tree 2: the pruned value.  (An element inside the band counts as kept here: its tile is on
+    // the dirty list and its second-tree partial is recomputed from the final tensor, so the value does not matter.)
+    __device__ __forceinline__ float term(float x) const {
+        const float t = fsub(x, mean);
+        return fmul(t, t);
+    }
+    __device__ __forceinline__ float term2(float x) const { return fabsf(x) < lo ? 0.f : x; }
     // an element inside the band: decided later with the exact threshold (rare: ~1e-5 of the elements).  A free
     // function on purpose: a non-inlined MEMBER would take `this` and push the whole visitor into local memory.
     __device__ __forceinline__ void band(int64_t g, float x) {
@@ -483,32 +498,26 @@ struct VisitApplyQuant {
 // ---------------------------------------------------------------------------------------------
 // The tree kernel: one tile (= one depth-`depth` subtree of NumPy's recursion, 2041..4096 elements) per loop
 // iteration.
-//   stage   coalesced 128-bit loads, the visitor's term of every element goes to shared memory; the tile is
-//           stored with 8 floats of padding per 128 so that the strided leaf reads below are conflict free
+//   stage   the RAW tile arrives in shared memory by ONE bulk-asynchronous copy (cp.async.bulk + mbarrier), double
+//           buffered: the copy of tile i+1 is in flight while tile i is visited, summed and folded.  The visitor reads
+//           the staged values for its side effects (apply, mask, statistics, compaction)
 //   leaves  8 lanes per depth-5 node of the tile's sub-tree: NumPy's 8 strided accumulators per leaf (a node
-//           that is still > 128 elements splits once more into two leaves)
+//           that is still > 128 elements splits once more into two leaves); the tree TERM of an element (x, (x-mean)^2,
+//           the pruned value) is computed from the staged raw value on the fly
 //   fold    warp 0 folds the <= 32 node values up the sub-tree while the other warps stage the next tile
 // ---------------------------------------------------------------------------------------------
-constexpr int NP_TILE_SMEM = NP_TILE_MAX + (NP_TILE_MAX >> 7) * 8 + 16;
-
-__device__ __forceinline__ int np_pad(int e) { return e + ((e >> 7) << 3); }
-
 // sum of the leaf [o, o + s) of the staged tile in NumPy's order; called by the 8 lanes j = 0..7 of a group,
-// every lane returns the leaf's value.  s <= 128, o a multiple of 8.
-__device__ __forceinline__ float np_leaf_sum(const float *tile, int o, int s, int j) {
+// every lane returns the leaf's value.  s <= 128, o a multiple of 8.  f: the tree term of a raw element.
+template <class F>
+__device__ __forceinline__ float np_leaf_sum(const float *tile, int o, int s, int j, F f) {
     float r = 0.f;
     const int rows = s >> 3;  // full rows of 8 consecutive elements
-    // row i lives at pA[8 i] before the leaf crosses a multiple of 128 and at pA[8 i + 8] after it (the padding
-    // grows by 8 there; a row never straddles the crossing because o is a multiple of 8)
-    const float *pA = tile + np_pad(o + j);
-    const int istar = (128 - (o & 127)) >> 3;
+    const float *pA = tile + o + j;
     if (rows > 0) {
-        r = pA[0];
+        r = f(pA[0]);
 #pragma unroll
-        for (int i = 1; i < 16; ++i) {
-            const float *q = i >= istar ? pA + 8 : pA;
-            if (i < rows) r = fadd(r, q[8 * i]);
-        }
+        for (int i = 1; i < 16; ++i)
+            if (i < rows) r = fadd(r, f(pA[8 * i]));
     }
     // the 8 lanes of the group only: groups of one warp may be in different branches
     const unsigned gmask = 0xffu << (threadIdx.x & 24);
@@ -516,10 +525,10 @@ __device__ __forceinline__ float np_leaf_sum(const float *tile, int o, int s, in
     r = fadd(r, __shfl_xor_sync(gmask, r, 2));
     r = fadd(r, __shfl_xor_sync(gmask, r, 4));
     if (rows > 0) {
-        for (int i = rows << 3; i < s; ++i) r = fadd(r, tile[np_pad(o + i)]);
+        for (int i = rows << 3; i < s; ++i) r = fadd(r, f(tile[o + i]));
     } else {  // n < 8: plain sequential sum starting from 0
         r = 0.f;
-        for (int i = 0; i < s; ++i) r = fadd(r, tile[np_pad(o + i)]);
+        for (int i = 0; i < s; ++i) r = fadd(r, f(tile[o + i]));
     }
     return r;
 }
@@ -572,15 +581,28 @@ __global__ void np_tiles_kernel(int64_t n, int depth, NpTileDesc *desc) {
     desc[t] = d;
 }
 
-// value of the node `gd` of the staged tile `tl` (NumPy order); called by the 8 lanes j = 0..7 of a group
-__device__ __forceinline__ float np_node_value(const float *tl, uint32_t gd, int j) {
+// value of the node `gd` of the staged tile `tl` (NumPy order); called by the 8 lanes j = 0..7 of a group.
+// The tile lies in shared memory as in global memory (no padding).  A full leaf is 16 rows of 8 floats, lane j adds row
+// after row into accumulator j; the four groups of a warp work on leaves 128 floats apart, i.e. on the SAME eight banks
+// in every row.  They are therefore skewed by one row each: in step s group g reads row s - g (19 steps instead of 16), so
+// that the four groups always touch four different bank octets -- conflict free without padding, which lets the tile
+// arrive by a single bulk copy.  The additions of an accumulator happen in row order as in NumPy.
+template <class F>
+__device__ __forceinline__ float np_node_value(const float *tl, uint32_t gd, int j, F f) {
     const int o = gd & 8191, s = (gd >> 13) & 255;
     float val;
-    if (s == 128 && (o & 127) == 0) {  // the common case: a full, aligned leaf -- no address arithmetic
-        const float *p = tl + np_pad(o) + j;
-        val = p[0];
+    if (s == 128 && (o & 127) == 0) {  // the common case: a full, aligned leaf
+        const int g = (threadIdx.x >> 3) & 3;
+        const float *p = tl + o + j - 8 * g;
+        val = 0.f;
 #pragma unroll
-        for (int i = 1; i < 16; ++i) val = fadd(val, p[8 * i]);
+        for (int st = 0; st < 19; ++st) {
+            const int i = st - g;
+            if (i >= 0 && i < 16) {
+                const float x = f(p[8 * st]);
+                val = i == 0 ? x : fadd(val, x);
+            }
+        }
         const unsigned gmask = 0xffu << (threadIdx.x & 24);
         val = fadd(val, __shfl_xor_sync(gmask, val, 1));
         val = fadd(val, __shfl_xor_sync(gmask, val, 2));
@@ -588,81 +610,135 @@ __device__ __forceinline__ float np_node_value(const float *tl, uint32_t gd, int
     } else if (s > 128) {  // a depth-5 node that splits once more: two leaves
         int n2 = s >> 1;
         n2 -= n2 & 7;
-        const float l = np_leaf_sum(tl, o, n2, j);
-        const float r = np_leaf_sum(tl, o + n2, s - n2, j);
+        const float l = np_leaf_sum(tl, o, n2, j, f);
+        const float r = np_leaf_sum(tl, o + n2, s - n2, j, f);
         val = fadd(l, r);
     } else {
-        val = np_leaf_sum(tl, o, s, j);
+        val = np_leaf_sum(tl, o, s, j, f);
     }
     return val;
 }
 
+// ---- bulk-asynchronous copy + mbarrier (PTX; SASS: UBLKCP / SYNCS) --------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    const uint32_t addr = smem_addr(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+// dynamic shared memory of np_tree_kernel<V>: float raw[2][NP_TILE_MAX] (the double-buffered staged tile, as it lies in global memory), then for
+// kCompact float s_out[2][NP_TILE_MAX]
+template <class V>
+constexpr size_t np_tree_smem() {
+    return sizeof(float) * (2 * (size_t)NP_TILE_MAX + (V::kCompact ? 2 * (size_t)NP_TILE_MAX : 0));
+}
+
 // a: this rank's shard (elements [shard_begin, ...) of the flattened tensor); tiles [t0, t1) belong to it -- or, with a
 // tile list, the tiles tile_list[0, *list_count).
-// Dynamic shared memory: kCompact: float s_out[2][NP_TILE_MAX] (32 KB); kSecondTree: float tile2[NP_TILE_SMEM] after it.
 template <class V>
 __global__ void __launch_bounds__(NP_THREADS, V::kSecondTree ? 3 : 4) np_tree_kernel(const float *a, uint32_t t0, uint32_t t1, int64_t shard_begin,
                                                              int vec_ok, const NpTileDesc *__restrict__ desc, float *partials,
                                                              const uint32_t *__restrict__ tile_list, const unsigned int *list_count,
                                                              V v) {
-    __shared__ __align__(16) float tile[NP_TILE_SMEM];
     __shared__ float heap_val[2][64];
     __shared__ float heap_val2[V::kSecondTree ? 2 : 1][64];
     __shared__ unsigned int s_cnt[2];   // survivors staged so far in s_out[b]
     __shared__ unsigned int s_fcnt[2];  // ... of the completed tile in s_out[b], waiting to be flushed to s_base[b]
     __shared__ unsigned long long s_base[2];
     __shared__ int s_dirty[2];
+    __shared__ __align__(8) unsigned long long mbar[2];  // "tile staged" of raw[b]
     extern __shared__ __align__(16) unsigned char np_dyn_smem[];
-    float(*s_out)[NP_TILE_MAX] = reinterpret_cast<float(*)[NP_TILE_MAX]>(np_dyn_smem);
-    float *tile2 = reinterpret_cast<float *>(np_dyn_smem) + (V::kCompact ? 2 * NP_TILE_MAX : 0);
+    float(*raw)[NP_TILE_MAX] = reinterpret_cast<float(*)[NP_TILE_MAX]>(np_dyn_smem);
+    float(*s_out)[NP_TILE_MAX] = reinterpret_cast<float(*)[NP_TILE_MAX]>(np_dyn_smem + 2 * sizeof(float) * NP_TILE_MAX);
     __shared__ BlockAux aux;
 
     v.begin();
-    if (V::kTileCount || V::kCompact) {
-        if (threadIdx.x < 2) {
-            s_cnt[threadIdx.x] = 0;
-            s_fcnt[threadIdx.x] = 0;
-            s_base[threadIdx.x] = 0;
-            s_dirty[threadIdx.x] = 0;
-        }
-        __syncthreads();
+    if (threadIdx.x < 2) {
+        s_cnt[threadIdx.x] = 0;
+        s_fcnt[threadIdx.x] = 0;
+        s_base[threadIdx.x] = 0;
+        s_dirty[threadIdx.x] = 0;
+        mbar_init(&mbar[threadIdx.x], 1);
     }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
     const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;
-    int buf = 0;
     const uint32_t n_mine = tile_list ? *list_count : t1 - t0;
+    auto tile_id = [&](uint32_t it) { return tile_list ? tile_list[it] : t0 + it; };
+    // a tile travels by bulk copies when the tensor is 16-byte aligned and the tile is a whole number of 16-byte pieces
+    // (tile offsets are multiples of 8 elements; only the last tile of a tensor can be ragged)
+    auto bulk_ok = [&](int sz) { return vec_ok && (sz & 3) == 0; };
+    // ONE bulk copy per tile (<= 16 KB; the copy engine's rate is per operation: 32 copies of 512 B per tile, landing in a
+    // padded layout, ran 35 % slower than ordinary loads), issued by one thread into raw[b]
+    auto issue = [&](uint32_t it, int b) {
+        const uint32_t t = tile_id(it);
+        const int sz = desc[t].sz;
+        if (!bulk_ok(sz) || lane_id() != 0) return;
+        const float *src = a + (desc[t].off - shard_begin);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer's previous readers were ordinary loads
+        mbar_expect_tx(&mbar[b], (uint32_t)sz * 4u);
+        bulk_copy_g2s(&raw[b][0], src, (uint32_t)sz * 4u, &mbar[b]);
+    };
+    if (blockIdx.x < n_mine && warp_id() == 1) issue(blockIdx.x, 0);
+    int buf = 0;
+    uint32_t phase0 = 0, phase1 = 0;  // completed bulk stagings of raw[0] / raw[1] (the parity mbar_wait looks for)
     for (uint32_t it = blockIdx.x; it < n_mine; it += gridDim.x, buf ^= 1) {
-        const uint32_t t = tile_list ? tile_list[it] : t0 + it;
+        const uint32_t t = tile_id(it);
         const int64_t off = desc[t].off - shard_begin;  // offset inside the shard
         const int sz = desc[t].sz;
         const uint32_t gd = desc[t].grp[grp];
-        // ---- stage + visit: global -> terms in shared memory
         const float *src = a + off;
+        // ---- the next tile's copies go out first (its buffer was last read before the barrier that ended the previous
+        // iteration), then wait for this tile
+        if (it + gridDim.x < n_mine && warp_id() == 1) issue(it + gridDim.x, buf ^ 1);
+        float *tl = raw[buf];
+        if (bulk_ok(sz)) {
+            if (buf == 0) {
+                mbar_wait(&mbar[0], phase0 & 1u);
+                ++phase0;
+            } else {
+                mbar_wait(&mbar[1], phase1 & 1u);
+                ++phase1;
+            }
+        } else {  // unaligned tensor or the ragged last tile: ordinary loads into the same padded layout
+            for (int i = threadIdx.x; i < sz; i += NP_THREADS) tl[i] = v.load1(src + i);
+            __syncthreads();
+        }
+        // ---- visit: the visitor's side effects from the staged values (apply / mask / statistics / compaction)
         if (vec_ok) {
             const int nvec = sz >> 2;
             constexpr int NV = NP_TILE_MAX / 4 / NP_THREADS;
-            float4 x[NV];
+            constexpr int RSTRIDE = 4 * NP_THREADS;
+            const int sidx0 = 4 * (int)threadIdx.x;
             if constexpr (V::kSecondTree) {
                 float4 y2[NV];
                 int cnt = 0;
-                // element 4 i of the tile lives at tile[np_pad(4 i)]; i = r * NP_THREADS + tid, and 4 * NP_THREADS is a
-                // multiple of 128, so the padded index advances by a constant per r
-                constexpr int RSTRIDE = 4 * NP_THREADS + ((4 * NP_THREADS) >> 7) * 8;
-                const int sidx0 = np_pad(4 * (int)threadIdx.x);
                 auto stage = [&](auto full_c) {
                     constexpr bool FULL = decltype(full_c)::value;  // a complete 4096-element tile: no bounds checks
-#pragma unroll
-                    for (int r = 0; r < NV; ++r) {  // all loads first: the in-place stores would otherwise fence them
-                        const int i = r * NP_THREADS + threadIdx.x;
-                        if (FULL || i < nvec) x[r] = v.load4(src + 4 * i);
-                    }
 #pragma unroll
                     for (int r = 0; r < NV; ++r) {
                         const int i = r * NP_THREADS + threadIdx.x;
                         y2[r] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (FULL || i < nvec) {
-                            float4 y = v.visit4(off + 4 * i, src + 4 * i, x[r], y2[r]);
-                            *reinterpret_cast<float4 *>(&tile[sidx0 + r * RSTRIDE]) = y;
-                            *reinterpret_cast<float4 *>(&tile2[sidx0 + r * RSTRIDE]) = y2[r];
+                            const float4 x = *reinterpret_cast<const float4 *>(&tl[sidx0 + r * RSTRIDE]);
+                            (void)v.visit4(off + 4 * i, src + 4 * i, x, y2[r]);
                         }
                         cnt += (y2[r].x != 0.f) + (y2[r].y != 0.f) + (y2[r].z != 0.f) + (y2[r].w != 0.f);
                     }
@@ -693,36 +769,28 @@ __global__ void __launch_bounds__(NP_THREADS, V::kSecondTree ? 3 : 4) np_tree_ke
                 }
                 for (int i = (nvec << 2) + threadIdx.x; i < sz; i += NP_THREADS) {  // ragged end of the last tile
                     float y2s;
-                    tile[np_pad(i)] = v.visit1(off + i, src + i, v.load1(src + i), y2s);
-                    tile2[np_pad(i)] = y2s;
+                    (void)v.visit1(off + i, src + i, tl[i], y2s);
                     if (y2s != 0.f) s_out[buf][atomicAdd(&s_cnt[buf], 1u)] = y2s;
                 }
             } else {
 #pragma unroll
-                for (int r = 0; r < NV; ++r) {  // all loads first: the in-place visitor's stores would otherwise fence them
-                    const int i = r * NP_THREADS + threadIdx.x;
-                    if (i < nvec) x[r] = v.load4(src + 4 * i);
-                }
-#pragma unroll
                 for (int r = 0; r < NV; ++r) {
                     const int i = r * NP_THREADS + threadIdx.x;
                     if (i < nvec) {
-                        float4 y = v.visit4(off + 4 * i, src + 4 * i, x[r]);
-                        *reinterpret_cast<float4 *>(&tile[np_pad(4 * i)]) = y;
+                        const float4 x = *reinterpret_cast<const float4 *>(&tl[sidx0 + r * RSTRIDE]);
+                        (void)v.visit4(off + 4 * i, src + 4 * i, x);
                     }
                 }
-                for (int i = (nvec << 2) + threadIdx.x; i < sz; i += NP_THREADS)
-                    tile[np_pad(i)] = v.visit1(off + i, src + i, v.load1(src + i));
+                for (int i = (nvec << 2) + threadIdx.x; i < sz; i += NP_THREADS) (void)v.visit1(off + i, src + i, tl[i]);
             }
         } else {
             for (int i = threadIdx.x; i < sz; i += NP_THREADS) {
                 if constexpr (V::kSecondTree) {
                     float y2s;
-                    tile[np_pad(i)] = v.visit1(off + i, src + i, v.load1(src + i), y2s);
-                    tile2[np_pad(i)] = y2s;
+                    (void)v.visit1(off + i, src + i, tl[i], y2s);
                     if (y2s != 0.f) s_out[buf][atomicAdd(&s_cnt[buf], 1u)] = y2s;
                 } else {
-                    tile[np_pad(i)] = v.visit1(off + i, src + i, v.load1(src + i));
+                    (void)v.visit1(off + i, src + i, tl[i]);
                 }
             }
         }
@@ -734,38 +802,21 @@ __global__ void __launch_bounds__(NP_THREADS, V::kSecondTree ? 3 : 4) np_tree_ke
         if constexpr (V::kSecondTree) {
             if (v.take_dirty()) s_dirty[buf] = 1;
         }
-        __syncthreads();  // tile complete (also: warp 0 finished folding the tile before the previous one)
-        if constexpr (V::kSecondTree) {
-            // the other buffer's flag: warp 0 read it (fold of the previous tile) before arriving at the barrier above, and
-            // the next tile's staging sets it again only after the barrier below
-            if (threadIdx.x == 96) s_dirty[buf ^ 1] = 0;
-        }
-        if constexpr (V::kCompact) {
-            // flush the previous tile's survivors: its stage, count and global base are complete since the barrier
-            const int pb = buf ^ 1;
-            const unsigned int c = s_fcnt[pb];
-            if (c) {
-                const unsigned long long b = s_base[pb];
-                if (b + c <= v.capacity)
-                    for (unsigned int i = threadIdx.x; i < c; i += NP_THREADS) v.out[b + i] = s_out[pb][i];
-            }
-        }
-        // ---- leaves: the 8 lanes of group `grp` sum the node described by gd
+        // ---- leaves: the 8 lanes of group `grp` sum the node described by gd, the terms computed from the staged values
         {
             const int h = (gd >> 21) & 63;
-            const float val = np_node_value(tile, gd, j);
+            const float val = np_node_value(tl, gd, j, [&](float x) { return v.term(x); });
             if (j == 0 && (gd >> 27)) heap_val[buf][h] = val;
             if constexpr (V::kSecondTree) {
-                const float val2 = np_node_value(tile2, gd, j);
+                const float val2 = np_node_value(tl, gd, j, [&](float x) { return v.term2(x); });
                 if (j == 0 && (gd >> 27)) heap_val2[buf][h] = val2;
             }
         }
         if constexpr (V::kCompact && !V::kSecondTree) {
-            // survivors of the tile, straight from the staged values (the terms themselves for this visitor), compacted
-            // into the shared-memory stage s_out[buf]: a warp takes the 512 elements [512 w, 512 (w + 1)), counts, and
-            // reserves its slots of the stage with one shared-memory atomic (warp order inside the tile is arbitrary --
-            // the consumer is a sort).  (The fused visitor compacts from its registers while staging.)
-            const float *vals = tile;
+            // survivors of the tile, straight from the staged values, compacted into the shared-memory stage s_out[buf]: a
+            // warp takes the 512 elements [512 w, 512 (w + 1)), counts, and reserves its slots of the stage with one
+            // shared-memory atomic (warp order inside the tile is arbitrary -- the consumer is a sort).
+            const float *vals = tl;
             const int lane = lane_id(), wbase_e = warp_id() * 512;
             float4 xs[4];
             int cnt = 0;
@@ -773,7 +824,7 @@ __global__ void __launch_bounds__(NP_THREADS, V::kSecondTree ? 3 : 4) np_tree_ke
             for (int r = 0; r < 4; ++r) {
                 const int e = wbase_e + r * 128 + lane * 4;
                 xs[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (e < sz) xs[r] = *reinterpret_cast<const float4 *>(&vals[np_pad(e)]);
+                if (e < sz) xs[r] = *reinterpret_cast<const float4 *>(&vals[e]);
                 if (e + 3 >= sz) {  // tail of the (globally last) tile: mask what lies beyond it
                     if (e + 1 >= sz) xs[r].y = 0.f;
                     if (e + 2 >= sz) xs[r].z = 0.f;
@@ -801,8 +852,24 @@ __global__ void __launch_bounds__(NP_THREADS, V::kSecondTree ? 3 : 4) np_tree_ke
                 if (xs[r].w != 0.f) *dst++ = xs[r].w;
             }
         }
-        __syncthreads();  // node values visible; the tile buffers may be overwritten
-        // ---- fold (warp 0): internal nodes take left + right, level by level
+        __syncthreads();  // node values, survivor stage and dirty flag of this tile complete; raw[buf ^ 1]'s readers are done
+        if constexpr (V::kSecondTree) {
+            // the other buffer's flag: warp 0 read it (fold of the previous tile) before arriving at the barrier above, and
+            // the next tile's visit sets it again only after the barrier below
+            if (threadIdx.x == 96) s_dirty[buf ^ 1] = 0;
+        }
+        if constexpr (V::kCompact) {
+            // flush the previous tile's survivors: its stage, count and global base are complete since the barrier
+            const int pb = buf ^ 1;
+            const unsigned int c = s_fcnt[pb];
+            if (c) {
+                const unsigned long long b = s_base[pb];
+                if (b + c <= v.capacity)
+                    for (unsigned int i = threadIdx.x; i < c; i += NP_THREADS) v.out[b + i] = s_out[pb][i];
+            }
+        }
+        if constexpr (V::kCompact || V::kSecondTree) __syncthreads();  // the stage / flag of the other buffer may be written again
+        // ---- fold (warp 0): internal nodes take left + right, level by level, while the other warps visit the next tile
         if (threadIdx.x < 32) {
             const int lane = threadIdx.x;
             const uint32_t internal = desc[t].internal;
@@ -827,12 +894,12 @@ __global__ void __launch_bounds__(NP_THREADS, V::kSecondTree ? 3 : 4) np_tree_ke
         }
         if constexpr (V::kCompact) {
             // one global atomic per tile reserves the output slots; the copy stage -> global happens after the next
-            // barrier (the next tile's "tile complete"), so the atomic's latency is off the critical path
+            // tile's barrier, so the atomic's latency is off the critical path
             if (threadIdx.x == 64) {
                 const unsigned int c = s_cnt[buf];
                 s_base[buf] = c ? atomicAdd(v.cursor, (unsigned long long)c) : 0ull;
-                s_fcnt[buf] = c;  // read by the flush after the next tile's first barrier
-                s_cnt[buf] = 0;   // next written by the tile after next, which starts after the next tile's second barrier
+                s_fcnt[buf] = c;  // read by the flush after the next tile's barrier
+                s_cnt[buf] = 0;   // next written by the tile after next, which starts after the next tile's barrier
             }
         }
     }
@@ -1170,8 +1237,8 @@ static NpTileDesc *run_tree(nnc_ctx *ctx, const float *d_w, V v, const FinArgs &
     }
     if (ctx->world > 1) NNC_CUDA(cudaMemsetAsync(partials, 0, sizeof(float) * (2 * (size_t)p.num_tiles + 2), ctx->stream));
     const uint32_t t0 = ctx->sh.t0, t1 = ctx->sh.t1;
-    const size_t dyn = (V::kCompact ? 2 * sizeof(float) * NP_TILE_MAX : 0) + (V::kSecondTree ? sizeof(float) * NP_TILE_SMEM : 0);
-    if (V::kCompact) func_dyn_smem(ctx, (const void *)np_tree_kernel<V>, dyn);
+    const size_t dyn = np_tree_smem<V>();
+    func_dyn_smem(ctx, (const void *)np_tree_kernel<V>, dyn);
     if (t1 > t0)
         NNC_LAUNCH_AS(ctx, V::kName, np_tree_kernel<V>, tree_grid(ctx, t1 - t0), NP_THREADS, dyn, d_w, t0, t1, ctx->sh.begin,
                    aligned16(d_w) ? 1 : 0, desc, partials, (const uint32_t *)nullptr, (const unsigned int *)nullptr, v);
@@ -1275,8 +1342,9 @@ void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth,
                    (unsigned long long)fuse->capacity);
         NNC_LAUNCH(ctx, quant_scalars_kernel, 1, 1, 0, ctx->d_scal, cursor);
         // tiles that held undecided elements: their partial of the second tree from the final tensor
+        func_dyn_smem(ctx, (const void *)np_tree_kernel<VisitPlain>, np_tree_smem<VisitPlain>());
         NNC_LAUNCH_AS(ctx, VisitPlain::kName, np_tree_kernel<VisitPlain>, std::max(1, std::min<int>(ctx->sm_count * 4, (int)std::min<uint32_t>(p.num_tiles, 1u << 20))),
-                   NP_THREADS, 0, d_w, 0u, 0u, ctx->sh.begin, aligned16(d_w) ? 1 : 0, desc, partials2, (const uint32_t *)dirty_list,
+                   NP_THREADS, np_tree_smem<VisitPlain>(), d_w, 0u, 0u, ctx->sh.begin, aligned16(d_w) ? 1 : 0, desc, partials2, (const uint32_t *)dirty_list,
                    (const unsigned int *)dirty_count, VisitPlain{});
         exchange_scalars(ctx, EX_PRUNE);
         if (ctx->world > 1) comm_allreduce(ctx, reinterpret_cast<int64_t *>(partials2), (int)((p.num_tiles + 1) / 2), 0);
