@@ -67,8 +67,6 @@ void arena_reset(nnc_ctx *ctx) {
     }
     ctx->ws_off = 0;
     ctx->call_bytes = 0;
-    ctx->desc_n = -1;
-    ctx->desc_ptr = nullptr;
 }
 
 void arena_reserve(nnc_ctx *ctx, size_t bytes) {
@@ -416,6 +414,7 @@ void nnc_ctx_destroy(nnc_ctx *ctx) {
     if (ctx->peer_local) cudaFree(ctx->peer_local);
     for (void *p : ctx->overflow) cudaFree(p);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->desc_ptr) cudaFree(ctx->desc_ptr);
     if (ctx->d_scal) cudaFree(ctx->d_scal);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
@@ -910,7 +909,7 @@ int nnc_compress_f32(nnc_ctx *ctx, float *w, int64_t n, double threshold, int st
     if (write_back) stage_finish(ctx, sw);  // a device-resident tensor was pruned in place already
     if (mask_bits) pack_bits_device(ctx, d_mask_bytes, n, static_cast<uint8_t *>(sm.dev));
     stage_finish(ctx, sm);
-    read_scalars(ctx);
+    if (sw.host || sm.host) NNC_CUDA(cudaStreamSynchronize(ctx->stream));  // host copies complete (the scalars were read by prune_device)
     prof_mark(ctx, "prune_d2h");
     if (thr_out) *thr_out = ctx->h_scal->thr;
     if (n_pruned_out) *n_pruned_out = (int64_t)ctx->h_scal->n_pruned;

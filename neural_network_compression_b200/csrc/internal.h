@@ -90,8 +90,9 @@ struct nnc_ctx {
     size_t call_bytes = 0;      // bytes requested by the current call
     size_t high_water = 0;      // largest call so far: the main block is regrown to this at the next reset
     std::vector<void *> overflow;  // extra blocks taken when the main block was too small
-    int64_t desc_n = -1;           // reduction-tree tile descriptors already built in this call's arena (reduce_np.cu)
-    void *desc_ptr = nullptr;
+    int64_t desc_n = -1;           // reduction-tree tile descriptors of an n-element tensor (reduce_np.cu): they only depend
+    void *desc_ptr = nullptr;      // on n, so they are kept across calls in an allocation of their own
+    size_t desc_bytes = 0;
     bool user_stream = false;
     // optional per-kernel CUDA-event timing (benchmarks): one event pair per launch, folded by kernel name
     bool ktime = false;

@@ -152,60 +152,58 @@ __global__ void __launch_bounds__(1024) kh_base_kernel(const unsigned long long 
 }
 
 // ---- scatter: non-stable partition by the high digit --------------------------------------------------------
-// Shared memory (dynamic): stage[KH_TILE] | keys[KH_TILE] | hist[nb] | gbase[nb] (u64) | run[nb] (u64)
-__global__ void __launch_bounds__(KH_THREADS, 2) kh_scatter_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int64_t n,
+// Output: the LOW KH_LOW bits of every key as uint16 (inside a bucket the high digit is the bucket itself): half the
+// write traffic of a 32-bit key, and half the read of the histogram kernel.
+// Shared memory (dynamic): keys[KH_TILE] | hist[nb] | gbase[nb] (u64) | run[nb] (u64) -- 72 KB at 2048 buckets, three
+// CTAs per SM; the tile goes from global memory straight to registers (four 128-bit loads per thread).
+template <int MIN_CTAS, int THREADS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) kh_scatter_kernel(const uint32_t *__restrict__ in, uint16_t *__restrict__ out, int64_t n,
                                                                 int64_t tiles_per_chunk, int nb, KhKeyMap km,
                                                                 const unsigned long long *__restrict__ bucket_off,
                                                                 const uint32_t *__restrict__ crel_lo, const uint32_t *__restrict__ crel_hi) {
     extern __shared__ __align__(16) unsigned char kh_smem[];
-    uint32_t *stage = reinterpret_cast<uint32_t *>(kh_smem);
-    uint32_t *keys = stage + KH_TILE;
+    uint32_t *keys = reinterpret_cast<uint32_t *>(kh_smem);
     unsigned long long *gbase = reinterpret_cast<unsigned long long *>(keys + KH_TILE);
     unsigned long long *run = gbase + nb;
     uint32_t *hist = reinterpret_cast<uint32_t *>(run + nb);
-    __shared__ uint32_t s_warp[KH_THREADS / 32];
+    __shared__ uint32_t s_warp[32];
+    constexpr int ITEMS = KH_TILE / THREADS;
     const int lane = lane_id(), wid = warp_id();
-    for (int d = threadIdx.x; d < nb; d += KH_THREADS)
+    for (int d = threadIdx.x; d < nb; d += THREADS)
         run[d] = bucket_off[d] + (((unsigned long long)crel_hi[(size_t)blockIdx.x * nb + d] << 32) | crel_lo[(size_t)blockIdx.x * nb + d]);
     const int64_t n_tiles = (n + KH_TILE - 1) / KH_TILE;
     const int64_t t0 = (int64_t)blockIdx.x * tiles_per_chunk, t1 = min(n_tiles, t0 + tiles_per_chunk);
     const bool src_aligned = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
-    const int per = (nb + KH_THREADS - 1) / KH_THREADS;  // bins per thread in the scan (consecutive bins)
-    auto fetch = [&](int64_t tile) {
-        const int64_t tile_base = tile * KH_TILE;
-        if (src_aligned && tile_base + KH_TILE <= n) {
-#pragma unroll
-            for (int c = 0; c < KH_TILE / 4 / KH_THREADS; ++c) {
-                const int chunk = c * KH_THREADS + threadIdx.x;
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&stage[4 * chunk]);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(in + tile_base + 4 * chunk) : "memory");
-            }
-        } else {
-            for (int i = threadIdx.x; i < KH_TILE; i += KH_THREADS) stage[i] = tile_base + i < n ? in[tile_base + i] : 0u;
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    if (t0 < t1) fetch(t0);
+    const int per = (nb + THREADS - 1) / THREADS;  // bins per thread in the scan (consecutive bins)
     for (int64_t tile = t0; tile < t1; ++tile) {
         const int64_t tile_base = tile * KH_TILE;
         const int valid = (int)min((int64_t)KH_TILE, n - tile_base);
-        for (int d = threadIdx.x; d < nb; d += KH_THREADS) hist[d] = 0;
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();  // staged tile complete, counters cleared, previous tile's write-out finished
-        uint32_t key[KH_ITEMS];
-        uint32_t rank[KH_ITEMS];
+        // registers: 16 keys + 8 words of packed 13-bit ranks (three CTAs of 512 threads leave 42 registers per thread);
+        // a key beyond the end of the array is the sentinel ~0 (a real key has at most KH_LOW + KH_MAX_HB bits)
+        uint32_t key[ITEMS];
+        if (src_aligned && valid == KH_TILE) {
 #pragma unroll
-        for (int i = 0; i < KH_ITEMS; ++i) {
-            const int e = i * KH_THREADS + threadIdx.x;
-            key[i] = kh_key(stage[e], km);
-        }
+            for (int c = 0; c < ITEMS / 4; ++c) {
+                const uint4 v = ld_stream_u4(in + tile_base + 4 * (c * THREADS + threadIdx.x));
+                key[4 * c] = kh_key(v.x, km), key[4 * c + 1] = kh_key(v.y, km), key[4 * c + 2] = kh_key(v.z, km), key[4 * c + 3] = kh_key(v.w, km);
+            }
+        } else {
 #pragma unroll
-        for (int i = 0; i < KH_ITEMS; ++i) {
-            const int e = i * KH_THREADS + threadIdx.x;
-            rank[i] = e < valid ? atomicAdd(&hist[key[i] >> KH_LOW], 1u) : 0u;
+            for (int i = 0; i < ITEMS; ++i) {
+                const int e = i * THREADS + threadIdx.x;
+                key[i] = e < valid ? kh_key(in[tile_base + e], km) : 0xffffffffu;
+            }
         }
-        __syncthreads();  // stage consumed, counts complete
-        if (tile + 1 < t1) fetch(tile + 1);
+        for (int d = threadIdx.x; d < nb; d += THREADS) hist[d] = 0;
+        __syncthreads();  // counters cleared, previous tile's write-out finished
+        uint32_t rank2[ITEMS / 2];  // two ranks (< KH_TILE = 2^13) per word
+#pragma unroll
+        for (int i = 0; i < ITEMS; i += 2) {
+            const uint32_t r0 = key[i] != 0xffffffffu ? atomicAdd(&hist[key[i] >> KH_LOW], 1u) : 0u;
+            const uint32_t r1 = key[i + 1] != 0xffffffffu ? atomicAdd(&hist[key[i + 1] >> KH_LOW], 1u) : 0u;
+            rank2[i / 2] = r0 | (r1 << 16);
+        }
+        __syncthreads();  // counts complete
         // exclusive scan of the digit counts (thread t owns bins [t * per, t * per + per))
         if (per == 4) {  // 2048 buckets: 128-bit shared-memory accesses (consecutive 16-byte pieces: conflict free)
             const int b0 = threadIdx.x * 4;
@@ -259,26 +257,25 @@ __global__ void __launch_bounds__(KH_THREADS, 2) kh_scatter_kernel(const uint32_
         }
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < KH_ITEMS; ++i) {
-            const int e = i * KH_THREADS + threadIdx.x;
-            if (e < valid) keys[hist[key[i] >> KH_LOW] + rank[i]] = key[i];
-        }
+        for (int i = 0; i < ITEMS; ++i)
+            if (key[i] != 0xffffffffu) keys[hist[key[i] >> KH_LOW] + ((rank2[i / 2] >> (16 * (i & 1))) & 0xffffu)] = key[i];
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < KH_ITEMS; ++j) {
-            const int p = threadIdx.x + j * KH_THREADS;
+        for (int j = 0; j < ITEMS; ++j) {
+            const int p = threadIdx.x + j * THREADS;
             if (p < valid) {
                 const uint32_t k = keys[p];
-                out[gbase[k >> KH_LOW] + p] = k;
+                out[gbase[k >> KH_LOW] + p] = (uint16_t)(k & (KH_BINS - 1));
             }
         }
     }
 }
 
 // ---- hist: low-digit histogram of one work item (<= KH_CHUNK keys of one bucket) in shared memory -----------
-// IN_FLOAT: the input is the raw survivor array (no partition pass ran: keybits <= KH_LOW, one bucket).
+// IN_FLOAT: the input is the raw survivor array (no partition pass ran: keybits <= KH_LOW, one bucket); otherwise the
+// partition pass's uint16 low digits.
 template <bool IN_FLOAT>
-__global__ void __launch_bounds__(1024) kh_hist_kernel(const uint32_t *__restrict__ in, int nb, int low_bins, KhKeyMap km,
+__global__ void __launch_bounds__(1024) kh_hist_kernel(const void *__restrict__ in_raw, int nb, int low_bins, KhKeyMap km,
                                                        const unsigned long long *__restrict__ bucket_off,
                                                        const uint32_t *__restrict__ item_off, uint32_t *__restrict__ H,
                                                        uint32_t *__restrict__ tnz) {
@@ -301,47 +298,58 @@ __global__ void __launch_bounds__(1024) kh_hist_kernel(const uint32_t *__restric
     for (int i = threadIdx.x; i < low_bins; i += 1024) kh_bins[i] = 0;
     __syncthreads();
     const uint32_t lmask = (uint32_t)low_bins - 1u;
-    auto one = [&](uint32_t v) {
-        const uint32_t k = IN_FLOAT ? kh_key(v, km) : v;
-        atomicAdd(&kh_bins[k & lmask], 1u);
-    };
-    // head up to the first 16-byte boundary, vector body, tail
-    const uint32_t *p = in + beg;
     const unsigned long long cnt = end - beg;
-    unsigned long long head = ((16u - (unsigned)(reinterpret_cast<uintptr_t>(p) & 15u)) & 15u) >> 2;
-    if (head > cnt) head = cnt;
-    if (threadIdx.x < head) one(p[threadIdx.x]);
-    const unsigned long long nvec = (cnt - head) >> 2;
-    const uint32_t *pv = p + head;
-    unsigned long long i = threadIdx.x;
-    for (; i + 3 * 1024 < nvec; i += 4 * 1024) {  // four 16-byte loads in flight per thread (one CTA per SM: 64 KB in flight)
-        const uint4 v0 = ld_stream_u4(pv + 4 * i), v1 = ld_stream_u4(pv + 4 * (i + 1024));
-        const uint4 v2 = ld_stream_u4(pv + 4 * (i + 2048)), v3 = ld_stream_u4(pv + 4 * (i + 3072));
-        one(v0.x);
-        one(v0.y);
-        one(v0.z);
-        one(v0.w);
-        one(v1.x);
-        one(v1.y);
-        one(v1.z);
-        one(v1.w);
-        one(v2.x);
-        one(v2.y);
-        one(v2.z);
-        one(v2.w);
-        one(v3.x);
-        one(v3.y);
-        one(v3.z);
-        one(v3.w);
+    if (IN_FLOAT) {
+        auto one = [&](uint32_t v) { atomicAdd(&kh_bins[kh_key(v, km) & lmask], 1u); };
+        // head up to the first 16-byte boundary, vector body, tail
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(in_raw) + beg;
+        unsigned long long head = ((16u - (unsigned)(reinterpret_cast<uintptr_t>(p) & 15u)) & 15u) >> 2;
+        if (head > cnt) head = cnt;
+        if (threadIdx.x < head) one(p[threadIdx.x]);
+        const unsigned long long nvec = (cnt - head) >> 2;
+        const uint32_t *pv = p + head;
+        for (unsigned long long i = threadIdx.x; i < nvec; i += 1024) {
+            const uint4 v = ld_stream_u4(pv + 4 * i);
+            one(v.x);
+            one(v.y);
+            one(v.z);
+            one(v.w);
+        }
+        for (unsigned long long j = head + (nvec << 2) + threadIdx.x; j < cnt; j += 1024) one(p[j]);
+    } else {
+        auto one = [&](uint32_t v) { atomicAdd(&kh_bins[v & lmask], 1u); };
+        auto two = [&](uint32_t w) {
+            one(w & 0xffffu);
+            one(w >> 16);
+        };
+        // eight 16-bit keys per 128-bit load: head up to the first 16-byte boundary, vector body, tail
+        const uint16_t *p = reinterpret_cast<const uint16_t *>(in_raw) + beg;
+        unsigned long long head = ((16u - (unsigned)(reinterpret_cast<uintptr_t>(p) & 15u)) & 15u) >> 1;
+        if (head > cnt) head = cnt;
+        if (threadIdx.x < head) one(p[threadIdx.x]);
+        const unsigned long long nvec = (cnt - head) >> 3;
+        const uint32_t *pv = reinterpret_cast<const uint32_t *>(p + head);
+        unsigned long long i = threadIdx.x;
+        for (; i + 1024 < nvec; i += 2 * 1024) {  // two 16-byte loads in flight per thread
+            const uint4 v0 = ld_stream_u4(pv + 4 * i), v1 = ld_stream_u4(pv + 4 * (i + 1024));
+            two(v0.x);
+            two(v0.y);
+            two(v0.z);
+            two(v0.w);
+            two(v1.x);
+            two(v1.y);
+            two(v1.z);
+            two(v1.w);
+        }
+        for (; i < nvec; i += 1024) {
+            const uint4 v = ld_stream_u4(pv + 4 * i);
+            two(v.x);
+            two(v.y);
+            two(v.z);
+            two(v.w);
+        }
+        for (unsigned long long j = head + (nvec << 3) + threadIdx.x; j < cnt; j += 1024) one(p[j]);
     }
-    for (; i < nvec; i += 1024) {
-        const uint4 v = ld_stream_u4(pv + 4 * i);
-        one(v.x);
-        one(v.y);
-        one(v.z);
-        one(v.w);
-    }
-    for (unsigned long long j = head + (nvec << 2) + threadIdx.x; j < cnt; j += 1024) one(p[j]);
     __syncthreads();
     uint32_t *Hb = H + ((size_t)b << KH_LOW);
     if (items_b == 1) {
@@ -397,41 +405,46 @@ __global__ void __launch_bounds__(KH_HT) kh_tilecount_kernel(const uint32_t *__r
     }
 }
 
-// one CTA per 1024-bin tile, four bins per thread
+// 1024-bin tiles, four bins per thread; a CTA walks tiles with a grid stride (65 536 one-tile CTAs cost more in block
+// scheduling than in memory traffic)
 __global__ void __launch_bounds__(KH_HT / 4) kh_compact_kernel(const uint32_t *__restrict__ H, const uint32_t *__restrict__ tnz,
-                                                               const unsigned long long *__restrict__ toff, KhKeyMap km,
+                                                               const unsigned long long *__restrict__ toff, long long n_htiles, KhKeyMap km,
                                                                float *__restrict__ val, uint32_t *__restrict__ cnt) {
-    __shared__ int s_warp[KH_HT / 128];
-    if (tnz[blockIdx.x] == 0) return;
-    const uint32_t key0 = blockIdx.x * KH_HT + threadIdx.x * 4;
-    const uint4 c = *reinterpret_cast<const uint4 *>(H + key0);
-    const int mine = (c.x != 0) + (c.y != 0) + (c.z != 0) + (c.w != 0);
-    int incl = mine;
+    __shared__ int s_warp[2][KH_HT / 128];
+    int par = 0;
+    for (long long tile = blockIdx.x; tile < n_htiles; tile += gridDim.x) {
+        if (tnz[tile] == 0) continue;  // uniform over the CTA
+        const uint32_t key0 = (uint32_t)tile * KH_HT + threadIdx.x * 4;
+        const uint4 c = ld_stream_u4(H + key0);
+        const int mine = (c.x != 0) + (c.y != 0) + (c.z != 0) + (c.w != 0);
+        int incl = mine;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane_id() >= o) incl += t;
-    }
-    if (lane_id() == 31) s_warp[warp_id()] = incl;
-    __syncthreads();
-    int before = incl - mine;
-    for (int w = 0; w < warp_id(); ++w) before += s_warp[w];
-    unsigned long long at = toff[blockIdx.x] + (unsigned long long)before;
-    if (c.x) {
-        val[at] = __uint_as_float(kh_unkey(key0, km));
-        cnt[at++] = c.x;
-    }
-    if (c.y) {
-        val[at] = __uint_as_float(kh_unkey(key0 + 1, km));
-        cnt[at++] = c.y;
-    }
-    if (c.z) {
-        val[at] = __uint_as_float(kh_unkey(key0 + 2, km));
-        cnt[at++] = c.z;
-    }
-    if (c.w) {
-        val[at] = __uint_as_float(kh_unkey(key0 + 3, km));
-        cnt[at++] = c.w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane_id() >= o) incl += t;
+        }
+        if (lane_id() == 31) s_warp[par][warp_id()] = incl;
+        __syncthreads();
+        int before = incl - mine;
+        for (int w = 0; w < warp_id(); ++w) before += s_warp[par][w];
+        par ^= 1;  // the next tile writes the other copy: no second barrier needed
+        unsigned long long at = toff[tile] + (unsigned long long)before;
+        if (c.x) {
+            val[at] = __uint_as_float(kh_unkey(key0, km));
+            cnt[at++] = c.x;
+        }
+        if (c.y) {
+            val[at] = __uint_as_float(kh_unkey(key0 + 1, km));
+            cnt[at++] = c.y;
+        }
+        if (c.z) {
+            val[at] = __uint_as_float(kh_unkey(key0 + 2, km));
+            cnt[at++] = c.z;
+        }
+        if (c.w) {
+            val[at] = __uint_as_float(kh_unkey(key0 + 3, km));
+            cnt[at++] = c.w;
+        }
     }
 }
 
@@ -464,13 +477,16 @@ SortedRuns hist_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n, uint32
     const size_t n_bins = (size_t)1 << keybits;
     func_dyn_smem(ctx, (const void *)kh_hist_kernel<true>, KH_BINS * 4);
     func_dyn_smem(ctx, (const void *)kh_hist_kernel<false>, KH_BINS * 4);
-    func_dyn_smem(ctx, (const void *)kh_scatter_kernel, KH_TILE * 8 + (1 << KH_MAX_HB) * 20);
+    func_dyn_smem(ctx, (const void *)kh_scatter_kernel<2, 512>, KH_TILE * 4 + (1 << KH_MAX_HB) * 20);
+    func_dyn_smem(ctx, (const void *)kh_scatter_kernel<3, 512>, KH_TILE * 4 + (1 << KH_MAX_HB) * 20);
+    func_dyn_smem(ctx, (const void *)kh_scatter_kernel<2, 1024>, KH_TILE * 4 + (1 << KH_MAX_HB) * 20);
     uint32_t *H = arena_alloc_t<uint32_t>(ctx, std::max<size_t>(n_bins, KH_HT));
     if (hb == 0) NNC_CUDA(cudaMemsetAsync(H, 0, sizeof(uint32_t) * std::max<size_t>(n_bins, KH_HT), ctx->stream));
     unsigned long long *bucket_off = arena_alloc_t<unsigned long long>(ctx, (size_t)nb + 1);
     uint32_t *item_off = arena_alloc_t<uint32_t>(ctx, (size_t)nb + 1);
     const uint32_t *a = reinterpret_cast<const uint32_t *>(d_a);
     uint32_t *b = reinterpret_cast<uint32_t *>(d_b);
+    uint16_t *b16 = reinterpret_cast<uint16_t *>(d_b);  // the partition pass's output: low digits
     const int max_items = (int)std::min<int64_t>(n / KH_CHUNK + nb, (int64_t)1 << 30);
     const long long n_htiles = (long long)(std::max<size_t>(n_bins, KH_HT) / KH_HT);
     const int tiles_per_bucket = (int)(n_htiles / nb);  // 32 with a partition pass, max(low_bins, 1024) / 1024 without
@@ -478,7 +494,9 @@ SortedRuns hist_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n, uint32
     NNC_CUDA(cudaMemsetAsync(tnz, 0, sizeof(uint32_t) * ((size_t)n_htiles + 1), ctx->stream));
     if (hb > 0) {
         const int64_t n_tiles = (n + KH_TILE - 1) / KH_TILE;
-        const int64_t want_chunks = std::min<int64_t>(1024, (int64_t)ctx->sm_count * 2);
+        const char *occ_env = getenv("NNC_SCATTER_CTAS");
+        const int scatter_ctas = (occ_env && atoi(occ_env) == 3) ? 3 : 2;  // resident scatter CTAs per SM: one chunk each
+        const int64_t want_chunks = std::min<int64_t>(1024, (int64_t)ctx->sm_count * scatter_ctas);
         const int64_t tiles_per_chunk = (n_tiles + want_chunks - 1) / want_chunks;
         const int chunks = (int)((n_tiles + tiles_per_chunk - 1) / tiles_per_chunk);
         uint32_t *chunk_hist = arena_alloc_t<uint32_t>(ctx, (size_t)chunks * nb);
@@ -488,23 +506,32 @@ SortedRuns hist_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n, uint32
         NNC_LAUNCH(ctx, kh_count_kernel, chunks, KH_THREADS, nb * 4, a, n, tiles_per_chunk, nb, km, chunk_hist);
         NNC_LAUNCH(ctx, kh_crel_kernel, (nb + 127) / 128, 128, 0, chunk_hist, chunks, nb, crel_lo, crel_hi, tot);
         NNC_LAUNCH(ctx, kh_base_kernel, 1, 1024, 0, tot, nb, bucket_off, item_off);
-        NNC_LAUNCH(ctx, kh_scatter_kernel, chunks, KH_THREADS, KH_TILE * 8 + nb * 20, a, b, n, tiles_per_chunk, nb, km, bucket_off,
-                   crel_lo, crel_hi);
+        // two CTAs per SM (64 registers) by default; three (42 registers: spills) measured slower, NNC_SCATTER_CTAS=3 selects it
+        const char *thr_env = getenv("NNC_SCATTER_THREADS");
+        if (thr_env && atoi(thr_env) == 1024)  // 2 CTAs x 1024 threads x 8 keys: 32 registers, full occupancy
+            NNC_LAUNCH_AS(ctx, "kh_scatter_kernel", (kh_scatter_kernel<2, 1024>), chunks, 1024, KH_TILE * 4 + nb * 20, a, b16, n, tiles_per_chunk,
+                          nb, km, bucket_off, crel_lo, crel_hi);
+        else if (scatter_ctas == 2)
+            NNC_LAUNCH_AS(ctx, "kh_scatter_kernel", (kh_scatter_kernel<2, 512>), chunks, 512, KH_TILE * 4 + nb * 20, a, b16, n, tiles_per_chunk, nb,
+                          km, bucket_off, crel_lo, crel_hi);
+        else
+            NNC_LAUNCH_AS(ctx, "kh_scatter_kernel", (kh_scatter_kernel<3, 512>), chunks, 512, KH_TILE * 4 + nb * 20, a, b16, n, tiles_per_chunk, nb,
+                          km, bucket_off, crel_lo, crel_hi);
         NNC_LAUNCH(ctx, kh_zero_kernel, nb, 1024, 0, H, item_off);
-        NNC_LAUNCH(ctx, kh_hist_kernel<false>, max_items, 1024, low_bins * 4, b, nb, low_bins, km, bucket_off, item_off, H, tnz);
+        NNC_LAUNCH(ctx, kh_hist_kernel<false>, max_items, 1024, low_bins * 4, (const void *)b16, nb, low_bins, km, bucket_off, item_off, H, tnz);
     } else {
         const unsigned long long h_off[2] = {0ull, (unsigned long long)n};
         const uint32_t h_items[2] = {0u, (uint32_t)((n + KH_CHUNK - 1) / KH_CHUNK)};
         NNC_CUDA(cudaMemcpyAsync(bucket_off, h_off, sizeof(h_off), cudaMemcpyHostToDevice, ctx->stream));
         NNC_CUDA(cudaMemcpyAsync(item_off, h_items, sizeof(h_items), cudaMemcpyHostToDevice, ctx->stream));
         NNC_CUDA(cudaStreamSynchronize(ctx->stream));  // the two host arrays are on this frame
-        NNC_LAUNCH(ctx, kh_hist_kernel<true>, (int)h_items[1], 1024, low_bins * 4, a, 1, low_bins, km, bucket_off, item_off, H, tnz);
+        NNC_LAUNCH(ctx, kh_hist_kernel<true>, (int)h_items[1], 1024, low_bins * 4, (const void *)a, 1, low_bins, km, bucket_off, item_off, H, tnz);
     }
     // non-empty bins -> entries; the survivor buffers are dead from here on and take the entries
     unsigned long long *toff = arena_alloc_t<unsigned long long>(ctx, (size_t)n_htiles + 2);
     NNC_LAUNCH(ctx, kh_tilecount_kernel, nb, KH_HT, 0, H, item_off, tiles_per_bucket, tnz);
     exclusive_scan_u32_u64(ctx, tnz, n_htiles, toff);
-    NNC_LAUNCH(ctx, kh_compact_kernel, (int)n_htiles, KH_HT / 4, 0, H, tnz, toff, km, d_a, b);
+    NNC_LAUNCH(ctx, kh_compact_kernel, (int)std::min<long long>(n_htiles, (long long)ctx->sm_count * 32), KH_HT / 4, 0, H, tnz, toff, n_htiles, km, d_a, b);
     unsigned long long n_ent = 0;
     NNC_CUDA(cudaMemcpyAsync(&n_ent, toff + n_htiles, sizeof(n_ent), cudaMemcpyDeviceToHost, ctx->stream));
     NNC_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -33,39 +33,60 @@ namespace nnc {
 // prep: per-tile sums of q, samples, moments
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ll_tilesum_kernel(const float *__restrict__ ks, const unsigned int *__restrict__ cnt,
-                                                         long long n_ent, float mean, double scale, long long *tsum,
+                                                         long long n_ent, float mean, double scale, float scale_f, long long *tsum,
                                                          long long *tcnt, float *samp, LloydDevice *st) {
     const long long n_tiles = (n_ent + LL_TS - 1) / LL_TS;
-    const int wpb = blockDim.x >> 5;
+    const int wpb = blockDim.x >> 5, lane = lane_id();
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(ks) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(cnt) & 15u) == 0);
     long long s1 = 0;
     unsigned __int128 s2 = 0;  // sum of count * q^2 (q^2 < 2^61, count < 2^32)
     for (long long t = blockIdx.x * (long long)wpb + warp_id(); t < n_tiles; t += (long long)gridDim.x * wpb) {
-        long long base = t * LL_TS;
+        const long long base = t * LL_TS;
         long long acc = 0, cacc = 0;
-#pragma unroll 4
-        for (int j = 0; j < LL_TS / 32; ++j) {
-            long long i = base + j * 32 + lane_id();
-            if (i < n_ent) {
-                float x = ks[i];
-                const long long c = cnt ? (long long)cnt[i] : 1ll;
-                long long q = fixed_q(fsub(x, mean), scale);
-                acc += q * c;
-                cacc += c;
-                s2 += (unsigned __int128)(unsigned long long)(q * q) * (unsigned long long)c;
-                if (j == 0 && lane_id() == 0) samp[t] = x;
+        auto one = [&](float x, unsigned int cu) {
+            const long long c = (long long)cu;
+            const long long q = fixed_qf(fsub(x, mean), scale_f, scale);
+            acc += q * c;
+            cacc += c;
+            s2 += (unsigned __int128)(unsigned long long)(q * q) * (unsigned long long)c;
+        };
+        if (vec_ok && base + LL_TS <= n_ent) {  // a full tile: four 128-bit loads of values (and counts) in flight per lane
+            const float *pk = ks + base + 4 * lane;
+            const float4 a0 = ld_vol_f4(pk), a1 = ld_vol_f4(pk + 128), a2 = ld_vol_f4(pk + 256), a3 = ld_vol_f4(pk + 384);
+            uint4 c0 = make_uint4(1u, 1u, 1u, 1u), c1 = c0, c2 = c0, c3 = c0;
+            if (cnt) {
+                const unsigned int *pc = cnt + base + 4 * lane;
+                c0 = ld_vol_u4(pc);
+                c1 = ld_vol_u4(pc + 128);
+                c2 = ld_vol_u4(pc + 256);
+                c3 = ld_vol_u4(pc + 384);
+            }
+            if (lane == 0) samp[t] = a0.x;
+            one(a0.x, c0.x); one(a0.y, c0.y); one(a0.z, c0.z); one(a0.w, c0.w);
+            one(a1.x, c1.x); one(a1.y, c1.y); one(a1.z, c1.z); one(a1.w, c1.w);
+            one(a2.x, c2.x); one(a2.y, c2.y); one(a2.z, c2.z); one(a2.w, c2.w);
+            one(a3.x, c3.x); one(a3.y, c3.y); one(a3.z, c3.z); one(a3.w, c3.w);
+        } else {
+            for (int j = 0; j < LL_TS / 32; ++j) {
+                const long long i = base + j * 32 + lane;
+                if (i < n_ent) {
+                    const float x = ks[i];
+                    one(x, cnt ? cnt[i] : 1u);
+                    if (j == 0 && lane == 0) samp[t] = x;
+                }
             }
         }
         acc = warp_sum_ll(acc);
-        if (lane_id() == 0) tsum[t] = acc;
+        if (lane == 0) tsum[t] = acc;
         if (tcnt) {
             cacc = warp_sum_ll(cacc);
-            if (lane_id() == 0) tcnt[t] = cacc;
+            if (lane == 0) tcnt[t] = cacc;
         }
         s1 += acc;  // every lane holds the warp total; only lane 0 contributes below
     }
     unsigned long long s2lo = warp_sum_ull((unsigned long long)(s2 & 0x7fffffffull));
     unsigned long long s2hi = warp_sum_ull((unsigned long long)(s2 >> 31));
-    if (lane_id() == 0) {
+    if (lane == 0) {
         atomicAdd((unsigned long long *)&st->s1, (unsigned long long)s1);
         atomicAdd(&st->s2_lo, s2lo);
         atomicAdd(&st->s2_hi, s2hi);
@@ -963,7 +984,10 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
     NNC_CUDA(cudaMemcpyAsync(d_init, h_init, sizeof(float) * k, cudaMemcpyHostToDevice, ctx->stream));
     if (n_tiles > 0) {
         int grid = (int)std::min<long long>((long long)ctx->sm_count * 8, (n_tiles + 7) / 8);
-        NNC_LAUNCH(ctx, ll_tilesum_kernel, grid, 256, 0, h.d_sorted, h.d_cnt, n_ent, mean, scale, tsum, tcnt, samp, st);
+        const int sh = 30 - E;  // 2^(30-E) as a float when it is a normal one (fixed_qf), else the float64 scaling
+        float scale_f = 0.f;
+        if (sh >= -126 && sh <= 127) scale_f = ldexpf(1.0f, sh);
+        NNC_LAUNCH(ctx, ll_tilesum_kernel, grid, 256, 0, h.d_sorted, h.d_cnt, n_ent, mean, scale, scale_f, tsum, tcnt, samp, st);
     }
     exclusive_scan_i64(ctx, tsum, n_tiles, ptile);
     if (ctile) exclusive_scan_i64(ctx, tcnt, n_tiles, ctile);
@@ -1005,7 +1029,7 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         lloyd_fast_launch(ctx, st, h.d_sorted, samp, ptile, d_init, h_hist ? 1 : 0, pc);
         if (kt) klaunch_end(ctx);
         NNC_CUDA(cudaMemcpyAsync(&ctl, &st->iter, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
-        NNC_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (world > 1) NNC_CUDA(cudaStreamSynchronize(ctx->stream));  // one rank: the outcome is read with the results below (one sync)
         hist_done = h_hist != nullptr;
     } else if (one_launch) {
         func_dyn_smem(ctx, (const void *)ll_loop_kernel, sizeof(LoopSmem));
@@ -1047,8 +1071,11 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
             if (ctl.done || launched >= max_iter) break;
         }
     }
-    if (!fast && one_launch && ctl.gbail) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: the grid barrier of the loop kernel timed out (iter %d)", ctl.iter);
-    if (!ctl.done) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: loop ended without a stop decision (iter %d)", ctl.iter);
+    const bool deferred_ctl = fast && world == 1;  // ctl arrives with the final synchronize
+    if (!deferred_ctl) {
+        if (!fast && one_launch && ctl.gbail) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: the grid barrier of the loop kernel timed out (iter %d)", ctl.iter);
+        if (!ctl.done) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: loop ended without a stop decision (iter %d)", ctl.iter);
+    }
     if (world > 1 && ctx->peer_enabled) {
         int comm_error = 0;
         NNC_CUDA(cudaMemcpy(&comm_error, &st->comm_error, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1071,6 +1098,7 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         NNC_CUDA(cudaMemcpyAsync(h_hist, st->hist, sizeof(int64_t) * k, cudaMemcpyDeviceToHost, ctx->stream));
     }
     NNC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (deferred_ctl && !ctl.done) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: loop ended without a stop decision (iter %d)", ctl.iter);
     prof_mark(ctx, "lloyd_iters");
     if (getenv("NNC_LLOYD_LOG")) {
         const int cnt = std::min(ctl.n_iter, LL_LOG);

@@ -39,14 +39,26 @@ struct NpWarpScratch {
     float val[16];
 };
 
+struct PopState {  // relocation: the two cursors of every distinct index's member stream and the keys of their heads
+    long long pl[LF_KMAX], pr[LF_KMAX];
+    unsigned long long reml[LF_KMAX], remr[LF_KMAX];  // samples left in the entry under the left / right cursor
+    uint32_t kl[LF_KMAX][3], kr[LF_KMAX][3];          // FarKey (d2, gap, ordx) of the heads
+    int flags[LF_KMAX];                               // bit 0: left head valid, bit 1: right head valid
+};
+
 struct FastUpdate {  // scratch of the update step (CTA 0)
     long long Wd[LF_KMAX], Sd[LF_KMAX];       // per distinct index
     long long W[LF_KMAX], S[LF_KMAX];         // per cluster id
     long long first[LF_KMAX], last[LF_KMAX];  // member cursors per distinct index
     // two-candidate zones gathered from the chunk slots: what a distinct index gets as the LEFT candidate (a) of the zone to
     // its right and as the RIGHT candidate (b) of the zone to its left (a pair of candidates occurs in one region only)
-    long long aW[LF_KMAX], aS[LF_KMAX], af[LF_KMAX], al[LF_KMAX];
-    long long bW[LF_KMAX], bS[LF_KMAX], bf[LF_KMAX], bl[LF_KMAX];
+    union {  // the gather scratch is dead when relocation starts
+        struct {
+            long long aW[LF_KMAX], aS[LF_KMAX], af[LF_KMAX], al[LF_KMAX];
+            long long bW[LF_KMAX], bS[LF_KMAX], bf[LF_KMAX], bl[LF_KMAX];
+        };
+        PopState pop;
+    };
     float raw[LF_KMAX], cnew[LF_KMAX], sq[LF_KMAX];
     int empt[LF_KMAX];
     float far_x[LF_KMAX];
@@ -70,7 +82,21 @@ struct FastZone {
     long long rp[LF_R];  // copy of CTA 0's region positions
     int s_warp[32];
 };
+struct FastConst {  // read once from the LloydDevice header
+    int k, rank, world, max_iter;
+    long long n, n_nz, n0, n_ent;
+    const unsigned int *cnt;
+    unsigned long long *cand;
+    float mean, xabs_max;
+    double scale, inv_scale;  // 2^(30-E) and its (exact) reciprocal
+};
+
 struct FastSmem {
+    FastConst K;            // kernel-lifetime constants (same in every CTA)
+    SearchConst C;
+    long long hint[32][10]; // per warp and boundary slot: the tile found by the previous search (-1: none)
+    int merge_cur[64];      // relocation: read cursors of the ranks' candidate lists
+
     RegionTableT<LF_KMAX> tab;  // built redundantly by every CTA
     float c[LF_KMAX];           // centred centroids by cluster id
     int perm[LF_KMAX];          // sorted order of the previous table build
@@ -95,16 +121,10 @@ struct FastSmem {
     long long xbuf[2 * LF_KMAX];  // staging of the peer exchange
 };
 
+// (FastConst and SearchConst are placed in shared memory by the kernel: as kernel-lifetime registers they were spilled, and
+// with 214 KB of the SM's 256 KB configured as shared memory the spills miss the remaining L1 and go to L2)
 static_assert(sizeof(FastSmem) <= 227 * 1024, "FastSmem must fit the 227 KB of shared memory a CTA can opt into");
 
-struct FastConst {  // read once from the LloydDevice header
-    int k, rank, world, max_iter;
-    long long n, n_nz, n0, n_ent;
-    const unsigned int *cnt;
-    unsigned long long *cand;
-    float mean, xabs_max;
-    double scale, inv_scale;  // 2^(30-E) and its (exact) reciprocal
-};
 
 // NumPy's pairwise float32 sum (numpy/_core/src/umath/loops_utils.h.src) of a[0, n), n <= 1024, by ONE WARP: the leaves
 // (<= 128 elements: 8 strided accumulators, combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the n % 8 tail) are
@@ -548,153 +568,174 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
     if (n_empty > 0) {
         // Streams of candidates: for every distinct index its members walked from the left end and from the right end
         // (|x' - c| is V-shaped along a cluster's sorted members), plus the zero run.  The farthest remaining sample
-        // overall is always at the head of one of the streams; pop n_empty times.  Thread di owns both cursors of
-        // distinct index di; the owner of the zero run's cluster also owns the zero run (a third head).
-        long long pl = -1, pr = -2;  // empty stream when pl > pr
-        unsigned long long reml = 0, remr = 0;  // samples left in the entry under the left / right cursor
+        // overall is always at the head of one of the streams; pop n_empty times.
+        // The heads are set up by all threads (one stream each, loads in parallel); the pops themselves are a serial
+        // chain and run in ONE warp out of shared memory -- lane l owns the streams l, l + 32, ... and keeps the best of
+        // them in registers; a pop is a warp arg-max (shuffles), the winner's lane advances that stream and rescans its
+        // own streams.  No block barrier inside the chain (with one barrier pair per pop a pop cost 4 us).
+        PopState &P = U.pop;
         const unsigned int *__restrict__ ecnt = K.cnt;
         auto cnt_at = [&](long long p) -> unsigned long long { return ecnt ? (unsigned long long)ecnt[p] : 1ull; };
-        float cown = 0.f;
-        FarKey kl{0, 0, 0}, kr{0, 0, 0};
-        float xl = 0.f, xr = 0.f;
-        bool has_l = false, has_r = false;
         if (tid < m) {
-            cown = T.dv[tid];
+            long long pl = -1, pr = -2;  // empty stream when pl > pr
+            unsigned long long reml = 0, remr = 0;
+            const float cown = T.dv[tid];
             if (U.last[tid] >= U.first[tid] && U.last[tid] >= 0) {
                 pl = U.first[tid];
                 pr = U.last[tid];
                 reml = cnt_at(pl);
                 remr = cnt_at(pr);
             }
-        }
-        auto refresh = [&]() {
-            has_l = has_r = false;
-            if (tid < m && pl <= pr) {
-                xl = fsub(ks[pl], mean);
-                kl = far_key(xl, cown);
-                has_l = true;
+            int flags = 0;
+            if (pl <= pr) {
+                const FarKey kl = far_key(fsub(ks[pl], mean), cown);
+                P.kl[tid][0] = kl.d2, P.kl[tid][1] = kl.gap, P.kl[tid][2] = kl.ordx;
+                flags |= 1;
                 if (pr > pl) {
-                    xr = fsub(ks[pr], mean);
-                    kr = far_key(xr, cown);
-                    has_r = true;
+                    const FarKey kr = far_key(fsub(ks[pr], mean), cown);
+                    P.kr[tid][0] = kr.d2, P.kr[tid][1] = kr.gap, P.kr[tid][2] = kr.ordx;
+                    flags |= 2;
                 }
             }
-        };
-        refresh();
-        if (tid == 0) U.zero_left = K.n0;
+            P.pl[tid] = pl;
+            P.pr[tid] = pr;
+            P.reml[tid] = reml;
+            P.remr[tid] = remr;
+            P.flags[tid] = flags;
+        }
+        if (tid == 0) {
+            U.zero_left = K.n0;
+            U.winner = 0;  // pops done
+        }
         __syncthreads();
-        const FarKey kz = far_key(x0, U.zdi >= 0 ? T.dv[U.zdi] : 0.f);
         unsigned long long *my_cand = K.cand + (size_t)K.rank * k * 2;
-        const int nw = (m + 31) >> 5;  // warps that own streams
-        int n_done = 0;
-        for (int pop = 0; pop < n_empty; ++pop) {
+        if (warp_id() == 0) {
+            const int lane = lane_id();
+            const int zdi = U.zdi;
+            const FarKey kz = far_key(x0, zdi >= 0 ? T.dv[zdi] : 0.f);
+            long long zero_left = K.n0;  // kept by every lane (uniform)
+            // best head among the streams of this lane: (key, stream, which head: 0 left, 1 right, 2 zero run)
             FarKey best{0, 0, 0};
-            int who = -1;  // best head of this thread: 0 = left, 1 = right, 2 = zero run
-            if (has_l) {
-                best = kl;
-                who = 0;
-            }
-            if (has_r && (who < 0 || far_before(kr, best))) {
-                best = kr;
-                who = 1;
-            }
-            if (tid == U.zdi && U.zero_left > 0 && (who < 0 || far_before(kz, best))) {
-                best = kz;
-                who = 2;
-            }
-            int owner = who >= 0 ? tid : -1;
-            if (warp_id() < nw) {
+            int bi = -1, bwho = -1;
+            auto rescan = [&]() {
+                best = FarKey{0, 0, 0};
+                bi = -1;
+                bwho = -1;
+                for (int i = lane; i < m; i += 32) {
+                    const int fl = P.flags[i];
+                    if (fl & 1) {
+                        const FarKey kl{P.kl[i][0], P.kl[i][1], P.kl[i][2]};
+                        if (bi < 0 || far_before(kl, best)) {
+                            best = kl;
+                            bi = i;
+                            bwho = 0;
+                        }
+                    }
+                    if (fl & 2) {
+                        const FarKey kr{P.kr[i][0], P.kr[i][1], P.kr[i][2]};
+                        if (bi < 0 || far_before(kr, best)) {
+                            best = kr;
+                            bi = i;
+                            bwho = 1;
+                        }
+                    }
+                    if (i == zdi && zero_left > 0 && (bi < 0 || far_before(kz, best))) {
+                        best = kz;
+                        bi = i;
+                        bwho = 2;
+                    }
+                }
+            };
+            rescan();
+            int n_done = 0;
+            for (int pop = 0; pop < n_empty; ++pop) {
+                FarKey wk = best;
+                int wi = bi, ww = bwho;
+#pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     FarKey ob;
-                    ob.d2 = __shfl_xor_sync(0xffffffffu, best.d2, o);
-                    ob.gap = __shfl_xor_sync(0xffffffffu, best.gap, o);
-                    ob.ordx = __shfl_xor_sync(0xffffffffu, best.ordx, o);
-                    const int oo = __shfl_xor_sync(0xffffffffu, owner, o);
-                    if (oo >= 0 && (owner < 0 || far_before(ob, best) || (!far_before(best, ob) && oo < owner))) {
-                        best = ob;
-                        owner = oo;
+                    ob.d2 = __shfl_xor_sync(0xffffffffu, wk.d2, o);
+                    ob.gap = __shfl_xor_sync(0xffffffffu, wk.gap, o);
+                    ob.ordx = __shfl_xor_sync(0xffffffffu, wk.ordx, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, wi, o), ow = __shfl_xor_sync(0xffffffffu, ww, o);
+                    // farther key wins; equal keys: the lower stream, then the lower head (left, right, zero run)
+                    if (oi >= 0 && (wi < 0 || far_before(ob, wk) || (!far_before(wk, ob) && (oi < wi || (oi == wi && ow < ww))))) {
+                        wk = ob;
+                        wi = oi;
+                        ww = ow;
                     }
                 }
-                if (lane_id() == 0) {
-                    U.rk_d2[warp_id()] = best.d2;
-                    U.rk_gap[warp_id()] = best.gap;
-                    U.rk_ord[warp_id()] = best.ordx;
-                    U.rk_who[warp_id()] = owner;
-                }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                for (int w = 1; w < nw; ++w) {
-                    const FarKey ob{U.rk_d2[w], U.rk_gap[w], U.rk_ord[w]};
-                    const int oo = U.rk_who[w];
-                    if (oo >= 0 && (owner < 0 || far_before(ob, best) || (!far_before(best, ob) && oo < owner))) {
-                        best = ob;
-                        owner = oo;
-                    }
-                }
-                U.winner = owner;
-            }
-            __syncthreads();
-            if (U.winner < 0) break;  // this rank has no sample left
-            if (tid == U.winner) {
-                // candidate = (dist^2, ulp gap | x', old cluster id + 1): the local list comes out in descending order
-                const FarKey kk = who == 0 ? kl : (who == 1 ? kr : kz);
-                const int old_id = who == 2 ? T.down[U.zdi] : T.down[tid];
-                my_cand[2 * pop] = ((unsigned long long)kk.d2 << 32) | kk.gap;
-                my_cand[2 * pop + 1] = ((unsigned long long)kk.ordx << 32) | (unsigned)(old_id + 1);
-                if (who == 2) {
-                    U.zero_left -= 1;
-                } else if (who == 0) {
-                    if (reml > 1) {
-                        reml -= 1;
-                    } else {
-                        // next member from the left: value and count of a candidate position are loaded together (one
-                        // round trip), the label check uses the loaded value
-                        float x = 0.f;
-                        unsigned long long c = 1ull;
-                        do {
-                            ++pl;
-                            if (pl > pr) break;
-                            x = ks[pl];
-                            c = cnt_at(pl);
-                        } while (fast_label_of(S, mean, pl, x) != tid);
-                        has_l = false;
-                        if (pl <= pr) {
-                            reml = pl == pr ? remr : c;
-                            xl = fsub(x, mean);
-                            kl = far_key(xl, cown);
-                            has_l = true;
+                if (wi < 0) break;  // this rank has no sample left
+                if (ww == 2) zero_left -= 1;
+                if (lane == (wi & 31)) {
+                    const int i = wi;
+                    // candidate = (dist^2, ulp gap | x', old cluster id + 1): the local list comes out in descending order
+                    my_cand[2 * pop] = ((unsigned long long)wk.d2 << 32) | wk.gap;
+                    my_cand[2 * pop + 1] = ((unsigned long long)wk.ordx << 32) | (unsigned)(T.down[i] + 1);
+                    if (ww == 0) {
+                        if (P.reml[i] > 1) {
+                            P.reml[i] -= 1;
+                        } else {
+                            // next member from the left: value and count of a candidate position are loaded together
+                            // (one round trip), the label check uses the loaded value
+                            long long pl = P.pl[i];
+                            const long long pr = P.pr[i];
+                            float x = 0.f;
+                            unsigned long long c = 1ull;
+                            do {
+                                ++pl;
+                                if (pl > pr) break;
+                                x = ks[pl];
+                                c = cnt_at(pl);
+                            } while (fast_label_of(S, mean, pl, x) != i);
+                            int fl = P.flags[i] & ~1;
+                            if (pl <= pr) {
+                                P.reml[i] = pl == pr ? P.remr[i] : c;
+                                const FarKey kl = far_key(fsub(x, mean), T.dv[i]);
+                                P.kl[i][0] = kl.d2, P.kl[i][1] = kl.gap, P.kl[i][2] = kl.ordx;
+                                fl |= 1;
+                            }
+                            if (pl >= pr) fl &= ~2;  // the cursors met: the left one owns what is left
+                            P.pl[i] = pl;
+                            P.flags[i] = fl;
                         }
-                        if (pl >= pr) has_r = false;  // the cursors met: the left one owns what is left
-                    }
-                } else {
-                    if (remr > 1) {
-                        remr -= 1;
-                    } else {
-                        float x = 0.f;
-                        unsigned long long c = 1ull;
-                        do {
-                            --pr;
-                            if (pr < pl) break;
-                            x = ks[pr];
-                            c = cnt_at(pr);
-                        } while (fast_label_of(S, mean, pr, x) != tid);
-                        has_r = false;
-                        if (pr > pl) {
-                            remr = c;
-                            xr = fsub(x, mean);
-                            kr = far_key(xr, cown);
-                            has_r = true;
-                        } else if (pr < pl) {
-                            has_l = false;
+                    } else if (ww == 1) {
+                        if (P.remr[i] > 1) {
+                            P.remr[i] -= 1;
+                        } else {
+                            const long long pl = P.pl[i];
+                            long long pr = P.pr[i];
+                            float x = 0.f;
+                            unsigned long long c = 1ull;
+                            do {
+                                --pr;
+                                if (pr < pl) break;
+                                x = ks[pr];
+                                c = cnt_at(pr);
+                            } while (fast_label_of(S, mean, pr, x) != i);
+                            int fl = P.flags[i] & ~2;
+                            if (pr > pl) {
+                                P.remr[i] = c;
+                                const FarKey kr = far_key(fsub(x, mean), T.dv[i]);
+                                P.kr[i][0] = kr.d2, P.kr[i][1] = kr.gap, P.kr[i][2] = kr.ordx;
+                                fl |= 2;
+                            } else if (pr < pl) {
+                                fl &= ~1;
+                            }
+                            P.pr[i] = pr;
+                            P.flags[i] = fl;
                         }
                     }
                 }
+                __syncwarp();
+                if (lane == (wi & 31)) rescan();  // only this lane's streams (and its view of the zero run) changed
+                else if (ww == 2 && lane == (zdi & 31)) rescan();
+                n_done = pop + 1;
             }
-            n_done = pop + 1;
-            __syncthreads();
+            if (lane == 0) U.winner = n_done;
         }
         __syncthreads();
+        const int n_done = U.winner;
         // unused slots of this rank, and (before the all-gather) every slot of the other ranks, hold zeros
         for (int i = tid; i < K.world * k; i += NT) {
             const int r = i / k, j = i - r * k;
@@ -719,7 +760,7 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
         __syncthreads();
         if (tid == 0) {
             const int world = K.world;
-            int cur[64];
+            int *cur = S.merge_cur;
             for (int r = 0; r < world; ++r) cur[r] = 0;
             int n_moved = 0;
             bool skip = false;
@@ -859,29 +900,39 @@ __global__ void __launch_bounds__(THREADS, 1)
     const int NW = n_cta * (NT / 32);                  // warps of the cluster
     const int gw = (int)cta * (NT / 32) + warp_id();  // warp index inside the cluster
 
-    FastConst K;
-    K.k = st->k;
-    K.rank = st->rank;
-    K.world = st->world;
-    K.max_iter = st->max_iter;
-    K.n = st->n;
-    K.n_nz = st->n_nz;
-    K.n0 = st->n0;
-    K.n_ent = st->n_ent;
-    K.cnt = st->cnt;
-    K.cand = st->cand;
-    K.mean = st->mean;
-    K.xabs_max = st->xabs_max;
-    K.scale = st->scale;
-    K.inv_scale = __ddiv_rn(1.0, K.scale);
-    const int k = K.k;
-    SearchConst C = search_const(st, ks, samp, ptile);
-    if (C.n_tiles > 64) {  // top level of the tile-sample index in shared memory (the samples never change)
-        C.top_step = (C.n_tiles + LL_TOP - 1) / LL_TOP;
-        C.top_n = (int)((C.n_tiles + C.top_step - 1) / C.top_step);
-        for (int i = tid; i < C.top_n; i += NT) S.top[i] = samp[(long long)i * C.top_step];
-        C.top = S.top;
+    // kernel-lifetime constants: built by thread 0 in shared memory, read from there (see FastSmem)
+    if (tid == 0) {
+        FastConst Kc;
+        Kc.k = st->k;
+        Kc.rank = st->rank;
+        Kc.world = st->world;
+        Kc.max_iter = st->max_iter;
+        Kc.n = st->n;
+        Kc.n_nz = st->n_nz;
+        Kc.n0 = st->n0;
+        Kc.n_ent = st->n_ent;
+        Kc.cnt = st->cnt;
+        Kc.cand = st->cand;
+        Kc.mean = st->mean;
+        Kc.xabs_max = st->xabs_max;
+        Kc.scale = st->scale;
+        Kc.inv_scale = __ddiv_rn(1.0, Kc.scale);
+        S.K = Kc;
+        SearchConst Cc = search_const(st, ks, samp, ptile);
+        if (Cc.n_tiles > 64) {  // top level of the tile-sample index in shared memory (the samples never change)
+            Cc.top_step = (Cc.n_tiles + LL_TOP - 1) / LL_TOP;
+            Cc.top_n = (int)((Cc.n_tiles + Cc.top_step - 1) / Cc.top_step);
+            Cc.top = S.top;
+        }
+        S.C = Cc;
     }
+    for (int i = tid; i < 32 * 10; i += NT) (&S.hint[0][0])[i] = -1;
+    __syncthreads();
+    const FastConst &K = S.K;
+    const SearchConst &C = S.C;
+    const int k = K.k;
+    if (C.top)
+        for (int i = tid; i < C.top_n; i += NT) S.top[i] = samp[(long long)i * C.top_step];
     const long long total_q = C.n_tiles > 0 ? ptile[C.n_tiles] : 0ll;
     unsigned long long xseq = (pc.enabled && cta == 0) ? *peer_counter(pc) : 0ull;
     // ---- init: centre the initial centroids; tolerance from the exact integer moments of all n samples
@@ -939,9 +990,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     };
     const bool logger = want_log && cta == 0 && tid == 0;
 
-    long long hint[10];  // tile found last time for each boundary slot of this warp (<= 1022 boundaries over >= 128 warps)
-#pragma unroll
-    for (int i = 0; i < 10; ++i) hint[i] = -1;
+    long long *hint = S.hint[warp_id()];  // tile found last time for each boundary slot of this warp (<= 1022 boundaries over >= 128 warps)
 
     cluster.sync();  // every CTA's shared state is initialised before anybody writes into CTA 0's
     // One loop body for the Lloyd iterations AND the closing histogram round (one more E-step against c_emit, counts only):

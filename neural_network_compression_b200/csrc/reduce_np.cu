@@ -1229,11 +1229,21 @@ static NpTileDesc *run_tree(nnc_ctx *ctx, const float *d_w, V v, const FinArgs &
     NpPlan p = np_plan(n);
     float *partials = arena_alloc_t<float>(ctx, 2 * (size_t)p.num_tiles + 2);
     NpTileDesc *desc = static_cast<NpTileDesc *>(ctx->desc_ptr);
-    if (ctx->desc_n != n || !desc) {  // the descriptors only depend on n: built once per call
-        desc = arena_alloc_t<NpTileDesc>(ctx, p.num_tiles);
+    if (ctx->desc_n != n || !desc) {  // the descriptors only depend on n: built once, kept for the following calls
+        const size_t need = sizeof(NpTileDesc) * (size_t)p.num_tiles;
+        if (need > ctx->desc_bytes) {
+            if (ctx->desc_ptr) {
+                NNC_CUDA(cudaStreamSynchronize(ctx->stream));
+                cudaFree(ctx->desc_ptr);
+                ctx->desc_ptr = nullptr;
+                ctx->desc_bytes = 0;
+            }
+            NNC_CUDA(cudaMalloc(&ctx->desc_ptr, need));
+            ctx->desc_bytes = need;
+        }
+        desc = static_cast<NpTileDesc *>(ctx->desc_ptr);
         NNC_LAUNCH(ctx, np_tiles_kernel, (p.num_tiles + 127) / 128, 128, 0, n, p.depth, desc);
         ctx->desc_n = n;
-        ctx->desc_ptr = desc;
     }
     if (ctx->world > 1) NNC_CUDA(cudaMemsetAsync(partials, 0, sizeof(float) * (2 * (size_t)p.num_tiles + 2), ctx->stream));
     const uint32_t t0 = ctx->sh.t0, t1 = ctx->sh.t1;
