@@ -311,6 +311,8 @@ def run_b200(args):
     ctx = N.default_context(local)
     if world > 1:
         U.init_distributed(device=local)
+    if world > 1:
+        ctx.hint_global_size(args.n)  # every rank knows the layer's size: no all-reduce + host round trip per call to agree on it
     lo, hi = U.shard_range(args.n, rank, world)  # contiguous slice of the flattened layer owned by this rank
     n_local = hi - lo
     K, W = args.steps, args.warmup

@@ -162,6 +162,11 @@ int nnc_grad_segsum_f32(nnc_ctx *ctx, const float *grad, const void *codes, int6
                         double *out);
 
 /* ---- multi-GPU (one process per GPU; contiguous shards of the flattened tensor) ------------ */
+/* Multi-GPU: tells the context the element count of the WHOLE tensor the next sharded calls work on (0: ask the ranks
+ * with an all-reduce at the start of every call, the default).  All ranks must give the same value.  Saves one
+ * all-reduce and one host round trip per call; the reference has no counterpart (single process). */
+int nnc_ctx_hint_global_n(nnc_ctx *ctx, int64_t n_global);
+
 /* The library does not own a communicator.  The host supplies an all-reduce callback that reduces
  * `count` int64 values (DEVICE buffer, in place; op 0 sum, 1 min, 2 max) across ranks on `stream`;
  * all exchanged quantities are integers, so the result is bit-identical for any rank count.

@@ -35,7 +35,7 @@ EXPORTS = [
     "nnc_kmeans1d_f32", "nnc_assign_f32", "nnc_unpack_gather_f32", "nnc_grad_segsum_f32", "nnc_ctx_set_comm",
     "nnc_ctx_set_kernel_timing", "nnc_last_kernel_times", "nnc_ctx_total_launches",
     "nnc_compress_f32", "nnc_shard_range", "nnc_comm_unique_id", "nnc_ctx_init_nccl",
-    "nnc_peer_mailbox_create", "nnc_peer_mailbox_connect", "nnc_pack_bits_u8",
+    "nnc_peer_mailbox_create", "nnc_peer_mailbox_connect", "nnc_pack_bits_u8", "nnc_ctx_hint_global_n",
 ]
 
 
@@ -140,6 +140,7 @@ def lib():
         L.nnc_unpack_gather_f32.argtypes = [vp, vp, i64, i32, vp, i32, vp]
         L.nnc_grad_segsum_f32.argtypes = [vp, vp, vp, i64, i32, i32, vp]
         L.nnc_pack_bits_u8.argtypes = [vp, vp, i64, vp]
+        L.nnc_ctx_hint_global_n.argtypes = [vp, i64]
         L.nnc_ctx_set_kernel_timing.argtypes = [vp, i32, C.c_char_p]
         L.nnc_last_kernel_times.argtypes = [vp, P(C.c_char_p)]
         L.nnc_ctx_total_launches.argtypes = [vp, P(i64)]
@@ -240,6 +241,10 @@ class Context:
         assert len(unique_id) == 128
         check(lib().nnc_ctx_init_nccl(self._h, unique_id, int(rank), int(world)))
         self.rank, self.world = int(rank), int(world)
+
+    def hint_global_size(self, n_global: int):
+        """Sharded calls: the element count of the whole tensor (same on every rank; 0 = ask the ranks in every call)."""
+        check(lib().nnc_ctx_hint_global_n(self._h, int(n_global)))
 
     def peer_mailbox_create(self, world: int) -> bytes:
         buf = C.create_string_buffer(64)

@@ -272,7 +272,16 @@ void comm_allreduce(nnc_ctx *ctx, int64_t *d_buf, int count, int op) {
 
 void read_scalars(nnc_ctx *ctx) {
     NNC_CUDA(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, ctx->stream));
+    int comm_error = 0;
+    if (ctx->d_comm_error) NNC_CUDA(cudaMemcpyAsync(&comm_error, ctx->d_comm_error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     NNC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (comm_error) {
+        // a rank did not arrive at an in-kernel exchange: the ranks' sequence counters may differ from here on, so the
+        // mailboxes are not used again by this context (the NCCL path takes over) until they are reconnected
+        ctx->peer_enabled = false;
+        cudaMemsetAsync(ctx->d_comm_error, 0, sizeof(int), ctx->stream);
+        NNC_FAIL(NNC_ERR_COMM, "a rank did not arrive at an in-kernel peer exchange (time-out); peer exchange disabled on this context");
+    }
 }
 
 // ---- host-side float32 helpers (every rounding explicit: host code is built with -ffp-contract=off) ----
@@ -328,12 +337,18 @@ static void shard_setup(nnc_ctx *ctx, int64_t n_local) {
         ctx->sh.t1 = n_local > 0 ? np_plan(n_local).num_tiles : 0;
         return;
     }
-    int64_t *d = arena_alloc_t<int64_t>(ctx, 1);
-    NNC_CUDA(cudaMemcpyAsync(d, &n_local, sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-    comm_allreduce(ctx, d, 1, 0);
     int64_t n_global = 0;
-    NNC_CUDA(cudaMemcpyAsync(&n_global, d, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    NNC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->hint_n_global > 0) {
+        // the caller told every rank the size of the whole tensor (nnc_ctx_hint_global_n): no all-reduce, no host round trip;
+        // a rank whose slice does not fit the shard map of that size fails below like without the hint
+        n_global = ctx->hint_n_global;
+    } else {
+        int64_t *d = arena_alloc_t<int64_t>(ctx, 1);
+        NNC_CUDA(cudaMemcpyAsync(d, &n_local, sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+        comm_allreduce(ctx, d, 1, 0);
+        NNC_CUDA(cudaMemcpyAsync(&n_global, d, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        NNC_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     int64_t b = 0, e = 0;
     uint32_t t0 = 0, t1 = 0;
     if (n_global <= 0) NNC_FAIL(NNC_ERR_BAD_ARG, "sharded call on an empty tensor");
@@ -415,6 +430,7 @@ void nnc_ctx_destroy(nnc_ctx *ctx) {
     for (void *p : ctx->overflow) cudaFree(p);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->desc_ptr) cudaFree(ctx->desc_ptr);
+    if (ctx->d_comm_error) cudaFree(ctx->d_comm_error);
     if (ctx->d_scal) cudaFree(ctx->d_scal);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
@@ -565,6 +581,13 @@ int nnc_peer_mailbox_connect(nnc_ctx *ctx, const char *handles, int rank, int wo
     }
     ctx->peer_enabled = true;
     ctx->peer_seq = 0;
+    NNC_CATCH
+}
+
+int nnc_ctx_hint_global_n(nnc_ctx *ctx, int64_t n_global) {
+    NNC_TRY
+    if (!ctx || n_global < 0) NNC_FAIL(NNC_ERR_BAD_ARG, "nnc_ctx_hint_global_n: bad argument");
+    ctx->hint_n_global = n_global;
     NNC_CATCH
 }
 

@@ -119,12 +119,14 @@ struct nnc_ctx {
         uint32_t t0 = 0, t1 = 0;
     } sh;
     int rank = 0, world = 1;
+    int64_t hint_n_global = 0;  // > 0: the sharded calls take this as the size of the whole tensor (nnc_ctx_hint_global_n)
     void *nccl_comm = nullptr;  // ncclComm_t when the library owns a communicator (nnc_ctx_init_nccl)
     // peer mailboxes for the in-kernel exchanges of the Lloyd loop (peer.cuh; nnc_peer_mailbox_create / _connect)
     bool peer_enabled = false;
     void *peer_local = nullptr;
     void *peer_mail[16] = {nullptr};
     unsigned long long peer_seq = 0;
+    int *d_comm_error = nullptr;  // set by an in-kernel exchange that timed out (reduce_np.cu: np_final_peer_kernel)
     nnc_allreduce_i64_fn allreduce = nullptr;
     void *allreduce_user = nullptr;
     // kernels whose dynamic shared-memory limit has been raised ON THIS CONTEXT'S DEVICE (the attribute is per device)

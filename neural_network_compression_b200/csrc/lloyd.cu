@@ -1077,9 +1077,12 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         if (!ctl.done) NNC_FAIL(NNC_ERR_INTERNAL, "k-means: loop ended without a stop decision (iter %d)", ctl.iter);
     }
     if (world > 1 && ctx->peer_enabled) {
-        int comm_error = 0;
-        NNC_CUDA(cudaMemcpy(&comm_error, &st->comm_error, sizeof(int), cudaMemcpyDeviceToHost));
-        if (comm_error) NNC_FAIL(NNC_ERR_COMM, "k-means: a rank did not arrive at an in-kernel peer exchange (time-out)");
+        int comm_error = fast ? ctl.pad : 0;  // the cluster kernel reports it with the loop's outcome
+        if (!fast) NNC_CUDA(cudaMemcpy(&comm_error, &st->comm_error, sizeof(int), cudaMemcpyDeviceToHost));
+        if (comm_error) {
+            ctx->peer_enabled = false;  // the ranks' exchange counters may differ now: no further in-kernel exchanges on this context
+            NNC_FAIL(NNC_ERR_COMM, "k-means: a rank did not arrive at an in-kernel peer exchange (time-out); peer exchange disabled on this context");
+        }
     }
     NNC_CUDA(cudaMemcpyAsync(h_centred_final, st->c, sizeof(float) * k, cudaMemcpyDeviceToHost, ctx->stream));
     NNC_CUDA(cudaMemcpyAsync(h_centred_emit, st->c_emit, sizeof(float) * k, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1093,7 +1096,7 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
             NNC_LAUNCH(ctx, ll_zone_kernel, zone_grid, 256, sizeof(ZoneSmem), st, h.d_sorted);
             NNC_LAUNCH(ctx, ll_count_kernel, 1, TB_THREADS, 0, st);
         }
-        comm_allreduce(ctx, reinterpret_cast<int64_t *>(st->hist), k, 0);
+        if (!(fast && peer)) comm_allreduce(ctx, reinterpret_cast<int64_t *>(st->hist), k, 0);  // (the cluster kernel summed it over the mailboxes)
         static_assert(sizeof(long long) == sizeof(int64_t), "histogram element size");
         NNC_CUDA(cudaMemcpyAsync(h_hist, st->hist, sizeof(int64_t) * k, cudaMemcpyDeviceToHost, ctx->stream));
     }

@@ -1075,7 +1075,16 @@ __global__ void __launch_bounds__(THREADS, 1)
                 __syncthreads();
                 if (tid == 0 && K.n0 > 0) Wd[zone_argmin(fsub(0.f, K.mean), T.dv, T.dcn, T.down, 0, m - 1)] += K.n0;
                 __syncthreads();
-                if (tid < m) st->hist[T.down[tid]] = Wd[tid];
+                if (pc.enabled) {  // code histogram of all ranks: exact counts summed over the mailboxes
+                    if (tid < k) S.xbuf[tid] = 0;
+                    __syncthreads();
+                    if (tid < m) S.xbuf[T.down[tid]] = Wd[tid];
+                    __syncthreads();
+                    if (!peer_allreduce_sum(pc, S.xbuf, k, ++xseq) && tid == 0) st->pad2 = 1;
+                    if (tid < k) st->hist[tid] = S.xbuf[tid];
+                } else if (tid < m) {
+                    st->hist[T.down[tid]] = Wd[tid];
+                }
             }
         }
         if (stamp) sl[5] = now();
@@ -1107,6 +1116,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 st->n_reloc = S.n_reloc;
                 st->n_iter = S.n_iter;
                 st->comm_error = S.comm_error;
+                st->pad2 = S.comm_error;  // travels with the loop's outcome (one read-back)
             }
         }
         if (!want_hist) break;

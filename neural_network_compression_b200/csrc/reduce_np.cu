@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "peer.cuh"
 #include "table.cuh"
 
 namespace nnc {
@@ -619,6 +620,39 @@ __device__ __forceinline__ float np_node_value(const float *tl, uint32_t gd, int
     return val;
 }
 
+// both trees of the fused pass from ONE read of the staged values (full leaves; other shapes take the two single passes)
+template <class F1, class F2>
+__device__ __forceinline__ void np_node_value2(const float *tl, uint32_t gd, int j, F1 f1, F2 f2, float &v1, float &v2) {
+    const int o = gd & 8191, s = (gd >> 13) & 255;
+    if (s == 128 && (o & 127) == 0) {
+        const int g = (threadIdx.x >> 3) & 3;
+        const float *p = tl + o + j - 8 * g;
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int st = 0; st < 19; ++st) {
+            const int i = st - g;
+            if (i >= 0 && i < 16) {
+                const float x = p[8 * st];
+                const float x1 = f1(x), x2 = f2(x);
+                a = i == 0 ? x1 : fadd(a, x1);
+                b = i == 0 ? x2 : fadd(b, x2);
+            }
+        }
+        const unsigned gmask = 0xffu << (threadIdx.x & 24);
+        a = fadd(a, __shfl_xor_sync(gmask, a, 1));
+        b = fadd(b, __shfl_xor_sync(gmask, b, 1));
+        a = fadd(a, __shfl_xor_sync(gmask, a, 2));
+        b = fadd(b, __shfl_xor_sync(gmask, b, 2));
+        a = fadd(a, __shfl_xor_sync(gmask, a, 4));
+        b = fadd(b, __shfl_xor_sync(gmask, b, 4));
+        v1 = a;
+        v2 = b;
+    } else {
+        v1 = np_node_value(tl, gd, j, f1);
+        v2 = np_node_value(tl, gd, j, f2);
+    }
+}
+
 // ---- bulk-asynchronous copy + mbarrier (PTX; SASS: UBLKCP / SYNCS) --------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
@@ -805,11 +839,16 @@ __global__ void __launch_bounds__(NP_THREADS, V::kSecondTree ? 3 : 4) np_tree_ke
         // ---- leaves: the 8 lanes of group `grp` sum the node described by gd, the terms computed from the staged values
         {
             const int h = (gd >> 21) & 63;
-            const float val = np_node_value(tl, gd, j, [&](float x) { return v.term(x); });
-            if (j == 0 && (gd >> 27)) heap_val[buf][h] = val;
             if constexpr (V::kSecondTree) {
-                const float val2 = np_node_value(tl, gd, j, [&](float x) { return v.term2(x); });
-                if (j == 0 && (gd >> 27)) heap_val2[buf][h] = val2;
+                float val, val2;
+                np_node_value2(tl, gd, j, [&](float x) { return v.term(x); }, [&](float x) { return v.term2(x); }, val, val2);
+                if (j == 0 && (gd >> 27)) {
+                    heap_val[buf][h] = val;
+                    heap_val2[buf][h] = val2;
+                }
+            } else {
+                const float val = np_node_value(tl, gd, j, [&](float x) { return v.term(x); });
+                if (j == 0 && (gd >> 27)) heap_val[buf][h] = val;
             }
         }
         if constexpr (V::kCompact && !V::kSecondTree) {
@@ -947,18 +986,8 @@ __global__ void __launch_bounds__(512) np_fold1024_kernel(const float *__restric
     if (threadIdx.x == 0) out[blockIdx.x] = s[0];
 }
 
-__global__ void __launch_bounds__(1024) np_final_kernel(float *partials, uint32_t count, DevScalars *sc, FinArgs fa) {
-    float *src = partials, *dst = partials + count;
-    for (uint32_t len = count; len > 1; len >>= 1) {
-        uint32_t half = len >> 1;
-        for (uint32_t i = threadIdx.x; i < half; i += blockDim.x) dst[i] = fadd(src[2 * i], src[2 * i + 1]);
-        __syncthreads();
-        float *tmp = src;
-        src = dst;
-        dst = tmp;
-    }
-    if (threadIdx.x != 0) return;
-    float total = src[0];
+// scalar epilogue of a finished tree sum `total` (one thread)
+__device__ void np_final_epilogue(float total, DevScalars *sc, const FinArgs &fa) {
     sc->tree_sum = total;
     double nd = (double)fa.n;
     if (fa.mode == FIN_MEAN || fa.mode == FIN_PRUNE1) {
@@ -994,6 +1023,27 @@ __global__ void __launch_bounds__(1024) np_final_kernel(float *partials, uint32_
         bool ok = (thr_f >= lo && thr_f <= hi) || (thr != thr) || (lo == 0.f && hi == 0.f && !(thr > 0));
         sc->spec_failed = ok ? 0 : 1;
     }
+}
+
+// folds a[0, count) (count a power of two) pairwise in place (ping-pong with the `count` floats behind it); result in
+// a[0] or a[count] -- the returned pointer.  All threads of one CTA.
+__device__ float *np_fold_pow2(float *a, uint32_t count) {
+    float *src = a, *dst = a + count;
+    for (uint32_t len = count; len > 1; len >>= 1) {
+        const uint32_t half = len >> 1;
+        for (uint32_t i = threadIdx.x; i < half; i += blockDim.x) dst[i] = fadd(src[2 * i], src[2 * i + 1]);
+        __syncthreads();
+        float *tmp = src;
+        src = dst;
+        dst = tmp;
+    }
+    return src;
+}
+
+__global__ void __launch_bounds__(1024) np_final_kernel(float *partials, uint32_t count, DevScalars *sc, FinArgs fa) {
+    float *src = np_fold_pow2(partials, count);
+    if (threadIdx.x != 0) return;
+    np_final_epilogue(src[0], sc, fa);
 }
 
 // Decide the band elements with the exact threshold.  With `out` (fused k-means prologue, VisitApplyQuant) the decided
@@ -1214,6 +1264,122 @@ static void launch_final(nnc_ctx *ctx, float *partials, uint32_t count, const Fi
     }
 }
 
+// ---- the same over NVLink peer memory (one box, peer mailboxes connected, power-of-two rank count) -----------------------
+// A rank's tiles are a complete sub-tree of the fold when the rank count is a power of two that divides the tile count:
+// the rank folds ITS partials to one float, and ONE in-kernel exchange (peer.cuh: stores into every rank's mailbox, flags,
+// local polling) carries that float together with the scalars the pass produced.  Every rank then folds the `world` floats
+// up the remaining levels -- the same additions as the single-rank fold -- and combines the scalars in rank order.
+// Replaces, per pass: a memset + an NCCL all-reduce of all tile partials (1 MB at 2^30 weights) + up to three small NCCL
+// all-reduces with their pack / unpack kernels.
+enum { EXW_PARTIAL = 0, EXW_SUM = 1, EXW_SUMSQ = 2, EXW_NPRUNED = 3, EXW_DROPPED = 4, EXW_NNZ = 5, EXW_NONFINITE = 6, EXW_MAXORD = 7,
+       EXW_MINORD = 8, EXW_AMAX = 9, EXW_AMIN = 10, EXW_COUNT = 11 };
+
+__global__ void __launch_bounds__(1024) np_final_peer_kernel(float *local, uint32_t count_local, DevScalars *sc, FinArgs fa, int modes,
+                                                             PeerComm pc, unsigned long long *gathered, int *comm_error) {
+    __shared__ unsigned long long words[EXW_COUNT];
+    __shared__ float top[2 * PEER_MAX_WORLD];
+    float *src = np_fold_pow2(local, count_local);
+    if (threadIdx.x == 0) {
+        words[EXW_PARTIAL] = (unsigned long long)__float_as_uint(src[0]);
+        words[EXW_SUM] = (unsigned long long)__double_as_longlong(sc->sum_d);
+        words[EXW_SUMSQ] = (unsigned long long)__double_as_longlong(sc->sumsq_d);
+        words[EXW_NPRUNED] = sc->n_pruned;
+        words[EXW_DROPPED] = sc->band_dropped;
+        words[EXW_NNZ] = sc->n_nz;
+        words[EXW_NONFINITE] = sc->n_nonfinite;
+        words[EXW_MAXORD] = sc->max_ord;
+        words[EXW_MINORD] = sc->min_ord;
+        words[EXW_AMAX] = sc->amax_bits;
+        words[EXW_AMIN] = sc->amin_nz_m1;
+    }
+    __syncthreads();
+    unsigned long long xseq = *peer_counter(pc);
+    const bool ok = peer_allgather(pc, words, EXW_COUNT, gathered, EXW_COUNT, ++xseq);
+    if (threadIdx.x == 0) {
+        *peer_counter(pc) = xseq;
+        if (!ok) *comm_error = 1;
+    }
+    if (threadIdx.x < (unsigned)pc.world) top[threadIdx.x] = __uint_as_float((uint32_t)gathered[(size_t)threadIdx.x * EXW_COUNT + EXW_PARTIAL]);
+    __syncthreads();
+    float *t = np_fold_pow2(top, (uint32_t)pc.world);
+    if (threadIdx.x != 0) return;
+    const int world = pc.world;
+    if (modes & (1 << EX_STATS)) {
+        double a = 0.0, b = 0.0;
+        for (int r = 0; r < world; ++r) {  // rank order: every rank gets the same double
+            a += __longlong_as_double((long long)gathered[(size_t)r * EXW_COUNT + EXW_SUM]);
+            b += __longlong_as_double((long long)gathered[(size_t)r * EXW_COUNT + EXW_SUMSQ]);
+        }
+        sc->sum_d = a;
+        sc->sumsq_d = b;
+    }
+    if (modes & (1 << EX_PRUNE)) {
+        unsigned long long a = 0, b = 0;
+        for (int r = 0; r < world; ++r) {
+            a += gathered[(size_t)r * EXW_COUNT + EXW_NPRUNED];
+            b += gathered[(size_t)r * EXW_COUNT + EXW_DROPPED];
+        }
+        sc->n_pruned = a;
+        sc->band_dropped = b;
+    }
+    if (modes & (1 << EX_QUANT)) {
+        sc->n_nz_local = sc->n_nz;
+        unsigned long long a = 0, b = 0;
+        uint32_t mx = 0, mn = 0xffffffffu, am = 0, an = 0xffffffffu;
+        for (int r = 0; r < world; ++r) {
+            const unsigned long long *g = gathered + (size_t)r * EXW_COUNT;
+            a += g[EXW_NNZ];
+            b += g[EXW_NONFINITE];
+            mx = max(mx, (uint32_t)g[EXW_MAXORD]);
+            mn = min(mn, (uint32_t)g[EXW_MINORD]);
+            am = max(am, (uint32_t)g[EXW_AMAX]);
+            an = min(an, (uint32_t)g[EXW_AMIN]);
+        }
+        sc->n_nz = a;
+        sc->n_nonfinite = b;
+        sc->max_ord = mx;
+        sc->min_ord = mn;
+        sc->amax_bits = am;
+        sc->amin_nz_m1 = an;
+    }
+    np_final_epilogue(t[0], sc, fa);
+}
+
+static bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
+
+// true when the fold + exchange of a pass can run over the peer mailboxes (see np_final_peer_kernel)
+static bool peer_final_ok(nnc_ctx *ctx, uint32_t num_tiles) {
+    return ctx->world > 1 && ctx->peer_enabled && ctx->world <= PEER_MAX_WORLD && is_pow2((uint32_t)ctx->world) && num_tiles >= (uint32_t)ctx->world &&
+           num_tiles % (uint32_t)ctx->world == 0 && !getenv("NNC_NO_PEER_FINAL");
+}
+
+// partials: the 2 * num_tiles + 2 floats of a tree (this rank's tiles filled); modes: bit mask of (1 << EX_*)
+static void launch_final_peer(nnc_ctx *ctx, float *partials, uint32_t num_tiles, const FinArgs &fa, int modes) {
+    const uint32_t L = num_tiles / (uint32_t)ctx->world;
+    float *mine = partials + ctx->sh.t0;  // [t0, t0 + L): a complete sub-tree
+    float *scratch = arena_alloc_t<float>(ctx, 2 * (size_t)std::max<uint32_t>(L, 2048) + 16);
+    float *local = scratch;
+    uint32_t count = L;
+    if (L >= 4096) {  // first stage of the local fold: 1024 partials per CTA (complete sub-trees again)
+        NNC_LAUNCH(ctx, np_fold1024_kernel, L / 1024, 512, 0, mine, scratch);
+        count = L / 1024;
+    } else {
+        NNC_CUDA(cudaMemcpyAsync(scratch, mine, sizeof(float) * L, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    PeerComm pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.enabled = 1;
+    pc.rank = ctx->rank;
+    pc.world = ctx->world;
+    for (int r = 0; r < ctx->world; ++r) pc.mail[r] = static_cast<unsigned long long *>(ctx->peer_mail[r]);
+    unsigned long long *gathered = arena_alloc_t<unsigned long long>(ctx, (size_t)ctx->world * EXW_COUNT);
+    if (!ctx->d_comm_error) {
+        NNC_CUDA(cudaMalloc(&ctx->d_comm_error, sizeof(int)));
+        NNC_CUDA(cudaMemsetAsync(ctx->d_comm_error, 0, sizeof(int), ctx->stream));
+    }
+    NNC_LAUNCH(ctx, np_final_peer_kernel, 1, 1024, 0, local, count, ctx->d_scal, fa, modes, pc, gathered, ctx->d_comm_error);
+}
+
 static int tree_grid(nnc_ctx *ctx, uint32_t tiles) {
     int64_t g = (int64_t)ctx->sm_count * 8;
     if ((int64_t)tiles < g) g = tiles;
@@ -1245,13 +1411,18 @@ static NpTileDesc *run_tree(nnc_ctx *ctx, const float *d_w, V v, const FinArgs &
         NNC_LAUNCH(ctx, np_tiles_kernel, (p.num_tiles + 127) / 128, 128, 0, n, p.depth, desc);
         ctx->desc_n = n;
     }
-    if (ctx->world > 1) NNC_CUDA(cudaMemsetAsync(partials, 0, sizeof(float) * (2 * (size_t)p.num_tiles + 2), ctx->stream));
+    const bool peer_final = peer_final_ok(ctx, p.num_tiles);
+    if (ctx->world > 1 && !peer_final) NNC_CUDA(cudaMemsetAsync(partials, 0, sizeof(float) * (2 * (size_t)p.num_tiles + 2), ctx->stream));
     const uint32_t t0 = ctx->sh.t0, t1 = ctx->sh.t1;
     const size_t dyn = np_tree_smem<V>();
     func_dyn_smem(ctx, (const void *)np_tree_kernel<V>, dyn);
     if (t1 > t0)
         NNC_LAUNCH_AS(ctx, V::kName, np_tree_kernel<V>, tree_grid(ctx, t1 - t0), NP_THREADS, dyn, d_w, t0, t1, ctx->sh.begin,
                    aligned16(d_w) ? 1 : 0, desc, partials, (const uint32_t *)nullptr, (const unsigned int *)nullptr, v);
+    if (peer_final) {  // local fold + one in-kernel exchange (partial and scalars together) + the top of the fold
+        launch_final_peer(ctx, partials, p.num_tiles, fa, exchange_mode == EX_NONE ? 0 : (1 << exchange_mode));
+        return desc;
+    }
     if (ctx->world > 1) comm_allreduce(ctx, reinterpret_cast<int64_t *>(partials), (int)((p.num_tiles + 1) / 2), 0);
     exchange_scalars(ctx, exchange_mode);
     launch_final(ctx, partials, p.num_tiles, fa);
@@ -1328,7 +1499,8 @@ void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth,
         uint32_t *dirty_list = arena_alloc_t<uint32_t>(ctx, (size_t)p.num_tiles);
         unsigned long long *ctr = arena_alloc_t<unsigned long long>(ctx, 2);  // survivor cursor, dirty-tile count
         NNC_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), ctx->stream));
-        if (ctx->world > 1) NNC_CUDA(cudaMemsetAsync(partials2, 0, sizeof(float) * (2 * (size_t)p.num_tiles + 2), ctx->stream));
+        const bool peer_final2 = peer_final_ok(ctx, p.num_tiles);
+        if (ctx->world > 1 && !peer_final2) NNC_CUDA(cudaMemsetAsync(partials2, 0, sizeof(float) * (2 * (size_t)p.num_tiles + 2), ctx->stream));
         cursor = ctr;
         unsigned int *dirty_count = reinterpret_cast<unsigned int *>(ctr + 1);
         VisitApplyQuant v2;
@@ -1356,10 +1528,14 @@ void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth,
         NNC_LAUNCH_AS(ctx, VisitPlain::kName, np_tree_kernel<VisitPlain>, std::max(1, std::min<int>(ctx->sm_count * 4, (int)std::min<uint32_t>(p.num_tiles, 1u << 20))),
                    NP_THREADS, np_tree_smem<VisitPlain>(), d_w, 0u, 0u, ctx->sh.begin, aligned16(d_w) ? 1 : 0, desc, partials2, (const uint32_t *)dirty_list,
                    (const unsigned int *)dirty_count, VisitPlain{});
-        exchange_scalars(ctx, EX_PRUNE);
-        if (ctx->world > 1) comm_allreduce(ctx, reinterpret_cast<int64_t *>(partials2), (int)((p.num_tiles + 1) / 2), 0);
-        exchange_scalars(ctx, EX_QUANT);
-        launch_final(ctx, partials2, p.num_tiles, FinArgs{FIN_MEAN, ng, 0.0, 0, 1});
+        if (peer_final2) {
+            launch_final_peer(ctx, partials2, p.num_tiles, FinArgs{FIN_MEAN, ng, 0.0, 0, 1}, (1 << EX_PRUNE) | (1 << EX_QUANT));
+        } else {
+            exchange_scalars(ctx, EX_PRUNE);
+            if (ctx->world > 1) comm_allreduce(ctx, reinterpret_cast<int64_t *>(partials2), (int)((p.num_tiles + 1) / 2), 0);
+            exchange_scalars(ctx, EX_QUANT);
+            launch_final(ctx, partials2, p.num_tiles, FinArgs{FIN_MEAN, ng, 0.0, 0, 1});
+        }
         prof_mark(ctx, "fixup");
     } else {
     VisitCenSqApply v2;
