@@ -9,6 +9,7 @@
 // Packed layout: code i occupies bits [i*bits, (i+1)*bits) of a little-endian byte stream.  A thread owns
 // 8 consecutive weights, hence exactly `bits` consecutive bytes of the stream.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "internal.h"
@@ -195,6 +196,10 @@ __global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__rest
         const int64_t first = (int64_t)blockIdx.x * EM_THREADS + threadIdx.x;
         if (first < n_chunks) load_chunk(first, xn);
     }
+    // two copies of the loop: with and without the histogram bookkeeping (the fused compress path takes the code histogram
+    // from the Lloyd kernel; the kernel is issue bound, every instruction per element counts)
+    auto run = [&](auto hist_c) {
+    constexpr bool HIST = decltype(hist_c)::value;
     for (int64_t chunk = (int64_t)blockIdx.x * EM_THREADS + threadIdx.x; chunk < n_chunks; chunk += stride) {
         const int64_t base = chunk * EM_PER;
         float x[EM_PER];
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__rest
         if (chunk + stride < n_chunks) load_chunk(chunk + stride, xn);
         // phase 1, branch free: LUT entry of every element (pruned weights take the known label of 0.0)
         int id[EM_PER];
-        uint32_t slow = 0;
+        uint32_t any = 0;
 #pragma unroll
         for (int j = 0; j < EM_PER; ++j) {
             const bool zero = x[j] == 0.f;
@@ -213,8 +218,13 @@ __global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__rest
             if (e & EM_L2) e = S.lut2[(e & (EM_L2 - 1)) * EM_SUB + (f % EM_SUB)];
             e = zero ? (uint32_t)zid : e;
             id[j] = (int)e;
-            slow |= (e >> 15) << j;
-            zcount += zero;
+            any |= e;
+            if (HIST) zcount += zero;
+        }
+        uint32_t slow = 0;
+        if (any & EM_SLOW) {  // which of the eight need the search (rare: their fine bucket holds a boundary or a zone)
+#pragma unroll
+            for (int j = 0; j < EM_PER; ++j) slow |= ((uint32_t)id[j] >> 15) << j;
         }
         // phase 2: the few elements whose fine bucket holds a region boundary or a zone (one pass per thread)
         while (slow) {
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__rest
 #pragma unroll
             for (int q = 0; q < EM_PER; ++q) id[q] = q == j ? lab : id[q];
         }
-        if (want_hist) {
+        if (HIST) {
 #pragma unroll
             for (int j = 0; j < EM_PER; ++j)
                 if (x[j] != 0.f) atomicAdd(&S.hist[id[j]], 1u);  // NaN never gets here (rejected upstream)
@@ -304,6 +314,11 @@ __global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__rest
             }
         }
     }
+    };
+    if (want_hist)
+        run(std::true_type{});
+    else
+        run(std::false_type{});
     if (INERTIA) {
         inert = warp_sum_ull(inert);
         if (lane_id() == 0 && inert) atomicAdd(&ed->inertia_q, inert);

@@ -1116,7 +1116,7 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         unsigned int tb[2];
         NNC_CUDA(cudaMemcpy(tb, st->logT[LL_LOG - 1], sizeof(tb), cudaMemcpyDeviceToHost));
         fprintf(stderr, "[nnc lloyd] four bare grid barriers: %.2f us\n", (tb[1] - tb[0]) * 1e-3);
-        long long zp[4], up[8];
+        long long zp[4], up[12];
         if (atoi(getenv("NNC_LLOYD_LOG")) > 1) {  // per-CTA time stamps of iteration 6 (cluster kernel)
             unsigned long long sl[16 * 8];
             NNC_CUDA(cudaMemcpy(sl, st->logZ, sizeof(sl), cudaMemcpyDeviceToHost));
@@ -1128,9 +1128,13 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
                             (long long)(sl[8 * c + 5] - sl[8 * c + 4]), (long long)(sl[8 * c + 6] - sl[8 * c + 5]));
         }
         NNC_CUDA(cudaMemcpy(zp, st->logZ + LL_LOG - 16, sizeof(zp), cudaMemcpyDeviceToHost));
-        NNC_CUDA(cudaMemcpy(up, st->logZ + LL_LOG - 32, sizeof(up), cudaMemcpyDeviceToHost));
+        NNC_CUDA(cudaMemcpy(up, st->logZ + LL_LOG - 32, sizeof(long long) * 8, cudaMemcpyDeviceToHost));
         fprintf(stderr, "[nnc lloyd] zone profile (cycles): prefix %lld elements %lld flush %lld\n", zp[1], zp[2], zp[3]);
         fprintf(stderr, "[nnc lloyd] update profile (cycles): safe %lld zero-run %lld per-id+empties %lld reloc %lld average %lld conv %lld end %lld\n", up[1], up[2], up[3], up[4], up[5], up[6], up[7]);
+        for (int w = 0; w < 2; ++w) {
+            NNC_CUDA(cudaMemcpy(up, st->logZ + LL_LOG - 48 - 16 * w, sizeof(up), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[nnc lloyd] update profile of iteration %d (cycles): safe %lld zero-run %lld per-id+empties %lld reloc %lld average %lld conv %lld end %lld | relocation: streams filled %lld pops done %lld (%lld rounds, %lld refills)\n", w, up[1], up[2], up[3], up[4], up[5], up[6], up[7], up[8], up[9], up[10] & 0xffff, up[10] >> 16);
+        }
         for (int i = 0; i < cnt; ++i)
             fprintf(stderr, "[nnc lloyd] iter %d zone_elems %lld (%.3f%% of survivors) groups %d distinct %d empty %d | us: search %.1f zone %.1f update %.1f table %.1f\n", i, z[i],
                     h.n_nz ? 100.0 * (double)z[i] / (double)h.n_nz : 0.0, g[i], mm[i], ee[i], tt[4 * i] * 1e-3, tt[4 * i + 1] * 1e-3,

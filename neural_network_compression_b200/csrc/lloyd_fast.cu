@@ -39,11 +39,16 @@ struct NpWarpScratch {
     float val[16];
 };
 
-struct PopState {  // relocation: the two cursors of every distinct index's member stream and the keys of their heads
-    long long pl[LF_KMAX], pr[LF_KMAX];
-    unsigned long long reml[LF_KMAX], remr[LF_KMAX];  // samples left in the entry under the left / right cursor
-    uint32_t kl[LF_KMAX][3], kr[LF_KMAX][3];          // FarKey (d2, gap, ordx) of the heads
-    int flags[LF_KMAX];                               // bit 0: left head valid, bit 1: right head valid
+// relocation: every distinct index has two candidate streams -- its members below its centroid walked from the left end
+// (stream 2 i) and its members at or above it walked from the right end (stream 2 i + 1); along each stream the FarKey
+// decreases strictly.  The first LF_POP_D members of every stream are PRELOADED by all threads at once (one memory round
+// trip), so that the serial pop chain runs out of shared memory; a stream that is drained deeper refills itself (rare).
+constexpr int LF_POP_D = 4;  // preloaded members per stream for m <= LF_KMAX / 2 distinct centroids (2 above)
+struct PopState {
+    uint4 hk[2 * LF_KMAX];    // head of the stream: FarKey (d2, gap, ordx) and the samples left in it (0: stream empty)
+    uint4 ent[3 * LF_KMAX];   // [stream * (D - 1) + j]: preloaded member j + 1 (key, multiplicity)
+    int next_off[2 * LF_KMAX];  // entries already walked from the stream's end (where a refill continues); -1: nothing left
+    unsigned char head[2 * LF_KMAX], depth[2 * LF_KMAX];  // preloaded members: the one in hk, how many there are
 };
 
 struct FastUpdate {  // scratch of the update step (CTA 0)
@@ -468,6 +473,82 @@ __device__ void fast_gather_zones(cg::cluster_group &cluster, FastSmem &S, bool 
     }
 }
 
+// relocation: (re)loads up to D members of candidate stream sidx, starting `off` entries from the stream's end (one thread)
+__device__ __noinline__ void pop_fill(FastSmem &S, const FastConst &K, const float *__restrict__ ks, int sidx, int D, int off) {
+    FastUpdate &U = S.u.up;
+    PopState &P = U.pop;
+    const RegionTableT<LF_KMAX> &T = S.tab;
+    const unsigned int *__restrict__ ecnt = K.cnt;
+    const int i = sidx >> 1;
+    const bool right = sidx & 1;
+    const long long first = U.first[i], last = U.last[i];
+    const float c = T.dv[i], mean = K.mean;
+    int n = 0, next = -1;
+    P.hk[sidx] = make_uint4(0u, 0u, 0u, 0u);
+    if (last >= first && last >= 0) {
+        for (;;) {
+            float x[LF_POP_D];
+            unsigned int cn[LF_POP_D];
+#pragma unroll
+            for (int j = 0; j < LF_POP_D; ++j) {  // all loads in flight
+                const long long p = right ? last - off - j : first + off + j;
+                const bool ok = j < D && p >= first && p <= last;
+                x[j] = ok ? ld_vol_f1(ks + p) : 0.f;
+                cn[j] = 1u;
+                if (ok && ecnt) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(cn[j]) : "l"(ecnt + p));
+            }
+            bool ended = false;
+            int r = -1;  // region of the previous position (the walk moves one entry at a time: one search, then steps)
+#pragma unroll
+            for (int j = 0; j < LF_POP_D; ++j) {
+                if (j >= D || ended) continue;
+                const long long p = right ? last - off - j : first + off + j;
+                if (p < first || p > last) {
+                    ended = true;
+                    continue;
+                }
+                const float xc = fsub(x[j], mean);
+                if (right ? !(xc >= c) : !(xc < c)) {  // the other stream's half of the cluster
+                    ended = true;
+                    continue;
+                }
+                if (r < 0) {
+                    int lo = 0, hi = T.R;  // largest r with rpos[r] <= p
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (S.rpos[mid] <= p)
+                            lo = mid;
+                        else
+                            hi = mid;
+                    }
+                    r = lo;
+                } else if (right) {
+                    while (S.rpos[r] > p) --r;
+                } else {
+                    while (r + 1 < T.R && S.rpos[r + 1] <= p) ++r;
+                }
+                const int lab = T.rJ1[r] == T.rJ2[r] ? T.rJ1[r] : zone_argmin(xc, T.dv, T.dcn, T.down, T.rJ2[r], T.rJ1[r]);
+                if (lab != i) continue;  // a neighbour's member inside a zone
+                const FarKey key = far_key(xc, c);
+                const uint4 e = make_uint4(key.d2, key.gap, key.ordx, cn[j]);
+                if (n == 0)
+                    P.hk[sidx] = e;
+                else
+                    P.ent[sidx * (D - 1) + n - 1] = e;
+                ++n;
+            }
+            if (ended) break;
+            off += D;
+            next = off;
+            if (n > 0) break;
+            next = -1;  // nothing but neighbours so far: keep walking
+        }
+    }
+    P.head[sidx] = 0;
+    P.depth[sidx] = (unsigned char)n;
+    P.next_off[sidx] = next;
+}
+
 // ---- update step (CTA 0 only; S is its own shared memory): per-cluster counts / sums, label-equality proxy, empty-cluster
 // relocation, averages, centre shift, convergence.  Mirrors update_phase of lloyd.cu statement by statement.
 __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const FastConst &K, const float *__restrict__ ks,
@@ -566,239 +647,185 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
     const int n_empty = U.n_empty;
     if (prof) prof[3] = clock64();
     if (n_empty > 0) {
-        // Streams of candidates: for every distinct index its members walked from the left end and from the right end
-        // (|x' - c| is V-shaped along a cluster's sorted members), plus the zero run.  The farthest remaining sample
-        // overall is always at the head of one of the streams; pop n_empty times.
-        // The heads are set up by all threads (one stream each, loads in parallel); the pops themselves are a serial
-        // chain and run in ONE warp out of shared memory -- lane l owns the streams l, l + 32, ... and keeps the best of
-        // them in registers; a pop is a warp arg-max (shuffles), the winner's lane advances that stream and rescans its
-        // own streams.  No block barrier inside the chain (with one barrier pair per pop a pop cost 4 us).
+        // Candidate streams (PopState).  The farthest remaining sample overall is always at the head of one of the
+        // streams (or is the zero run); pop n_empty times.  The pops are a serial chain and run in ONE warp out of shared
+        // memory: lane l owns the streams l, l + 32, ... and keeps the best of their heads in registers; a pop is a warp
+        // arg-max (four redux operations), the winner's lane advances that stream and rescans its own heads.  Equal
+        // samples (an entry's multiplicity, the zero run) are taken in one pop.
         PopState &P = U.pop;
-        const unsigned int *__restrict__ ecnt = K.cnt;
-        auto cnt_at = [&](long long p) -> unsigned long long { return ecnt ? (unsigned long long)ecnt[p] : 1ull; };
-        if (tid < m) {
-            long long pl = -1, pr = -2;  // empty stream when pl > pr
-            unsigned long long reml = 0, remr = 0;
-            const float cown = T.dv[tid];
-            if (U.last[tid] >= U.first[tid] && U.last[tid] >= 0) {
-                pl = U.first[tid];
-                pr = U.last[tid];
-                reml = cnt_at(pl);
-                remr = cnt_at(pr);
-            }
-            int flags = 0;
-            if (pl <= pr) {
-                const FarKey kl = far_key(fsub(ks[pl], mean), cown);
-                P.kl[tid][0] = kl.d2, P.kl[tid][1] = kl.gap, P.kl[tid][2] = kl.ordx;
-                flags |= 1;
-                if (pr > pl) {
-                    const FarKey kr = far_key(fsub(ks[pr], mean), cown);
-                    P.kr[tid][0] = kr.d2, P.kr[tid][1] = kr.gap, P.kr[tid][2] = kr.ordx;
-                    flags |= 2;
-                }
-            }
-            P.pl[tid] = pl;
-            P.pr[tid] = pr;
-            P.reml[tid] = reml;
-            P.remr[tid] = remr;
-            P.flags[tid] = flags;
-        }
-        if (tid == 0) {
-            U.zero_left = K.n0;
-            U.winner = 0;  // pops done
-        }
+        const int D = 2 * m * LF_POP_D <= 4 * LF_KMAX ? LF_POP_D : 2;
+        for (int sidx = tid; sidx < 2 * m; sidx += NT) pop_fill(S, K, ks, sidx, D, 0);
+        if (tid == 0) U.winner = 0;  // pops done
         __syncthreads();
-        unsigned long long *my_cand = K.cand + (size_t)K.rank * k * 2;
+        if (prof) prof[8] = clock64();
+        int n_rounds = 0, n_refill = 0;
+        long long *cand = S.xbuf;  // this rank's list, descending: (d2 << 32 | gap, ordx << 32 | old cluster id + 1)
         if (warp_id() == 0) {
             const int lane = lane_id();
-            const int zdi = U.zdi;
+            const int zdi = U.zdi, ZS = 2 * m;  // the zero run is one more stream, owned by lane 0
             const FarKey kz = far_key(x0, zdi >= 0 ? T.dv[zdi] : 0.f);
-            long long zero_left = K.n0;  // kept by every lane (uniform)
-            // best head among the streams of this lane: (key, stream, which head: 0 left, 1 right, 2 zero run)
-            FarKey best{0, 0, 0};
-            int bi = -1, bwho = -1;
+            long long zero_left = zdi >= 0 ? K.n0 : 0;  // kept by every lane (uniform)
+            uint32_t bd = 0, bg = 0, bo = 0;
+            int bs = -1;
+            // the rescan is on the serial chain: eight heads per step with their loads in flight together and a
+            // comparison TREE (a running arg-max over 16 heads is 16 dependent steps).  An empty head is the key (0, 0, 0),
+            // below every real key (ordx of a finite float is never 0); equal keys keep the lower stream.
+            struct Cand {
+                unsigned long long kk;
+                uint32_t o;
+                int st;
+            };
+            auto pick = [](const Cand &a, const Cand &b) { return (b.kk > a.kk || (b.kk == a.kk && b.o > a.o)) ? b : a; };
             auto rescan = [&]() {
-                best = FarKey{0, 0, 0};
-                bi = -1;
-                bwho = -1;
-                for (int i = lane; i < m; i += 32) {
-                    const int fl = P.flags[i];
-                    if (fl & 1) {
-                        const FarKey kl{P.kl[i][0], P.kl[i][1], P.kl[i][2]};
-                        if (bi < 0 || far_before(kl, best)) {
-                            best = kl;
-                            bi = i;
-                            bwho = 0;
-                        }
+                Cand best{0ull, 0u, -1};
+                for (int base = lane; base < 2 * m; base += 256) {
+                    Cand c[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int i = base + 32 * j;
+                        const uint4 e = i < 2 * m ? P.hk[i] : make_uint4(0u, 0u, 0u, 0u);
+                        const bool v = e.w != 0u;
+                        c[j].kk = v ? (((unsigned long long)e.x << 32) | e.y) : 0ull;
+                        c[j].o = v ? e.z : 0u;
+                        c[j].st = v ? i : -1;
                     }
-                    if (fl & 2) {
-                        const FarKey kr{P.kr[i][0], P.kr[i][1], P.kr[i][2]};
-                        if (bi < 0 || far_before(kr, best)) {
-                            best = kr;
-                            bi = i;
-                            bwho = 1;
-                        }
-                    }
-                    if (i == zdi && zero_left > 0 && (bi < 0 || far_before(kz, best))) {
-                        best = kz;
-                        bi = i;
-                        bwho = 2;
-                    }
+                    c[0] = pick(c[0], c[1]);
+                    c[2] = pick(c[2], c[3]);
+                    c[4] = pick(c[4], c[5]);
+                    c[6] = pick(c[6], c[7]);
+                    c[0] = pick(c[0], c[2]);
+                    c[4] = pick(c[4], c[6]);
+                    best = pick(best, pick(c[0], c[4]));
                 }
+                if (lane == 0 && zero_left > 0)
+                    best = pick(best, Cand{((unsigned long long)kz.d2 << 32) | kz.gap, kz.ordx, ZS});
+                bd = (uint32_t)(best.kk >> 32);
+                bg = (uint32_t)best.kk;
+                bo = best.o;
+                bs = best.st;
             };
             rescan();
-            int n_done = 0;
-            for (int pop = 0; pop < n_empty; ++pop) {
-                FarKey wk = best;
-                int wi = bi, ww = bwho;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    FarKey ob;
-                    ob.d2 = __shfl_xor_sync(0xffffffffu, wk.d2, o);
-                    ob.gap = __shfl_xor_sync(0xffffffffu, wk.gap, o);
-                    ob.ordx = __shfl_xor_sync(0xffffffffu, wk.ordx, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, wi, o), ow = __shfl_xor_sync(0xffffffffu, ww, o);
-                    // farther key wins; equal keys: the lower stream, then the lower head (left, right, zero run)
-                    if (oi >= 0 && (wi < 0 || far_before(ob, wk) || (!far_before(wk, ob) && (oi < wi || (oi == wi && ow < ww))))) {
-                        wk = ob;
-                        wi = oi;
-                        ww = ow;
-                    }
+            int pop = 0;
+            while (pop < n_empty) {
+                if (!__ballot_sync(0xffffffffu, bs >= 0)) break;  // this rank has no sample left
+                bool in = bs >= 0;
+                const uint32_t M1 = __reduce_max_sync(0xffffffffu, in ? bd : 0u);
+                in = in && bd == M1;
+                const uint32_t M2 = __reduce_max_sync(0xffffffffu, in ? bg : 0u);
+                in = in && bg == M2;
+                const uint32_t M3 = __reduce_max_sync(0xffffffffu, in ? bo : 0u);
+                in = in && bo == M3;
+                const int ws = (int)__reduce_min_sync(0xffffffffu, in ? (unsigned)bs : 0xffffffffu);  // equal keys: the lower stream
+                // samples taken from this entry: all of them, or what is still needed
+                long long avail = ws == ZS ? zero_left : (long long)P.hk[ws].w;
+                const int take = (int)llmin2(avail, (long long)(n_empty - pop));
+                const int di = ws == ZS ? zdi : (ws >> 1);
+                const unsigned long long ca = ((unsigned long long)M1 << 32) | M2;
+                const unsigned long long cb = ((unsigned long long)M3 << 32) | (unsigned)(T.down[di] + 1);
+                for (int q = lane; q < take; q += 32) {
+                    cand[2 * (pop + q)] = (long long)ca;
+                    cand[2 * (pop + q) + 1] = (long long)cb;
                 }
-                if (wi < 0) break;  // this rank has no sample left
-                if (ww == 2) zero_left -= 1;
-                if (lane == (wi & 31)) {
-                    const int i = wi;
-                    // candidate = (dist^2, ulp gap | x', old cluster id + 1): the local list comes out in descending order
-                    my_cand[2 * pop] = ((unsigned long long)wk.d2 << 32) | wk.gap;
-                    my_cand[2 * pop + 1] = ((unsigned long long)wk.ordx << 32) | (unsigned)(T.down[i] + 1);
-                    if (ww == 0) {
-                        if (P.reml[i] > 1) {
-                            P.reml[i] -= 1;
+                pop += take;
+                if (ws == ZS) {
+                    zero_left -= take;
+                    if (lane == 0) rescan();
+                } else if (lane == (ws & 31)) {
+                    const unsigned left = P.hk[ws].w - (unsigned)take;
+                    if (left) {
+                        P.hk[ws].w = left;
+                    } else {
+                        const int h = P.head[ws] + 1;
+                        if (h < P.depth[ws]) {
+                            P.hk[ws] = P.ent[ws * (D - 1) + h - 1];
+                            P.head[ws] = (unsigned char)h;
+                        } else if (P.next_off[ws] >= 0) {
+                            pop_fill(S, K, ks, ws, D, P.next_off[ws]);  // drained deeper than the preload: a memory round trip
+                            ++n_refill;
                         } else {
-                            // next member from the left: value and count of a candidate position are loaded together
-                            // (one round trip), the label check uses the loaded value
-                            long long pl = P.pl[i];
-                            const long long pr = P.pr[i];
-                            float x = 0.f;
-                            unsigned long long c = 1ull;
-                            do {
-                                ++pl;
-                                if (pl > pr) break;
-                                x = ks[pl];
-                                c = cnt_at(pl);
-                            } while (fast_label_of(S, mean, pl, x) != i);
-                            int fl = P.flags[i] & ~1;
-                            if (pl <= pr) {
-                                P.reml[i] = pl == pr ? P.remr[i] : c;
-                                const FarKey kl = far_key(fsub(x, mean), T.dv[i]);
-                                P.kl[i][0] = kl.d2, P.kl[i][1] = kl.gap, P.kl[i][2] = kl.ordx;
-                                fl |= 1;
-                            }
-                            if (pl >= pr) fl &= ~2;  // the cursors met: the left one owns what is left
-                            P.pl[i] = pl;
-                            P.flags[i] = fl;
-                        }
-                    } else if (ww == 1) {
-                        if (P.remr[i] > 1) {
-                            P.remr[i] -= 1;
-                        } else {
-                            const long long pl = P.pl[i];
-                            long long pr = P.pr[i];
-                            float x = 0.f;
-                            unsigned long long c = 1ull;
-                            do {
-                                --pr;
-                                if (pr < pl) break;
-                                x = ks[pr];
-                                c = cnt_at(pr);
-                            } while (fast_label_of(S, mean, pr, x) != i);
-                            int fl = P.flags[i] & ~2;
-                            if (pr > pl) {
-                                P.remr[i] = c;
-                                const FarKey kr = far_key(fsub(x, mean), T.dv[i]);
-                                P.kr[i][0] = kr.d2, P.kr[i][1] = kr.gap, P.kr[i][2] = kr.ordx;
-                                fl |= 2;
-                            } else if (pr < pl) {
-                                fl &= ~1;
-                            }
-                            P.pr[i] = pr;
-                            P.flags[i] = fl;
+                            P.hk[ws].w = 0;
                         }
                     }
+                    rescan();  // only this lane's streams changed
                 }
                 __syncwarp();
-                if (lane == (wi & 31)) rescan();  // only this lane's streams (and its view of the zero run) changed
-                else if (ww == 2 && lane == (zdi & 31)) rescan();
-                n_done = pop + 1;
+                ++n_rounds;
             }
-            if (lane == 0) U.winner = n_done;
+            if (lane == 0) U.winner = pop;
+            n_refill = __reduce_add_sync(0xffffffffu, n_refill);
+            if (prof) {
+                prof[9] = clock64();
+                prof[10] = n_rounds | ((long long)n_refill << 16);
+            }
         }
         __syncthreads();
         const int n_done = U.winner;
-        // unused slots of this rank, and (before the all-gather) every slot of the other ranks, hold zeros
-        for (int i = tid; i < K.world * k; i += NT) {
-            const int r = i / k, j = i - r * k;
-            if (r != K.rank || j >= n_done) {
-                K.cand[2 * (size_t)i] = 0;
-                K.cand[2 * (size_t)i + 1] = 0;
+        if (!pc.enabled) {
+            // one rank: its list is the global list.  np.max(distances) == 0 -> relocation is skipped altogether
+            // (_k_means_common.pyx:192-195)
+            const bool skip = n_done > 0 && ((unsigned long long)cand[0] >> 32) == 0ull;
+            if (!skip) {
+                for (int i = tid; i < n_done; i += NT) {
+                    const unsigned long long bb = (unsigned long long)cand[2 * i + 1];
+                    U.far_x[i] = ord2f((uint32_t)(bb >> 32));
+                    U.far_old[i] = (int)(bb & 0xffffffffull) - 1;
+                }
             }
-        }
-        __threadfence_block();
-        __syncthreads();
-        if (pc.enabled) {  // fused all-gather of the candidate lists (n_empty is the same on every rank)
-            const int cnt = 2 * n_empty;
-            const unsigned long long *mine = K.cand + (size_t)K.rank * k * 2;
-            for (int i = tid; i < cnt; i += NT) S.xbuf[i] = (long long)mine[i];
+            if (tid == 0) U.winner = skip ? 0 : n_done;  // samples to move
             __syncthreads();
-            if (!peer_allgather(pc, reinterpret_cast<const unsigned long long *>(S.xbuf), cnt, K.cand, (size_t)k * 2, ++xseq) &&
+        } else {
+            // unused slots of this rank hold zeros; fused all-gather of the candidate lists (n_empty is the same on every rank)
+            for (int i = 2 * n_done + tid; i < 2 * n_empty; i += NT) cand[i] = 0;
+            __syncthreads();
+            if (!peer_allgather(pc, reinterpret_cast<const unsigned long long *>(cand), 2 * n_empty, K.cand, (size_t)k * 2, ++xseq) &&
                 tid == 0)
                 S.comm_error = 1;
-        }
-        // ---- 5b. the n_empty farthest samples over all ranks (every rank's list is in descending order: a W-way merge by
-        // one thread), moved to the empty clusters in ascending id order
-        __syncthreads();
-        if (tid == 0) {
-            const int world = K.world;
-            int *cur = S.merge_cur;
-            for (int r = 0; r < world; ++r) cur[r] = 0;
-            int n_moved = 0;
-            bool skip = false;
-            for (int i = 0; i < n_empty; ++i) {
-                int br = -1;
-                unsigned long long ba = 0, bb = 0;
-                for (int r = 0; r < world; ++r) {
-                    if (cur[r] >= k) continue;
-                    const unsigned long long a = K.cand[2 * ((size_t)r * k + cur[r])], b = K.cand[2 * ((size_t)r * k + cur[r]) + 1];
-                    if ((b & 0xffffffffull) == 0) continue;  // list exhausted
-                    if (br < 0 || a > ba || (a == ba && (b >> 32) > (bb >> 32))) {
-                        br = r;
-                        ba = a;
-                        bb = b;
+            __threadfence_block();
+            __syncthreads();
+            // ---- 5b. the n_empty farthest samples over all ranks (every rank's list is in descending order: a W-way merge by
+            // one thread)
+            if (tid == 0) {
+                const int world = K.world;
+                int *cur = S.merge_cur;
+                for (int r = 0; r < world; ++r) cur[r] = 0;
+                int n_moved = 0;
+                for (int i = 0; i < n_empty; ++i) {
+                    int br = -1;
+                    unsigned long long ba = 0, bb = 0;
+                    for (int r = 0; r < world; ++r) {
+                        if (cur[r] >= n_empty) continue;
+                        const unsigned long long a = K.cand[2 * ((size_t)r * k + cur[r])], b = K.cand[2 * ((size_t)r * k + cur[r]) + 1];
+                        if ((b & 0xffffffffull) == 0) continue;  // list exhausted
+                        if (br < 0 || a > ba || (a == ba && (b >> 32) > (bb >> 32))) {
+                            br = r;
+                            ba = a;
+                            bb = b;
+                        }
                     }
+                    if (br < 0) break;
+                    // np.max(distances) == 0 -> relocation is skipped altogether (_k_means_common.pyx:192-195)
+                    if (i == 0 && (ba >> 32) == 0ull) break;
+                    cur[br]++;
+                    U.far_x[i] = ord2f((uint32_t)(bb >> 32));
+                    U.far_old[i] = (int)(bb & 0xffffffffull) - 1;
+                    n_moved = i + 1;
                 }
-                if (br < 0) break;
-                // np.max(distances) == 0 -> relocation is skipped altogether (_k_means_common.pyx:192-195)
-                if (i == 0 && (ba >> 32) == 0ull) {
-                    skip = true;
-                    break;
-                }
-                cur[br]++;
-                U.far_x[i] = ord2f((uint32_t)(bb >> 32));
-                U.far_old[i] = (int)(bb & 0xffffffffull) - 1;
-                n_moved = i + 1;
+                U.winner = n_moved;
             }
-            if (!skip) {
-                for (int i = 0; i < n_moved; ++i) {
-                    const int nwid = U.empt[i], od = U.far_old[i];
-                    const long long q = fixed_q(U.far_x[i], scale);
-                    U.S[od] -= q;
-                    U.S[nwid] = q;
-                    U.W[nwid] = 1;
-                    U.W[od] -= 1;
-                }
-                S.n_reloc += n_moved;
+            __syncthreads();
+        }
+        // the far samples move to the empty clusters in ascending id order
+        if (tid == 0) {
+            const int n_moved = U.winner;
+            for (int i = 0; i < n_moved; ++i) {
+                const int nwid = U.empt[i], od = U.far_old[i];
+                const long long q = fixed_q(U.far_x[i], scale);
+                U.S[od] -= q;
+                U.S[nwid] = q;
+                U.W[nwid] = 1;
+                U.W[od] -= 1;
             }
+            S.n_reloc += n_moved;
         }
         __syncthreads();
     }
@@ -1053,12 +1080,24 @@ __global__ void __launch_bounds__(THREADS, 1)
         // ---- M-step (CTA 0), or the counts of the closing round
         if (cta == 0) {
             if (!hist_round) {
-                long long up[8];
+                long long up[12];
+                up[8] = up[9] = up[10] = 0;
                 const int it_now = S.iter;
                 fast_update_step(cluster, S, K, ks, pc, xseq, tol, pull, lg ? up : nullptr);
-                if (lg && it_now == 6) {
+                if (lg && (it_now == 6 || it_now < 2)) {  // update profile of iterations 6, 0 and 1
                     up[7] = clock64();
-                    for (int i = 0; i < 8; ++i) st->logZ[LL_LOG - 32 + i] = up[i] - up[0];
+                    const int at = it_now == 6 ? 32 : it_now == 0 ? 48 : 64;
+                    for (int i = 0; i < 10; ++i) st->logZ[LL_LOG - at + i] = up[i] ? up[i] - up[0] : 0;
+                    st->logZ[LL_LOG - at + 10] = up[10];
+                }
+                if (lg && it_now < LL_LOG - 64 && want_log == 1) {  // (the per-CTA stamps of NNC_LLOYD_LOG=2 share logZ)
+                    long long z = 0;
+                    for (int r = 0; r < R; ++r)
+                        if (S.tab.rJ1[r] != S.tab.rJ2[r]) z += S.rpos[r + 1] - S.rpos[r];
+                    st->logZ[it_now] = z;
+                    st->logG[it_now] = R;
+                    st->logM[it_now] = S.tab.m;
+                    st->logE[it_now] = S.u.up.n_empty;
                 }
             } else {
                 long long *Wd = S.u.up.Wd;

@@ -82,6 +82,7 @@ struct BlockAux {  // shared scratch for visitor epilogues
 // 1.5e-5 wide).
 struct VisitStats {
     static constexpr const char *kName = "np_tree_kernel<VisitStats>";
+    static constexpr int kStageBufs = 3;  // staged tiles in flight + the one being worked on
     static constexpr bool kTileCount = false;
     static constexpr bool kSecondTree = false;
     static constexpr bool kCompact = false;
@@ -136,6 +137,7 @@ struct VisitStats {
 // plain centred squares (nnc_stats second pass, non-speculative prune fallback)
 struct VisitCenSq {
     static constexpr const char *kName = "np_tree_kernel<VisitCenSq>";
+    static constexpr int kStageBufs = 3;  // staged tiles in flight + the one being worked on
     static constexpr bool kTileCount = false;
     static constexpr bool kSecondTree = false;
     static constexpr bool kCompact = false;
@@ -160,6 +162,7 @@ struct VisitCenSq {
 // pass 2 of pruning: centred squares + speculative apply (see file header).
 struct VisitCenSqApply {
     static constexpr const char *kName = "np_tree_kernel<VisitCenSqApply>";
+    static constexpr int kStageBufs = 2;  // staged tiles in flight + the one being worked on
     static constexpr bool kTileCount = false;
     static constexpr bool kSecondTree = false;
     static constexpr bool kCompact = false;
@@ -251,6 +254,7 @@ struct VisitCenSqApply {
 // non-zero elements (the radix-sort key range), non-finite detection (|x| bits >= 0x7f800000).
 struct VisitQuant {
     static constexpr const char *kName = "np_tree_kernel<VisitQuant>";
+    static constexpr int kStageBufs = 2;  // staged tiles in flight + the one being worked on
     static constexpr bool kTileCount = false;
     static constexpr bool kSecondTree = false;
     static constexpr bool kCompact = true;  // the kernel also writes the non-zero elements of every tile to `out`
@@ -323,6 +327,7 @@ struct VisitQuant {
 // plain term = x (re-reduction of single tiles, see VisitApplyQuant)
 struct VisitPlain {
     static constexpr const char *kName = "np_tree_kernel<VisitPlain>";
+    static constexpr int kStageBufs = 3;  // staged tiles in flight + the one being worked on
     static constexpr bool kTileCount = false;
     static constexpr bool kSecondTree = false;
     static constexpr bool kCompact = false;
@@ -357,6 +362,7 @@ static __device__ __noinline__ void band_append(DevScalars *sc, long long *side_
 // second-tree partial; the few listed tiles are re-reduced from the final tensor afterwards (VisitPlain).
 struct VisitApplyQuant {
     static constexpr const char *kName = "np_tree_kernel<VisitApplyQuant>";
+    static constexpr int kStageBufs = 2;  // staged tiles in flight + the one being worked on
     static constexpr bool kTileCount = false;
     static constexpr bool kSecondTree = true;
     static constexpr bool kCompact = true;
@@ -595,15 +601,21 @@ __device__ __forceinline__ float np_node_value(const float *tl, uint32_t gd, int
     if (s == 128 && (o & 127) == 0) {  // the common case: a full, aligned leaf
         const int g = (threadIdx.x >> 3) & 3;
         const float *p = tl + o + j - 8 * g;
+        // row i = st - g: steps 0..2 start the groups one after the other, steps 4..15 are unconditional for every group
+        // (1 <= i <= 15), steps 16..18 let the later groups finish
         val = 0.f;
 #pragma unroll
-        for (int st = 0; st < 19; ++st) {
-            const int i = st - g;
-            if (i >= 0 && i < 16) {
+        for (int st = 0; st < 4; ++st) {
+            if (st >= g) {
                 const float x = f(p[8 * st]);
-                val = i == 0 ? x : fadd(val, x);
+                val = st == g ? x : fadd(val, x);
             }
         }
+#pragma unroll
+        for (int st = 4; st < 16; ++st) val = fadd(val, f(p[8 * st]));
+#pragma unroll
+        for (int st = 16; st < 19; ++st)
+            if (st - g < 16) val = fadd(val, f(p[8 * st]));
         const unsigned gmask = 0xffu << (threadIdx.x & 24);
         val = fadd(val, __shfl_xor_sync(gmask, val, 1));
         val = fadd(val, __shfl_xor_sync(gmask, val, 2));
@@ -629,13 +641,26 @@ __device__ __forceinline__ void np_node_value2(const float *tl, uint32_t gd, int
         const float *p = tl + o + j - 8 * g;
         float a = 0.f, b = 0.f;
 #pragma unroll
-        for (int st = 0; st < 19; ++st) {
-            const int i = st - g;
-            if (i >= 0 && i < 16) {
+        for (int st = 0; st < 4; ++st) {
+            if (st >= g) {
                 const float x = p[8 * st];
                 const float x1 = f1(x), x2 = f2(x);
-                a = i == 0 ? x1 : fadd(a, x1);
-                b = i == 0 ? x2 : fadd(b, x2);
+                a = st == g ? x1 : fadd(a, x1);
+                b = st == g ? x2 : fadd(b, x2);
+            }
+        }
+#pragma unroll
+        for (int st = 4; st < 16; ++st) {
+            const float x = p[8 * st];
+            a = fadd(a, f1(x));
+            b = fadd(b, f2(x));
+        }
+#pragma unroll
+        for (int st = 16; st < 19; ++st) {
+            if (st - g < 16) {
+                const float x = p[8 * st];
+                a = fadd(a, f1(x));
+                b = fadd(b, f2(x));
             }
         }
         const unsigned gmask = 0xffu << (threadIdx.x & 24);
@@ -681,7 +706,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 // kCompact float s_out[2][NP_TILE_MAX]
 template <class V>
 constexpr size_t np_tree_smem() {
-    return sizeof(float) * (2 * (size_t)NP_TILE_MAX + (V::kCompact ? 2 * (size_t)NP_TILE_MAX : 0));
+    return sizeof(float) * ((size_t)V::kStageBufs * NP_TILE_MAX + (V::kCompact ? 2 * (size_t)NP_TILE_MAX : 0));
 }
 
 // a: this rank's shard (elements [shard_begin, ...) of the flattened tensor); tiles [t0, t1) belong to it -- or, with a
@@ -697,10 +722,11 @@ __global__ void __launch_bounds__(NP_THREADS, V::kSecondTree ? 3 : 4) np_tree_ke
     __shared__ unsigned int s_fcnt[2];  // ... of the completed tile in s_out[b], waiting to be flushed to s_base[b]
     __shared__ unsigned long long s_base[2];
     __shared__ int s_dirty[2];
-    __shared__ __align__(8) unsigned long long mbar[2];  // "tile staged" of raw[b]
+    constexpr int NBUF = V::kStageBufs;
+    __shared__ __align__(8) unsigned long long mbar[NBUF];  // "tile staged" of raw[b]
     extern __shared__ __align__(16) unsigned char np_dyn_smem[];
     float(*raw)[NP_TILE_MAX] = reinterpret_cast<float(*)[NP_TILE_MAX]>(np_dyn_smem);
-    float(*s_out)[NP_TILE_MAX] = reinterpret_cast<float(*)[NP_TILE_MAX]>(np_dyn_smem + 2 * sizeof(float) * NP_TILE_MAX);
+    float(*s_out)[NP_TILE_MAX] = reinterpret_cast<float(*)[NP_TILE_MAX]>(np_dyn_smem + NBUF * sizeof(float) * NP_TILE_MAX);
     __shared__ BlockAux aux;
 
     v.begin();
@@ -709,8 +735,8 @@ __global__ void __launch_bounds__(NP_THREADS, V::kSecondTree ? 3 : 4) np_tree_ke
         s_fcnt[threadIdx.x] = 0;
         s_base[threadIdx.x] = 0;
         s_dirty[threadIdx.x] = 0;
-        mbar_init(&mbar[threadIdx.x], 1);
     }
+    if (threadIdx.x < NBUF) mbar_init(&mbar[threadIdx.x], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;
@@ -730,10 +756,14 @@ __global__ void __launch_bounds__(NP_THREADS, V::kSecondTree ? 3 : 4) np_tree_ke
         mbar_expect_tx(&mbar[b], (uint32_t)sz * 4u);
         bulk_copy_g2s(&raw[b][0], src, (uint32_t)sz * 4u, &mbar[b]);
     };
-    if (blockIdx.x < n_mine && warp_id() == 1) issue(blockIdx.x, 0);
-    int buf = 0;
-    uint32_t phase0 = 0, phase1 = 0;  // completed bulk stagings of raw[0] / raw[1] (the parity mbar_wait looks for)
-    for (uint32_t it = blockIdx.x; it < n_mine; it += gridDim.x, buf ^= 1) {
+    // NBUF - 1 tiles ahead: the copies of the next tiles are in flight while this one is visited, summed and folded
+    if (warp_id() == 1)
+        for (int a0 = 0; a0 < NBUF - 1; ++a0)
+            if (blockIdx.x + (uint32_t)a0 * gridDim.x < n_mine) issue(blockIdx.x + (uint32_t)a0 * gridDim.x, a0);
+    int buf = 0;              // parity of the tile: node values, survivor stage, dirty flag
+    int rb = 0;               // staging buffer of the tile
+    uint32_t phase_bits = 0;  // bit b: parity of the next completed bulk staging of raw[b]
+    for (uint32_t it = blockIdx.x; it < n_mine; it += gridDim.x, buf ^= 1, rb = rb + 1 == NBUF ? 0 : rb + 1) {
         const uint32_t t = tile_id(it);
         const int64_t off = desc[t].off - shard_begin;  // offset inside the shard
         const int sz = desc[t].sz;
@@ -741,16 +771,14 @@ __global__ void __launch_bounds__(NP_THREADS, V::kSecondTree ? 3 : 4) np_tree_ke
         const float *src = a + off;
         // ---- the next tile's copies go out first (its buffer was last read before the barrier that ended the previous
         // iteration), then wait for this tile
-        if (it + gridDim.x < n_mine && warp_id() == 1) issue(it + gridDim.x, buf ^ 1);
-        float *tl = raw[buf];
+        {
+            const uint32_t ahead = it + (uint32_t)(NBUF - 1) * gridDim.x;  // goes into the buffer the previous tile used
+            if (ahead < n_mine && warp_id() == 1) issue(ahead, rb == 0 ? NBUF - 1 : rb - 1);
+        }
+        float *tl = raw[rb];
         if (bulk_ok(sz)) {
-            if (buf == 0) {
-                mbar_wait(&mbar[0], phase0 & 1u);
-                ++phase0;
-            } else {
-                mbar_wait(&mbar[1], phase1 & 1u);
-                ++phase1;
-            }
+            mbar_wait(&mbar[rb], (phase_bits >> rb) & 1u);
+            phase_bits ^= 1u << rb;
         } else {  // unaligned tensor or the ragged last tile: ordinary loads into the same padded layout
             for (int i = threadIdx.x; i < sz; i += NP_THREADS) tl[i] = v.load1(src + i);
             __syncthreads();
@@ -891,7 +919,7 @@ __global__ void __launch_bounds__(NP_THREADS, V::kSecondTree ? 3 : 4) np_tree_ke
                 if (xs[r].w != 0.f) *dst++ = xs[r].w;
             }
         }
-        __syncthreads();  // node values, survivor stage and dirty flag of this tile complete; raw[buf ^ 1]'s readers are done
+        __syncthreads();  // node values, survivor stage and dirty flag of this tile complete; the previous tile's staging buffer has no readers left
         if constexpr (V::kSecondTree) {
             // the other buffer's flag: warp 0 read it (fold of the previous tile) before arriving at the barrier above, and
             // the next tile's visit sets it again only after the barrier below
