@@ -1131,6 +1131,20 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         NNC_CUDA(cudaMemcpy(up, st->logZ + LL_LOG - 32, sizeof(long long) * 8, cudaMemcpyDeviceToHost));
         fprintf(stderr, "[nnc lloyd] zone profile (cycles): prefix %lld elements %lld flush %lld\n", zp[1], zp[2], zp[3]);
         fprintf(stderr, "[nnc lloyd] update profile (cycles): safe %lld zero-run %lld per-id+empties %lld reloc %lld average %lld conv %lld end %lld\n", up[1], up[2], up[3], up[4], up[5], up[6], up[7]);
+        {
+            int dbg[8], d2[8];
+            NNC_CUDA(cudaMemcpy(dbg, st->logG + LL_LOG - 8, sizeof(dbg), cudaMemcpyDeviceToHost));
+            NNC_CUDA(cudaMemcpy(d2, st->logG + LL_LOG - 16, sizeof(d2), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[nnc lloyd] zones not evaluated: boundary before the data %d, ragged / unaligned %d, too wide %d | chunk pass saw: two-candidate zones %d, generic zones %d\n",
+                    d2[5], d2[6], d2[7], d2[0], d2[1]);
+            fprintf(stderr, "[nnc lloyd] pair searches: %d zones evaluated, %d zones left to the chunk pass, %d other pairs | E-steps with zs = 0 / 1 / 2: %d %d %d\n",
+                    dbg[7], dbg[6], dbg[5], dbg[4], dbg[3], dbg[2]);
+        }
+        {
+            long long pp[5];
+            NNC_CUDA(cudaMemcpy(pp, st->logZ + LL_LOG - 80, sizeof(pp), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[nnc lloyd] pair search of warp 0 (cycles): located %lld tiles loaded %lld scanned %lld reduced %lld\n", pp[1], pp[2], pp[3], pp[4]);
+        }
         for (int w = 0; w < 2; ++w) {
             NNC_CUDA(cudaMemcpy(up, st->logZ + LL_LOG - 48 - 16 * w, sizeof(up), cudaMemcpyDeviceToHost));
             fprintf(stderr, "[nnc lloyd] update profile of iteration %d (cycles): safe %lld zero-run %lld per-id+empties %lld reloc %lld average %lld conv %lld end %lld | relocation: streams filled %lld pops done %lld (%lld rounds, %lld refills)\n", w, up[1], up[2], up[3], up[4], up[5], up[6], up[7], up[8], up[9], up[10] & 0xffff, up[10] >> 16);

@@ -43,10 +43,11 @@ struct NpWarpScratch {
 // (stream 2 i) and its members at or above it walked from the right end (stream 2 i + 1); along each stream the FarKey
 // decreases strictly.  The first LF_POP_D members of every stream are PRELOADED by all threads at once (one memory round
 // trip), so that the serial pop chain runs out of shared memory; a stream that is drained deeper refills itself (rare).
-constexpr int LF_POP_D = 4;  // preloaded members per stream for m <= LF_KMAX / 2 distinct centroids (2 above)
+constexpr int LF_POP_D = 6;      // preloaded members per stream for m <= LF_KMAX / 2 distinct centroids (3 above)
+constexpr int LF_POP_ENT = 2560;  // preloaded members behind the heads, all streams: [stream * (D - 1) + j] = member j + 1 (key,
+                                  // multiplicity); they live in the chunk-slot array, which is dead during the relocation
 struct PopState {
     uint4 hk[2 * LF_KMAX];    // head of the stream: FarKey (d2, gap, ordx) and the samples left in it (0: stream empty)
-    uint4 ent[3 * LF_KMAX];   // [stream * (D - 1) + j]: preloaded member j + 1 (key, multiplicity)
     int next_off[2 * LF_KMAX];  // entries already walked from the stream's end (where a refill continues); -1: nothing left
     unsigned char head[2 * LF_KMAX], depth[2 * LF_KMAX];  // preloaded members: the one in hk, how many there are
 };
@@ -83,9 +84,16 @@ struct ZoneSlot {               // result of one two-candidate chunk, written by
     unsigned int ends;          // first / last member of a and of b as chunk offsets + 1 (0: none), one byte each
     unsigned int pad;
 };
+struct FusedZone {             // a two-candidate zone evaluated by the warp that searched its two boundaries
+    long long Wb, Sb;           // (count, fixed-point sum) of the members of candidate b
+    unsigned short fa, la, fb, lb;  // first / last member of a and of b as offsets from the zone's first entry, + 1 (0: none)
+    unsigned int tag;           // number of the E-step that wrote it (anything else: the zone is left to the chunk pass)
+    unsigned int pad;
+};
 struct FastZone {
     long long rp[LF_R];  // copy of CTA 0's region positions
     int s_warp[32];
+    unsigned char hd[LF_R];  // the region is a zone that the search pass has evaluated
 };
 struct FastConst {  // read once from the LloydDevice header
     int k, rank, world, max_iter;
@@ -120,7 +128,8 @@ struct FastSmem {
     NpWarpScratch np;         // leaf list of NumPy's pairwise sum over k values (built once) + its scratch
     int np_leaves;
     int cpre[LF_R];           // chunks of the zones before region r (SAFE regions: none); same numbers in every CTA
-    ZoneSlot slot[LF_MAXCH];  // CTA 0: per-chunk results of the two-candidate zones (remote plain stores, one writer each)
+    alignas(16) ZoneSlot slot[LF_MAXCH];  // CTA 0: per-chunk results of the two-candidate zones (remote plain stores, one writer each)
+    FusedZone fz[LF_KMAX];    // CTA 0: zones evaluated in the search pass, by the distinct index of candidate a (one writer each)
     long long Wprev[LF_KMAX], Sprev[LF_KMAX];
     float c_emit[LF_KMAX];
     long long xbuf[2 * LF_KMAX];  // staging of the peer exchange
@@ -271,17 +280,298 @@ __device__ __noinline__ void fast_zone_generic(FastSmem &S, const FastConst &K, 
     }
 }
 
-// returns (uniform over the cluster) whether any chunk took the generic path, i.e. whether CTA 0 has partials to pull
-__device__ bool fast_zone_step(FastSmem &S, FastSmem *S0, const FastConst &K, const SearchConst &C, const float *__restrict__ ks,
-                               int gw, int NW, long long *prof = nullptr) {
+// ---- search pass: one warp takes TWO consecutive region boundaries t1 <= t2 -- in a regular table the two ends of the zone
+// between two adjacent centroids.  A zone holds ~100 sorted entries, so both boundaries lie in the same 512-entry tile (or
+// in two adjacent ones): the tiles are located for both thresholds at once, loaded once, both prefix (position, count,
+// sum) triples come out of the same registers, and the float32 label rule of the zone's entries is evaluated on the spot.
+// That is two memory round trips (tile samples, tiles) for what were two boundary searches of three round trips each, a
+// cluster barrier and a second pass over the zone's entries.  Returns whether the zone was evaluated; if not (zone wider
+// than two tiles, ragged last tile, unaligned arrays) it is left to the chunk pass.
+// the plain search as a CALL: it is the cold path here, and inlined it would share (and blow) the register budget of the
+// pair search
+__device__ __noinline__ void boundary_search_call(const SearchConst &C, float t, long long *out3, long long *hint) {
+    long long pos, cn, sum;
+    warp_boundary_search(C, t, pos, cn, sum, hint);
+    out3[0] = pos;
+    out3[1] = cn;
+    out3[2] = sum;
+}
+struct PairOut {
+    long long pos1, cnt1, sum1, pos2, cnt2, sum2;
+    long long Wb, Sb;
+    unsigned int fa, la, fb, lb;  // offsets from pos1, + 1 (0: none)
+};
+// first tiles whose first key FAILS fl(key - mean) < t1 / < t2 (t1 <= t2), exactly: the shared-memory top level gives a
+// bracket of <= top_step tiles, and ALL tile samples of the bracket are read in one round trip (a boundary moves by tens of
+// tiles per Lloyd iteration on a 2^30-element tensor: a tile remembered from the previous iteration misses most of the time)
+constexpr int LP_PER = 12;  // samples per lane in the final round: brackets of up to 384 tiles
+__device__ __forceinline__ void warp_locate_pair(const SearchConst &C, float t1, float t2, long long &g1, long long &g2) {
+    const int lane = lane_id();
+    const float mean = C.mean;
+    auto bracket = [&](float t, long long &lo, long long &hi) {
+        lo = 0;
+        hi = C.n_tiles;  // the answer lies in [lo, hi]
+        if (C.top) {
+            int a = 0, b = C.top_n;  // first top index failing lies in [a, b]
+            while (a < b) {
+                const int span = b - a, step = (span + 31) >> 5;
+                const int cs = a + lane * step;
+                const int last = min(cs + step, b) - 1;
+                const bool p = cs < b ? (fsub(C.top[last], mean) < t) : false;
+                const int c = __popc(__ballot_sync(0xffffffffu, p));
+                const int na = min(a + c * step, b);
+                if (na >= b) {
+                    a = b;
+                    break;
+                }
+                b = min(na + step, b) - 1;
+                a = na;
+            }
+            if (a == 0) {
+                hi = 0;
+            } else {
+                lo = (long long)(a - 1) * C.top_step + 1;
+                hi = a < C.top_n ? (long long)a * C.top_step : C.n_tiles;
+            }
+        }
+        while (hi - lo > 32 * LP_PER) {  // huge arrays only: 32-ary rounds over the tile samples
+            const long long span = hi - lo, step = (span + 31) >> 5;
+            const long long cs = lo + (long long)lane * step;
+            const long long last = llmin2(cs + step, hi) - 1;
+            const bool p = cs < hi ? (fsub(C.samp[last], mean) < t) : false;
+            const int c = __popc(__ballot_sync(0xffffffffu, p));
+            const long long nlo = llmin2(lo + (long long)c * step, hi);
+            if (nlo >= hi) {
+                lo = hi;
+                break;
+            }
+            hi = llmin2(nlo + step, hi) - 1;
+            lo = nlo;
+        }
+    };
+    long long lo1, hi1, lo2, hi2;
+    bracket(t1, lo1, hi1);
+    bracket(t2, lo2, hi2);
+    float sv[LP_PER];
+    auto load = [&](long long lo, long long hi) {
+#pragma unroll
+        for (int i = 0; i < LP_PER; ++i) {
+            const long long idx = lo + lane + 32 * i;
+            sv[i] = idx < hi ? ld_vol_f1(C.samp + idx) : INFINITY;
+        }
+    };
+    auto count = [&](float t) {
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < LP_PER; ++i) c += fsub(sv[i], mean) < t;  // (the padding +inf never counts)
+        return __reduce_add_sync(0xffffffffu, c);
+    };
+    load(lo1, hi1);
+    g1 = lo1 + count(t1);
+    if (lo2 != lo1 || hi2 != hi1) load(lo2, hi2);  // the thresholds straddle a top-level sample (rare)
+    g2 = lo2 + count(t2);
+}
+
+__device__ __forceinline__ bool warp_pair_search(const SearchConst &C, float t1, float t2, bool want_zone, float va, float na,
+                                                 float vb, float nb, bool b_wins_ties, PairOut &o, long long *pp = nullptr) {
+    const int lane = lane_id();
+    const float mean = C.mean;
+    long long g1, g2;
+    if (pp) pp[0] = clock64();
+    warp_locate_pair(C, t1, t2, g1, g2);
+    if (pp) pp[1] = clock64();
+    // the fast path needs 16-byte aligned arrays and a tile under the first boundary (g1 = 0: it lies before all data)
+    if (!(C.vec_ok && g1 >= 1)) {
+        if (pp) pp[5] = g1 < 1 ? 1 : 2;
+        long long r3[3];
+        boundary_search_call(C, t1, r3, nullptr);
+        o.pos1 = r3[0], o.cnt1 = r3[1], o.sum1 = r3[2];
+        boundary_search_call(C, t2, r3, nullptr);
+        o.pos2 = r3[0], o.cnt2 = r3[1], o.sum2 = r3[2];
+        return false;
+    }
+    float4 a0, a1, a2, a3, b0, b1, b2, b3;
+    uint4 c0 = make_uint4(1u, 1u, 1u, 1u), c1 = c0, c2 = c0, c3 = c0, d0 = c0, d1 = c0, d2 = c0, d3 = c0;
+    long long psA = 0, pcA = 0, psB = 0, pcB = 0;
+    const bool two = g2 != g1;
+    constexpr int LP_MID = 14;  // tiles between A and B that are still walked here (offsets of the ends fit 16 bits)
+    if (g2 - g1 - 1 > LP_MID) want_zone = false;  // an enormous zone: left to the chunk pass
+    if (pp) pp[5] = want_zone ? 0 : 3;
+    const long long baseA = (g1 - 1) * LL_TS, baseB = (g2 - 1) * LL_TS;
+    {
+        // the last tile of the array may be ragged: what lies beyond n_ent reads as (+inf, count 0) -- above every threshold
+        auto ldk = [&](long long i) {
+            if (i + 3 < C.n_ent) return ld_vol_f4(C.ks + i);
+            return make_float4(i < C.n_ent ? C.ks[i] : INFINITY, i + 1 < C.n_ent ? C.ks[i + 1] : INFINITY,
+                               i + 2 < C.n_ent ? C.ks[i + 2] : INFINITY, INFINITY);
+        };
+        auto ldc = [&](long long i) {
+            if (i + 3 < C.n_ent) return ld_vol_u4(C.cnt + i);
+            return make_uint4(i < C.n_ent ? C.cnt[i] : 0u, i + 1 < C.n_ent ? C.cnt[i + 1] : 0u, i + 2 < C.n_ent ? C.cnt[i + 2] : 0u, 0u);
+        };
+        const long long ia = baseA + 4 * lane, ib = baseB + 4 * lane;
+        a0 = ldk(ia);
+        a1 = ldk(ia + 128);
+        a2 = ldk(ia + 256);
+        a3 = ldk(ia + 384);
+        if (two) {
+            b0 = ldk(ib);
+            b1 = ldk(ib + 128);
+            b2 = ldk(ib + 256);
+            b3 = ldk(ib + 384);
+        }
+        if (C.cnt) {
+            c0 = ldc(ia);
+            c1 = ldc(ia + 128);
+            c2 = ldc(ia + 256);
+            c3 = ldc(ia + 384);
+            pcA = ld_vol_s64(C.ctile + (g1 - 1));
+            if (two) {
+                d0 = ldc(ib);
+                d1 = ldc(ib + 128);
+                d2 = ldc(ib + 256);
+                d3 = ldc(ib + 384);
+                pcB = ld_vol_s64(C.ctile + (g2 - 1));
+            }
+        }
+        psA = ld_vol_s64(C.ptile + (g1 - 1));
+        if (two) psB = ld_vol_s64(C.ptile + (g2 - 1));
+    }
+    if (pp) pp[2] = clock64() + (__float_as_int(a0.x) & __float_as_int(a3.w) & (int)psA & 0);  // (after the tile has arrived)
+    int n1 = 0, n2 = 0;
+    long long q1 = 0, q2 = 0, w1 = 0, w2 = 0, Wb = 0, Sb = 0;
+    unsigned int ma = 0, mb = 0;  // per lane: which of its 32 slots (16 of tile A, 16 of tile B) hold a member of a / of b
+    const bool single = !two;
+    auto one = [&](float x, unsigned int c, int slot, bool inB) {
+        const float xc = fsub(x, mean);
+        const long long q = fixed_qf(xc, C.scale_f, C.scale) * (long long)c;
+        const bool lt1 = !inB && xc < t1, lt2 = (inB || single) ? xc < t2 : true;
+        if (lt1) {
+            q1 += q;
+            w1 += c;
+            n1 += 1;
+        }
+        if ((inB || single) && lt2) {
+            q2 += q;
+            w2 += c;
+            n2 += 1;
+        }
+        if (want_zone && !lt1 && lt2) {  // inside the zone: the float32 rule between its two candidates
+            const float m2x = fmul(-2.0f, xc);
+            const float da = skl_dist(m2x, va, na), db = skl_dist(m2x, vb, nb);
+            const bool isb = db < da || (db == da && b_wins_ties);
+            if (isb) {
+                Wb += c;
+                Sb += q;
+                mb |= 1u << slot;
+            } else {
+                ma |= 1u << slot;
+            }
+        }
+    };
+    one(a0.x, c0.x, 0, false); one(a0.y, c0.y, 1, false); one(a0.z, c0.z, 2, false); one(a0.w, c0.w, 3, false);
+    one(a1.x, c1.x, 4, false); one(a1.y, c1.y, 5, false); one(a1.z, c1.z, 6, false); one(a1.w, c1.w, 7, false);
+    one(a2.x, c2.x, 8, false); one(a2.y, c2.y, 9, false); one(a2.z, c2.z, 10, false); one(a2.w, c2.w, 11, false);
+    one(a3.x, c3.x, 12, false); one(a3.y, c3.y, 13, false); one(a3.z, c3.z, 14, false); one(a3.w, c3.w, 15, false);
+    if (two) {
+        one(b0.x, d0.x, 16, true); one(b0.y, d0.y, 17, true); one(b0.z, d0.z, 18, true); one(b0.w, d0.w, 19, true);
+        one(b1.x, d1.x, 20, true); one(b1.y, d1.y, 21, true); one(b1.z, d1.z, 22, true); one(b1.w, d1.w, 23, true);
+        one(b2.x, d2.x, 24, true); one(b2.y, d2.y, 25, true); one(b2.z, d2.z, 26, true); one(b2.w, d2.w, 27, true);
+        one(b3.x, d3.x, 28, true); one(b3.y, d3.y, 29, true); one(b3.z, d3.z, 30, true); one(b3.w, d3.w, 31, true);
+    }
+    if (pp) pp[3] = clock64() + (n1 & 0) + (int)(q1 & 0) + (int)(Sb & 0);
+    n1 = __reduce_add_sync(0xffffffffu, n1);
+    n2 = __reduce_add_sync(0xffffffffu, n2);
+    o.pos1 = baseA + n1;
+    o.sum1 = psA + warp_sum_ll(q1);
+    o.cnt1 = C.cnt ? pcA + warp_sum_ll(w1) : o.pos1;
+    o.pos2 = baseB + n2;
+    o.sum2 = (two ? psB : psA) + warp_sum_ll(q2);
+    o.cnt2 = C.cnt ? (two ? pcB : pcA) + warp_sum_ll(w2) : o.pos2;
+    if (want_zone) {
+        // slot s of this lane is the entry baseA + tile offset + ((s % 16) / 4) * 128 + 4 * lane + (s % 4), tile offset 0
+        // for s < 16 (tile A) and boff for tile B; a lane's slots are in ascending position order, so its first / last
+        // member is the lowest / highest set bit
+        const unsigned boff = (unsigned)(baseB - baseA);
+        auto at = [&](int sl) { return (unsigned)((sl >> 4) ? boff : 0u) + (unsigned)(((sl >> 2) & 3) * 128 + 4 * lane + (sl & 3)); };
+        unsigned fa = ma ? at(__ffs(ma) - 1) : 0xffffffffu, fb = mb ? at(__ffs(mb) - 1) : 0xffffffffu;
+        unsigned la = ma ? at(31 - __clz(ma)) + 1u : 0u, lb = mb ? at(31 - __clz(mb)) + 1u : 0u;
+        // a zone wider than two tiles (centroids close together in a dense part of the data): the tiles between A and B
+        // lie inside the zone entirely; one more round trip each
+        for (long long tm = g1; tm < g2 - 1; ++tm) {
+            const long long bm = tm * LL_TS;
+            const float *pk = C.ks + bm + 4 * lane;
+            const float4 m0 = ld_vol_f4(pk), m1 = ld_vol_f4(pk + 128), m2 = ld_vol_f4(pk + 256), m3 = ld_vol_f4(pk + 384);
+            uint4 e0 = make_uint4(1u, 1u, 1u, 1u), e1 = e0, e2 = e0, e3 = e0;
+            if (C.cnt) {
+                const unsigned int *pc = C.cnt + bm + 4 * lane;
+                e0 = ld_vol_u4(pc), e1 = ld_vol_u4(pc + 128), e2 = ld_vol_u4(pc + 256), e3 = ld_vol_u4(pc + 384);
+            }
+            unsigned int xa = 0, xb = 0;
+            auto mid = [&](float x, unsigned int c, int slot) {
+                const float xc = fsub(x, mean);
+                const float m2x = fmul(-2.0f, xc);
+                const float da = skl_dist(m2x, va, na), db = skl_dist(m2x, vb, nb);
+                if (db < da || (db == da && b_wins_ties)) {
+                    Wb += c;
+                    Sb += fixed_qf(xc, C.scale_f, C.scale) * (long long)c;
+                    xb |= 1u << slot;
+                } else {
+                    xa |= 1u << slot;
+                }
+            };
+            mid(m0.x, e0.x, 0); mid(m0.y, e0.y, 1); mid(m0.z, e0.z, 2); mid(m0.w, e0.w, 3);
+            mid(m1.x, e1.x, 4); mid(m1.y, e1.y, 5); mid(m1.z, e1.z, 6); mid(m1.w, e1.w, 7);
+            mid(m2.x, e2.x, 8); mid(m2.y, e2.y, 9); mid(m2.z, e2.z, 10); mid(m2.w, e2.w, 11);
+            mid(m3.x, e3.x, 12); mid(m3.y, e3.y, 13); mid(m3.z, e3.z, 14); mid(m3.w, e3.w, 15);
+            const unsigned moff = (unsigned)(bm - baseA);
+            auto atm = [&](int sl) { return moff + (unsigned)((sl >> 2) * 128 + 4 * lane + (sl & 3)); };
+            if (xa) {
+                fa = min(fa, atm(__ffs(xa) - 1));
+                la = max(la, atm(31 - __clz(xa)) + 1u);
+            }
+            if (xb) {
+                fb = min(fb, atm(__ffs(xb) - 1));
+                lb = max(lb, atm(31 - __clz(xb)) + 1u);
+            }
+        }
+        o.Wb = warp_sum_ll(Wb);
+        o.Sb = warp_sum_ll(Sb);
+        const unsigned z0 = (unsigned)n1;  // offset of the zone's first entry in tile A
+        const unsigned rfa = __reduce_min_sync(0xffffffffu, fa), rfb = __reduce_min_sync(0xffffffffu, fb);
+        const unsigned rla = __reduce_max_sync(0xffffffffu, la), rlb = __reduce_max_sync(0xffffffffu, lb);
+        o.fa = rfa == 0xffffffffu ? 0u : rfa - z0 + 1u;
+        o.fb = rfb == 0xffffffffu ? 0u : rfb - z0 + 1u;
+        o.la = rla ? rla - z0 : 0u;  // (position + 1) - z0 = offset + 1
+        o.lb = rlb ? rlb - z0 : 0u;
+    }
+    if (pp) pp[4] = clock64() + (int)(o.sum2 & 0);
+    return want_zone;
+}
+
+// returns (uniform over the cluster):
+// 0: the search pass evaluated every non-empty zone, nothing done (and no barrier needed); 1: chunks into CTA 0's slots;
+// 2: some chunks took the generic path, CTA 0 has partials to pull
+__device__ int fast_zone_step(FastSmem &S, FastSmem *S0, const FastConst &K, const SearchConst &C, const float *__restrict__ ks,
+                              int gw, int NW, unsigned int etag, long long *prof = nullptr, int *dbg = nullptr) {
     const int NT = blockDim.x;
     if (prof) prof[0] = clock64();
     FastZone &Z = S.u.zn;
     const RegionTableT<LF_KMAX> &T = S.tab;
     const int R = T.R, tid = threadIdx.x, lane = lane_id();
-    if (R <= 1) return false;
-    for (int r = tid; r <= R; r += NT) Z.rp[r] = S0->rpos[r];
-    __syncthreads();
+    if (R <= 1) return 0;
+    int left = 0;
+    for (int r = tid; r < R; r += NT) {
+        const long long lo = S0->rpos[r], hi = S0->rpos[r + 1];
+        const int J2 = T.rJ2[r], J1 = T.rJ1[r];
+        const bool handled = J1 == J2 + 1 && S0->fz[J2].tag == etag;
+        Z.rp[r] = lo;
+        Z.hd[r] = handled;
+        left |= J1 > J2 && hi > lo && !handled;
+        if (dbg && blockIdx.x == 0 && J1 > J2 && hi > lo && !handled) atomicAdd(&dbg[J1 == J2 + 1 ? 0 : 1], 1);
+    }
+    if (tid == 0) Z.rp[R] = S0->rpos[R];
+    if (!__syncthreads_or(left)) return 0;
     // chunks per zone -> exclusive prefix over the regions (every CTA computes the same numbers)
     int any_generic = 0;
     {
@@ -289,7 +579,7 @@ __device__ bool fast_zone_step(FastSmem &S, FastSmem *S0, const FastConst &K, co
         const int lo = min(R, tid * per), hi = min(R, lo + per);
         int sum = 0;
         for (int r = lo; r < hi; ++r) {
-            const bool zone = T.rJ1[r] > T.rJ2[r];
+            const bool zone = T.rJ1[r] > T.rJ2[r] && !Z.hd[r];
             const long long sz = zone ? Z.rp[r + 1] - Z.rp[r] : 0ll;
             const long long nch = (sz + LF_CH - 1) / LF_CH;
             sum += (int)llmin2(nch, 1ll << 24);
@@ -299,7 +589,7 @@ __device__ bool fast_zone_step(FastSmem &S, FastSmem *S0, const FastConst &K, co
         int run = incl - sum;
         for (int r = lo; r < hi; ++r) {
             S.cpre[r] = run;
-            const bool zone = T.rJ1[r] > T.rJ2[r];
+            const bool zone = T.rJ1[r] > T.rJ2[r] && !Z.hd[r];
             const long long sz = zone ? Z.rp[r + 1] - Z.rp[r] : 0ll;
             run += (int)llmin2((sz + LF_CH - 1) / LF_CH, 1ll << 24);
         }
@@ -387,12 +677,13 @@ __device__ bool fast_zone_step(FastSmem &S, FastSmem *S0, const FastConst &K, co
     }
     if (prof) prof[2] = clock64();
     if (prof) prof[3] = clock64();
-    return any_generic != 0;
+    return any_generic ? 2 : 1;
 }
 
 // CTA 0: per distinct index (count, sum, first / last member) of the ZONE entries -> U.Wd / Sd / first / last, from the chunk
 // slots of the two-candidate zones and, when `pull`, from the generic partials of every CTA (DSMEM loads).
-__device__ void fast_gather_zones(cg::cluster_group &cluster, FastSmem &S, bool pull) {
+__device__ void fast_gather_zones(cg::cluster_group &cluster, FastSmem &S, int zs, unsigned int etag) {
+    const bool pull = zs == 2, chunks = zs != 0;
     FastUpdate &U = S.u.up;
     const RegionTableT<LF_KMAX> &T = S.tab;
     const int NT = blockDim.x, n_cta = (int)cluster.num_blocks(), tid = threadIdx.x, m = T.m, R = T.R;
@@ -405,9 +696,26 @@ __device__ void fast_gather_zones(cg::cluster_group &cluster, FastSmem &S, bool 
     for (int r = tid; r < R; r += NT) {
         const int J2 = T.rJ2[r], J1 = T.rJ1[r];
         if (J1 != J2 + 1) continue;
+        const long long lo = S.rpos[r];
+        if (S.fz[J2].tag == etag) {  // evaluated by the search pass
+            const FusedZone &z = S.fz[J2];
+            U.aW[J2] = (S.rcnt[r + 1] - S.rcnt[r]) - z.Wb;
+            U.aS[J2] = (S.rsum[r + 1] - S.rsum[r]) - z.Sb;
+            U.bW[J1] = z.Wb;
+            U.bS[J1] = z.Sb;
+            if (z.fa) {
+                U.af[J2] = lo + z.fa - 1;
+                U.al[J2] = lo + z.la - 1;
+            }
+            if (z.fb) {
+                U.bf[J1] = lo + z.fb - 1;
+                U.bl[J1] = lo + z.lb - 1;
+            }
+            continue;
+        }
+        if (!chunks) continue;
         const int c0 = S.cpre[r], c1 = min(S.cpre[r + 1], LF_MAXCH);
         if (c0 >= c1) continue;
-        const long long lo = S.rpos[r];
         long long Wb = 0, Sb = 0, Wt = 0, St = 0, fa = 0x7fffffffffffffffll, la = -1, fb = 0x7fffffffffffffffll, lb = -1;
         for (int c = c0; c < c1; ++c) {
             const ZoneSlot &sl = S.slot[c];
@@ -473,6 +781,9 @@ __device__ void fast_gather_zones(cg::cluster_group &cluster, FastSmem &S, bool 
     }
 }
 
+static_assert(sizeof(ZoneSlot) * LF_MAXCH >= sizeof(uint4) * LF_POP_ENT && 2 * LF_KMAX * 2 <= LF_POP_ENT, "PopState entries alias the chunk slots");
+__device__ __forceinline__ uint4 *pop_ent(FastSmem &S) { return reinterpret_cast<uint4 *>(S.slot); }
+
 // relocation: (re)loads up to D members of candidate stream sidx, starting `off` entries from the stream's end (one thread)
 __device__ __noinline__ void pop_fill(FastSmem &S, const FastConst &K, const float *__restrict__ ks, int sidx, int D, int off) {
     FastUpdate &U = S.u.up;
@@ -534,7 +845,7 @@ __device__ __noinline__ void pop_fill(FastSmem &S, const FastConst &K, const flo
                 if (n == 0)
                     P.hk[sidx] = e;
                 else
-                    P.ent[sidx * (D - 1) + n - 1] = e;
+                    pop_ent(S)[sidx * (D - 1) + n - 1] = e;
                 ++n;
             }
             if (ended) break;
@@ -549,10 +860,84 @@ __device__ __noinline__ void pop_fill(FastSmem &S, const FastConst &K, const flo
     P.next_off[sidx] = next;
 }
 
+// relocation: one WARP refills the window of candidate stream sidx from `off` entries behind the stream's end -- 32 entries
+// in one coalesced round trip, every lane checks its entry, the first D members go into the window
+__device__ __noinline__ void pop_refill_warp(FastSmem &S, const FastConst &K, const float *__restrict__ ks, int sidx, int D, int off) {
+    FastUpdate &U = S.u.up;
+    PopState &P = U.pop;
+    const RegionTableT<LF_KMAX> &T = S.tab;
+    const unsigned int *__restrict__ ecnt = K.cnt;
+    const int lane = lane_id();
+    const int i = sidx >> 1;
+    const bool right = sidx & 1;
+    const long long first = U.first[i], last = U.last[i];
+    const float c = T.dv[i], mean = K.mean;
+    int n = 0, next = -1;
+    for (;;) {
+        const long long p = right ? last - off - lane : first + off + lane;
+        const bool inside = p >= first && p <= last;
+        float x = 0.f;
+        unsigned int cn = 1u;
+        if (inside) {
+            x = ld_vol_f1(ks + p);
+            if (ecnt) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(cn) : "l"(ecnt + p));
+        }
+        const float xc = fsub(x, mean);
+        const bool stop = !inside || (right ? !(xc >= c) : !(xc < c));  // the stream ends at the first such entry
+        const unsigned stops = __ballot_sync(0xffffffffu, stop);
+        const int e = stops ? __ffs(stops) - 1 : 32;
+        bool member = false;
+        if (lane < e) {
+            int lo = 0, hi = T.R;  // largest r with rpos[r] <= p
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (S.rpos[mid] <= p)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            const int lab = T.rJ1[lo] == T.rJ2[lo] ? T.rJ1[lo] : zone_argmin(xc, T.dv, T.dcn, T.down, T.rJ2[lo], T.rJ1[lo]);
+            member = lab == i;
+        }
+        const unsigned mem = __ballot_sync(0xffffffffu, member);
+        const int rank = __popc(mem & ((1u << lane) - 1u));
+        if (member && rank < D) {
+            const FarKey key = far_key(xc, c);
+            const uint4 ent = make_uint4(key.d2, key.gap, key.ordx, cn);
+            if (rank == 0)
+                P.hk[sidx] = ent;
+            else
+                pop_ent(S)[sidx * (D - 1) + rank - 1] = ent;
+        }
+        const int found = __popc(mem);
+        n = min(found, D);
+        if (found > D) {  // continue right behind the last member that went into the window
+            const unsigned kept = __fns(mem, 0, D);  // lane of the D-th member
+            next = off + (int)kept + 1;
+            break;
+        }
+        if (e < 32) {
+            next = -1;
+            break;
+        }
+        off += 32;
+        next = off;
+        if (n > 0) break;
+    }
+    if (lane == 0) {
+        if (n == 0) P.hk[sidx] = make_uint4(0u, 0u, 0u, 0u);
+        P.head[sidx] = 0;
+        P.depth[sidx] = (unsigned char)n;
+        P.next_off[sidx] = next;
+    }
+    __syncwarp();
+}
+
 // ---- update step (CTA 0 only; S is its own shared memory): per-cluster counts / sums, label-equality proxy, empty-cluster
 // relocation, averages, centre shift, convergence.  Mirrors update_phase of lloyd.cu statement by statement.
 __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const FastConst &K, const float *__restrict__ ks,
-                                 const PeerComm &pc, unsigned long long &xseq, float tol, bool pull, long long *prof = nullptr) {
+                                 const PeerComm &pc, unsigned long long &xseq, float tol, int zs, unsigned int etag,
+                                 long long *prof = nullptr) {
     FastUpdate &U = S.u.up;
     const int NT = blockDim.x, n_cta = (int)cluster.num_blocks();
     if (prof) prof[0] = clock64();
@@ -562,7 +947,7 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
     const double scale = K.scale;
     const float x0 = fsub(0.f, mean);
     // ---- 1. per distinct index: zone entries (chunk slots, generic partials) + SAFE regions
-    fast_gather_zones(cluster, S, pull);
+    fast_gather_zones(cluster, S, zs, etag);
     if (tid < k) {
         U.W[tid] = 0;
         U.S[tid] = 0;
@@ -648,116 +1033,118 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
     if (prof) prof[3] = clock64();
     if (n_empty > 0) {
         // Candidate streams (PopState).  The farthest remaining sample overall is always at the head of one of the
-        // streams (or is the zero run); pop n_empty times.  The pops are a serial chain and run in ONE warp out of shared
-        // memory: lane l owns the streams l, l + 32, ... and keeps the best of their heads in registers; a pop is a warp
-        // arg-max (four redux operations), the winner's lane advances that stream and rescans its own heads.  Equal
-        // samples (an entry's multiplicity, the zero run) are taken in one pop.
+        // streams (or is the zero run); pop until n_empty samples are taken.  The pops are a serial chain, so a round is
+        // kept short: every thread owns the heads of its streams (one each for m <= NT / 2), a round is a warp arg-max
+        // (four redux operations), one block barrier, and the same arg-max over the warps' winners; the owner of the
+        // winning stream advances it out of the preloaded window, or its WARP refills the window in one coalesced round
+        // trip.  Equal samples (an entry's multiplicity, the zero run) are taken in one round.
         PopState &P = U.pop;
-        const int D = 2 * m * LF_POP_D <= 4 * LF_KMAX ? LF_POP_D : 2;
+        const int D = 2 * m * (LF_POP_D - 1) <= LF_POP_ENT ? LF_POP_D : 3;
         for (int sidx = tid; sidx < 2 * m; sidx += NT) pop_fill(S, K, ks, sidx, D, 0);
-        if (tid == 0) U.winner = 0;  // pops done
         __syncthreads();
         if (prof) prof[8] = clock64();
         int n_rounds = 0, n_refill = 0;
         long long *cand = S.xbuf;  // this rank's list, descending: (d2 << 32 | gap, ordx << 32 | old cluster id + 1)
-        if (warp_id() == 0) {
-            const int lane = lane_id();
-            const int zdi = U.zdi, ZS = 2 * m;  // the zero run is one more stream, owned by lane 0
+        int pop = 0;
+        {
+            const int lane = lane_id(), wid = warp_id(), nw = NT >> 5;
+            const int zdi = U.zdi, ZS = 2 * m;  // the zero run is one more stream
             const FarKey kz = far_key(x0, zdi >= 0 ? T.dv[zdi] : 0.f);
-            long long zero_left = zdi >= 0 ? K.n0 : 0;  // kept by every lane (uniform)
-            uint32_t bd = 0, bg = 0, bo = 0;
-            int bs = -1;
-            // the rescan is on the serial chain: eight heads per step with their loads in flight together and a
-            // comparison TREE (a running arg-max over 16 heads is 16 dependent steps).  An empty head is the key (0, 0, 0),
-            // below every real key (ordx of a finite float is never 0); equal keys keep the lower stream.
-            struct Cand {
-                unsigned long long kk;
-                uint32_t o;
-                int st;
-            };
-            auto pick = [](const Cand &a, const Cand &b) { return (b.kk > a.kk || (b.kk == a.kk && b.o > a.o)) ? b : a; };
-            auto rescan = [&]() {
-                Cand best{0ull, 0u, -1};
-                for (int base = lane; base < 2 * m; base += 256) {
-                    Cand c[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int i = base + 32 * j;
-                        const uint4 e = i < 2 * m ? P.hk[i] : make_uint4(0u, 0u, 0u, 0u);
-                        const bool v = e.w != 0u;
-                        c[j].kk = v ? (((unsigned long long)e.x << 32) | e.y) : 0ull;
-                        c[j].o = v ? e.z : 0u;
-                        c[j].st = v ? i : -1;
-                    }
-                    c[0] = pick(c[0], c[1]);
-                    c[2] = pick(c[2], c[3]);
-                    c[4] = pick(c[4], c[5]);
-                    c[6] = pick(c[6], c[7]);
-                    c[0] = pick(c[0], c[2]);
-                    c[4] = pick(c[4], c[6]);
-                    best = pick(best, pick(c[0], c[4]));
+            long long zero_left = zdi >= 0 ? K.n0 : 0;  // kept by every thread (uniform)
+            // [2][32] winners of the warps and their multiplicities, double buffered (one barrier per round); they live in
+            // the part of the gather scratch that PopState does not cover
+            static_assert(sizeof(PopState) <= 6 * LF_KMAX * sizeof(long long), "bf / bl of the gather scratch must stay free");
+            uint4 *arg = reinterpret_cast<uint4 *>(U.bl);
+            unsigned int *argw = reinterpret_cast<unsigned int *>(U.bf);
+            for (;;) {
+                // best head among this thread's streams (the empty head is the key (0, 0, 0), below every real key)
+                uint32_t bd = 0, bg = 0, bo = 0, bs = 0xffffffffu, bw = 0;
+                for (int i = tid; i < 2 * m; i += NT) {
+                    const uint4 e = P.hk[i];
+                    if (e.w && (bs == 0xffffffffu || e.x > bd || (e.x == bd && (e.y > bg || (e.y == bg && e.z > bo)))))
+                        bd = e.x, bg = e.y, bo = e.z, bs = (uint32_t)i, bw = e.w;
                 }
-                if (lane == 0 && zero_left > 0)
-                    best = pick(best, Cand{((unsigned long long)kz.d2 << 32) | kz.gap, kz.ordx, ZS});
-                bd = (uint32_t)(best.kk >> 32);
-                bg = (uint32_t)best.kk;
-                bo = best.o;
-                bs = best.st;
-            };
-            rescan();
-            int pop = 0;
-            while (pop < n_empty) {
-                if (!__ballot_sync(0xffffffffu, bs >= 0)) break;  // this rank has no sample left
-                bool in = bs >= 0;
-                const uint32_t M1 = __reduce_max_sync(0xffffffffu, in ? bd : 0u);
-                in = in && bd == M1;
-                const uint32_t M2 = __reduce_max_sync(0xffffffffu, in ? bg : 0u);
-                in = in && bg == M2;
-                const uint32_t M3 = __reduce_max_sync(0xffffffffu, in ? bo : 0u);
-                in = in && bo == M3;
-                const int ws = (int)__reduce_min_sync(0xffffffffu, in ? (unsigned)bs : 0xffffffffu);  // equal keys: the lower stream
+                const uint32_t mine = bs;
+                auto warp_best = [&]() {  // arg-max over the lanes; equal keys: the lower stream
+                    bool in = bs != 0xffffffffu;
+                    const uint32_t M1 = __reduce_max_sync(0xffffffffu, in ? bd : 0u);
+                    in = in && bd == M1;
+                    const uint32_t M2 = __reduce_max_sync(0xffffffffu, in ? bg : 0u);
+                    in = in && bg == M2;
+                    const uint32_t M3 = __reduce_max_sync(0xffffffffu, in ? bo : 0u);
+                    in = in && bo == M3;
+                    bs = __reduce_min_sync(0xffffffffu, in ? bs : 0xffffffffu);
+                    bd = M1, bg = M2, bo = M3;
+                };
+                warp_best();
+                uint4 *slot = arg + ((n_rounds & 1) << 5);
+                unsigned int *slotw = argw + ((n_rounds & 1) << 5);
+                if (lane == 0) slot[wid] = make_uint4(bd, bg, bo, bs);
+                if (mine != 0xffffffffu && mine == bs) slotw[wid] = bw;  // (the one lane that owns the warp's winner)
+                __syncthreads();
+                {
+                    const uint4 e = lane < nw ? slot[lane] : make_uint4(0u, 0u, 0u, 0xffffffffu);
+                    bd = e.x, bg = e.y, bo = e.z, bs = e.w;
+                    bw = lane < nw ? slotw[lane] : 0u;
+                }
+                const uint32_t wmine = bs;
+                warp_best();
+                {
+                    const unsigned who = __ballot_sync(0xffffffffu, wmine != 0xffffffffu && wmine == bs);
+                    bw = __shfl_sync(0xffffffffu, bw, who ? __ffs(who) - 1 : 0);
+                }
+                if (zero_left > 0 && (bs == 0xffffffffu || kz.d2 > bd || (kz.d2 == bd && (kz.gap > bg || (kz.gap == bg && kz.ordx > bo)))))
+                    bd = kz.d2, bg = kz.gap, bo = kz.ordx, bs = (uint32_t)ZS;
+                if (bs == 0xffffffffu) break;  // this rank has no sample left
+                const int ws = (int)bs;
                 // samples taken from this entry: all of them, or what is still needed
-                long long avail = ws == ZS ? zero_left : (long long)P.hk[ws].w;
+                const long long avail = ws == ZS ? zero_left : (long long)bw;
                 const int take = (int)llmin2(avail, (long long)(n_empty - pop));
-                const int di = ws == ZS ? zdi : (ws >> 1);
-                const unsigned long long ca = ((unsigned long long)M1 << 32) | M2;
-                const unsigned long long cb = ((unsigned long long)M3 << 32) | (unsigned)(T.down[di] + 1);
-                for (int q = lane; q < take; q += 32) {
-                    cand[2 * (pop + q)] = (long long)ca;
-                    cand[2 * (pop + q) + 1] = (long long)cb;
+                if (wid == 0) {
+                    const int di = ws == ZS ? zdi : (ws >> 1);
+                    const unsigned long long ca = ((unsigned long long)bd << 32) | bg;
+                    const unsigned long long cb = ((unsigned long long)bo << 32) | (unsigned)(T.down[di] + 1);
+                    for (int q = lane; q < take; q += 32) {
+                        cand[2 * (pop + q)] = (long long)ca;
+                        cand[2 * (pop + q) + 1] = (long long)cb;
+                    }
                 }
                 pop += take;
+                ++n_rounds;
                 if (ws == ZS) {
                     zero_left -= take;
-                    if (lane == 0) rescan();
-                } else if (lane == (ws & 31)) {
-                    const unsigned left = P.hk[ws].w - (unsigned)take;
-                    if (left) {
-                        P.hk[ws].w = left;
-                    } else {
-                        const int h = P.head[ws] + 1;
-                        if (h < P.depth[ws]) {
-                            P.hk[ws] = P.ent[ws * (D - 1) + h - 1];
-                            P.head[ws] = (unsigned char)h;
-                        } else if (P.next_off[ws] >= 0) {
-                            pop_fill(S, K, ks, ws, D, P.next_off[ws]);  // drained deeper than the preload: a memory round trip
-                            ++n_refill;
+                } else if (wid == ((ws % NT) >> 5)) {  // the warp of the stream's owner
+                    int refill = 0;
+                    if (lane == (ws & 31)) {
+                        const unsigned left = P.hk[ws].w - (unsigned)take;
+                        if (left) {
+                            P.hk[ws].w = left;
                         } else {
-                            P.hk[ws].w = 0;
+                            const int h = P.head[ws] + 1;
+                            if (h < P.depth[ws]) {
+                                P.hk[ws] = pop_ent(S)[ws * (D - 1) + h - 1];
+                                P.head[ws] = (unsigned char)h;
+                            } else if (P.next_off[ws] >= 0) {
+                                refill = 1;
+                            } else {
+                                P.hk[ws].w = 0;
+                            }
                         }
                     }
-                    rescan();  // only this lane's streams changed
+                    if (__any_sync(0xffffffffu, refill)) {  // drained deeper than the window: one coalesced round trip
+                        pop_refill_warp(S, K, ks, ws, D, P.next_off[ws]);
+                        ++n_refill;
+                    }
                 }
-                __syncwarp();
-                ++n_rounds;
+                if (pop >= n_empty) break;
             }
-            if (lane == 0) U.winner = pop;
-            n_refill = __reduce_add_sync(0xffffffffu, n_refill);
             if (prof) {
                 prof[9] = clock64();
                 prof[10] = n_rounds | ((long long)n_refill << 16);
             }
         }
+        __syncthreads();
+        if (tid == 0) U.winner = pop;
         __syncthreads();
         const int n_done = U.winner;
         if (!pc.enabled) {
@@ -954,6 +1341,8 @@ __global__ void __launch_bounds__(THREADS, 1)
         S.C = Cc;
     }
     for (int i = tid; i < 32 * 10; i += NT) (&S.hint[0][0])[i] = -1;
+    for (int i = tid; i < LF_KMAX; i += NT) S.fz[i].tag = 0u;  // E-steps are numbered from 1
+    if (want_log && cta == 0 && tid < 16) st->logG[LL_LOG - 16 + tid] = 0;
     __syncthreads();
     const FastConst &K = S.K;
     const SearchConst &C = S.C;
@@ -1024,6 +1413,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     // a second copy of the E-step would double the kernel's code, and this kernel is bound by instruction fetch as much as
     // by memory latency (every phase is straight-line code executed once per iteration).
     bool hist_round = false;
+    unsigned int estep = 0;
     for (int it = 0;; ++it) {
         unsigned long long tl[5];
         const bool lg = logger && !hist_round;
@@ -1049,16 +1439,52 @@ __global__ void __launch_bounds__(THREADS, 1)
         const bool stamp = want_log > 1 && tid == 0 && it == 6 && !hist_round;
         unsigned long long *sl = reinterpret_cast<unsigned long long *>(st->logZ) + 8 * cta;  // [cta][8] ns stamps
         if (stamp) sl[0] = now();
+        const unsigned int etag = ++estep;  // this E-step's number (per-thread copy, the same everywhere)
         {
             int trip = 0;
+            const RegionTableT<LF_KMAX> &T = S.tab;
 #pragma unroll 1
-            for (int r = 1 + gw; r < R; r += NW, ++trip) {  // one warp per region boundary
-                long long pos, cn, sum;
-                warp_boundary_search(C, S.tab.rstart[r], pos, cn, sum, &hint[trip < 10 ? trip : 9]);
+            for (int b1 = 1 + 2 * gw; b1 < R; b1 += 2 * NW, ++trip) {  // one warp per PAIR of region boundaries
+                if (b1 + 1 >= R) {  // a last single boundary
+                    long long r3[3];
+                    boundary_search_call(C, T.rstart[b1], r3, &hint[trip < 10 ? trip : 9]);
+                    if (lane_id() == 0) {
+                        S0->rpos[b1] = r3[0];
+                        S0->rcnt[b1] = r3[1];
+                        S0->rsum[b1] = r3[2];
+                    }
+                    continue;
+                }
+                const int J2 = T.rJ2[b1], J1 = T.rJ1[b1];  // region b1 lies between the two boundaries
+                const bool zone2 = J1 == J2 + 1;
+                PairOut o;
+                long long pp[6];
+                const bool prof_pair = lg && tid == 0 && it == 6;
+                const bool done = warp_pair_search(C, T.rstart[b1], T.rstart[b1 + 1], zone2, T.dv[J2], T.dcn[J2], T.dv[J1],
+                                                   T.dcn[J1], T.down[J1] < T.down[J2], o, want_log ? pp : nullptr);
+                if (prof_pair)
+                    for (int i = 0; i < 5; ++i) st->logZ[LL_LOG - 80 + i] = pp[i] - pp[0];
+                if (want_log && lane_id() == 0 && zone2 && !done) atomicAdd(&st->logG[LL_LOG - 12 + (int)pp[5]], 1);
+                if (want_log && lane_id() == 0) atomicAdd(&st->logG[LL_LOG - 1 - (done ? 0 : (zone2 ? 1 : 2))], 1);
                 if (lane_id() == 0) {
-                    S0->rpos[r] = pos;
-                    S0->rcnt[r] = cn;
-                    S0->rsum[r] = sum;
+                    S0->rpos[b1] = o.pos1;
+                    S0->rcnt[b1] = o.cnt1;
+                    S0->rsum[b1] = o.sum1;
+                    S0->rpos[b1 + 1] = o.pos2;
+                    S0->rcnt[b1 + 1] = o.cnt2;
+                    S0->rsum[b1 + 1] = o.sum2;
+                    if (zone2) {
+                        FusedZone *z = &S0->fz[J2];
+                        if (done) {
+                            z->Wb = o.Wb;
+                            z->Sb = o.Sb;
+                            z->fa = (unsigned short)o.fa;
+                            z->la = (unsigned short)o.la;
+                            z->fb = (unsigned short)o.fb;
+                            z->lb = (unsigned short)o.lb;
+                        }
+                        z->tag = done ? etag : 0u;
+                    }
                 }
             }
         }
@@ -1066,15 +1492,16 @@ __global__ void __launch_bounds__(THREADS, 1)
         cluster.sync();
         if (stamp) sl[2] = now();
         if (lg) tl[1] = now();
-        bool pull = false;
+        int zs = 0;
         {
-            long long zp[4];
-            pull = fast_zone_step(S, S0, K, C, ks, gw, NW, lg ? zp : nullptr);
+            long long zp[4] = {0, 0, 0, 0};
+            zs = fast_zone_step(S, S0, K, C, ks, gw, NW, etag, lg ? zp : nullptr, want_log ? &st->logG[LL_LOG - 16] : nullptr);
             if (lg && S.iter == 6)
                 for (int i = 0; i < 4; ++i) st->logZ[LL_LOG - 16 + i] = zp[i] - zp[0];
+            if (stamp) sl[3] = now();
+            if (want_log && cta == 0 && tid == 0) atomicAdd(&st->logG[LL_LOG - 4 - zs], 1);
+            if (zs) cluster.sync();  // (uniform) nothing was left to the chunk pass: CTA 0 already has everything
         }
-        if (stamp) sl[3] = now();
-        cluster.sync();
         if (stamp) sl[4] = now();
         if (lg) tl[2] = now();
         // ---- M-step (CTA 0), or the counts of the closing round
@@ -1083,7 +1510,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 long long up[12];
                 up[8] = up[9] = up[10] = 0;
                 const int it_now = S.iter;
-                fast_update_step(cluster, S, K, ks, pc, xseq, tol, pull, lg ? up : nullptr);
+                fast_update_step(cluster, S, K, ks, pc, xseq, tol, zs, etag, lg ? up : nullptr);
                 if (lg && (it_now == 6 || it_now < 2)) {  // update profile of iterations 6, 0 and 1
                     up[7] = clock64();
                     const int at = it_now == 6 ? 32 : it_now == 0 ? 48 : 64;
@@ -1104,7 +1531,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 const RegionTableT<LF_KMAX> &T = S.tab;
                 const int m = T.m;
                 if (tid < k) st->hist[tid] = 0;
-                fast_gather_zones(cluster, S, pull);
+                fast_gather_zones(cluster, S, zs, etag);
                 __syncthreads();
                 for (int r = tid; r < R; r += NT) {
                     if (T.rJ1[r] != T.rJ2[r]) continue;
