@@ -36,10 +36,6 @@ struct EmitDevice {
     int rid[2 * TB_KMAX + 2];          // cluster id of a SAFE region, -1 for a ZONE
     int zid;                           // cluster id of the value 0.0 (the pruned weights)
     float lut_lo, lut_scale;           // fine bucket(x') = min(int((x' - lut_lo) * lut_scale), EM_FINE - 1)
-    alignas(16) uint32_t lut_cnt[EM_LUT];  // boundaries per coarse bucket (scratch of the table kernel)
-    alignas(16) uint16_t lut_rlo[EM_LUT];  // region of the first x' of every coarse bucket (scratch)
-    alignas(16) uint16_t lut_did[EM_LUT];  // dense index of a bucket that holds boundaries (scratch)
-    alignas(16) uint32_t sub_cnt[EM_DMAX * EM_SUB];
     alignas(16) uint16_t lut[EM_LUT];
     alignas(16) uint16_t lut2[EM_DMAX * EM_SUB];
 };
@@ -62,18 +58,39 @@ __device__ __forceinline__ int region_from(const float *s_start, int R, int r0, 
     return r;
 }
 
+// One CTA; every working array lives in shared memory (as global-memory arrays the dependent look-ups of this kernel -- a
+// chain of ~50 round trips -- cost 86 us, on the critical path between the Lloyd loop and the emission pass)
+struct EmitTabSmem {
+    TableScratch S;
+    RegionTable T;
+    uint32_t scan[32];
+    int rid[2 * TB_KMAX + 2];
+    uint32_t cnt[EM_LUT];  // boundaries per coarse bucket; afterwards per fine bucket of the buckets with a table
+    uint16_t rlo[EM_LUT];  // region of the first x' of every coarse bucket
+    uint16_t did[EM_LUT];  // dense index of a bucket that holds boundaries
+    float c[TB_KMAX];
+};
+static_assert(EM_DMAX * EM_SUB <= EM_LUT, "the fine counts reuse the coarse count array");
+static_assert(sizeof(EmitTabSmem) <= 227 * 1024, "EmitTabSmem must fit the shared memory a CTA can opt into");
+
 __global__ void __launch_bounds__(TB_THREADS) emit_table_kernel(EmitDevice *ed, int k, float xabs_max, float mean, float lut_lo,
                                                                 float lut_scale) {
-    __shared__ TableScratch S;
-    __shared__ uint32_t s_scan[32];
-    build_region_table(ed->c, k, xabs_max, &ed->tab, S);
-    const RegionTable &T = ed->tab;
-    const int R = T.R, tid = threadIdx.x;
-    for (int r = tid; r < R; r += TB_THREADS) ed->rid[r] = T.rJ1[r] == T.rJ2[r] ? T.down[T.rJ1[r]] : -1;
-    for (int b = tid; b < EM_LUT; b += TB_THREADS) ed->lut_cnt[b] = 0;
-    for (int i = tid; i < EM_DMAX * EM_SUB; i += TB_THREADS) ed->sub_cnt[i] = 0;
+    extern __shared__ __align__(16) unsigned char tab_smem_raw[];
+    EmitTabSmem &M = *reinterpret_cast<EmitTabSmem *>(tab_smem_raw);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < k; i += TB_THREADS) M.c[i] = ed->c[i];
     __syncthreads();
-    for (int r = 1 + tid; r < R; r += TB_THREADS) atomicAdd(&ed->lut_cnt[lut_fine_clamped(T.rstart[r], lut_lo, lut_scale) / EM_SUB], 1u);
+    build_region_table(M.c, k, xabs_max, &M.T, M.S);
+    const RegionTable &T = M.T;
+    const int R = T.R;
+    for (int r = tid; r < R; r += TB_THREADS) {
+        const int id = T.rJ1[r] == T.rJ2[r] ? T.down[T.rJ1[r]] : -1;
+        M.rid[r] = id;
+        ed->rid[r] = id;
+    }
+    for (int b = tid; b < EM_LUT; b += TB_THREADS) M.cnt[b] = 0;
+    __syncthreads();
+    for (int r = 1 + tid; r < R; r += TB_THREADS) atomicAdd(&M.cnt[lut_fine_clamped(T.rstart[r], lut_lo, lut_scale) / EM_SUB], 1u);
     __syncthreads();
     // exclusive scans over the coarse buckets: boundaries before the bucket (-> region of its first x') and
     // buckets holding boundaries before it (-> dense index)
@@ -81,51 +98,73 @@ __global__ void __launch_bounds__(TB_THREADS) emit_table_kernel(EmitDevice *ed, 
     uint32_t loc[PER], sum = 0, dsum = 0;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
-        loc[i] = ed->lut_cnt[tid * PER + i];
+        loc[i] = M.cnt[tid * PER + i];
         sum += loc[i];
         dsum += loc[i] != 0;
     }
-    uint32_t incl = block_scan_incl<uint32_t>(sum, [](uint32_t a, uint32_t b) { return a + b; }, s_scan);
-    uint32_t dincl = block_scan_incl<uint32_t>(dsum, [](uint32_t a, uint32_t b) { return a + b; }, s_scan);
+    uint32_t incl = block_scan_incl<uint32_t>(sum, [](uint32_t a, uint32_t b) { return a + b; }, M.scan);
+    uint32_t dincl = block_scan_incl<uint32_t>(dsum, [](uint32_t a, uint32_t b) { return a + b; }, M.scan);
     uint32_t run = incl - sum, drun = dincl - dsum;
+    __syncthreads();  // every thread has its counts in registers: the count array becomes the fine counts
+    alignas(16) uint16_t ent[PER];
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         const int b = tid * PER + i;
-        const int rid = ed->rid[run];
+        const int rid = M.rid[run];
         uint32_t e;
         if (loc[i] == 0)
             e = rid >= 0 ? (uint32_t)rid : (EM_SLOW | run);
         else
             e = drun < (uint32_t)EM_DMAX ? (EM_L2 | drun) : (EM_SLOW | run);
-        ed->lut[b] = (uint16_t)e;
-        ed->lut_rlo[b] = (uint16_t)run;
-        ed->lut_did[b] = (uint16_t)(loc[i] != 0 && drun < (uint32_t)EM_DMAX ? drun : 0xffffu);
+        ent[i] = (uint16_t)e;
+        M.rlo[b] = (uint16_t)run;
+        M.did[b] = (uint16_t)(loc[i] != 0 && drun < (uint32_t)EM_DMAX ? drun : 0xffffu);
+        M.cnt[b] = 0;  // (b < EM_DMAX * EM_SUB <= EM_LUT covers the fine counts)
         run += loc[i];
         drun += loc[i] != 0;
+    }
+    {  // this thread's PER consecutive entries in one go
+        static_assert(PER * sizeof(uint16_t) % 16 == 0, "vector store of the LUT entries");
+        uint4 *dst = reinterpret_cast<uint4 *>(ed->lut + tid * PER);
+        const uint4 *src = reinterpret_cast<const uint4 *>(ent);
+#pragma unroll
+        for (int i = 0; i < (int)(PER * sizeof(uint16_t) / 16); ++i) dst[i] = src[i];
     }
     __syncthreads();
     // second level: boundaries per fine bucket of the buckets that have a table
     for (int r = 1 + tid; r < R; r += TB_THREADS) {
         const int f = lut_fine_clamped(T.rstart[r], lut_lo, lut_scale);
-        const uint32_t did = ed->lut_did[f / EM_SUB];
-        if (did != 0xffffu) atomicAdd(&ed->sub_cnt[did * EM_SUB + (f % EM_SUB)], 1u);
+        const uint32_t did = M.did[f / EM_SUB];
+        if (did != 0xffffu) atomicAdd(&M.cnt[did * EM_SUB + (f % EM_SUB)], 1u);
     }
     __syncthreads();
     for (int b = tid; b < EM_LUT; b += TB_THREADS) {
-        const uint32_t did = ed->lut_did[b];
+        const uint32_t did = M.did[b];
         if (did == 0xffffu) continue;
-        uint32_t r = ed->lut_rlo[b];
+        uint32_t r = M.rlo[b];
         for (int f = 0; f < EM_SUB; ++f) {
-            const uint32_t c = ed->sub_cnt[did * EM_SUB + f];
-            const int rid = ed->rid[r];
+            const uint32_t c = M.cnt[did * EM_SUB + f];
+            const int rid = M.rid[r];
             ed->lut2[did * EM_SUB + f] = (uint16_t)((c == 0 && rid >= 0) ? (uint32_t)rid : (EM_SLOW | r));
             r += c;
         }
     }
+    {  // the table itself, for the emission kernel
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&M.T);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&ed->tab);
+        for (int i = tid; i < (int)(sizeof(RegionTable) / 4); i += TB_THREADS) dst[i] = src[i];
+    }
     if (tid == 0) {  // label of the pruned weights (value 0.0)
         const float x0 = fsub(0.f, mean);
-        int r = 0;
-        while (r + 1 < R && T.rstart[r + 1] <= x0) ++r;
+        int lo = 0, hi = R;  // largest r with rstart[r] <= x0 (rstart[0] = -inf)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (T.rstart[mid] <= x0)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const int r = lo;
         ed->zid = T.rJ1[r] == T.rJ2[r] ? T.down[T.rJ1[r]] : T.down[zone_argmin(x0, T.dv, T.dcn, T.down, T.rJ2[r], T.rJ1[r])];
         ed->lut_lo = lut_lo;
         ed->lut_scale = lut_scale;
@@ -390,7 +429,8 @@ void emit_device(nnc_ctx *ctx, const float *d_w, int64_t n, const float *h_centr
     volatile float span = xhi - xlo;
     float lut_scale = span > 0.f ? (float)((double)EM_FINE / (double)span * (1.0 - 1e-6)) : 0.f;
     if (!isfinite(lut_scale)) lut_scale = 0.f;
-    NNC_LAUNCH(ctx, emit_table_kernel, 1, TB_THREADS, 0, ed, k, xabs, mean, xlo, lut_scale);
+    func_dyn_smem(ctx, (const void *)emit_table_kernel, sizeof(EmitTabSmem));
+    NNC_LAUNCH(ctx, emit_table_kernel, 1, TB_THREADS, sizeof(EmitTabSmem), ed, k, xabs, mean, xlo, lut_scale);
     const bool vec = ((reinterpret_cast<uintptr_t>(d_w) & 15u) == 0) &&
                      (!d_labels || (reinterpret_cast<uintptr_t>(d_labels) & 15u) == 0) &&
                      (!d_ris || (reinterpret_cast<uintptr_t>(d_ris) & 15u) == 0) &&

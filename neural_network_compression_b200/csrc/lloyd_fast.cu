@@ -999,7 +999,7 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
             S.xbuf[m + tid] = U.Sd[tid];
         }
         __syncthreads();
-        if (!peer_allreduce_sum(pc, S.xbuf, 2 * m, ++xseq) && tid == 0) S.comm_error = 1;
+        if (!peer_allreduce_sum_tagged(pc, S.xbuf, 2 * m, ++xseq) && tid == 0) S.comm_error = 1;
         if (tid < m) {
             U.Wd[tid] = S.xbuf[tid];
             U.Sd[tid] = S.xbuf[m + tid];
@@ -1380,7 +1380,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
         __syncthreads();
         if (pc.enabled) {
-            if (!peer_allreduce_sum(pc, S.xbuf, 3, ++xseq) && tid == 0) S.comm_error = 1;
+            if (!peer_allreduce_sum_tagged(pc, S.xbuf, 3, ++xseq) && tid == 0) S.comm_error = 1;
         }
         if (tid == 0) {
             const __int128 s1 = (__int128)S.xbuf[0];
@@ -1546,7 +1546,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                     __syncthreads();
                     if (tid < m) S.xbuf[T.down[tid]] = Wd[tid];
                     __syncthreads();
-                    if (!peer_allreduce_sum(pc, S.xbuf, k, ++xseq) && tid == 0) st->pad2 = 1;
+                    if (!peer_allreduce_sum_tagged(pc, S.xbuf, k, ++xseq) && tid == 0) st->pad2 = 1;
                     if (tid < k) st->hist[tid] = S.xbuf[tid];
                 } else if (tid < m) {
                     st->hist[T.down[tid]] = Wd[tid];

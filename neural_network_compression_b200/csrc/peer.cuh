@@ -1,7 +1,8 @@
 // peer.cuh -- in-kernel exchange between the ranks of one box over NVLink / NVSwitch peer memory.
 //
 // Every rank owns a "mailbox" in its own HBM, IPC-mapped by all the other ranks:
-//     data  [2 parities][world senders][words]      flags [2 parities][world senders]
+//     data  [2 parities][world senders][words]      flags [2 parities][world senders]      counter
+//     tagged data [2 parities][world senders][words]   (slots of the tagged exchange: they only ever hold tagged words)
 // An exchange with sequence number seq: each rank stores its vector into slot [seq & 1][rank] of EVERY mailbox
 // (plain 8-byte stores through the peer mapping), fences, then raises flag [seq & 1][rank] = seq everywhere; it
 // then waits until all the flags of its OWN mailbox have reached seq and reads the world vectors locally.  Sums
@@ -28,7 +29,7 @@ struct PeerComm {
 };
 
 __host__ __device__ inline size_t peer_mailbox_bytes(int world) {
-    return sizeof(unsigned long long) * (2 * (size_t)world * PEER_WORDS + 2 * (size_t)world * 16 + 16);
+    return sizeof(unsigned long long) * (4 * (size_t)world * PEER_WORDS + 2 * (size_t)world * 16 + 16);
 }
 // number of exchanges this rank has executed (its own mailbox; read at kernel start, written back at kernel end)
 __device__ __forceinline__ unsigned long long *peer_counter(const PeerComm &pc) {
@@ -36,6 +37,9 @@ __device__ __forceinline__ unsigned long long *peer_counter(const PeerComm &pc) 
 }
 __device__ __forceinline__ unsigned long long *peer_slot(unsigned long long *mail, int world, int parity, int sender) {
     return mail + ((size_t)parity * world + sender) * PEER_WORDS;
+}
+__device__ __forceinline__ unsigned long long *peer_slot_tagged(unsigned long long *mail, int world, int parity, int sender) {
+    return mail + 2 * (size_t)world * PEER_WORDS + 2 * (size_t)world * 16 + 16 + ((size_t)parity * world + sender) * PEER_WORDS;
 }
 __device__ __forceinline__ unsigned long long *peer_flag(unsigned long long *mail, int world, int parity, int sender) {
     return mail + 2 * (size_t)world * PEER_WORDS + ((size_t)parity * world + sender) * 16;  // one 128-byte line each
@@ -96,6 +100,97 @@ __device__ inline bool peer_allreduce_sum(const PeerComm &pc, long long *data, i
     }
     __syncthreads();
     return ok;
+}
+
+// all-reduce (sum, rank order) of data[0, count), count <= PEER_WORDS / 2, with the sequence number travelling INSIDE the
+// data: every 64-bit value goes out as two 8-byte words (tag | low half, tag | high half), tag = the low bits of seq with
+// the top bit set (never the 0 of a fresh mailbox).  An 8-byte store is single-copy atomic, so a word that carries the
+// right tag carries its payload: no fence between data and flag, no flag -- one NVLink one-way latency per exchange
+// instead of store / system fence / flag / poll / read.  Its slots are separate from the flagged exchange's (a stale
+// untagged word must never be taken for a tagged one); parity rule and sequence counter are shared with it (a rank can be
+// at most one exchange ahead of the slowest one).
+__device__ __forceinline__ unsigned long long peer_tag(unsigned long long seq) { return ((seq & 0x7fffffffull) | 0x80000000ull) << 32; }
+// sends data[0, count) of this rank as tagged words to every mailbox (all threads of one CTA)
+__device__ __forceinline__ void peer_send_tagged(const PeerComm &pc, const unsigned long long *data, int count, unsigned long long seq) {
+    const int parity = (int)(seq & 1ull);
+    const unsigned long long tag = peer_tag(seq);
+    for (int p = 0; p < pc.world; ++p) {
+        unsigned long long *dst = peer_slot_tagged(pc.mail[p], pc.world, parity, pc.rank);
+        for (int i = threadIdx.x; i < count; i += blockDim.x) {
+            const unsigned long long v = data[i];
+            st_sys_u64(dst + 2 * i, tag | (v & 0xffffffffull));
+            st_sys_u64(dst + 2 * i + 1, tag | (v >> 32));
+        }
+    }
+}
+// value i of the senders g .. g + 3 (those below world), polled out of this rank's own mailbox until all have arrived;
+// the loads of the four senders are in flight together.  false: timed out.
+__device__ __forceinline__ bool peer_poll4_tagged(const PeerComm &pc, unsigned long long seq, int i, int g, unsigned long long *vals) {
+    const int parity = (int)(seq & 1ull);
+    const unsigned long long tag = peer_tag(seq);
+    unsigned long long lo[4], hi[4];
+    unsigned pending = (1u << min(4, pc.world - g)) - 1u;
+    long long spins = 0;
+    while (pending) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (pending >> r & 1u) {
+                const unsigned long long *src = peer_slot_tagged(pc.mail[pc.rank], pc.world, parity, g + r) + 2 * i;
+                lo[r] = ld_sys_u64(src);
+                hi[r] = ld_sys_u64(src + 1);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if ((pending >> r & 1u) && (lo[r] & 0xffffffff00000000ull) == tag && (hi[r] & 0xffffffff00000000ull) == tag) {
+                pending &= ~(1u << r);
+                vals[r] = (hi[r] << 32) | (lo[r] & 0xffffffffull);
+            }
+        if (pending && ++spins > (1ll << 24)) return false;  // ~ seconds: give up instead of hanging the device
+    }
+    return true;
+}
+
+__device__ inline bool peer_allreduce_sum_tagged(const PeerComm &pc, long long *data, int count, unsigned long long seq) {
+    __shared__ int s_ok_t;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) s_ok_t = 1;
+    peer_send_tagged(pc, reinterpret_cast<const unsigned long long *>(data), count, seq);
+    __syncthreads();  // everybody has read data[] (it is overwritten below), s_ok_t is set
+    for (int i = tid; i < count; i += nt) {
+        long long sum = 0;
+        for (int g = 0; g < pc.world; g += 4) {
+            unsigned long long v[4] = {0ull, 0ull, 0ull, 0ull};
+            if (!peer_poll4_tagged(pc, seq, i, g, v)) s_ok_t = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (g + r < pc.world) sum += (long long)v[r];  // rank order
+        }
+        data[i] = sum;
+    }
+    __syncthreads();
+    return s_ok_t != 0;
+}
+
+// all-gather with tagged words: out[r * stride + i] = rank r's data[i], i < count <= PEER_WORDS / 2 (out: any memory)
+__device__ inline bool peer_allgather_tagged(const PeerComm &pc, const unsigned long long *data, int count, unsigned long long *out,
+                                             size_t stride, unsigned long long seq) {
+    __shared__ int s_ok_g;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) s_ok_g = 1;
+    peer_send_tagged(pc, data, count, seq);
+    __syncthreads();
+    for (int i = tid; i < count; i += nt) {
+        for (int g = 0; g < pc.world; g += 4) {
+            unsigned long long v[4] = {0ull, 0ull, 0ull, 0ull};
+            if (!peer_poll4_tagged(pc, seq, i, g, v)) s_ok_g = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (g + r < pc.world) out[(size_t)(g + r) * stride + i] = v[r];
+        }
+    }
+    __syncthreads();
+    return s_ok_g != 0;
 }
 
 // all-gather: out[r * stride + i] = rank r's data[i], i < count

@@ -1322,7 +1322,7 @@ __global__ void __launch_bounds__(1024) np_final_peer_kernel(float *local, uint3
     }
     __syncthreads();
     unsigned long long xseq = *peer_counter(pc);
-    const bool ok = peer_allgather(pc, words, EXW_COUNT, gathered, EXW_COUNT, ++xseq);
+    const bool ok = peer_allgather_tagged(pc, words, EXW_COUNT, gathered, EXW_COUNT, ++xseq);
     if (threadIdx.x == 0) {
         *peer_counter(pc) = xseq;
         if (!ok) *comm_error = 1;
