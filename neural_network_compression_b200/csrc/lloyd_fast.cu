@@ -130,6 +130,7 @@ struct FastSmem {
     int cpre[LF_R];           // chunks of the zones before region r (SAFE regions: none); same numbers in every CTA
     alignas(16) ZoneSlot slot[LF_MAXCH];  // CTA 0: per-chunk results of the two-candidate zones (remote plain stores, one writer each)
     FusedZone fz[LF_KMAX];    // CTA 0: zones evaluated in the search pass, by the distinct index of candidate a (one writer each)
+    unsigned int zflag;       // CTA 0: (E-step number << 1) | "a non-empty zone is left to the chunk pass"
     long long Wprev[LF_KMAX], Sprev[LF_KMAX];
     float c_emit[LF_KMAX];
     long long xbuf[2 * LF_KMAX];  // staging of the peer exchange
@@ -179,7 +180,8 @@ __device__ float np_pairwise_warp(const float *a, int n, NpWarpScratch &W, int n
         if (sz >= 8) {
             r = a[o + j];
             const int full = sz - (sz % 8);
-            for (int i = 8; i < full; i += 8) r = fadd(r, a[o + i + j]);
+#pragma unroll 8
+            for (int i = 8; i < full; i += 8) r = fadd(r, a[o + i + j]);  // (unrolled: the loads run ahead of the add chain)
         }
         r = fadd(r, __shfl_xor_sync(0xffffffffu, r, 1));
         r = fadd(r, __shfl_xor_sync(0xffffffffu, r, 2));
@@ -560,18 +562,41 @@ __device__ int fast_zone_step(FastSmem &S, FastSmem *S0, const FastConst &K, con
     const RegionTableT<LF_KMAX> &T = S.tab;
     const int R = T.R, tid = threadIdx.x, lane = lane_id();
     if (R <= 1) return 0;
-    int left = 0;
+    // Is any non-empty zone left?  CTA 0 looks (its own shared memory) and publishes the answer; the other CTAs poll ONE
+    // word of it.  (With every CTA reading the positions and tags of all regions out of CTA 0, 23 K remote loads converged
+    // on one SM in every iteration: 6 us per CTA, and CTA 0's own update step ran against that traffic.)
+    if (&S == S0) {
+        int left = 0;
+        for (int r = tid; r < R; r += NT) {
+            const int J2 = T.rJ2[r], J1 = T.rJ1[r];
+            const bool open = J1 > J2 && S.rpos[r + 1] > S.rpos[r] && !(J1 == J2 + 1 && S.fz[J2].tag == etag);
+            left |= open;
+            if (dbg && open) atomicAdd(&dbg[J1 == J2 + 1 ? 0 : 1], 1);
+        }
+        left = __syncthreads_or(left);
+        if (tid == 0) *(volatile unsigned int *)&S.zflag = (etag << 1) | (unsigned)(left != 0);
+        if (!left) return 0;
+    } else {
+        if (tid == 0) {
+            unsigned int v;
+            long long spins = 0;
+            do {
+                v = *(volatile unsigned int *)&S0->zflag;
+            } while ((v >> 1) != (etag & 0x7fffffffu) && ++spins < (1ll << 26));
+            Z.s_warp[0] = (int)(v & 1u);
+        }
+        __syncthreads();
+        const int left = Z.s_warp[0];
+        __syncthreads();
+        if (!left) return 0;
+    }
     for (int r = tid; r < R; r += NT) {
-        const long long lo = S0->rpos[r], hi = S0->rpos[r + 1];
         const int J2 = T.rJ2[r], J1 = T.rJ1[r];
-        const bool handled = J1 == J2 + 1 && S0->fz[J2].tag == etag;
-        Z.rp[r] = lo;
-        Z.hd[r] = handled;
-        left |= J1 > J2 && hi > lo && !handled;
-        if (dbg && blockIdx.x == 0 && J1 > J2 && hi > lo && !handled) atomicAdd(&dbg[J1 == J2 + 1 ? 0 : 1], 1);
+        Z.rp[r] = S0->rpos[r];
+        Z.hd[r] = J1 == J2 + 1 && S0->fz[J2].tag == etag;
     }
     if (tid == 0) Z.rp[R] = S0->rpos[R];
-    if (!__syncthreads_or(left)) return 0;
+    __syncthreads();
     // chunks per zone -> exclusive prefix over the regions (every CTA computes the same numbers)
     int any_generic = 0;
     {
@@ -744,36 +769,39 @@ __device__ void fast_gather_zones(cg::cluster_group &cluster, FastSmem &S, int z
         U.bl[J1] = lb;
     }
     __syncthreads();
-    for (int i = tid; i < m; i += NT) {
-        long long w = U.aW[i] + U.bW[i], sm = U.aS[i] + U.bS[i];
-        long long mn = llmin2(U.af[i], U.bf[i]), mx = llmax2(U.al[i], U.bl[i]);
-        if (pull) {  // generic chunks: every CTA's local partials, one array at a time with its loads in flight together
-            long long v[LF_CL_MAX];
+    if (pull) {
+        // generic chunks: every CTA's local partials.  16 consecutive lanes take one distinct index, one CTA each (four
+        // remote loads in flight per lane), and fold over the CTAs with shuffles.
+        static_assert(LF_CL_MAX == 16, "the fold below is over 16 lanes");
+        for (int base = 0; base < m * LF_CL_MAX; base += NT) {  // (NT is a multiple of 32: whole warps stay together)
+            const int idx = base + tid, cta = idx & (LF_CL_MAX - 1), i = idx >> 4;
+            long long w = 0, sm = 0, mn = 0x7fffffffffffffffll, mx = -1;
+            if (i < m && cta < n_cta) {
+                const volatile FastSmem *Sr = (const volatile FastSmem *)cluster.map_shared_rank(&S, cta);
+                w = (long long)Sr->zW[i];
+                sm = Sr->zS[i];
+                mn = Sr->zmin[i];
+                mx = Sr->zmax[i];
+            }
 #pragma unroll
-            for (int cta = 0; cta < LF_CL_MAX; ++cta)
-                if (cta < n_cta) v[cta] = (long long)((const volatile FastSmem *)cluster.map_shared_rank(&S, cta))->zW[i];
-#pragma unroll
-            for (int cta = 0; cta < LF_CL_MAX; ++cta)
-                if (cta < n_cta) w += v[cta];
-#pragma unroll
-            for (int cta = 0; cta < LF_CL_MAX; ++cta)
-                if (cta < n_cta) v[cta] = ((const volatile FastSmem *)cluster.map_shared_rank(&S, cta))->zS[i];
-#pragma unroll
-            for (int cta = 0; cta < LF_CL_MAX; ++cta)
-                if (cta < n_cta) sm += v[cta];
-#pragma unroll
-            for (int cta = 0; cta < LF_CL_MAX; ++cta)
-                if (cta < n_cta) v[cta] = ((const volatile FastSmem *)cluster.map_shared_rank(&S, cta))->zmin[i];
-#pragma unroll
-            for (int cta = 0; cta < LF_CL_MAX; ++cta)
-                if (cta < n_cta) mn = llmin2(mn, v[cta]);
-#pragma unroll
-            for (int cta = 0; cta < LF_CL_MAX; ++cta)
-                if (cta < n_cta) v[cta] = ((const volatile FastSmem *)cluster.map_shared_rank(&S, cta))->zmax[i];
-#pragma unroll
-            for (int cta = 0; cta < LF_CL_MAX; ++cta)
-                if (cta < n_cta) mx = llmax2(mx, v[cta]);
+            for (int o = 1; o < LF_CL_MAX; o <<= 1) {
+                w += __shfl_xor_sync(0xffffffffu, w, o);
+                sm += __shfl_xor_sync(0xffffffffu, sm, o);
+                mn = llmin2(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                mx = llmax2(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+            if (i < m && cta == 0) {  // (a distinct index is folded by exactly one group of lanes)
+                U.aW[i] += w;
+                U.aS[i] += sm;
+                U.af[i] = llmin2(U.af[i], mn);
+                U.al[i] = llmax2(U.al[i], mx);
+            }
         }
+        __syncthreads();
+    }
+    for (int i = tid; i < m; i += NT) {
+        const long long w = U.aW[i] + U.bW[i], sm = U.aS[i] + U.bS[i];
+        const long long mn = llmin2(U.af[i], U.bf[i]), mx = llmax2(U.al[i], U.bl[i]);
         U.Wd[i] = w;
         U.Sd[i] = sm;
         U.first[i] = mn;
@@ -1342,6 +1370,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
     for (int i = tid; i < 32 * 10; i += NT) (&S.hint[0][0])[i] = -1;
     for (int i = tid; i < LF_KMAX; i += NT) S.fz[i].tag = 0u;  // E-steps are numbered from 1
+    if (tid == 0) S.zflag = 0u;
     if (want_log && cta == 0 && tid < 16) st->logG[LL_LOG - 16 + tid] = 0;
     __syncthreads();
     const FastConst &K = S.K;
@@ -1444,7 +1473,10 @@ __global__ void __launch_bounds__(THREADS, 1)
             int trip = 0;
             const RegionTableT<LF_KMAX> &T = S.tab;
 #pragma unroll 1
-            for (int b1 = 1 + 2 * gw; b1 < R; b1 += 2 * NW, ++trip) {  // one warp per PAIR of region boundaries
+            // one warp per PAIR of region boundaries; consecutive pairs go to different CTAs (the wide zones -- centroids
+            // close together where the data are dense -- are neighbours, and a CTA full of them finished last)
+            const int gwi = warp_id() * n_cta + (int)cta;
+            for (int b1 = 1 + 2 * gwi; b1 < R; b1 += 2 * NW, ++trip) {
                 if (b1 + 1 >= R) {  // a last single boundary
                     long long r3[3];
                     boundary_search_call(C, T.rstart[b1], r3, &hint[trip < 10 ? trip : 9]);
