@@ -22,7 +22,7 @@ constexpr int EM_SUB = 32;          // fine buckets per coarse bucket (second le
 constexpr int EM_FINE = EM_LUT * EM_SUB;
 constexpr int EM_DMAX = 512;        // coarse buckets that get a second-level table
 // LUT entry (16 bit): 00 | cluster id        the whole bucket lies in one SAFE region
-//                     01 | table index       second-level table (first level only)
+//                     01 | table index * 32  second-level table (first level only)
 //                     10 | region            resolve by search starting at that region (boundary or ZONE inside)
 constexpr uint32_t EM_SLOW = 0x8000, EM_L2 = 0x4000;
 
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(TB_THREADS) emit_table_kernel(EmitDevice *ed, 
         if (loc[i] == 0)
             e = rid >= 0 ? (uint32_t)rid : (EM_SLOW | run);
         else
-            e = drun < (uint32_t)EM_DMAX ? (EM_L2 | drun) : (EM_SLOW | run);
+            e = drun < (uint32_t)EM_DMAX ? (EM_L2 | (drun * EM_SUB)) : (EM_SLOW | run);  // (first index of its table)
         ent[i] = (uint16_t)e;
         M.rlo[b] = (uint16_t)run;
         M.did[b] = (uint16_t)(loc[i] != 0 && drun < (uint32_t)EM_DMAX ? drun : 0xffffu);
@@ -217,35 +217,24 @@ __global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__rest
     const int64_t n_chunks = (n + EM_PER - 1) / EM_PER;
     const int64_t total_bytes = (n * bits + 7) / 8;
     const int64_t stride = (int64_t)gridDim.x * EM_THREADS;
-    // the loads of the next chunk are issued before the current one is processed: 64 B per thread in flight
-    auto load_chunk = [&](int64_t chunk, float *x) {
-        const int64_t base = chunk * EM_PER;
-        const int cnt = (int)min((int64_t)EM_PER, n - base);
-        if (VEC && cnt == EM_PER) {
-            float4 a = ld_stream_f4(w + base), b = ld_stream_f4(w + base + 4);
-            x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w;
-            x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < EM_PER; ++j) x[j] = j < cnt ? w[base + j] : 0.f;
-        }
+    const int64_t first = (int64_t)blockIdx.x * EM_THREADS + threadIdx.x;
+    // complete chunks of an aligned tensor take the fast loop: two register sets in turn, the loads of the next chunk
+    // (32 B per thread) issued before the current one is processed; what is left (a ragged last chunk, or everything for an
+    // unaligned tensor) takes the generic loop below
+    const int64_t n_full = VEC ? n / EM_PER : 0;
+    auto load_full = [&](int64_t chunk, float *x) {
+        const float4 a = ld_stream_f4(w + chunk * EM_PER), b = ld_stream_f4(w + chunk * EM_PER + 4);
+        x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w;
+        x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
     };
-    float xn[EM_PER];
-    {
-        const int64_t first = (int64_t)blockIdx.x * EM_THREADS + threadIdx.x;
-        if (first < n_chunks) load_chunk(first, xn);
-    }
     // two copies of the loop: with and without the histogram bookkeeping (the fused compress path takes the code histogram
     // from the Lloyd kernel; the kernel is issue bound, every instruction per element counts)
     auto run = [&](auto hist_c) {
     constexpr bool HIST = decltype(hist_c)::value;
-    for (int64_t chunk = (int64_t)blockIdx.x * EM_THREADS + threadIdx.x; chunk < n_chunks; chunk += stride) {
+    auto body = [&](const float *x, int64_t chunk, auto full_c) {
+        constexpr bool FULL = decltype(full_c)::value;
         const int64_t base = chunk * EM_PER;
-        float x[EM_PER];
-        const int cnt = (int)min((int64_t)EM_PER, n - base);
-#pragma unroll
-        for (int j = 0; j < EM_PER; ++j) x[j] = xn[j];
-        if (chunk + stride < n_chunks) load_chunk(chunk + stride, xn);
+        const int cnt = FULL ? EM_PER : (int)min((int64_t)EM_PER, n - base);
         // phase 1, branch free: LUT entry of every element (pruned weights take the known label of 0.0)
         int id[EM_PER];
         uint32_t any = 0;
@@ -254,7 +243,7 @@ __global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__rest
             const bool zero = x[j] == 0.f;
             const int f = lut_fine(fsub(x[j], mean), lut_lo, lut_scale);
             uint32_t e = S.lut[f / EM_SUB];
-            if (e & EM_L2) e = S.lut2[(e & (EM_L2 - 1)) * EM_SUB + (f % EM_SUB)];
+            if (e & EM_L2) e = S.lut2[(e & (EM_L2 - 1)) + (f % EM_SUB)];
             e = zero ? (uint32_t)zid : e;
             id[j] = (int)e;
             any |= e;
@@ -299,7 +288,7 @@ __global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__rest
             }
         }
         if (labels) {
-            if (VEC && cnt == EM_PER) {
+            if (FULL) {
                 reinterpret_cast<int4 *>(labels + base)[0] = make_int4(id[0], id[1], id[2], id[3]);
                 reinterpret_cast<int4 *>(labels + base)[1] = make_int4(id[4], id[5], id[6], id[7]);
             } else {
@@ -307,7 +296,7 @@ __global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__rest
             }
         }
         if (ris) {
-            if (VEC && cnt == EM_PER) {
+            if (FULL) {
                 st_stream_f4(ris + base, make_float4(S.val[id[0]], S.val[id[1]], S.val[id[2]], S.val[id[3]]));
                 st_stream_f4(ris + base + 4, make_float4(S.val[id[4]], S.val[id[5]], S.val[id[6]], S.val[id[7]]));
             } else {
@@ -315,7 +304,7 @@ __global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__rest
             }
         }
         if (packed) {
-            if (BITS == 8 && VEC && cnt == EM_PER) {
+            if (BITS == 8 && FULL) {
                 const uint32_t lo = (uint32_t)id[0] | ((uint32_t)id[1] << 8) | ((uint32_t)id[2] << 16) | ((uint32_t)id[3] << 24);
                 const uint32_t hi = (uint32_t)id[4] | ((uint32_t)id[5] << 8) | ((uint32_t)id[6] << 16) | ((uint32_t)id[7] << 24);
                 *reinterpret_cast<uint2 *>(packed + base) = make_uint2(lo, hi);
@@ -335,7 +324,7 @@ __global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__rest
                 }
                 const int64_t byte0 = chunk * bits;
                 uint8_t *dst = packed + byte0;
-                const bool full = byte0 + bits <= total_bytes;
+                const bool full = FULL || byte0 + bits <= total_bytes;
                 if (VEC && full && bits == 8) {
                     *reinterpret_cast<unsigned long long *>(dst) = lo64;
                 } else if (VEC && full && bits == 4) {
@@ -352,6 +341,28 @@ __global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__rest
                 }
             }
         }
+    };
+    {
+        float xa[EM_PER], xb[EM_PER];
+        int64_t c = first;
+        if (c < n_full) load_full(c, xa);
+        while (c < n_full) {
+            const int64_t c1 = c + stride;
+            if (c1 < n_full) load_full(c1, xb);
+            body(xa, c, std::true_type{});
+            if (c1 >= n_full) break;
+            c = c1 + stride;
+            if (c < n_full) load_full(c, xa);
+            body(xb, c1, std::true_type{});
+        }
+    }
+    for (int64_t chunk = n_full + first; chunk < n_chunks; chunk += stride) {
+        const int64_t base = chunk * EM_PER;
+        const int cnt = (int)min((int64_t)EM_PER, n - base);
+        float x[EM_PER];
+#pragma unroll
+        for (int j = 0; j < EM_PER; ++j) x[j] = j < cnt ? w[base + j] : 0.f;
+        body(x, chunk, std::false_type{});
     }
     };
     if (want_hist)
@@ -364,7 +375,7 @@ __global__ void __launch_bounds__(EM_THREADS, 2) emit_kernel(const float *__rest
     }
     if (want_hist) {
         // the thread that handled the last chunk counted its padding as zeros: take it back
-        if ((n_chunks - 1) % stride == (int64_t)blockIdx.x * EM_THREADS + threadIdx.x) zcount -= (unsigned int)(n_chunks * EM_PER - n);
+        if ((n_chunks - 1 - n_full) % stride == first) zcount -= (unsigned int)(n_chunks * EM_PER - n);
         unsigned long long z = warp_sum_ull((unsigned long long)zcount);
         if (lane_id() == 0) S.red[warp_id()] = z;
         __syncthreads();
