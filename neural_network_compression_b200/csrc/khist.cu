@@ -271,6 +271,143 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) kh_scatter_kernel(const uin
     }
 }
 
+// ---- scatter with software write combining (opt-in: NNC_SCATTER_WC=1; measured slower, see hist_sort_f32) ------
+// The partition above writes, per tile and bucket, a run of ~4 keys (8 bytes): every 32-byte sector of the output is
+// written in several pieces, tiles apart, and each piece costs a read-fill of the sector from DRAM (measured: 1.4 x the
+// algorithmic traffic and 22 % of the HBM rate).  Here every CTA keeps a 16-key buffer per bucket in shared memory
+// (position-major: wc[slot][bucket]) and writes a bucket's keys only as complete, 32-byte ALIGNED sectors; what is left
+// in the buffers goes out once, at the end of the CTA's chunk (and a partial first sector once per bucket and chunk,
+// because a chunk's part of a bucket starts anywhere).
+// Shared memory (dynamic): stage[KH_TILE] u16 | wc[16][nb] u16 | hist[nb] u32 | wpos[nb] u64 | fill[nb] u8 -- 106 KB at
+// 2048 buckets: two CTAs per SM.  nb <= KH_WC_MAX_NB; `out` 32-byte aligned.
+constexpr int KH_WC = 16;
+constexpr int KH_WC_MAX_NB = 2048;
+__host__ __device__ inline size_t kh_wc_smem(int nb) { return (size_t)KH_TILE * 2 + (size_t)KH_WC * nb * 2 + (size_t)nb * 4 + (size_t)nb * 8 + (size_t)nb; }
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) kh_scatter_wc_kernel(const uint32_t *__restrict__ in, uint16_t *__restrict__ out, int64_t n,
+                                                                    int64_t tiles_per_chunk, int nb, KhKeyMap km,
+                                                                    const unsigned long long *__restrict__ bucket_off,
+                                                                    const uint32_t *__restrict__ crel_lo, const uint32_t *__restrict__ crel_hi) {
+    extern __shared__ __align__(16) unsigned char kh_smem[];
+    unsigned long long *wpos = reinterpret_cast<unsigned long long *>(kh_smem);          // first unwritten position of the bucket
+    uint32_t *hist = reinterpret_cast<uint32_t *>(wpos + nb);                            // count, then start in the stage
+    uint16_t *stage = reinterpret_cast<uint16_t *>(hist + nb);                           // the tile's low digits in bucket order
+    uint16_t *wc = stage + KH_TILE;                                                      // [KH_WC][nb]
+    uint8_t *fill = reinterpret_cast<uint8_t *>(wc + (size_t)KH_WC * nb);                // keys waiting in the bucket's buffer
+    __shared__ uint32_t s_warp[32];
+    constexpr int ITEMS = KH_TILE / THREADS;
+    constexpr int PER = KH_WC_MAX_NB / THREADS;  // consecutive buckets per thread (scan and write-out)
+    const int lane = lane_id(), wid = warp_id();
+    for (int d = threadIdx.x; d < nb; d += THREADS) {
+        wpos[d] = bucket_off[d] + (((unsigned long long)crel_hi[(size_t)blockIdx.x * nb + d] << 32) | crel_lo[(size_t)blockIdx.x * nb + d]);
+        fill[d] = 0;
+    }
+    const int64_t n_tiles = (n + KH_TILE - 1) / KH_TILE;
+    const int64_t t0 = (int64_t)blockIdx.x * tiles_per_chunk, t1 = min(n_tiles, t0 + tiles_per_chunk);
+    const bool src_aligned = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+    const int b0 = threadIdx.x * PER;
+    for (int64_t tile = t0; tile < t1; ++tile) {
+        const int64_t tile_base = tile * KH_TILE;
+        const int valid = (int)min((int64_t)KH_TILE, n - tile_base);
+        uint32_t key[ITEMS];  // a key beyond the end of the array is the sentinel ~0
+        if (src_aligned && valid == KH_TILE) {
+#pragma unroll
+            for (int c = 0; c < ITEMS / 4; ++c) {
+                const uint4 v = ld_stream_u4(in + tile_base + 4 * (c * THREADS + threadIdx.x));
+                key[4 * c] = kh_key(v.x, km), key[4 * c + 1] = kh_key(v.y, km), key[4 * c + 2] = kh_key(v.z, km), key[4 * c + 3] = kh_key(v.w, km);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const int e = i * THREADS + threadIdx.x;
+                key[i] = e < valid ? kh_key(in[tile_base + e], km) : 0xffffffffu;
+            }
+        }
+        for (int d = threadIdx.x; d < nb; d += THREADS) hist[d] = 0;
+        __syncthreads();  // counters cleared; the previous tile's write-out has finished with the stage
+        uint32_t rank2[ITEMS / 2];  // two ranks (< KH_TILE = 2^13) per word
+#pragma unroll
+        for (int i = 0; i < ITEMS; i += 2) {
+            const uint32_t r0 = key[i] != 0xffffffffu ? atomicAdd(&hist[key[i] >> KH_LOW], 1u) : 0u;
+            const uint32_t r1 = key[i + 1] != 0xffffffffu ? atomicAdd(&hist[key[i + 1] >> KH_LOW], 1u) : 0u;
+            rank2[i / 2] = r0 | (r1 << 16);
+        }
+        __syncthreads();  // counts complete
+        // exclusive scan of the bucket counts; the thread keeps the counts and starts of its PER buckets
+        uint32_t cnt[PER], st[PER];
+        uint32_t loc = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            cnt[j] = b0 + j < nb ? hist[b0 + j] : 0u;
+            loc += cnt[j];
+        }
+        uint32_t incl = loc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        uint32_t run0 = incl - loc;
+        for (int w2 = 0; w2 < wid; ++w2) run0 += s_warp[w2];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            st[j] = run0;
+            if (b0 + j < nb) hist[b0 + j] = run0;
+            run0 += cnt[j];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i)
+            if (key[i] != 0xffffffffu)
+                stage[hist[key[i] >> KH_LOW] + ((rank2[i / 2] >> (16 * (i & 1))) & 0xffffu)] = (uint16_t)(key[i] & (KH_BINS - 1));
+        __syncthreads();
+        // write-out: per bucket the pending keys are buffer ++ this tile's run; complete aligned sectors go out
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int b = b0 + j;
+            if (b >= nb) break;
+            const uint32_t c = cnt[j], s0 = st[j], f = fill[b];
+            if (c == 0) continue;
+            const unsigned long long wp = wpos[b];
+            const uint32_t total = f + c;
+            uint32_t v0 = 0, need = KH_WC - (uint32_t)(wp & (KH_WC - 1));
+            auto get = [&](uint32_t v) -> uint32_t { return v < f ? wc[(size_t)v * nb + b] : stage[s0 + v - f]; };
+            while (total - v0 >= need) {
+                uint16_t *dst = out + wp + v0;
+                if (need == KH_WC) {
+                    uint32_t w8[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) w8[t] = get(v0 + 2 * t) | (get(v0 + 2 * t + 1) << 16);
+                    reinterpret_cast<uint4 *>(dst)[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+                    reinterpret_cast<uint4 *>(dst)[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+                } else {  // up to the first sector boundary of this chunk's part of the bucket (once per bucket and chunk)
+                    for (uint32_t t = 0; t < need; ++t) dst[t] = (uint16_t)get(v0 + t);
+                }
+                v0 += need;
+                need = KH_WC;
+            }
+            const uint32_t r = total - v0;
+            if (v0 == 0) {  // nothing went out: append the run to the buffer
+                for (uint32_t t = 0; t < c; ++t) wc[(size_t)(f + t) * nb + b] = stage[s0 + t];
+            } else {  // (a flush always drains the old buffer: f < need) the rest of the run starts the buffer anew
+                for (uint32_t t = 0; t < r; ++t) wc[(size_t)t * nb + b] = stage[s0 + (v0 - f) + t];
+            }
+            fill[b] = (uint8_t)r;
+            wpos[b] = wp + v0;
+        }
+        // (the next tile's first barrier comes after its loads: nobody overwrites the stage or the counters before it)
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < nb; d += THREADS) {  // what is left in the buffers
+        const uint32_t f = fill[d];
+        const unsigned long long wp = wpos[d];
+        for (uint32_t t = 0; t < f; ++t) out[wp + t] = wc[(size_t)t * nb + d];
+    }
+}
+
 // ---- hist: low-digit histogram of one work item (<= KH_CHUNK keys of one bucket) in shared memory -----------
 // IN_FLOAT: the input is the raw survivor array (no partition pass ran: keybits <= KH_LOW, one bucket); otherwise the
 // partition pass's uint16 low digits.
@@ -508,7 +645,16 @@ SortedRuns hist_sort_f32(nnc_ctx *ctx, float *d_a, float *d_b, int64_t n, uint32
         NNC_LAUNCH(ctx, kh_base_kernel, 1, 1024, 0, tot, nb, bucket_off, item_off);
         // two CTAs per SM (64 registers) by default; three (42 registers: spills) measured slower, NNC_SCATTER_CTAS=3 selects it
         const char *thr_env = getenv("NNC_SCATTER_THREADS");
-        if (thr_env && atoi(thr_env) == 1024)  // 2 CTAs x 1024 threads x 8 keys: 32 registers, full occupancy
+        // NNC_SCATTER_WC=1: complete 32-byte sectors out of per-bucket buffers in shared memory.  Measured and rejected: it
+        // removes the partial-sector read-fills (the 1.4 x DRAM traffic of the plain partition), but the partition is bound
+        // by its barriers and dependent shared-memory phases, not by DRAM, and the sector assembly adds to them
+        // (1.62 ms against 1.40 ms at 2^30 weights)
+        const bool wc_ok = nb <= KH_WC_MAX_NB && (reinterpret_cast<uintptr_t>(b16) & 31u) == 0 && getenv("NNC_SCATTER_WC");
+        if (wc_ok) {
+            func_dyn_smem(ctx, (const void *)kh_scatter_wc_kernel<512>, kh_wc_smem(KH_WC_MAX_NB));
+            NNC_LAUNCH_AS(ctx, "kh_scatter_kernel", (kh_scatter_wc_kernel<512>), chunks, 512, kh_wc_smem(nb), a, b16, n, tiles_per_chunk, nb, km,
+                          bucket_off, crel_lo, crel_hi);
+        } else if (thr_env && atoi(thr_env) == 1024)  // 2 CTAs x 1024 threads x 8 keys: 32 registers, full occupancy
             NNC_LAUNCH_AS(ctx, "kh_scatter_kernel", (kh_scatter_kernel<2, 1024>), chunks, 1024, KH_TILE * 4 + nb * 20, a, b16, n, tiles_per_chunk,
                           nb, km, bucket_off, crel_lo, crel_hi);
         else if (scatter_ctas == 2)
