@@ -175,23 +175,40 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) kh_scatter_kernel(const uin
     const int64_t t0 = (int64_t)blockIdx.x * tiles_per_chunk, t1 = min(n_tiles, t0 + tiles_per_chunk);
     const bool src_aligned = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
     const int per = (nb + THREADS - 1) / THREADS;  // bins per thread in the scan (consecutive bins)
-    for (int64_t tile = t0; tile < t1; ++tile) {
+    // registers: 16 keys + 8 words of packed 13-bit ranks (three CTAs of 512 threads leave 42 registers per thread).
+    // The RAW words of the next tile are loaded into the key registers as soon as the current tile's keys are staged in
+    // shared memory: the load latency hides behind the write-out instead of standing at the top of every tile.
+    uint32_t key[ITEMS];
+    auto load_raw = [&](int64_t tile) {
         const int64_t tile_base = tile * KH_TILE;
         const int valid = (int)min((int64_t)KH_TILE, n - tile_base);
-        // registers: 16 keys + 8 words of packed 13-bit ranks (three CTAs of 512 threads leave 42 registers per thread);
-        // a key beyond the end of the array is the sentinel ~0 (a real key has at most KH_LOW + KH_MAX_HB bits)
-        uint32_t key[ITEMS];
         if (src_aligned && valid == KH_TILE) {
 #pragma unroll
             for (int c = 0; c < ITEMS / 4; ++c) {
                 const uint4 v = ld_stream_u4(in + tile_base + 4 * (c * THREADS + threadIdx.x));
-                key[4 * c] = kh_key(v.x, km), key[4 * c + 1] = kh_key(v.y, km), key[4 * c + 2] = kh_key(v.z, km), key[4 * c + 3] = kh_key(v.w, km);
+                key[4 * c] = v.x, key[4 * c + 1] = v.y, key[4 * c + 2] = v.z, key[4 * c + 3] = v.w;
             }
         } else {
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
                 const int e = i * THREADS + threadIdx.x;
-                key[i] = e < valid ? kh_key(in[tile_base + e], km) : 0xffffffffu;
+                key[i] = e < valid ? in[tile_base + e] : 0u;
+            }
+        }
+    };
+    if (t0 < t1) load_raw(t0);
+    for (int64_t tile = t0; tile < t1; ++tile) {
+        const int64_t tile_base = tile * KH_TILE;
+        const int valid = (int)min((int64_t)KH_TILE, n - tile_base);
+        // raw word -> key; a key beyond the end of the array is the sentinel ~0 (a real key has at most KH_LOW + KH_MAX_HB bits)
+        if (src_aligned && valid == KH_TILE) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) key[i] = kh_key(key[i], km);
+        } else {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const int e = i * THREADS + threadIdx.x;
+                key[i] = e < valid ? kh_key(key[i], km) : 0xffffffffu;
             }
         }
         for (int d = threadIdx.x; d < nb; d += THREADS) hist[d] = 0;
@@ -260,6 +277,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) kh_scatter_kernel(const uin
         for (int i = 0; i < ITEMS; ++i)
             if (key[i] != 0xffffffffu) keys[hist[key[i] >> KH_LOW] + ((rank2[i / 2] >> (16 * (i & 1))) & 0xffffu)] = key[i];
         __syncthreads();
+        if (tile + 1 < t1) load_raw(tile + 1);  // (the key registers are dead: the tile is in shared memory)
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
             const int p = threadIdx.x + j * THREADS;
