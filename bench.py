@@ -772,7 +772,7 @@ def run_config(args):
     # worker threads have their own contexts in the batched mode: kernel times come from this thread's context only
     ktimes = {name: ms / max(c, 1) * c for name, (c, ms) in ctx.last_kernel_times().items()}
     ctx.set_kernel_timing(False)
-    launches0 = ctx.total_launches()
+    launches0 = N.total_launches_all()  # (the batched configs run on worker threads with contexts of their own)
     total_ms = 0.0
     t_region0 = time.time()
     for i in range(K):
@@ -788,7 +788,7 @@ def run_config(args):
         total_ms += ev0.elapsed_time(ev1)
     t_region1 = time.time()
     clk = clocks.stop(t_region0, t_region1) if rank == 0 else None
-    launches = ctx.total_launches() - launches0
+    launches = N.total_launches_all() - launches0
     if dist is not None:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

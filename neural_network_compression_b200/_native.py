@@ -289,7 +289,20 @@ def default_context(device: int | None = None) -> Context:
         cache = _tls.ctx = {}
     if device not in cache:
         cache[device] = Context(device)
+        with _all_lock:
+            _all_contexts.append(cache[device])
     return cache[device]
+
+
+_all_contexts: list = []  # every default context of the process (the batched calls run on worker threads with their own)
+_all_lock = threading.Lock()
+
+
+def total_launches_all() -> int:
+    """Kernel launches of all default contexts of this process (main thread and batch workers)."""
+    with _all_lock:
+        ctxs = list(_all_contexts)
+    return sum(c.total_launches() for c in ctxs)
 
 
 # ---- buffer plumbing -------------------------------------------------------------------------------------

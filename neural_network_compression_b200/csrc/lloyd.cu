@@ -818,7 +818,7 @@ __global__ void __launch_bounds__(TB_THREADS) ll_count_kernel(LloydDevice *st) {
 // Grid barrier: every CTA's thread 0 publishes its arrival with a release-ordered atomic and spins with acquire loads
 // until all CTAs of the current epoch have arrived; the surrounding __syncthreads extend the ordering to the whole
 // CTA (the acquire invalidates the SM's L1, so the plain loads of the next phase see the other CTAs' stores).
-// A CTA that waits for more than a few seconds gives up and raises *bail (checked by the host): the kernel then runs
+// A CTA that waits for minutes gives up and raises *bail (checked by the host): the kernel then runs
 // through without waiting instead of hanging the device.
 __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &epoch, volatile int *bail) {
     __syncthreads();
@@ -832,7 +832,9 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &ep
         for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
             if (v >= target) break;
-            if (++spins > (1ll << 22)) {
+            // longer than the longest wait of CTA 0 inside a peer exchange (peer.cuh: 2^26 polls): a CTA must not give up
+            // here while CTA 0 is still, legitimately, waiting for a slow rank
+            if (++spins > (1ll << 27)) {
                 *bail = 1;
                 break;
             }

@@ -1298,6 +1298,7 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
         } else if (tot <= tol) {
             stop = 1;
         }
+        if (S.comm_error) stop = 1;  // an exchange timed out: the call fails; do not wait through the remaining iterations
         if (tid == 0) {
             U.strict = strict;
             U.stop = stop;
@@ -1617,7 +1618,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 st->pad2 = S.comm_error;  // travels with the loop's outcome (one read-back)
             }
         }
-        if (!want_hist) break;
+        if (!want_hist || S0->comm_error) break;  // (after a time-out the histogram round would only wait again)
         hist_round = true;  // code histogram of the final labelling: the E-step once more, against c_emit
         if (tid < k) S.c[tid] = S0->c_emit[tid];
         __syncthreads();

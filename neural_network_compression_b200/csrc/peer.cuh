@@ -79,7 +79,7 @@ __device__ inline bool peer_publish_and_wait(const PeerComm &pc, const unsigned 
         const unsigned long long *f = peer_flag(pc.mail[pc.rank], pc.world, parity, tid);
         long long spins = 0;
         while (ld_acquire_sys_u64(f) < seq) {
-            if (++spins > (1ll << 27)) {  // ~ seconds: give up instead of hanging the device
+            if (++spins > (1ll << 26)) {  // tens of seconds: give up instead of hanging the device (shorter than the grid barrier's limit)
                 s_ok = 0;
                 break;
             }
