@@ -633,18 +633,20 @@ def run_config(args):
             work["t"] = [m.clone() for m in master]
 
         def step():
-            return U.compress_tensors(work["t"], qs, True, bits, mode)
+            return U.compress_model(work["t"], qs, True, bits, mode)
 
         def e2e_step():
-            return U.compress_tensors([t.copy() for t in host], qs, True, bits, mode)
+            return U.compress_model([t.copy() for t in host], qs, True, bits, mode)
 
         h2d = 4 * units
-        d2h = units * (1 + 4 + 4)  # mask, ris (float32), labels (int32): what the reference's helpers return
+        cb = bits if mode == "linear" else bits + 1  # (density init has 2^bits + 1 centroids)
+        d2h = units * 4 + units + (units * cb + 7) // 8  # pruned weights back in place, mask, packed codes
         workload = ("%s: every kernel and bias pruned with the trainer's thresholds, then %d-bit %s-init k-means, all "
-                    "tensors in one batched call (utility.compress_tensors)" %
+                    "tensors in one native batched call (utility.compress_model -> nnc_compress_many_f32; mask, codebook and "
+                    "packed codes out)" %
                     ("LeNet300-100 (784-300-100-10), 6 tensors" if cfgname == "c1" else "LeNet5 conv+dense layers, 8 tensors", bits, mode))
         sfrac = 0.35
-        step_bytes = 13.0 + 4.0 + 4.0 + 4.0 + 52.0 * sfrac  # prune + quantize with dense ris and labels out
+        step_bytes = 13.0 + 4.0 + cb / 8.0 + 52.0 * sfrac  # prune + quantize, packed codes out
 
         def cpu():
             from oracle import oracle as O

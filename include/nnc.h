@@ -161,6 +161,39 @@ int nnc_pack_bits_u8(nnc_ctx *ctx, const uint8_t *src, int64_t n, uint8_t *dst_b
 int nnc_grad_segsum_f32(nnc_ctx *ctx, const float *grad, const void *codes, int64_t n, int bits, int k,
                         double *out);
 
+/* ---- all tensors of a model in one call (le_net_5.py:17-34 / le_net_300.py: the trainer walks the layers, pruning
+ * every kernel and bias, trainer.py:177-193, then quantising every array, trainer.py:50-70) -----------------------
+ * One job per tensor; the jobs run concurrently on a pool of native worker threads, each with a context and a stream of
+ * its own (LeNet tensors have 10 .. 627 200 weights: every one of them is bound by launch latency and host round trips,
+ * which overlap across the workers without an interpreter in between).  Results are bit-identical to the per-tensor
+ * calls: nnc_compress_f32 for mode 0 (linear init), nnc_prune_f32 + nnc_weight_cdf_f32 + the density init of
+ * utility.py:210-223 + nnc_kmeans1d_f32 for mode 1 (density init: 2^bits + 1 centroids, as the reference has it).
+ * A tensor with fewer than 2^bits + 1 weights is pruned only (k = 0), like get_quantized_weight (utility.py:202-204). */
+typedef struct {
+    float *w;             /* in: n weights, host or device; pruned in place when prune != 0 */
+    int64_t n;
+    double threshold;     /* pruning quality parameter of this tensor */
+    int prune;            /* 0: the tensor is taken as it is */
+    int pad_;
+    uint8_t *mask;        /* out: n bytes (1 = pruned), same memory space as w; may be NULL when prune == 0 */
+    float *centers;       /* out: k floats (host) */
+    float *centred;       /* out: k floats (host) */
+    uint8_t *packed;      /* out: ceil(n * code_bits / 8) bytes, same memory space as w */
+    int64_t *hist;        /* out: k counts (host) */
+    nnc_kmeans_info info; /* out */
+    double thr;           /* out: the threshold applied */
+    int64_t n_pruned;     /* out */
+    int k;                /* out: clusters (0: not quantised) */
+    int code_bits;        /* out: bits per packed code */
+    int status;           /* out: NNC_OK or the error of this tensor */
+    char error[196];      /* out: its message */
+} nnc_tensor_job;
+
+/* mode: 0 linear, 1 density.  max_workers <= 0: the default (8).  Returns NNC_OK when every job succeeded, else the first
+ * failing job's status (all jobs are attempted).  ctx gives the device and the stream the tensors were produced on. */
+int nnc_compress_many_f32(nnc_ctx *ctx, nnc_tensor_job *jobs, int count, int std_smooth, int threshold_mode, int bits, int mode,
+                          int max_workers);
+
 /* ---- multi-GPU (one process per GPU; contiguous shards of the flattened tensor) ------------ */
 /* Multi-GPU: tells the context the element count of the WHOLE tensor the next sharded calls work on (0: ask the ranks
  * with an all-reduce at the start of every call, the default).  All ranks must give the same value.  Saves one

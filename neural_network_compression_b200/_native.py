@@ -33,7 +33,7 @@ EXPORTS = [
     "nnc_timer_start", "nnc_timer_stop", "nnc_last_profile", "nnc_stats_f32", "nnc_prune_f32", "nnc_mask_apply_f32",
     "nnc_compact_nonzero_f32", "nnc_minmax_f32", "nnc_hist_edges_f32", "nnc_weight_cdf_f32", "nnc_gather_f32",
     "nnc_kmeans1d_f32", "nnc_assign_f32", "nnc_unpack_gather_f32", "nnc_grad_segsum_f32", "nnc_ctx_set_comm",
-    "nnc_ctx_set_kernel_timing", "nnc_last_kernel_times", "nnc_ctx_total_launches",
+    "nnc_ctx_set_kernel_timing", "nnc_last_kernel_times", "nnc_ctx_total_launches", "nnc_compress_many_f32",
     "nnc_compress_f32", "nnc_shard_range", "nnc_comm_unique_id", "nnc_ctx_init_nccl",
     "nnc_peer_mailbox_create", "nnc_peer_mailbox_connect", "nnc_pack_bits_u8", "nnc_ctx_hint_global_n",
 ]
@@ -56,6 +56,29 @@ class KMeansInfo(C.Structure):
         ("tol", C.c_float),
         ("inertia", C.c_double),
         ("n_nonzero", C.c_int64),
+    ]
+
+
+class TensorJob(C.Structure):
+    """nnc_tensor_job (include/nnc.h): one tensor of nnc_compress_many_f32."""
+    _fields_ = [
+        ("w", C.c_void_p),
+        ("n", C.c_int64),
+        ("threshold", C.c_double),
+        ("prune", C.c_int),
+        ("pad_", C.c_int),
+        ("mask", C.c_void_p),
+        ("centers", C.c_void_p),
+        ("centred", C.c_void_p),
+        ("packed", C.c_void_p),
+        ("hist", C.c_void_p),
+        ("info", KMeansInfo),
+        ("thr", C.c_double),
+        ("n_pruned", C.c_int64),
+        ("k", C.c_int),
+        ("code_bits", C.c_int),
+        ("status", C.c_int),
+        ("error", C.c_char * 196),
     ]
 
 
@@ -140,6 +163,7 @@ def lib():
         L.nnc_unpack_gather_f32.argtypes = [vp, vp, i64, i32, vp, i32, vp]
         L.nnc_grad_segsum_f32.argtypes = [vp, vp, vp, i64, i32, i32, vp]
         L.nnc_pack_bits_u8.argtypes = [vp, vp, i64, vp]
+        L.nnc_compress_many_f32.argtypes = [vp, P(TensorJob), i32, i32, i32, i32, i32, i32]
         L.nnc_ctx_hint_global_n.argtypes = [vp, i64]
         L.nnc_ctx_set_kernel_timing.argtypes = [vp, i32, C.c_char_p]
         L.nnc_last_kernel_times.argtypes = [vp, P(C.c_char_p)]

@@ -712,6 +712,76 @@ def assign_codes(weights, kmeans: KMeansResult, want_labels=True, want_packed=Tr
     return labels, packed, hist
 
 
+def compress_model(tensors, thresholds=None, std_smooth=True, bits=4, mode="linear", workers=8):
+    """All tensors of a model compressed in ONE native call (nnc_compress_many_f32): what the trainer does layer by layer
+    and tensor by tensor (prune every kernel / bias, trainer.py:177-193; quantise every array, trainer.py:50-70;
+    le_net_5.py:17-34), keeping the compressed form of every tensor -- mask, codebook, packed indices, histogram -- like
+    compress_weight.  The tensors run concurrently on a pool of native worker threads with a context and stream each; no
+    interpreter between a tensor's ~25 launches.  Bit-identical to compress_weight per tensor.
+
+    tensors: float32 ndarrays / torch tensors (pruned in place).  thresholds: one quality parameter per tensor, or None for
+    an already pruned model.  mode: "linear" or "density" (2**bits + 1 centroids, as the reference has it).
+    Returns [(mask or None, KMeansResult or None)] in input order; a tensor with fewer than 2**bits + 1 elements comes back
+    pruned and unquantised (None), like get_quantized_weight (utility.py:202-204)."""
+    tensors = list(tensors)
+    if thresholds is not None and len(thresholds) != len(tensors):
+        raise ValueError("one threshold per tensor")
+    if mode not in ("linear", "density"):
+        raise Exception(" error mode not found")
+    if not tensors:
+        return []
+    bufs = [_Buf(t, "tensors[%d]" % i, writable=thresholds is not None) for i, t in enumerate(tensors)]
+    devices = {b.device for b in bufs if b.device is not None}
+    if len(devices) > 1:
+        raise ValueError("compress_model: all device tensors must live on one GPU")
+    ctx = _ctx_for(next((b for b in bufs if b.device is not None), bufs[0]))
+    k_lin = 2 ** bits
+    k_max = k_lin + (1 if mode == "density" else 0)
+    cbits = index_bits(k_max)
+    jobs = (N.TensorJob * len(bufs))()
+    keep = []
+    # NEP-50: a np.float64 threshold promotes the comparison to float64, a Python float does not; one mode per call
+    modes = {isinstance(q, np.float64) for q in thresholds} if thresholds is not None else {False}
+    if len(modes) > 1:
+        raise ValueError("compress_model: thresholds must be all Python floats or all numpy.float64")
+    thr_mode = int(modes.pop())
+    for i, b in enumerate(bufs):
+        q = thresholds[i] if thresholds is not None else 0.0
+        mask = b.empty(b.n, np.uint8) if thresholds is not None else None
+        packed = b.empty((b.n * cbits + 7) // 8, np.uint8) if b.n >= k_lin + 1 else None
+        centers, centred, hist = np.empty(k_max, np.float32), np.empty(k_max, np.float32), np.empty(k_max, np.int64)
+        keep.append((mask, packed, centers, centred, hist))
+        j = jobs[i]
+        j.w, j.n, j.threshold, j.prune = b.ptr, b.n, float(q), int(thresholds is not None)
+        j.mask, j.packed = N.ptr(mask), N.ptr(packed)
+        j.centers, j.centred, j.hist = N.ptr(centers), N.ptr(centred), N.ptr(hist)
+    rc = N.lib().nnc_compress_many_f32(ctx.handle, jobs, len(bufs), int(bool(std_smooth)), thr_mode, int(bits),
+                                       0 if mode == "linear" else 1, int(workers))
+    if rc == N.NNC_ERR_NONFINITE:
+        raise ValueError("Input X contains NaN or infinity.")
+    N.check(rc)
+    out = []
+    for i, b in enumerate(bufs):
+        b.finish()
+        mask, packed, centers, centred, hist = keep[i]
+        j = jobs[i]
+        m = None
+        if mask is not None:
+            m = (mask.view(np.bool_) if isinstance(mask, np.ndarray) else mask.bool()).reshape(tuple(b.shape))
+        if j.k == 0:
+            print("not enough bits:", b.n, " vs ", k_lin)
+            out.append((m, None))
+            continue
+        k = int(j.k)
+        info = j.info
+        out.append((m, KMeansResult(
+            cluster_centers_=centers[:k].reshape(-1, 1), labels_=None, n_iter_=info.n_iter, inertia_=info.inertia,
+            packed_codes=packed, code_bits=int(j.code_bits), code_histogram=hist[:k], centred_centers=centred[:k],
+            mean=np.float32(info.mean), strict_convergence=bool(info.strict), n_relocations=info.n_relocations,
+            n_nonzero=info.n_nonzero, tol_=float(info.tol), profile={})))
+    return out
+
+
 def dequantize(packed_codes, n: int, bits: int, cluster_centers, like=None):
     """cluster_centers_[codes] from packed n-bit codes (the decode side of utility.py:239)."""
     values = np.ascontiguousarray(np.asarray(cluster_centers, dtype=np.float32).ravel())

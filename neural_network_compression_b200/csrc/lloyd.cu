@@ -1028,7 +1028,7 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
     if (fast) {
         const bool kt = ctx->ktime && (ctx->kfilter.empty() || strstr("ll_fast_kernel", ctx->kfilter.c_str()));
         if (kt) klaunch_begin(ctx, "ll_fast_kernel");
-        lloyd_fast_launch(ctx, st, h.d_sorted, samp, ptile, d_init, h_hist ? 1 : 0, pc);
+        lloyd_fast_launch(ctx, st, h.d_sorted, samp, ptile, d_init, h_hist ? 1 : 0, pc, k);
         if (kt) klaunch_end(ctx);
         NNC_CUDA(cudaMemcpyAsync(&ctl, &st->iter, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
         if (world > 1) NNC_CUDA(cudaStreamSynchronize(ctx->stream));  // one rank: the outcome is read with the results below (one sync)

@@ -555,7 +555,7 @@ __device__ __forceinline__ bool warp_pair_search(const SearchConst &C, float t1,
 // 0: the search pass evaluated every non-empty zone, nothing done (and no barrier needed); 1: chunks into CTA 0's slots;
 // 2: some chunks took the generic path, CTA 0 has partials to pull
 __device__ int fast_zone_step(FastSmem &S, FastSmem *S0, const FastConst &K, const SearchConst &C, const float *__restrict__ ks,
-                              int gw, int NW, unsigned int etag, long long *prof = nullptr, int *dbg = nullptr) {
+                              int gw, int NW, unsigned int etag, bool cta0, long long *prof = nullptr, int *dbg = nullptr) {
     const int NT = blockDim.x;
     if (prof) prof[0] = clock64();
     FastZone &Z = S.u.zn;
@@ -565,7 +565,7 @@ __device__ int fast_zone_step(FastSmem &S, FastSmem *S0, const FastConst &K, con
     // Is any non-empty zone left?  CTA 0 looks (its own shared memory) and publishes the answer; the other CTAs poll ONE
     // word of it.  (With every CTA reading the positions and tags of all regions out of CTA 0, 23 K remote loads converged
     // on one SM in every iteration: 6 us per CTA, and CTA 0's own update step ran against that traffic.)
-    if (&S == S0) {
+    if (cta0) {
         int left = 0;
         for (int r = tid; r < R; r += NT) {
             const int J2 = T.rJ2[r], J1 = T.rJ1[r];
@@ -1528,7 +1528,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         int zs = 0;
         {
             long long zp[4] = {0, 0, 0, 0};
-            zs = fast_zone_step(S, S0, K, C, ks, gw, NW, etag, lg ? zp : nullptr, want_log ? &st->logG[LL_LOG - 16] : nullptr);
+            zs = fast_zone_step(S, S0, K, C, ks, gw, NW, etag, cta == 0, lg ? zp : nullptr, want_log ? &st->logG[LL_LOG - 16] : nullptr);
             if (lg && S.iter == 6)
                 for (int i = 0; i < 4; ++i) st->logZ[LL_LOG - 16 + i] = zp[i] - zp[0];
             if (stamp) sl[3] = now();
@@ -1662,7 +1662,7 @@ static cudaError_t fast_launch_shape(nnc_ctx *ctx, int n_cta, bool probe_only, L
 }
 
 void lloyd_fast_launch(nnc_ctx *ctx, LloydDevice *st, const float *d_sorted, const float *samp, const long long *ptile,
-                       const float *d_init, int want_hist, const PeerComm &pc) {
+                       const float *d_init, int want_hist, const PeerComm &pc, int k) {
     const int want_log = getenv("NNC_LLOYD_LOG") ? atoi(getenv("NNC_LLOYD_LOG")) : 0;
     if (ctx->fast_cluster == 0) {  // decide once per context (= per device)
         int want = 16;
@@ -1672,11 +1672,19 @@ void lloyd_fast_launch(nnc_ctx *ctx, LloydDevice *st, const float *d_sorted, con
             ctx->fast_cluster = 16;
         cudaGetLastError();
     }
+    // The cluster is as large as the E-step needs: one warp per pair of region boundaries, at most k - 1 pairs.  A small
+    // codebook (2- to 5-bit quantisation) runs in 1 - 2 CTAs: cheaper barriers, and the clusters of a model's tensors run
+    // side by side (16-CTA clusters of several streams were observed to run one after the other).
+    // (four pairs per CTA -- one per warp scheduler: a pair search is a long dependent chain, co-resident searches on one
+    // scheduler take turns)
+    int n_cta = 1;
+    while (n_cta < ctx->fast_cluster && n_cta * 4 < k - 1) n_cta <<= 1;
+    if (getenv("NNC_LLOYD_FULL_CLUSTER")) n_cta = ctx->fast_cluster;
     cudaError_t e = ctx->fast_cluster == 16
-                        ? fast_launch_shape<512>(ctx, 16, false, st, d_sorted, samp, ptile, d_init, want_hist, want_log, pc)
-                        : fast_launch_shape<1024>(ctx, 8, false, st, d_sorted, samp, ptile, d_init, want_hist, want_log, pc);
+                        ? fast_launch_shape<512>(ctx, n_cta, false, st, d_sorted, samp, ptile, d_init, want_hist, want_log, pc)
+                        : fast_launch_shape<1024>(ctx, n_cta, false, st, d_sorted, samp, ptile, d_init, want_hist, want_log, pc);
     ctx->launches++;
-    if (e != cudaSuccess) NNC_FAIL(NNC_ERR_CUDA, "ll_fast_kernel launch (cluster of %d): %s", ctx->fast_cluster, cudaGetErrorString(e));
+    if (e != cudaSuccess) NNC_FAIL(NNC_ERR_CUDA, "ll_fast_kernel launch (cluster of %d): %s", n_cta, cudaGetErrorString(e));
 }
 
 }  // namespace nnc

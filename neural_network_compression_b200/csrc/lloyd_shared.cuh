@@ -326,6 +326,6 @@ __device__ __forceinline__ FarKey far_key(float xc, float c) {
 // lloyd_fast.cu: the loop as one thread-block cluster with its state in shared memory (k <= 512)
 bool lloyd_fast_applicable(int k);
 void lloyd_fast_launch(nnc_ctx *ctx, LloydDevice *st, const float *d_sorted, const float *samp, const long long *ptile,
-                       const float *d_init, int want_hist, const PeerComm &pc);
+                       const float *d_init, int want_hist, const PeerComm &pc, int k);
 
 }  // namespace nnc

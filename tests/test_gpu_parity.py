@@ -418,6 +418,56 @@ def test_compress_tensors_batched_equals_per_tensor(U, on_device):
             assert np.array_equal(to_np(k1.labels_), k0.labels_)
 
 
+@pytest.mark.parametrize("on_device", [False, True])
+def test_compress_model_native_batch_equals_per_tensor(U, on_device):
+    """SURVEY 8f row 4, the native form: nnc_compress_many_f32 (a pool of native worker threads, one context and stream
+    each) gives every tensor of LeNet300-100 (2-bit density, config 1) and LeNet5 (4-bit linear, config 2) the same mask,
+    codebook, packed codes and histogram as the per-tensor helpers -- and the dequantised tensor equals the oracle's."""
+    import torch
+
+    for tensors, bits, mode in ((D.lenet300_tensors(), 2, "density"), (D.lenet5_tensors(), 4, "linear")):
+        flat, qs = [], []
+        for name, w, b, (qw, qb) in tensors:
+            flat += [w, b]
+            qs += [qw, qb]
+        single = []
+        for t, q in zip(flat, qs):
+            t = t.copy()
+            m = U.prune_weigth(t, q, True)
+            if t.size < 2 ** bits + 1:
+                single.append((m, t, None, None))
+                continue
+            cdfs = U.get_weight_distribution(t, skip_zeros=True) if mode == "density" else None
+            ris, km = U.get_quantized_weight(t, bits, mode, cdfs)
+            space = O.init_centroids(t, bits, mode, cdfs)
+            det = O.kmeans1d(t, space, mode=O.MODE_DET)
+            assert km.cluster_centers_.tobytes() == det.cluster_centers_.tobytes()
+            single.append((m, t, ris, km))
+        for rep in range(2):  # the second call reuses the pool and its contexts
+            batch_in = [torch.from_numpy(t.copy()).cuda() if on_device else t.copy() for t in flat]
+            out = U.compress_model(batch_in, qs, True, bits, mode)
+            assert len(out) == len(flat)
+            to_np = (lambda x: x.cpu().numpy()) if on_device else (lambda x: x)
+            for (m1, k1), (m0, pruned0, ris0, k0), t_in in zip(out, single, batch_in):
+                assert np.array_equal(to_np(m1), m0)
+                assert to_np(t_in).tobytes() == pruned0.tobytes()  # pruned in place
+                if k0 is None:
+                    assert k1 is None
+                    continue
+                assert k1.cluster_centers_.tobytes() == k0.cluster_centers_.tobytes()
+                assert k1.n_iter_ == k0.n_iter_
+                assert np.array_equal(k1.code_histogram, np.bincount(k0.labels_, minlength=k1.cluster_centers_.size))
+                deq = U.dequantize(k1.packed_codes, t_in.size if not on_device else t_in.numel(), k1.code_bits, k1.cluster_centers_)
+                assert to_np(deq).reshape(ris0.shape).tobytes() == np.ascontiguousarray(ris0).tobytes()
+    # no thresholds: an already pruned model is only quantised
+    pruned = [s_[1] for s_ in single]
+    out = U.compress_model([p.copy() for p in pruned], None, True, 4, "linear")
+    for (m1, k1), (m0, p0, ris0, k0) in zip(out, single):
+        assert m1 is None
+        if k0 is not None:
+            assert k1.cluster_centers_.tobytes() == k0.cluster_centers_.tobytes()
+
+
 def test_kmeans_errors(U):
     w = D.gaussian(1000, seed=2)
     with pytest.raises(Exception, match="error mode not found"):
