@@ -801,7 +801,8 @@ def run_config(args):
     if not args.no_e2e:
         if cfgname == "c5":
             g_host, p_host = g.cpu().numpy(), packed.cpu().numpy()
-        e2e_step()
+        for _ in range(2):  # untimed: the first call grows the workspace arenas, the second runs with the regrown blocks
+            e2e_step()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         n_e2e = max(1, min(K, args.e2e_steps))
