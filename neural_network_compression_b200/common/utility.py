@@ -795,6 +795,12 @@ def dequantize(packed_codes, n: int, bits: int, cluster_centers, like=None):
         out = np.empty(int(n), dtype=np.float32)
         dev = None
     ctx = N.default_context(dev)
+    if dev is not None:  # run on the stream the codes were produced on (the context keeps the stream of its previous call)
+        import torch
+
+        ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    else:
+        ctx.set_stream(None)
     N.check(N.lib().nnc_unpack_gather_f32(ctx.handle, N.ptr(packed_codes), int(n), int(bits), N.ptr(values), values.size,
                                           N.ptr(out)))
     return out

@@ -87,28 +87,49 @@ struct VisitStats {
     static constexpr bool kSecondTree = false;
     static constexpr bool kCompact = false;
     DevScalars *sc;
+    // The fp64 side sums feed the ESTIMATE of the std that places the speculation band of the pruning pass.  Their
+    // float32 partials are taken of x - shift, shift = the mean of the first few elements: with the raw values a tensor with
+    // |mean| >> std (normalisation scales, biases) lost (mean / std)^2 * 1e-7 of the variance and missed the 2^-16 band.
+    // The shift is undone in float64 at the end of every tile (sum x, sum x^2 keep their meaning for the exchange).
+    const float *probe = nullptr;  // this rank's elements
+    int64_t probe_n = 0;
+    float shift = 0.f;
+    unsigned int cnt = 0;
     double s = 0.0, s2 = 0.0;
     float ts = 0.f, ts2 = 0.f;
     uint32_t amax = 0u;  // largest |x| bit pattern (the fused compress path takes its key range and NaN check from it)
-    __device__ __forceinline__ void begin() {}
+    __device__ __forceinline__ void begin() {
+        const int m = (int)(probe_n < 16 ? probe_n : 16);
+        float a = 0.f;
+        for (int i = 0; i < m; ++i) a += probe[i];  // (every thread: the same loads in the same order)
+        a = m > 0 ? a / (float)m : 0.f;
+        shift = (a - a == 0.f) ? a : 0.f;  // a non-finite probe: no shift
+    }
     __device__ __forceinline__ float4 load4(const float *p) const { return ld_stream_f4(p); }
     __device__ __forceinline__ float load1(const float *p) const { return ld_stream_f1(p); }
     __device__ __forceinline__ float one(float x) {
-        ts += x;
-        ts2 = fmaf(x, x, ts2);
+        const float d = x - shift;
+        ts += d;
+        ts2 = fmaf(d, d, ts2);
         amax = max(amax, __float_as_uint(x) & 0x7fffffffu);
         return x;
     }
     __device__ __forceinline__ float term(float x) const { return x; }
     __device__ __forceinline__ float4 visit4(int64_t, const float *, float4 x) {
+        cnt += 4;
         return make_float4(one(x.x), one(x.y), one(x.z), one(x.w));
     }
-    __device__ __forceinline__ float visit1(int64_t, const float *, float x) { return one(x); }
+    __device__ __forceinline__ float visit1(int64_t, const float *, float x) {
+        cnt += 1;
+        return one(x);
+    }
     __device__ __forceinline__ void end_tile() {
-        s += (double)ts;
-        s2 += (double)ts2;
+        const double sh = (double)shift, c = (double)cnt, t = (double)ts;
+        s += t + c * sh;
+        s2 += (double)ts2 + 2.0 * sh * t + c * sh * sh;
         ts = 0.f;
         ts2 = 0.f;
+        cnt = 0;
     }
     __device__ void finish(BlockAux &aux) {
         double a = warp_sum_d(s), b = warp_sum_d(s2);
@@ -1471,8 +1492,9 @@ void np_stats(nnc_ctx *ctx, const float *d_w, int64_t n) {
     clear_scalars(ctx);
     VisitStats v1;
     v1.sc = ctx->d_scal;
+    v1.probe = d_w;
+    v1.probe_n = n;
     const int64_t ng = ctx->sh.n_global;
-    (void)n;
     run_tree(ctx, d_w, v1, FinArgs{FIN_MEAN, ng, 0.0, 0, 1}, EX_NONE);
     VisitCenSq v2;
     v2.sc = ctx->d_scal;
@@ -1512,6 +1534,8 @@ void prune_device(nnc_ctx *ctx, float *d_w, int64_t n, double q, int std_smooth,
     // pass 1: NumPy mean + fp64 estimate of the std -> speculation band
     VisitStats v1;
     v1.sc = ctx->d_scal;
+    v1.probe = d_w;
+    v1.probe_n = n;
     const int64_t ng = ctx->sh.n_global;
     run_tree(ctx, d_w, v1, FinArgs{FIN_PRUNE1, ng, q, thr_mode, 1}, EX_STATS);
     prof_mark(ctx, "mean");

@@ -79,6 +79,22 @@ def test_prune_sizes(U, n, q):
     _check_prune(U, D.gaussian(n, seed=n), q)
 
 
+@pytest.mark.parametrize("ratio", [20.0, 300.0, 5000.0])
+def test_prune_mean_far_from_zero(U, ratio):
+    """|mean| >> std (normalisation scales, biases): the threshold sits in the middle of the data and the estimate behind the
+    speculation band must not lose the variance in sum(x^2) / n - mean^2.  Bit-identical mask, no
+    speculation failure, also through the fused compress path."""
+    rng = np.random.default_rng(int(ratio))
+    for n in (1 << 20, 300_001):
+        w = (1.0 + rng.standard_normal(n) / ratio).astype(np.float32)
+        _check_prune(U, w, float(ratio))          # threshold ~ |mean|: about half of the elements go
+        _check_prune(U, w, float(ratio) * 0.999)
+        w2, w3 = w.copy(), w.copy()
+        mask, km = U.compress_weight(w2, float(ratio), True, 4, "linear")
+        assert np.array_equal(mask.reshape(w.shape), O.prune_weigth(w3, float(ratio)))
+        assert w2.tobytes() == w3.tobytes()
+
+
 def test_prune_hard_threshold_and_f64_scalar(U):
     w = D.gaussian(50001, seed=3)
     _check_prune(U, w, 0.01, std_smooth=False)
