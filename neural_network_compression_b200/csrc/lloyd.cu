@@ -1134,6 +1134,10 @@ LloydResult lloyd_run(nnc_ctx *ctx, LloydHandle &h, const float *h_init, int max
         fprintf(stderr, "[nnc lloyd] zone profile (cycles): prefix %lld elements %lld flush %lld\n", zp[1], zp[2], zp[3]);
         fprintf(stderr, "[nnc lloyd] update profile (cycles): safe %lld zero-run %lld per-id+empties %lld reloc %lld average %lld conv %lld end %lld\n", up[1], up[2], up[3], up[4], up[5], up[6], up[7]);
         {
+            int d3[8];
+            NNC_CUDA(cudaMemcpy(d3, st->logG + LL_LOG - 24, sizeof(d3), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[nnc lloyd] iteration 6: zones by tiles between their two boundaries (0, 1, ..., >= 7): %d %d %d %d %d %d %d %d\n", d3[0], d3[1],
+                    d3[2], d3[3], d3[4], d3[5], d3[6], d3[7]);
             int dbg[8], d2[8];
             NNC_CUDA(cudaMemcpy(dbg, st->logG + LL_LOG - 8, sizeof(dbg), cudaMemcpyDeviceToHost));
             NNC_CUDA(cudaMemcpy(d2, st->logG + LL_LOG - 16, sizeof(d2), cudaMemcpyDeviceToHost));

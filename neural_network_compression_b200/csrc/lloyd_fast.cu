@@ -398,7 +398,7 @@ __device__ __forceinline__ bool warp_pair_search(const SearchConst &C, float t1,
     const bool two = g2 != g1;
     constexpr int LP_MID = 14;  // tiles between A and B that are still walked here (offsets of the ends fit 16 bits)
     if (g2 - g1 - 1 > LP_MID) want_zone = false;  // an enormous zone: left to the chunk pass
-    if (pp) pp[5] = want_zone ? 0 : 3;
+    if (pp) pp[5] = (want_zone ? 0 : 3) | ((g2 - g1) << 8);
     const long long baseA = (g1 - 1) * LL_TS, baseB = (g2 - 1) * LL_TS;
     {
         // the last tile of the array may be ragged: what lies beyond n_ent reads as (+inf, count 0) -- above every threshold
@@ -1372,7 +1372,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     for (int i = tid; i < 32 * 10; i += NT) (&S.hint[0][0])[i] = -1;
     for (int i = tid; i < LF_KMAX; i += NT) S.fz[i].tag = 0u;  // E-steps are numbered from 1
     if (tid == 0) S.zflag = 0u;
-    if (want_log && cta == 0 && tid < 16) st->logG[LL_LOG - 16 + tid] = 0;
+    if (want_log && cta == 0 && tid < 24) st->logG[LL_LOG - 24 + tid] = 0;
     __syncthreads();
     const FastConst &K = S.K;
     const SearchConst &C = S.C;
@@ -1497,7 +1497,8 @@ __global__ void __launch_bounds__(THREADS, 1)
                                                    T.dcn[J1], T.down[J1] < T.down[J2], o, want_log ? pp : nullptr);
                 if (prof_pair)
                     for (int i = 0; i < 5; ++i) st->logZ[LL_LOG - 80 + i] = pp[i] - pp[0];
-                if (want_log && lane_id() == 0 && zone2 && !done) atomicAdd(&st->logG[LL_LOG - 12 + (int)pp[5]], 1);
+                if (want_log && lane_id() == 0 && zone2 && !done) atomicAdd(&st->logG[LL_LOG - 12 + (int)(pp[5] & 0xff)], 1);
+                if (want_log && lane_id() == 0 && zone2 && it == 6) atomicAdd(&st->logG[LL_LOG - 24 + (int)min(7ll, pp[5] >> 8)], 1);
                 if (want_log && lane_id() == 0) atomicAdd(&st->logG[LL_LOG - 1 - (done ? 0 : (zone2 ? 1 : 2))], 1);
                 if (lane_id() == 0) {
                     S0->rpos[b1] = o.pos1;
