@@ -28,6 +28,30 @@ def test_library_exports_every_declared_symbol():
     assert N.lib().nnc_version() == 100
 
 
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of nnc_kmeans_info and nnc_tensor_job have the size and field offsets a C compiler gives the
+    declarations in include/nnc.h (the binding a maintainer of the reference would write is exactly this)."""
+    import subprocess
+
+    from neural_network_compression_b200 import _native as N
+
+    fields = ["w", "n", "threshold", "prune", "mask", "centers", "centred", "packed", "hist", "info", "thr", "n_pruned", "k",
+              "code_bits", "status", "error"]
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "nnc.h"\nint main(void) {\n'
+        '  printf("%zu %zu\\n", sizeof(nnc_kmeans_info), sizeof(nnc_tensor_job));\n'
+        + "".join('  printf("%%zu\\n", offsetof(nnc_tensor_job, %s));\n' % f for f in fields)
+        + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert int(out[0]) == ctypes.sizeof(N.KMeansInfo)
+    assert int(out[1]) == ctypes.sizeof(N.TensorJob)
+    for f, off in zip(fields, out[2:]):
+        assert getattr(N.TensorJob, f).offset == int(off), f
+
+
 def test_no_cpu_fallback_without_device():
     import torch
 
