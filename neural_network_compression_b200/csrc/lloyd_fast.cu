@@ -396,7 +396,8 @@ __device__ __forceinline__ bool warp_pair_search(const SearchConst &C, float t1,
     uint4 c0 = make_uint4(1u, 1u, 1u, 1u), c1 = c0, c2 = c0, c3 = c0, d0 = c0, d1 = c0, d2 = c0, d3 = c0;
     long long psA = 0, pcA = 0, psB = 0, pcB = 0;
     const bool two = g2 != g1;
-    constexpr int LP_MID = 14;  // tiles between A and B that are still walked here (offsets of the ends fit 16 bits)
+    constexpr int LP_MID = 2;  // tiles between A and B that are still walked here, one after the other; wider zones (near-duplicate
+                               // centroids after a relocation) go to the chunk pass, where all warps share them
     if (g2 - g1 - 1 > LP_MID) want_zone = false;  // an enormous zone: left to the chunk pass
     if (pp) pp[5] = (want_zone ? 0 : 3) | ((g2 - g1) << 8);
     const long long baseA = (g1 - 1) * LL_TS, baseB = (g2 - 1) * LL_TS;
