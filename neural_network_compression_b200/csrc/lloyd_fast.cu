@@ -1193,7 +1193,7 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
             // unused slots of this rank hold zeros; fused all-gather of the candidate lists (n_empty is the same on every rank)
             for (int i = 2 * n_done + tid; i < 2 * n_empty; i += NT) cand[i] = 0;
             __syncthreads();
-            if (!peer_allgather(pc, reinterpret_cast<const unsigned long long *>(cand), 2 * n_empty, K.cand, (size_t)k * 2, ++xseq) &&
+            if (!peer_allgather_tagged(pc, reinterpret_cast<const unsigned long long *>(cand), 2 * n_empty, K.cand, (size_t)k * 2, ++xseq) &&
                 tid == 0)
                 S.comm_error = 1;
             __threadfence_block();
