@@ -20,7 +20,6 @@ static void exclusive_scan(nnc_ctx *ctx, const TIn *d_in, long long n, TOut *d_o
     chunks = (int)((n + chunk - 1) / chunk);
     TOut *chunk_sum = arena_alloc_t<TOut>(ctx, (size_t)chunks + 1);
     NNC_LAUNCH(ctx, (scan_chunk_sum_kernel<TIn, TOut>), chunks, 1024, 0, d_in, n, chunk, chunk_sum);
-    NNC_LAUNCH(ctx, (scan_chunk_offsets_kernel<TOut>), 1, 1024, 0, chunk_sum, chunks, d_out + n);
     NNC_LAUNCH(ctx, (scan_chunk_apply_kernel<TIn, TOut>), chunks, 1024, 0, d_in, n, chunk, chunk_sum, d_out);
 }
 

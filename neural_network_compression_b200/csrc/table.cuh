@@ -124,8 +124,9 @@ __device__ __forceinline__ TOut cta_exclusive_scan(const TIn *__restrict__ in, l
     return carry;
 }
 
-// ---- multi-CTA exclusive scan: chunk sums -> (one CTA) scan of the chunk sums -> per-chunk rescan with its offset.
-// out[0, n) = exclusive prefix, out[n] = total.  chunk_sum: gridDim.x + 1 entries of scratch.
+// ---- multi-CTA exclusive scan: chunk sums -> per-chunk rescan; every CTA of the second kernel adds up the sums of the
+// chunks before it itself (at most 1024 of them: one per thread), which saves a launch of a one-CTA kernel in between.
+// out[0, n) = exclusive prefix, out[n] = total.  chunk_sum: gridDim.x entries of scratch.
 template <class TIn, class TOut>
 __global__ void __launch_bounds__(1024) scan_chunk_sum_kernel(const TIn *__restrict__ in, long long n, long long chunk, TOut *chunk_sum) {
     __shared__ TOut s_warp[32];
@@ -135,22 +136,22 @@ __global__ void __launch_bounds__(1024) scan_chunk_sum_kernel(const TIn *__restr
     const TOut incl = block_scan_incl<TOut>(sum, [](TOut a, TOut b) { return a + b; }, s_warp);
     if (threadIdx.x == blockDim.x - 1) chunk_sum[blockIdx.x] = incl;
 }
-template <class TOut>
-__global__ void __launch_bounds__(1024) scan_chunk_offsets_kernel(TOut *chunk_sum, int chunks, TOut *total_out) {
-    __shared__ TOut s_warp[32];
-    const TOut v = (int)threadIdx.x < chunks ? chunk_sum[threadIdx.x] : (TOut)0;
-    const TOut incl = block_scan_incl<TOut>(v, [](TOut a, TOut b) { return a + b; }, s_warp);
-    if ((int)threadIdx.x < chunks) chunk_sum[threadIdx.x] = incl - v;
-    if (threadIdx.x == blockDim.x - 1) *total_out = incl;
-}
 template <class TIn, class TOut>
 __global__ void __launch_bounds__(1024) scan_chunk_apply_kernel(const TIn *__restrict__ in, long long n, long long chunk,
-                                                                const TOut *__restrict__ chunk_off, TOut *__restrict__ out) {
+                                                                const TOut *__restrict__ chunk_sum, TOut *__restrict__ out) {
     __shared__ TOut s_warp[32];
     __shared__ TOut s_total;
     constexpr int PER = 4;
     const long long lo = (long long)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
-    TOut carry = chunk_off[blockIdx.x];
+    TOut carry;
+    {  // offset of this chunk (gridDim.x <= blockDim.x)
+        const TOut mine = threadIdx.x < blockIdx.x ? chunk_sum[threadIdx.x] : (TOut)0;
+        const TOut incl = block_scan_incl<TOut>(mine, [](TOut a, TOut b) { return a + b; }, s_warp);
+        if (threadIdx.x == blockDim.x - 1) s_total = incl;
+        __syncthreads();
+        carry = s_total;
+        __syncthreads();
+    }
     for (long long base = lo; base < hi; base += (long long)blockDim.x * PER) {
         const long long i0 = base + (long long)threadIdx.x * PER;
         TOut v[PER], sum = 0;
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(1024) scan_chunk_apply_kernel(const TIn *__res
         carry += s_total;
         __syncthreads();
     }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = carry;  // the total
 }
 
 template <int KM>
