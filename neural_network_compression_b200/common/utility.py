@@ -734,17 +734,17 @@ def compress_model(tensors, thresholds=None, std_smooth=True, bits=4, mode="line
     devices = {b.device for b in bufs if b.device is not None}
     if len(devices) > 1:
         raise ValueError("compress_model: all device tensors must live on one GPU")
+    # NEP-50: a np.float64 threshold promotes the comparison to float64, a Python float does not; one mode per call
+    modes = {isinstance(q, np.float64) for q in thresholds} if thresholds is not None else {False}
+    if len(modes) > 1:
+        raise ValueError("compress_model: thresholds must be all Python floats or all numpy.float64")
+    thr_mode = int(modes.pop())
     ctx = _ctx_for(next((b for b in bufs if b.device is not None), bufs[0]))
     k_lin = 2 ** bits
     k_max = k_lin + (1 if mode == "density" else 0)
     cbits = index_bits(k_max)
     jobs = (N.TensorJob * len(bufs))()
     keep = []
-    # NEP-50: a np.float64 threshold promotes the comparison to float64, a Python float does not; one mode per call
-    modes = {isinstance(q, np.float64) for q in thresholds} if thresholds is not None else {False}
-    if len(modes) > 1:
-        raise ValueError("compress_model: thresholds must be all Python floats or all numpy.float64")
-    thr_mode = int(modes.pop())
     for i, b in enumerate(bufs):
         q = thresholds[i] if thresholds is not None else 0.0
         mask = b.empty(b.n, np.uint8) if thresholds is not None else None

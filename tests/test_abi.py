@@ -92,3 +92,13 @@ def test_reference_argument_errors():
     small = np.ones(4, dtype=np.float32)
     out, km = utility.get_quantized_weight(small, 2, "linear")  # n < 2^bits + 1 (utility.py:202-204)
     assert out is small and km is None
+    # the whole-model calls validate their arguments before touching a device
+    with pytest.raises(ValueError, match="one threshold per tensor"):
+        utility.compress_model([w, w], [0.5], True, 4, "linear")
+    with pytest.raises(Exception, match="error mode not found"):
+        utility.compress_model([w], [0.5], True, 4, "forgy")
+    with pytest.raises(ValueError, match="all Python floats or all numpy.float64"):
+        utility.compress_model([w, w], [0.5, np.float64(0.5)], True, 4, "linear")
+    with pytest.raises(TypeError, match="float32"):
+        utility.compress_model([w.astype(np.float64)], [0.5], True, 4, "linear")
+    assert utility.compress_model([], None) == []
