@@ -517,10 +517,10 @@ def result_hash(torch, dist, dev, lo, hi, mask, km, thr, n_pruned, n_iters):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` captures on this workload
-# (2^30 weights, 1 GPU; profiles/r1_summary.md)
+# (2^30 weights, 1 GPU; profiles/r2_summary.md)
 NCU_TRAFFIC = {
-    "np_tree_kernel<VisitApplyQuant>": [11.01e9, "profiles/r1_summary.md section 3 (ncu --set full capture prof_r1_final.ncu-rep: dram__bytes_read.sum 4.333 GB + dram__bytes_write.sum 6.674 GB)"],
-    "kh_scatter_kernel": [3.84e9, "profiles/r1_summary.md section 3 (prof_r1_final.ncu-rep: 1.962 GB read + 1.880 GB written)"],
+    "np_tree_kernel<VisitApplyQuant>": [11.01e9, "profiles/r2_summary.md section 3 (ncu --set full capture prof_r2_final.ncu-rep: dram__bytes_read.sum 4.334 GB + dram__bytes_write.sum 6.674 GB)"],
+    "kh_scatter_kernel": [2.90e9, "profiles/r2_summary.md section 3 (prof_r2_final.ncu-rep: 1.819 GB read + 1.083 GB written)"],
     "(rs_scatter_kernel<A, B>)": [3.135e9, "profiles/r1_summary.md (gpurun_out/prof_r1_scatter.ncu-rep)"],
 }
 
