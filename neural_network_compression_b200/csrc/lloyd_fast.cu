@@ -6,19 +6,24 @@
 // neural_network_compression/common/utility.py:237-238) -- bit-identical results, checked against the cooperative
 // loop kernel and the oracle.  What changes is where the iteration state lives and how the CTAs synchronise.
 //
-// An iteration on the sorted survivors is latency, not bandwidth: <= 2(m-1) boundary searches (three dependent memory
-// round trips each), ~0.01 % of the entries evaluated with the float32 label rule, and a k-element update.  The
-// cooperative kernel (ll_loop_kernel) spends ~43 us per iteration on that: the region table, the searched positions
-// and the per-cluster partials live in global memory (every phase starts with dependent L2 round trips), CTA 0 runs
-// the serial phases, and three software grid barriers of 1.6 us separate the phases.  Here:
-//   * one cluster of LF_CL CTAs x 1024 threads (256 warps >= the boundaries of a 256-cluster codebook);
+// An iteration on the sorted survivors is latency, not bandwidth: <= m - 1 pairs of boundary searches, ~0.01 % of the
+// entries evaluated with the float32 label rule, and a k-element update.  The cooperative kernel (ll_loop_kernel) spends
+// ~43 us per iteration on that: the region table, the searched positions and the per-cluster partials live in global
+// memory (every phase starts with dependent L2 round trips), CTA 0 runs the serial phases, and three software grid
+// barriers of 1.6 us separate the phases.  Here:
+//   * one cluster of up to 16 CTAs x 512 threads (a non-portable cluster size; 8 x 1024 is the fallback), one CTA per four
+//     boundary pairs: 16 CTAs for an 8-bit codebook, one for a 2-bit one;
 //   * every CTA builds the region table REDUNDANTLY in its own shared memory from its copy of the centroids
 //     (deterministic: identical tables, no broadcast of 14 KB);
-//   * searched positions and zone partials go to CTA 0's shared memory through distributed shared memory
-//     (st.shared::cluster / atom.shared::cluster, ~215 cycles) instead of L2;
-//   * phases are separated by the hardware cluster barrier (~380 cycles) instead of a spinning grid barrier;
-//   * CTA 0 updates the centroids out of shared memory only (with the NVLink peer exchange on several GPUs) and the
-//     other CTAs pull the k new centroids over DSMEM.
+//   * one warp per PAIR of region boundaries locates both, loads the tile(s) under them once, takes both prefix triples
+//     and evaluates the zone between them from the same registers (warp_pair_search); results go to CTA 0's shared memory
+//     by plain distributed-shared-memory stores, one writer per slot (remote atomics lost updates: never used);
+//   * what the pair search cannot evaluate (multi-candidate zones, very wide zones) goes to a chunk pass over all warps;
+//     CTA 0 publishes whether there is anything left, and usually there is not;
+//   * phases are separated by the hardware cluster barrier instead of a spinning grid barrier;
+//   * CTA 0 updates the centroids out of shared memory only -- empty clusters are refilled by a block-wide tournament over
+//     preloaded candidate streams; on several GPUs the exact (count, sum) pairs are all-reduced with tagged words over
+//     NVLink peer memory (peer.cuh) -- and the other CTAs pull the k new centroids over DSMEM.
 // k <= LF_KMAX (512: 8-bit codebooks and the 257-centroid density init); larger k keeps ll_loop_kernel.
 #include <cooperative_groups.h>
 #include <stdlib.h>
