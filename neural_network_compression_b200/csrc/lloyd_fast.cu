@@ -980,26 +980,91 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
     const float mean = K.mean;
     const double scale = K.scale;
     const float x0 = fsub(0.f, mean);
-    // ---- 1. per distinct index: zone entries (chunk slots, generic partials) + SAFE regions
-    fast_gather_zones(cluster, S, zs, etag);
-    if (tid < k) {
-        U.W[tid] = 0;
-        U.S[tid] = 0;
+    const int iter_now = S.iter;  // (read before any barrier: thread 0 advances it at the very end)
+    // ---- 1. per distinct index: zone entries + SAFE regions.
+    // The regular case first -- the table alternates SAFE(i), ZONE(i, i+1), SAFE(i+1), ... and the search pass evaluated
+    // every non-empty zone (zs == 0): distinct index i is candidate b of region 2i - 1, owns region 2i and is candidate a of
+    // region 2i + 1, so one thread per index adds its three pieces up directly; no scatter, no zeroing, one barrier.
+    bool regular = zs == 0 && R == 2 * m - 1 && m <= NT;
+    if (regular) {
+        bool ok = true;
+        if (tid < m) {
+            const int i = tid;
+            long long W = 0, Ssum = 0, fi = 0x7fffffffffffffffll, la = -1;
+            ok = T.rJ1[2 * i] == i && T.rJ2[2 * i] == i;
+            if (i > 0) {  // region 2i - 1: zone (i - 1 | i), this index is b
+                const int r = 2 * i - 1;
+                ok = ok && T.rJ2[r] == i - 1 && T.rJ1[r] == i;
+                const long long lo = S.rpos[r];
+                const FusedZone &z = S.fz[i - 1];
+                if (S.rpos[r + 1] > lo && z.tag == etag) {
+                    W += z.Wb;
+                    Ssum += z.Sb;
+                    if (z.fb) {
+                        fi = llmin2(fi, lo + z.fb - 1);
+                        la = llmax2(la, lo + z.lb - 1);
+                    }
+                }
+            }
+            {  // region 2i: SAFE
+                const int r = 2 * i;
+                const long long lo = S.rpos[r], hi = S.rpos[r + 1];
+                if (hi > lo) {
+                    W += S.rcnt[r + 1] - S.rcnt[r];
+                    Ssum += S.rsum[r + 1] - S.rsum[r];
+                    fi = llmin2(fi, lo);
+                    la = llmax2(la, hi - 1);
+                }
+            }
+            if (i < m - 1) {  // region 2i + 1: zone (i | i + 1), this index is a
+                const int r = 2 * i + 1;
+                const long long lo = S.rpos[r];
+                const FusedZone &z = S.fz[i];
+                if (S.rpos[r + 1] > lo && z.tag == etag) {
+                    W += (S.rcnt[r + 1] - S.rcnt[r]) - z.Wb;
+                    Ssum += (S.rsum[r + 1] - S.rsum[r]) - z.Sb;
+                    if (z.fa) {
+                        fi = llmin2(fi, lo + z.fa - 1);
+                        la = llmax2(la, lo + z.la - 1);
+                    }
+                }
+            }
+            U.Wd[i] = W;
+            U.Sd[i] = Ssum;
+            U.first[i] = fi;
+            U.last[i] = la;
+        }
+        if (tid < k) {
+            U.W[tid] = 0;
+            U.S[tid] = 0;
+        }
+        if (tid == 0) {
+            U.same = 1;
+            U.n_empty = 0;
+        }
+        regular = __syncthreads_and(ok) != 0;  // (an irregular table: the general path below redoes everything)
     }
-    if (tid == 0) {
-        U.same = 1;
-        U.n_empty = 0;
-    }
-    __syncthreads();
-    for (int r = tid; r < R; r += NT) {  // SAFE regions: positions [rpos[r], rpos[r+1]) carry one label
-        if (T.rJ1[r] != T.rJ2[r]) continue;
-        const int di = T.rJ1[r];
-        const long long lo = S.rpos[r], hi = S.rpos[r + 1];
-        if (hi > lo) {
-            U.Wd[di] += S.rcnt[r + 1] - S.rcnt[r];  // (J, J) occurs in at most one region: no conflicts
-            U.Sd[di] += S.rsum[r + 1] - S.rsum[r];
-            U.first[di] = llmin2(U.first[di], lo);
-            U.last[di] = llmax2(U.last[di], hi - 1);
+    if (!regular) {
+        fast_gather_zones(cluster, S, zs, etag);
+        if (tid < k) {
+            U.W[tid] = 0;
+            U.S[tid] = 0;
+        }
+        if (tid == 0) {
+            U.same = 1;
+            U.n_empty = 0;
+        }
+        __syncthreads();
+        for (int r = tid; r < R; r += NT) {  // SAFE regions: positions [rpos[r], rpos[r+1]) carry one label
+            if (T.rJ1[r] != T.rJ2[r]) continue;
+            const int di = T.rJ1[r];
+            const long long lo = S.rpos[r], hi = S.rpos[r + 1];
+            if (hi > lo) {
+                U.Wd[di] += S.rcnt[r + 1] - S.rcnt[r];  // (J, J) occurs in at most one region: no conflicts
+                U.Sd[di] += S.rsum[r + 1] - S.rsum[r];
+                U.first[di] = llmin2(U.first[di], lo);
+                U.last[di] = llmax2(U.last[di], hi - 1);
+            }
         }
     }
     // ---- 2. zero run: the label of x'_0 = fl(0 - mean) is a region-table lookup -- the table is exact for every point of
@@ -1056,14 +1121,14 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
     }
     const int any_differs = __syncthreads_or(differs);
     // ---- 5. empty clusters (ascending id) and relocation
-    {
-        const int e = (tid < k) && (U.W[tid] == 0);
+    const int e = (tid < k) && (U.W[tid] == 0);
+    const int n_empty = __syncthreads_count(e);  // (almost always 0: the scan below is skipped)
+    if (tid == 0) U.n_empty = n_empty;
+    if (n_empty > 0) {
         const int incl = block_scan_incl<int>(e, [](int a, int b) { return a + b; }, U.red_i);
         if (e) U.empt[incl - 1] = tid;
-        if (tid == NT - 1) U.n_empty = incl;
         __syncthreads();
     }
-    const int n_empty = U.n_empty;
     if (prof) prof[3] = clock64();
     if (n_empty > 0) {
         // Candidate streams (PopState).  The farthest remaining sample overall is always at the head of one of the
@@ -1255,6 +1320,7 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
     // S / 2^s == S * 2^-s exactly (a power-of-two scaling of the double image of S), without a float64 division
     if (tid < k) U.raw[tid] = (float)__dmul_rn((double)U.S[tid], K.inv_scale);
     // argmax of the counts, lowest id on ties (np.argmax): key = count << 10 | (1023 - id), count < 2^53
+    int amax_all = 0;
     {
         unsigned long long key = tid < k ? (((unsigned long long)U.W[tid] << 10) | (unsigned long long)(1023 - tid)) : 0ull;
         for (int o = 16; o > 0; o >>= 1) {
@@ -1263,15 +1329,13 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
         }
         if (lane_id() == 0) U.red_w[warp_id()] = key;
         __syncthreads();
-        if (tid == 0) {
-            const int nwk = (k + 31) >> 5;
-            for (int w = 1; w < nwk; ++w) key = U.red_w[w] > key ? U.red_w[w] : key;
-            U.winner = 1023 - (int)(key & 1023ull);
-        }
-        __syncthreads();
+        const int nwk = (k + 31) >> 5;  // every thread folds the warps' winners itself: no second barrier
+        key = U.red_w[0];
+        for (int w = 1; w < nwk; ++w) key = U.red_w[w] > key ? U.red_w[w] : key;
+        amax_all = 1023 - (int)(key & 1023ull);
     }
     if (tid < k) {
-        const int amax = U.winner;
+        const int amax = amax_all;
         // (float)(1.0 / (double)W): for W < 2^24 (exact in float32) the float32 division gives the same value -- double
         // rounding is innocuous for a quotient of float32 operands when the wide format has >= 2 * 24 + 2 bits
         auto avg = [&](int j) {
@@ -1314,24 +1378,23 @@ __device__ void fast_update_step(cg::cluster_group &cluster, FastSmem &S, const 
     if (prof) prof[6] = clock64();
     {
         const int strict = U.strict, stop = U.stop;
-        const int last_iter = S.iter + 1 >= K.max_iter;
+        const int last_iter = iter_now + 1 >= K.max_iter;
         if (tid < k) {
             // labels of a strict stop belong to the centroids the E-step used; otherwise a final E-step with the new
-            // centroids follows (emit.cu)
+            // centroids follows (emit.cu).  (A thread touches only its own centroid: no barrier between the two stores.)
             if (stop || last_iter) S.c_emit[tid] = strict ? S.c[tid] : U.cnew[tid];
+            S.c[tid] = U.cnew[tid];
         }
-        __syncthreads();
-        if (tid < k) S.c[tid] = U.cnew[tid];
         if (tid == 0) {
-            S.iter += 1;
+            S.iter = iter_now + 1;
             if (stop || last_iter) {
                 S.done = 1;
                 S.strict = strict;
-                S.n_iter = S.iter;
+                S.n_iter = iter_now + 1;
             }
         }
     }
-    __syncthreads();
+    // (no barrier here: the caller's cluster barrier follows)
 }
 
 template <int THREADS>
