@@ -41,7 +41,9 @@ constexpr int LF_R = 2 * LF_KMAX + 2;
 // scratch of np_pairwise_warp
 struct NpWarpScratch {
     short off[16], len[16];
-    float val[16];
+    float val[32];              // [0, 16): the leaves' sums, [16, 32): the internal nodes of the fold
+    short fl[16], fr[16];       // fold program: node t = val[fl[t]] + val[fr[t]] (built once: the tree depends only on n)
+    int n_ops, root;
 };
 
 // relocation: every distinct index has two candidate streams -- its members below its centroid walked from the left end
@@ -169,9 +171,22 @@ static __device__ float np_fold_leaves(int n, const NpWarpScratch &W, int &idx) 
     const float r = np_fold_leaves(n - n2, W, idx);
     return fadd(l, r);
 }
+// the fold over the leaves as a straight-line program (the recursion costs a stack frame in local memory -- L2 latency in
+// this kernel -- on every call; the program is built once per kernel).  Returns the index of the value holding the sum.
+static __device__ int np_fold_prog(int n, NpWarpScratch &W, int &leaf, int &n_ops) {
+    if (n <= 128) return leaf++;
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    const int l = np_fold_prog(n2, W, leaf, n_ops);
+    const int r = np_fold_prog(n - n2, W, leaf, n_ops);
+    W.fl[n_ops] = (short)l;
+    W.fr[n_ops] = (short)r;
+    return 16 + n_ops++;
+}
 // n_leaves < 0: build the leaf list first (it only depends on n: callers with a fixed n build it once and pass the count)
 __device__ float np_pairwise_warp(const float *a, int n, NpWarpScratch &W, int n_leaves = -1) {  // one whole warp; result in lane 0
     const int lane = lane_id(), grp = lane >> 3, j = lane & 7;
+    const bool n_leaves_given = n_leaves >= 0;
     if (n_leaves < 0) {
         if (lane == 0) n_leaves = np_leaf_list(0, n, W, 0);
         n_leaves = __shfl_sync(0xffffffffu, n_leaves, 0);
@@ -204,8 +219,13 @@ __device__ float np_pairwise_warp(const float *a, int n, NpWarpScratch &W, int n
     __syncwarp();
     float tot = 0.f;
     if (lane == 0) {
-        int idx = 0;
-        tot = np_fold_leaves(n, W, idx);
+        if (n_leaves_given) {  // the fold program was built with the leaf list
+            for (int t = 0; t < W.n_ops; ++t) W.val[16 + t] = fadd(W.val[W.fl[t]], W.val[W.fr[t]]);
+            tot = W.val[W.root];
+        } else {
+            int idx = 0;
+            tot = np_fold_leaves(n, W, idx);
+        }
     }
     return tot;
 }
@@ -1457,6 +1477,11 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
     if (tid == 0) {
         S.np_leaves = np_leaf_list(0, k, S.np, 0);
+        {
+            int leaf = 0, n_ops = 0;
+            S.np.root = np_fold_prog(k, S.np, leaf, n_ops);
+            S.np.n_ops = n_ops;
+        }
         S.done = 0;
         S.iter = 0;
         S.strict = 0;
