@@ -426,18 +426,18 @@ __device__ __forceinline__ bool warp_pair_search(const SearchConst &C, float t1,
     if (g2 - g1 - 1 > LP_MID) want_zone = false;  // an enormous zone: left to the chunk pass
     if (pp) pp[5] = (want_zone ? 0 : 3) | ((g2 - g1) << 8);
     const long long baseA = (g1 - 1) * LL_TS, baseB = (g2 - 1) * LL_TS;
+    // the last tile of the array may be ragged: what lies beyond n_ent reads as (+inf, count 0) -- above every threshold
+    auto ldk = [&](long long i) {
+        if (i + 3 < C.n_ent) return ld_vol_f4(C.ks + i);
+        return make_float4(i < C.n_ent ? C.ks[i] : INFINITY, i + 1 < C.n_ent ? C.ks[i + 1] : INFINITY,
+                           i + 2 < C.n_ent ? C.ks[i + 2] : INFINITY, INFINITY);
+    };
+    auto ldc = [&](long long i) {
+        if (i + 3 < C.n_ent) return ld_vol_u4(C.cnt + i);
+        return make_uint4(i < C.n_ent ? C.cnt[i] : 0u, i + 1 < C.n_ent ? C.cnt[i + 1] : 0u, i + 2 < C.n_ent ? C.cnt[i + 2] : 0u, 0u);
+    };
+    const long long ia = baseA + 4 * lane, ib = baseB + 4 * lane;
     {
-        // the last tile of the array may be ragged: what lies beyond n_ent reads as (+inf, count 0) -- above every threshold
-        auto ldk = [&](long long i) {
-            if (i + 3 < C.n_ent) return ld_vol_f4(C.ks + i);
-            return make_float4(i < C.n_ent ? C.ks[i] : INFINITY, i + 1 < C.n_ent ? C.ks[i + 1] : INFINITY,
-                               i + 2 < C.n_ent ? C.ks[i + 2] : INFINITY, INFINITY);
-        };
-        auto ldc = [&](long long i) {
-            if (i + 3 < C.n_ent) return ld_vol_u4(C.cnt + i);
-            return make_uint4(i < C.n_ent ? C.cnt[i] : 0u, i + 1 < C.n_ent ? C.cnt[i + 1] : 0u, i + 2 < C.n_ent ? C.cnt[i + 2] : 0u, 0u);
-        };
-        const long long ia = baseA + 4 * lane, ib = baseB + 4 * lane;
         a0 = ldk(ia);
         a1 = ldk(ia + 128);
         a2 = ldk(ia + 256);
@@ -454,13 +454,7 @@ __device__ __forceinline__ bool warp_pair_search(const SearchConst &C, float t1,
             c2 = ldc(ia + 256);
             c3 = ldc(ia + 384);
             pcA = ld_vol_s64(C.ctile + (g1 - 1));
-            if (two) {
-                d0 = ldc(ib);
-                d1 = ldc(ib + 128);
-                d2 = ldc(ib + 256);
-                d3 = ldc(ib + 384);
-                pcB = ld_vol_s64(C.ctile + (g2 - 1));
-            }
+            if (two) pcB = ld_vol_s64(C.ctile + (g2 - 1));
         }
         psA = ld_vol_s64(C.ptile + (g1 - 1));
         if (two) psB = ld_vol_s64(C.ptile + (g2 - 1));
@@ -499,6 +493,12 @@ __device__ __forceinline__ bool warp_pair_search(const SearchConst &C, float t1,
     };
     one(a0.x, c0.x, 0, false); one(a0.y, c0.y, 1, false); one(a0.z, c0.z, 2, false); one(a0.w, c0.w, 3, false);
     one(a1.x, c1.x, 4, false); one(a1.y, c1.y, 5, false); one(a1.z, c1.z, 6, false); one(a1.w, c1.w, 7, false);
+    if (two && C.cnt) {  // the second tile's multiplicities are requested only now: sixteen registers less at the peak
+        d0 = ldc(ib);
+        d1 = ldc(ib + 128);
+        d2 = ldc(ib + 256);
+        d3 = ldc(ib + 384);
+    }
     one(a2.x, c2.x, 8, false); one(a2.y, c2.y, 9, false); one(a2.z, c2.z, 10, false); one(a2.w, c2.w, 11, false);
     one(a3.x, c3.x, 12, false); one(a3.y, c3.y, 13, false); one(a3.z, c3.z, 14, false); one(a3.w, c3.w, 15, false);
     if (two) {
