@@ -335,11 +335,15 @@ constexpr int LP_PER = 12;  // samples per lane in the final round: brackets of 
 __device__ __forceinline__ void warp_locate_pair(const SearchConst &C, float t1, float t2, long long &g1, long long &g2) {
     const int lane = lane_id();
     const float mean = C.mean;
+    int a_top = -1;  // first failing top-level sample of the previous threshold (-1: none yet)
     auto bracket = [&](float t, long long &lo, long long &hi) {
         lo = 0;
         hi = C.n_tiles;  // the answer lies in [lo, hi]
         if (C.top) {
             int a = 0, b = C.top_n;  // first top index failing lies in [a, b]
+            // thresholds come in ascending order: the second one usually falls between the same two top-level samples
+            if (a_top >= 0 && (a_top == C.top_n || !(fsub(C.top[a_top], mean) < t))) a = b = a_top;
+            else if (a_top > 0) a = a_top;  // (samples below a_top satisfy the smaller threshold, hence this one)
             while (a < b) {
                 const int span = b - a, step = (span + 31) >> 5;
                 const int cs = a + lane * step;
@@ -354,6 +358,7 @@ __device__ __forceinline__ void warp_locate_pair(const SearchConst &C, float t1,
                 b = min(na + step, b) - 1;
                 a = na;
             }
+            a_top = a;
             if (a == 0) {
                 hi = 0;
             } else {
